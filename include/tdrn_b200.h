@@ -1,0 +1,183 @@
+/*
+ * tdrn_b200.h -- C ABI of libtdrn_b200.so: the B200 (sm_100a) implementation of the TDRN /
+ * DualRefineDet inference hot path.
+ *
+ * Every entry point is extern "C", takes plain pointers and sizes (no torch / THC types), returns
+ * 0 on success or a negative TDRN_E* code, never allocates device memory (the caller owns every
+ * buffer, including scratch), launches on the stream it is given and does not synchronise unless
+ * the comment says so.  tdrn_last_error() returns the thread-local message of the last failure.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the upstream
+ * SeanChenxy/TDRN checkout).  INTEGRATION.md shows the reference-side bindings.
+ *
+ * Layout conventions: "NCHW" tensors are the reference's; "NHWC" are the library's internal
+ * activations.  Pointers are DEVICE pointers unless the parameter name ends in _host.
+ */
+#ifndef TDRN_B200_H_
+#define TDRN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDRN_OK            0
+#define TDRN_EINVAL       -1   /* bad argument / shape check failed (reference: THArgCheck -> RuntimeError) */
+#define TDRN_ECUDA        -2   /* CUDA runtime / launch error (reference only printf'd these) */
+#define TDRN_EWORKSPACE   -3   /* caller-provided workspace too small */
+#define TDRN_EUNSUPPORTED -4   /* configuration not implemented by this kernel */
+
+#define TDRN_F32  0
+#define TDRN_BF16 1
+
+typedef void *tdrn_stream_t;   /* cudaStream_t */
+
+const char *tdrn_last_error(void);
+int tdrn_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py "gpu_launches"). */
+long long tdrn_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * A5  PriorBox.forward        layers/functions/prior_box.py:33-64  (host, float64 -> fp32)
+ * ars is [n_levels][4] (unused entries ignored), n_ar[k] = len(aspect_ratios[k]);
+ * max_sizes_host may be NULL (cfg['max_sizes'] == []).  out_host may be NULL to query *num_priors.
+ * ------------------------------------------------------------------------------------------ */
+int tdrn_prior_box(int image_size, int n_levels, const int *feature_maps_host, const int *steps_host,
+                   const int *min_sizes_host, const int *max_sizes_host, const int *n_ar_host,
+                   const int *ars_host, int flip, int clip, float *out_host, int *num_priors);
+
+/* ------------------------------------------------------------------------------------------
+ * A3  deform_conv_forward_cuda   utils/deformconv/deform_conv_cuda.h:1-7, deform_conv_cuda.c:98-213
+ * Same argument meaning as the reference (NCHW fp32 input/offset/output, weight [Cout,Cin,kH,kW],
+ * no bias) minus the caller-owned `columns`/`ones` scratch, which no longer exists: the sampled
+ * columns never leave the SM.  fp32 exact path (SIMT); shape errors return TDRN_EINVAL.
+ * ------------------------------------------------------------------------------------------ */
+int tdrn_deform_conv_forward(const float *input, const float *weight, const float *offset, float *output,
+                             int B, int Cin, int H, int W, int Cout, int kW, int kH, int dW, int dH,
+                             int padW, int padH, int dilationH, int dilationW, int deformable_group,
+                             tdrn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A8  NMS   utils/nms_wrapper.py:23-31 -> utils/nms/cpu_nms.pyx:17-68 (the rule Detect uses);
+ *           replaces `_nms` utils/nms/gpu_nms.hpp:1-2 (which used `>` and needed pre-sorted input).
+ * dets [n,5] = (x1,y1,x2,y2,score) fp32, any order.  Sorts (descending score, ties -> lower
+ * index), suppresses j when IoU(+1 convention) >= thresh (compared in double like the Cython
+ * code), stops after max_keep boxes are kept (max_keep <= 0: no limit).  keep [<= n] int32 indices
+ * into dets in score order, *num_keep on device.  workspace >= tdrn_nms_workspace_bytes(n).
+ * tdrn_nms_host: host pointers, synchronous, allocates its own scratch (drop-in for `_nms`).
+ * ------------------------------------------------------------------------------------------ */
+size_t tdrn_nms_workspace_bytes(int n);
+int tdrn_nms(const float *dets, int n, double thresh, int max_keep, int *keep, int *num_keep,
+             void *workspace, size_t workspace_bytes, tdrn_stream_t stream);
+int tdrn_nms_host(int *keep_out_host, int *num_out_host, const float *dets_host, int boxes_num,
+                  int boxes_dim, double thresh, int device_id);
+
+/* ------------------------------------------------------------------------------------------
+ * A6  decode / center_size   layers/box_utils.py:176-195, :16-25 as applied by
+ *     layers/functions/detection.py:43-48.  loc [B,P,4], priors [P,4] (cx,cy,w,h),
+ *     arm_loc [B,P,4] or NULL -> boxes [B,P,4] (x1,y1,x2,y2 normalised).
+ * ------------------------------------------------------------------------------------------ */
+int tdrn_decode(const float *loc, const float *priors, const float *arm_loc, int B, int P, float *boxes,
+                tdrn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A8  Detect.forward   layers/functions/detection.py:25-70
+ * loc [B,P,4], conf [B*P,C] (softmax scores), priors [P,4], arm_loc [B,P,4] or NULL,
+ * scale_host[4] -> out [B,C,top_k,5] = (score,x1,y1,x2,y2), class 0 rows zero.
+ * Candidate test `score > conf_thresh` in fp32; NMS as tdrn_nms with max_keep = top_k.
+ * ------------------------------------------------------------------------------------------ */
+size_t tdrn_detect_workspace_bytes(int B, int P, int C, int top_k);
+int tdrn_detect(const float *loc, const float *conf, const float *priors, const float *arm_loc,
+                const float *scale_host, int B, int P, int C, int top_k, float conf_thresh,
+                double nms_thresh, float *out, void *workspace, size_t workspace_bytes,
+                tdrn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A1/A2/A2m/A9 layer operators (replace the cuDNN calls behind nn.Conv2d / ConvTranspose2d /
+ * BatchNorm2d / MaxPool2d / Softmax in model/networks.py:136-163,736-745,
+ * model/dualrefinedet_vggbn.py:119-206, and L2Norm layers/modules/l2norm.py:17-21).
+ * Activations are NHWC in `dtype` (TDRN_F32 or TDRN_BF16); accumulation is always fp32.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct tdrn_conv_desc {
+    int B, H, W, Cin;          /* input  [B,H,W,Cin] NHWC                                          */
+    int Cout, kh, kw;          /* weight packed [kh*kw*Cin][Cout] (tap-major, then cin), BN folded  */
+    int stride, pad, dil;
+    int relu;                  /* apply max(0,.) after bias (+ residual)                            */
+    int deconv2x2;             /* 1: ConvTranspose2d k2 s2 (weight packed [Cin][4*Cout], n=(ij,co)) */
+    int dg;                    /* >0: deformable conv with dg offset groups (offsets NHWC fp32
+                                  [B,Ho,Wo,dg*2*kh*kw]); sampler = deform_conv_cuda_kernel.cu:16-51 */
+    int in_dtype, out_dtype;   /* TDRN_F32 / TDRN_BF16                                              */
+    /* output addressing (elements): out[b*out_sb + (y*Wo+x)*out_sp + co]; lets heads write straight
+       into the NHWC-flattened [B,P,4] / [B,P,C] tensors the reference builds with permute+cat.    */
+    long long out_sb, out_sp;
+    long long in_sb;           /* input batch stride in elements; 0 = H*W*Cin (lets the 1x1 offset conv read
+                                  the ARM regression straight out of the flattened [B,P,4] tensor)        */
+} tdrn_conv_desc;
+
+/* fp32-accurate SIMT implicit GEMM (also bf16 in/out with fp32 accumulate). bias/residual may be NULL;
+   residual has the output's addressing and dtype (pass residual == out to accumulate, as the
+   multihead `l(ob,f) + l2(ob,f2)` does).  offsets must be non-NULL iff d->dg > 0. */
+int tdrn_conv2d(const tdrn_conv_desc *d, const void *in, const float *weight_f32, const float *bias,
+                const void *residual, const float *offsets, void *out, tdrn_stream_t stream);
+
+/* tcgen05/TMEM/TMA implicit GEMM, bf16 in, fp32 accumulate, bf16 or fp32 out.
+   weight_bf16 packed [Cout_pad][kh*kw*Cin] K-major (Cout_pad = Cout rounded up to 16).
+   Requires Cin % 64 == 0.  Returns TDRN_EUNSUPPORTED otherwise (caller picks tdrn_conv2d). */
+int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in_bf16, const void *weight_bf16, const float *bias,
+                   const void *residual, void *out, tdrn_stream_t stream);
+
+/* Depthwise 3x3 (+folded BN bias, ReLU): conv_dw first half, model/networks.py:738-740.
+   weight packed [9][C] fp32. */
+int tdrn_dwconv3x3(const void *in, const float *weight, const float *bias, void *out, int B, int H, int W,
+                   int C, int stride, int relu, int dtype, tdrn_stream_t stream);
+
+/* First conv (Cin=3) reading the reference's NCHW fp32 image directly, writing NHWC `out_dtype`.
+   weight packed [27][Cout] fp32 (tap-major, then cin). stride 1 (VGG conv1_1) or 2 (MobileNet). */
+int tdrn_conv_first(const float *x_nchw, const float *weight, const float *bias, void *out, int B, int H,
+                    int W, int Cout, int stride, int relu, int out_dtype, tdrn_stream_t stream);
+
+/* MaxPool2d(2,2, ceil_mode) NHWC. */
+int tdrn_maxpool2x2(const void *in, void *out, int B, int H, int W, int C, int ceil_mode, int dtype,
+                    tdrn_stream_t stream);
+
+/* L2Norm: out = weight[c] * x / (sqrt(sum_c x^2) + 1e-10), NHWC. */
+int tdrn_l2norm(const void *in, const float *weight, void *out, long long pixels, int C, int dtype,
+                tdrn_stream_t stream);
+
+/* Row softmax over C classes, fp32 [rows, C] (nn.Softmax(dim=1), dualrefinedet_vggbn.py:196). In place ok. */
+int tdrn_softmax(const float *in, float *out, long long rows, int C, tdrn_stream_t stream);
+
+/* NHWC (dtype) -> NCHW fp32 (to hand offset maps back in the reference layout) and the reverse. */
+int tdrn_nhwc_to_nchw_f32(const void *in, float *out, int B, int H, int W, int C, int dtype, tdrn_stream_t stream);
+int tdrn_nchw_f32_to_nhwc(const float *in, void *out, int B, int C, int H, int W, int dtype, tdrn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused deformable ODM / TDRN head (replaces the per-sample im2col + SGEMM loop,
+ * deform_conv_cuda.c:157-193, for loc and conf together; model/dualrefinedet_vggbn.py:181-197).
+ * bf16 tcgen05 kernel: the bilinear-sampled im2col tile is built in shared memory and consumed by
+ * tcgen05.mma in place (the fp32-exact equivalent is tdrn_conv2d with dg > 0).
+ *   feat    [B,H,W,Cin] NHWC bf16                    offsets  [B,H,W,dg*2*kh*kw] NHWC fp32
+ *   weight  loc||conf rows concatenated, N = 12 + 3*C: [N_pad][kh*kw*Cin] bf16 K-major (N_pad = N up to 16)
+ *   Optional second head (multihead 5x5): feat shared, offsets2/weight2 with kh2=kw2=5, pad 2;
+ *   its result is added to the first (l(ob,f)+l2(ob,f2)).
+ *   loc_out  [B,P,4] fp32 and conf_out [B,P,C] fp32 are written at prior offset `prior_off`
+ *   (prior index = prior_off + (y*W+x)*3 + a); if softmax != 0 conf_out holds softmax over C.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct tdrn_deform_head_desc {
+    int B, H, W, Cin, num_classes, dg;
+    int kh, pad;               /* first head (square kernel, stride 1, dilation 1) */
+    int kh2, pad2;             /* second head, kh2 == 0: absent                    */
+    int P, prior_off;
+    int softmax;
+} tdrn_deform_head_desc;
+
+int tdrn_deform_head(const tdrn_deform_head_desc *d, const void *feat, const float *offsets,
+                     const void *weight, const float *offsets2, const void *weight2,
+                     float *loc_out, float *conf_out, tdrn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDRN_B200_H_ */

@@ -1,0 +1,71 @@
+"""ctypes loader for libtdrn_b200.so (the C ABI declared in include/tdrn_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, an exception is
+raised.  Device memory, streams and torch.distributed come from PyTorch (plumbing only).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtdrn_b200.so')
+
+F32, BF16 = 0, 1
+
+
+class TdrnError(RuntimeError):
+    pass
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in
+                ('B', 'H', 'W', 'Cin', 'Cout', 'kh', 'kw', 'stride', 'pad', 'dil', 'relu', 'deconv2x2', 'dg',
+                 'in_dtype', 'out_dtype')] + [('out_sb', ctypes.c_longlong), ('out_sp', ctypes.c_longlong), ('in_sb', ctypes.c_longlong)]
+
+
+class DeformHeadDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in
+                ('B', 'H', 'W', 'Cin', 'num_classes', 'dg', 'kh', 'pad', 'kh2', 'pad2', 'P', 'prior_off', 'softmax')]
+
+
+_lib = None
+
+EXPORTS = [
+    'tdrn_last_error', 'tdrn_version', 'tdrn_launch_count', 'tdrn_prior_box', 'tdrn_deform_conv_forward',
+    'tdrn_nms_workspace_bytes', 'tdrn_nms', 'tdrn_nms_host', 'tdrn_decode', 'tdrn_detect_workspace_bytes',
+    'tdrn_detect', 'tdrn_conv2d', 'tdrn_conv2d_tc', 'tdrn_dwconv3x3', 'tdrn_conv_first', 'tdrn_maxpool2x2',
+    'tdrn_l2norm', 'tdrn_softmax', 'tdrn_nhwc_to_nchw_f32', 'tdrn_nchw_f32_to_nhwc', 'tdrn_deform_head',
+]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TdrnError('%s not found: build it with `python -m tdrn_b200.build` (nvcc, sm_100a). '
+                            'There is no CPU fallback.' % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.tdrn_last_error.restype = ctypes.c_char_p
+        L.tdrn_launch_count.restype = ctypes.c_longlong
+        L.tdrn_nms_workspace_bytes.restype = ctypes.c_size_t
+        L.tdrn_detect_workspace_bytes.restype = ctypes.c_size_t
+        _lib = L
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        raise TdrnError('%s failed (rc=%d): %s' % (what or 'tdrn call', rc, lib().tdrn_last_error().decode()))
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (or None)."""
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def stream_handle():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count():
+    return int(lib().tdrn_launch_count())

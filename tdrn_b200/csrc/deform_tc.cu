@@ -1,0 +1,307 @@
+// deform_tc.cu -- fused deformable detection head on tcgen05 (bf16 in, fp32 accumulate).
+//
+// Replaces, for the ODM heads of DualRefineDet (model/dualrefinedet_vggbn.py:180-197) and the
+// temporal heads of TDRN (model/ssd4scale_vgg.py:106-109), the reference's per-sample loop
+//   zero(output); deformable_im2col -> columns[K, HW] fp32 in HBM; SGEMM     (deform_conv_cuda.c:157-193)
+// executed once for `loc` and once again -- same sampling -- for `conf`.  Here:
+//   * loc and conf weights are concatenated along N (12 + 3*C rows), so every sampled value feeds
+//     all outputs of its pixel;
+//   * the bilinear-sampled im2col tile (sampler rules of deform_conv_cuda_kernel.cu:16-51,195-203)
+//     is produced by 8 warps straight into shared memory in the 128B-swizzled K-major UMMA layout
+//     (each corner read is a 16-byte channels-last vector, 8 lanes cover a 128-byte line) and is
+//     consumed in place by tcgen05.mma: the column buffer never exists in HBM;
+//   * the optional 5x5 "multihead" (l(ob,f) + l2(ob,f2), :182-183) simply continues the K loop into
+//     the same TMEM accumulator;
+//   * the epilogue stages the 128 x N fp32 tile through shared memory, applies the class softmax
+//     (nn.Softmax(dim=1) on view(-1, C), :196) and writes loc [B,P,4] / conf [B,P,C] rows coalesced
+//     at their prior offsets (the reference's permute(0,2,3,1).contiguous().view + cat).
+//
+// Warp roles (320 threads): warps 0-7 A producers (then epilogue), warp 8 weight TMA, warp 9 TMEM
+// allocator + MMA issuer.
+#include "tc_common.cuh"
+
+namespace tdrn {
+namespace tc {
+
+struct DeformP {
+    const __nv_bfloat16 *feat;       // [B,H,W,Cin]
+    const float *off[2];             // [B,H,W,dg*2*taps]
+    int B, H, W, Cin, dg, cpg;
+    int k[2], pad[2], taps[2];       // head 1 / head 2 (taps[1] == 0: absent)
+    int M;                           // B*H*W
+    int n_total, n_pad16, C;         // 12 + 3*C
+    int P, prior_off, softmax;
+    float *loc_out, *conf_out;
+    uint32_t b_bytes;
+};
+
+template <int NMAX> struct DfCfg {
+    static constexpr int A_BYTES = 128 * 128;
+    static constexpr int B_BYTES = NMAX * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = 3;
+    static constexpr int TMEM_COLS = NMAX;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+};
+
+constexpr int DF_PRODUCER_WARPS = 8;
+constexpr int DF_THREADS = (DF_PRODUCER_WARPS + 2) * 32;
+
+template <int NMAX>
+__global__ void __launch_bounds__(DF_THREADS) deform_head_kernel(const __grid_constant__ CUtensorMap tmB0,
+                                                                 const __grid_constant__ CUtensorMap tmB1, const DeformP p)
+{
+    using Cfg = DfCfg<NMAX>;
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[Cfg::STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[Cfg::STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    uint8_t *tiles = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * 128;
+    const int cblocks = p.Cin >> 6;
+    const int kb_head0 = p.taps[0] * cblocks;
+    const int num_kb = kb_head0 + p.taps[1] * cblocks;
+    const int HW = p.H * p.W;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmB0);
+        if (p.taps[1]) tma_prefetch_desc(&tmB1);
+#pragma unroll
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], DF_PRODUCER_WARPS + 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == DF_PRODUCER_WARPS + 1) tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < DF_PRODUCER_WARPS) {
+        // ===================== A producers: bilinear-sampled im2col straight into smem =====================
+        const int sub = lane >> 3, chunk = lane & 7;       // 4 rows per pass, 8 x 16B chunks per row
+        int rb[4], ry[4], rx[4];
+        bool rvalid[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = warp * 16 + i * 4 + sub;
+            const int m = m0 + r;
+            rvalid[i] = m < p.M;
+            const int mm = rvalid[i] ? m : 0;
+            rb[i] = mm / HW;
+            const int rem = mm - rb[i] * HW;
+            ry[i] = rem / p.W; rx[i] = rem - ry[i] * p.W;
+        }
+        int poff[4][4];          // pixel offsets (elements / Cin) of the 4 corners, per row slot
+        float pw[4][4];          // bilinear weights (0 when the sample is outside the map)
+        const int blocks_per_group = p.cpg >> 6;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int head = kb >= kb_head0 ? 1 : 0;
+            const int kl = head ? kb - kb_head0 : kb;
+            const int tap = kl / cblocks, cb = kl - tap * cblocks;
+            if (cb % blocks_per_group == 0) {
+                // new (tap, deformable group): recompute sampling geometry for my 4 rows
+                const int g = (cb << 6) / p.cpg;
+                const int kk = p.k[head];
+                const int ti = tap / kk, tj = tap - ti * kk;
+                const int oc = p.dg * 2 * p.taps[head];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float *op = p.off[head] + ((long long)rb[i] * HW + ry[i] * p.W + rx[i]) * oc + (g * 2 * p.taps[head] + 2 * tap);
+                    const float oh = rvalid[i] ? __ldg(op) : 0.f, ow = rvalid[i] ? __ldg(op + 1) : 0.f;
+                    const int y0 = ry[i] - p.pad[head], x0 = rx[i] - p.pad[head];          // stride 1
+                    const float h_im = (float)(y0 + ti) + oh, w_im = (float)(x0 + tj) + ow; // .cu:195-196 (dilation 1)
+                    const bool inside = rvalid[i] && h_im >= 0.f && w_im >= 0.f && h_im < (float)p.H && w_im < (float)p.W;   // .cu:197
+                    float h = (float)ti + oh, w = (float)tj + ow;                            // map_h/map_w .cu:198-199
+                    const int cur_h = p.H - y0, cur_w = p.W - x0;
+                    int h_low = (int)floorf(h), w_low = (int)floorf(w), h_high, w_high;      // .cu:21-37
+                    if (h_low >= cur_h - 1) { h_high = h_low = cur_h - 1; h = (float)h_low; } else { h_high = h_low + 1; }
+                    if (w_low >= cur_w - 1) { w_high = w_low = cur_w - 1; w = (float)w_low; } else { w_high = w_low + 1; }
+                    const float lh = h - (float)h_low, lw = w - (float)w_low, hh = 1.f - lh, hw = 1.f - lw;
+                    const int ya = min(max(y0 + h_low, 0), p.H - 1), yb = min(max(y0 + h_high, 0), p.H - 1);
+                    const int xa = min(max(x0 + w_low, 0), p.W - 1), xb = min(max(x0 + w_high, 0), p.W - 1);
+                    const int base = rb[i] * HW;
+                    poff[i][0] = base + ya * p.W + xa; poff[i][1] = base + ya * p.W + xb;
+                    poff[i][2] = base + yb * p.W + xa; poff[i][3] = base + yb * p.W + xb;
+                    pw[i][0] = inside ? hh * hw : 0.f; pw[i][1] = inside ? hh * lw : 0.f;
+                    pw[i][2] = inside ? lh * hw : 0.f; pw[i][3] = inside ? lh * lw : 0.f;
+                }
+            }
+            // gather the 4 corners of my 4 (row, chunk) slots: 16 independent 16-byte loads in flight
+            uint4 cv[4][4];
+            const __nv_bfloat16 *fb = p.feat + (cb << 6) + (chunk << 3);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cv[i][q] = __ldg((const uint4 *)(fb + (long long)poff[i][q] * p.Cin));
+
+            const int s = kb % Cfg::STAGES;
+            const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            uint8_t *sa = tiles + s * Cfg::STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = warp * 16 + i * 4 + sub;
+                uint4 o;
+                __nv_bfloat162 *ob = (__nv_bfloat162 *)&o;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float2 a = __bfloat1622float2(((const __nv_bfloat162 *)&cv[i][0])[e]);
+                    float2 b = __bfloat1622float2(((const __nv_bfloat162 *)&cv[i][1])[e]);
+                    float2 c = __bfloat1622float2(((const __nv_bfloat162 *)&cv[i][2])[e]);
+                    float2 d = __bfloat1622float2(((const __nv_bfloat162 *)&cv[i][3])[e]);
+                    const float vx = pw[i][0] * a.x + pw[i][1] * b.x + pw[i][2] * c.x + pw[i][3] * d.x;   // .cu:49
+                    const float vy = pw[i][0] * a.y + pw[i][1] * b.y + pw[i][2] * c.y + pw[i][3] * d.y;
+                    ob[e] = __floats2bfloat162_rn(vx, vy);
+                }
+                *(uint4 *)(sa + sw128_offset(r, chunk)) = o;
+            }
+            fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[s]);
+        }
+    } else if (warp == DF_PRODUCER_WARPS) {
+        // ===================== weight (B operand) TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % Cfg::STAGES;
+                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t *sb = tiles + s * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+                mbar_expect_tx(&full_bar[s], p.b_bytes);
+                if (kb < kb_head0) tma_load_2d(sb, &tmB0, &full_bar[s], kb * 64, 0);
+                else tma_load_2d(sb, &tmB1, &full_bar[s], (kb - kb_head0) * 64, 0);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, p.n_pad16);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % Cfg::STAGES;
+                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+                const uint64_t adesc = umma_desc_sw128(sa);
+                const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&tmem_full_bar);
+        }
+        __syncwarp();
+    }
+
+    // ===================== epilogue =====================
+    // All MMAs (hence all smem operand reads) are complete once tmem_full fires; the stage buffers are
+    // reused as a [128][n_pad16+1] fp32 staging tile.
+    float *stg = (float *)tiles;
+    const int lds = p.n_pad16 + 1;
+    if (warp < 4) {
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const int r = warp * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int c0 = 0; c0 < p.n_pad16; c0 += 16) {
+            float v[16];
+            tmem_ld16(trow + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) stg[r * lds + c0 + j] = v[j];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == DF_PRODUCER_WARPS + 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+
+    const int C = p.C;
+    if (p.softmax) {
+        for (int t = threadIdx.x; t < 128 * 3; t += DF_THREADS) {
+            const int r = t / 3, a = t - r * 3;
+            float *row = stg + r * lds + 12 + a * C;
+            float mx = -INFINITY;
+            for (int c = 0; c < C; ++c) mx = fmaxf(mx, row[c]);
+            float sum = 0.f;
+            for (int c = 0; c < C; ++c) { const float e = expf(row[c] - mx); row[c] = e; sum += e; }
+            const float inv = 1.f / sum;
+            for (int c = 0; c < C; ++c) row[c] *= inv;
+        }
+        __syncthreads();
+    }
+    const int rows = min(128, p.M - m0);
+    for (int e = threadIdx.x; e < rows * 12; e += DF_THREADS) {
+        const int r = e / 12, j = e - r * 12;
+        const int m = m0 + r, b = m / HW, pix = m - b * HW;
+        p.loc_out[((long long)b * p.P + p.prior_off + pix * 3) * 4 + j] = stg[r * lds + j];
+    }
+    const int nc = 3 * C;
+    for (int e = threadIdx.x; e < rows * nc; e += DF_THREADS) {
+        const int r = e / nc, j = e - r * nc;
+        const int m = m0 + r, b = m / HW, pix = m - b * HW;
+        p.conf_out[((long long)b * p.P + p.prior_off + pix * 3) * C + j] = stg[r * lds + 12 + j];
+    }
+}
+
+template <int NMAX>
+static int launch_deform(const CUtensorMap &t0, const CUtensorMap &t1, const DeformP &p, cudaStream_t st)
+{
+    using Cfg = DfCfg<NMAX>;
+    TDRN_CUDA(cudaFuncSetAttribute(deform_head_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    deform_head_kernel<NMAX><<<(p.M + 127) / 128, DF_THREADS, Cfg::SMEM_BYTES, st>>>(t0, t1, p);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
+}  // namespace tc
+}  // namespace tdrn
+
+using namespace tdrn;
+using namespace tdrn::tc;
+
+extern "C" int tdrn_deform_head(const tdrn_deform_head_desc *d, const void *feat, const float *offsets,
+                                const void *weight, const float *offsets2, const void *weight2,
+                                float *loc_out, float *conf_out, tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(d && feat && offsets && weight && loc_out && conf_out, "tdrn_deform_head: null argument");
+    TDRN_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->num_classes > 0 && d->dg > 0, "tdrn_deform_head: bad shape");
+    TDRN_REQUIRE(d->kh > 0 && 2 * d->pad == d->kh - 1, "tdrn_deform_head: head 1 must be 'same' (2*pad == k-1)");
+    TDRN_REQUIRE(d->kh2 == 0 || (2 * d->pad2 == d->kh2 - 1 && offsets2 && weight2), "tdrn_deform_head: bad second head");
+    TDRN_REQUIRE(d->Cin % d->dg == 0, "input channels must divide deformable group size");
+    const int cpg = d->Cin / d->dg;
+    DeformP p{};
+    p.n_total = 12 + 3 * d->num_classes;
+    p.n_pad16 = (p.n_total + 15) & ~15;
+    if (d->Cin % 64 != 0 || cpg % 64 != 0 || p.n_pad16 > 256) {
+        set_error("tdrn_deform_head: needs Cin %% 64 == 0, (Cin/dg) %% 64 == 0 and 12+3*C <= 256 (got Cin=%d dg=%d C=%d)",
+                  d->Cin, d->dg, d->num_classes);
+        return TDRN_EUNSUPPORTED;
+    }
+    p.feat = (const __nv_bfloat16 *)feat; p.off[0] = offsets; p.off[1] = offsets2;
+    p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.dg = d->dg; p.cpg = cpg;
+    p.k[0] = d->kh; p.pad[0] = d->pad; p.taps[0] = d->kh * d->kh;
+    p.k[1] = d->kh2 ? d->kh2 : 1; p.pad[1] = d->pad2; p.taps[1] = d->kh2 * d->kh2;
+    p.M = d->B * d->H * d->W; p.C = d->num_classes; p.P = d->P; p.prior_off = d->prior_off; p.softmax = d->softmax;
+    p.loc_out = loc_out; p.conf_out = conf_out;
+    const int nmax = p.n_pad16 > 128 ? 256 : 128;
+    const int b_rows = p.n_pad16;
+    p.b_bytes = (uint32_t)b_rows * 128u;
+
+    CUtensorMap t0, t1;
+    for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !d->kh2) { t1 = t0; break; }
+        const uint64_t K = (uint64_t)p.taps[h] * d->Cin;
+        const uint64_t dims[2] = {K, (uint64_t)p.n_pad16};
+        const uint64_t str[1] = {K * 2};
+        const uint32_t box[2] = {64, (uint32_t)b_rows};
+        int rc = make_tmap_bf16(h ? &t1 : &t0, h ? weight2 : weight, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    cudaStream_t st = as_stream(stream);
+    return nmax == 256 ? launch_deform<256>(t0, t1, p, st) : launch_deform<128>(t0, t1, p, st);
+}

@@ -1,0 +1,493 @@
+// simt_ops.cu -- fp32-accurate CUDA-core kernels of the hot path (sm_100a).
+//
+//   * conv_simt_kernel : strided implicit-GEMM convolution / ConvTranspose2d(k2,s2) / deformable
+//     convolution with fp32 accumulation.  It is the fp32 ("1e-4") path for every layer and the
+//     fallback-free implementation of the odd shapes the tcgen05 kernel does not take (Cin=3,
+//     Cin%64!=0).  Generic element strides let the same kernel consume the reference's NCHW
+//     tensors (tdrn_deform_conv_forward) and the library's NHWC activations.
+//   * depthwise 3x3, maxpool 2x2 (ceil), L2Norm, row softmax, NCHW<->NHWC.
+//
+// Reference semantics restated here (paths relative to the upstream checkout):
+//   deformable sampler     utils/deformconv/deform_conv_cuda_kernel.cu:16-51, :157-208
+//   L2Norm                 layers/modules/l2norm.py:17-21
+//   vgg()/conv_dw()        model/networks.py:136-163, :736-745
+#include "common.cuh"
+#include <math.h>
+
+namespace tdrn {
+
+struct ConvP {
+    const void *in; const float *w; const float *bias; const void *res; const float *off; void *out;
+    int B, Cin, H, W, Cout, kh, kw, stride, pad, dil, Ho, Wo;
+    int M, N, K;
+    long long in_sb, in_sy, in_sx, in_sc;
+    long long w_sn, w_sc, w_st;
+    long long out_sb, out_sy, out_sx, out_sc;
+    long long off_sb, off_sy, off_sx, off_sc;
+    int dg, cpg, relu, deconv;
+};
+
+// Bilinear sample with the reference's border rules.  (y0,x0) = top-left tap origin
+// (h_in,w_in at .cu:177-178), (ti,tj) tap, (oh,ow) learned offsets.  Arithmetic is kept in the
+// reference's order with explicit round-to-nearest ops so the sampled column value is bit-identical
+// to the scalar C oracle (no FMA contraction).
+template <typename TIn>
+__device__ __forceinline__ float deform_sample(const TIn *__restrict__ plane, long long sy, long long sx,
+                                               int H, int W, int y0, int x0, int di, int dj, float oh, float ow)
+{
+    const float h_im = __fadd_rn((float)(y0 + di), oh);          // .cu:195
+    const float w_im = __fadd_rn((float)(x0 + dj), ow);          // .cu:196
+    if (!(h_im >= 0.f && w_im >= 0.f && h_im < (float)H && w_im < (float)W)) return 0.f;   // .cu:197
+    float h = __fadd_rn((float)di, oh);                          // map_h .cu:198
+    float w = __fadd_rn((float)dj, ow);                          // map_w .cu:199
+    const int cur_h = H - y0, cur_w = W - x0;                    // .cu:200-201
+    int h_low = (int)floorf(h), w_low = (int)floorf(w);          // .cu:21-22
+    int h_high, w_high;
+    if (h_low >= cur_h - 1) { h_high = h_low = cur_h - 1; h = (float)h_low; } else { h_high = h_low + 1; }
+    if (w_low >= cur_w - 1) { w_high = w_low = cur_w - 1; w = (float)w_low; } else { w_high = w_low + 1; }
+    const float lh = __fsub_rn(h, (float)h_low), lw = __fsub_rn(w, (float)w_low);
+    const float hh = __fsub_rn(1.f, lh), hw = __fsub_rn(1.f, lw);
+    // absolute coordinates; the clamp only matters for the measure-zero fp32 rounding case where the
+    // reference itself would read one element outside the plane with weight 0.
+    const int ya = min(max(y0 + h_low, 0), H - 1), yb = min(max(y0 + h_high, 0), H - 1);
+    const int xa = min(max(x0 + w_low, 0), W - 1), xb = min(max(x0 + w_high, 0), W - 1);
+    const float v1 = to_f32(plane[ya * sy + xa * sx]);
+    const float v2 = to_f32(plane[ya * sy + xb * sx]);
+    const float v3 = to_f32(plane[yb * sy + xa * sx]);
+    const float v4 = to_f32(plane[yb * sy + xb * sx]);
+    const float w1 = __fmul_rn(hh, hw), w2 = __fmul_rn(hh, lw), w3 = __fmul_rn(lh, hw), w4 = __fmul_rn(lh, lw);
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1), __fmul_rn(w2, v2)), __fmul_rn(w3, v3)), __fmul_rn(w4, v4));
+}
+
+template <typename TIn, typename TOut, int BM, int BN, bool DEFORM>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const ConvP p)
+{
+    constexpr int BK = 16, TM = BM / 16, TN = BN / 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    __shared__ int row_b[BM], row_y[BM], row_x[BM];
+
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const TIn *__restrict__ in = (const TIn *)p.in;
+
+    for (int r = tid; r < BM; r += 256) {
+        const int m = m0 + r;
+        if (m < p.M) {
+            const int hw = p.Ho * p.Wo;
+            const int b = m / hw, rem = m - b * hw;
+            row_b[r] = b; row_y[r] = rem / p.Wo; row_x[r] = rem % p.Wo;
+        } else {
+            row_b[r] = -1; row_y[r] = 0; row_x[r] = 0;
+        }
+    }
+    __syncthreads();
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    const int kl = tid % BK, r0 = tid / BK;
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+        // ---- A tile: As[kl][r] = im2col(row r, k0+kl) ----
+        {
+            const int k = k0 + kl;
+            const bool kvalid = k < p.K;
+            const int tap = kvalid ? k / p.Cin : 0;
+            const int c = kvalid ? k - tap * p.Cin : 0;
+            const int ti = tap / p.kw, tj = tap - ti * p.kw;
+#pragma unroll
+            for (int i = 0; i < BM / 16; ++i) {
+                const int r = r0 + i * 16;
+                const int b = row_b[r];
+                float v = 0.f;
+                if (kvalid && b >= 0) {
+                    const int y0 = row_y[r] * p.stride - p.pad, x0 = row_x[r] * p.stride - p.pad;
+                    if (!DEFORM) {
+                        const int yy = y0 + ti * p.dil, xx = x0 + tj * p.dil;
+                        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+                            v = to_f32(in[b * p.in_sb + yy * p.in_sy + xx * p.in_sx + c * p.in_sc]);
+                    } else {
+                        const int g = c / p.cpg;
+                        const float *op = p.off + b * p.off_sb + row_y[r] * p.off_sy + row_x[r] * p.off_sx
+                                          + (long long)(g * 2 * p.kh * p.kw + 2 * tap) * p.off_sc;
+                        const float oh = op[0], ow = op[p.off_sc];
+                        v = deform_sample<TIn>(in + b * p.in_sb + c * p.in_sc, p.in_sy, p.in_sx, p.H, p.W,
+                                               y0, x0, ti * p.dil, tj * p.dil, oh, ow);
+                    }
+                }
+                As[kl][r] = v;
+            }
+        }
+        // ---- B tile: Bs[k][n] = weight(k0+k, n0+n) ----
+        for (int idx = tid; idx < BK * BN; idx += 256) {
+            const int kk = idx / BN, nl = idx - kk * BN;
+            const int k = k0 + kk, n = n0 + nl;
+            float v = 0.f;
+            if (k < p.K && n < p.N) {
+                const int tap = k / p.Cin, c = k - tap * p.Cin;
+                if (!p.deconv) v = p.w[n * p.w_sn + c * p.w_sc + tap * p.w_st];
+                else { const int ij = n / p.Cout, co = n - ij * p.Cout; v = p.w[co * p.w_sn + c * p.w_sc + ij * p.w_st]; }
+            }
+            Bs[kk][nl] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], bv[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    TOut *__restrict__ out = (TOut *)p.out;
+    const TOut *__restrict__ res = (const TOut *)p.res;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int r = ty * TM + i;
+        const int b = row_b[r];
+        if (b < 0) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            if (n >= p.N) continue;
+            int co = n, oy = row_y[r], ox = row_x[r];
+            if (p.deconv) { const int ij = n / p.Cout; co = n - ij * p.Cout; oy = 2 * oy + (ij >> 1); ox = 2 * ox + (ij & 1); }
+            const long long o = b * p.out_sb + oy * p.out_sy + ox * p.out_sx + co * p.out_sc;
+            float v = acc[i][j];
+            if (p.bias) v += p.bias[co];
+            if (res) v += to_f32(res[o]);
+            if (p.relu) v = fmaxf(v, 0.f);
+            out[o] = from_f32<TOut>(v);
+        }
+    }
+}
+
+template <typename TIn, typename TOut, bool DEFORM>
+static int launch_conv_t(const ConvP &p, cudaStream_t st)
+{
+    if (p.N > 16) {
+        dim3 grid(ceil_div(p.M, 128), ceil_div(p.N, 64));
+        conv_simt_kernel<TIn, TOut, 128, 64, DEFORM><<<grid, 256, 0, st>>>(p);
+    } else {
+        dim3 grid(ceil_div(p.M, 64), 1);
+        conv_simt_kernel<TIn, TOut, 64, 16, DEFORM><<<grid, 256, 0, st>>>(p);
+    }
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
+static int launch_conv(const ConvP &p, int in_dtype, int out_dtype, cudaStream_t st)
+{
+    const bool d = p.dg > 0;
+    if (in_dtype == TDRN_F32 && out_dtype == TDRN_F32)
+        return d ? launch_conv_t<float, float, true>(p, st) : launch_conv_t<float, float, false>(p, st);
+    if (in_dtype == TDRN_BF16 && out_dtype == TDRN_BF16)
+        return d ? launch_conv_t<__nv_bfloat16, __nv_bfloat16, true>(p, st) : launch_conv_t<__nv_bfloat16, __nv_bfloat16, false>(p, st);
+    if (in_dtype == TDRN_BF16 && out_dtype == TDRN_F32)
+        return d ? launch_conv_t<__nv_bfloat16, float, true>(p, st) : launch_conv_t<__nv_bfloat16, float, false>(p, st);
+    if (in_dtype == TDRN_F32 && out_dtype == TDRN_BF16 && !d)
+        return launch_conv_t<float, __nv_bfloat16, false>(p, st);
+    set_error("conv: unsupported dtype combination in=%d out=%d deform=%d", in_dtype, out_dtype, (int)d);
+    return TDRN_EUNSUPPORTED;
+}
+
+static int conv_out_dim(int in, int k, int stride, int pad, int dil) { return (in + 2 * pad - (dil * (k - 1) + 1)) / stride + 1; }
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 3x3, pad 1 (conv_dw first half, model/networks.py:738-740), NHWC, weight [9][C]
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void dwconv3x3_kernel(const T *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias,
+                                 T *__restrict__ out, int B, int H, int W, int C, int Ho, int Wo, int stride, int relu)
+{
+    const long long total = (long long)B * Ho * Wo * C;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        long long pix = idx / C;
+        const int x = (int)(pix % Wo); pix /= Wo;
+        const int y = (int)(pix % Ho);
+        const int b = (int)(pix / Ho);
+        float acc = bias ? bias[c] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int yy = y * stride - 1 + i;
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int xx = x * stride - 1 + j;
+                if (xx < 0 || xx >= W) continue;
+                acc = fmaf(to_f32(in[(((long long)b * H + yy) * W + xx) * C + c]), w[(i * 3 + j) * C + c], acc);
+            }
+        }
+        if (relu) acc = fmaxf(acc, 0.f);
+        out[idx] = from_f32<T>(acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPool2d(2, 2, ceil_mode) NHWC
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool2x2_kernel(const T *__restrict__ in, T *__restrict__ out, int B, int H, int W, int C, int Ho, int Wo)
+{
+    const long long total = (long long)B * Ho * Wo * C;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        long long pix = idx / C;
+        const int x = (int)(pix % Wo); pix /= Wo;
+        const int y = (int)(pix % Ho);
+        const int b = (int)(pix / Ho);
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int yy = 2 * y + i, xx = 2 * x + j;
+                if (yy < H && xx < W) m = fmaxf(m, to_f32(in[(((long long)b * H + yy) * W + xx) * C + c]));
+            }
+        out[idx] = from_f32<T>(m);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// L2Norm (layers/modules/l2norm.py:17-21): one warp per pixel
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void l2norm_kernel(const T *__restrict__ in, const float *__restrict__ weight, T *__restrict__ out, long long pixels, int C)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long p = warp; p < pixels; p += nwarps) {
+        const T *row = in + p * C;
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) { const float v = to_f32(row[c]); s = fmaf(v, v, s); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float norm = sqrtf(s) + 1e-10f;
+        for (int c = lane; c < C; c += 32) out[p * C + c] = from_f32<T>(weight[c] * (to_f32(row[c]) / norm));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row softmax (nn.Softmax(dim=1)): one warp per row
+// ------------------------------------------------------------------------------------------------
+__global__ void softmax_rows_kernel(const float *__restrict__ in, float *__restrict__ out, long long rows, int C)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < rows; r += nwarps) {
+        const float *row = in + r * C;
+        float m = -INFINITY;
+        for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += expf(row[c] - m);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        for (int c = lane; c < C; c += 32) out[r * C + c] = expf(row[c] - m) / s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout transforms (tiled through shared memory so both sides are coalesced)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T *__restrict__ in, float *__restrict__ out, int HW, int C)
+{
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        if (p < HW && c < C) tile[i][threadIdx.x] = to_f32(in[((long long)b * HW + p) * C + c]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        if (p < HW && c < C) out[((long long)b * C + c) * HW + p] = tile[threadIdx.x][i];
+    }
+}
+
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float *__restrict__ in, T *__restrict__ out, int C, int HW)
+{
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        if (p < HW && c < C) tile[i][threadIdx.x] = in[((long long)b * C + c) * HW + p];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        if (p < HW && c < C) out[((long long)b * HW + p) * C + c] = from_f32<T>(tile[threadIdx.x][i]);
+    }
+}
+
+static int grid_1d(long long total, int block) { long long g = (total + block - 1) / block; return (int)(g > 148LL * 32 ? 148 * 32 : (g < 1 ? 1 : g)); }
+
+}  // namespace tdrn
+
+using namespace tdrn;
+
+extern "C" int tdrn_conv2d(const tdrn_conv_desc *d, const void *in, const float *weight, const float *bias,
+                           const void *residual, const float *offsets, void *out, tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(d && in && weight && out, "tdrn_conv2d: null argument");
+    TDRN_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "tdrn_conv2d: bad shape");
+    TDRN_REQUIRE((d->dg > 0) == (offsets != nullptr), "tdrn_conv2d: offsets must be given iff dg > 0");
+    TDRN_REQUIRE(d->dg == 0 || d->Cin % d->dg == 0, "tdrn_conv2d: Cin %% dg != 0");
+    TDRN_REQUIRE(!(d->deconv2x2 && d->dg), "tdrn_conv2d: deconv and deform are exclusive");
+    ConvP p{};
+    p.in = in; p.w = weight; p.bias = bias; p.res = residual; p.off = offsets; p.out = out;
+    p.B = d->B; p.Cin = d->Cin; p.H = d->H; p.W = d->W; p.Cout = d->Cout;
+    p.relu = d->relu; p.deconv = d->deconv2x2; p.dg = d->dg; p.cpg = d->dg > 0 ? d->Cin / d->dg : d->Cin;
+    int out_w;
+    if (d->deconv2x2) {
+        p.kh = p.kw = 1; p.stride = 1; p.pad = 0; p.dil = 1; p.Ho = d->H; p.Wo = d->W;
+        p.N = 4 * d->Cout; p.K = d->Cin;
+        p.w_sc = 4LL * d->Cout; p.w_st = d->Cout; p.w_sn = 1;      // packed [Cin][ij][Cout]
+        out_w = 2 * d->W;
+    } else {
+        p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pad = d->pad; p.dil = d->dil;
+        p.Ho = conv_out_dim(d->H, d->kh, d->stride, d->pad, d->dil);
+        p.Wo = conv_out_dim(d->W, d->kw, d->stride, d->pad, d->dil);
+        TDRN_REQUIRE(p.Ho > 0 && p.Wo > 0, "convolution input is too small (output would be %dx%d)", p.Ho, p.Wo);
+        p.N = d->Cout; p.K = d->kh * d->kw * d->Cin;
+        p.w_st = (long long)d->Cin * d->Cout; p.w_sc = d->Cout; p.w_sn = 1;   // packed [tap][cin][cout]
+        out_w = p.Wo;
+    }
+    p.M = d->B * p.Ho * p.Wo;
+    p.in_sb = d->in_sb > 0 ? d->in_sb : (long long)d->H * d->W * d->Cin; p.in_sy = (long long)d->W * d->Cin; p.in_sx = d->Cin; p.in_sc = 1;
+    p.out_sb = d->out_sb; p.out_sx = d->out_sp; p.out_sy = (long long)out_w * d->out_sp; p.out_sc = 1;
+    if (d->dg > 0) {
+        const long long oc = (long long)d->dg * 2 * d->kh * d->kw;
+        p.off_sb = (long long)p.Ho * p.Wo * oc; p.off_sy = (long long)p.Wo * oc; p.off_sx = oc; p.off_sc = 1;
+    }
+    return launch_conv(p, d->in_dtype, d->out_dtype, as_stream(stream));
+}
+
+extern "C" int tdrn_conv_first(const float *x, const float *weight, const float *bias, void *out, int B, int H,
+                               int W, int Cout, int stride, int relu, int out_dtype, tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(x && weight && out && B > 0 && H > 0 && W > 0 && Cout > 0, "tdrn_conv_first: bad argument");
+    TDRN_REQUIRE(stride == 1 || stride == 2, "tdrn_conv_first: stride must be 1 or 2");
+    ConvP p{};
+    p.in = x; p.w = weight; p.bias = bias; p.out = out;
+    p.B = B; p.Cin = 3; p.H = H; p.W = W; p.Cout = Cout; p.kh = p.kw = 3; p.stride = stride; p.pad = 1; p.dil = 1;
+    p.Ho = conv_out_dim(H, 3, stride, 1, 1); p.Wo = conv_out_dim(W, 3, stride, 1, 1);
+    p.M = B * p.Ho * p.Wo; p.N = Cout; p.K = 27; p.relu = relu; p.cpg = 3;
+    p.in_sb = 3LL * H * W; p.in_sc = (long long)H * W; p.in_sy = W; p.in_sx = 1;        // NCHW image
+    p.w_st = 3LL * Cout; p.w_sc = Cout; p.w_sn = 1;
+    p.out_sb = (long long)p.Ho * p.Wo * Cout; p.out_sy = (long long)p.Wo * Cout; p.out_sx = Cout; p.out_sc = 1;
+    return launch_conv(p, TDRN_F32, out_dtype, as_stream(stream));
+}
+
+extern "C" int tdrn_deform_conv_forward(const float *input, const float *weight, const float *offset, float *output,
+                                        int B, int Cin, int H, int W, int Cout, int kW, int kH, int dW, int dH,
+                                        int padW, int padH, int dilationH, int dilationW, int deformable_group,
+                                        tdrn_stream_t stream)
+{
+    // shape_check, utils/deformconv/deform_conv_cuda.c:7-96
+    TDRN_REQUIRE(input && weight && offset && output, "deform_conv_forward: null tensor");
+    TDRN_REQUIRE(kW > 0 && kH > 0, "kernel size should be greater than zero, but got kH: %d kW: %d", kH, kW);
+    TDRN_REQUIRE(dW > 0 && dH > 0, "stride should be greater than zero, but got dH: %d dW: %d", dH, dW);
+    TDRN_REQUIRE(dilationW > 0 && dilationH > 0, "dilation should be greater than 0, but got dilationH: %d dilationW: %d", dilationH, dilationW);
+    TDRN_REQUIRE(B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, "deform_conv_forward: bad shape");
+    TDRN_REQUIRE(deformable_group > 0 && Cin % deformable_group == 0, "input channels must divide deformable group size");
+    TDRN_REQUIRE(dW == dH && padW == padH && dilationW == dilationH, "deform_conv_forward: only square stride/pad/dilation are implemented");
+    ConvP p{};
+    p.in = input; p.w = weight; p.off = offset; p.out = output;
+    p.B = B; p.Cin = Cin; p.H = H; p.W = W; p.Cout = Cout; p.kh = kH; p.kw = kW; p.stride = dH; p.pad = padH; p.dil = dilationH;
+    p.Ho = conv_out_dim(H, kH, dH, padH, dilationH); p.Wo = conv_out_dim(W, kW, dW, padW, dilationW);
+    TDRN_REQUIRE(p.Ho > 0 && p.Wo > 0, "Given input size: (%d x %d x %d). Calculated output size: (%d x %d x %d). Output size is too small",
+                 Cin, H, W, Cout, p.Ho, p.Wo);
+    p.M = B * p.Ho * p.Wo; p.N = Cout; p.K = kH * kW * Cin; p.dg = deformable_group; p.cpg = Cin / deformable_group;
+    p.in_sb = (long long)Cin * H * W; p.in_sc = (long long)H * W; p.in_sy = W; p.in_sx = 1;
+    p.w_sn = (long long)Cin * kH * kW; p.w_sc = (long long)kH * kW; p.w_st = 1;             // reference [Cout,Cin,kH,kW]
+    const long long hw = (long long)p.Ho * p.Wo;
+    p.out_sb = Cout * hw; p.out_sc = hw; p.out_sy = p.Wo; p.out_sx = 1;
+    p.off_sb = (long long)deformable_group * 2 * kH * kW * hw; p.off_sc = hw; p.off_sy = p.Wo; p.off_sx = 1;
+    return launch_conv(p, TDRN_F32, TDRN_F32, as_stream(stream));
+}
+
+extern "C" int tdrn_dwconv3x3(const void *in, const float *weight, const float *bias, void *out, int B, int H, int W,
+                              int C, int stride, int relu, int dtype, tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(in && weight && out && B > 0 && H > 0 && W > 0 && C > 0, "tdrn_dwconv3x3: bad argument");
+    const int Ho = conv_out_dim(H, 3, stride, 1, 1), Wo = conv_out_dim(W, 3, stride, 1, 1);
+    const long long total = (long long)B * Ho * Wo * C;
+    if (dtype == TDRN_F32)
+        dwconv3x3_kernel<float><<<grid_1d(total, 256), 256, 0, as_stream(stream)>>>((const float *)in, weight, bias, (float *)out, B, H, W, C, Ho, Wo, stride, relu);
+    else
+        dwconv3x3_kernel<__nv_bfloat16><<<grid_1d(total, 256), 256, 0, as_stream(stream)>>>((const __nv_bfloat16 *)in, weight, bias, (__nv_bfloat16 *)out, B, H, W, C, Ho, Wo, stride, relu);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
+extern "C" int tdrn_maxpool2x2(const void *in, void *out, int B, int H, int W, int C, int ceil_mode, int dtype, tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0, "tdrn_maxpool2x2: bad argument");
+    const int Ho = ceil_mode ? (H + 1) / 2 : H / 2, Wo = ceil_mode ? (W + 1) / 2 : W / 2;
+    const long long total = (long long)B * Ho * Wo * C;
+    if (dtype == TDRN_F32)
+        maxpool2x2_kernel<float><<<grid_1d(total, 256), 256, 0, as_stream(stream)>>>((const float *)in, (float *)out, B, H, W, C, Ho, Wo);
+    else
+        maxpool2x2_kernel<__nv_bfloat16><<<grid_1d(total, 256), 256, 0, as_stream(stream)>>>((const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, B, H, W, C, Ho, Wo);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
+extern "C" int tdrn_l2norm(const void *in, const float *weight, void *out, long long pixels, int C, int dtype, tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(in && weight && out && pixels > 0 && C > 0, "tdrn_l2norm: bad argument");
+    const int grid = grid_1d(pixels * 32, 256);
+    if (dtype == TDRN_F32)
+        l2norm_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)in, weight, (float *)out, pixels, C);
+    else
+        l2norm_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16 *)in, weight, (__nv_bfloat16 *)out, pixels, C);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
+extern "C" int tdrn_softmax(const float *in, float *out, long long rows, int C, tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(in && out && rows > 0 && C > 0, "tdrn_softmax: bad argument");
+    softmax_rows_kernel<<<grid_1d(rows * 32, 256), 256, 0, as_stream(stream)>>>(in, out, rows, C);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
+extern "C" int tdrn_nhwc_to_nchw_f32(const void *in, float *out, int B, int H, int W, int C, int dtype, tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0, "tdrn_nhwc_to_nchw_f32: bad argument");
+    dim3 grid(ceil_div(H * W, 32), ceil_div(C, 32), B), block(32, 8);
+    if (dtype == TDRN_F32) nhwc_to_nchw_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float *)in, out, H * W, C);
+    else nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16 *)in, out, H * W, C);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
+extern "C" int tdrn_nchw_f32_to_nhwc(const float *in, void *out, int B, int C, int H, int W, int dtype, tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(in && out && B > 0 && H > 0 && W > 0 && C > 0, "tdrn_nchw_f32_to_nhwc: bad argument");
+    dim3 grid(ceil_div(H * W, 32), ceil_div(C, 32), B), block(32, 8);
+    if (dtype == TDRN_F32) nchw_to_nhwc_kernel<float><<<grid, block, 0, as_stream(stream)>>>(in, (float *)out, C, H * W);
+    else nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(stream)>>>(in, (__nv_bfloat16 *)out, C, H * W);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}

@@ -1,0 +1,239 @@
+"""Host-side executor shared by the detector modules.
+
+The reference forward passes (model/dualrefinedet_vggbn.py:119-206,
+model/dualrefinedet_mobilenet.py:127-199, model/refinedet_vgg.py:109-219,
+model/ssd4scale_vgg.py:71-135) are re-expressed as sequences of C-ABI operator calls on NHWC
+activations.  BatchNorm is folded into the preceding conv at pack time, ReLU / bias / residual add are
+conv epilogues, permute(0,2,3,1)+view+cat of the heads disappears because NHWC heads write straight
+into the flattened [B,P,4] / [B,P,C] outputs.
+
+precision: 'fp32' -> fp32 activations, SIMT fp32 kernels (1e-4 path)
+           'bf16' -> bf16 activations, tcgen05 implicit-GEMM convs + fused deformable head (2e-2 path)
+"""
+import os
+
+import torch
+
+from .. import ops
+
+VGG_CFG = [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'C', 512, 512, 512, 'M', 512, 512, 512]
+NUM_BOX = 3
+
+
+def level_sizes(size):
+    """Feature-map sides of the four pyramid levels (stride 8/16/32/64; pool3 is ceil_mode)."""
+    s = size
+    s = s // 2            # pool1
+    s = s // 2            # pool2
+    s = (s + 1) // 2      # pool3 'C'
+    l0 = s
+    l1 = l0 // 2          # pool4
+    l2 = l1 // 2          # pool5
+    l3 = (l2 + 2 - 3) // 2 + 1   # extras 3x3 s2 p1
+    return [l0, l1, l2, l3]
+
+
+class Engine(object):
+    def __init__(self, module, precision):
+        if precision not in ('fp32', 'bf16'):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        self.act = torch.bfloat16 if precision == 'bf16' else torch.float32
+        self.use_tc = precision == 'bf16' and os.environ.get('TDRN_DISABLE_TC', '0') != '1'
+        self.sd = {k: v for k, v in module.state_dict().items()}
+        p = next(module.parameters())
+        if not p.is_cuda:
+            raise NotImplementedError('tdrn_b200 runs on CUDA only: call net.to("cuda") first (no CPU fallback)')
+        self.device = p.device
+        self.pk = {}
+
+    # ---- weight packing -------------------------------------------------------------------------
+    def _bn(self, name):
+        return (self.sd[name + '.weight'], self.sd[name + '.bias'], self.sd[name + '.running_mean'],
+                self.sd[name + '.running_var'])
+
+    def packed(self, name, stride=1, pad=0, dil=1, bn=None, deconv=False):
+        pc = self.pk.get(name)
+        if pc is None:
+            pc = ops.PackedConv(self.sd[name + '.weight'], self.sd.get(name + '.bias'),
+                                self._bn(bn) if bn else None, stride, pad, dil, deconv, self.device,
+                                want_bf16=self.precision == 'bf16')
+            self.pk[name] = pc
+        return pc
+
+    def packed_dw(self, name, bn, stride):
+        pd = self.pk.get(name)
+        if pd is None:
+            pd = ops.PackedDw(self.sd[name + '.weight'], self._bn(bn), stride, self.device)
+            self.pk[name] = pd
+        return pd
+
+    def vec(self, name):
+        v = self.pk.get(name)
+        if v is None:
+            v = self.sd[name].detach().float().contiguous().to(self.device)
+            self.pk[name] = v
+        return v
+
+    # ---- operators ------------------------------------------------------------------------------
+    def conv(self, name, x, stride=1, pad=0, dil=1, bn=None, relu=False, deconv=False, **kw):
+        pc = self.packed(name, stride, pad, dil, bn, deconv)
+        use_tc = (self.use_tc and pc.w_bf16 is not None and x.dtype == torch.bfloat16
+                  and not kw.get('dg') and kw.get('in_shape') is None)
+        return ops.conv2d(x, pc, relu=relu, use_tc=use_tc, **kw)
+
+    def conv_first(self, name, x_nchw, stride, bn):
+        pc = self.packed(name, stride, 1, 1, bn)
+        return ops.conv_first(x_nchw, pc, True, self.act)
+
+    # ---- VGG trunk: vgg() model/networks.py:136-163 + extras, forward :130-153 --------------------
+    def vgg_trunk(self, x_nchw, bn, with_extras=True):
+        split43, split53 = (23, 33)[bn], (30, 43)[bn]
+        sources = []
+        idx, x = 0, None
+        step = 3 if bn else 2
+
+        def conv_block(i, x, pad=1, dil=1):
+            bnn = 'backbone.%d' % (i + 1) if bn else None
+            if x is None:
+                return self.conv_first('backbone.%d' % i, x_nchw, 1, bnn)
+            return self.conv('backbone.%d' % i, x, 1, pad, dil, bn=bnn, relu=True)
+
+        for v in VGG_CFG:
+            if idx == split43:
+                sources.append(ops.l2norm(x, self.vec('L2Norm_4_3.weight')))
+            if v == 'M' or v == 'C':
+                x = ops.maxpool2x2(x, ceil_mode=(v == 'C'))
+                idx += 1
+            else:
+                x = conv_block(idx, x)
+                idx += step
+        assert idx == split53
+        sources.append(ops.l2norm(x, self.vec('L2Norm_5_3.weight')))
+        x = ops.maxpool2x2(x, False)                      # pool5 (pool5_ds=True)
+        idx += 1
+        x = conv_block(idx, x, 6, 6)                      # conv6: 3x3 dilation 6
+        idx += step
+        x = conv_block(idx, x, 0, 1)                      # conv7: 1x1
+        sources.append(x)
+        if with_extras:
+            if bn:
+                x = self.conv('extras.0', x, bn='extras.1', relu=True)
+                x = self.conv('extras.3', x, 2, 1, bn='extras.4', relu=True)
+            else:
+                x = self.conv('extras.0', x, relu=True)
+                x = self.conv('extras.2', x, 2, 1, relu=True)
+            sources.append(x)
+        return sources
+
+    # ---- TCB / FPN: dualrefinedet_vggbn.py:166-179 -------------------------------------------------
+    def fpn(self, arm_sources):
+        x = self.conv('last_layer_trans.0', arm_sources[3], 1, 1, relu=True)
+        x = self.conv('last_layer_trans.2', x, 1, 1)
+        x = self.conv('last_layer_trans.3', x, 1, 1)
+        odm = [x]
+        trans = []
+        for k in range(3):
+            t = self.conv('trans_layers.%d.0' % k, arm_sources[k], 1, 1, relu=True)
+            trans.append(self.conv('trans_layers.%d.2' % k, t, 1, 1))
+        for k in range(3):
+            t = trans[2 - k]
+            # relu(up(x) + t): ConvTranspose2d k2 s2 as a pixel-shuffled GEMM with residual epilogue
+            u = self.conv('up_layers.%d' % k, x, deconv=True, relu=True, residual=t)
+            x = self.conv('latent_layers.%d' % k, u, 1, 1, relu=True)
+            odm.append(x)
+        odm.reverse()
+        return odm
+
+    # ---- heads ----------------------------------------------------------------------------------
+    def head_into(self, name, x, flat, per_prior, prior_off, P, pad=1, residual=False, offsets=None, dg=0):
+        """conv head writing NHWC-flattened rows into flat [B, P*per_prior] at prior offset."""
+        B = x.shape[0]
+        cout = NUM_BOX * per_prior
+        view = flat.view(B, P * per_prior)[:, prior_off * per_prior:]
+        return self.conv(name, x, 1, pad, out=view, out_sb=P * per_prior, out_sp=cout,
+                         residual=view if residual else None, offsets=offsets, dg=dg)
+
+    def arm_heads(self, arm_sources, P, lv_off, multihead, with_offsets=True):
+        """arm_loc + 1x1 offset convs: dualrefinedet_vggbn.py:154-165."""
+        B = arm_sources[0].shape[0]
+        arm_loc = torch.empty(B, P, 4, dtype=torch.float32, device=self.device)
+        offs, offs2 = [], []
+        for k, a in enumerate(arm_sources):
+            self.head_into('arm_loc.%d' % k, a, arm_loc, 4, lv_off[k], P)
+            if with_offsets:
+                H, W = a.shape[1], a.shape[2]
+                view = arm_loc.view(B, P * 4)[:, lv_off[k] * 4:]
+                kw = dict(in_shape=(B, H, W, 12), in_sb=P * 4, out_dtype=torch.float32)
+                offs.append(self.conv('offset.%d' % k, view, **kw))
+                if multihead:
+                    offs2.append(self.conv('offset2.%d' % k, view, **kw))
+        return arm_loc, offs, offs2
+
+    def deform_heads(self, feats, offs, offs2, P, lv_off, num_classes, dg, multihead, loc_name='odm_loc',
+                     conf_name='odm_conf', softmax=True):
+        """Deformable loc/conf heads (+5x5 multihead) and softmax: dualrefinedet_vggbn.py:180-197."""
+        B = feats[0].shape[0]
+        loc = torch.empty(B, P, 4, dtype=torch.float32, device=self.device)
+        conf = torch.empty(B, P, num_classes, dtype=torch.float32, device=self.device)
+        fused = self.use_tc and feats[0].dtype == torch.bfloat16 and all(f.shape[3] % 64 == 0 for f in feats)
+        for k, f in enumerate(feats):
+            if fused:
+                w1 = self.fused_head_weight(loc_name, conf_name, k)
+                w2 = self.fused_head_weight(loc_name + '_2', conf_name + '_2', k) if multihead else None
+                ops.deform_head(f, offs[k], w1, num_classes, dg, 3, 1, loc, conf, P, lv_off[k],
+                                offsets2=offs2[k] if multihead else None, w2_bf16=w2,
+                                kh2=5 if multihead else 0, pad2=2 if multihead else 0, softmax=softmax)
+            else:
+                self.head_into('%s.%d' % (loc_name, k), f, loc, 4, lv_off[k], P, 1, offsets=offs[k], dg=dg)
+                self.head_into('%s.%d' % (conf_name, k), f, conf, num_classes, lv_off[k], P, 1, offsets=offs[k], dg=dg)
+                if multihead:
+                    self.head_into('%s_2.%d' % (loc_name, k), f, loc, 4, lv_off[k], P, 2, True, offs2[k], dg)
+                    self.head_into('%s_2.%d' % (conf_name, k), f, conf, num_classes, lv_off[k], P, 2, True, offs2[k], dg)
+        conf2d = conf.view(B * P, num_classes)
+        if softmax and not fused:
+            ops.softmax_rows(conf2d, out=conf2d)
+        return loc, conf2d
+
+    def fused_head_weight(self, loc_name, conf_name, k):
+        """loc||conf rows concatenated, K-major bf16 [N_pad, kh*kw*Cin] for the fused tcgen05 head."""
+        key = 'fused.%s.%s.%d' % (loc_name, conf_name, k)
+        w = self.pk.get(key)
+        if w is None:
+            wl = self.sd['%s.%d.weight' % (loc_name, k)].detach().double().cpu()
+            wc = self.sd['%s.%d.weight' % (conf_name, k)].detach().double().cpu()
+            wcat = torch.cat([wl, wc], 0)                                  # [N, Cin, kh, kw]
+            n, cin, kh, kw = wcat.shape
+            wk = wcat.permute(0, 2, 3, 1).reshape(n, kh * kw * cin)
+            n_pad = (n + 15) // 16 * 16
+            wp = torch.zeros(n_pad, wk.shape[1], dtype=torch.float64)
+            wp[:n] = wk
+            w = wp.to(torch.bfloat16).contiguous().to(self.device)
+            self.pk[key] = w
+        return w
+
+    def plain_heads(self, feats, P, lv_off, num_classes, multihead, loc_name, conf_name, softmax=True,
+                    keep_loc_maps=False):
+        """Plain-conv loc/conf heads (RefineDet ODM refinedet_vgg.py:185-194, SSD4Scale static :111-117)."""
+        B = feats[0].shape[0]
+        loc = torch.empty(B, P, 4, dtype=torch.float32, device=self.device)
+        conf = torch.empty(B, P, num_classes, dtype=torch.float32, device=self.device)
+        for k, f in enumerate(feats):
+            self.head_into('%s.%d' % (loc_name, k), f, loc, 4, lv_off[k], P, 1)
+            self.head_into('%s.%d' % (conf_name, k), f, conf, num_classes, lv_off[k], P, 1)
+            if multihead:
+                self.head_into('%s_2.%d' % (loc_name, k), f, loc, 4, lv_off[k], P, 2, True)
+                self.head_into('%s_2.%d' % (conf_name, k), f, conf, num_classes, lv_off[k], P, 2, True)
+        conf2d = conf.view(B * P, num_classes)
+        if softmax:
+            ops.softmax_rows(conf2d, out=conf2d)
+        return loc, conf2d
+
+
+def prior_layout(feats):
+    """Prior counts/offsets for NHWC-flattened heads: index = off_k + (y*W+x)*3 + a."""
+    offs, p = [], 0
+    for f in feats:
+        offs.append(p)
+        p += f.shape[1] * f.shape[2] * NUM_BOX
+    return p, offs

@@ -1,0 +1,70 @@
+"""DualRefineDet-MobileNet: drop-in for the reference's model/dualrefinedet_mobilenet.py.
+
+``build_net(phase, size, num_classes, def_groups, multihead)`` (:210-214); state-dict keys :19-121;
+forward outputs (:183-189): (arm_loc, None, odm_loc, softmax(conf)).
+"""
+import torch.nn as nn
+
+from ..layers.modules.l2norm import L2Norm
+from ._base import DetectorBase
+from ._engine import prior_layout
+from .dualrefinedet_vggbn import add_fpn, add_deform_heads, _list
+from .networks import conv_dw
+from .. import ops
+
+DW_CFG = [(32, 64, 1), (64, 128, 2), (128, 128, 1), (128, 256, 1), (256, 256, 1), (256, 512, 2),
+          (512, 512, 1), (512, 512, 1), (512, 512, 1), (512, 512, 1), (512, 512, 1),
+          (512, 1024, 2), (1024, 1024, 1)]
+
+
+class RefineSSD(DetectorBase):
+    def __init__(self, size, num_classes=21, phase='train', def_groups=1, multihead=False):
+        super(RefineSSD, self).__init__()
+        self.num_classes, self.size, self.phase = num_classes, size, phase
+        self.def_groups, self.multihead = def_groups, multihead
+        first = nn.Sequential(nn.Conv2d(3, 32, 3, 2, 1, bias=False), nn.BatchNorm2d(32), nn.ReLU(inplace=True))
+        self.backbone = nn.ModuleList([first] + [conv_dw(i, o, s) for (i, o, s) in DW_CFG])
+        self.L2Norm_4_3 = L2Norm(512, 20)
+        self.L2Norm_5_3 = L2Norm(1024, 8)
+        self.extras = nn.ModuleList([
+            nn.Sequential(nn.Conv2d(cin, 256, kernel_size=1), nn.BatchNorm2d(256), nn.ReLU(inplace=True),
+                          conv_dw(256, 512, 2)) for cin in (1024, 512)])
+        src = [512, 1024, 512, 512]
+        add_fpn(self, src, bias=False)
+        self.arm_loc = _list(lambda k: nn.Conv2d(src[k], 12, kernel_size=3, stride=1, padding=1, bias=False))
+        add_deform_heads(self, num_classes, def_groups, multihead, False)
+        if phase == 'test':
+            self.softmax = nn.Softmax(dim=1)
+
+    def _dw_block(self, E, name, x, stride):
+        """conv_dw (networks.py:736-745): depthwise 3x3+BN+ReLU then pointwise 1x1+BN+ReLU."""
+        x = ops.dwconv3x3(x, E.packed_dw(name + '.0', name + '.1', stride), relu=True)
+        return E.conv(name + '.3', x, bn=name + '.4', relu=True)
+
+    def forward(self, x):
+        E = self.engine()
+        x = self._check_input(x)
+        x = E.conv_first('backbone.0.0', x, 2, 'backbone.0.1')
+        arm_sources = []
+        for n, (i, o, s) in enumerate(DW_CFG):
+            if n + 1 == 12:
+                arm_sources.append(ops.l2norm(x, E.vec('L2Norm_4_3.weight')))
+            x = self._dw_block(E, 'backbone.%d' % (n + 1), x, s)
+        arm_sources.append(ops.l2norm(x, E.vec('L2Norm_5_3.weight')))
+        for e in range(2):
+            x = E.conv('extras.%d.0' % e, x, bn='extras.%d.1' % e, relu=True)
+            x = self._dw_block(E, 'extras.%d.3' % e, x, 2)
+            arm_sources.append(x)
+        P, lv = prior_layout(arm_sources)
+        arm_loc, offs, offs2 = E.arm_heads(arm_sources, P, lv, self.multihead)
+        odm_sources = E.fpn(arm_sources)
+        odm_loc, conf = E.deform_heads(odm_sources, offs, offs2, P, lv, self.num_classes, self.def_groups,
+                                       self.multihead)
+        return arm_loc, None, odm_loc, conf
+
+
+def build_net(phase, size=320, num_classes=21, def_groups=1, multihead=False):
+    if size not in [320, 512]:
+        print("Error: Sorry only SSD320 and SSD512 is supported currently!")
+        return
+    return RefineSSD(size, num_classes=num_classes, phase=phase, def_groups=def_groups, multihead=multihead)

@@ -1,0 +1,302 @@
+"""Thin torch-tensor wrappers over the C ABI (include/tdrn_b200.h).
+
+PyTorch supplies device memory and the current stream; every computation is a call into
+libtdrn_b200.so.  Tensors named ``*_nhwc`` are [B,H,W,C] contiguous activations (fp32 or bf16).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import F32, BF16, ConvDesc, DeformHeadDesc, check, ptr, stream_handle
+
+BN_EPS = 1e-5
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError('unsupported dtype %s' % t.dtype)
+
+
+def _torch_dt(code):
+    return torch.float32 if code == F32 else torch.bfloat16
+
+
+def _cuda(t, name):
+    if not t.is_cuda:
+        raise NotImplementedError('%s must be a CUDA tensor: tdrn_b200 has no CPU path' % name)
+    return t.contiguous()
+
+
+def conv_out(n, k, stride, pad, dil):
+    return (n + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+
+
+class PackedConv(object):
+    """Weights of one conv layer, BN-folded, packed for both kernels.
+
+    w_f32  [kh*kw*Cin, Cout] fp32 (tap-major, then cin)      -> tdrn_conv2d (SIMT, fp32 accumulate)
+    w_bf16 [Cout_pad, kh*kw*Cin] bf16, K-major               -> tdrn_conv2d_tc (tcgen05)
+    deconv (ConvTranspose2d k2 s2, weight [Cin,Cout,2,2]): w_f32 [Cin, 4*Cout] with n = (i*2+j)*Cout+co
+    """
+
+    def __init__(self, weight, bias=None, bn=None, stride=1, pad=0, dil=1, deconv=False, device='cuda',
+                 want_bf16=True):
+        w = weight.detach().double().cpu()
+        b = bias.detach().double().cpu() if bias is not None else None
+        self.deconv = deconv
+        self.stride, self.pad, self.dil = stride, pad, dil
+        if deconv:
+            self.cin, self.cout, self.kh, self.kw = w.shape[0], w.shape[1], 2, 2
+            assert tuple(w.shape[2:]) == (2, 2) and bn is None
+            self.w_f32 = w.permute(0, 2, 3, 1).reshape(self.cin, 4 * self.cout).float().contiguous().to(device)
+            # K-major rows n = (i*2+j)*Cout + co
+            wk = w.permute(2, 3, 1, 0).reshape(4 * self.cout, self.cin)
+        else:
+            self.cout, self.cin, self.kh, self.kw = w.shape
+            if bn is not None:                      # fold eval-mode BatchNorm2d (eps 1e-5) in float64
+                gamma, beta, mean, var = [t.detach().double().cpu() for t in bn]
+                scale = gamma / torch.sqrt(var + BN_EPS)
+                w = w * scale.view(-1, 1, 1, 1)
+                b = (b if b is not None else torch.zeros_like(mean)) - mean
+                b = b * scale + beta
+            self.w_f32 = w.permute(2, 3, 1, 0).reshape(self.kh * self.kw * self.cin, self.cout).float().contiguous().to(device)
+            wk = w.permute(0, 2, 3, 1).reshape(self.cout, self.kh * self.kw * self.cin)
+        self.bias = b.float().contiguous().to(device) if b is not None else None
+        self.w_bf16 = None
+        if want_bf16 and self.cin % 64 == 0:
+            rows = wk.shape[0]
+            rows_pad = (rows + 15) // 16 * 16
+            wp = torch.zeros(rows_pad, wk.shape[1], dtype=torch.float64)
+            wp[:rows] = wk
+            self.w_bf16 = wp.to(torch.bfloat16).contiguous().to(device)
+
+
+def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_sb=None, out_sp=None,
+           offsets=None, dg=0, use_tc=False, in_shape=None, in_sb=0):
+    """out = act(conv(x) + bias (+ residual)).  ``out`` may be a view into a larger flat buffer, in which
+    case out_sb/out_sp give the per-image and per-pixel strides (elements)."""
+    if in_shape is not None:          # x is a strided view (e.g. one level of the flat [B,P,4] ARM output)
+        x = x_nhwc
+        B, H, W, Cin = in_shape
+    else:
+        x = _cuda(x_nhwc, 'input')
+        B, H, W, Cin = x.shape
+    assert Cin == pc.cin, (Cin, pc.cin)
+    if pc.deconv:
+        Ho, Wo = 2 * H, 2 * W
+    else:
+        Ho, Wo = conv_out(H, pc.kh, pc.stride, pc.pad, pc.dil), conv_out(W, pc.kw, pc.stride, pc.pad, pc.dil)
+    if out is None:
+        odt = out_dtype if out_dtype is not None else x.dtype
+        out = torch.empty(B, Ho, Wo, pc.cout, dtype=odt, device=x.device)
+    if out_sb is None:
+        out_sb, out_sp = Ho * Wo * pc.cout, pc.cout
+    d = ConvDesc(B=B, H=H, W=W, Cin=Cin, Cout=pc.cout, kh=pc.kh, kw=pc.kw, stride=pc.stride, pad=pc.pad,
+                 dil=pc.dil, relu=int(relu), deconv2x2=int(pc.deconv), dg=dg, in_dtype=_dt(x),
+                 out_dtype=_dt(out), out_sb=out_sb, out_sp=out_sp, in_sb=in_sb)
+    L = _lib.lib()
+    if use_tc:
+        if pc.w_bf16 is None or x.dtype != torch.bfloat16 or dg:
+            raise _lib.TdrnError('tcgen05 conv needs bf16 input, Cin %% 64 == 0 and no offsets')
+        check(L.tdrn_conv2d_tc(ctypes.byref(d), ptr(x), ptr(pc.w_bf16), ptr(pc.bias), ptr(residual), ptr(out),
+                               stream_handle()), 'tdrn_conv2d_tc')
+    else:
+        check(L.tdrn_conv2d(ctypes.byref(d), ptr(x), ptr(pc.w_f32), ptr(pc.bias), ptr(residual), ptr(offsets),
+                            ptr(out), stream_handle()), 'tdrn_conv2d')
+    return out
+
+
+def conv_first(x_nchw, pc, relu, out_dtype):
+    x = _cuda(x_nchw, 'input')
+    if x.dtype != torch.float32:
+        raise TypeError('network input must be float32 NCHW (reference boundary)')
+    B, C, H, W = x.shape
+    assert C == 3 and pc.kh == 3 and pc.pad == 1
+    Ho, Wo = conv_out(H, 3, pc.stride, 1, 1), conv_out(W, 3, pc.stride, 1, 1)
+    out = torch.empty(B, Ho, Wo, pc.cout, dtype=out_dtype, device=x.device)
+    check(_lib.lib().tdrn_conv_first(ptr(x), ptr(pc.w_f32), ptr(pc.bias), ptr(out), B, H, W, pc.cout, pc.stride,
+                                     int(relu), _dt(out), stream_handle()), 'tdrn_conv_first')
+    return out
+
+
+class PackedDw(object):
+    """Depthwise 3x3 weights [C,1,3,3] (+BN) -> [9, C] fp32."""
+
+    def __init__(self, weight, bn, stride, device='cuda'):
+        w = weight.detach().double().cpu()
+        gamma, beta, mean, var = [t.detach().double().cpu() for t in bn]
+        scale = gamma / torch.sqrt(var + BN_EPS)
+        w = w * scale.view(-1, 1, 1, 1)
+        self.c = w.shape[0]
+        self.stride = stride
+        self.w = w.reshape(self.c, 9).t().float().contiguous().to(device)
+        self.bias = (beta - mean * scale).float().contiguous().to(device)
+
+
+def dwconv3x3(x_nhwc, pd, relu=True):
+    x = _cuda(x_nhwc, 'input')
+    B, H, W, C = x.shape
+    Ho, Wo = conv_out(H, 3, pd.stride, 1, 1), conv_out(W, 3, pd.stride, 1, 1)
+    out = torch.empty(B, Ho, Wo, C, dtype=x.dtype, device=x.device)
+    check(_lib.lib().tdrn_dwconv3x3(ptr(x), ptr(pd.w), ptr(pd.bias), ptr(out), B, H, W, C, pd.stride, int(relu),
+                                    _dt(x), stream_handle()), 'tdrn_dwconv3x3')
+    return out
+
+
+def maxpool2x2(x_nhwc, ceil_mode=False):
+    x = _cuda(x_nhwc, 'input')
+    B, H, W, C = x.shape
+    Ho, Wo = ((H + 1) // 2, (W + 1) // 2) if ceil_mode else (H // 2, W // 2)
+    out = torch.empty(B, Ho, Wo, C, dtype=x.dtype, device=x.device)
+    check(_lib.lib().tdrn_maxpool2x2(ptr(x), ptr(out), B, H, W, C, int(ceil_mode), _dt(x), stream_handle()),
+          'tdrn_maxpool2x2')
+    return out
+
+
+def l2norm(x_nhwc, weight_f32):
+    x = _cuda(x_nhwc, 'input')
+    out = torch.empty_like(x)
+    C = x.shape[-1]
+    check(_lib.lib().tdrn_l2norm(ptr(x), ptr(weight_f32), ptr(out), ctypes.c_longlong(x.numel() // C), C, _dt(x),
+                                 stream_handle()), 'tdrn_l2norm')
+    return out
+
+
+def softmax_rows(x, out=None):
+    x = _cuda(x, 'input')
+    assert x.dtype == torch.float32 and x.dim() == 2
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().tdrn_softmax(ptr(x), ptr(out), ctypes.c_longlong(x.shape[0]), x.shape[1], stream_handle()),
+          'tdrn_softmax')
+    return out
+
+
+def nhwc_to_nchw_f32(x_nhwc):
+    x = _cuda(x_nhwc, 'input')
+    B, H, W, C = x.shape
+    out = torch.empty(B, C, H, W, dtype=torch.float32, device=x.device)
+    check(_lib.lib().tdrn_nhwc_to_nchw_f32(ptr(x), ptr(out), B, H, W, C, _dt(x), stream_handle()),
+          'tdrn_nhwc_to_nchw_f32')
+    return out
+
+
+def nchw_f32_to_nhwc(x_nchw, dtype):
+    x = _cuda(x_nchw, 'input')
+    assert x.dtype == torch.float32
+    B, C, H, W = x.shape
+    out = torch.empty(B, H, W, C, dtype=dtype, device=x.device)
+    check(_lib.lib().tdrn_nchw_f32_to_nhwc(ptr(x), ptr(out), B, C, H, W, _dt(out), stream_handle()),
+          'tdrn_nchw_f32_to_nhwc')
+    return out
+
+
+def deform_conv_nchw(input, offset, weight, stride, pad, dil, dg):
+    """The reference operator boundary: deform_conv_forward_cuda (NCHW fp32)."""
+    for name, t in (('input', input), ('offset', offset), ('weight', weight)):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise NotImplementedError('%s must be a torch.cuda.FloatTensor' % name)   # networks.py:632-640
+    input, offset, weight = input.contiguous(), offset.contiguous(), weight.contiguous()
+    if input.dim() != 4:
+        raise ValueError('Expected 4D tensor as input, got {}D tensor instead.'.format(input.dim()))
+    B, C, H, W = input.shape
+    Cout, Cin, kh, kw = weight.shape
+    Ho, Wo = conv_out(H, kh, stride[0], pad[0], dil[0]), conv_out(W, kw, stride[1], pad[1], dil[1])
+    if Ho <= 0 or Wo <= 0:
+        raise ValueError('convolution input is too small (output would be {}x{}x{}x{})'.format(B, Cout, Ho, Wo))
+    if Cin != C:
+        raise RuntimeError('invalid number of input planes, expected: %d, but got: %d' % (Cin, C))
+    if tuple(offset.shape) != (B, dg * 2 * kh * kw, Ho, Wo):
+        raise RuntimeError('invalid offset shape %s, expected %s' % (tuple(offset.shape), (B, dg * 2 * kh * kw, Ho, Wo)))
+    out = torch.empty(B, Cout, Ho, Wo, dtype=torch.float32, device=input.device)
+    check(_lib.lib().tdrn_deform_conv_forward(ptr(input), ptr(weight), ptr(offset), ptr(out), B, C, H, W, Cout,
+                                              kw, kh, stride[1], stride[0], pad[1], pad[0], dil[0], dil[1], dg,
+                                              stream_handle()), 'tdrn_deform_conv_forward')
+    return out
+
+
+def deform_head(feat_nhwc, offsets, w_bf16, num_classes, dg, kh, pad, loc_out, conf_out, P, prior_off,
+                offsets2=None, w2_bf16=None, kh2=0, pad2=0, softmax=True):
+    x = _cuda(feat_nhwc, 'feat')
+    B, H, W, Cin = x.shape
+    d = DeformHeadDesc(B=B, H=H, W=W, Cin=Cin, num_classes=num_classes, dg=dg, kh=kh, pad=pad, kh2=kh2, pad2=pad2,
+                       P=P, prior_off=prior_off, softmax=int(softmax))
+    check(_lib.lib().tdrn_deform_head(ctypes.byref(d), ptr(x), ptr(offsets), ptr(w_bf16), ptr(offsets2),
+                                      ptr(w2_bf16), ptr(loc_out), ptr(conf_out), stream_handle()), 'tdrn_deform_head')
+
+
+def decode(loc, priors, arm_loc=None):
+    loc, priors = _cuda(loc, 'loc').float(), _cuda(priors, 'priors').float()
+    B, P, _ = loc.shape
+    arm = _cuda(arm_loc, 'arm_loc').float() if arm_loc is not None else None
+    out = torch.empty(B, P, 4, dtype=torch.float32, device=loc.device)
+    check(_lib.lib().tdrn_decode(ptr(loc), ptr(priors), ptr(arm), B, P, ptr(out), stream_handle()), 'tdrn_decode')
+    return out
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def detect(loc, conf, priors, arm_loc, scale, num_classes, top_k, conf_thresh, nms_thresh, out=None):
+    loc = _cuda(loc, 'loc_data').float()
+    conf = _cuda(conf, 'conf_data').float()
+    priors = _cuda(priors, 'prior_data').float()
+    arm = _cuda(arm_loc, 'arm_loc_data').float() if arm_loc is not None else None
+    B, P = loc.shape[0], priors.shape[0]
+    L = _lib.lib()
+    nbytes = L.tdrn_detect_workspace_bytes(B, P, num_classes, top_k)
+    ws = _workspace(nbytes, loc.device)
+    if out is None:
+        out = torch.empty(B, num_classes, top_k, 5, dtype=torch.float32, device=loc.device)
+    sc = (ctypes.c_float * 4)(*[float(v) for v in scale])
+    check(L.tdrn_detect(ptr(loc), ptr(conf), ptr(priors), ptr(arm), sc, B, P, num_classes, top_k,
+                        ctypes.c_float(conf_thresh), ctypes.c_double(nms_thresh), ptr(out), ptr(ws),
+                        ctypes.c_size_t(ws.numel()), stream_handle()), 'tdrn_detect')
+    return out
+
+
+def nms_device(dets, thresh, max_keep=0):
+    """dets [n,5] CUDA fp32 -> (keep int32 [n], num_keep int32 [1]) on device."""
+    dets = _cuda(dets, 'dets').float()
+    n = dets.shape[0]
+    L = _lib.lib()
+    ws = _workspace(L.tdrn_nms_workspace_bytes(n), dets.device)
+    keep = torch.empty(max(n, 1), dtype=torch.int32, device=dets.device)
+    num = torch.zeros(1, dtype=torch.int32, device=dets.device)
+    check(L.tdrn_nms(ptr(dets), n, ctypes.c_double(thresh), max_keep, ptr(keep), ptr(num), ptr(ws),
+                     ctypes.c_size_t(ws.numel()), stream_handle()), 'tdrn_nms')
+    return keep, num
+
+
+def prior_box(cfg):
+    """PriorBox.forward via the C ABI (host) -> CPU fp32 tensor [P,4]."""
+    n = len(cfg['feature_maps'])
+    ia = lambda v: (ctypes.c_int * len(v))(*[int(t) for t in v])
+    ars, n_ar = [], []
+    for a in cfg['aspect_ratios']:
+        if len(a) > 4:
+            raise ValueError('at most 4 aspect ratios per level are supported')
+        ars += [int(t) for t in a] + [0] * (4 - len(a))
+        n_ar.append(len(a))
+    mx = ia(cfg['max_sizes']) if len(cfg['max_sizes']) else None
+    num = ctypes.c_int(0)
+    L = _lib.lib()
+    args = (int(cfg['min_dim']), n, ia(cfg['feature_maps']), ia(cfg['steps']), ia(cfg['min_sizes']), mx, ia(n_ar),
+            ia(ars), int(bool(cfg['flip'])), int(bool(cfg['clip'])))
+    check(L.tdrn_prior_box(*args, None, ctypes.byref(num)), 'tdrn_prior_box')
+    out = torch.empty(num.value, 4, dtype=torch.float32)
+    check(L.tdrn_prior_box(*args, ptr(out), ctypes.byref(num)), 'tdrn_prior_box')
+    return out

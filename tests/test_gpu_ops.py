@@ -1,0 +1,140 @@
+"""GPU parity: fp32 SIMT operators called through the C ABI vs the oracle / plain torch fp32."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize('k,pad,dg,stride,dil,cin,cout,h,w', [
+    (3, 1, 1, 1, 1, 8, 6, 9, 11), (3, 1, 2, 1, 1, 8, 12, 9, 11), (5, 2, 1, 1, 1, 8, 6, 7, 7),
+    (3, 1, 4, 2, 1, 8, 6, 10, 9), (3, 2, 1, 1, 2, 4, 5, 9, 9), (3, 1, 8, 1, 1, 64, 75, 10, 10),
+    (1, 0, 1, 1, 1, 6, 4, 5, 5)])
+def test_deform_conv_forward_nchw_vs_oracle(k, pad, dg, stride, dil, cin, cout, h, w):
+    """tdrn_deform_conv_forward == deform_conv_forward_cuda semantics (border rules included)."""
+    from oracle import deform_conv_ref as R
+    from tdrn_b200.model.networks import ConvOffset2d
+    g = torch.Generator().manual_seed(k * 100 + dg)
+    x = torch.randn(2, cin, h, w, generator=g)
+    m = ConvOffset2d(cin, cout, k, stride=stride, padding=pad, dilation=dil, num_deformable_groups=dg)
+    ho, wo = R.output_size(h, w, k, k, stride, pad, dil)
+    off = torch.randn(2, dg * 2 * k * k, ho, wo, generator=g) * 2.5
+    ref = R.deform_conv_forward(x, off, m.weight.detach(), stride, pad, dil, dg)
+    out = m.cuda()(x.cuda(), off.cuda())
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert rel_err(out.cpu().numpy(), ref.numpy()) < 1e-5          # fp32: accumulation order only
+
+
+def test_deform_conv_border_probes():
+    from tdrn_b200.model.networks import conv_offset2d
+    x = (torch.arange(16, dtype=torch.float32).view(1, 1, 4, 4) + 1).cuda()
+    w = torch.ones(1, 1, 1, 1).cuda()
+    def at(dy, dx):
+        off = torch.zeros(1, 2, 4, 4); off[0, 0] = dy; off[0, 1] = dx
+        return conv_offset2d(x, off.cuda(), w)[0, 0].cpu()
+    assert at(-0.5, 0.0)[0, 0] == 0
+    assert at(0.5, 0.0)[3, 2] == 15
+    assert at(0.0, 0.75)[1, 3] == 8
+    assert at(1.0, 0.0)[3, 0] == 0
+
+
+def test_deform_conv_shape_errors():
+    from tdrn_b200.model.networks import conv_offset2d
+    x = torch.zeros(1, 4, 5, 5).cuda()
+    w = torch.zeros(3, 4, 3, 3).cuda()
+    with pytest.raises(ValueError):
+        conv_offset2d(torch.zeros(4, 5, 5).cuda(), torch.zeros(1, 18, 5, 5).cuda(), w, padding=1)
+    with pytest.raises(RuntimeError):
+        conv_offset2d(x, torch.zeros(1, 18, 4, 4).cuda(), w, padding=1)       # wrong offset map size
+    with pytest.raises(ValueError):
+        conv_offset2d(torch.zeros(1, 4, 2, 2).cuda(), torch.zeros(1, 18, 1, 1).cuda(), w)   # too small
+
+
+@pytest.mark.parametrize('cin,cout,k,stride,pad,dil,h,w,relu,bias', [
+    (3, 16, 3, 1, 1, 1, 13, 9, True, True), (16, 24, 3, 1, 1, 1, 12, 12, True, True),
+    (32, 12, 3, 1, 1, 1, 10, 10, False, True), (16, 40, 1, 1, 0, 1, 7, 5, True, False),
+    (16, 32, 3, 2, 1, 1, 10, 10, True, True), (16, 32, 3, 1, 6, 6, 10, 10, True, True),
+    (12, 18, 1, 1, 0, 1, 5, 5, False, True), (8, 75, 5, 1, 2, 1, 6, 6, False, False)])
+def test_conv2d_simt_vs_torch(cin, cout, k, stride, pad, dil, h, w, relu, bias):
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(3, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) * 0.2
+    b = torch.randn(cout, generator=g) if bias else None
+    ref = F.conv2d(x, wt, b, stride, pad, dil)
+    if relu:
+        ref = F.relu(ref)
+    pc = ops.PackedConv(wt, b, None, stride, pad, dil, device='cuda', want_bf16=False)
+    out = ops.conv2d(_nhwc(x).cuda(), pc, relu=relu)
+    assert rel_err(_nchw(out).cpu().numpy(), ref.numpy()) < 1e-5
+
+
+def test_conv2d_bn_fold_residual_and_deconv():
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 16, 6, 7, generator=g)
+    wt = torch.randn(8, 16, 3, 3, generator=g) * 0.2
+    b = torch.randn(8, generator=g)
+    bn = (torch.rand(8, generator=g) + 0.5, torch.randn(8, generator=g), torch.randn(8, generator=g), torch.rand(8, generator=g) + 0.5)
+    ref = F.relu(F.batch_norm(F.conv2d(x, wt, b, 1, 1), bn[2], bn[3], bn[0], bn[1], False, 0.0, 1e-5))
+    pc = ops.PackedConv(wt, b, bn, 1, 1, 1, device='cuda', want_bf16=False)
+    out = ops.conv2d(_nhwc(x).cuda(), pc, relu=True)
+    assert rel_err(_nchw(out).cpu().numpy(), ref.numpy()) < 1e-5
+    # ConvTranspose2d k2 s2 + residual + relu  (dualrefinedet_vggbn.py:177)
+    wd = torch.randn(16, 8, 2, 2, generator=g) * 0.3
+    bd = torch.randn(8, generator=g)
+    t = torch.randn(2, 8, 12, 14, generator=g)
+    ref = F.relu(F.conv_transpose2d(x, wd, bd, 2, 0) + t)
+    pd = ops.PackedConv(wd, bd, None, deconv=True, device='cuda', want_bf16=False)
+    out = ops.conv2d(_nhwc(x).cuda(), pd, relu=True, residual=_nhwc(t).cuda())
+    assert rel_err(_nchw(out).cpu().numpy(), ref.numpy()) < 1e-5
+
+
+def test_conv_first_nchw_input():
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 3, 20, 24, generator=g)
+    for stride, cout in ((1, 64), (2, 32)):
+        wt = torch.randn(cout, 3, 3, 3, generator=g) * 0.3
+        b = torch.randn(cout, generator=g)
+        ref = F.relu(F.conv2d(x, wt, b, stride, 1))
+        pc = ops.PackedConv(wt, b, None, stride, 1, 1, device='cuda', want_bf16=False)
+        out = ops.conv_first(x.cuda(), pc, True, torch.float32)
+        assert rel_err(_nchw(out).cpu().numpy(), ref.numpy()) < 1e-5
+
+
+def test_pool_l2norm_softmax_dw_layout(golden):
+    from tdrn_b200 import ops
+    from tdrn_b200.layers.modules import L2Norm
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 24, 11, 13, generator=g)
+    for ceil in (False, True):
+        ref = F.max_pool2d(x, 2, 2, ceil_mode=ceil)
+        out = ops.maxpool2x2(_nhwc(x).cuda(), ceil)
+        assert torch.equal(_nchw(out).cpu(), ref)
+    gs = golden('small_cases')
+    l2 = L2Norm(16, 10)
+    with torch.no_grad():
+        l2.weight.copy_(torch.from_numpy(gs['l2_w']))
+    y = l2.cuda()(torch.from_numpy(gs['l2_x']).cuda())
+    assert rel_err(y.cpu().numpy(), gs['l2_y']) < 1e-6
+    z = torch.randn(1000, 21, generator=g) * 3
+    assert rel_err(ops.softmax_rows(z.cuda()).cpu().numpy(), F.softmax(z, 1).numpy()) < 1e-6
+    wd = torch.randn(24, 1, 3, 3, generator=g)
+    bn = (torch.rand(24, generator=g) + 0.5, torch.randn(24, generator=g), torch.randn(24, generator=g), torch.rand(24, generator=g) + 0.5)
+    for stride in (1, 2):
+        ref = F.relu(F.batch_norm(F.conv2d(x, wd, None, stride, 1, 1, 24), bn[2], bn[3], bn[0], bn[1], False, 0.0, 1e-5))
+        out = ops.dwconv3x3(_nhwc(x).cuda(), ops.PackedDw(wd, bn, stride, 'cuda'))
+        assert rel_err(_nchw(out).cpu().numpy(), ref.numpy()) < 1e-5
+    assert torch.equal(ops.nhwc_to_nchw_f32(ops.nchw_f32_to_nhwc(x.cuda(), torch.float32)).cpu(), x)

@@ -1,0 +1,141 @@
+"""GPU parity: decode / NMS / Detect through the C ABI.  Integer outputs are compared bit-exactly."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_dets(n, seed, spread=300.0, size=80.0):
+    rng = np.random.RandomState(seed)
+    xy = rng.rand(n, 2) * spread
+    wh = rng.rand(n, 2) * size + 4
+    return np.hstack([xy, xy + wh, rng.rand(n, 1)]).astype(np.float32)
+
+
+@pytest.mark.parametrize('n,seed,thresh', [(1, 0, 0.45), (2, 1, 0.45), (33, 2, 0.3), (256, 3, 0.45), (257, 4, 0.45),
+                                           (1000, 5, 0.45), (6375, 6, 0.45), (6375, 7, 0.7), (16320, 8, 0.45)])
+def test_nms_wrapper_bit_exact(n, seed, thresh):
+    from oracle import c_oracle as C
+    from tdrn_b200.utils.nms_wrapper import nms
+    dets = _rand_dets(n, seed, spread=300.0 if n < 5000 else 900.0)
+    keep = nms(dets, thresh, force_cpu=True)
+    assert keep == C.cpu_nms(dets, thresh)
+
+
+def test_nms_dense_overlaps_ties_and_max_keep(golden):
+    from oracle import c_oracle as C, nms_ref as N
+    from tdrn_b200.utils.nms_wrapper import nms
+    from tdrn_b200 import ops
+    # heavy suppression: everything piled on a few centres; quantised scores -> many exact ties
+    rng = np.random.RandomState(11)
+    c = rng.randint(0, 5, size=3000)
+    xy = c[:, None] * 60.0 + rng.rand(3000, 2) * 6
+    dets = np.hstack([xy, xy + 40 + rng.rand(3000, 2) * 4, np.round(rng.rand(3000, 1), 2)]).astype(np.float32)
+    assert nms(dets, 0.45) == C.cpu_nms(dets, 0.45) == N.cpu_nms(dets, 0.45)
+    # identical boxes with identical scores: only the lowest index survives
+    d = np.tile(np.array([[5, 5, 50, 50, 0.5]], np.float32), (700, 1))
+    assert nms(d, 0.45) == [0]
+    # IoU exactly at the threshold is suppressed (>=, cpu_nms.pyx:65): boxes 0..9 and 5..14 (+1 convention) -> 5/15
+    e = np.array([[0, 0, 9, 0, 0.9], [5, 0, 14, 0, 0.8]], np.float32)
+    assert nms(e, 1.0 / 3.0) == C.cpu_nms(e, 1.0 / 3.0)
+    # golden from the reference's py_cpu_nms.py
+    g = golden('small_cases')
+    assert nms(g['nms_dets'], 0.45) == g['nms_keep_py_cpu_nms'].tolist()
+    # device API with early exit
+    dets = _rand_dets(5000, 12)
+    keep, num = ops.nms_device(torch.from_numpy(dets).cuda(), 0.45, max_keep=200)
+    n = int(num.item())
+    assert n == 200 and keep[:n].cpu().tolist() == C.cpu_nms(dets, 0.45)[:200]
+
+
+def test_decode_matches_reference_golden(golden):
+    from tdrn_b200 import ops
+    from tdrn_b200.layers.functions import PriorBox
+    from tdrn_b200.data import mb_cfg
+    from oracle.make_golden import syn_inputs
+    g = golden('small_cases')
+    loc, arm, conf = syn_inputs()
+    pri = PriorBox(mb_cfg['VOC_320']).forward()
+    dec = ops.decode(loc.cuda(), pri.cuda(), arm.cuda()).cpu().numpy()
+    ref = g['syn_decode']
+    # identical op order; only expf may differ from the CPU libm by an ulp or two
+    assert np.abs(dec - ref).max() <= 8 * np.spacing(np.float32(np.abs(ref).max()))
+    dec1 = ops.decode(loc.cuda(), pri.cuda(), None).cpu().numpy()
+    from oracle import c_oracle as C
+    assert np.abs(dec1 - C.decode(loc.numpy(), pri.numpy(), None)).max() <= 8 * np.spacing(np.float32(np.abs(dec1).max()))
+
+
+@pytest.mark.parametrize('top_k,conf_t,nms_t,use_arm,scale', [
+    (200, 0.01, 0.45, True, [320.] * 4), (50, 0.05, 0.3, False, [500., 375., 500., 375.]), (5, 0.2, 0.45, True, [320.] * 4)])
+def test_detect_bit_exact_given_decoded_boxes(top_k, conf_t, nms_t, use_arm, scale):
+    """Detect output == oracle Detect run on the boxes the GPU decoded (isolates the <=2 ulp expf)."""
+    from oracle import c_oracle as C
+    from oracle.make_golden import syn_inputs
+    from tdrn_b200 import ops
+    from tdrn_b200.layers.functions import Detect, PriorBox
+    from tdrn_b200.data import mb_cfg
+    loc, arm, conf = syn_inputs()
+    if not use_arm:
+        loc = loc * 0.1
+    pri = PriorBox(mb_cfg['VOC_320']).forward()
+    det = Detect(21, 0, top_k, conf_t, nms_t)
+    out = det.forward(loc.cuda(), conf.cuda(), pri.cuda(), arm_loc_data=arm.cuda() if use_arm else None,
+                      scale=torch.tensor(scale))
+    assert tuple(out.shape) == (2, 21, top_k, 5) and out.dtype == torch.float32
+    boxes = ops.decode(loc.cuda(), pri.cuda(), arm.cuda() if use_arm else None).cpu().numpy()
+    ref = C.detect(boxes, conf.numpy(), np.asarray(scale, np.float32), 21, top_k, conf_t, nms_t)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert not out[:, 0].any()
+
+
+def test_detect_matches_reference_golden(golden):
+    """End to end vs the arrays the reference's own Detect produced (tolerating decode ulps)."""
+    from oracle.make_golden import syn_inputs
+    from tdrn_b200.layers.functions import Detect, PriorBox
+    from tdrn_b200.data import mb_cfg
+    g = golden('small_cases')
+    loc, arm, conf = syn_inputs()
+    pri = PriorBox(mb_cfg['VOC_320']).forward()
+    out = Detect(21, 0, 200, 0.01, 0.45).forward(loc.cuda(), conf.cuda(), pri.cuda(), arm_loc_data=arm.cuda()).cpu().numpy()
+    ref = g['syn_detect']
+    assert np.array_equal(out[..., 0], ref[..., 0])                     # same detections kept, same order
+    assert np.abs(out[..., 1:] - ref[..., 1:]).max() < 1e-5
+
+
+def test_detect_random_init_regime_and_empty():
+    """Regime R (every prior is a candidate for every class) and the no-candidate case."""
+    from oracle import c_oracle as C
+    from tdrn_b200 import ops
+    from tdrn_b200.layers.functions import Detect, PriorBox
+    from tdrn_b200.data import mb_cfg
+    g = torch.Generator().manual_seed(21)
+    P, Cn, B = 6375, 21, 2
+    pri = PriorBox(mb_cfg['VOC_320']).forward()
+    loc = torch.randn(B, P, 4, generator=g) * 0.5
+    arm = torch.randn(B, P, 4, generator=g) * 0.5
+    conf = torch.softmax(torch.randn(B * P, Cn, generator=g) * 0.1, 1)      # ~1/21 everywhere > 0.01
+    out = Detect(Cn, 0, 200, 0.01, 0.45).forward(loc.cuda(), conf.cuda(), pri.cuda(), arm_loc_data=arm.cuda())
+    boxes = ops.decode(loc.cuda(), pri.cuda(), arm.cuda()).cpu().numpy()
+    ref = C.detect(boxes, conf.numpy(), np.array([320.] * 4, np.float32), Cn, 200, 0.01, 0.45)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    out = Detect(Cn, 0, 200, 0.99, 0.45).forward(loc.cuda(), conf.cuda(), pri.cuda(), arm_loc_data=arm.cuda())
+    assert not out.any()
+
+
+def test_detect_coco512_shape():
+    from oracle import c_oracle as C
+    from tdrn_b200 import ops
+    from tdrn_b200.layers.functions import Detect, PriorBox
+    from tdrn_b200.data import mb_cfg
+    g = torch.Generator().manual_seed(22)
+    P, Cn, B = 16320, 81, 1
+    pri = PriorBox(mb_cfg['VOC_512_RefineDet']).forward()
+    loc = torch.randn(B, P, 4, generator=g) * 0.5
+    logits = torch.randn(B * P, Cn, generator=g) * 2
+    logits[:, 0] += 3
+    conf = torch.softmax(logits, 1)
+    out = Detect(Cn, 0, 100, 0.01, 0.45).forward(loc.cuda(), conf.cuda(), pri.cuda(), scale=torch.tensor([512.] * 4))
+    boxes = ops.decode(loc.cuda(), pri.cuda(), None).cpu().numpy()
+    ref = C.detect(boxes, conf.numpy(), np.array([512.] * 4, np.float32), Cn, 100, 0.01, 0.45)
+    assert np.array_equal(out.cpu().numpy(), ref)

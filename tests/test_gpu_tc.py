@@ -1,0 +1,128 @@
+"""GPU parity: tcgen05 kernels (implicit-GEMM conv, fused deformable head) vs fp32 references computed
+from the SAME bf16-rounded operands (so the only difference is fp32 accumulation order)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize('b,cin,cout,k,pad,dil,h,w,relu', [
+    (2, 64, 64, 3, 1, 1, 32, 32, True),        # conv1_2 class (BN=64 tile)
+    (1, 64, 128, 3, 1, 1, 24, 40, True),       # conv2_1 class (BN=128)
+    (2, 128, 256, 3, 1, 1, 20, 20, True),      # conv3 class (BN=256), 20x20 boxes
+    (1, 256, 512, 3, 1, 1, 40, 40, True),      # conv4 class: two N tiles, 40-wide rows
+    (3, 512, 1024, 3, 6, 6, 10, 10, True),     # conv6: dilation 6
+    (3, 1024, 256, 1, 0, 1, 10, 10, True),     # extras.0 / conv7 class: 1x1
+    (7, 512, 256, 3, 1, 1, 5, 5, False),       # last_layer_trans: 5x5 maps, several images per tile
+    (2, 64, 64, 3, 1, 1, 17, 23, False),       # ragged sizes
+    (1, 192, 96, 5, 2, 1, 9, 9, False),        # 5x5 kernel, Cout not a multiple of 64
+])
+def test_conv_tc_vs_fp32(b, cin, cout, k, pad, dil, h, w, relu):
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(cin + cout + k)
+    x = _bf(torch.randn(b, cin, h, w, generator=g))
+    wt = _bf(torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5)
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv2d(x, wt, bias, 1, pad, dil)
+    if relu:
+        ref = F.relu(ref)
+    pc = ops.PackedConv(wt, bias, None, 1, pad, dil, device='cuda')
+    out = ops.conv2d(_nhwc(x).cuda().to(torch.bfloat16), pc, relu=relu, out_dtype=torch.float32, use_tc=True)
+    torch.cuda.synchronize()
+    assert rel_err(_nchw(out).cpu().numpy(), ref.numpy()) < 2e-5
+    out16 = ops.conv2d(_nhwc(x).cuda().to(torch.bfloat16), pc, relu=relu, use_tc=True)
+    assert out16.dtype == torch.bfloat16
+    assert rel_err(_nchw(out16.float()).cpu().numpy(), ref.numpy()) < 6e-3     # bf16 output rounding
+
+
+def test_conv_tc_head_into_flat_buffer_and_deconv():
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    # ARM head: Cout=12, fp32 rows written at a prior offset of a flat [B,P,4] tensor
+    B, H, W, P, off = 2, 10, 10, 6375, 6000
+    x = _bf(torch.randn(B, 128, H, W, generator=g))
+    wt = _bf(torch.randn(12, 128, 3, 3, generator=g) * 0.05)
+    bias = torch.randn(12, generator=g)
+    ref = F.conv2d(x, wt, bias, 1, 1).permute(0, 2, 3, 1).reshape(B, -1)
+    pc = ops.PackedConv(wt, bias, None, 1, 1, 1, device='cuda')
+    flat = torch.zeros(B, P * 4, device='cuda')
+    ops.conv2d(_nhwc(x).cuda().to(torch.bfloat16), pc, out=flat[:, off * 4:], out_sb=P * 4, out_sp=12, use_tc=True)
+    assert rel_err(flat[:, off * 4:off * 4 + H * W * 12].cpu().numpy(), ref.numpy()) < 2e-5
+    assert not flat[:, :off * 4].any() and not flat[:, off * 4 + H * W * 12:].any()
+    # ConvTranspose2d k2 s2 + residual + ReLU
+    xd = _bf(torch.randn(2, 256, 5, 5, generator=g))
+    wd = _bf(torch.randn(256, 256, 2, 2, generator=g) * 0.06)
+    bd = torch.randn(256, generator=g) * 0.1
+    t = _bf(torch.randn(2, 256, 10, 10, generator=g))
+    ref = F.relu(F.conv_transpose2d(xd, wd, bd, 2, 0) + t)
+    pd = ops.PackedConv(wd, bd, None, deconv=True, device='cuda')
+    out = ops.conv2d(_nhwc(xd).cuda().to(torch.bfloat16), pd, relu=True, residual=_nhwc(t).cuda().to(torch.bfloat16), use_tc=True)
+    assert rel_err(_nchw(out.float()).cpu().numpy(), ref.numpy()) < 6e-3
+
+
+@pytest.mark.parametrize('B,H,W,cin,C,dg,multihead', [
+    (2, 10, 10, 256, 21, 1, False), (1, 40, 40, 256, 21, 1, True), (3, 5, 5, 256, 21, 1, True),
+    (1, 16, 16, 256, 81, 1, False), (2, 10, 10, 512, 31, 8, False), (1, 10, 10, 1024, 31, 8, False)])
+def test_deform_head_tc_vs_oracle(B, H, W, cin, C, dg, multihead):
+    from oracle import deform_conv_ref as R
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(B * H + C)
+    x = _bf(torch.randn(B, cin, H, W, generator=g))
+    wl = _bf(torch.randn(12, cin, 3, 3, generator=g) * 0.03)
+    wc = _bf(torch.randn(3 * C, cin, 3, 3, generator=g) * 0.03)
+    off = torch.randn(B, dg * 18, H, W, generator=g) * 1.5
+    loc_ref = R.deform_conv_forward(x, off, wl, 1, 1, 1, dg)
+    conf_ref = R.deform_conv_forward(x, off, wc, 1, 1, 1, dg)
+    w2 = off2 = None
+    if multihead:
+        wl2 = _bf(torch.randn(12, cin, 5, 5, generator=g) * 0.02)
+        wc2 = _bf(torch.randn(3 * C, cin, 5, 5, generator=g) * 0.02)
+        off2 = torch.randn(B, dg * 50, H, W, generator=g) * 1.5
+        loc_ref = loc_ref + R.deform_conv_forward(x, off2, wl2, 1, 2, 1, dg)
+        conf_ref = conf_ref + R.deform_conv_forward(x, off2, wc2, 1, 2, 1, dg)
+        w2 = torch.cat([wl2, wc2], 0)
+
+    def pack(wcat):
+        n, ci, kh, kw = wcat.shape
+        wk = wcat.permute(0, 2, 3, 1).reshape(n, kh * kw * ci)
+        wp = torch.zeros((n + 15) // 16 * 16, wk.shape[1])
+        wp[:n] = wk
+        return wp.to(torch.bfloat16).cuda()
+
+    P, poff = H * W * 3 + 11, 5
+    loc = torch.zeros(B, P, 4, device='cuda')
+    conf = torch.zeros(B, P, C, device='cuda')
+    ops.deform_head(_nhwc(x).cuda().to(torch.bfloat16), _nhwc(off).cuda(), pack(torch.cat([wl, wc], 0)), C, dg, 3, 1,
+                    loc, conf, P, poff, offsets2=_nhwc(off2).cuda() if multihead else None,
+                    w2_bf16=pack(w2) if multihead else None, kh2=5 if multihead else 0, pad2=2 if multihead else 0,
+                    softmax=False)
+    torch.cuda.synchronize()
+    lr = loc_ref.permute(0, 2, 3, 1).reshape(B, H * W * 3, 4)
+    cr = conf_ref.permute(0, 2, 3, 1).reshape(B, H * W * 3, C)
+    # the sampled A tile is rounded to bf16 before the MMA -> ~2^-9 relative per element
+    assert rel_err(loc[:, poff:poff + H * W * 3].cpu().numpy(), lr.numpy()) < 1e-2
+    assert rel_err(conf[:, poff:poff + H * W * 3].cpu().numpy(), cr.numpy()) < 1e-2
+    assert not loc[:, :poff].any() and not loc[:, poff + H * W * 3:].any()
+    conf2 = torch.zeros(B, P, C, device='cuda')
+    ops.deform_head(_nhwc(x).cuda().to(torch.bfloat16), _nhwc(off).cuda(), pack(torch.cat([wl, wc], 0)), C, dg, 3, 1,
+                    loc, conf2, P, poff, offsets2=_nhwc(off2).cuda() if multihead else None,
+                    w2_bf16=pack(w2) if multihead else None, kh2=5 if multihead else 0, pad2=2 if multihead else 0,
+                    softmax=True)
+    sm = torch.softmax(conf[:, poff:poff + H * W * 3], -1)
+    assert rel_err(conf2[:, poff:poff + H * W * 3].cpu().numpy(), sm.cpu().numpy()) < 1e-5
