@@ -200,15 +200,22 @@ def run_gpu(args, rank, world, local_rank):
             static_out = hot_path(static_x)
     stream.synchronize()
 
+    def replay():
+        if args.no_graph:
+            with torch.no_grad():
+                static_out.copy_(hot_path(static_x))
+        else:
+            graph.replay()
+
     def step_device(i):
         static_x.copy_(dev_x[i % n_in], non_blocking=True)      # device->device: the frames are already in HBM
-        graph.replay()
+        replay()
         if world > 1:
             dist.all_gather_into_tensor(gathered, static_out)
 
     def step_e2e(i):
         static_x.copy_(host_x[i % n_in], non_blocking=True)     # pinned host -> device
-        graph.replay()
+        replay()
         if world > 1:
             dist.all_gather_into_tensor(gathered, static_out)
         host_out.copy_(static_out, non_blocking=True)           # detections -> host
@@ -319,6 +326,7 @@ def main():
     ap.add_argument('--impl', default='tdrn_b200', choices=['tdrn_b200', 'reference'])
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay (profiling)')
     ap.add_argument('--detail', action='store_true', help='print the per-layer CUDA-event breakdown to stderr')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

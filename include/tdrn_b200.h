@@ -114,6 +114,9 @@ typedef struct tdrn_conv_desc {
     long long out_sb, out_sp;
     long long in_sb;           /* input batch stride in elements; 0 = H*W*Cin (lets the 1x1 offset conv read
                                   the ARM regression straight out of the flattened [B,P,4] tensor)        */
+    int pool2x2;               /* 1: fuse the following MaxPool2d(2,2) (vgg() 'M'/'C', networks.py:141-143) into
+                                  the epilogue; output is [B,Ho/2,Wo/2,Cout]. tdrn_conv2d_tc only, needs
+                                  Wo % 16 == 0 and Ho % 8 == 0                                             */
 } tdrn_conv_desc;
 
 /* fp32-accurate SIMT implicit GEMM (also bf16 in/out with fp32 accumulate). bias/residual may be NULL;
@@ -124,7 +127,7 @@ int tdrn_conv2d(const tdrn_conv_desc *d, const void *in, const float *weight_f32
 
 /* tcgen05/TMEM/TMA implicit GEMM, bf16 in, fp32 accumulate, bf16 or fp32 out.
    weight_bf16 packed [Cout_pad][kh*kw*Cin] K-major (Cout_pad = Cout rounded up to 16).
-   Requires Cin % 64 == 0.  Returns TDRN_EUNSUPPORTED otherwise (caller picks tdrn_conv2d). */
+   Requires Cin % 64 == 0 and stride 1 or 2.  Returns TDRN_EUNSUPPORTED otherwise (caller picks tdrn_conv2d). */
 int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in_bf16, const void *weight_bf16, const float *bias,
                    const void *residual, void *out, tdrn_stream_t stream);
 

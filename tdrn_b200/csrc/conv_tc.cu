@@ -3,18 +3,24 @@
 // Replaces the cuDNN calls behind every dense nn.Conv2d / nn.ConvTranspose2d(k2,s2) of the detectors
 // (model/networks.py:136-163 vgg(), model/dualrefinedet_vggbn.py:30-50,97-114)
 // for bf16 NHWC activations.  BatchNorm is folded into weight/bias on the host; bias, residual add
-// (`up(x) + t`, dualrefinedet_vggbn.py:177), ReLU and the output cast are the epilogue.
+// (`up(x) + t`, dualrefinedet_vggbn.py:177), ReLU, the following MaxPool2d(2,2) and the output cast
+// are the epilogue.
 //
 // GEMM view:  D[M = 128 output pixels, N <= BN couts] = sum over (tap, 64-channel block)
 //             A[128 px, 64 ch] * B[N, 64 ch]^T,  fp32 accumulation in TMEM.
 //   A : no im2col buffer anywhere.  One 4-D TMA box (64 ch, bw, bh, bn) of the NHWC input, shifted by
-//       the tap offset; out-of-bounds rows/cols (the conv zero padding) are zero-filled by TMA.
-//       The box lands in shared memory as 128-byte rows with the 128B swizzle = the canonical
-//       K-major UMMA layout, pixel index (n, y, x) = tile row.
+//       the tap offset (element stride 2 for the stride-2 conv); out-of-bounds rows/cols (the conv zero
+//       padding) are zero-filled by TMA.  The box lands in shared memory as 128-byte rows with the
+//       128B swizzle = the canonical K-major UMMA layout, pixel index (n, y, x) = tile row.
 //   B : packed weights [Cout_pad][kh*kw*Cin] bf16 (k = tap*Cin + c), 2-D TMA box (64, BN).
-//   Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + single-thread MMA issuer,
-//   warps 2-5 epilogue (tcgen05.ld -> bias/residual/ReLU -> global).  Two CTAs are co-resident per SM
-//   (<= 97 KB smem, <= 256 TMEM columns each) so one tile's epilogue overlaps the other's main loop.
+//
+// Persistent, warp-specialised: grid = min(#tiles, #SMs), each CTA walks tiles blockIdx.x, +grid, ...
+//   warp 0   TMA producer            (ring of STAGES smem stages, full/empty mbarriers)
+//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2-5 epilogue: tcgen05.ld -> bias / residual / ReLU / 2x2 max-pool (warp shuffles) -> global
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1; the smem ring is 192 KB deep so TMA latency is hidden even when a layer has
+// fewer tiles than SMs (the 10x10 / 5x5 pyramid levels).
 #include "tc_common.cuh"
 
 namespace tdrn {
@@ -34,12 +40,12 @@ EncodeTiledFn get_encode_tiled()
 }
 
 int make_tmap_bf16(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                   const uint32_t *box)
+                   const uint32_t *box, const uint32_t *elem_strides)
 {
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return TDRN_ECUDA; }
     cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bdim[5]; cuuint32_t estr[5];
-    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = elem_strides ? elem_strides[i] : 1; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bdim, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -54,58 +60,55 @@ int make_tmap_bf16(CUtensorMap *m, const void *base, int rank, const uint64_t *d
 }
 
 struct TcConvP {
-    int H, W, B;                 // output (= tile) space
+    int H, W, B;                 // output (= tile) space, before pooling
     int bw, bh, bn;              // A box: bw*bh*bn <= 128 pixels
-    int tiles_w, tiles_h;
+    int tiles_w, tiles_h, m_tiles, n_tiles;
     int Cin, Cout, n_total;      // n_total = Cout, or 4*Cout for the k2s2 deconv
-    int kw, taps, pad, dil;
+    int kw, taps, pad, dil, stride;
     uint32_t a_bytes;            // bytes one A box deposits (bw*bh*bn*128)
     uint32_t b_bytes;            // bytes one B box deposits (min(BN, n_pad16)*128)
     const float *bias; const void *res; void *out;
     long long out_sb, out_sp; int out_w;
-    int relu, deconv, out_f32;
+    int relu, deconv, out_f32, pool;
 };
 
 template <int BN> struct TcCfg {
     static constexpr int A_BYTES = 128 * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
-    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // + slack for manual 1024B alignment
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;          // 4 / 6 / 8 stages for BN = 256 / 128 / 64
+    static constexpr int TMEM_COLS = 2 * BN;                           // double-buffered accumulator
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;     // + slack for manual 1024B alignment
 };
 
+constexpr int TC_THREADS = 192;
+
 template <int BN>
-__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB, const TcConvP p)
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB, const TcConvP p)
 {
     using Cfg = TcCfg<BN>;
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[Cfg::STAGES];
     __shared__ __align__(8) uint64_t empty_bar[Cfg::STAGES];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_s;
 
     uint8_t *tiles = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // ---- tile coordinates -------------------------------------------------------------------
-    const int tw = blockIdx.x % p.tiles_w;
-    const int th = (blockIdx.x / p.tiles_w) % p.tiles_h;
-    const int tn = blockIdx.x / (p.tiles_w * p.tiles_h);
-    const int w0 = tw * p.bw, h0 = th * p.bh, b0 = tn * p.bn;
-    const int n0 = blockIdx.y * BN;
     const int n_pad16 = (p.n_total + 15) & ~15;
-    const int n_eff = min(BN, n_pad16 - n0);                 // UMMA N of this CTA (multiple of 16)
     const int cblocks = p.Cin >> 6;
     const int num_kb = p.taps * cblocks;
+    const int total_tiles = p.m_tiles * p.n_tiles;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
 #pragma unroll
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&tmem_full_bar, 1);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
@@ -117,38 +120,53 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % Cfg::STAGES;
-                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                uint8_t *sa = tiles + s * Cfg::STAGE_BYTES;
-                uint8_t *sb = sa + Cfg::A_BYTES;
-                const int tap = kb / cblocks, cb = kb - tap * cblocks;
-                const int tr = tap / p.kw, ts = tap - tr * p.kw;
-                mbar_expect_tx(&full_bar[s], p.a_bytes + p.b_bytes);
-                tma_load_4d(sa, &tmA, &full_bar[s], cb * 64, w0 + ts * p.dil - p.pad, h0 + tr * p.dil - p.pad, b0);
-                tma_load_2d(sb, &tmB, &full_bar[s], kb * 64, n0);
+            uint32_t it = 0;                                   // running k-block counter across tiles
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+                const int w0 = tw * p.bw * p.stride - p.pad, h0 = th * p.bh * p.stride - p.pad, b0 = tn * p.bn;
+                const int n0 = nt * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % Cfg::STAGES;
+                    const uint32_t ph = (it / Cfg::STAGES) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    uint8_t *sa = tiles + s * Cfg::STAGE_BYTES;
+                    const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                    const int tr = tap / p.kw, ts = tap - tr * p.kw;
+                    mbar_expect_tx(&full_bar[s], p.a_bytes + p.b_bytes);
+                    tma_load_4d(sa, &tmA, &full_bar[s], cb * 64, w0 + ts * p.dil, h0 + tr * p.dil, b0);
+                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[s], kb * 64, n0);
+                }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, n_eff);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % Cfg::STAGES;
-                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
-                mbar_wait(&full_bar[s], ph);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+                const int nt = tile / p.m_tiles;
+                const int n_eff = min(BN, n_pad16 - nt * BN);           // UMMA N (multiple of 16)
+                const uint32_t idesc = umma_idesc_bf16(128, n_eff);
+                const uint32_t buf = tcount & 1u;
+                mbar_wait(&tmem_empty_bar[buf], ((tcount >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
                 tc_fence_after();
-                const uint32_t sa = smem_u32(tiles + s * Cfg::STAGE_BYTES);
-                const uint64_t adesc = umma_desc_sw128(sa);
-                const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
+                const uint32_t d_tmem = tmem_base + buf * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % Cfg::STAGES;
+                    const uint32_t ph = (it / Cfg::STAGES) & 1u;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_sw128(sa);
+                    const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)      // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle atom
-                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                umma_commit(&empty_bar[s]);     // frees the smem stage when these MMAs retire
+                    for (int k = 0; k < 4; ++k)      // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle atom
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_commit(&empty_bar[s]);     // frees the smem stage when these MMAs retire
+                }
+                umma_commit(&tmem_full_bar[buf]);   // accumulator of this tile complete
             }
-            umma_commit(&tmem_full_bar);        // accumulator complete
         }
         __syncwarp();
     } else {
@@ -156,61 +174,86 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         const int quad = warp & 3;              // TMEM lane quadrant this warp may read
         const int r = quad * 32 + lane;
         const int wl = r % p.bw, hl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
-        const int x = w0 + wl, y = h0 + hl, b = b0 + nl;
-        const bool valid = nl < p.bn && x < p.W && y < p.H && b < p.B;
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-        for (int c0 = 0; c0 < n_eff; c0 += 16) {
-            float v[16];
-            tmem_ld16(trow + (uint32_t)c0, v);
-            const int n = n0 + c0;
-            if (!valid || n >= p.n_total) continue;
-            int co = n, oy = y, ox = x;
-            if (p.deconv) { const int ij = n / p.Cout; co = n - ij * p.Cout; oy = 2 * y + (ij >> 1); ox = 2 * x + (ij & 1); }
-            const long long o = (long long)b * p.out_sb + ((long long)oy * p.out_w + ox) * p.out_sp + co;
-            const int nv = min(16, p.n_total - n);
-            if (p.bias) {
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+            const int x = tw * p.bw + wl, y = th * p.bh + hl, b = tn * p.bn + nl;
+            const int n0 = nt * BN;
+            const int n_eff = min(BN, n_pad16 - n0);
+            const bool valid = nl < p.bn && x < p.W && y < p.H && b < p.B;
+            const uint32_t buf = tcount & 1u;
+            mbar_wait(&tmem_full_bar[buf], (tcount >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
+            for (int c0 = 0; c0 < n_eff; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + (uint32_t)c0, v);
+                const int n = n0 + c0;
+                if (n >= p.n_total) continue;                       // warp-uniform
+                int co = n, oy = y, ox = x;
+                if (p.deconv) { const int ij = n / p.Cout; co = n - ij * p.Cout; oy = 2 * y + (ij >> 1); ox = 2 * x + (ij & 1); }
+                const int nv = min(16, p.n_total - n);
+                if (p.bias) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) if (j < nv) v[j] += __ldg(p.bias + co + j);
-            }
-            if (p.out_f32) {
-                float *op = (float *)p.out + o;
-                if (p.res) { const float *rp = (const float *)p.res + o;
+                    for (int j = 0; j < 16; ++j) if (j < nv) v[j] += __ldg(p.bias + co + j);
+                }
+                bool store = valid;
+                if (p.pool) {
+                    // MaxPool2d(2,2) fused: the 2x2 partners of pixel (hl, wl) live in lanes ^1 and ^bw of this warp
+                    // (bw is a power of two <= 16, bh even, tile rows are (h, w)-ordered). relu/max commute.
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (j < nv) v[j] += rp[j]; }
+                    for (int j = 0; j < 16; ++j) {
+                        float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                        v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, p.bw));
+                    }
+                    store = valid && !(wl & 1) && !(hl & 1);
+                    oy = y >> 1; ox = x >> 1;
+                }
+                if (!store) continue;
+                const long long o = (long long)b * p.out_sb + ((long long)oy * p.out_w + ox) * p.out_sp + co;
+                if (p.out_f32) {
+                    float *op = (float *)p.out + o;
+                    if (p.res) { const float *rp = (const float *)p.res + o;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) if (j < nv) op[j] = p.relu ? fmaxf(v[j], 0.f) : v[j];
-            } else {
-                __nv_bfloat16 *op = (__nv_bfloat16 *)p.out + o;
-                const bool vec = nv == 16 && ((o & 7) == 0);
-                if (p.res) {
-                    const __nv_bfloat16 *rp = (const __nv_bfloat16 *)p.res + o;
+                        for (int j = 0; j < 16; ++j) if (j < nv) v[j] += rp[j]; }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (j < nv) op[j] = p.relu ? fmaxf(v[j], 0.f) : v[j];
+                } else {
+                    __nv_bfloat16 *op = (__nv_bfloat16 *)p.out + o;
+                    const bool vec = nv == 16 && ((o & 7) == 0);
+                    if (p.res) {
+                        const __nv_bfloat16 *rp = (const __nv_bfloat16 *)p.res + o;
+                        if (vec) {
+                            uint4 q[2]; q[0] = ((const uint4 *)rp)[0]; q[1] = ((const uint4 *)rp)[1];
+                            const __nv_bfloat16 *rb = (const __nv_bfloat16 *)q;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] += __bfloat162float(rb[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) if (j < nv) v[j] += __bfloat162float(rp[j]);
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
                     if (vec) {
-                        uint4 q[2]; q[0] = ((const uint4 *)rp)[0]; q[1] = ((const uint4 *)rp)[1];
-                        const __nv_bfloat16 *rb = (const __nv_bfloat16 *)q;
+                        uint4 q[2];
+                        __nv_bfloat162 *qb = (__nv_bfloat162 *)q;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += __bfloat162float(rb[j]);
+                        for (int j = 0; j < 8; ++j) qb[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        ((uint4 *)op)[0] = q[0]; ((uint4 *)op)[1] = q[1];
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) if (j < nv) v[j] += __bfloat162float(rp[j]);
+                        for (int j = 0; j < 16; ++j) if (j < nv) op[j] = __float2bfloat16_rn(v[j]);
                     }
                 }
-                if (p.relu) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-                }
-                if (vec) {
-                    uint4 q[2];
-                    __nv_bfloat162 *qb = (__nv_bfloat162 *)q;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) qb[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                    ((uint4 *)op)[0] = q[0]; ((uint4 *)op)[1] = q[1];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) if (j < nv) op[j] = __float2bfloat16_rn(v[j]);
-                }
             }
+            // all tcgen05.ld of this tile are complete (tmem_ld16 waits): hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
     }
 
@@ -221,12 +264,12 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 
 // Pick the A box (bw, bh, bn), bw*bh*bn <= 128, maximising useful rows; bn > 1 only when one image's
 // whole map fits (the 10x10 and 5x5 pyramid levels).  Ties -> wider rows.
-static void pick_box(int B, int H, int W, int &bw, int &bh, int &bn)
+static void pick_box(int B, int H, int W, int max_w, int max_h, int &bw, int &bh, int &bn)
 {
     double best = -1;
     bw = bh = bn = 1;
-    for (int w = 1; w <= W && w <= 128; ++w)
-        for (int h = 1; h <= H && w * h <= 128; ++h) {
+    for (int w = 1; w <= W && w <= 128 && w <= max_w; ++w)
+        for (int h = 1; h <= H && w * h <= 128 && h <= max_h; ++h) {
             const int nmax = (w == W && h == H) ? 128 / (w * h) : 1;
             for (int n = 1; n <= nmax && n <= B; ++n) {
                 const long long tiles = (long long)((W + w - 1) / w) * ((H + h - 1) / h) * ((B + n - 1) / n);
@@ -236,12 +279,20 @@ static void pick_box(int B, int H, int W, int &bw, int &bh, int &bn)
         }
 }
 
+static int g_num_sms = 0;
+
 template <int BN>
-static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcConvP &p, int m_tiles, int n_tiles, cudaStream_t st)
+static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcConvP &p, cudaStream_t st)
 {
     using Cfg = TcCfg<BN>;
+    if (!g_num_sms) {
+        int dev = 0;
+        TDRN_CUDA(cudaGetDevice(&dev));
+        TDRN_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
     TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    conv_tc_kernel<BN><<<dim3(m_tiles, n_tiles), 192, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+    const int total = p.m_tiles * p.n_tiles;
+    conv_tc_kernel<BN><<<total < g_num_sms ? total : g_num_sms, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }
@@ -257,39 +308,53 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
 {
     TDRN_REQUIRE(d && in && weight && out, "tdrn_conv2d_tc: null argument");
     if (d->in_dtype != TDRN_BF16 || d->Cin % 64 != 0 || d->dg != 0 || d->in_sb != 0 ||
-        (!d->deconv2x2 && d->stride != 1)) {
-        set_error("tdrn_conv2d_tc: needs bf16 input, Cin %% 64 == 0, stride 1, no offsets (got dtype=%d Cin=%d stride=%d dg=%d)",
+        (!d->deconv2x2 && d->stride != 1 && d->stride != 2)) {
+        set_error("tdrn_conv2d_tc: needs bf16 input, Cin %% 64 == 0, stride 1 or 2, no offsets (got dtype=%d Cin=%d stride=%d dg=%d)",
                   d->in_dtype, d->Cin, d->stride, d->dg);
         return TDRN_EUNSUPPORTED;
     }
     TcConvP p{};
     const int kh = d->deconv2x2 ? 1 : d->kh, kw = d->deconv2x2 ? 1 : d->kw;
     const int pad = d->deconv2x2 ? 0 : d->pad, dil = d->deconv2x2 ? 1 : d->dil;
-    p.H = d->H + 2 * pad - dil * (kh - 1);
-    p.W = d->W + 2 * pad - dil * (kw - 1);
+    const int stride = d->deconv2x2 ? 1 : d->stride;
+    p.H = (d->H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
+    p.W = (d->W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
     TDRN_REQUIRE(p.H > 0 && p.W > 0, "convolution input is too small (output would be %dx%d)", p.H, p.W);
     p.B = d->B; p.Cin = d->Cin; p.Cout = d->Cout; p.n_total = d->deconv2x2 ? 4 * d->Cout : d->Cout;
-    p.kw = kw; p.taps = kh * kw; p.pad = pad; p.dil = dil;
+    p.kw = kw; p.taps = kh * kw; p.pad = pad; p.dil = dil; p.stride = stride;
     p.bias = bias; p.res = residual; p.out = out;
-    p.out_sb = d->out_sb; p.out_sp = d->out_sp; p.out_w = d->deconv2x2 ? 2 * p.W : p.W;
-    p.relu = d->relu; p.deconv = d->deconv2x2; p.out_f32 = d->out_dtype == TDRN_F32;
+    p.out_sb = d->out_sb; p.out_sp = d->out_sp;
+    p.relu = d->relu; p.deconv = d->deconv2x2; p.out_f32 = d->out_dtype == TDRN_F32; p.pool = d->pool2x2;
     TDRN_REQUIRE(!d->deconv2x2 || d->Cout % 16 == 0, "tdrn_conv2d_tc: deconv needs Cout %% 16 == 0");
-    pick_box(p.B, p.H, p.W, p.bw, p.bh, p.bn);
+    if (p.pool) {
+        if (d->deconv2x2 || residual || p.W % 16 != 0 || p.H % 8 != 0) {
+            set_error("tdrn_conv2d_tc: fused 2x2 max-pool needs W %% 16 == 0, H %% 8 == 0, no residual/deconv (got %dx%d)", p.H, p.W);
+            return TDRN_EUNSUPPORTED;
+        }
+        p.bw = 16; p.bh = 8; p.bn = 1;
+        p.out_w = p.W / 2;
+    } else {
+        // element-strided boxes are limited to 256 traversed elements per dimension
+        pick_box(p.B, p.H, p.W, 256 / stride, 256 / stride, p.bw, p.bh, p.bn);
+        p.out_w = d->deconv2x2 ? 2 * p.W : p.W;
+    }
     p.tiles_w = (p.W + p.bw - 1) / p.bw; p.tiles_h = (p.H + p.bh - 1) / p.bh;
     const int tiles_n = (p.B + p.bn - 1) / p.bn;
     p.a_bytes = (uint32_t)(p.bw * p.bh * p.bn) * 128u;
-    const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+    p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
 
     const int n_pad16 = (p.n_total + 15) & ~15;
     const int BN = n_pad16 > 128 ? 256 : (n_pad16 > 64 ? 128 : 64);
-    const int n_tiles = (n_pad16 + BN - 1) / BN;
+    p.n_tiles = (n_pad16 + BN - 1) / BN;
 
     CUtensorMap tmA, tmB;
     {
         const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
         const uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
-        const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-        int rc = make_tmap_bf16(&tmA, in, 4, dims, str, box);
+        // with element stride s TMA loads ceil(box / s) elements: box = n * s loads exactly n
+        const uint32_t box[4] = {64, (uint32_t)(p.bw * stride), (uint32_t)(p.bh * stride), (uint32_t)p.bn};
+        const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+        int rc = make_tmap_bf16(&tmA, in, 4, dims, str, box, es);
         if (rc) return rc;
     }
     {
@@ -299,11 +364,11 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         const uint32_t b_rows = (uint32_t)(n_pad16 < BN ? n_pad16 : BN);
         const uint32_t box[2] = {64, b_rows};
         p.b_bytes = b_rows * 128u;
-        int rc = make_tmap_bf16(&tmB, weight, 2, dims, str, box);
+        int rc = make_tmap_bf16(&tmB, weight, 2, dims, str, box, nullptr);
         if (rc) return rc;
     }
     cudaStream_t st = as_stream(stream);
-    if (BN == 256) return launch_tc<256>(tmA, tmB, p, m_tiles, n_tiles, st);
-    if (BN == 128) return launch_tc<128>(tmA, tmB, p, m_tiles, n_tiles, st);
-    return launch_tc<64>(tmA, tmB, p, m_tiles, n_tiles, st);
+    if (BN == 256) return launch_tc<256>(tmA, tmB, p, st);
+    if (BN == 128) return launch_tc<128>(tmA, tmB, p, st);
+    return launch_tc<64>(tmA, tmB, p, st);
 }

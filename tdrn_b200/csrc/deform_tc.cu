@@ -299,7 +299,7 @@ extern "C" int tdrn_deform_head(const tdrn_deform_head_desc *d, const void *feat
         const uint64_t dims[2] = {K, (uint64_t)p.n_pad16};
         const uint64_t str[1] = {K * 2};
         const uint32_t box[2] = {64, (uint32_t)b_rows};
-        int rc = make_tmap_bf16(h ? &t1 : &t0, h ? weight2 : weight, 2, dims, str, box);
+        int rc = make_tmap_bf16(h ? &t1 : &t0, h ? weight2 : weight, 2, dims, str, box, nullptr);
         if (rc) return rc;
     }
     cudaStream_t st = as_stream(stream);

@@ -203,6 +203,9 @@ static int launch_conv(const ConvP &p, int in_dtype, int out_dtype, cudaStream_t
 
 static int conv_out_dim(int in, int k, int stride, int pad, int dil) { return (in + 2 * pad - (dil * (k - 1) + 1)) / stride + 1; }
 
+int launch_conv_first(const float *x, const float *w, const float *bias, void *out, int B, int H, int W, int Cout,
+                      int Ho, int Wo, int stride, int relu, int out_dtype, cudaStream_t st);   // conv_first.cu
+
 // ------------------------------------------------------------------------------------------------
 // depthwise 3x3, pad 1 (conv_dw first half, model/networks.py:738-740), NHWC, weight [9][C]
 // ------------------------------------------------------------------------------------------------
@@ -352,6 +355,7 @@ extern "C" int tdrn_conv2d(const tdrn_conv_desc *d, const void *in, const float 
     TDRN_REQUIRE((d->dg > 0) == (offsets != nullptr), "tdrn_conv2d: offsets must be given iff dg > 0");
     TDRN_REQUIRE(d->dg == 0 || d->Cin % d->dg == 0, "tdrn_conv2d: Cin %% dg != 0");
     TDRN_REQUIRE(!(d->deconv2x2 && d->dg), "tdrn_conv2d: deconv and deform are exclusive");
+    if (d->pool2x2) { set_error("tdrn_conv2d: fused max-pool is only implemented by tdrn_conv2d_tc"); return TDRN_EUNSUPPORTED; }
     ConvP p{};
     p.in = in; p.w = weight; p.bias = bias; p.res = residual; p.off = offsets; p.out = out;
     p.B = d->B; p.Cin = d->Cin; p.H = d->H; p.W = d->W; p.Cout = d->Cout;
@@ -386,6 +390,9 @@ extern "C" int tdrn_conv_first(const float *x, const float *weight, const float 
 {
     TDRN_REQUIRE(x && weight && out && B > 0 && H > 0 && W > 0 && Cout > 0, "tdrn_conv_first: bad argument");
     TDRN_REQUIRE(stride == 1 || stride == 2, "tdrn_conv_first: stride must be 1 or 2");
+    if (Cout % 16 == 0 && Cout <= 64)            // register-tiled direct kernel (conv_first.cu)
+        return launch_conv_first(x, weight, bias, out, B, H, W, Cout, conv_out_dim(H, 3, stride, 1, 1),
+                                 conv_out_dim(W, 3, stride, 1, 1), stride, relu, out_dtype, as_stream(stream));
     ConvP p{};
     p.in = x; p.w = weight; p.bias = bias; p.out = out;
     p.B = B; p.Cin = 3; p.H = H; p.W = W; p.Cout = Cout; p.kh = p.kw = 3; p.stride = stride; p.pad = 1; p.dil = 1;

@@ -145,7 +145,7 @@ EncodeTiledFn get_encode_tiled();   // conv_tc.cu
 // bf16 tensor, innermost dim contiguous, 128B swizzle, zero OOB fill. dims/strides innermost first;
 // strides_bytes has rank-1 entries (dims 1..rank-1).
 int make_tmap_bf16(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                   const uint32_t *box);
+                   const uint32_t *box, const uint32_t *elem_strides /* NULL = all 1 */);
 
 }  // namespace tc
 }  // namespace tdrn

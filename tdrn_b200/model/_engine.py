@@ -79,7 +79,14 @@ class Engine(object):
     def conv(self, name, x, stride=1, pad=0, dil=1, bn=None, relu=False, deconv=False, **kw):
         pc = self.packed(name, stride, pad, dil, bn, deconv)
         use_tc = (self.use_tc and pc.w_bf16 is not None and x.dtype == torch.bfloat16
-                  and not kw.get('dg') and kw.get('in_shape') is None and (stride == 1 or deconv))
+                  and not kw.get('dg') and kw.get('in_shape') is None and (stride in (1, 2) or deconv))
+        ceil_mode = kw.pop('ceil_mode', False)
+        if kw.pop('pool', False):
+            # MaxPool2d(2,2) after the conv: fused into the tcgen05 epilogue when the map tiles as 16x8 boxes
+            H, W = x.shape[1], x.shape[2]
+            if use_tc and stride == 1 and 2 * pad == dil * (pc.kh - 1) and W % 16 == 0 and H % 8 == 0:
+                return ops.conv2d(x, pc, relu=relu, use_tc=True, pool=True, **kw)
+            return ops.maxpool2x2(ops.conv2d(x, pc, relu=relu, use_tc=use_tc, **kw), ceil_mode)
         return ops.conv2d(x, pc, relu=relu, use_tc=use_tc, **kw)
 
     def conv_first(self, name, x_nchw, stride, bn):
@@ -93,21 +100,34 @@ class Engine(object):
         idx, x = 0, None
         step = 3 if bn else 2
 
-        def conv_block(i, x, pad=1, dil=1):
+        def conv_block(i, x, pad=1, dil=1, pool=None):
             bnn = 'backbone.%d' % (i + 1) if bn else None
             if x is None:
                 return self.conv_first('backbone.%d' % i, x_nchw, 1, bnn)
+            if pool is not None:
+                return self.conv('backbone.%d' % i, x, 1, pad, dil, bn=bnn, relu=True, pool=True, ceil_mode=pool)
             return self.conv('backbone.%d' % i, x, 1, pad, dil, bn=bnn, relu=True)
 
-        for v in VGG_CFG:
+        n_cfg = len(VGG_CFG)
+        ci = 0
+        while ci < n_cfg:
+            v = VGG_CFG[ci]
             if idx == split43:
                 sources.append(ops.l2norm(x, self.vec('L2Norm_4_3.weight')))
             if v == 'M' or v == 'C':
                 x = ops.maxpool2x2(x, ceil_mode=(v == 'C'))
                 idx += 1
             else:
-                x = conv_block(idx, x)
-                idx += step
+                nxt = VGG_CFG[ci + 1] if ci + 1 < n_cfg else None
+                # conv followed by a pool whose input nobody else needs (not conv4_3 -> L2Norm): fuse the pool
+                if x is not None and nxt in ('M', 'C') and idx + step != split43 and (nxt == 'M' or x.shape[1] % 2 == 0):
+                    x = conv_block(idx, x, pool=(nxt == 'C'))
+                    idx += step + 1
+                    ci += 1
+                else:
+                    x = conv_block(idx, x)
+                    idx += step
+            ci += 1
         assert idx == split53
         sources.append(ops.l2norm(x, self.vec('L2Norm_5_3.weight')))
         x = ops.maxpool2x2(x, False)                      # pool5 (pool5_ds=True)

@@ -3,6 +3,7 @@
 ``build_net(phase, size, num_classes, def_groups, multihead)`` (:210-214); state-dict keys :19-121;
 forward outputs (:183-189): (arm_loc, None, odm_loc, softmax(conf)).
 """
+import torch
 import torch.nn as nn
 
 from ..layers.modules.l2norm import L2Norm
@@ -41,7 +42,8 @@ class RefineSSD(DetectorBase):
         x = ops.dwconv3x3(x, E.packed_dw(name + '.0', name + '.1', stride), relu=True)
         return E.conv(name + '.3', x, bn=name + '.4', relu=True)
 
-    def forward(self, x):
+    def forward(self, x, _offsets=None):
+        """``_offsets``: test hook, see dualrefinedet_vggbn.RefineSSD.forward."""
         E = self.engine()
         x = self._check_input(x)
         x = E.conv_first('backbone.0.0', x, 2, 'backbone.0.1')
@@ -57,6 +59,9 @@ class RefineSSD(DetectorBase):
             arm_sources.append(x)
         P, lv = prior_layout(arm_sources)
         arm_loc, offs, offs2 = E.arm_heads(arm_sources, P, lv, self.multihead)
+        if _offsets is not None:
+            offs = [ops.nchw_f32_to_nhwc(o.float(), torch.float32) for o in _offsets[0]]
+            offs2 = [ops.nchw_f32_to_nhwc(o.float(), torch.float32) for o in (_offsets[1] or [])]
         odm_sources = E.fpn(arm_sources)
         odm_loc, conf = E.deform_heads(odm_sources, offs, offs2, P, lv, self.num_classes, self.def_groups,
                                        self.multihead)

@@ -110,7 +110,7 @@ class PackedConv(object):
 
 
 def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_sb=None, out_sp=None,
-           offsets=None, dg=0, use_tc=False, in_shape=None, in_sb=0):
+           offsets=None, dg=0, use_tc=False, in_shape=None, in_sb=0, pool=False):
     """out = act(conv(x) + bias (+ residual)).  ``out`` may be a view into a larger flat buffer, in which
     case out_sb/out_sp give the per-image and per-pixel strides (elements)."""
     if in_shape is not None:          # x is a strided view (e.g. one level of the flat [B,P,4] ARM output)
@@ -124,14 +124,15 @@ def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_
         Ho, Wo = 2 * H, 2 * W
     else:
         Ho, Wo = conv_out(H, pc.kh, pc.stride, pc.pad, pc.dil), conv_out(W, pc.kw, pc.stride, pc.pad, pc.dil)
+    Hs, Ws = (Ho // 2, Wo // 2) if pool else (Ho, Wo)        # stored map (after the fused 2x2 max-pool)
     if out is None:
         odt = out_dtype if out_dtype is not None else x.dtype
-        out = torch.empty(B, Ho, Wo, pc.cout, dtype=odt, device=x.device)
+        out = torch.empty(B, Hs, Ws, pc.cout, dtype=odt, device=x.device)
     if out_sb is None:
-        out_sb, out_sp = Ho * Wo * pc.cout, pc.cout
+        out_sb, out_sp = Hs * Ws * pc.cout, pc.cout
     d = ConvDesc(B=B, H=H, W=W, Cin=Cin, Cout=pc.cout, kh=pc.kh, kw=pc.kw, stride=pc.stride, pad=pc.pad,
                  dil=pc.dil, relu=int(relu), deconv2x2=int(pc.deconv), dg=dg, in_dtype=_dt(x),
-                 out_dtype=_dt(out), out_sb=out_sb, out_sp=out_sp, in_sb=in_sb)
+                 out_dtype=_dt(out), out_sb=out_sb, out_sp=out_sp, in_sb=in_sb, pool2x2=int(pool))
     L = _lib.lib()
     flops = 2.0 * B * (H * W * 4 if pc.deconv else Ho * Wo * pc.kh * pc.kw) * Cin * pc.cout
     if use_tc:

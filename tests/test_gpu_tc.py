@@ -32,6 +32,9 @@ def _bf(x):
     (7, 512, 256, 3, 1, 1, 5, 5, False),       # last_layer_trans: 5x5 maps, several images per tile
     (2, 64, 64, 3, 1, 1, 17, 23, False),       # ragged sizes
     (1, 192, 96, 5, 2, 1, 9, 9, False),        # 5x5 kernel, Cout not a multiple of 64
+    (4, 64, 64, 3, 1, 1, 96, 96, True),        # 288 tiles > #SMs: persistent loop, both TMEM buffers, ring wrap
+    (8, 128, 512, 3, 1, 1, 40, 40, True),      # 224 (m,n) tiles, BN=256
+    (5, 64, 128, 3, 1, 1, 48, 48, False),      # BN=128, 6-stage ring
 ])
 def test_conv_tc_vs_fp32(b, cin, cout, k, pad, dil, h, w, relu):
     from tdrn_b200 import ops
@@ -49,6 +52,35 @@ def test_conv_tc_vs_fp32(b, cin, cout, k, pad, dil, h, w, relu):
     out16 = ops.conv2d(_nhwc(x).cuda().to(torch.bfloat16), pc, relu=relu, use_tc=True)
     assert out16.dtype == torch.bfloat16
     assert rel_err(_nchw(out16.float()).cpu().numpy(), ref.numpy()) < 6e-3     # bf16 output rounding
+
+
+@pytest.mark.parametrize('b,cin,cout,h,w', [(2, 64, 64, 32, 32), (3, 64, 128, 48, 80), (1, 256, 256, 80, 80), (2, 128, 128, 160, 160)])
+def test_conv_tc_fused_maxpool(b, cin, cout, h, w):
+    """conv + BN-folded bias + ReLU + MaxPool2d(2,2) in one kernel (vgg() 'M'/'C' after conv1_2/2_2/3_3)."""
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(cin + h)
+    x = _bf(torch.randn(b, cin, h, w, generator=g))
+    wt = _bf(torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5)
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.max_pool2d(F.relu(F.conv2d(x, wt, bias, 1, 1)), 2, 2)
+    pc = ops.PackedConv(wt, bias, None, 1, 1, 1, device='cuda')
+    out = ops.conv2d(_nhwc(x).cuda().to(torch.bfloat16), pc, relu=True, out_dtype=torch.float32, use_tc=True, pool=True)
+    assert tuple(out.shape) == (b, h // 2, w // 2, cout)
+    assert rel_err(_nchw(out).cpu().numpy(), ref.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize('b,cin,cout,h,w', [(3, 256, 512, 10, 10), (2, 64, 96, 17, 23), (1, 128, 64, 40, 40)])
+def test_conv_tc_stride2(b, cin, cout, h, w):
+    """3x3 stride-2 pad-1 conv (extras.3) through TMA element strides."""
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(cin + h + 1)
+    x = _bf(torch.randn(b, cin, h, w, generator=g))
+    wt = _bf(torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5)
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.relu(F.conv2d(x, wt, bias, 2, 1))
+    pc = ops.PackedConv(wt, bias, None, 2, 1, 1, device='cuda')
+    out = ops.conv2d(_nhwc(x).cuda().to(torch.bfloat16), pc, relu=True, out_dtype=torch.float32, use_tc=True)
+    assert rel_err(_nchw(out).cpu().numpy(), ref.numpy()) < 2e-5
 
 
 def test_conv_tc_head_into_flat_buffer_and_deconv():
