@@ -254,6 +254,9 @@ def run_gpu(args, rank, world, local_rank):
     # ---- roofline leg: per-call CUDA events on the launching stream, eager (same kernels as the graph) ----
     roof = None
     if rank == 0:
+        # per-kernel timing needs the kernels serialised on one stream: switch the engine's fork/join branches
+        # off for this leg only (the timed legs above run the multi-stream graph)
+        net.engine().multi_stream = False
         with torch.cuda.stream(stream), torch.no_grad():
             hot_path(dev_x[1])
             stream.synchronize()
@@ -261,6 +264,7 @@ def run_gpu(args, rank, world, local_rank):
             for i in range(max(2, min(args.steps, 5))):
                 hot_path(dev_x[i % n_in])
             rec = ops.prof_end()
+        net.engine().multi_stream = True
         agg, detail = {}, {}
         for label, work, ms in rec:
             a = agg.setdefault(label.split('|')[0], [0.0, 0.0, 0])

@@ -33,6 +33,7 @@ struct DeformP {
     int P, prior_off, softmax;
     float *loc_out, *conf_out;
     uint32_t b_bytes;
+    int geo_per_row;                 // (taps0 + taps1) * dg geometry entries per tile row
 };
 
 template <int NMAX> struct DfCfg {
@@ -41,14 +42,26 @@ template <int NMAX> struct DfCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = 3;
     static constexpr int TMEM_COLS = NMAX;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+    static constexpr int SMEM_STAGES_BYTES = STAGES * STAGE_BYTES + 1024;   // + geometry cache (run-time size)
 };
+
+// Bilinear blend of two packed bf16 channels from the 4 corners, fp32 arithmetic, one bf16x2 result.
+__device__ __forceinline__ uint32_t blend2(uint32_t a, uint32_t b, uint32_t c, uint32_t d, float w1, float w2, float w3, float w4)
+{
+    float lo = w1 * __uint_as_float(a << 16), hi = w1 * __uint_as_float(a & 0xffff0000u);
+    lo = fmaf(w2, __uint_as_float(b << 16), lo); hi = fmaf(w2, __uint_as_float(b & 0xffff0000u), hi);
+    lo = fmaf(w3, __uint_as_float(c << 16), lo); hi = fmaf(w3, __uint_as_float(c & 0xffff0000u), hi);
+    lo = fmaf(w4, __uint_as_float(d << 16), lo); hi = fmaf(w4, __uint_as_float(d & 0xffff0000u), hi);
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 
 constexpr int DF_PRODUCER_WARPS = 8;
 constexpr int DF_THREADS = (DF_PRODUCER_WARPS + 2) * 32;
 
 template <int NMAX>
-__global__ void __launch_bounds__(DF_THREADS) deform_head_kernel(const __grid_constant__ CUtensorMap tmB0,
+__global__ void __launch_bounds__(DF_THREADS, 1) deform_head_kernel(const __grid_constant__ CUtensorMap tmB0,
                                                                  const __grid_constant__ CUtensorMap tmB1, const DeformP p)
 {
     using Cfg = DfCfg<NMAX>;
@@ -75,6 +88,41 @@ __global__ void __launch_bounds__(DF_THREADS) deform_head_kernel(const __grid_co
         fence_barrier_init();
     }
     if (warp == DF_PRODUCER_WARPS + 1) tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
+
+    // ---- per-tile sampling geometry cache: one 12-byte entry per (row, head, tap, deformable group) ----------
+    //   word0 = pixel index of the (low,low) corner | dx << 28 | dy << 29 | inside << 30 ; word1 = lh ; word2 = lw
+    unsigned *geo = (unsigned *)(tiles + Cfg::STAGES * Cfg::STAGE_BYTES);
+    for (int e = threadIdx.x; e < 128 * p.geo_per_row; e += DF_THREADS) {
+        const int r = e / p.geo_per_row, gi = e - r * p.geo_per_row;
+        const int head = gi >= p.taps[0] * p.dg ? 1 : 0;
+        const int gl = head ? gi - p.taps[0] * p.dg : gi;
+        const int tap = gl / p.dg, g = gl - tap * p.dg;
+        const int m = m0 + r;
+        const bool rvalid = m < p.M;
+        const int mm = rvalid ? m : 0;
+        const int rb = mm / HW, rem = mm - rb * HW;
+        const int ry = rem / p.W, rx = rem - ry * p.W;
+        const int kk = p.k[head];
+        const int ti = tap / kk, tj = tap - ti * kk;
+        const int oc = p.dg * 2 * p.taps[head];
+        const float *op = p.off[head] + ((long long)rb * HW + rem) * oc + (g * 2 * p.taps[head] + 2 * tap);
+        const float oh = rvalid ? __ldg(op) : 0.f, ow = rvalid ? __ldg(op + 1) : 0.f;
+        const int y0 = ry - p.pad[head], x0 = rx - p.pad[head];                          // stride 1
+        const float h_im = (float)(y0 + ti) + oh, w_im = (float)(x0 + tj) + ow;          // .cu:195-196 (dilation 1)
+        const bool inside = rvalid && h_im >= 0.f && w_im >= 0.f && h_im < (float)p.H && w_im < (float)p.W;   // .cu:197
+        float h = (float)ti + oh, w = (float)tj + ow;                                     // map_h / map_w .cu:198-199
+        const int cur_h = p.H - y0, cur_w = p.W - x0;
+        int h_low = (int)floorf(h), w_low = (int)floorf(w), h_high, w_high;               // .cu:21-37
+        if (h_low >= cur_h - 1) { h_high = h_low = cur_h - 1; h = (float)h_low; } else { h_high = h_low + 1; }
+        if (w_low >= cur_w - 1) { w_high = w_low = cur_w - 1; w = (float)w_low; } else { w_high = w_low + 1; }
+        const float lh = h - (float)h_low, lw = w - (float)w_low;
+        const int ya = min(max(y0 + h_low, 0), p.H - 1), yb = min(max(y0 + h_high, 0), p.H - 1);
+        const int xa = min(max(x0 + w_low, 0), p.W - 1), xb = min(max(x0 + w_high, 0), p.W - 1);
+        const unsigned base = (unsigned)(rb * HW + ya * p.W + xa);
+        geo[(size_t)e * 3 + 0] = inside ? (base | ((unsigned)(xb - xa) << 28) | ((unsigned)(yb - ya) << 29) | (1u << 30)) : 0u;
+        geo[(size_t)e * 3 + 1] = __float_as_uint(lh);
+        geo[(size_t)e * 3 + 2] = __float_as_uint(lw);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -82,86 +130,59 @@ __global__ void __launch_bounds__(DF_THREADS) deform_head_kernel(const __grid_co
 
     if (warp < DF_PRODUCER_WARPS) {
         // ===================== A producers: bilinear-sampled im2col straight into smem =====================
+        // k-blocks run channel-block-major (cb, tap): all taps of one 64-channel slab are sampled back to
+        // back, so the slab's footprint (tile rows +- kernel radius +- offsets, ~50 KB) stays L1-resident.
         const int sub = lane >> 3, chunk = lane & 7;       // 4 rows per pass, 8 x 16B chunks per row
-        int rb[4], ry[4], rx[4];
-        bool rvalid[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = warp * 16 + i * 4 + sub;
-            const int m = m0 + r;
-            rvalid[i] = m < p.M;
-            const int mm = rvalid[i] ? m : 0;
-            rb[i] = mm / HW;
-            const int rem = mm - rb[i] * HW;
-            ry[i] = rem / p.W; rx[i] = rem - ry[i] * p.W;
-        }
-        int poff[4][4];          // pixel offsets (elements / Cin) of the 4 corners, per row slot
-        float pw[4][4];          // bilinear weights (0 when the sample is outside the map)
         const int blocks_per_group = p.cpg >> 6;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int head = kb >= kb_head0 ? 1 : 0;
-            const int kl = head ? kb - kb_head0 : kb;
-            const int tap = kl / cblocks, cb = kl - tap * cblocks;
-            if (cb % blocks_per_group == 0) {
-                // new (tap, deformable group): recompute sampling geometry for my 4 rows
-                const int g = (cb << 6) / p.cpg;
-                const int kk = p.k[head];
-                const int ti = tap / kk, tj = tap - ti * kk;
-                const int oc = p.dg * 2 * p.taps[head];
+        int kb = 0;
+        for (int head = 0; head < 2; ++head) {
+            const int taps = p.taps[head];
+            const int gbase = head ? p.taps[0] * p.dg : 0;
+            for (int cb = 0; cb < (taps ? cblocks : 0); ++cb) {
+                const int g = cb / blocks_per_group;
+                const __nv_bfloat16 *fb = p.feat + (cb << 6) + (chunk << 3);
+                for (int tap = 0; tap < taps; ++tap, ++kb) {
+                    const int gi = gbase + tap * p.dg + g;
+                    // geometry of my 4 (row, chunk) slots from the per-tile cache; 16 independent 16-byte loads in flight
+                    uint4 cv[4][4];
+                    float lh[4], lw[4];
+                    unsigned fl[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float *op = p.off[head] + ((long long)rb[i] * HW + ry[i] * p.W + rx[i]) * oc + (g * 2 * p.taps[head] + 2 * tap);
-                    const float oh = rvalid[i] ? __ldg(op) : 0.f, ow = rvalid[i] ? __ldg(op + 1) : 0.f;
-                    const int y0 = ry[i] - p.pad[head], x0 = rx[i] - p.pad[head];          // stride 1
-                    const float h_im = (float)(y0 + ti) + oh, w_im = (float)(x0 + tj) + ow; // .cu:195-196 (dilation 1)
-                    const bool inside = rvalid[i] && h_im >= 0.f && w_im >= 0.f && h_im < (float)p.H && w_im < (float)p.W;   // .cu:197
-                    float h = (float)ti + oh, w = (float)tj + ow;                            // map_h/map_w .cu:198-199
-                    const int cur_h = p.H - y0, cur_w = p.W - x0;
-                    int h_low = (int)floorf(h), w_low = (int)floorf(w), h_high, w_high;      // .cu:21-37
-                    if (h_low >= cur_h - 1) { h_high = h_low = cur_h - 1; h = (float)h_low; } else { h_high = h_low + 1; }
-                    if (w_low >= cur_w - 1) { w_high = w_low = cur_w - 1; w = (float)w_low; } else { w_high = w_low + 1; }
-                    const float lh = h - (float)h_low, lw = w - (float)w_low, hh = 1.f - lh, hw = 1.f - lw;
-                    const int ya = min(max(y0 + h_low, 0), p.H - 1), yb = min(max(y0 + h_high, 0), p.H - 1);
-                    const int xa = min(max(x0 + w_low, 0), p.W - 1), xb = min(max(x0 + w_high, 0), p.W - 1);
-                    const int base = rb[i] * HW;
-                    poff[i][0] = base + ya * p.W + xa; poff[i][1] = base + ya * p.W + xb;
-                    poff[i][2] = base + yb * p.W + xa; poff[i][3] = base + yb * p.W + xb;
-                    pw[i][0] = inside ? hh * hw : 0.f; pw[i][1] = inside ? hh * lw : 0.f;
-                    pw[i][2] = inside ? lh * hw : 0.f; pw[i][3] = inside ? lh * lw : 0.f;
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = warp * 16 + i * 4 + sub;
+                        const unsigned *ge = geo + ((size_t)r * p.geo_per_row + gi) * 3;
+                        const unsigned w0 = ge[0];
+                        lh[i] = __uint_as_float(ge[1]); lw[i] = __uint_as_float(ge[2]); fl[i] = w0;
+                        const int base = (int)(w0 & 0x0fffffffu);
+                        const int dx = (w0 >> 28) & 1u, dy = ((w0 >> 29) & 1u) ? p.W : 0;
+                        const __nv_bfloat16 *pa = fb + (long long)base * p.Cin;
+                        cv[i][0] = __ldg((const uint4 *)pa);
+                        cv[i][1] = __ldg((const uint4 *)(pa + (long long)dx * p.Cin));
+                        cv[i][2] = __ldg((const uint4 *)(pa + (long long)dy * p.Cin));
+                        cv[i][3] = __ldg((const uint4 *)(pa + (long long)(dy + dx) * p.Cin));
+                    }
+                    const int s = kb % Cfg::STAGES;
+                    const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    uint8_t *sa = tiles + s * Cfg::STAGE_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = warp * 16 + i * 4 + sub;
+                        const float in = ((fl[i] >> 30) & 1u) ? 1.f : 0.f;       // 0: sample outside the map (.cu:197)
+                        const float hh = 1.f - lh[i], hw = 1.f - lw[i];
+                        const float w1 = in * hh * hw, w2 = in * hh * lw[i], w3 = in * lh[i] * hw, w4 = in * lh[i] * lw[i];
+                        uint4 o;                                                 // .cu:49, two channels per 32-bit lane
+                        o.x = blend2(cv[i][0].x, cv[i][1].x, cv[i][2].x, cv[i][3].x, w1, w2, w3, w4);
+                        o.y = blend2(cv[i][0].y, cv[i][1].y, cv[i][2].y, cv[i][3].y, w1, w2, w3, w4);
+                        o.z = blend2(cv[i][0].z, cv[i][1].z, cv[i][2].z, cv[i][3].z, w1, w2, w3, w4);
+                        o.w = blend2(cv[i][0].w, cv[i][1].w, cv[i][2].w, cv[i][3].w, w1, w2, w3, w4);
+                        *(uint4 *)(sa + sw128_offset(r, chunk)) = o;
+                    }
+                    fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[s]);
                 }
             }
-            // gather the 4 corners of my 4 (row, chunk) slots: 16 independent 16-byte loads in flight
-            uint4 cv[4][4];
-            const __nv_bfloat16 *fb = p.feat + (cb << 6) + (chunk << 3);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) cv[i][q] = __ldg((const uint4 *)(fb + (long long)poff[i][q] * p.Cin));
-
-            const int s = kb % Cfg::STAGES;
-            const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
-            mbar_wait(&empty_bar[s], ph ^ 1u);
-            uint8_t *sa = tiles + s * Cfg::STAGE_BYTES;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = warp * 16 + i * 4 + sub;
-                uint4 o;
-                __nv_bfloat162 *ob = (__nv_bfloat162 *)&o;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float2 a = __bfloat1622float2(((const __nv_bfloat162 *)&cv[i][0])[e]);
-                    float2 b = __bfloat1622float2(((const __nv_bfloat162 *)&cv[i][1])[e]);
-                    float2 c = __bfloat1622float2(((const __nv_bfloat162 *)&cv[i][2])[e]);
-                    float2 d = __bfloat1622float2(((const __nv_bfloat162 *)&cv[i][3])[e]);
-                    const float vx = pw[i][0] * a.x + pw[i][1] * b.x + pw[i][2] * c.x + pw[i][3] * d.x;   // .cu:49
-                    const float vy = pw[i][0] * a.y + pw[i][1] * b.y + pw[i][2] * c.y + pw[i][3] * d.y;
-                    ob[e] = __floats2bfloat162_rn(vx, vy);
-                }
-                *(uint4 *)(sa + sw128_offset(r, chunk)) = o;
-            }
-            fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[s]);
         }
     } else if (warp == DF_PRODUCER_WARPS) {
         // ===================== weight (B operand) TMA producer =====================
@@ -252,8 +273,13 @@ template <int NMAX>
 static int launch_deform(const CUtensorMap &t0, const CUtensorMap &t1, const DeformP &p, cudaStream_t st)
 {
     using Cfg = DfCfg<NMAX>;
-    TDRN_CUDA(cudaFuncSetAttribute(deform_head_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    deform_head_kernel<NMAX><<<(p.M + 127) / 128, DF_THREADS, Cfg::SMEM_BYTES, st>>>(t0, t1, p);
+    const size_t smem = (size_t)Cfg::SMEM_STAGES_BYTES + (size_t)128 * p.geo_per_row * 12;
+    if (smem > 227 * 1024) {
+        set_error("tdrn_deform_head: geometry cache does not fit (%zu bytes of shared memory needed)", smem);
+        return TDRN_EUNSUPPORTED;
+    }
+    TDRN_CUDA(cudaFuncSetAttribute(deform_head_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    deform_head_kernel<NMAX><<<(p.M + 127) / 128, DF_THREADS, smem, st>>>(t0, t1, p);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }
@@ -288,6 +314,7 @@ extern "C" int tdrn_deform_head(const tdrn_deform_head_desc *d, const void *feat
     p.k[1] = d->kh2 ? d->kh2 : 1; p.pad[1] = d->pad2; p.taps[1] = d->kh2 * d->kh2;
     p.M = d->B * d->H * d->W; p.C = d->num_classes; p.P = d->P; p.prior_off = d->prior_off; p.softmax = d->softmax;
     p.loc_out = loc_out; p.conf_out = conf_out;
+    p.geo_per_row = (p.taps[0] + p.taps[1]) * d->dg;
     const int nmax = p.n_pad16 > 128 ? 256 : 128;
     const int b_rows = p.n_pad16;
     p.b_bytes = (uint32_t)b_rows * 128u;

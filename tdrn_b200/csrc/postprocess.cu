@@ -6,22 +6,33 @@
 //   decode_transpose_kernel : boxes[B,P,4] = decode(loc, center_size(decode(arm_loc, priors)))
 //                             (layers/box_utils.py:176-195, :16-25) and scoresT[B,C,P] (class-major
 //                             copy of conf so every (image, class) segment is one coalesced row).
-//   nms_segment_kernel      : one CTA per (image, class): threshold + compaction, bitonic sort on
-//                             (score, ~index) 64-bit keys in shared memory, chunked greedy NMS with
-//                             a 256x256 suppression bitmask per chunk resolved by one warp with
-//                             shuffles, early exit once top_k boxes are kept (exactly equivalent,
-//                             SURVEY.md 8a "Exactness note for A8").
+//   nms_segment_kernel      : one CTA per (image, class) segment.  Greedy NMS only ever consumes the
+//                             highest-scoring candidates until top_k boxes are kept (SURVEY.md 8a
+//                             "Exactness note for A8"), so instead of sorting all P candidates the
+//                             kernel works in descending score BATCHES:
+//       1. radix-select (12/12/8/8.. bit digits, shared-memory histograms) the cut-off such that
+//          the next <= 1024 candidates in (score desc, index asc) order are selected;
+//       2. bitonic-sort that batch on 64-bit (score, ~index) keys in shared memory;
+//       3. greedy NMS in chunks of 32: 8 lanes per candidate scan the kept list, a 32x32
+//          suppression matrix resolves the chunk with warp shuffles;
+//       4. stop when top_k boxes are kept or the candidates are exhausted, else next batch.
+//     The visiting order is exactly the reference's (descending score, pinned tie rule), so the
+//     result is identical to a full sort + full scan.
 //
 // Bit-exactness: every fp32 operation of the reference's IoU (cpu_nms.pyx:24,57-65) and of decode
 // is issued with explicit round-to-nearest intrinsics in the reference's order so that nvcc cannot
-// contract them into FMAs; `ovr >= thresh` is the reference's float-vs-double compare.
+// contract them into FMAs; `ovr >= thresh` is the reference's float-vs-double compare (the division
+// is skipped only when the outcome is certain by a 1e-6 relative margin, 16x the rounding error).
 #include "common.cuh"
 #include <math.h>
 
 namespace tdrn {
 
-constexpr int NMS_THREADS = 256;           // == chunk size of the greedy scan
-constexpr int NMS_WORDS = NMS_THREADS / 32;
+constexpr int NMS_THREADS = 256;
+constexpr int NMS_CAP = 1024;              // candidates sorted per batch
+constexpr int NMS_KSEL = 512;              // every batch holds at least min(KSEL, remaining) candidates
+constexpr int NMS_BINS = 4096;             // histogram bins (12-bit digit)
+constexpr int NMS_CH = 32;                 // candidates per greedy chunk
 
 __device__ __forceinline__ float4 decode_box(float4 l, float4 p)
 {
@@ -82,11 +93,11 @@ struct NmsP {
     const float *dets;        // [n,5]
     int n;
     int *keep; int *num_keep;
-    float *kept_ws;           // [max_keep*5] global scratch for the kept list
+    float *kept_ws;           // [5][kept_cap] global scratch for the kept list (SoA)
     // common
-    int max_keep;
+    int max_keep;             // <= 0: unlimited
+    int kept_cap;             // stride of the kept SoA arrays
     float thr_up;             // smallest float >= (double) nms threshold
-    int n_pad_max;            // keys[] capacity (power of two)
 };
 
 __device__ __forceinline__ bool iou_ge(float4 a, float aarea, float4 b, float barea, float thr)
@@ -97,8 +108,16 @@ __device__ __forceinline__ bool iou_ge(float4 a, float aarea, float4 b, float ba
     const float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
     const float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
     const float inter = __fmul_rn(w, h);
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
-    return ovr >= thr;
+    const float uni = __fsub_rn(__fadd_rn(aarea, barea), inter);
+    if (uni > 0.f) {
+        // ovr = rn(inter / uni) carries <= 2^-24 relative error; decide without the division when the
+        // real quotient is further than 1e-6 (relative) from the threshold.
+        if (inter == 0.f) return 0.f >= thr;
+        const float t = __fmul_rn(thr, uni);
+        if (inter > __fmul_rn(t, 1.000001f)) return true;
+        if (inter < __fmul_rn(t, 0.999999f)) return false;
+    }
+    return __fdiv_rn(inter, uni) >= thr;
 }
 
 __device__ __forceinline__ float box_area(float4 b)
@@ -107,19 +126,30 @@ __device__ __forceinline__ float box_area(float4 b)
     return __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
 }
 
+// order-preserving fp32 -> u32 (handles negative scores in standalone mode)
+__device__ __forceinline__ unsigned score_key(float s)
+{
+    const unsigned u = __float_as_uint(s);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
 // One CTA per segment.  DETECT: grid (C, B); class 0 only zero-fills.  Standalone: grid (1).
 template <bool DETECT>
 __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long *keys = (unsigned long long *)smem_raw;                       // [n_pad_max]
-    float *kept_s = (float *)(keys + p.n_pad_max);                                    // DETECT: [max_keep*5]
-    __shared__ float4 cbox[NMS_THREADS];
-    __shared__ float carea[NMS_THREADS];
-    __shared__ int cidx[NMS_THREADS];
-    __shared__ unsigned char calive[NMS_THREADS];
-    __shared__ unsigned cmask[NMS_THREADS][NMS_WORDS];
-    __shared__ int s_count, s_kept;
+    float *kept_s = (float *)smem_raw;                                      // DETECT: [5][kept_cap]
+    __shared__ unsigned long long keys[NMS_CAP];
+    __shared__ unsigned hist[NMS_BINS];
+    __shared__ unsigned part[NMS_THREADS];
+    __shared__ float4 cbox[NMS_CH];
+    __shared__ float carea[NMS_CH];
+    __shared__ int cidx[NMS_CH];
+    __shared__ unsigned csup[NMS_CH];        // suppressed by an earlier-kept box
+    __shared__ unsigned crow[NMS_CH];        // bit j: candidate j (> i) overlaps candidate i
+    __shared__ unsigned long long s_lo;
+    __shared__ unsigned s_nsel, s_total, s_kept;
+    __shared__ int s_done;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int cl = 0, b = 0;
@@ -139,122 +169,192 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
         n_in = p.n;
     }
     float *kept = DETECT ? kept_s : p.kept_ws;
+    const int kc = p.kept_cap;
+    float *kx1 = kept, *ky1 = kept + kc, *kx2 = kept + 2 * kc, *ky2 = kept + 3 * kc, *kar = kept + 4 * kc;
 
-    // ---- 1. threshold + compaction into 64-bit keys: (score bits << 32) | ~index -------------------
-    if (tid == 0) { s_count = 0; s_kept = 0; }
-    __syncthreads();
-    for (int i0 = 0; i0 < n_in; i0 += NMS_THREADS) {
-        const int i = i0 + tid;
-        bool take = false; float s = 0.f;
-        if (i < n_in) {
-            s = DETECT ? sc[i] : p.dets[5 * (long long)i + 4];
-            take = DETECT ? (s > p.conf_thresh) : true;          // strict fp32 compare, detection.py:53
-        }
-        const unsigned ballot = __ballot_sync(0xffffffffu, take);
-        int base = 0;
-        if (lane == 0 && ballot) base = atomicAdd(&s_count, __popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (take) {
-            // order-preserving map of fp32 to u32 (handles negative scores in standalone mode)
-            unsigned u = __float_as_uint(s);
-            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-            keys[base + __popc(ballot & ((1u << lane) - 1))] = ((unsigned long long)u << 32) | (unsigned)(0xffffffffu - (unsigned)i);
-        }
-    }
-    __syncthreads();
-    const int count = s_count;
-    int n_pad = 32;
-    while (n_pad < count) n_pad <<= 1;
-    for (int i = count + tid; i < n_pad; i += NMS_THREADS) keys[i] = 0ull;
-    __syncthreads();
+    // composite key of element i, or 0 if it is not a candidate / not below the current bound
+    auto key_of = [&](int i, unsigned long long hi_incl) -> unsigned long long {
+        const float s = DETECT ? sc[i] : p.dets[5 * (long long)i + 4];
+        if (DETECT && !(s > p.conf_thresh)) return 0ull;           // strict fp32 compare, detection.py:53
+        const unsigned long long c = ((unsigned long long)score_key(s) << 32) | (unsigned)(0xffffffffu - (unsigned)i);
+        return c <= hi_incl ? c : 0ull;
+    };
 
-    // ---- 2. bitonic sort, descending ----------------------------------------------------------------
-    for (int k = 2; k <= n_pad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (n_pad >> 1); t += NMS_THREADS) {
-                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int hi = lo | j;
-                const unsigned long long a = keys[lo], c = keys[hi];
-                const bool desc = (lo & k) == 0;
-                if (desc ? (a < c) : (a > c)) { keys[lo] = c; keys[hi] = a; }
+    unsigned long long hi_incl = ~0ull;
+    unsigned kept_n = 0, processed = 0, total = 0;
+    const unsigned max_keep = p.max_keep > 0 ? (unsigned)p.max_keep : 0xffffffffu;
+    bool first = true;
+
+    while (true) {
+        // ---- 1. radix select the lower bound `lo` of the next batch: {c : lo <= c <= hi_incl}, size <= CAP ----------
+        unsigned long long prefix_val = 0ull, prefix_mask = 0ull;
+        unsigned need = NMS_KSEL, above_total = 0;
+        const int shifts[7] = {52, 40, 32, 24, 16, 8, 0};
+        const int bits[7] = {12, 12, 8, 8, 8, 8, 8};
+        for (int lv = 0; lv < 7; ++lv) {
+            for (int i = tid; i < NMS_BINS; i += NMS_THREADS) hist[i] = 0;
+            __syncthreads();
+            const int sh = shifts[lv];
+            const unsigned dmask = (1u << bits[lv]) - 1u;
+            for (int i = tid; i < n_in; i += NMS_THREADS) {
+                const unsigned long long c = key_of(i, hi_incl);
+                if (c != 0ull && (c & prefix_mask) == prefix_val) atomicAdd(&hist[(unsigned)(c >> sh) & dmask], 1u);
             }
             __syncthreads();
-        }
-    }
-
-    // ---- 3. chunked greedy NMS ----------------------------------------------------------------------
-    int kept_n = 0;
-    const int max_keep = p.max_keep > 0 ? p.max_keep : count;
-    for (int c0 = 0; c0 < count && kept_n < max_keep; c0 += NMS_THREADS) {
-        const int cnt = min(NMS_THREADS, count - c0);
-        float4 bx = make_float4(0, 0, 0, 0); float area = 0.f; bool alive = false; int src = 0;
-        if (tid < cnt) {
-            src = (int)(0xffffffffu - (unsigned)(keys[c0 + tid] & 0xffffffffull));
-            if (DETECT) {
-                const float4 nb = p.boxes[(long long)b * p.P + src];
-                bx = make_float4(__fmul_rn(nb.x, p.scale.x), __fmul_rn(nb.y, p.scale.y),
-                                 __fmul_rn(nb.z, p.scale.z), __fmul_rn(nb.w, p.scale.w));   // detection.py:59
-            } else {
-                const float *d = p.dets + 5 * (long long)src;
-                bx = make_float4(d[0], d[1], d[2], d[3]);
-            }
-            area = box_area(bx);
-            alive = true;
-            for (int q = 0; q < kept_n; ++q) {                      // phase 1: vs boxes kept in earlier chunks
-                const float4 kb = make_float4(kept[q * 5 + 0], kept[q * 5 + 1], kept[q * 5 + 2], kept[q * 5 + 3]);
-                if (iou_ge(kb, kept[q * 5 + 4], bx, area, p.thr_up)) { alive = false; break; }
-            }
-        }
-        cbox[tid] = bx; carea[tid] = area; cidx[tid] = src; calive[tid] = alive ? 1 : 0;
-        __syncthreads();
-        if (alive) {                                                // phase 2a: my suppression row (j > tid)
+            // per-thread partial sums over 16 bins, grouped from the top bin downwards
+            {
+                unsigned s = 0;
+                const int base = NMS_BINS - 1 - tid * (NMS_BINS / NMS_THREADS);
 #pragma unroll
-            for (int w = 0; w < NMS_WORDS; ++w) {
-                unsigned m = 0;
-                if (w >= (tid >> 5)) {
-                    const int jb = w * 32;
-                    for (int jj = 0; jj < 32; ++jj) {
-                        const int j = jb + jj;
-                        if (j > tid && j < cnt && iou_ge(bx, area, cbox[j], carea[j], p.thr_up)) m |= 1u << jj;
+                for (int k = 0; k < NMS_BINS / NMS_THREADS; ++k) s += hist[base - k];
+                part[tid] = s;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned cum = 0, tot = 0;
+                for (int t = 0; t < NMS_THREADS; ++t) tot += part[t];
+                if (lv == 0 && first) s_total = tot;
+                int done = 0;
+                unsigned long long lo = 0ull;
+                if (lv == 0 && tot <= (unsigned)NMS_CAP) {          // everything that is left fits in one batch
+                    done = 1; lo = 1ull; s_nsel = tot;
+                } else {
+                    int t = 0;
+                    while (cum + part[t] < need) { cum += part[t]; ++t; }   // group holding the need-th largest
+                    int d = NMS_BINS - 1 - t * (NMS_BINS / NMS_THREADS);
+                    while (cum + hist[d] < need) { cum += hist[d]; --d; }   // digit holding it
+                    const unsigned inbin = hist[d];
+                    const unsigned long long pv = prefix_val | ((unsigned long long)d << sh);
+                    if (above_total + cum + inbin <= (unsigned)NMS_CAP) {   // take the whole bucket: batch complete
+                        done = 1; lo = pv; s_nsel = above_total + cum + inbin;
+                        if (lo == 0ull) lo = 1ull;
+                    } else {                                         // refine inside bucket d at the next digit
+                        lo = pv;
+                        s_nsel = cum;                                // (re-used to pass `cum` to all threads)
                     }
                 }
-                cmask[tid][w] = m;
+                s_lo = lo; s_done = done;
             }
+            __syncthreads();
+            if (s_done) break;
+            prefix_val = s_lo;
+            prefix_mask |= (unsigned long long)dmask << sh;
+            need -= s_nsel; above_total += s_nsel;
+            __syncthreads();
+        }
+        if (first) { total = s_total; first = false; }
+        const unsigned long long lo = s_lo;
+        const unsigned n_sel = s_nsel;
+        if (n_sel == 0) break;
+        __syncthreads();
+
+        // ---- 2. gather the batch and bitonic-sort it (descending) ------------------------------------------------
+        if (tid == 0) s_nsel = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < n_in; i0 += NMS_THREADS) {
+            const int i = i0 + tid;
+            const unsigned long long c = i < n_in ? key_of(i, hi_incl) : 0ull;
+            const bool take = c >= lo && c != 0ull;
+            const unsigned ballot = __ballot_sync(0xffffffffu, take);
+            unsigned base = 0;
+            if (lane == 0 && ballot) base = atomicAdd(&s_nsel, (unsigned)__popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (take) keys[base + __popc(ballot & ((1u << lane) - 1u))] = c;
         }
         __syncthreads();
-        if (warp == 0) {                                            // phase 2b: serial resolve, one warp
-            unsigned removed = 0;                                   // lane w (< NMS_WORDS) owns word w
-            for (int i = 0; i < cnt; ++i) {
-                const unsigned r = __shfl_sync(0xffffffffu, removed, i >> 5);
-                if (calive[i] && !((r >> (i & 31)) & 1u)) {
-                    if (lane == 0) {
-                        const float4 kb = cbox[i];
-                        kept[kept_n * 5 + 0] = kb.x; kept[kept_n * 5 + 1] = kb.y; kept[kept_n * 5 + 2] = kb.z;
-                        kept[kept_n * 5 + 3] = kb.w; kept[kept_n * 5 + 4] = carea[i];
-                        if (DETECT) {
-                            const float4 nb = p.boxes[(long long)b * p.P + cidx[i]];
-                            float *o = out_seg + kept_n * 5;         // detection.py:61-63
-                            o[0] = sc[cidx[i]]; o[1] = nb.x; o[2] = nb.y; o[3] = nb.z; o[4] = nb.w;
-                        } else {
-                            p.keep[kept_n] = cidx[i];
-                        }
-                    }
-                    ++kept_n;
-                    if (lane < NMS_WORDS) removed |= cmask[i][lane];
-                    if (kept_n >= max_keep) break;
+        int n_pad = 32;
+        while (n_pad < (int)n_sel) n_pad <<= 1;
+        for (int i = n_sel + tid; i < n_pad; i += NMS_THREADS) keys[i] = 0ull;
+        __syncthreads();
+        for (int k = 2; k <= n_pad; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (n_pad >> 1); t += NMS_THREADS) {
+                    const int lo_i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int hi_i = lo_i | j;
+                    const unsigned long long a = keys[lo_i], c = keys[hi_i];
+                    const bool desc = (lo_i & k) == 0;
+                    if (desc ? (a < c) : (a > c)) { keys[lo_i] = c; keys[hi_i] = a; }
                 }
+                __syncthreads();
             }
-            if (lane == 0) s_kept = kept_n;
         }
-        __threadfence_block();
+
+        // ---- 3. greedy NMS over the sorted batch, 32 candidates per chunk -----------------------------------------
+        for (unsigned c0 = 0; c0 < n_sel && kept_n < max_keep; c0 += NMS_CH) {
+            const int cnt = min(NMS_CH, (int)(n_sel - c0));
+            if (tid < cnt) {
+                const int src = (int)(0xffffffffu - (unsigned)(keys[c0 + tid] & 0xffffffffull));
+                float4 bx;
+                if (DETECT) {
+                    const float4 nb = p.boxes[(long long)b * p.P + src];
+                    bx = make_float4(__fmul_rn(nb.x, p.scale.x), __fmul_rn(nb.y, p.scale.y),
+                                     __fmul_rn(nb.z, p.scale.z), __fmul_rn(nb.w, p.scale.w));   // detection.py:59
+                } else {
+                    const float *d = p.dets + 5 * (long long)src;
+                    bx = make_float4(d[0], d[1], d[2], d[3]);
+                }
+                cbox[tid] = bx; carea[tid] = box_area(bx); cidx[tid] = src;
+            }
+            __syncthreads();
+            {
+                // thread (ci, l): candidate ci = tid / 8, sub-lane l = tid % 8
+                const int ci = tid >> 3, l = tid & 7;
+                bool sup = false;
+                unsigned row = 0;
+                if (ci < cnt) {
+                    const float4 bx = cbox[ci];
+                    const float ar = carea[ci];
+                    for (unsigned q = l; q < kept_n && !sup; q += 8)        // vs boxes kept so far
+                        sup = iou_ge(make_float4(kx1[q], ky1[q], kx2[q], ky2[q]), kar[q], bx, ar, p.thr_up);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {                         // my 4 columns of the 32x32 chunk matrix
+                        const int j = l * 4 + jj;
+                        if (j > ci && j < cnt && iou_ge(bx, ar, cbox[j], carea[j], p.thr_up)) row |= 1u << j;
+                    }
+                }
+                // combine the 8 sub-lanes of each candidate (they sit in the same warp, aligned groups of 8)
+                unsigned s = sup ? 1u : 0u;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) { s |= __shfl_xor_sync(0xffffffffu, s, o); row |= __shfl_xor_sync(0xffffffffu, row, o); }
+                if (l == 0 && ci < NMS_CH) { csup[ci] = s; crow[ci] = row; }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const bool alive = lane < cnt && !csup[lane];
+                const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+                const unsigned myrow = crow[lane];
+                unsigned removed = 0, keepmask = 0, k = kept_n;
+                for (int i = 0; i < cnt && k < max_keep; ++i) {              // uniform across the warp
+                    const unsigned ri = __shfl_sync(0xffffffffu, myrow, i);
+                    if (((alive_mask >> i) & 1u) && !((removed >> i) & 1u)) { keepmask |= 1u << i; removed |= ri; ++k; }
+                }
+                if ((keepmask >> lane) & 1u) {
+                    const unsigned pos = kept_n + __popc(keepmask & ((1u << lane) - 1u));
+                    const float4 kb = cbox[lane];
+                    kx1[pos] = kb.x; ky1[pos] = kb.y; kx2[pos] = kb.z; ky2[pos] = kb.w; kar[pos] = carea[lane];
+                    if (DETECT) {
+                        const float4 nb = p.boxes[(long long)b * p.P + cidx[lane]];
+                        float *o = out_seg + pos * 5;                       // detection.py:61-63
+                        o[0] = sc[cidx[lane]]; o[1] = nb.x; o[2] = nb.y; o[3] = nb.z; o[4] = nb.w;
+                    } else {
+                        p.keep[pos] = cidx[lane];
+                    }
+                }
+                if (lane == 0) s_kept = k;
+            }
+            __syncthreads();
+            kept_n = s_kept;
+        }
+        processed += n_sel;
+        if (kept_n >= max_keep || processed >= total) break;
+        hi_incl = lo - 1ull;
         __syncthreads();
-        kept_n = s_kept;
     }
 
     if (DETECT) {
         for (int i = kept_n * 5 + tid; i < p.top_k * 5; i += NMS_THREADS) out_seg[i] = 0.f;
     } else if (tid == 0) {
-        *p.num_keep = kept_n;
+        *p.num_keep = (int)kept_n;
     }
 }
 
@@ -264,8 +364,6 @@ static float thresh_up(double t)
     if ((double)f < t) f = nextafterf(f, INFINITY);
     return f;
 }
-
-static int pow2_at_least(int n) { int v = 32; while (v < n) v <<= 1; return v; }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -317,10 +415,11 @@ extern "C" int tdrn_detect(const float *loc, const float *conf, const float *pri
     p.boxes = (const float4 *)boxes; p.scoresT = scoresT; p.out = out; p.P = P; p.C = C; p.top_k = top_k;
     p.conf_thresh = conf_thresh;
     p.scale = make_float4(scale_host[0], scale_host[1], scale_host[2], scale_host[3]);
-    p.max_keep = top_k; p.thr_up = thresh_up(nms_thresh); p.n_pad_max = pow2_at_least(P);
-    const size_t smem = (size_t)p.n_pad_max * 8 + (size_t)top_k * 5 * sizeof(float);
-    TDRN_REQUIRE(smem <= 200 * 1024, "tdrn_detect: P=%d / top_k=%d exceed the shared-memory sort capacity", P, top_k);
-    TDRN_CUDA(cudaFuncSetAttribute(nms_segment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p.max_keep = top_k; p.kept_cap = top_k; p.thr_up = thresh_up(nms_thresh);
+    const size_t smem = (size_t)top_k * 5 * sizeof(float);
+    TDRN_REQUIRE(smem <= 150 * 1024, "tdrn_detect: top_k=%d exceeds the shared-memory kept-list capacity", top_k);
+    if (smem > 16 * 1024)
+        TDRN_CUDA(cudaFuncSetAttribute(nms_segment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_segment_kernel<true><<<dim3(C, B), NMS_THREADS, smem, st>>>(p);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
@@ -344,14 +443,8 @@ extern "C" int tdrn_nms(const float *dets, int n, double thresh, int max_keep, i
     }
     NmsP p{};
     p.dets = dets; p.n = n; p.keep = keep; p.num_keep = num_keep; p.kept_ws = (float *)workspace;
-    p.max_keep = max_keep; p.thr_up = thresh_up(thresh); p.n_pad_max = pow2_at_least(n);
-    const size_t smem = (size_t)p.n_pad_max * 8;
-    if (smem > 200 * 1024) {
-        set_error("tdrn_nms: n=%d exceeds the single-CTA shared-memory sort capacity (25600 boxes)", n);
-        return TDRN_EUNSUPPORTED;
-    }
-    TDRN_CUDA(cudaFuncSetAttribute(nms_segment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_segment_kernel<false><<<1, NMS_THREADS, smem, st>>>(p);
+    p.max_keep = max_keep; p.kept_cap = n; p.thr_up = thresh_up(thresh);
+    nms_segment_kernel<false><<<1, NMS_THREADS, 0, st>>>(p);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }

@@ -46,6 +46,8 @@ class Engine(object):
             raise NotImplementedError('tdrn_b200 runs on CUDA only: call net.to("cuda") first (no CPU fallback)')
         self.device = p.device
         self.pk = {}
+        self.multi_stream = os.environ.get('TDRN_SINGLE_STREAM', '0') != '1'
+        self._side = []
 
     # ---- weight packing -------------------------------------------------------------------------
     def _bn(self, name):
@@ -74,6 +76,36 @@ class Engine(object):
             v = self.sd[name].detach().float().contiguous().to(self.device)
             self.pk[name] = v
         return v
+
+    # ---- stream-level concurrency -----------------------------------------------------------------
+    def parallel(self, fns):
+        """Run independent closures on side streams (fork after the current stream, join back into it).
+        The four pyramid levels' heads and the TCB branches are independent and each of them is far too
+        small to fill 148 SMs (7..100 CTAs), so they are issued as parallel branches; under CUDA-graph
+        capture the event dependencies become parallel graph branches.  Returns the closures' results."""
+        if len(fns) <= 1 or not self.multi_stream:
+            return [f() for f in fns]
+        main = torch.cuda.current_stream()
+        while len(self._side) < len(fns) - 1:
+            self._side.append(torch.cuda.Stream(self.device))
+        fork = torch.cuda.Event()
+        fork.record(main)
+        results = [None] * len(fns)
+        joins = []
+        for i, f in enumerate(fns[1:]):
+            st = self._side[i]
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                results[i + 1] = f()
+                ev = torch.cuda.Event()
+                ev.record(st)
+            joins.append(ev)
+            for t in _tensors(results[i + 1]):
+                t.record_stream(main)            # allocated on the side stream, consumed on the main one
+        results[0] = fns[0]()
+        for ev in joins:
+            main.wait_event(ev)
+        return results
 
     # ---- operators ------------------------------------------------------------------------------
     def conv(self, name, x, stride=1, pad=0, dil=1, bn=None, relu=False, deconv=False, **kw):
@@ -152,10 +184,18 @@ class Engine(object):
         x = self.conv('last_layer_trans.2', x, 1, 1)
         x = self.conv('last_layer_trans.3', x, 1, 1)
         odm = [x]
-        trans = []
-        for k in range(3):
-            t = self.conv('trans_layers.%d.0' % k, arm_sources[k], 1, 1, relu=True)
-            trans.append(self.conv('trans_layers.%d.2' % k, t, 1, 1))
+        return self.fpn_topdown(x, odm, [self.trans_branch(arm_sources[k], k) for k in range(3)])
+
+    def last_trans(self, src3):
+        x = self.conv('last_layer_trans.0', src3, 1, 1, relu=True)
+        x = self.conv('last_layer_trans.2', x, 1, 1)
+        return self.conv('last_layer_trans.3', x, 1, 1)
+
+    def trans_branch(self, src, k):
+        t = self.conv('trans_layers.%d.0' % k, src, 1, 1, relu=True)
+        return self.conv('trans_layers.%d.2' % k, t, 1, 1)
+
+    def fpn_topdown(self, x, odm, trans):
         for k in range(3):
             t = trans[2 - k]
             # relu(up(x) + t): ConvTranspose2d k2 s2 as a pixel-shuffled GEMM with residual epilogue
@@ -178,17 +218,48 @@ class Engine(object):
         """arm_loc + 1x1 offset convs: dualrefinedet_vggbn.py:154-165."""
         B = arm_sources[0].shape[0]
         arm_loc = torch.empty(B, P, 4, dtype=torch.float32, device=self.device)
-        offs, offs2 = [], []
-        for k, a in enumerate(arm_sources):
+
+        def level(k):
+            a = arm_sources[k]
             self.head_into('arm_loc.%d' % k, a, arm_loc, 4, lv_off[k], P)
+            o = o2 = None
             if with_offsets:
                 H, W = a.shape[1], a.shape[2]
                 view = arm_loc.view(B, P * 4)[:, lv_off[k] * 4:]
                 kw = dict(in_shape=(B, H, W, 12), in_sb=P * 4, out_dtype=torch.float32)
-                offs.append(self.conv('offset.%d' % k, view, **kw))
+                o = self.conv('offset.%d' % k, view, **kw)
                 if multihead:
-                    offs2.append(self.conv('offset2.%d' % k, view, **kw))
+                    o2 = self.conv('offset2.%d' % k, view, **kw)
+            return o, o2
+
+        res = self.parallel([(lambda k=k: level(k)) for k in range(len(arm_sources))])
+        offs = [r[0] for r in res] if with_offsets else []
+        offs2 = [r[1] for r in res] if with_offsets and multihead else []
         return arm_loc, offs, offs2
+
+    def arm_and_tcb(self, arm_sources, P, lv_off, multihead):
+        """ARM heads (+offset convs) of the four levels, the three TCB transfer branches and the top
+        last_layer_trans chain are mutually independent: one fork/join."""
+        B = arm_sources[0].shape[0]
+        arm_loc = torch.empty(B, P, 4, dtype=torch.float32, device=self.device)
+
+        def level(k):
+            a = arm_sources[k]
+            self.head_into('arm_loc.%d' % k, a, arm_loc, 4, lv_off[k], P)
+            H, W = a.shape[1], a.shape[2]
+            view = arm_loc.view(B, P * 4)[:, lv_off[k] * 4:]
+            kw = dict(in_shape=(B, H, W, 12), in_sb=P * 4, out_dtype=torch.float32)
+            o = self.conv('offset.%d' % k, view, **kw)
+            o2 = self.conv('offset2.%d' % k, view, **kw) if multihead else None
+            return o, o2
+
+        fns = [lambda: self.last_trans(arm_sources[3])]
+        fns += [(lambda k=k: self.trans_branch(arm_sources[k], k)) for k in range(3)]
+        fns += [(lambda k=k: level(k)) for k in range(4)]
+        res = self.parallel(fns)
+        x, trans, lv = res[0], res[1:4], res[4:8]
+        odm = self.fpn_topdown(x, [x], trans)
+        return arm_loc, [r[0] for r in lv], ([r[1] for r in lv] if multihead else []), odm
 
     def deform_heads(self, feats, offs, offs2, P, lv_off, num_classes, dg, multihead, loc_name='odm_loc',
                      conf_name='odm_conf', softmax=True):
@@ -197,19 +268,23 @@ class Engine(object):
         loc = torch.empty(B, P, 4, dtype=torch.float32, device=self.device)
         conf = torch.empty(B, P, num_classes, dtype=torch.float32, device=self.device)
         fused = self.use_tc and feats[0].dtype == torch.bfloat16 and all(f.shape[3] % 64 == 0 for f in feats)
-        for k, f in enumerate(feats):
+
+        def level(k):
+            f = feats[k]
             if fused:
                 w1 = self.fused_head_weight(loc_name, conf_name, k)
                 w2 = self.fused_head_weight(loc_name + '_2', conf_name + '_2', k) if multihead else None
                 ops.deform_head(f, offs[k], w1, num_classes, dg, 3, 1, loc, conf, P, lv_off[k],
                                 offsets2=offs2[k] if multihead else None, w2_bf16=w2,
                                 kh2=5 if multihead else 0, pad2=2 if multihead else 0, softmax=softmax)
-            else:
+            else:  # noqa: E101
                 self.head_into('%s.%d' % (loc_name, k), f, loc, 4, lv_off[k], P, 1, offsets=offs[k], dg=dg)
                 self.head_into('%s.%d' % (conf_name, k), f, conf, num_classes, lv_off[k], P, 1, offsets=offs[k], dg=dg)
                 if multihead:
                     self.head_into('%s_2.%d' % (loc_name, k), f, loc, 4, lv_off[k], P, 2, True, offs2[k], dg)
                     self.head_into('%s_2.%d' % (conf_name, k), f, conf, num_classes, lv_off[k], P, 2, True, offs2[k], dg)
+
+        self.parallel([(lambda k=k: level(k)) for k in range(len(feats))])
         conf2d = conf.view(B * P, num_classes)
         if softmax and not fused:
             ops.softmax_rows(conf2d, out=conf2d)
@@ -220,15 +295,9 @@ class Engine(object):
         key = 'fused.%s.%s.%d' % (loc_name, conf_name, k)
         w = self.pk.get(key)
         if w is None:
-            wl = self.sd['%s.%d.weight' % (loc_name, k)].detach().double().cpu()
-            wc = self.sd['%s.%d.weight' % (conf_name, k)].detach().double().cpu()
-            wcat = torch.cat([wl, wc], 0)                                  # [N, Cin, kh, kw]
-            n, cin, kh, kw = wcat.shape
-            wk = wcat.permute(0, 2, 3, 1).reshape(n, kh * kw * cin)
-            n_pad = (n + 15) // 16 * 16
-            wp = torch.zeros(n_pad, wk.shape[1], dtype=torch.float64)
-            wp[:n] = wk
-            w = wp.to(torch.bfloat16).contiguous().to(self.device)
+            wl = self.sd['%s.%d.weight' % (loc_name, k)].detach()
+            wc = self.sd['%s.%d.weight' % (conf_name, k)].detach()
+            w = ops.pack_deform_head_weight(torch.cat([wl, wc], 0), self.device)   # [N = 12 + 3C, Cin, kh, kw]
             self.pk[key] = w
         return w
 
@@ -238,16 +307,29 @@ class Engine(object):
         B = feats[0].shape[0]
         loc = torch.empty(B, P, 4, dtype=torch.float32, device=self.device)
         conf = torch.empty(B, P, num_classes, dtype=torch.float32, device=self.device)
-        for k, f in enumerate(feats):
+
+        def level(k):
+            f = feats[k]
             self.head_into('%s.%d' % (loc_name, k), f, loc, 4, lv_off[k], P, 1)
             self.head_into('%s.%d' % (conf_name, k), f, conf, num_classes, lv_off[k], P, 1)
             if multihead:
                 self.head_into('%s_2.%d' % (loc_name, k), f, loc, 4, lv_off[k], P, 2, True)
                 self.head_into('%s_2.%d' % (conf_name, k), f, conf, num_classes, lv_off[k], P, 2, True)
+
+        self.parallel([(lambda k=k: level(k)) for k in range(len(feats))])
         conf2d = conf.view(B * P, num_classes)
         if softmax:
             ops.softmax_rows(conf2d, out=conf2d)
         return loc, conf2d
+
+
+def _tensors(obj):
+    if torch.is_tensor(obj):
+        yield obj
+    elif isinstance(obj, (list, tuple)):
+        for o in obj:
+            for t in _tensors(o):
+                yield t
 
 
 def prior_layout(feats):

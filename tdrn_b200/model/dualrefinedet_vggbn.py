@@ -78,11 +78,10 @@ class RefineSSD(DetectorBase):
         x = self._check_input(x)
         arm_sources = E.vgg_trunk(x, self.bn)
         P, lv = prior_layout(arm_sources)
-        arm_loc, offs, offs2 = E.arm_heads(arm_sources, P, lv, self.multihead)
+        arm_loc, offs, offs2, odm_sources = E.arm_and_tcb(arm_sources, P, lv, self.multihead)
         if _offsets is not None:
             offs = [ops.nchw_f32_to_nhwc(o.float(), torch.float32) for o in _offsets[0]]
             offs2 = [ops.nchw_f32_to_nhwc(o.float(), torch.float32) for o in (_offsets[1] or [])]
-        odm_sources = E.fpn(arm_sources)
         odm_loc, conf = E.deform_heads(odm_sources, offs, offs2, P, lv, self.num_classes, self.def_groups,
                                        self.multihead)
         return arm_loc, [ops.nhwc_to_nchw_f32(o) for o in offs], odm_loc, conf

@@ -261,6 +261,19 @@ def deform_conv_nchw(input, offset, weight, stride, pad, dil, dg):
     return out
 
 
+def pack_deform_head_weight(wcat, device='cuda'):
+    """[N, Cin, kh, kw] (loc rows then conf rows) -> bf16 [N_pad16, K] K-major for tdrn_deform_head, with
+    k = (cb * taps + tap) * 64 + c: channel-block-major so all taps of one 64-channel slab are consecutive."""
+    w = wcat.detach().double().cpu()
+    n, cin, kh, kw = w.shape
+    assert cin % 64 == 0
+    wk = w.permute(0, 2, 3, 1).reshape(n, kh * kw, cin // 64, 64).permute(0, 2, 1, 3).reshape(n, kh * kw * cin)
+    n_pad = (n + 15) // 16 * 16
+    wp = torch.zeros(n_pad, wk.shape[1], dtype=torch.float64)
+    wp[:n] = wk
+    return wp.to(torch.bfloat16).contiguous().to(device)
+
+
 def deform_head(feat_nhwc, offsets, w_bf16, num_classes, dg, kh, pad, loc_out, conf_out, P, prior_off,
                 offsets2=None, w2_bf16=None, kh2=0, pad2=0, softmax=True):
     x = _cuda(feat_nhwc, 'feat')

@@ -130,12 +130,7 @@ def test_deform_head_tc_vs_oracle(B, H, W, cin, C, dg, multihead):
         conf_ref = conf_ref + R.deform_conv_forward(x, off2, wc2, 1, 2, 1, dg)
         w2 = torch.cat([wl2, wc2], 0)
 
-    def pack(wcat):
-        n, ci, kh, kw = wcat.shape
-        wk = wcat.permute(0, 2, 3, 1).reshape(n, kh * kw * ci)
-        wp = torch.zeros((n + 15) // 16 * 16, wk.shape[1])
-        wp[:n] = wk
-        return wp.to(torch.bfloat16).cuda()
+    pack = ops.pack_deform_head_weight
 
     P, poff = H * W * 3 + 11, 5
     loc = torch.zeros(B, P, 4, device='cuda')
