@@ -163,6 +163,7 @@ def run_gpu(args, rank, world, local_rank):
     from tdrn_b200.utils.synthetic import frames as make_frames
     from tdrn_b200.layers.functions import Detect, PriorBox
     from tdrn_b200.data import mb_cfg
+    from tdrn_b200.utils.shard import gather_detections
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -211,13 +212,13 @@ def run_gpu(args, rank, world, local_rank):
         static_x.copy_(dev_x[i % n_in], non_blocking=True)      # device->device: the frames are already in HBM
         replay()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, static_out)
+            gather_detections(static_out, out=gathered)
 
     def step_e2e(i):
         static_x.copy_(host_x[i % n_in], non_blocking=True)     # pinned host -> device
         replay()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, static_out)
+            gather_detections(static_out, out=gathered)
         host_out.copy_(static_out, non_blocking=True)           # detections -> host
 
     def timed(step_fn, steps, warmup):

@@ -23,12 +23,18 @@ relative to the upstream reference checkout):
   ``tests/golden/*.npz`` (see ``oracle/make_golden.py``).
 
 Parity pin status: the reference ships no golden vectors or known-answer tests for this
-path.  The Python model / Detect / PriorBox restatements are pinned
-against outputs of the reference's own Python files executed in the build container
-(fixtures under tests/golden, generator committed).  The two *native* pieces -- the CUDA
-deformable conv and the Cython NMS -- cannot be compiled or run anywhere we have access to
-(torch.utils.ffi/THC removed; Cython 0.25 source rejects Cython 3/NumPy 2), so for those two
-functions the status is "parity unpinned": the restatement follows the source line by line
-and is cross-checked against torchvision.ops.deform_conv2d (interior), F.conv2d (zero
-offset) and the reference's importable utils/nms/py_cpu_nms.py.
+path.  Pins used instead:
+  * Python model / Detect / PriorBox restatements: outputs of the reference's own Python files
+    executed in the build container (fixtures under tests/golden, generator committed).
+  * Deformable-conv sampler (the parity-critical native piece): the reference's OWN CUDA kernel
+    file utils/deformconv/deform_conv_cuda_kernel.cu compiles unmodified with nvcc for sm_100a
+    (oracle/build_ref.py -> oracle/_ref/libtdrn_ref_native.so) and is run on the GPU box next to
+    the restatements and the product (tests/test_gpu_ref_native.py).  Its THC host wrapper
+    (deform_conv_cuda.c) cannot be built (torch 0.4 THC); the wrapper's loop is 20 lines of
+    zero + im2col + SGEMM and is restated in oracle/ref_native.deform_conv_forward.
+  * NMS: the reference's GPU kernel utils/nms/nms_kernel.cu (`_nms`) is compiled and run the same
+    way (IoU +1 convention, bitmask reduction); the Cython CPU variant that Detect actually calls
+    (cpu_nms.pyx, suppress at ovr >= thresh instead of >) cannot be built under Cython 3 /
+    NumPy 2 -- for that one comparison operator the status is "parity unpinned"; it is restated
+    line by line and cross-checked against the importable utils/nms/py_cpu_nms.py.
 """

@@ -1,0 +1,94 @@
+"""Pins against the REAL reference native code: the reference's own CUDA sources
+(utils/deformconv/deform_conv_cuda_kernel.cu, utils/nms/nms_kernel.cu) are compiled unmodified by
+oracle/build_ref.py into oracle/_ref/libtdrn_ref_native.so (built in the container that has /root/reference; the
+.so travels to the GPU box) and run here on the B200 next to the oracle restatements and the product kernels.
+
+  * deformable im2col: reference kernel vs oracle (C scalar + torch restatement).  The reference is built
+    with nvcc's default -fmad=true (its make.sh:11 passes no flag), so its bilinear blend may contract
+    into FMAs; the oracle is contraction-free.  Tolerance: 4 ulp of the largest corner value; the zero /
+    non-zero pattern of the border rules (.cu:195-203, :25-37) must match exactly.
+  * deformable conv forward: product tdrn_deform_conv_forward (fp32) vs reference im2col + fp32 GEMM, 1e-4.
+  * NMS: reference GPU `_nms` (suppress when IoU > thresh) vs product tdrn_nms (IoU >= thresh, the CPU rule
+    Detect uses): identical keep lists whenever no pair sits exactly on the threshold.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_native, c_oracle, deform_conv_ref, nms_ref
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not ref_native.available(), reason='oracle/_ref not built (needs /root/reference)')]
+
+CASES = [  # C, H, W, k, stride, pad, dil, dg, offset sigma
+    (8, 9, 11, 3, 1, 1, 1, 1, 2.0),
+    (16, 10, 10, 3, 1, 1, 1, 2, 3.0),
+    (64, 20, 20, 5, 1, 2, 1, 1, 2.0),
+    (32, 13, 17, 3, 2, 1, 1, 4, 1.5),
+    (16, 12, 12, 3, 1, 2, 2, 8, 2.5),
+    (6, 32, 32, 3, 1, 1, 1, 2, 0.0),      # the shape family of utils/deformconv/test.py (6 ch, dg 2), zero offsets
+]
+
+
+def _case(c, h, w, k, s, p, d, dg, sigma, seed):
+    g = torch.Generator().manual_seed(seed)
+    ho = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
+    wo = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
+    inp = torch.randn(c, h, w, generator=g)
+    off = torch.randn(dg * 2 * k * k, ho, wo, generator=g) * sigma
+    # exact-integer and exact-border offsets exercise the `h_low >= H-1` and validity branches
+    off.view(-1)[::7] = torch.round(off.view(-1)[::7])
+    return inp, off
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_reference_im2col_kernel_matches_oracle(case):
+    c, h, w, k, s, p, d, dg, sigma = case
+    inp, off = _case(*case, seed=3)
+    ref = ref_native.deformable_im2col(inp.cuda(), off.cuda(), k, k, s, p, d, dg).cpu()
+    ora = deform_conv_ref.deform_im2col(inp, off, k, k, s, p, d, dg)
+    assert ref.shape == ora.shape
+    tol = 4 * np.finfo(np.float32).eps * float(inp.abs().max())
+    assert float((ref - ora).abs().max()) <= tol
+    # border semantics: samples the reference zeroes are exactly the samples the oracle zeroes
+    assert torch.equal(ref == 0, ora == 0)
+    # the C restatement agrees with the torch restatement bit for bit, hence with the reference to `tol`
+    wone = torch.zeros(1, c, k, k)
+    wone[0, 0, 0, 0] = 1.0                       # picks column row 0 out of the C oracle's conv
+    got = c_oracle.deform_conv_forward(inp[None].numpy(), off[None].numpy(), wone.numpy(), s, p, d, dg)
+    assert np.array_equal(got.reshape(-1), ora[0].numpy())
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_product_deform_conv_matches_reference_kernel(case):
+    from tdrn_b200.model.networks import conv_offset2d
+    c, h, w, k, s, p, d, dg, sigma = case
+    inp, off = _case(*case, seed=5)
+    B, cout = 3, 21
+    g = torch.Generator().manual_seed(9)
+    x = torch.stack([inp * (i + 1) for i in range(B)]).cuda()
+    o = torch.stack([off.roll(i, 1) for i in range(B)]).cuda()
+    wt = (torch.randn(cout, c, k, k, generator=g) / (c * k * k) ** 0.5).cuda()
+    ref = ref_native.deform_conv_forward(x, o, wt, s, p, d, dg)
+    got = conv_offset2d(x, o, wt, s, p, d, dg)
+    assert got.shape == ref.shape
+    err = float((got - ref).abs().max() / ref.abs().max())
+    assert err < 1e-4, err
+
+
+def _boxes(n, seed, spread=300.0):
+    rng = np.random.RandomState(seed)
+    xy = rng.uniform(0, spread, (n, 2))
+    wh = rng.uniform(8, 90, (n, 2))
+    s = rng.permutation(n).astype(np.float32) / n + 0.001          # distinct scores: no tie-order ambiguity
+    return np.hstack([xy, xy + wh, s[:, None]]).astype(np.float32)
+
+
+@pytest.mark.parametrize('n,thresh', [(1, 0.45), (63, 0.45), (64, 0.3), (65, 0.5), (1000, 0.45), (6375, 0.45)])
+def test_product_nms_matches_reference_gpu_kernel(n, thresh):
+    from tdrn_b200.utils.nms_wrapper import nms
+    dets = _boxes(n, n)
+    ref = ref_native.gpu_nms(dets, thresh)
+    got = nms(dets, thresh)
+    ora = nms_ref.cpu_nms(dets, thresh)
+    assert [int(i) for i in ref] == [int(i) for i in got] == [int(i) for i in ora]

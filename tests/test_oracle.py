@@ -136,3 +136,14 @@ def test_deform_conv_interior_matches_torchvision():
     a = R.deform_conv_forward(x, off, w, 1, 1, 1, 1)
     b = tv.deform_conv2d(x, off, w, None, 1, 1, 1)
     assert rel_err(a[..., 2:-2, 2:-2].numpy(), b[..., 2:-2, 2:-2].numpy()) < 1e-5
+
+
+def test_reference_native_library_builds_and_exports():
+    """oracle/_ref: the reference's own .cu files compile unmodified (nvcc, sm_100a) and export the two doors."""
+    import ctypes
+    from oracle import build_ref
+    path = build_ref.build()
+    if path is None:
+        pytest.skip('reference checkout absent and oracle/_ref not prebuilt')
+    L = ctypes.CDLL(path)
+    assert hasattr(L, 'ref_deformable_im2col') and hasattr(L, 'ref_gpu_nms')
