@@ -214,14 +214,46 @@ def run_gpu(args, rank, world, local_rank):
         if world > 1:
             gather_detections(static_out, out=gathered)
 
+    # e2e: software-pipelined like a production feeder -- the pinned-host -> device copy of step i+1 runs on a copy
+    # stream while step i computes; every step still pays its own H2D (39 MB) and D2H (2.7 MB) inside the timed
+    # region, they just overlap with the previous / next step's kernels instead of serialising with them.
+    copy_stream = torch.cuda.Stream(dev)
+    staging = [torch.empty_like(dev_x[0]) for _ in range(2)]
+    staged_ev = [torch.cuda.Event() for _ in range(2)]       # H2D into staging[j] finished
+    consumed_ev = [torch.cuda.Event() for _ in range(2)]     # staging[j] copied into the graph's input
+    out_ready, out_copied = torch.cuda.Event(), torch.cuda.Event()
+    dev_out = torch.empty_like(static_out)
+    pipe = {'primed': -1}
+
+    def prefetch(i):
+        j = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed_ev[j])
+            staging[j].copy_(host_x[i % n_in], non_blocking=True)
+            staged_ev[j].record(copy_stream)
+        pipe['primed'] = i
+
     def step_e2e(i):
-        static_x.copy_(host_x[i % n_in], non_blocking=True)     # pinned host -> device
+        if pipe['primed'] != i:
+            prefetch(i)
+        j = i % 2
+        stream.wait_event(staged_ev[j])
+        static_x.copy_(staging[j], non_blocking=True)           # 39 MB device->device, ~15 us
+        consumed_ev[j].record(stream)
+        prefetch(i + 1)                                         # next step's H2D overlaps this step's kernels
         replay()
         if world > 1:
             gather_detections(static_out, out=gathered)
-        host_out.copy_(static_out, non_blocking=True)           # detections -> host
+        stream.wait_event(out_copied)                           # previous D2H has drained dev_out
+        dev_out.copy_(static_out, non_blocking=True)
+        out_ready.record(stream)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(out_ready)
+            host_out.copy_(dev_out, non_blocking=True)          # detections -> pinned host
+            out_copied.record(copy_stream)
 
     def timed(step_fn, steps, warmup):
+        pipe['primed'] = -1
         with torch.cuda.stream(stream):
             for i in range(warmup):
                 step_fn(i)
@@ -233,6 +265,7 @@ def run_gpu(args, rank, world, local_rank):
             e0.record(stream)
             for i in range(steps):
                 step_fn(warmup + i)
+            stream.wait_stream(copy_stream)                     # e2e: the last step's D2H is inside the timed region
             e1.record(stream)
             stream.synchronize()
             if world > 1:

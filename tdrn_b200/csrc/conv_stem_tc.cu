@@ -1,0 +1,244 @@
+// conv_stem_tc.cu -- the Cin = 3 stem convolution (VGG conv1_1 + folded BN + ReLU, model/networks.py:146 with
+// in_channels = 3, first entry of vgg_base) on the tensor cores.
+//
+// The layer is 0.35 GFLOP/frame but writes the largest activation of the network (B x 320 x 320 x 64 bf16 =
+// 419 MB at b32), so it is HBM-write bound; the CUDA-core version (conv_first.cu) was FMA-issue bound at ~0.9 TB/s.
+// Here the 27-tap dot product runs as a K = 32 (27 + zero pad) tcgen05 GEMM:
+//   A [128 pixels x 32] bf16 : im2col rows built by 4 producer warps from a fp32 NCHW patch staged in shared
+//                              memory (the reference's input layout is read directly, no layout/cast pass),
+//                              written in the 128B-swizzled K-major UMMA layout (logical chunks 0..3 of each row);
+//   B [64 couts x 32]   bf16 : converted once per CTA from the packed fp32 weights [27][64];
+//   D [128 x 64] fp32 in TMEM, double buffered; 4 epilogue warps add bias, ReLU, cast to bf16 into a swizzled
+//   staging tile and ONE thread issues a TMA store (cp.async.bulk.tensor ... global <- shared) of the 16 KB box,
+//   so the NHWC output is written as full 128-byte lines.
+// Persistent grid (2 CTAs per SM), tile = bw x bh output pixels of one image (64x2, 32x4 or 16x8).
+#include "tc_common.cuh"
+
+namespace tdrn {
+namespace tc {
+
+struct StemP {
+    const float *x;        // [B,3,H,W] fp32 (reference layout)
+    const float *w;        // [27][64] fp32, k = (i*3+j)*3 + c
+    const float *bias;     // [64] or NULL
+    int B, H, W;
+    int bw, bh, tiles_w, tiles_h, total;
+    int relu;
+};
+
+constexpr int ST_THREADS = 288;          // warps 0-3 producers, 4 MMA, 5-8 epilogue
+constexpr int ST_COUT = 64;
+constexpr int ST_PATCH_MAX = 3 * 4 * 66; // floats; the largest of the three tile shapes (64x2)
+constexpr int ST_PRE = (ST_PATCH_MAX + 127) / 128;
+constexpr int ST_SMEM = 2 * 16384 + 2 * 16384 + 8192 + 2 * ST_PATCH_MAX * 4 + 256 + 1024;
+
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *src, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"((uint64_t)m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __grid_constant__ CUtensorMap tmO, const StemP p)
+{
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2];
+    __shared__ uint32_t tmem_base_s;
+
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base;                                   // 2 x [128 rows][128 B]
+    uint8_t *sO = base + 2 * 16384;                       // 2 x [128 rows][128 B] output staging
+    uint8_t *sB = base + 4 * 16384;                       // [64 rows][128 B]
+    float *sP = (float *)(base + 4 * 16384 + 8192);       // 2 x patch [3][bh+2][bw+2]
+    float *sBias = sP + 2 * ST_PATCH_MAX;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int PH = p.bh + 2, PW = p.bw + 2, PN = 3 * PH * PW;
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmO);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(&tmem_base_s, 128);
+    // B operand: w[k][n] fp32 -> bf16 rows n, logical chunks 0..3 (k 0..31, zero beyond 27)
+    for (int e = tid; e < ST_COUT * 4; e += ST_THREADS) {
+        const int n = e >> 2, chunk = e & 3;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int k = chunk * 8 + j; v[j] = k < 27 ? __ldg(p.w + k * ST_COUT + n) : 0.f; }
+        uint4 q;
+        q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+        *(uint4 *)(sB + sw128_offset(n, chunk)) = q;
+    }
+    if (tid < ST_COUT) sBias[tid] = p.bias ? p.bias[tid] : 0.f;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < 4) {
+        // ===================== producers: fp32 NCHW patch -> bf16 im2col rows =====================
+        float pre[ST_PRE];
+        auto load_patch = [&](int tile) {
+            const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+            const int y0 = (rem / p.tiles_w) * p.bh - 1, x0 = (rem % p.tiles_w) * p.bw - 1;
+            const float *xb = p.x + (long long)b * 3 * p.H * p.W;
+#pragma unroll
+            for (int q = 0; q < ST_PRE; ++q) {
+                const int e = tid + q * 128;
+                float v = 0.f;
+                if (e < PN) {
+                    const int c = e / (PH * PW), r2 = e - c * (PH * PW);
+                    const int py = r2 / PW, px = r2 - py * PW;
+                    const int iy = y0 + py, ix = x0 + px;
+                    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(xb + ((long long)c * p.H + iy) * p.W + ix);
+                }
+                pre[q] = v;
+            }
+        };
+        auto store_patch = [&](int buf) {
+#pragma unroll
+            for (int q = 0; q < ST_PRE; ++q) {
+                const int e = tid + q * 128;
+                if (e < PN) sP[buf * ST_PATCH_MAX + e] = pre[q];
+            }
+        };
+        int tile = blockIdx.x;
+        if (tile < p.total) { load_patch(tile); store_patch(0); }
+        named_bar(1, 128);
+        const int wl = tid % p.bw, hl = tid / p.bw;
+        for (uint32_t it = 0; tile < p.total; tile += gridDim.x, ++it) {
+            const int s = it & 1;
+            const int next = tile + gridDim.x;
+            if (next < p.total) load_patch(next);                       // global loads in flight during the build
+            mbar_wait(&a_empty[s], ((it >> 1) & 1u) ^ 1u);
+            const float *P = sP + s * ST_PATCH_MAX;
+            uint32_t kw[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+                float v[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = 2 * k2 + h;                           // compile-time after unrolling
+                    if (k < 27) { const int t = k / 3, c = k - t * 3, i = t / 3, j = t - i * 3; v[h] = P[(c * PH + hl + i) * PW + wl + j]; }
+                    else v[h] = 0.f;
+                }
+                kw[k2] = pack_bf16x2(v[0], v[1]);
+            }
+            uint8_t *a = sA + s * 16384;
+#pragma unroll
+            for (int chunk = 0; chunk < 4; ++chunk)
+                *(uint4 *)(a + sw128_offset(tid, chunk)) = make_uint4(kw[4 * chunk], kw[4 * chunk + 1], kw[4 * chunk + 2], kw[4 * chunk + 3]);
+            fence_proxy_async_smem();
+            named_bar(1, 128);                                          // A tile complete, patch[s] fully consumed
+            if (tid == 0) mbar_arrive(&a_full[s]);
+            if (next < p.total) store_patch(s ^ 1);
+            named_bar(1, 128);                                          // patch[s^1] visible to the next build
+        }
+    } else if (warp == 4) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, ST_COUT);
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(sB));
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++it) {
+                const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
+                mbar_wait(&t_empty[s], ph ^ 1u);
+                mbar_wait(&a_full[s], ph);
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * 16384));
+                umma_bf16(tmem_base + s * ST_COUT, adesc, bdesc, idesc, 0u);
+                umma_bf16(tmem_base + s * ST_COUT, adesc + 2, bdesc + 2, idesc, 1u);
+                umma_commit(&a_empty[s]);
+                umma_commit(&t_full[s]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue: TMEM -> bias/ReLU/bf16 -> swizzled smem -> TMA store =====================
+        const int et = tid - 160;
+        const int quad = warp & 3, r = quad * 32 + lane;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++it) {
+            const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
+            if (et == 0) bulk_wait_read<1>();                            // the store that last read sO[s] has drained
+            named_bar(2, 128);
+            mbar_wait(&t_full[s], ph);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + s * ST_COUT;
+            uint8_t *o = sO + s * 16384;
+#pragma unroll
+            for (int c0 = 0; c0 < ST_COUT; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + (uint32_t)c0, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { v[j] += sBias[c0 + j]; if (p.relu) v[j] = fmaxf(v[j], 0.f); }
+                *(uint4 *)(o + sw128_offset(r, c0 >> 3)) =
+                    make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                *(uint4 *)(o + sw128_offset(r, (c0 >> 3) + 1)) =
+                    make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[s]);
+            fence_proxy_async_smem();
+            named_bar(2, 128);
+            if (et == 0) {
+                const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+                tma_store_4d(&tmO, o, 0, (rem % p.tiles_w) * p.bw, (rem / p.tiles_w) * p.bh, b);
+                bulk_commit();
+            }
+        }
+        if (et == 0) bulk_wait_read<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
+}
+
+// -> TDRN_EUNSUPPORTED when the shape does not tile (caller falls back to the CUDA-core stem)
+int launch_conv_stem_tc(const float *x, const float *w, const float *bias, void *out, int B, int H, int W, int relu,
+                        cudaStream_t st)
+{
+    StemP p{};
+    if (W % 64 == 0 && H % 2 == 0) { p.bw = 64; p.bh = 2; }
+    else if (W % 32 == 0 && H % 4 == 0) { p.bw = 32; p.bh = 4; }
+    else if (W % 16 == 0 && H % 8 == 0) { p.bw = 16; p.bh = 8; }
+    else return TDRN_EUNSUPPORTED;
+    p.x = x; p.w = w; p.bias = bias; p.B = B; p.H = H; p.W = W; p.relu = relu;
+    p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.total = p.tiles_w * p.tiles_h * B;
+    CUtensorMap tmO;
+    const uint64_t dims[4] = {ST_COUT, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {ST_COUT * 2, (uint64_t)W * ST_COUT * 2, (uint64_t)H * W * ST_COUT * 2};
+    const uint32_t box[4] = {ST_COUT, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+    int rc = make_tmap_bf16(&tmO, out, 4, dims, str, box, nullptr);
+    if (rc) return rc;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        TDRN_CUDA(cudaGetDevice(&dev));
+        TDRN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    TDRN_CUDA(cudaFuncSetAttribute(conv_stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+    const int grid = p.total < 2 * num_sms ? p.total : 2 * num_sms;
+    conv_stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM, st>>>(tmO, p);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
+}  // namespace tc
+}  // namespace tdrn

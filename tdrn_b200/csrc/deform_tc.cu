@@ -7,8 +7,9 @@
 //   * loc and conf weights are concatenated along N (12 + 3*C rows), so every sampled value feeds
 //     all outputs of its pixel;
 //   * the bilinear-sampled im2col tile (sampler rules of deform_conv_cuda_kernel.cu:16-51,195-203)
-//     is produced by 8 warps straight into shared memory in the 128B-swizzled K-major UMMA layout
-//     (each corner read is a 16-byte channels-last vector, 8 lanes cover a 128-byte line) and is
+//     is produced by 16 warps straight into shared memory in the 128B-swizzled K-major UMMA layout
+//     (each corner read is a 16-byte channels-last vector, the 8 lanes of a quarter-warp cover one
+//     128-byte line) and is
 //     consumed in place by tcgen05.mma: the column buffer never exists in HBM;
 //   * the optional 5x5 "multihead" (l(ob,f) + l2(ob,f2), :182-183) simply continues the K loop into
 //     the same TMEM accumulator;
@@ -16,9 +17,10 @@
 //     (nn.Softmax(dim=1) on view(-1, C), :196) and writes loc [B,P,4] / conf [B,P,C] rows coalesced
 //     at their prior offsets (the reference's permute(0,2,3,1).contiguous().view + cat).
 //
-// Warp roles (320 threads): warps 0-7 A producers (then epilogue), warp 8 weight TMA, warp 9 TMEM
+// Warp roles (576 threads): warps 0-15 A producers (then epilogue), warp 16 weight TMA, warp 17 TMEM
 // allocator + MMA issuer.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace tdrn {
 namespace tc {
@@ -34,6 +36,7 @@ struct DeformP {
     float *loc_out, *conf_out;
     uint32_t b_bytes;
     int geo_per_row;                 // (taps0 + taps1) * dg geometry entries per tile row
+    int stages;                      // smem ring depth (3, or 2 when the geometry cache is large: dg = 8)
 };
 
 template <int NMAX> struct DfCfg {
@@ -45,8 +48,33 @@ template <int NMAX> struct DfCfg {
     static constexpr int SMEM_STAGES_BYTES = STAGES * STAGE_BYTES + 1024;   // + geometry cache (run-time size)
 };
 
-// Bilinear blend of two packed bf16 channels from the 4 corners, fp32 arithmetic, one bf16x2 result.
-__device__ __forceinline__ uint32_t blend2(uint32_t a, uint32_t b, uint32_t c, uint32_t d, float w1, float w2, float w3, float w4)
+// Packed-pair fp32 arithmetic (Blackwell FFMA2 / FMUL2): one instruction blends both channels of a bf16x2 word.
+__device__ __forceinline__ uint64_t pair_of(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+// bf16x2 word -> (lo, hi) fp32 pair: a bf16 is the upper half of the fp32 with the same value
+__device__ __forceinline__ uint64_t unpack_bf16x2(uint32_t a)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a << 16), "r"(a & 0xffff0000u));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
+{
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t blend2s(uint32_t a, uint32_t b, uint32_t c, uint32_t d, float w1, float w2, float w3, float w4)
 {
     float lo = w1 * __uint_as_float(a << 16), hi = w1 * __uint_as_float(a & 0xffff0000u);
     lo = fmaf(w2, __uint_as_float(b << 16), lo); hi = fmaf(w2, __uint_as_float(b & 0xffff0000u), hi);
@@ -56,11 +84,24 @@ __device__ __forceinline__ uint32_t blend2(uint32_t a, uint32_t b, uint32_t c, u
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// Bilinear blend of two packed bf16 channels from the 4 corners (.cu:49), fp32 arithmetic, one bf16x2 result.
+__device__ __forceinline__ uint32_t blend2(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint64_t w1, uint64_t w2, uint64_t w3, uint64_t w4)
+{
+    uint64_t acc = mul2(w1, unpack_bf16x2(a));
+    acc = fma2(w2, unpack_bf16x2(b), acc);
+    acc = fma2(w3, unpack_bf16x2(c), acc);
+    acc = fma2(w4, unpack_bf16x2(d), acc);
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc));
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 
-constexpr int DF_PRODUCER_WARPS = 8;
+constexpr int DF_PRODUCER_WARPS = 16;
 constexpr int DF_THREADS = (DF_PRODUCER_WARPS + 2) * 32;
 
-template <int NMAX>
+template <int NMAX, bool F2>
 __global__ void __launch_bounds__(DF_THREADS, 1) deform_head_kernel(const __grid_constant__ CUtensorMap tmB0,
                                                                  const __grid_constant__ CUtensorMap tmB1, const DeformP p)
 {
@@ -89,9 +130,10 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform_head_kernel(const __grid
     }
     if (warp == DF_PRODUCER_WARPS + 1) tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
 
-    // ---- per-tile sampling geometry cache: one 12-byte entry per (row, head, tap, deformable group) ----------
-    //   word0 = pixel index of the (low,low) corner | dx << 28 | dy << 29 | inside << 30 ; word1 = lh ; word2 = lw
-    unsigned *geo = (unsigned *)(tiles + Cfg::STAGES * Cfg::STAGE_BYTES);
+    // ---- per-tile sampling geometry cache: one 16-byte entry per (row, head, tap, deformable group) ----------
+    //   x = byte offset of the (low,low) corner pixel in feat | dx << 30 | dy << 31
+    //   y = in * (1 - lh), z = in * lh, w = lw      (in = 0 when the sample lies outside the map, .cu:197)
+    uint4 *geo = (uint4 *)(tiles + p.stages * Cfg::STAGE_BYTES);
     for (int e = threadIdx.x; e < 128 * p.geo_per_row; e += DF_THREADS) {
         const int r = e / p.geo_per_row, gi = e - r * p.geo_per_row;
         const int head = gi >= p.taps[0] * p.dg ? 1 : 0;
@@ -118,10 +160,13 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform_head_kernel(const __grid
         const float lh = h - (float)h_low, lw = w - (float)w_low;
         const int ya = min(max(y0 + h_low, 0), p.H - 1), yb = min(max(y0 + h_high, 0), p.H - 1);
         const int xa = min(max(x0 + w_low, 0), p.W - 1), xb = min(max(x0 + w_high, 0), p.W - 1);
-        const unsigned base = (unsigned)(rb * HW + ya * p.W + xa);
-        geo[(size_t)e * 3 + 0] = inside ? (base | ((unsigned)(xb - xa) << 28) | ((unsigned)(yb - ya) << 29) | (1u << 30)) : 0u;
-        geo[(size_t)e * 3 + 1] = __float_as_uint(lh);
-        geo[(size_t)e * 3 + 2] = __float_as_uint(lw);
+        const unsigned base = (unsigned)(rb * HW + ya * p.W + xa) * (unsigned)(p.Cin * 2);
+        uint4 ent;
+        ent.x = inside ? (base | ((unsigned)(xb - xa) << 30) | ((unsigned)(yb - ya) << 31)) : 0u;
+        ent.y = __float_as_uint(inside ? 1.f - lh : 0.f);
+        ent.z = __float_as_uint(inside ? lh : 0.f);
+        ent.w = __float_as_uint(lw);
+        geo[e] = ent;
     }
     tc_fence_before();
     __syncthreads();
@@ -132,55 +177,69 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform_head_kernel(const __grid
         // ===================== A producers: bilinear-sampled im2col straight into smem =====================
         // k-blocks run channel-block-major (cb, tap): all taps of one 64-channel slab are sampled back to
         // back, so the slab's footprint (tile rows +- kernel radius +- offsets, ~50 KB) stays L1-resident.
-        const int sub = lane >> 3, chunk = lane & 7;       // 4 rows per pass, 8 x 16B chunks per row
+        // 16 warps x 32 lanes; per k-block a lane produces the 16-byte channel chunk `chunk` of two tile rows.  The
+        // 8 lanes of a quarter-warp cover one row's whole 128-byte line, so every corner read is ONE L1 wavefront
+        // per quarter-warp (a full line) and the swizzled 16-byte stores are bank-conflict free.
+        const int chunk = lane & 7, sub = lane >> 3;
         const int blocks_per_group = p.cpg >> 6;
-        int kb = 0;
+        const int r0 = warp * 8 + sub, r1 = r0 + 4;
+        const uint32_t geo_s = smem_u32(geo);
+        const uint32_t geo_row0 = geo_s + (uint32_t)r0 * (uint32_t)p.geo_per_row * 16u;
+        const uint32_t geo_row1 = geo_s + (uint32_t)r1 * (uint32_t)p.geo_per_row * 16u;
+        const uint32_t tiles_s = smem_u32(tiles);
+        const uint32_t st_off0 = sw128_offset(r0, chunk), st_off1 = sw128_offset(r1, chunk);
+        const char *fbytes = (const char *)p.feat;
+        const uint32_t cin2 = (uint32_t)p.Cin * 2u, row2 = (uint32_t)p.W * cin2;
+        uint32_t s = 0, ph = 1;                                  // ring stage and the parity empty_bar[s] must have passed
         for (int head = 0; head < 2; ++head) {
             const int taps = p.taps[head];
-            const int gbase = head ? p.taps[0] * p.dg : 0;
+            const uint32_t gstep = (uint32_t)p.dg * 16u;
             for (int cb = 0; cb < (taps ? cblocks : 0); ++cb) {
                 const int g = cb / blocks_per_group;
-                const __nv_bfloat16 *fb = p.feat + (cb << 6) + (chunk << 3);
-                for (int tap = 0; tap < taps; ++tap, ++kb) {
-                    const int gi = gbase + tap * p.dg + g;
-                    // geometry of my 4 (row, chunk) slots from the per-tile cache; 16 independent 16-byte loads in flight
-                    uint4 cv[4][4];
-                    float lh[4], lw[4];
-                    unsigned fl[4];
+                uint32_t goff = (uint32_t)((head ? p.taps[0] * p.dg : 0) + g) * 16u;
+                const uint32_t lane_off = (uint32_t)(cb << 7) + (uint32_t)(chunk << 4);
+                for (int tap = 0; tap < taps; ++tap, goff += gstep) {
+                    uint4 cv[2][4];                      // 2 rows x 4 corners: 8 independent 16-byte loads in flight
+                    float f[2][4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = warp * 16 + i * 4 + sub;
-                        const unsigned *ge = geo + ((size_t)r * p.geo_per_row + gi) * 3;
-                        const unsigned w0 = ge[0];
-                        lh[i] = __uint_as_float(ge[1]); lw[i] = __uint_as_float(ge[2]); fl[i] = w0;
-                        const int base = (int)(w0 & 0x0fffffffu);
-                        const int dx = (w0 >> 28) & 1u, dy = ((w0 >> 29) & 1u) ? p.W : 0;
-                        const __nv_bfloat16 *pa = fb + (long long)base * p.Cin;
-                        cv[i][0] = __ldg((const uint4 *)pa);
-                        cv[i][1] = __ldg((const uint4 *)(pa + (long long)dx * p.Cin));
-                        cv[i][2] = __ldg((const uint4 *)(pa + (long long)dy * p.Cin));
-                        cv[i][3] = __ldg((const uint4 *)(pa + (long long)(dy + dx) * p.Cin));
+                    for (int i = 0; i < 2; ++i) {
+                        uint32_t e0, e1, e2, e3;
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3) : "r"((i ? geo_row1 : geo_row0) + goff));
+                        const uint32_t oa = (e0 & 0x3fffffffu) + lane_off;
+                        const uint32_t dxb = (uint32_t)((int32_t)(e0 << 1) >> 31) & cin2;
+                        const uint32_t dyb = (uint32_t)((int32_t)e0 >> 31) & row2;
+                        const uint32_t oc = oa + dyb;
+                        cv[i][0] = __ldg((const uint4 *)(fbytes + oa));
+                        cv[i][1] = __ldg((const uint4 *)(fbytes + (oa + dxb)));
+                        cv[i][2] = __ldg((const uint4 *)(fbytes + oc));
+                        cv[i][3] = __ldg((const uint4 *)(fbytes + (oc + dxb)));
+                        const float hh = __uint_as_float(e1), lh = __uint_as_float(e2), lw = __uint_as_float(e3), hw = 1.f - lw;
+                        f[i][0] = hh * hw; f[i][1] = hh * lw; f[i][2] = lh * hw; f[i][3] = lh * lw;      // .cu:47 (x inside flag)
                     }
-                    const int s = kb % Cfg::STAGES;
-                    const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
-                    mbar_wait(&empty_bar[s], ph ^ 1u);
-                    uint8_t *sa = tiles + s * Cfg::STAGE_BYTES;
+                    mbar_wait(&empty_bar[s], ph);
+                    const uint32_t sa = tiles_s + s * (uint32_t)Cfg::STAGE_BYTES;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = warp * 16 + i * 4 + sub;
-                        const float in = ((fl[i] >> 30) & 1u) ? 1.f : 0.f;       // 0: sample outside the map (.cu:197)
-                        const float hh = 1.f - lh[i], hw = 1.f - lw[i];
-                        const float w1 = in * hh * hw, w2 = in * hh * lw[i], w3 = in * lh[i] * hw, w4 = in * lh[i] * lw[i];
-                        uint4 o;                                                 // .cu:49, two channels per 32-bit lane
-                        o.x = blend2(cv[i][0].x, cv[i][1].x, cv[i][2].x, cv[i][3].x, w1, w2, w3, w4);
-                        o.y = blend2(cv[i][0].y, cv[i][1].y, cv[i][2].y, cv[i][3].y, w1, w2, w3, w4);
-                        o.z = blend2(cv[i][0].z, cv[i][1].z, cv[i][2].z, cv[i][3].z, w1, w2, w3, w4);
-                        o.w = blend2(cv[i][0].w, cv[i][1].w, cv[i][2].w, cv[i][3].w, w1, w2, w3, w4);
-                        *(uint4 *)(sa + sw128_offset(r, chunk)) = o;
+                    for (int i = 0; i < 2; ++i) {
+                        uint32_t o0, o1, o2, o3;                             // .cu:49, two channels per 32-bit lane
+                        if (F2) {
+                            const uint64_t w1 = pair_of(f[i][0], f[i][0]), w2 = pair_of(f[i][1], f[i][1]);
+                            const uint64_t w3 = pair_of(f[i][2], f[i][2]), w4 = pair_of(f[i][3], f[i][3]);
+                            o0 = blend2(cv[i][0].x, cv[i][1].x, cv[i][2].x, cv[i][3].x, w1, w2, w3, w4);
+                            o1 = blend2(cv[i][0].y, cv[i][1].y, cv[i][2].y, cv[i][3].y, w1, w2, w3, w4);
+                            o2 = blend2(cv[i][0].z, cv[i][1].z, cv[i][2].z, cv[i][3].z, w1, w2, w3, w4);
+                            o3 = blend2(cv[i][0].w, cv[i][1].w, cv[i][2].w, cv[i][3].w, w1, w2, w3, w4);
+                        } else {
+                            o0 = blend2s(cv[i][0].x, cv[i][1].x, cv[i][2].x, cv[i][3].x, f[i][0], f[i][1], f[i][2], f[i][3]);
+                            o1 = blend2s(cv[i][0].y, cv[i][1].y, cv[i][2].y, cv[i][3].y, f[i][0], f[i][1], f[i][2], f[i][3]);
+                            o2 = blend2s(cv[i][0].z, cv[i][1].z, cv[i][2].z, cv[i][3].z, f[i][0], f[i][1], f[i][2], f[i][3]);
+                            o3 = blend2s(cv[i][0].w, cv[i][1].w, cv[i][2].w, cv[i][3].w, f[i][0], f[i][1], f[i][2], f[i][3]);
+                        }
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sa + (i ? st_off1 : st_off0)), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
                     }
                     fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&full_bar[s]);
+                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -188,8 +247,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform_head_kernel(const __grid
         // ===================== weight (B operand) TMA producer =====================
         if (lane == 0) {
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % Cfg::STAGES;
-                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 uint8_t *sb = tiles + s * Cfg::STAGE_BYTES + Cfg::A_BYTES;
                 mbar_expect_tx(&full_bar[s], p.b_bytes);
@@ -203,8 +262,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform_head_kernel(const __grid
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(128, p.n_pad16);
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % Cfg::STAGES;
-                const uint32_t ph = (uint32_t)(kb / Cfg::STAGES) & 1u;
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(tiles + s * Cfg::STAGE_BYTES);
@@ -269,17 +328,21 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform_head_kernel(const __grid
     }
 }
 
-template <int NMAX>
+template <int NMAX, bool F2>
 static int launch_deform(const CUtensorMap &t0, const CUtensorMap &t1, const DeformP &p, cudaStream_t st)
 {
     using Cfg = DfCfg<NMAX>;
-    const size_t smem = (size_t)Cfg::SMEM_STAGES_BYTES + (size_t)128 * p.geo_per_row * 12;
+    const size_t geo_bytes = (size_t)128 * p.geo_per_row * 16;
+    DeformP q = p;
+    q.stages = Cfg::STAGES;
+    size_t smem = (size_t)q.stages * Cfg::STAGE_BYTES + 1024 + geo_bytes;
+    if (smem > 227 * 1024) { q.stages = 2; smem = (size_t)q.stages * Cfg::STAGE_BYTES + 1024 + geo_bytes; }
     if (smem > 227 * 1024) {
         set_error("tdrn_deform_head: geometry cache does not fit (%zu bytes of shared memory needed)", smem);
         return TDRN_EUNSUPPORTED;
     }
-    TDRN_CUDA(cudaFuncSetAttribute(deform_head_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    deform_head_kernel<NMAX><<<(p.M + 127) / 128, DF_THREADS, smem, st>>>(t0, t1, p);
+    TDRN_CUDA(cudaFuncSetAttribute(deform_head_kernel<NMAX, F2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    deform_head_kernel<NMAX, F2><<<(p.M + 127) / 128, DF_THREADS, smem, st>>>(t0, t1, q);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }
@@ -330,5 +393,7 @@ extern "C" int tdrn_deform_head(const tdrn_deform_head_desc *d, const void *feat
         if (rc) return rc;
     }
     cudaStream_t st = as_stream(stream);
-    return nmax == 256 ? launch_deform<256>(t0, t1, p, st) : launch_deform<128>(t0, t1, p, st);
+    static const bool f2 = getenv("TDRN_DEFORM_SCALAR_BLEND") == nullptr;   // default: packed fp32x2 (FFMA2) blend
+    if (f2) return nmax == 256 ? launch_deform<256, true>(t0, t1, p, st) : launch_deform<128, true>(t0, t1, p, st);
+    return nmax == 256 ? launch_deform<256, false>(t0, t1, p, st) : launch_deform<128, false>(t0, t1, p, st);
 }

@@ -153,3 +153,28 @@ def test_deform_head_tc_vs_oracle(B, H, W, cin, C, dg, multihead):
                     softmax=True)
     sm = torch.softmax(conf[:, poff:poff + H * W * 3], -1)
     assert rel_err(conf2[:, poff:poff + H * W * 3].cpu().numpy(), sm.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize('b,h,w,relu', [
+    (2, 8, 64, True),          # 64x2 tiles, one tile row per image pair
+    (3, 20, 96, True),         # 32x4 tiles
+    (1, 24, 48, False),        # 16x8 tiles, negative outputs kept
+    (5, 64, 128, True),        # 640 tiles > 2 x #SMs: persistent loop wraps, both TMEM/staging buffers reused
+    (1, 10, 20, True),         # does not tile -> CUDA-core stem (same result contract)
+])
+def test_conv_stem_tc_vs_fp32(b, h, w, relu):
+    """conv1_1 as a K=32 tcgen05 GEMM (csrc/conv_stem_tc.cu): fp32 NCHW image in, NHWC bf16 out, bias+ReLU fused.
+    Reference: fp32 conv of the bf16-rounded image and weights (the MMA operands); 4e-3 = bf16 output rounding."""
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(b * 100 + h + w)
+    x = torch.randn(b, 3, h, w, generator=g)
+    wt = torch.randn(64, 3, 3, 3, generator=g) * 0.3
+    bias = torch.randn(64, generator=g)
+    ref = F.conv2d(_bf(x), _bf(wt), bias, 1, 1)
+    if relu:
+        ref = F.relu(ref)
+    pc = ops.PackedConv(wt, bias, None, 1, 1, 1, device='cuda', want_bf16=False)
+    out = ops.conv_first(x.cuda(), pc, relu, torch.bfloat16)
+    assert out.shape == (b, h, w, 64) and out.dtype == torch.bfloat16
+    tol = 4e-3 if (w % 16 == 0 and h % 2 == 0) else 8e-3      # the CUDA-core fallback multiplies un-rounded fp32 operands
+    assert rel_err(_nchw(out.float()).cpu().numpy(), ref.numpy()) < tol
