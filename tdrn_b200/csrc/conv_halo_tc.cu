@@ -1,0 +1,285 @@
+// conv_halo_tc.cu -- 3x3 / stride 1 / pad 1 implicit-GEMM convolution for the high-resolution, narrow layers
+// (VGG conv1_2 64->64 @320^2, conv2_1 64->128 @160^2; model/networks.py:136-163) on tcgen05, with
+//   * ONE shared-memory halo tile per (output tile, 64-channel block): a 4-D TMA box of 10 x 18 input pixels
+//     (8 x 16 outputs + the 3x3 halo, zero padding = TMA out-of-bounds fill).  The nine taps are nine UMMA
+//     A-descriptors into that same tile: start address shifted by (r*10 + s) 128-byte rows, stride between
+//     8-row core-matrix groups (SBO) = 10 rows = 1280 B.  The 128B swizzle is a function of the absolute
+//     shared-memory address on this hardware (scripts/umma_probe.py), so shifted / 1280-strided views read
+//     exactly what TMA wrote.  Compared with one box per tap (conv_tc.cu) the A operand crosses L2->SM once
+//     instead of nine times;
+//   * the whole weight tensor RESIDENT in shared memory (9 taps x Cin/64 blocks x Cout rows x 128 B, loaded
+//     once per persistent CTA), so the steady-state L2->SM traffic is 23 KB per 128-pixel tile.
+// conv_tc.cu's generic kernel moved 9 x (16 KB + Cout x 128 B) per tile and was L2-bandwidth bound on these
+// layers (385 TFLOP/s on conv1_2); here the tensor pipe / epilogue are the limit.
+// Warp roles: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-9 epilogue (two per TMEM lane
+// quadrant; bias, ReLU, optional fused 2x2 max-pool by warp shuffles, bf16/fp32 store); TMEM accumulator double-buffered.
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace tdrn {
+namespace tc {
+
+constexpr int HL_BW = 8, HL_BH = 16;                 // output tile
+constexpr int HL_PW = HL_BW + 2, HL_PH = HL_BH + 2;  // halo tile (pixels)
+constexpr int HL_A_BYTES = HL_PW * HL_PH * 128;      // 23040
+constexpr int HL_A_STRIDE = (HL_A_BYTES + 1023) & ~1023;
+constexpr int HL_THREADS = 320;                     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int HL_MAX_STAGES = 4;
+
+struct HaloP {
+    int H, W, B;
+    int tiles_w, tiles_h, total;
+    int Cin, cblocks, Cout, n_pad16;
+    int stages;
+    uint32_t w_bytes;            // resident weight bytes = 9 * cblocks * n_pad16 * 128
+    const float *bias; void *out;
+    long long out_sb, out_sp; int out_w;
+    int relu, out_f32, pool;
+    int debug_skip_epilogue;     // timing experiments only (TDRN_HALO_DEBUG=1): results are NOT written
+};
+
+// SWIZZLE_128B K-major descriptor with an arbitrary (16-byte aligned) start and stride between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB, const HaloP p)
+{
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t a_full[HL_MAX_STAGES], a_empty[HL_MAX_STAGES];
+    __shared__ __align__(8) uint64_t t_full[2], t_empty[2], w_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_bias[BN];
+
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    uint8_t *sW = base;                               // [9*cblocks][n_pad16 rows][128 B]
+    uint8_t *sA = base + p.w_bytes;                   // stages x HL_A_STRIDE (w_bytes is a multiple of 2048)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    const uint32_t kb_bytes = (uint32_t)p.n_pad16 * 128u;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 8); }
+        mbar_init(&w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, 2 * BN);
+    for (int i = threadIdx.x; i < BN; i += HL_THREADS) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(&w_bar, p.w_bytes);
+            for (int kb = 0; kb < 9 * p.cblocks; ++kb) tma_load_2d(sW + (size_t)kb * kb_bytes, &tmB, &w_bar, kb * 64, 0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x) {
+                const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+                const int y0 = (rem / p.tiles_w) * HL_BH - 1, x0 = (rem % p.tiles_w) * HL_BW - 1;
+                for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
+                    const uint32_t s = it % (uint32_t)p.stages, ph = (it / (uint32_t)p.stages) & 1u;
+                    mbar_wait(&a_empty[s], ph ^ 1u);
+                    mbar_expect_tx(&a_full[s], HL_A_BYTES);
+                    tma_load_4d(sA + (size_t)s * HL_A_STRIDE, &tmA, &a_full[s], cb * 64, x0, y0, b);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, p.n_pad16);
+            mbar_wait(&w_bar, 0);
+            tc_fence_after();
+            const uint32_t sW_u = smem_u32(sW), sA_u = smem_u32(sA);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++tcount) {
+                const uint32_t buf = tcount & 1u;
+                mbar_wait(&t_empty[buf], ((tcount >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BN;
+                for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
+                    const uint32_t s = it % (uint32_t)p.stages, ph = (it / (uint32_t)p.stages) & 1u;
+                    mbar_wait(&a_full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a0 = sA_u + s * (uint32_t)HL_A_STRIDE;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int tr = tap / 3, ts = tap - tr * 3;
+                        const uint64_t adesc = umma_desc_sw128_sbo(a0 + (uint32_t)(tr * HL_PW + ts) * 128u, HL_PW * 128u);
+                        const uint64_t bdesc = umma_desc_sw128(sW_u + (uint32_t)(tap * p.cblocks + cb) * kb_bytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cb | tap | k) != 0);
+                    }
+                    umma_commit(&a_empty[s]);
+                }
+                umma_commit(&t_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (warps 2..9) =====================
+        // Two warps per TMEM lane quadrant (hardware rule: a warp reads lanes 32*(warp%4)..+31); they split the
+        // accumulator's 32-column chunks between them.  bf16 outputs are packed BEFORE the 2x2 max-pool, so the
+        // pool is 2 shuffles + 2 packed max per channel PAIR (rounding is monotonic: max commutes with it).
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int r = quad * 32 + lane;
+        const int wl = r & (HL_BW - 1), hl = r >> 3;
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++tcount) {
+            const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+            const int x = (rem % p.tiles_w) * HL_BW + wl, y = (rem / p.tiles_w) * HL_BH + hl;
+            const bool valid = x < p.W && y < p.H;
+            const uint32_t buf = tcount & 1u;
+            mbar_wait(&t_full[buf], (tcount >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
+            for (int c0 = half * 32; c0 < (p.debug_skip_epilogue ? 0 : p.n_pad16); c0 += 64) {
+                float v[32];
+                tmem_ld32(trow + (uint32_t)c0, v);
+                if (c0 >= p.Cout) continue;                          // warp-uniform
+                const int nv = min(32, p.Cout - c0);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bq = *(const float4 *)(s_bias + c0 + j);
+                    v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                bool store = valid;
+                int oy = y, ox = x;
+                if (p.pool) { store = valid && !(wl & 1) && !(hl & 1); oy = y >> 1; ox = x >> 1; }
+                const long long o = (long long)b * p.out_sb + ((long long)oy * p.out_w + ox) * p.out_sp + c0;
+                if (p.out_f32) {
+                    if (p.pool) {
+                        // MaxPool2d(2,2): the 2x2 partners of pixel (hl, wl) are lanes ^1 and ^8 of this warp
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                            v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, HL_BW));
+                        }
+                    }
+                    if (!store) continue;
+                    float *op = (float *)p.out + o;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (j < nv) op[j] = v[j];
+                } else {
+                    uint32_t q[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        q[j] = *(const uint32_t *)&h2;
+                    }
+                    if (p.pool) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            uint32_t o1 = __shfl_xor_sync(0xffffffffu, q[j], 1);
+                            __nv_bfloat162 m = __hmax2(*(const __nv_bfloat162 *)&q[j], *(const __nv_bfloat162 *)&o1);
+                            uint32_t mw = *(const uint32_t *)&m;
+                            uint32_t o2 = __shfl_xor_sync(0xffffffffu, mw, HL_BW);
+                            m = __hmax2(m, *(const __nv_bfloat162 *)&o2);
+                            q[j] = *(const uint32_t *)&m;
+                        }
+                    }
+                    if (!store) continue;
+                    __nv_bfloat16 *op = (__nv_bfloat16 *)p.out + o;
+                    if (nv == 32 && ((o & 7) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ((uint4 *)op)[j] = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+                    } else {
+                        const __nv_bfloat16 *qb = (const __nv_bfloat16 *)q;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < nv) op[j] = qb[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
+}
+
+static int g_halo_sms = 0;
+
+template <int BN>
+static int launch_halo(const CUtensorMap &tmA, const CUtensorMap &tmB, const HaloP &p, size_t smem, cudaStream_t st)
+{
+    TDRN_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_halo_kernel<BN><<<p.total < g_halo_sms ? p.total : g_halo_sms, HL_THREADS, smem, st>>>(tmA, tmB, p);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
+// Returns TDRN_EUNSUPPORTED when the layer does not fit this kernel (the caller then uses the generic conv_tc path).
+int conv_halo_try(const tdrn_conv_desc *d, const void *in, const void *weight, const float *bias, const void *residual,
+                  void *out, cudaStream_t st)
+{
+    if (d->deconv2x2 || d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != 1 || d->dil != 1 || residual ||
+        d->Cin % 64 != 0 || d->Cout > 128 || d->in_sb != 0)
+        return TDRN_EUNSUPPORTED;
+    if (d->W % HL_BW != 0 || d->H % HL_BH != 0) return TDRN_EUNSUPPORTED;      // exact tiling only (40x40 and below stay generic)
+    HaloP p{};
+    p.H = d->H; p.W = d->W; p.B = d->B; p.Cin = d->Cin; p.cblocks = d->Cin / 64; p.Cout = d->Cout;
+    p.n_pad16 = (d->Cout + 15) & ~15;
+    p.w_bytes = 9u * (uint32_t)p.cblocks * (uint32_t)p.n_pad16 * 128u;
+    const size_t budget = 225 * 1024;
+    int stages = HL_MAX_STAGES;
+    while (stages >= 2 && 1024 + (size_t)p.w_bytes + (size_t)stages * HL_A_STRIDE > budget) --stages;
+    if (stages < 2) return TDRN_EUNSUPPORTED;                                   // weights too large to stay resident
+    p.stages = stages;
+    p.tiles_w = d->W / HL_BW; p.tiles_h = d->H / HL_BH; p.total = p.tiles_w * p.tiles_h * d->B;
+    p.bias = bias; p.out = out; p.out_sb = d->out_sb; p.out_sp = d->out_sp;
+    p.relu = d->relu; p.out_f32 = d->out_dtype == TDRN_F32; p.pool = d->pool2x2;
+    p.out_w = p.pool ? d->W / 2 : d->W;
+    { static const bool dbg = getenv("TDRN_HALO_DEBUG") != nullptr; p.debug_skip_epilogue = dbg; }
+    if (!g_halo_sms) {
+        int dev = 0;
+        TDRN_CUDA(cudaGetDevice(&dev));
+        TDRN_CUDA(cudaDeviceGetAttribute(&g_halo_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    CUtensorMap tmA, tmB;
+    {
+        const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        const uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+        const uint32_t box[4] = {64, HL_PW, HL_PH, 1};
+        int rc = make_tmap_bf16(&tmA, in, 4, dims, str, box, nullptr);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t K = 9ull * d->Cin;
+        const uint64_t dims[2] = {K, (uint64_t)p.n_pad16};
+        const uint64_t str[1] = {K * 2};
+        const uint32_t box[2] = {64, (uint32_t)p.n_pad16};
+        int rc = make_tmap_bf16(&tmB, weight, 2, dims, str, box, nullptr);
+        if (rc) return rc;
+    }
+    const size_t smem = 1024 + (size_t)p.w_bytes + (size_t)stages * HL_A_STRIDE;
+    return p.n_pad16 > 64 ? launch_halo<128>(tmA, tmB, p, smem, st) : launch_halo<64>(tmA, tmB, p, smem, st);
+}
+
+}  // namespace tc
+}  // namespace tdrn

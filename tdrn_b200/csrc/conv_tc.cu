@@ -22,6 +22,7 @@
 // main loop of tile i+1; the smem ring is 192 KB deep so TMA latency is hidden even when a layer has
 // fewer tiles than SMs (the 10x10 / 5x5 pyramid levels).
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace tdrn {
 namespace tc {
@@ -300,6 +301,11 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcCon
 }  // namespace tc
 }  // namespace tdrn
 
+namespace tdrn { namespace tc {
+int conv_halo_try(const tdrn_conv_desc *d, const void *in, const void *weight, const float *bias, const void *residual,
+                  void *out, cudaStream_t st);      // conv_halo_tc.cu
+} }
+
 using namespace tdrn;
 using namespace tdrn::tc;
 
@@ -312,6 +318,13 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         set_error("tdrn_conv2d_tc: needs bf16 input, Cin %% 64 == 0, stride 1 or 2, no offsets (got dtype=%d Cin=%d stride=%d dg=%d)",
                   d->in_dtype, d->Cin, d->stride, d->dg);
         return TDRN_EUNSUPPORTED;
+    }
+    {   // narrow high-resolution 3x3 layers: halo tile + resident weights (conv_halo_tc.cu)
+        static const bool no_halo = getenv("TDRN_NO_HALO") != nullptr;
+        if (!no_halo) {
+            const int rc = conv_halo_try(d, in, weight, bias, residual, out, as_stream(stream));
+            if (rc != TDRN_EUNSUPPORTED) return rc;
+        }
     }
     TcConvP p{};
     const int kh = d->deconv2x2 ? 1 : d->kh, kw = d->deconv2x2 ? 1 : d->kw;

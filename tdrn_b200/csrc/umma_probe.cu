@@ -1,0 +1,141 @@
+// umma_probe.cu -- development probe (not part of the public ABI): which shared-memory bytes does a
+// SWIZZLE_128B K-major UMMA A-descriptor read when its start address is not 1024-byte aligned and/or its
+// stride-byte-offset (SBO) is not a multiple of 1024?  The halo-tile convolution (conv_tc.cu) addresses the
+// nine taps of a 3x3 kernel as row-shifted views of ONE shared-memory tile and depends on the answer.
+//
+// Smem rows (128 B = 64 bf16) are filled in the layout TMA SWIZZLE_128B produces (16-byte chunk c of absolute
+// row R stored at chunk position c ^ (R & 7)); value = R (mode 0) or k (mode 1).  B = 64x64 identity, so
+// D[m][n] = A[m][n] and the output reveals the (row, column) every A element was fetched from.
+#include "tc_common.cuh"
+
+namespace tdrn {
+namespace tc {
+
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(float *out, int r0, int sbo_bytes, int base_offset, int mode, int rows)
+{
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base;                        // rows x 128 B
+    uint8_t *sB = base + ((rows * 128 + 1023) & ~1023);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < rows * 64; e += 128) {
+        const int R = e >> 6, k = e & 63;
+        const float v = mode == 0 ? (float)R : (float)k;
+        *(__nv_bfloat16 *)(sA + R * 128 + (((k >> 3) ^ (R & 7)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(v);
+    }
+    for (int e = tid; e < 64 * 64; e += 128) {
+        const int n = e >> 6, k = e & 63;
+        *(__nv_bfloat16 *)(sB + n * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(n == k ? 1.f : 0.f);
+    }
+    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 64);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t a_addr = smem_u32(sA) + (uint32_t)r0 * 128u;
+        uint64_t ad = 0;
+        ad |= (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+        ad |= (uint64_t)1 << 16;
+        ad |= (uint64_t)((uint32_t)sbo_bytes >> 4) << 32;
+        ad |= (uint64_t)1 << 46;
+        ad |= (uint64_t)(base_offset & 7) << 49;
+        ad |= (uint64_t)2 << 61;
+        const uint64_t bd = umma_desc_sw128(smem_u32(sB));
+        const uint32_t idesc = umma_idesc_bf16(128, 64);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, k != 0);
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        tmem_ld16(trow + (uint32_t)c0, v);
+        for (int j = 0; j < 16; ++j) out[tid * 64 + c0 + j] = v[j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+}
+
+}  // namespace tc
+}  // namespace tdrn
+
+using namespace tdrn;
+using namespace tdrn::tc;
+
+// out: device [128][64] fp32.  Synchronous.  Development aid (scripts/umma_probe.py), not declared in the header.
+extern "C" int tdrn_debug_umma_probe(float *out, int r0, int sbo_bytes, int base_offset, int mode, int rows)
+{
+    TDRN_REQUIRE(out && rows > 0 && rows <= 512, "umma probe: bad argument");
+    const int smem = ((rows * 128 + 1023) & ~1023) + 64 * 128 + 1024;
+    TDRN_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma_probe_kernel<<<1, 128, smem>>>(out, r0, sbo_bytes, base_offset, mode, rows);
+    TDRN_LAUNCH_CHECK();
+    TDRN_CUDA(cudaDeviceSynchronize());
+    return TDRN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// MMA issue-rate probe: every CTA issues `iters` groups of 4 x (M=128, N=n, K=16) tcgen05.mma on smem-resident
+// operands (no TMA, no epilogue), alternating between `nacc` TMEM accumulators, and reports clock64 cycles.
+// Answers "what can the tensor pipe sustain for narrow N tiles" (the bound of conv_halo_tc.cu's main loop).
+// ---------------------------------------------------------------------------------------------------------
+namespace tdrn {
+namespace tc {
+
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(long long *cycles, int n, int iters, int nacc, int a_shift_rows)
+{
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base;                        // 24 KB
+    uint8_t *sB = base + 24 * 1024;            // 256 x 128 B
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < (24 * 1024 + 32 * 1024) / 4; e += 128) ((uint32_t *)base)[e] = 0x3c003c00u;
+    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = umma_idesc_bf16(128, n);
+        const uint64_t bd = umma_desc_sw128(smem_u32(sB));
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const uint32_t a_addr = smem_u32(sA) + (uint32_t)((i % 9) * a_shift_rows) * 128u;
+            const uint64_t ad = umma_desc_sw128(a_addr);
+            const uint32_t d = tmem_base + (uint32_t)((i % nacc) * n);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, 1u);
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        cycles[blockIdx.x] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace tc
+}  // namespace tdrn
+
+extern "C" int tdrn_debug_umma_rate(long long *cycles_dev, int grid, int n, int iters, int nacc, int a_shift_rows)
+{
+    TDRN_REQUIRE(cycles_dev && grid > 0 && n >= 16 && n <= 256 && n % 16 == 0 && nacc >= 1 && nacc * n <= 512, "umma rate: bad argument");
+    const int smem = 24 * 1024 + 32 * 1024 + 1024;
+    TDRN_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma_rate_kernel<<<grid, 128, smem>>>(cycles_dev, n, iters, nacc, a_shift_rows);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}

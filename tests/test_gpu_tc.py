@@ -35,6 +35,9 @@ def _bf(x):
     (4, 64, 64, 3, 1, 1, 96, 96, True),        # 288 tiles > #SMs: persistent loop, both TMEM buffers, ring wrap
     (8, 128, 512, 3, 1, 1, 40, 40, True),      # 224 (m,n) tiles, BN=256
     (5, 64, 128, 3, 1, 1, 48, 48, False),      # BN=128, 6-stage ring
+    (2, 128, 32, 3, 1, 1, 32, 24, True),       # halo kernel: two resident channel blocks, Cout < 64
+    (1, 64, 48, 3, 1, 1, 16, 8, False),        # halo kernel: a single 8x16 tile, Cout = 48 (three 16-column chunks)
+    (3, 64, 128, 3, 1, 1, 64, 64, True),       # halo kernel BN=128 (conv2_1 class), 96 tiles
 ])
 def test_conv_tc_vs_fp32(b, cin, cout, k, pad, dil, h, w, relu):
     from tdrn_b200 import ops
