@@ -4,8 +4,9 @@
 // The layer is 0.35 GFLOP/frame but writes the largest activation of the network (B x 320 x 320 x 64 bf16 =
 // 419 MB at b32), so it is HBM-write bound; the CUDA-core version (conv_first.cu) was FMA-issue bound at ~0.9 TB/s.
 // Here the 27-tap dot product runs as a K = 32 (27 + zero pad) tcgen05 GEMM:
-//   A [128 pixels x 32] bf16 : im2col rows built by 4 producer warps from a fp32 NCHW patch staged in shared
-//                              memory (the reference's input layout is read directly, no layout/cast pass),
+//   A [128 pixels x 32] bf16 : im2col rows built by 4 producer warps from a fp32 NCHW patch that a 4-deep TMA
+//                              ring stages in shared memory (3-D boxes of the reference's own input layout; the
+//                              conv zero padding is the TMA out-of-bounds fill; no layout/cast pass),
 //                              written in the 128B-swizzled K-major UMMA layout (logical chunks 0..3 of each row);
 //   B [64 couts x 32]   bf16 : converted once per CTA from the packed fp32 weights [27][64];
 //   D [128 x 64] fp32 in TMEM, double buffered; 4 epilogue warps add bias, ReLU, cast to bf16 into a swizzled
@@ -13,6 +14,7 @@
 //   so the NHWC output is written as full 128-byte lines.
 // Persistent grid (2 CTAs per SM), tile = bw x bh output pixels of one image (64x2, 32x4 or 16x8).
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace tdrn {
 namespace tc {
@@ -22,15 +24,15 @@ struct StemP {
     const float *w;        // [27][64] fp32, k = (i*3+j)*3 + c
     const float *bias;     // [64] or NULL
     int B, H, W;
-    int bw, bh, tiles_w, tiles_h, total;
+    int bw, bh, pw, tiles_w, tiles_h, total;   // pw = patch pitch (bw + halo, padded so that pw*4 B is TMA-legal)
     int relu;
 };
 
-constexpr int ST_THREADS = 288;          // warps 0-3 producers, 4 MMA, 5-8 epilogue
+constexpr int ST_THREADS = 320;          // warps 0-3 producers, 4 MMA, 5-8 epilogue, 9 patch TMA
 constexpr int ST_COUT = 64;
-constexpr int ST_PATCH_MAX = 3 * 4 * 66; // floats; the largest of the three tile shapes (64x2)
-constexpr int ST_PRE = (ST_PATCH_MAX + 127) / 128;
-constexpr int ST_SMEM = 2 * 16384 + 2 * 16384 + 8192 + 2 * ST_PATCH_MAX * 4 + 256 + 1024;
+constexpr int ST_PSTAGES = 4;            // input-patch ring depth (hides HBM latency of the fp32 image reads)
+constexpr int ST_PATCH_BYTES = 4096;     // >= 3 ch x (bh+2) rows x (bw+8) cols x 4 B for the three tile shapes, 128B aligned
+constexpr int ST_SMEM = 2 * 16384 + 2 * 16384 + 8192 + ST_PSTAGES * ST_PATCH_BYTES + 256 + 1024;
 
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *src, int c0, int c1, int c2, int c3)
@@ -48,25 +50,29 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
     return r;
 }
 
-__global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __grid_constant__ CUtensorMap tmO, const StemP p)
+__global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmO, const StemP p)
 {
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2];
+    __shared__ __align__(8) uint64_t p_full[ST_PSTAGES], p_empty[ST_PSTAGES];
     __shared__ uint32_t tmem_base_s;
 
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = base;                                   // 2 x [128 rows][128 B]
     uint8_t *sO = base + 2 * 16384;                       // 2 x [128 rows][128 B] output staging
     uint8_t *sB = base + 4 * 16384;                       // [64 rows][128 B]
-    float *sP = (float *)(base + 4 * 16384 + 8192);       // 2 x patch [3][bh+2][bw+2]
-    float *sBias = sP + 2 * ST_PATCH_MAX;
+    uint8_t *sP = base + 4 * 16384 + 8192;                // ST_PSTAGES x patch [3][bh+2][bw+8] fp32
+    float *sBias = (float *)(sP + ST_PSTAGES * ST_PATCH_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int PH = p.bh + 2, PW = p.bw + 2, PN = 3 * PH * PW;
+    const int PH = p.bh + 2, PW = p.pw;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
 
     if (tid == 0) {
         tma_prefetch_desc(&tmO);
+        tma_prefetch_desc(&tmX);
+#pragma unroll
+        for (int s = 0; s < ST_PSTAGES; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], 1); }
 #pragma unroll
         for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
         fence_barrier_init();
@@ -90,42 +96,15 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp < 4) {
-        // ===================== producers: fp32 NCHW patch -> bf16 im2col rows =====================
-        float pre[ST_PRE];
-        auto load_patch = [&](int tile) {
-            const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
-            const int y0 = (rem / p.tiles_w) * p.bh - 1, x0 = (rem % p.tiles_w) * p.bw - 1;
-            const float *xb = p.x + (long long)b * 3 * p.H * p.W;
-#pragma unroll
-            for (int q = 0; q < ST_PRE; ++q) {
-                const int e = tid + q * 128;
-                float v = 0.f;
-                if (e < PN) {
-                    const int c = e / (PH * PW), r2 = e - c * (PH * PW);
-                    const int py = r2 / PW, px = r2 - py * PW;
-                    const int iy = y0 + py, ix = x0 + px;
-                    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(xb + ((long long)c * p.H + iy) * p.W + ix);
-                }
-                pre[q] = v;
-            }
-        };
-        auto store_patch = [&](int buf) {
-#pragma unroll
-            for (int q = 0; q < ST_PRE; ++q) {
-                const int e = tid + q * 128;
-                if (e < PN) sP[buf * ST_PATCH_MAX + e] = pre[q];
-            }
-        };
-        int tile = blockIdx.x;
-        if (tile < p.total) { load_patch(tile); store_patch(0); }
-        named_bar(1, 128);
+        // ===================== producers: fp32 NCHW patch (TMA ring) -> bf16 im2col rows =====================
         const int wl = tid % p.bw, hl = tid / p.bw;
-        for (uint32_t it = 0; tile < p.total; tile += gridDim.x, ++it) {
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++it) {
             const int s = it & 1;
-            const int next = tile + gridDim.x;
-            if (next < p.total) load_patch(next);                       // global loads in flight during the build
+            const uint32_t ps = it % ST_PSTAGES, pph = (it / ST_PSTAGES) & 1u;
+            mbar_wait(&p_full[ps], pph);
             mbar_wait(&a_empty[s], ((it >> 1) & 1u) ^ 1u);
-            const float *P = sP + s * ST_PATCH_MAX;
+            const float *P = (const float *)(sP + ps * ST_PATCH_BYTES);
             uint32_t kw[16];
 #pragma unroll
             for (int k2 = 0; k2 < 16; ++k2) {
@@ -133,7 +112,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int k = 2 * k2 + h;                           // compile-time after unrolling
-                    if (k < 27) { const int t = k / 3, c = k - t * 3, i = t / 3, j = t - i * 3; v[h] = P[(c * PH + hl + i) * PW + wl + j]; }
+                    if (k < 27) { const int t = k / 3, c = k - t * 3, i = t / 3, j = t - i * 3; v[h] = P[(c * PH + hl + i) * PW + wl + j + 3]; }
                     else v[h] = 0.f;
                 }
                 kw[k2] = pack_bf16x2(v[0], v[1]);
@@ -143,10 +122,8 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
             for (int chunk = 0; chunk < 4; ++chunk)
                 *(uint4 *)(a + sw128_offset(tid, chunk)) = make_uint4(kw[4 * chunk], kw[4 * chunk + 1], kw[4 * chunk + 2], kw[4 * chunk + 3]);
             fence_proxy_async_smem();
-            named_bar(1, 128);                                          // A tile complete, patch[s] fully consumed
-            if (tid == 0) mbar_arrive(&a_full[s]);
-            if (next < p.total) store_patch(s ^ 1);
-            named_bar(1, 128);                                          // patch[s^1] visible to the next build
+            named_bar(1, 128);                                          // A tile complete, patch[ps] fully consumed
+            if (tid == 0) { mbar_arrive(&a_full[s]); mbar_arrive(&p_empty[ps]); }
         }
     } else if (warp == 4) {
         // ===================== MMA issuer =====================
@@ -167,9 +144,23 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
             }
         }
         __syncwarp();
+    } else if (warp == 9) {
+        // ===================== input-patch TMA producer =====================
+        if (lane == 0) {
+            const uint32_t patch_bytes = (uint32_t)(3 * PH * PW * 4);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++it) {
+                const uint32_t ps = it % ST_PSTAGES, pph = (it / ST_PSTAGES) & 1u;
+                const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+                mbar_wait(&p_empty[ps], pph ^ 1u);
+                mbar_expect_tx(&p_full[ps], patch_bytes);
+                tma_load_4d(sP + ps * ST_PATCH_BYTES, &tmX, &p_full[ps], (rem % p.tiles_w) * p.bw - 4, (rem / p.tiles_w) * p.bh - 1, 0, b);
+            }
+        }
+        __syncwarp();
     } else {
         // ===================== epilogue: TMEM -> bias/ReLU/bf16 -> swizzled smem -> TMA store =====================
-        const int et = tid - 160;
+        const int et = tid - 160;                 // warps 5-8
         const int quad = warp & 3, r = quad * 32 + lane;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++it) {
@@ -221,6 +212,22 @@ int launch_conv_stem_tc(const float *x, const float *w, const float *bias, void 
     else return TDRN_EUNSUPPORTED;
     p.x = x; p.w = w; p.bias = bias; p.B = B; p.H = H; p.W = W; p.relu = relu;
     p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.total = p.tiles_w * p.tiles_h * B;
+    CUtensorMap tmX;
+    {   // fp32 NCHW image: dims (W, H, 3, B); box (bw+8, bh+2, 3, 1) starting at (x0-4, y0-1): out-of-bounds = conv padding
+        EncodeTiledFn enc = get_encode_tiled();
+        if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return TDRN_ECUDA; }
+        if ((W * 4) % 16 != 0 || ((uintptr_t)x & 15)) return TDRN_EUNSUPPORTED;
+        const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
+        const cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
+        p.pw = p.bw + 8;     // columns x0-4 .. x0+bw+3: TMA needs the innermost start coordinate 16-byte aligned (4 floats)
+        const cuuint32_t bdim[4] = {(cuuint32_t)p.pw, (cuuint32_t)(p.bh + 2), 3, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (3 * (p.bh + 2) * p.pw * 4 > ST_PATCH_BYTES) return TDRN_EUNSUPPORTED;
+        CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(x), gdim, gstr, bdim, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (stem input) failed (CUresult %d)", (int)r); return TDRN_ECUDA; }
+    }
     CUtensorMap tmO;
     const uint64_t dims[4] = {ST_COUT, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t str[3] = {ST_COUT * 2, (uint64_t)W * ST_COUT * 2, (uint64_t)H * W * ST_COUT * 2};
@@ -235,7 +242,7 @@ int launch_conv_stem_tc(const float *x, const float *w, const float *bias, void 
     }
     TDRN_CUDA(cudaFuncSetAttribute(conv_stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
     const int grid = p.total < 2 * num_sms ? p.total : 2 * num_sms;
-    conv_stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM, st>>>(tmO, p);
+    conv_stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM, st>>>(tmX, tmO, p);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }

@@ -357,7 +357,16 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
 
     const int n_pad16 = (p.n_total + 15) & ~15;
-    const int BN = n_pad16 > 128 ? 256 : (n_pad16 > 64 ? 128 : 64);
+    int BN = n_pad16 > 128 ? 256 : (n_pad16 > 64 ? 128 : 64);
+    // Small maps (the 10x10 / 5x5 pyramid levels, M <= 3200 rows at b32) yield a handful of 128-row tiles: with the
+    // widest N tile only 7..25 SMs would stream the whole weight tensor.  Narrower N tiles put 2-4x more SMs to
+    // work (the A re-reads this costs are tiny at these sizes).
+    if (!g_num_sms) {
+        int dev = 0;
+        TDRN_CUDA(cudaGetDevice(&dev));
+        TDRN_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    while (BN > 64 && p.m_tiles * ((n_pad16 + BN - 1) / BN) * 2 <= g_num_sms) BN >>= 1;
     p.n_tiles = (n_pad16 + BN - 1) / BN;
 
     CUtensorMap tmA, tmB;

@@ -139,3 +139,56 @@ extern "C" int tdrn_debug_umma_rate(long long *cycles_dev, int grid, int n, int 
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA fp32 box probe (development): load one (pw, ph, 3, 1) box of an NCHW fp32 image at (cx, cy) and copy it out.
+// ---------------------------------------------------------------------------------------------------------
+namespace tdrn {
+namespace tc {
+__global__ void tma_f32_probe_kernel(const __grid_constant__ CUtensorMap tm, float *out, int n, int cx, int cy, int b, int rank)
+{
+    __shared__ __align__(1024) float buf[4096];
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(&bar, (uint32_t)n * 4u);
+        if (rank == 4) tma_load_4d(buf, &tm, &bar, cx, cy, 0, b);
+        else asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                          ::"r"(smem_u32(buf)), "l"((uint64_t)&tm), "r"(smem_u32(&bar)), "r"(cx), "r"(cy), "r"(3 * b) : "memory");
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = buf[i];
+}
+}  // namespace tc
+}  // namespace tdrn
+
+extern "C" int tdrn_debug_tma_f32(const float *x, int B, int H, int W, int pw, int ph, int cx, int cy, int b, int rank, int l2promo, float *out)
+{
+    EncodeTiledFn enc = get_encode_tiled();
+    TDRN_REQUIRE(enc, "no encoder");
+    CUtensorMap tm;
+    CUresult r;
+    const CUtensorMapL2promotion promo = l2promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (l2promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rank == 4) {
+        const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
+        const cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
+        const cuuint32_t bdim[4] = {(cuuint32_t)pw, (cuuint32_t)ph, 3, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(x), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)3 * B};
+        const cuuint64_t gstr[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+        const cuuint32_t bdim[3] = {(cuuint32_t)pw, (cuuint32_t)ph, 3};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(x), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    TDRN_REQUIRE(r == CUDA_SUCCESS, "encode failed %d", (int)r);
+    tma_f32_probe_kernel<<<1, 128>>>(tm, out, pw * ph * 3, cx, cy, b, rank);
+    TDRN_LAUNCH_CHECK();
+    TDRN_CUDA(cudaDeviceSynchronize());
+    return TDRN_OK;
+}
