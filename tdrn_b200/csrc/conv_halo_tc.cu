@@ -50,6 +50,75 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
     return d;
 }
 
+// Epilogue of one 128-pixel tile: accumulator columns [0, ncols) at `trow` are output channels n0 .. n0+ncols-1.
+// `half` selects which of the two warps of this TMEM lane quadrant handles a 32-column chunk.
+__device__ __forceinline__ void halo_epilogue_tile(const HaloP &p, uint32_t trow, const float *s_bias, int n0, int ncols, int half,
+                                           int b, int x, int y, int wl, int hl)
+{
+    const bool valid = x < p.W && y < p.H;
+    for (int c0 = half * 32; c0 < (p.debug_skip_epilogue ? 0 : ncols); c0 += 64) {
+        float v[32];
+        tmem_ld32(trow + (uint32_t)c0, v);
+        if (n0 + c0 >= p.Cout) continue;                     // warp-uniform
+        const int nv = min(32, p.Cout - n0 - c0);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 bq = *(const float4 *)(s_bias + n0 + c0 + j);
+            v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
+        }
+        if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        bool store = valid;
+        int oy = y, ox = x;
+        if (p.pool) { store = valid && !(wl & 1) && !(hl & 1); oy = y >> 1; ox = x >> 1; }
+        const long long o = (long long)b * p.out_sb + ((long long)oy * p.out_w + ox) * p.out_sp + n0 + c0;
+        if (p.out_f32) {
+            if (p.pool) {
+                // MaxPool2d(2,2): the 2x2 partners of pixel (hl, wl) are lanes ^1 and ^8 of this warp
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                    v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, HL_BW));
+                }
+            }
+            if (!store) continue;
+            float *op = (float *)p.out + o;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nv) op[j] = v[j];
+        } else {
+            uint32_t q[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                q[j] = *(const uint32_t *)&h2;
+            }
+            if (p.pool) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    uint32_t o1 = __shfl_xor_sync(0xffffffffu, q[j], 1);
+                    __nv_bfloat162 m = __hmax2(*(const __nv_bfloat162 *)&q[j], *(const __nv_bfloat162 *)&o1);
+                    uint32_t mw = *(const uint32_t *)&m;
+                    uint32_t o2 = __shfl_xor_sync(0xffffffffu, mw, HL_BW);
+                    m = __hmax2(m, *(const __nv_bfloat162 *)&o2);
+                    q[j] = *(const uint32_t *)&m;
+                }
+            }
+            if (!store) continue;
+            __nv_bfloat16 *op = (__nv_bfloat16 *)p.out + o;
+            if (nv == 32 && ((o & 7) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ((uint4 *)op)[j] = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+            } else {
+                const __nv_bfloat16 *qb = (const __nv_bfloat16 *)q;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j < nv) op[j] = qb[j];
+            }
+        }
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB, const HaloP p)
@@ -146,72 +215,11 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_c
         for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++tcount) {
             const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
             const int x = (rem % p.tiles_w) * HL_BW + wl, y = (rem / p.tiles_w) * HL_BH + hl;
-            const bool valid = x < p.W && y < p.H;
             const uint32_t buf = tcount & 1u;
             mbar_wait(&t_full[buf], (tcount >> 1) & 1u);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
-            for (int c0 = half * 32; c0 < (p.debug_skip_epilogue ? 0 : p.n_pad16); c0 += 64) {
-                float v[32];
-                tmem_ld32(trow + (uint32_t)c0, v);
-                if (c0 >= p.Cout) continue;                          // warp-uniform
-                const int nv = min(32, p.Cout - c0);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 bq = *(const float4 *)(s_bias + c0 + j);
-                    v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
-                }
-                if (p.relu) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                }
-                bool store = valid;
-                int oy = y, ox = x;
-                if (p.pool) { store = valid && !(wl & 1) && !(hl & 1); oy = y >> 1; ox = x >> 1; }
-                const long long o = (long long)b * p.out_sb + ((long long)oy * p.out_w + ox) * p.out_sp + c0;
-                if (p.out_f32) {
-                    if (p.pool) {
-                        // MaxPool2d(2,2): the 2x2 partners of pixel (hl, wl) are lanes ^1 and ^8 of this warp
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-                            v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, HL_BW));
-                        }
-                    }
-                    if (!store) continue;
-                    float *op = (float *)p.out + o;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (j < nv) op[j] = v[j];
-                } else {
-                    uint32_t q[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                        q[j] = *(const uint32_t *)&h2;
-                    }
-                    if (p.pool) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            uint32_t o1 = __shfl_xor_sync(0xffffffffu, q[j], 1);
-                            __nv_bfloat162 m = __hmax2(*(const __nv_bfloat162 *)&q[j], *(const __nv_bfloat162 *)&o1);
-                            uint32_t mw = *(const uint32_t *)&m;
-                            uint32_t o2 = __shfl_xor_sync(0xffffffffu, mw, HL_BW);
-                            m = __hmax2(m, *(const __nv_bfloat162 *)&o2);
-                            q[j] = *(const uint32_t *)&m;
-                        }
-                    }
-                    if (!store) continue;
-                    __nv_bfloat16 *op = (__nv_bfloat16 *)p.out + o;
-                    if (nv == 32 && ((o & 7) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) ((uint4 *)op)[j] = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
-                    } else {
-                        const __nv_bfloat16 *qb = (const __nv_bfloat16 *)q;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (j < nv) op[j] = qb[j];
-                    }
-                }
-            }
+            halo_epilogue_tile(p, trow, s_bias, 0, p.n_pad16, half, b, x, y, wl, hl);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[buf]);
@@ -221,6 +229,164 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_c
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Streamed-weight variant for layers whose weights do not fit in shared memory (conv2_2 128->128 @160^2,
+// conv3_1 128->256 @80^2).  A work unit is a 16 x 16 pixel super-tile (two 8 x 16 M tiles side by side, ONE 18 x 18
+// halo box, tile 1's descriptors start 8 rows further) times one 128-wide N tile: each weight k-block (16 KB)
+// fetched from L2 feeds 2 x 4 MMAs, so the L2->SM traffic per MMA is 2.5x lower than conv_tc.cu's and the main
+// loop is MMA-issue bound (73 cycles per M=128, N=128, K=16 instruction) instead of L2 bound.
+// TMEM: 2 tiles x 128 columns, double buffered = all 512 columns.
+// Warps: 0 A-halo TMA, 1 MMA, 2-9 epilogue, 10 weight TMA.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int HS_PW = 2 * HL_BW + 2;                      // 18
+constexpr int HS_A_BYTES = HS_PW * HL_PH * 128;           // 41472
+constexpr int HS_A_STRIDE = (HS_A_BYTES + 1023) & ~1023;  // 41984
+constexpr int HS_A_STAGES = 2;
+constexpr int HS_BN = 128;
+constexpr int HS_B_BYTES = HS_BN * 128;                   // 16 KB per (tap, channel block)
+constexpr int HS_B_STAGES = 7;
+constexpr int HS_THREADS = 352;
+constexpr int HS_SMEM = 1024 + HS_A_STAGES * HS_A_STRIDE + HS_B_STAGES * HS_B_BYTES;
+
+__global__ void __launch_bounds__(HS_THREADS, 1) conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                         const __grid_constant__ CUtensorMap tmB, const HaloP p)
+{
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t a_full[HS_A_STAGES], a_empty[HS_A_STAGES];
+    __shared__ __align__(8) uint64_t b_full[HS_B_STAGES], b_empty[HS_B_STAGES];
+    __shared__ __align__(8) uint64_t t_full[2], t_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_bias[512];
+
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base;
+    uint8_t *sB = base + HS_A_STAGES * HS_A_STRIDE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pairs_w = p.tiles_w >> 1;                           // super-tiles per row
+    const int units_per_img = pairs_w * p.tiles_h;
+    const int n_tiles = p.n_pad16 / HS_BN;
+    const int m_units = units_per_img * p.B;
+    const int total = m_units * n_tiles;                          // unit = (n tile, super-tile); n-major so that
+                                                                  // concurrently running CTAs share the weight slice
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+#pragma unroll
+        for (int s = 0; s < HS_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+#pragma unroll
+        for (int s = 0; s < HS_B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+    for (int i = threadIdx.x; i < 512; i += HS_THREADS) s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===================== A (halo) TMA producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
+                const int mu = unit % m_units;
+                const int b = mu / units_per_img, rem = mu - b * units_per_img;
+                const int y0 = (rem / pairs_w) * HL_BH - 1, x0 = (rem % pairs_w) * (2 * HL_BW) - 1;
+                for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
+                    const uint32_t s = it % HS_A_STAGES, ph = (it / HS_A_STAGES) & 1u;
+                    mbar_wait(&a_empty[s], ph ^ 1u);
+                    mbar_expect_tx(&a_full[s], HS_A_BYTES);
+                    tma_load_4d(sA + (size_t)s * HS_A_STRIDE, &tmA, &a_full[s], cb * 64, x0, y0, b);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 10) {
+        // ===================== B (weight k-block) TMA producer =====================
+        if (lane == 0) {
+            uint32_t jt = 0;
+            for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
+                const int n0 = (unit / m_units) * HS_BN;
+                for (int cb = 0; cb < p.cblocks; ++cb)
+                    for (int tap = 0; tap < 9; ++tap, ++jt) {
+                        const uint32_t s = jt % HS_B_STAGES, ph = (jt / HS_B_STAGES) & 1u;
+                        mbar_wait(&b_empty[s], ph ^ 1u);
+                        mbar_expect_tx(&b_full[s], HS_B_BYTES);
+                        tma_load_2d(sB + (size_t)s * HS_B_BYTES, &tmB, &b_full[s], (tap * p.cblocks + cb) * 64, n0);
+                    }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, HS_BN);
+            const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+            uint32_t it = 0, jt = 0, tcount = 0;
+            for (int unit = blockIdx.x; unit < total; unit += gridDim.x, ++tcount) {
+                const uint32_t buf = tcount & 1u;
+                mbar_wait(&t_empty[buf], ((tcount >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * (2 * HS_BN);
+                for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
+                    const uint32_t sa = it % HS_A_STAGES, pha = (it / HS_A_STAGES) & 1u;
+                    mbar_wait(&a_full[sa], pha);
+                    tc_fence_after();
+                    const uint32_t a0 = sA_u + sa * (uint32_t)HS_A_STRIDE;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap, ++jt) {
+                        const int tr = tap / 3, ts = tap - tr * 3;
+                        const uint32_t sb = jt % HS_B_STAGES, phb = (jt / HS_B_STAGES) & 1u;
+                        mbar_wait(&b_full[sb], phb);
+                        tc_fence_after();
+                        const uint64_t bdesc = umma_desc_sw128(sB_u + sb * (uint32_t)HS_B_BYTES);
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) {
+                            const uint64_t adesc = umma_desc_sw128_sbo(a0 + (uint32_t)(tr * HS_PW + ts + mt * HL_BW) * 128u, HS_PW * 128u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d_tmem + mt * HS_BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (cb | tap | k) != 0);
+                        }
+                        umma_commit(&b_empty[sb]);
+                    }
+                    umma_commit(&a_empty[sa]);
+                }
+                umma_commit(&t_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (warps 2..9) =====================
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int r = quad * 32 + lane;
+        const int wl = r & (HL_BW - 1), hl = r >> 3;
+        uint32_t tcount = 0;
+        for (int unit = blockIdx.x; unit < total; unit += gridDim.x, ++tcount) {
+            const int mu = unit % m_units, n0 = (unit / m_units) * HS_BN;
+            const int b = mu / units_per_img, rem = mu - b * units_per_img;
+            const int y = (rem / pairs_w) * HL_BH + hl, xb = (rem % pairs_w) * (2 * HL_BW) + wl;
+            const uint32_t buf = tcount & 1u;
+            mbar_wait(&t_full[buf], (tcount >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (2 * HS_BN) + mt * HS_BN;
+                halo_epilogue_tile(p, trow, s_bias, n0, HS_BN, half, b, xb + mt * HL_BW, y, wl, hl);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 static int g_halo_sms = 0;
@@ -239,7 +405,7 @@ int conv_halo_try(const tdrn_conv_desc *d, const void *in, const void *weight, c
                   void *out, cudaStream_t st)
 {
     if (d->deconv2x2 || d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != 1 || d->dil != 1 || residual ||
-        d->Cin % 64 != 0 || d->Cout > 128 || d->in_sb != 0)
+        d->Cin % 64 != 0 || d->in_sb != 0)
         return TDRN_EUNSUPPORTED;
     if (d->W % HL_BW != 0 || d->H % HL_BH != 0) return TDRN_EUNSUPPORTED;      // exact tiling only (40x40 and below stay generic)
     HaloP p{};
@@ -249,7 +415,10 @@ int conv_halo_try(const tdrn_conv_desc *d, const void *in, const void *weight, c
     const size_t budget = 225 * 1024;
     int stages = HL_MAX_STAGES;
     while (stages >= 2 && 1024 + (size_t)p.w_bytes + (size_t)stages * HL_A_STRIDE > budget) --stages;
-    if (stages < 2) return TDRN_EUNSUPPORTED;                                   // weights too large to stay resident
+    const bool resident = stages >= 2 && d->Cout <= 128;
+    // weights too large to stay resident: streamed variant (two M tiles per weight k-block), 128-wide N tiles
+    const bool streamed = !resident && d->Cout % HS_BN == 0 && d->Cout <= 512 && d->W % (2 * HL_BW) == 0 && !getenv("TDRN_NO_HALO_STREAM");
+    if (!resident && !streamed) return TDRN_EUNSUPPORTED;
     p.stages = stages;
     p.tiles_w = d->W / HL_BW; p.tiles_h = d->H / HL_BH; p.total = p.tiles_w * p.tiles_h * d->B;
     p.bias = bias; p.out = out; p.out_sb = d->out_sb; p.out_sp = d->out_sp;
@@ -265,7 +434,7 @@ int conv_halo_try(const tdrn_conv_desc *d, const void *in, const void *weight, c
     {
         const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
         const uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
-        const uint32_t box[4] = {64, HL_PW, HL_PH, 1};
+        const uint32_t box[4] = {64, (uint32_t)(resident ? HL_PW : HS_PW), HL_PH, 1};
         int rc = make_tmap_bf16(&tmA, in, 4, dims, str, box, nullptr);
         if (rc) return rc;
     }
@@ -273,9 +442,16 @@ int conv_halo_try(const tdrn_conv_desc *d, const void *in, const void *weight, c
         const uint64_t K = 9ull * d->Cin;
         const uint64_t dims[2] = {K, (uint64_t)p.n_pad16};
         const uint64_t str[1] = {K * 2};
-        const uint32_t box[2] = {64, (uint32_t)p.n_pad16};
+        const uint32_t box[2] = {64, (uint32_t)(resident ? p.n_pad16 : HS_BN)};
         int rc = make_tmap_bf16(&tmB, weight, 2, dims, str, box, nullptr);
         if (rc) return rc;
+    }
+    if (!resident) {
+        const int total = (p.tiles_w / 2) * p.tiles_h * d->B * (p.n_pad16 / HS_BN);
+        TDRN_CUDA(cudaFuncSetAttribute(conv_halo_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HS_SMEM));
+        conv_halo_stream_kernel<<<total < g_halo_sms ? total : g_halo_sms, HS_THREADS, HS_SMEM, st>>>(tmA, tmB, p);
+        TDRN_LAUNCH_CHECK();
+        return TDRN_OK;
     }
     const size_t smem = 1024 + (size_t)p.w_bytes + (size_t)stages * HL_A_STRIDE;
     return p.n_pad16 > 64 ? launch_halo<128>(tmA, tmB, p, smem, st) : launch_halo<64>(tmA, tmB, p, smem, st);
