@@ -149,6 +149,12 @@ int tdrn_maxpool2x2(const void *in, void *out, int B, int H, int W, int C, int c
 int tdrn_l2norm(const void *in, const float *weight, void *out, long long pixels, int C, int dtype,
                 tdrn_stream_t stream);
 
+/* L2Norm and the MaxPool2d(2,2) of the SAME input in one pass (conv4_3 / conv5_3 feed both, model/
+   dualrefinedet_vggbn.py:130-148): out_norm [B,H,W,C], out_pool [B,H/2,W/2,C].  bf16, C in {256,512,1024}, even H and W;
+   TDRN_EUNSUPPORTED otherwise (caller uses tdrn_l2norm + tdrn_maxpool2x2). */
+int tdrn_l2norm_pool2x2(const void *in, const float *weight, void *out_norm, void *out_pool, int B, int H, int W,
+                        int C, int dtype, tdrn_stream_t stream);
+
 /* Row softmax over C classes, fp32 [rows, C] (nn.Softmax(dim=1), dualrefinedet_vggbn.py:196). In place ok. */
 int tdrn_softmax(const float *in, float *out, long long rows, int C, tdrn_stream_t stream);
 

@@ -286,6 +286,82 @@ __global__ void l2norm_kernel(const T *__restrict__ in, const float *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// L2Norm + the MaxPool2d(2,2) that follows the same tensor (conv4_3 -> {L2Norm_4_3, pool4}, conv5_3 ->
+// {L2Norm_5_3, pool5}; model/dualrefinedet_vggbn.py:130-148): x is read ONCE, both consumers' inputs are written.
+// bf16 NHWC, one warp per 2x2 window, 16-byte vector accesses (lane l owns channels v*256 + 8l .. +7).
+// ------------------------------------------------------------------------------------------------
+template <int CV>
+__global__ void __launch_bounds__(256, 4) l2norm_pool_kernel(const uint4 *__restrict__ in, const float *__restrict__ weight,
+                                                             uint4 *__restrict__ out_norm, uint4 *__restrict__ out_pool,
+                                                             int B, int H, int W)
+{
+    const int lane = threadIdx.x & 31;
+    const int Ho = H >> 1, Wo = W >> 1;
+    const long long win = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (win >= (long long)B * Ho * Wo) return;
+    const int b = (int)(win / (Ho * Wo)), rem = (int)(win - (long long)b * Ho * Wo);
+    const int py = rem / Wo, px = rem - py * Wo;
+    constexpr int PV = CV * 32;                                  // uint4 per pixel
+    const long long p00 = ((long long)b * H + 2 * py) * W + 2 * px;
+    // pass 1: per-pixel sum of squares + running 2x2 max (x is re-read from L1 in pass 2: keeps the register
+    // footprint small enough for 32 resident warps per SM, which is what a streaming kernel needs)
+    float ss[4];
+    uint4 mx[CV];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 *src = in + (p00 + (q >> 1) * W + (q & 1)) * PV + lane;
+        float s = 0.f;
+#pragma unroll
+        for (int v = 0; v < CV; ++v) {
+            const uint4 xv = __ldg(src + v * 32);
+            const uint32_t w4[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float lo = __uint_as_float(w4[j] << 16), hi = __uint_as_float(w4[j] & 0xffff0000u);
+                s = fmaf(lo, lo, s); s = fmaf(hi, hi, s);
+            }
+            if (q == 0) mx[v] = xv;
+            else {
+                const __nv_bfloat162 *x2 = (const __nv_bfloat162 *)&xv;
+                __nv_bfloat162 *m2 = (__nv_bfloat162 *)&mx[v];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m2[j] = __hmax2(m2[j], x2[j]);
+            }
+        }
+        ss[q] = s;
+    }
+    const long long po = ((long long)b * Ho + py) * Wo + px;
+#pragma unroll
+    for (int v = 0; v < CV; ++v) out_pool[po * PV + v * 32 + lane] = mx[v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ss[q] += __shfl_xor_sync(0xffffffffu, ss[q], o);
+    // pass 2: normalise.  x / norm is evaluated as x * (1 / norm): the result is rounded to bf16 (2^-9), the
+    // reciprocal's extra 2^-24 is invisible; the fp32 path keeps the exact division (l2norm_kernel).
+#pragma unroll
+    for (int v = 0; v < CV; ++v) {
+        const float4 wa = __ldg((const float4 *)(weight + v * 256 + lane * 8)), wb = __ldg((const float4 *)(weight + v * 256 + lane * 8 + 4));
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float inv = 1.f / (sqrtf(ss[q]) + 1e-10f);     // l2norm.py:18
+            const long long e = (p00 + (q >> 1) * W + (q & 1)) * PV + v * 32 + lane;
+            const uint4 xv = in[e];
+            const uint32_t w4[4] = {xv.x, xv.y, xv.z, xv.w};
+            uint32_t o4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float lo = __uint_as_float(w4[j] << 16), hi = __uint_as_float(w4[j] & 0xffff0000u);
+                const __nv_bfloat162 r = __floats2bfloat162_rn(wv[2 * j] * (lo * inv), wv[2 * j + 1] * (hi * inv));   // :19-20
+                o4[j] = *(const uint32_t *)&r;
+            }
+            out_norm[e] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row softmax (nn.Softmax(dim=1)): one warp per row
 // ------------------------------------------------------------------------------------------------
 __global__ void softmax_rows_kernel(const float *__restrict__ in, float *__restrict__ out, long long rows, int C)
@@ -474,6 +550,24 @@ extern "C" int tdrn_l2norm(const void *in, const float *weight, void *out, long 
         l2norm_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)in, weight, (float *)out, pixels, C);
     else
         l2norm_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16 *)in, weight, (__nv_bfloat16 *)out, pixels, C);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
+extern "C" int tdrn_l2norm_pool2x2(const void *in, const float *weight, void *out_norm, void *out_pool, int B, int H, int W,
+                                   int C, int dtype, tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(in && weight && out_norm && out_pool && B > 0 && H > 0 && W > 0 && C > 0, "tdrn_l2norm_pool2x2: bad argument");
+    if (dtype != TDRN_BF16 || (C != 256 && C != 512 && C != 1024) || (H & 1) || (W & 1)) {
+        set_error("tdrn_l2norm_pool2x2: needs bf16, C in {256,512,1024}, even H and W (got dtype=%d C=%d %dx%d)", dtype, C, H, W);
+        return TDRN_EUNSUPPORTED;
+    }
+    const long long windows = (long long)B * (H / 2) * (W / 2);
+    const int grid = (int)((windows * 32 + 255) / 256);
+    cudaStream_t st = as_stream(stream);
+    if (C == 256) l2norm_pool_kernel<1><<<grid, 256, 0, st>>>((const uint4 *)in, weight, (uint4 *)out_norm, (uint4 *)out_pool, B, H, W);
+    else if (C == 512) l2norm_pool_kernel<2><<<grid, 256, 0, st>>>((const uint4 *)in, weight, (uint4 *)out_norm, (uint4 *)out_pool, B, H, W);
+    else l2norm_pool_kernel<4><<<grid, 256, 0, st>>>((const uint4 *)in, weight, (uint4 *)out_norm, (uint4 *)out_pool, B, H, W);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }

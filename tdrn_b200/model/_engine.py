@@ -48,6 +48,8 @@ class Engine(object):
         self.pk = {}
         self.multi_stream = os.environ.get('TDRN_SINGLE_STREAM', '0') != '1'
         self._side = []
+        self._rr = 0
+        self.early_fork = os.environ.get('TDRN_EARLY_FORK', '0') != '0'   # measured: forking under conv5_x steals SMs from the critical path
 
     # ---- weight packing -------------------------------------------------------------------------
     def _bn(self, name):
@@ -107,6 +109,33 @@ class Engine(object):
             main.wait_event(ev)
         return results
 
+    def spawn(self, fn):
+        """Start ``fn`` on a side stream forked from the current point of the current stream (so it may begin
+        while later trunk layers are still being issued on the main stream).  -> handle for ``join``."""
+        if not self.multi_stream:
+            return (None, fn())
+        main = torch.cuda.current_stream()
+        if len(self._side) < 8:
+            self._side.append(torch.cuda.Stream(self.device))
+        st = self._side[self._rr % len(self._side)]
+        self._rr += 1
+        fork = torch.cuda.Event()
+        fork.record(main)
+        st.wait_event(fork)
+        with torch.cuda.stream(st):
+            res = fn()
+            done = torch.cuda.Event()
+            done.record(st)
+        for t in _tensors(res):
+            t.record_stream(main)
+        return (done, res)
+
+    def join(self, handle):
+        done, res = handle
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
+        return res
+
     # ---- operators ------------------------------------------------------------------------------
     def conv(self, name, x, stride=1, pad=0, dil=1, bn=None, relu=False, deconv=False, **kw):
         pc = self.packed(name, stride, pad, dil, bn, deconv)
@@ -126,7 +155,8 @@ class Engine(object):
         return ops.conv_first(x_nchw, pc, True, self.act)
 
     # ---- VGG trunk: vgg() model/networks.py:136-163 + extras, forward :130-153 --------------------
-    def vgg_trunk(self, x_nchw, bn, with_extras=True):
+    def vgg_trunk(self, x_nchw, bn, with_extras=True, on_source=None):
+        """``on_source(k, tensor)`` is called the moment ARM source k exists (lets the caller fork its heads early)."""
         split43, split53 = (23, 33)[bn], (30, 43)[bn]
         sources = []
         idx, x = 0, None
@@ -145,7 +175,17 @@ class Engine(object):
         while ci < n_cfg:
             v = VGG_CFG[ci]
             if idx == split43:
+                if v == 'M':                              # conv4_3 feeds L2Norm_4_3 and pool4: one pass over x
+                    s0, x = ops.l2norm_pool(x, self.vec('L2Norm_4_3.weight'))
+                    sources.append(s0)
+                    if on_source:
+                        on_source(0, s0)
+                    idx += 1
+                    ci += 1
+                    continue
                 sources.append(ops.l2norm(x, self.vec('L2Norm_4_3.weight')))
+                if on_source:
+                    on_source(0, sources[0])
             if v == 'M' or v == 'C':
                 x = ops.maxpool2x2(x, ceil_mode=(v == 'C'))
                 idx += 1
@@ -161,13 +201,17 @@ class Engine(object):
                     idx += step
             ci += 1
         assert idx == split53
-        sources.append(ops.l2norm(x, self.vec('L2Norm_5_3.weight')))
-        x = ops.maxpool2x2(x, False)                      # pool5 (pool5_ds=True)
+        s1, x = ops.l2norm_pool(x, self.vec('L2Norm_5_3.weight'))   # conv5_3 -> L2Norm_5_3 and pool5 (pool5_ds=True)
+        sources.append(s1)
+        if on_source:
+            on_source(1, s1)
         idx += 1
         x = conv_block(idx, x, 6, 6)                      # conv6: 3x3 dilation 6
         idx += step
         x = conv_block(idx, x, 0, 1)                      # conv7: 1x1
         sources.append(x)
+        if on_source:
+            on_source(2, x)
         if with_extras:
             if bn:
                 x = self.conv('extras.0', x, bn='extras.1', relu=True)
@@ -176,6 +220,8 @@ class Engine(object):
                 x = self.conv('extras.0', x, relu=True)
                 x = self.conv('extras.2', x, 2, 1, relu=True)
             sources.append(x)
+            if on_source:
+                on_source(3, x)
         return sources
 
     # ---- TCB / FPN: dualrefinedet_vggbn.py:166-179 -------------------------------------------------
@@ -260,6 +306,55 @@ class Engine(object):
         x, trans, lv = res[0], res[1:4], res[4:8]
         odm = self.fpn_topdown(x, [x], trans)
         return arm_loc, [r[0] for r in lv], ([r[1] for r in lv] if multihead else []), odm
+
+    def trunk_arm_tcb(self, x_nchw, bn, size, multihead, want_nchw_offsets=True):
+        """VGG trunk with the ARM heads (+1x1 offset convs) and the TCB transfer branches forked the moment their
+        source exists (dualrefinedet_vggbn.py:130-179): the 40x40 / 20x20 branches run under conv5_x .. extras
+        instead of after them, and the FPN top-down chain only waits for the branch it consumes.
+        -> arm_loc, offsets (NHWC), offsets2 (NHWC), offsets NCHW (or None), odm sources."""
+        B = x_nchw.shape[0]
+        sizes = level_sizes(size)
+        lv_off, P = [], 0
+        for sd in sizes:
+            lv_off.append(P)
+            P += sd * sd * NUM_BOX
+        arm_loc = torch.empty(B, P, 4, dtype=torch.float32, device=self.device)
+        handles = {}
+
+        def level(k, a):
+            self.head_into('arm_loc.%d' % k, a, arm_loc, 4, lv_off[k], P)
+            H, W = a.shape[1], a.shape[2]
+            view = arm_loc.view(B, P * 4)[:, lv_off[k] * 4:]
+            kw = dict(in_shape=(B, H, W, 12), in_sb=P * 4, out_dtype=torch.float32)
+            o = self.conv('offset.%d' % k, view, **kw)
+            o2 = self.conv('offset2.%d' % k, view, **kw) if multihead else None
+            on = ops.nhwc_to_nchw_f32(o) if want_nchw_offsets else None      # the reference returns NCHW offset maps
+            return o, o2, on
+
+        def on_source(k, a):
+            assert a.shape[1] == sizes[k], (a.shape, sizes)
+            if k < 3:
+                handles['trans', k] = self.spawn(lambda: self.trans_branch(a, k))
+            else:
+                handles['last'] = self.spawn(lambda: self.last_trans(a))
+            handles['arm', k] = self.spawn(lambda: level(k, a))
+
+        if self.early_fork:
+            self.vgg_trunk(x_nchw, bn, on_source=on_source)
+        else:
+            for k, a in enumerate(self.vgg_trunk(x_nchw, bn)):
+                on_source(k, a)
+        x = self.join(handles['last'])
+        odm = [x]
+        for k in range(3):
+            t = self.join(handles['trans', 2 - k])
+            u = self.conv('up_layers.%d' % k, x, deconv=True, relu=True, residual=t)
+            x = self.conv('latent_layers.%d' % k, u, 1, 1, relu=True)
+            odm.append(x)
+        odm.reverse()
+        lv = [self.join(handles['arm', k]) for k in range(4)]
+        return (arm_loc, [r[0] for r in lv], [r[1] for r in lv] if multihead else [],
+                [r[2] for r in lv] if want_nchw_offsets else None, odm, P, lv_off)
 
     def deform_heads(self, feats, offs, offs2, P, lv_off, num_classes, dg, multihead, loc_name='odm_loc',
                      conf_name='odm_conf', softmax=True):

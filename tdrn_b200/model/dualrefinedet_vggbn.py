@@ -76,15 +76,14 @@ class RefineSSD(DetectorBase):
         fp32 maps that replace the ARM-regressed offsets, to check the deformable heads in isolation."""
         E = self.engine()
         x = self._check_input(x)
-        arm_sources = E.vgg_trunk(x, self.bn)
-        P, lv = prior_layout(arm_sources)
-        arm_loc, offs, offs2, odm_sources = E.arm_and_tcb(arm_sources, P, lv, self.multihead)
+        arm_loc, offs, offs2, offs_nchw, odm_sources, P, lv = E.trunk_arm_tcb(x, self.bn, self.size, self.multihead)
         if _offsets is not None:
             offs = [ops.nchw_f32_to_nhwc(o.float(), torch.float32) for o in _offsets[0]]
             offs2 = [ops.nchw_f32_to_nhwc(o.float(), torch.float32) for o in (_offsets[1] or [])]
+            offs_nchw = [ops.nhwc_to_nchw_f32(o) for o in offs]
         odm_loc, conf = E.deform_heads(odm_sources, offs, offs2, P, lv, self.num_classes, self.def_groups,
                                        self.multihead)
-        return arm_loc, [ops.nhwc_to_nchw_f32(o) for o in offs], odm_loc, conf
+        return arm_loc, offs_nchw, odm_loc, conf
 
 
 def build_net(phase, size=320, num_classes=21, c7_channel=1024, def_groups=1, bn=True, multihead=False,

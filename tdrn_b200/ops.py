@@ -207,6 +207,20 @@ def l2norm(x_nhwc, weight_f32):
     return out
 
 
+def l2norm_pool(x_nhwc, weight_f32):
+    """-> (L2Norm(x), maxpool2x2(x)); one fused pass when the shape allows it (bf16, C in 256/512/1024, even H, W)."""
+    x = _cuda(x_nhwc, 'input')
+    B, H, W, C = x.shape
+    if x.dtype != torch.bfloat16 or C not in (256, 512, 1024) or H % 2 or W % 2:
+        return l2norm(x, weight_f32), maxpool2x2(x, False)
+    out_n = torch.empty_like(x)
+    out_p = torch.empty(B, H // 2, W // 2, C, dtype=x.dtype, device=x.device)
+    with _Timed('aux|l2norm+pool %d @%dx%d' % (C, H, W), float((2 * x.numel() + out_p.numel()) * 2)):
+        check(_lib.lib().tdrn_l2norm_pool2x2(ptr(x), ptr(weight_f32), ptr(out_n), ptr(out_p), B, H, W, C, _dt(x),
+                                             stream_handle()), 'tdrn_l2norm_pool2x2')
+    return out_n, out_p
+
+
 def softmax_rows(x, out=None):
     x = _cuda(x, 'input')
     assert x.dtype == torch.float32 and x.dim() == 2

@@ -138,3 +138,19 @@ def test_pool_l2norm_softmax_dw_layout(golden):
         out = ops.dwconv3x3(_nhwc(x).cuda(), ops.PackedDw(wd, bn, stride, 'cuda'))
         assert rel_err(_nchw(out).cpu().numpy(), ref.numpy()) < 1e-5
     assert torch.equal(ops.nhwc_to_nchw_f32(ops.nchw_f32_to_nhwc(x.cuda(), torch.float32)).cpu(), x)
+
+
+@pytest.mark.parametrize('b,c,h,w', [(2, 512, 40, 40), (3, 256, 6, 10), (1, 1024, 20, 20), (2, 512, 5, 5)])
+def test_l2norm_pool_fused(b, c, h, w):
+    """tdrn_l2norm_pool2x2 == (L2Norm, MaxPool2d(2,2)) of the same bf16 input; odd sizes fall back to the two kernels."""
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(c + h)
+    x = (torch.randn(b, h, w, c, generator=g) * 3).to(torch.bfloat16)
+    wt = torch.rand(c, generator=g) * 10 + 1
+    xf = x.float()
+    norm = xf.pow(2).sum(3, keepdim=True).sqrt() + 1e-10
+    ref_n = (wt * (xf / norm)).to(torch.bfloat16)
+    ref_p = F.max_pool2d(xf.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).to(torch.bfloat16)
+    out_n, out_p = ops.l2norm_pool(x.cuda(), wt.cuda())
+    assert torch.equal(out_p.cpu(), ref_p)
+    assert rel_err(out_n.float().cpu().numpy(), ref_n.float().numpy()) < 8e-3          # one bf16 ulp
