@@ -55,6 +55,18 @@ def peaks():
     return {'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'hbm_gbs': 6650.0, 'source': 'fallback (B200_PROFILING.md)'}
 
 
+def conv_traffic():
+    """DRAM bytes per launch of the conv family from the committed ncu --set full capture (profiles/conv_traffic.json,
+    written by scripts/ncu_traffic.py from the .ncu-rep of the same bench command); None when no capture is committed."""
+    path = os.path.join(ROOT, 'profiles', 'conv_traffic.json')
+    if not os.path.exists(path):
+        return None
+    try:
+        return json.load(open(path))['dram_bytes_per_launch']
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port of the reference's own CPU implementation)
 # ------------------------------------------------------------------------------------------------------
@@ -116,16 +128,19 @@ def run_reference(args, rank):
 # clocks sampler
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler(object):
+    """nvidia-smi polled every 20 ms for the whole run (its start-up takes 0.1-0.5 s, far longer than the timed
+    region, so it is launched before the warm-up); begin()/end() bracket the timed legs and only samples that
+    arrived inside the bracket are reported (falling back to the closest ones if the bracket was shorter than a poll)."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -133,24 +148,37 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        rows = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.03]
+        window = 'timed legs'
+        if not rows and self.rows and self.t0 is not None:     # bracket shorter than one poll: closest samples
+            mid = 0.5 * (self.t0 + self.t1)
+            rows = [r for t, r in sorted(self.rows, key=lambda tr: abs(tr[0] - mid))[:3]]
+            window = 'closest to the timed legs'
+        sm, mx, pw, reasons = [], None, [], set()
+        for r in rows:
             try:
-                sm.append(float(r[0])); mx = float(r[1])
+                sm.append(float(r[0])); mx = float(r[1]); pw.append(float(r[2]))
             except Exception:
                 continue
             for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
         sm.sort()
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'power_w_max': max(pw) if pw else None,
+                'reasons': sorted(reasons), 'samples': len(sm), 'window': window}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -167,6 +195,9 @@ def run_gpu(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -278,12 +309,11 @@ def run_gpu(args, rank, world, local_rank):
             ms = float(t.item())
         return ms
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.begin()
     ms_dev = timed(step_device, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    sampler.end()
+    clocks = sampler.stop() if rank == 0 else None          # sampled every 20 ms across both timed legs
 
     # ---- roofline leg: per-call CUDA events on the launching stream, eager (same kernels as the graph) ----
     roof = None
@@ -313,9 +343,10 @@ def run_gpu(args, rank, world, local_rank):
         tc = agg.get('conv_tc')
         if tc:
             tflops = tc[0] / (tc[1] * 1e-3) / 1e12
-            roof = {'kernel': 'conv_tc_kernel (tcgen05 implicit-GEMM conv, all launches)', 'bound': 'tensor',
+            roof = {'kernel': 'tcgen05 implicit-GEMM conv family (conv_halo_kernel, conv_halo_stream_kernel, conv_tc_kernel): '
+                              'all conv launches of the step, algorithmic FLOPs / summed CUDA-event time', 'bound': 'tensor',
                     'achieved': tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                    'frac': tflops / pk['bf16_tflops_sustained'], 'traffic': None,
+                    'frac': tflops / pk['bf16_tflops_sustained'], 'traffic': conv_traffic(),
                     'peak_source': pk['source'] + ', sustained bf16 (kernel timed inside a long step)',
                     'launches_per_step': tc[2] // max(2, min(args.steps, 5)),
                     'avg_launch_ms': tc[1] / tc[2], 'share_of_step': tc[1] / tot_ms}

@@ -407,7 +407,11 @@ int conv_halo_try(const tdrn_conv_desc *d, const void *in, const void *weight, c
     if (d->deconv2x2 || d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != 1 || d->dil != 1 || residual ||
         d->Cin % 64 != 0 || d->in_sb != 0)
         return TDRN_EUNSUPPORTED;
-    if (d->W % HL_BW != 0 || d->H % HL_BH != 0) return TDRN_EUNSUPPORTED;      // exact tiling only (40x40 and below stay generic)
+    // Exact tiling is needed by the fused pool and by the streamed variant; the resident-weight kernel also takes
+    // ragged maps (partial tiles: TMA zero-fills beyond the map, the epilogue masks), which is what makes the
+    // Cout = 12 ARM heads on 40x40 / 20x20 maps cheap: their cost is A traffic, cut ~6x by the halo tile.
+    const bool exact = d->W % HL_BW == 0 && d->H % HL_BH == 0;
+    if (!exact && (d->pool2x2 || d->Cout > 32)) return TDRN_EUNSUPPORTED;
     HaloP p{};
     p.H = d->H; p.W = d->W; p.B = d->B; p.Cin = d->Cin; p.cblocks = d->Cin / 64; p.Cout = d->Cout;
     p.n_pad16 = (d->Cout + 15) & ~15;
@@ -417,10 +421,10 @@ int conv_halo_try(const tdrn_conv_desc *d, const void *in, const void *weight, c
     while (stages >= 2 && 1024 + (size_t)p.w_bytes + (size_t)stages * HL_A_STRIDE > budget) --stages;
     const bool resident = stages >= 2 && d->Cout <= 128;
     // weights too large to stay resident: streamed variant (two M tiles per weight k-block), 128-wide N tiles
-    const bool streamed = !resident && d->Cout % HS_BN == 0 && d->Cout <= 512 && d->W % (2 * HL_BW) == 0 && !getenv("TDRN_NO_HALO_STREAM");
+    const bool streamed = !resident && exact && d->Cout % HS_BN == 0 && d->Cout <= 512 && d->W % (2 * HL_BW) == 0 && !getenv("TDRN_NO_HALO_STREAM");
     if (!resident && !streamed) return TDRN_EUNSUPPORTED;
     p.stages = stages;
-    p.tiles_w = d->W / HL_BW; p.tiles_h = d->H / HL_BH; p.total = p.tiles_w * p.tiles_h * d->B;
+    p.tiles_w = (d->W + HL_BW - 1) / HL_BW; p.tiles_h = (d->H + HL_BH - 1) / HL_BH; p.total = p.tiles_w * p.tiles_h * d->B;
     p.bias = bias; p.out = out; p.out_sb = d->out_sb; p.out_sp = d->out_sp;
     p.relu = d->relu; p.out_f32 = d->out_dtype == TDRN_F32; p.pool = d->pool2x2;
     p.out_w = p.pool ? d->W / 2 : d->W;

@@ -17,7 +17,7 @@
 // Persistent, warp-specialised: grid = min(#tiles, #SMs), each CTA walks tiles blockIdx.x, +grid, ...
 //   warp 0   TMA producer            (ring of STAGES smem stages, full/empty mbarriers)
 //   warp 1   TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2-5 epilogue: tcgen05.ld -> bias / residual / ReLU / 2x2 max-pool (warp shuffles) -> global
+//   warps 2-9 epilogue (two per TMEM lane quadrant): tcgen05.ld -> bias / residual / ReLU / 2x2 max-pool -> global
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1; the smem ring is 192 KB deep so TMA latency is hidden even when a layer has
 // fewer tiles than SMs (the 10x10 / 5x5 pyramid levels).
@@ -82,9 +82,12 @@ template <int BN> struct TcCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;     // + slack for manual 1024B alignment
 };
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 
-template <int BN>
+// CL = 2: the kernel runs as thread-block clusters of two CTAs that own two different M tiles of the SAME N tile and
+// walk the k-blocks in lock step; each CTA fetches half of every weight box and multicasts it into both CTAs'
+// shared memory, so the weight (B) traffic L2->SM per CTA is halved (the 40x40 / 20x20 layers are L2->SM bound).
+template <int BN, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB, const TcConvP p)
 {
@@ -101,20 +104,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int n_pad16 = (p.n_total + 15) & ~15;
     const int cblocks = p.Cin >> 6;
     const int num_kb = p.taps * cblocks;
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    // work unit = CL M tiles x one N tile; CTA `cr` of the cluster takes M tile mu*CL + cr (may be a dummy beyond
+    // m_tiles: its A boxes are entirely out of bounds -> zeros, its epilogue stores nothing)
+    const int cr = CL == 2 ? (int)cluster_ctarank() : 0;
+    const int m_units = (p.m_tiles + CL - 1) / CL;
+    const int total_tiles = m_units * p.n_tiles;
+    const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
 #pragma unroll
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
 #pragma unroll
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();          // the peer's barriers are initialised before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
@@ -122,21 +131,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;                                   // running k-block counter across tiles
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+            for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+                const int mt = (tile % m_units) * CL + cr, nt = tile / m_units;
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
                 const int w0 = tw * p.bw * p.stride - p.pad, h0 = th * p.bh * p.stride - p.pad, b0 = tn * p.bn;
                 const int n0 = nt * BN;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % Cfg::STAGES;
                     const uint32_t ph = (it / Cfg::STAGES) & 1u;
-                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_wait(&empty_bar[s], ph ^ 1u);        // CL = 2: both CTAs' MMAs have released stage s
                     uint8_t *sa = tiles + s * Cfg::STAGE_BYTES;
                     const int tap = kb / cblocks, cb = kb - tap * cblocks;
                     const int tr = tap / p.kw, ts = tap - tr * p.kw;
                     mbar_expect_tx(&full_bar[s], p.a_bytes + p.b_bytes);
                     tma_load_4d(sa, &tmA, &full_bar[s], cb * 64, w0 + ts * p.dil, h0 + tr * p.dil, b0);
-                    tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[s], kb * 64, n0);
+                    if (CL == 2) {
+                        const uint32_t half_rows = p.b_bytes >> 8;           // (b_bytes / 128) / 2 rows of the weight box
+                        tma_load_2d_mc(sa + Cfg::A_BYTES + cr * half_rows * 128u, &tmB, &full_bar[s], kb * 64,
+                                       n0 + cr * (int)half_rows, (uint16_t)3);
+                    } else {
+                        tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[s], kb * 64, n0);
+                    }
                 }
             }
         }
@@ -145,8 +160,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-                const int nt = tile / p.m_tiles;
+            for (int tile = unit0; tile < total_tiles; tile += unit_step, ++tcount) {
+                const int nt = tile / m_units;
                 const int n_eff = min(BN, n_pad16 - nt * BN);           // UMMA N (multiple of 16)
                 const uint32_t idesc = umma_idesc_bf16(128, n_eff);
                 const uint32_t buf = tcount & 1u;
@@ -164,40 +179,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                     for (int k = 0; k < 4; ++k)      // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle atom
                         umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                    umma_commit(&empty_bar[s]);     // frees the smem stage when these MMAs retire
+                    if (CL == 2) umma_commit_mc(&empty_bar[s], (uint16_t)3);   // both producers multicast into this stage
+                    else umma_commit(&empty_bar[s]);     // frees the smem stage when these MMAs retire
                 }
                 umma_commit(&tmem_full_bar[buf]);   // accumulator of this tile complete
             }
         }
         __syncwarp();
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+        // ===================== epilogue (warps 2..9) =====================
+        // Two warps per TMEM lane quadrant (a warp may only read lanes 32*(warp%4)..+31); they take alternate
+        // 16-column chunks.  The residual (`up(x) + t`) of the NEXT chunk is fetched before the current chunk is
+        // processed, so its global-memory latency overlaps the TMEM load / arithmetic / stores.
+        const int quad = warp & 3, half = (warp - 2) >> 2;
         const int r = quad * 32 + lane;
         const int wl = r % p.bw, hl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+        const bool res_bf16 = p.res != nullptr && !p.out_f32;
         uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-            const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+        for (int tile = unit0; tile < total_tiles; tile += unit_step, ++tcount) {
+            const int mt = (tile % m_units) * CL + cr, nt = tile / m_units;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
             const int x = tw * p.bw + wl, y = th * p.bh + hl, b = tn * p.bn + nl;
             const int n0 = nt * BN;
             const int n_eff = min(BN, n_pad16 - n0);
             const bool valid = nl < p.bn && x < p.W && y < p.H && b < p.B;
+            // element offset of output channel n of this thread's pixel (deconv: pixel-shuffled position)
+            auto out_off = [&](int n) -> long long {
+                int co = n, oy = y, ox = x;
+                if (p.deconv) { const int ij = n / p.Cout; co = n - ij * p.Cout; oy = 2 * y + (ij >> 1); ox = 2 * x + (ij & 1); }
+                else if (p.pool) { oy = y >> 1; ox = x >> 1; }
+                return (long long)b * p.out_sb + ((long long)oy * p.out_w + ox) * p.out_sp + co;
+            };
+            uint4 rn[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            auto prefetch_res = [&](int c0) {
+                const int n = n0 + c0;
+                if (!res_bf16 || !valid || c0 >= n_eff || n + 16 > p.n_total) return;
+                const long long o = out_off(n);
+                if (o & 7) return;
+                const uint4 *rp = (const uint4 *)((const __nv_bfloat16 *)p.res + o);
+                rn[0] = rp[0]; rn[1] = rp[1];
+            };
+            prefetch_res(half * 16);
             const uint32_t buf = tcount & 1u;
             mbar_wait(&tmem_full_bar[buf], (tcount >> 1) & 1u);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
-            for (int c0 = 0; c0 < n_eff; c0 += 16) {
+            for (int c0 = half * 16; c0 < n_eff; c0 += 32) {
+                const uint4 rc[2] = {rn[0], rn[1]};
+                prefetch_res(c0 + 32);
                 float v[16];
                 tmem_ld16(trow + (uint32_t)c0, v);
                 const int n = n0 + c0;
                 if (n >= p.n_total) continue;                       // warp-uniform
-                int co = n, oy = y, ox = x;
-                if (p.deconv) { const int ij = n / p.Cout; co = n - ij * p.Cout; oy = 2 * y + (ij >> 1); ox = 2 * x + (ij & 1); }
+                const int co = p.deconv ? n % p.Cout : n;
                 const int nv = min(16, p.n_total - n);
                 if (p.bias) {
+                    if (nv == 16) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (j < nv) v[j] += __ldg(p.bias + co + j);
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 bq = __ldg((const float4 *)(p.bias + co + j));      // co is a multiple of 16 here
+                            v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (j < nv) v[j] += __ldg(p.bias + co + j);
+                    }
                 }
                 bool store = valid;
                 if (p.pool) {
@@ -209,10 +255,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, p.bw));
                     }
                     store = valid && !(wl & 1) && !(hl & 1);
-                    oy = y >> 1; ox = x >> 1;
                 }
                 if (!store) continue;
-                const long long o = (long long)b * p.out_sb + ((long long)oy * p.out_w + ox) * p.out_sp + co;
+                const long long o = out_off(n);
                 if (p.out_f32) {
                     float *op = (float *)p.out + o;
                     if (p.res) { const float *rp = (const float *)p.res + o;
@@ -224,13 +269,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     __nv_bfloat16 *op = (__nv_bfloat16 *)p.out + o;
                     const bool vec = nv == 16 && ((o & 7) == 0);
                     if (p.res) {
-                        const __nv_bfloat16 *rp = (const __nv_bfloat16 *)p.res + o;
-                        if (vec) {
-                            uint4 q[2]; q[0] = ((const uint4 *)rp)[0]; q[1] = ((const uint4 *)rp)[1];
-                            const __nv_bfloat16 *rb = (const __nv_bfloat16 *)q;
+                        if (vec) {                                   // prefetched one chunk ago
+                            const __nv_bfloat16 *rb = (const __nv_bfloat16 *)rc;
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] += __bfloat162float(rb[j]);
                         } else {
+                            const __nv_bfloat16 *rp = (const __nv_bfloat16 *)p.res + o;
 #pragma unroll
                             for (int j = 0; j < 16; ++j) if (j < nv) v[j] += __bfloat162float(rp[j]);
                         }
@@ -260,6 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();          // no CTA leaves while its peer can still signal its barriers
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
@@ -283,7 +328,7 @@ static void pick_box(int B, int H, int W, int max_w, int max_h, int &bw, int &bh
 static int g_num_sms = 0;
 
 template <int BN>
-static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcConvP &p, cudaStream_t st)
+static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcConvP &p, bool use_cluster, cudaStream_t st)
 {
     using Cfg = TcCfg<BN>;
     if (!g_num_sms) {
@@ -291,9 +336,34 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcCon
         TDRN_CUDA(cudaGetDevice(&dev));
         TDRN_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (use_cluster) {
+        static int max_clusters[3] = {0, 0, 0};
+        const int slot = BN == 256 ? 2 : (BN == 128 ? 1 : 0);
+        TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (!max_clusters[slot]) {
+            cfg.gridDim = dim3(g_num_sms);
+            int n = 0;
+            TDRN_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BN, 2>, &cfg));
+            max_clusters[slot] = n > 0 ? n : 1;
+        }
+        const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
+        const int clusters = units < max_clusters[slot] ? units : max_clusters[slot];
+        cfg.gridDim = dim3(2 * clusters);
+        TDRN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 2>, tmA, tmB, p));
+        count_launch();
+        return TDRN_OK;
+    }
+    TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const int total = p.m_tiles * p.n_tiles;
-    conv_tc_kernel<BN><<<total < g_num_sms ? total : g_num_sms, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+    conv_tc_kernel<BN, 1><<<total < g_num_sms ? total : g_num_sms, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }
@@ -370,6 +440,7 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     p.n_tiles = (n_pad16 + BN - 1) / BN;
 
     CUtensorMap tmA, tmB;
+    bool use_cluster = false;
     {
         const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
         const uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
@@ -384,13 +455,19 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         const uint64_t dims[2] = {K, (uint64_t)n_pad16};
         const uint64_t str[1] = {K * 2};
         const uint32_t b_rows = (uint32_t)(n_pad16 < BN ? n_pad16 : BN);
-        const uint32_t box[2] = {64, b_rows};
+        // cluster pairs (two M tiles share every weight box, each CTA fetches and multicasts half of it): only when
+        // there are M-tile pairs, and the half box stays aligned to the 8-row swizzle atom
+        // Measured on B200 (profiles/r01b_*): no gain -- these layers are bound by tile fill and wave quantisation, not by
+        // L2->SM weight traffic -- so the cluster path is opt-in (TDRN_CLUSTER=1) and kept as a tested option.
+        static const bool want_cluster = getenv("TDRN_CLUSTER") != nullptr;
+        use_cluster = want_cluster && p.m_tiles >= 2 && (b_rows % 16u) == 0;
+        const uint32_t box[2] = {64, use_cluster ? b_rows / 2 : b_rows};
         p.b_bytes = b_rows * 128u;
         int rc = make_tmap_bf16(&tmB, weight, 2, dims, str, box, nullptr);
         if (rc) return rc;
     }
     cudaStream_t st = as_stream(stream);
-    if (BN == 256) return launch_tc<256>(tmA, tmB, p, st);
-    if (BN == 128) return launch_tc<128>(tmA, tmB, p, st);
-    return launch_tc<64>(tmA, tmB, p, st);
+    if (BN == 256) return launch_tc<256>(tmA, tmB, p, use_cluster, st);
+    if (BN == 128) return launch_tc<128>(tmA, tmB, p, use_cluster, st);
+    return launch_tc<64>(tmA, tmB, p, use_cluster, st);
 }
