@@ -67,6 +67,9 @@ struct TcConvP {
     int Cin, Cout, n_total;      // n_total = Cout, or 4*Cout for the k2s2 deconv
     int kw, taps, pad, dil, stride;
     uint32_t a_bytes;            // bytes one A box deposits (bw*bh*bn*128)
+    // ragged-tail tiles: when H = qh*bh + rr (rr > 0) with full-width single-image boxes, the rr leftover rows of g2
+    // consecutive images are batched into one tile (second tensor map, box (64, bw, rr, g2)); nA = #regular tiles
+    int nA, qh, rr, g2; uint32_t a_bytes2;
     uint32_t b_bytes;            // bytes one B box deposits (min(BN, n_pad16)*128)
     const float *bias; const void *res; void *out;
     long long out_sb, out_sp; int out_w;
@@ -89,6 +92,7 @@ constexpr int TC_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 e
 // shared memory, so the weight (B) traffic L2->SM per CTA is halved (the 40x40 / 20x20 layers are L2->SM bound).
 template <int BN, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmA2,
                                                                 const __grid_constant__ CUtensorMap tmB, const TcConvP p)
 {
     using Cfg = TcCfg<BN>;
@@ -113,6 +117,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
+        if (p.rr) tma_prefetch_desc(&tmA2);
         tma_prefetch_desc(&tmB);
 #pragma unroll
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
@@ -133,8 +138,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             uint32_t it = 0;                                   // running k-block counter across tiles
             for (int tile = unit0; tile < total_tiles; tile += unit_step) {
                 const int mt = (tile % m_units) * CL + cr, nt = tile / m_units;
+                const bool tail = p.rr && mt >= p.nA;           // ragged-tail tile (leftover rows of g2 images)
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-                const int w0 = tw * p.bw * p.stride - p.pad, h0 = th * p.bh * p.stride - p.pad, b0 = tn * p.bn;
+                const int w0 = tw * p.bw * p.stride - p.pad;
+                const int h0 = (tail ? p.qh * p.bh : th * p.bh) * p.stride - p.pad;
+                const int b0 = tail ? (mt - p.nA) * p.g2 : tn * p.bn;
+                const CUtensorMap *mapA = tail ? &tmA2 : &tmA;
+                const uint32_t a_bytes = tail ? p.a_bytes2 : p.a_bytes;
                 const int n0 = nt * BN;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % Cfg::STAGES;
@@ -143,8 +153,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     uint8_t *sa = tiles + s * Cfg::STAGE_BYTES;
                     const int tap = kb / cblocks, cb = kb - tap * cblocks;
                     const int tr = tap / p.kw, ts = tap - tr * p.kw;
-                    mbar_expect_tx(&full_bar[s], p.a_bytes + p.b_bytes);
-                    tma_load_4d(sa, &tmA, &full_bar[s], cb * 64, w0 + ts * p.dil, h0 + tr * p.dil, b0);
+                    mbar_expect_tx(&full_bar[s], a_bytes + p.b_bytes);
+                    tma_load_4d(sa, mapA, &full_bar[s], cb * 64, w0 + ts * p.dil, h0 + tr * p.dil, b0);
                     if (CL == 2) {
                         const uint32_t half_rows = p.b_bytes >> 8;           // (b_bytes / 128) / 2 rows of the weight box
                         tma_load_2d_mc(sa + Cfg::A_BYTES + cr * half_rows * 128u, &tmB, &full_bar[s], kb * 64,
@@ -194,15 +204,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const int r = quad * 32 + lane;
         const int wl = r % p.bw, hl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+        const int hl2 = p.rr ? (r / p.bw) % p.rr : 0, nl2 = p.rr ? r / (p.bw * p.rr) : 0;      // ragged-tail tiles
         const bool res_bf16 = p.res != nullptr && !p.out_f32;
         uint32_t tcount = 0;
         for (int tile = unit0; tile < total_tiles; tile += unit_step, ++tcount) {
             const int mt = (tile % m_units) * CL + cr, nt = tile / m_units;
+            const bool tail = p.rr && mt >= p.nA;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-            const int x = tw * p.bw + wl, y = th * p.bh + hl, b = tn * p.bn + nl;
+            const int x = tw * p.bw + wl;
+            const int y = tail ? p.qh * p.bh + hl2 : th * p.bh + hl;
+            const int b = tail ? (mt - p.nA) * p.g2 + nl2 : tn * p.bn + nl;
             const int n0 = nt * BN;
             const int n_eff = min(BN, n_pad16 - n0);
-            const bool valid = nl < p.bn && x < p.W && y < p.H && b < p.B;
+            const bool valid = (tail ? nl2 < p.g2 : nl < p.bn) && x < p.W && y < p.H && b < p.B;
             // element offset of output channel n of this thread's pixel (deconv: pixel-shuffled position)
             auto out_off = [&](int n) -> long long {
                 int co = n, oy = y, ox = x;
@@ -328,7 +342,7 @@ static void pick_box(int B, int H, int W, int max_w, int max_h, int &bw, int &bh
 static int g_num_sms = 0;
 
 template <int BN>
-static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcConvP &p, bool use_cluster, cudaStream_t st)
+static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmA2, const CUtensorMap &tmB, const TcConvP &p, bool use_cluster, cudaStream_t st)
 {
     using Cfg = TcCfg<BN>;
     if (!g_num_sms) {
@@ -357,13 +371,13 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcCon
         const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
         const int clusters = units < max_clusters[slot] ? units : max_clusters[slot];
         cfg.gridDim = dim3(2 * clusters);
-        TDRN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 2>, tmA, tmB, p));
+        TDRN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 2>, tmA, tmA2, tmB, p));
         count_launch();
         return TDRN_OK;
     }
     TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const int total = p.m_tiles * p.n_tiles;
-    conv_tc_kernel<BN, 1><<<total < g_num_sms ? total : g_num_sms, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+    conv_tc_kernel<BN, 1><<<total < g_num_sms ? total : g_num_sms, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, p);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }
@@ -425,6 +439,22 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     const int tiles_n = (p.B + p.bn - 1) / p.bn;
     p.a_bytes = (uint32_t)(p.bw * p.bh * p.bn) * 128u;
     p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+    // ragged tail: full-width single-image boxes that do not divide H (40x40 -> 13 boxes of 3 rows + 1 leftover row):
+    // batch the leftover rows of several images into one tile instead of spending a 128-row tile on rr*bw pixels
+    static const bool no_tail = getenv("TDRN_NO_TAIL_TILES") != nullptr;
+    if (!no_tail && !p.pool && !d->deconv2x2 && stride == 1 && p.bn == 1 && p.bw == p.W && p.H % p.bh != 0 && p.H > p.bh) {
+        p.qh = p.H / p.bh; p.rr = p.H - p.qh * p.bh;
+        p.g2 = 128 / (p.bw * p.rr);
+        if (p.g2 > p.B) p.g2 = p.B;
+        if (p.g2 >= 2) {
+            p.tiles_h = p.qh;                                        // regular tiles: mt = tn * qh + th
+            p.nA = p.qh * p.B;
+            p.m_tiles = p.nA + (p.B + p.g2 - 1) / p.g2;
+            p.a_bytes2 = (uint32_t)(p.bw * p.rr * p.g2) * 128u;
+        } else {
+            p.rr = 0;
+        }
+    }
 
     const int n_pad16 = (p.n_total + 15) & ~15;
     int BN = n_pad16 > 128 ? 256 : (n_pad16 > 64 ? 128 : 64);
@@ -439,7 +469,7 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     while (BN > 64 && p.m_tiles * ((n_pad16 + BN - 1) / BN) * 2 <= g_num_sms) BN >>= 1;
     p.n_tiles = (n_pad16 + BN - 1) / BN;
 
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmA2, tmB;
     bool use_cluster = false;
     {
         const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
@@ -449,6 +479,12 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
         int rc = make_tmap_bf16(&tmA, in, 4, dims, str, box, es);
         if (rc) return rc;
+        tmA2 = tmA;
+        if (p.rr) {
+            const uint32_t box2[4] = {64, (uint32_t)p.bw, (uint32_t)p.rr, (uint32_t)p.g2};
+            rc = make_tmap_bf16(&tmA2, in, 4, dims, str, box2, es);
+            if (rc) return rc;
+        }
     }
     {
         const uint64_t K = (uint64_t)p.taps * d->Cin;
@@ -467,7 +503,7 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         if (rc) return rc;
     }
     cudaStream_t st = as_stream(stream);
-    if (BN == 256) return launch_tc<256>(tmA, tmB, p, use_cluster, st);
-    if (BN == 128) return launch_tc<128>(tmA, tmB, p, use_cluster, st);
-    return launch_tc<64>(tmA, tmB, p, use_cluster, st);
+    if (BN == 256) return launch_tc<256>(tmA, tmA2, tmB, p, use_cluster, st);
+    if (BN == 128) return launch_tc<128>(tmA, tmA2, tmB, p, use_cluster, st);
+    return launch_tc<64>(tmA, tmA2, tmB, p, use_cluster, st);
 }
