@@ -93,7 +93,7 @@ struct NmsP {
     const float *dets;        // [n,5]
     int n;
     int *keep; int *num_keep;
-    float *kept_ws;           // [5][kept_cap] global scratch for the kept list (SoA)
+    float *kept_ws;           // global scratch for the kept list: float4 box[kept_cap] then float area[kept_cap]
     // common
     int max_keep;             // <= 0: unlimited
     int kept_cap;             // stride of the kept SoA arrays
@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
     }
     float *kept = DETECT ? kept_s : p.kept_ws;
     const int kc = p.kept_cap;
-    float *kx1 = kept, *ky1 = kept + kc, *kx2 = kept + 2 * kc, *ky2 = kept + 3 * kc, *kar = kept + 4 * kc;
+    float4 *kbox = (float4 *)kept;          // kept boxes as float4 (one 16-byte load per IoU test) + areas behind them
+    float *kar = kept + 4 * kc;
 
     // composite key of element i, or 0 if it is not a candidate / not below the current bound
     auto key_of = [&](int i, unsigned long long hi_incl) -> unsigned long long {
@@ -304,8 +305,9 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
                 if (ci < cnt) {
                     const float4 bx = cbox[ci];
                     const float ar = carea[ci];
+                    // (a group vote that stops all 8 sub-lanes at the first hit was measured slower: 0.276 vs 0.233 ms)
                     for (unsigned q = l; q < kept_n && !sup; q += 8)        // vs boxes kept so far
-                        sup = iou_ge(make_float4(kx1[q], ky1[q], kx2[q], ky2[q]), kar[q], bx, ar, p.thr_up);
+                        sup = iou_ge(kbox[q], kar[q], bx, ar, p.thr_up);
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {                         // my 4 columns of the 32x32 chunk matrix
                         const int j = l * 4 + jj;
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
                 if ((keepmask >> lane) & 1u) {
                     const unsigned pos = kept_n + __popc(keepmask & ((1u << lane) - 1u));
                     const float4 kb = cbox[lane];
-                    kx1[pos] = kb.x; ky1[pos] = kb.y; kx2[pos] = kb.z; ky2[pos] = kb.w; kar[pos] = carea[lane];
+                    kbox[pos] = kb; kar[pos] = carea[lane];
                     if (DETECT) {
                         const float4 nb = p.boxes[(long long)b * p.P + cidx[lane]];
                         float *o = out_seg + pos * 5;                       // detection.py:61-63
