@@ -126,8 +126,9 @@ int tdrn_conv2d(const tdrn_conv_desc *d, const void *in, const float *weight_f32
                 const void *residual, const float *offsets, void *out, tdrn_stream_t stream);
 
 /* tcgen05/TMEM/TMA implicit GEMM, bf16 in, fp32 accumulate, bf16 or fp32 out.
-   weight_bf16 packed [Cout_pad][kh*kw*Cin] K-major (Cout_pad = Cout rounded up to 16).
-   Requires Cin % 64 == 0 and stride 1 or 2.  Returns TDRN_EUNSUPPORTED otherwise (caller picks tdrn_conv2d). */
+   weight_bf16 packed [Cout_pad][kh*kw*Cin_pad] K-major (Cout_pad = Cout rounded up to 16, Cin_pad = Cin rounded up
+   to 64 with zero weights for the padding channels).
+   Requires Cin % 8 == 0 and stride 1 or 2.  Returns TDRN_EUNSUPPORTED otherwise (caller picks tdrn_conv2d). */
 int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in_bf16, const void *weight_bf16, const float *bias,
                    const void *residual, void *out, tdrn_stream_t stream);
 

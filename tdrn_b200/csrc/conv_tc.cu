@@ -397,9 +397,11 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
                               const void *residual, void *out, tdrn_stream_t stream)
 {
     TDRN_REQUIRE(d && in && weight && out, "tdrn_conv2d_tc: null argument");
-    if (d->in_dtype != TDRN_BF16 || d->Cin % 64 != 0 || d->dg != 0 || d->in_sb != 0 ||
+    // Cin that is a multiple of 8 but not of 64 (MobileNet's 32-channel stem output): the channel box still asks for 64
+    // channels, TMA zero-fills the ones beyond Cin, and the packed weights carry zero rows for them (K padded per tap).
+    if (d->in_dtype != TDRN_BF16 || d->Cin % 8 != 0 || d->dg != 0 || d->in_sb != 0 ||
         (!d->deconv2x2 && d->stride != 1 && d->stride != 2)) {
-        set_error("tdrn_conv2d_tc: needs bf16 input, Cin %% 64 == 0, stride 1 or 2, no offsets (got dtype=%d Cin=%d stride=%d dg=%d)",
+        set_error("tdrn_conv2d_tc: needs bf16 input, Cin %% 8 == 0, stride 1 or 2, no offsets (got dtype=%d Cin=%d stride=%d dg=%d)",
                   d->in_dtype, d->Cin, d->stride, d->dg);
         return TDRN_EUNSUPPORTED;
     }
@@ -417,7 +419,8 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     p.H = (d->H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
     p.W = (d->W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
     TDRN_REQUIRE(p.H > 0 && p.W > 0, "convolution input is too small (output would be %dx%d)", p.H, p.W);
-    p.B = d->B; p.Cin = d->Cin; p.Cout = d->Cout; p.n_total = d->deconv2x2 ? 4 * d->Cout : d->Cout;
+    // p.Cin is padded to 64: the k-block count and the weight K use it, the activation tensor map uses the real Cin
+    p.B = d->B; p.Cin = (d->Cin + 63) & ~63; p.Cout = d->Cout; p.n_total = d->deconv2x2 ? 4 * d->Cout : d->Cout;
     p.kw = kw; p.taps = kh * kw; p.pad = pad; p.dil = dil; p.stride = stride;
     p.bias = bias; p.res = residual; p.out = out;
     p.out_sb = d->out_sb; p.out_sp = d->out_sp;
@@ -487,7 +490,7 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         }
     }
     {
-        const uint64_t K = (uint64_t)p.taps * d->Cin;
+        const uint64_t K = (uint64_t)p.taps * p.Cin;
         const uint64_t dims[2] = {K, (uint64_t)n_pad16};
         const uint64_t str[1] = {K * 2};
         const uint32_t b_rows = (uint32_t)(n_pad16 < BN ? n_pad16 : BN);

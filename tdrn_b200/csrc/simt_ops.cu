@@ -240,6 +240,93 @@ __global__ void dwconv3x3_kernel(const T *__restrict__ in, const float *__restri
     }
 }
 
+// bf16 fast path: a thread owns 8 channels (one 16-byte vector) of XT consecutive output pixels of a row, so every
+// input vector it loads feeds up to three outputs; consecutive threads take consecutive channel groups (coalesced
+// 16-byte accesses); packed fp32x2 FMAs.  HBM-bound by design (the scalar kernel above was ~30x off).
+__device__ __forceinline__ unsigned long long dw_unpack(uint32_t a)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a << 16), "r"(a & 0xffff0000u));
+    return r;
+}
+__device__ __forceinline__ unsigned long long dw_fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long dw_pair(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+
+template <int STRIDE>
+__global__ void __launch_bounds__(128) dwconv3x3_bf16_kernel(const uint4 *__restrict__ in, const float *__restrict__ w,
+                                                             const float *__restrict__ bias, uint4 *__restrict__ out,
+                                                             int B, int H, int W, int C, int Ho, int Wo, int relu)
+{
+    constexpr int XT = 4, NCOL = (XT - 1) * STRIDE + 3;
+    const int CG = C >> 3, XS = (Wo + XT - 1) / XT;
+    const long long total = (long long)B * Ho * XS * CG;
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cg = (int)(idx % CG);
+    long long t = idx / CG;
+    const int xs = (int)(t % XS); t /= XS;
+    const int y = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const int x0 = xs * XT;
+    unsigned long long acc[XT][4];
+    {
+        const float4 b0 = bias ? __ldg((const float4 *)(bias + cg * 8)) : make_float4(0, 0, 0, 0);
+        const float4 b1 = bias ? __ldg((const float4 *)(bias + cg * 8 + 4)) : make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int p = 0; p < XT; ++p) { acc[p][0] = dw_pair(b0.x, b0.y); acc[p][1] = dw_pair(b0.z, b0.w); acc[p][2] = dw_pair(b1.x, b1.y); acc[p][3] = dw_pair(b1.z, b1.w); }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int yy = y * STRIDE - 1 + i;
+        if (yy < 0 || yy >= H) continue;
+        unsigned long long wt[3][4];                              // this kernel row's 3 taps x 8 channels
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float4 w0 = __ldg((const float4 *)(w + (i * 3 + j) * C + cg * 8)), w1 = __ldg((const float4 *)(w + (i * 3 + j) * C + cg * 8 + 4));
+            wt[j][0] = dw_pair(w0.x, w0.y); wt[j][1] = dw_pair(w0.z, w0.w); wt[j][2] = dw_pair(w1.x, w1.y); wt[j][3] = dw_pair(w1.z, w1.w);
+        }
+        const uint4 *row = in + (((long long)b * H + yy) * W) * CG + cg;
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c) {
+            const int xx = x0 * STRIDE - 1 + c;
+            if (xx < 0 || xx >= W) continue;
+            const uint4 v = __ldg(row + (long long)xx * CG);
+            const unsigned long long u[4] = {dw_unpack(v.x), dw_unpack(v.y), dw_unpack(v.z), dw_unpack(v.w)};
+#pragma unroll
+            for (int p = 0; p < XT; ++p) {
+                const int j = c - p * STRIDE;                      // tap column of input column c for output p
+                if (j < 0 || j > 2) continue;                      // compile-time after unrolling
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[p][q] = dw_fma2(wt[j][q], u[q], acc[p][q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < XT; ++p) {
+        const int x = x0 + p;
+        if (x >= Wo) break;
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[p][q]));
+            if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o[q]) : "f"(hi), "f"(lo));
+        }
+        out[(((long long)b * Ho + y) * Wo + x) * CG + cg] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // MaxPool2d(2, 2, ceil_mode) NHWC
 // ------------------------------------------------------------------------------------------------
@@ -321,7 +408,7 @@ __global__ void __launch_bounds__(256, 4) l2norm_pool_kernel(const uint4 *__rest
                 s = fmaf(lo, lo, s); s = fmaf(hi, hi, s);
             }
             if (q == 0) mx[v] = xv;
-            else {
+            else if (out_pool) {
                 const __nv_bfloat162 *x2 = (const __nv_bfloat162 *)&xv;
                 __nv_bfloat162 *m2 = (__nv_bfloat162 *)&mx[v];
 #pragma unroll
@@ -330,9 +417,11 @@ __global__ void __launch_bounds__(256, 4) l2norm_pool_kernel(const uint4 *__rest
         }
         ss[q] = s;
     }
-    const long long po = ((long long)b * Ho + py) * Wo + px;
+    if (out_pool) {                                              // NULL: plain L2Norm (any grouping of 4 pixels per warp)
+        const long long po = ((long long)b * Ho + py) * Wo + px;
 #pragma unroll
-    for (int v = 0; v < CV; ++v) out_pool[po * PV + v * 32 + lane] = mx[v];
+        for (int v = 0; v < CV; ++v) out_pool[po * PV + v * 32 + lane] = mx[v];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -521,6 +610,16 @@ extern "C" int tdrn_dwconv3x3(const void *in, const float *weight, const float *
     TDRN_REQUIRE(in && weight && out && B > 0 && H > 0 && W > 0 && C > 0, "tdrn_dwconv3x3: bad argument");
     const int Ho = conv_out_dim(H, 3, stride, 1, 1), Wo = conv_out_dim(W, 3, stride, 1, 1);
     const long long total = (long long)B * Ho * Wo * C;
+    if (dtype == TDRN_BF16 && C % 8 == 0 && (stride == 1 || stride == 2)) {
+        const long long threads = (long long)B * Ho * ((Wo + 3) / 4) * (C / 8);
+        const int grid = (int)((threads + 127) / 128);
+        if (stride == 1)
+            dwconv3x3_bf16_kernel<1><<<grid, 128, 0, as_stream(stream)>>>((const uint4 *)in, weight, bias, (uint4 *)out, B, H, W, C, Ho, Wo, relu);
+        else
+            dwconv3x3_bf16_kernel<2><<<grid, 128, 0, as_stream(stream)>>>((const uint4 *)in, weight, bias, (uint4 *)out, B, H, W, C, Ho, Wo, relu);
+        TDRN_LAUNCH_CHECK();
+        return TDRN_OK;
+    }
     if (dtype == TDRN_F32)
         dwconv3x3_kernel<float><<<grid_1d(total, 256), 256, 0, as_stream(stream)>>>((const float *)in, weight, bias, (float *)out, B, H, W, C, Ho, Wo, stride, relu);
     else
@@ -545,6 +644,17 @@ extern "C" int tdrn_maxpool2x2(const void *in, void *out, int B, int H, int W, i
 extern "C" int tdrn_l2norm(const void *in, const float *weight, void *out, long long pixels, int C, int dtype, tdrn_stream_t stream)
 {
     TDRN_REQUIRE(in && weight && out && pixels > 0 && C > 0, "tdrn_l2norm: bad argument");
+    if (dtype == TDRN_BF16 && (C == 256 || C == 512 || C == 1024) && pixels % 4 == 0 && pixels / 2 < (1LL << 30)) {
+        // vectorised path: the fused L2Norm+pool kernel without its pool output, 4 consecutive pixels per warp
+        const int Wv = (int)(pixels / 2);
+        const int g = (int)((pixels / 4 * 32 + 255) / 256);
+        cudaStream_t st = as_stream(stream);
+        if (C == 256) l2norm_pool_kernel<1><<<g, 256, 0, st>>>((const uint4 *)in, weight, (uint4 *)out, nullptr, 1, 2, Wv);
+        else if (C == 512) l2norm_pool_kernel<2><<<g, 256, 0, st>>>((const uint4 *)in, weight, (uint4 *)out, nullptr, 1, 2, Wv);
+        else l2norm_pool_kernel<4><<<g, 256, 0, st>>>((const uint4 *)in, weight, (uint4 *)out, nullptr, 1, 2, Wv);
+        TDRN_LAUNCH_CHECK();
+        return TDRN_OK;
+    }
     const int grid = grid_1d(pixels * 32, 256);
     if (dtype == TDRN_F32)
         l2norm_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)in, weight, (float *)out, pixels, C);

@@ -73,7 +73,7 @@ class PackedConv(object):
     """Weights of one conv layer, BN-folded, packed for both kernels.
 
     w_f32  [kh*kw*Cin, Cout] fp32 (tap-major, then cin)      -> tdrn_conv2d (SIMT, fp32 accumulate)
-    w_bf16 [Cout_pad, kh*kw*Cin] bf16, K-major               -> tdrn_conv2d_tc (tcgen05)
+    w_bf16 [Cout_pad, kh*kw*Cin_pad] bf16, K-major           -> tdrn_conv2d_tc (tcgen05); Cin_pad = Cin up to 64
     deconv (ConvTranspose2d k2 s2, weight [Cin,Cout,2,2]): w_f32 [Cin, 4*Cout] with n = (i*2+j)*Cout+co
     """
 
@@ -101,12 +101,14 @@ class PackedConv(object):
             wk = w.permute(0, 2, 3, 1).reshape(self.cout, self.kh * self.kw * self.cin)
         self.bias = b.float().contiguous().to(device) if b is not None else None
         self.w_bf16 = None
-        if want_bf16 and self.cin % 64 == 0:
+        if want_bf16 and self.cin % 8 == 0 and self.cin >= 16:
             rows = wk.shape[0]
             rows_pad = (rows + 15) // 16 * 16
-            wp = torch.zeros(rows_pad, wk.shape[1], dtype=torch.float64)
-            wp[:rows] = wk
-            self.w_bf16 = wp.to(torch.bfloat16).contiguous().to(device)
+            cin_pad = (self.cin + 63) // 64 * 64                 # K padded per tap: the TMA channel box is 64 wide
+            taps = wk.shape[1] // self.cin
+            wp = torch.zeros(rows_pad, taps, cin_pad, dtype=torch.float64)
+            wp[:rows, :, :self.cin] = wk.reshape(rows, taps, self.cin)
+            self.w_bf16 = wp.reshape(rows_pad, taps * cin_pad).to(torch.bfloat16).contiguous().to(device)
 
 
 def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_sb=None, out_sp=None,
@@ -181,8 +183,9 @@ def dwconv3x3(x_nhwc, pd, relu=True):
     B, H, W, C = x.shape
     Ho, Wo = conv_out(H, 3, pd.stride, 1, 1), conv_out(W, 3, pd.stride, 1, 1)
     out = torch.empty(B, Ho, Wo, C, dtype=x.dtype, device=x.device)
-    check(_lib.lib().tdrn_dwconv3x3(ptr(x), ptr(pd.w), ptr(pd.bias), ptr(out), B, H, W, C, pd.stride, int(relu),
-                                    _dt(x), stream_handle()), 'tdrn_dwconv3x3')
+    with _Timed('aux|dwconv3x3 %d s%d @%dx%d' % (C, pd.stride, H, W), float((x.numel() + out.numel()) * x.element_size())):
+        check(_lib.lib().tdrn_dwconv3x3(ptr(x), ptr(pd.w), ptr(pd.bias), ptr(out), B, H, W, C, pd.stride, int(relu),
+                                        _dt(x), stream_handle()), 'tdrn_dwconv3x3')
     return out
 
 

@@ -154,3 +154,31 @@ def test_l2norm_pool_fused(b, c, h, w):
     out_n, out_p = ops.l2norm_pool(x.cuda(), wt.cuda())
     assert torch.equal(out_p.cpu(), ref_p)
     assert rel_err(out_n.float().cpu().numpy(), ref_n.float().numpy()) < 8e-3          # one bf16 ulp
+
+
+@pytest.mark.parametrize('stride', [1, 2])
+@pytest.mark.parametrize('b,c,h,w', [(2, 24, 11, 13), (3, 64, 16, 16), (1, 256, 7, 9)])
+def test_dwconv3x3_bf16_vectorised(b, c, h, w, stride):
+    """Depthwise 3x3 + folded BN + ReLU (conv_dw first half, model/networks.py:738-740), bf16 fast path: 8 channels per
+    thread, 4 output pixels per thread; fp32 reference on the bf16-rounded input; tolerance = bf16 output rounding."""
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(c + h + stride)
+    x = torch.randn(b, c, h, w, generator=g).to(torch.bfloat16)
+    wd = torch.randn(c, 1, 3, 3, generator=g)
+    bn = (torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g), torch.randn(c, generator=g), torch.rand(c, generator=g) + 0.5)
+    ref = F.relu(F.batch_norm(F.conv2d(x.float(), wd, None, stride, 1, 1, c), bn[2], bn[3], bn[0], bn[1], False, 0.0, 1e-5))
+    out = ops.dwconv3x3(x.permute(0, 2, 3, 1).contiguous().cuda(), ops.PackedDw(wd, bn, stride, 'cuda'))
+    assert out.dtype == torch.bfloat16
+    assert rel_err(out.float().permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 6e-3
+
+
+def test_l2norm_bf16_vectorised():
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    for c, px in ((512, 40), (1024, 12), (256, 6)):
+        x = (torch.randn(2, px, 2, c, generator=g) * 2).to(torch.bfloat16)
+        wt = torch.rand(c, generator=g) * 20 + 1
+        xf = x.float()
+        ref = (wt * (xf / (xf.pow(2).sum(3, keepdim=True).sqrt() + 1e-10))).to(torch.bfloat16)
+        out = ops.l2norm(x.cuda(), wt.cuda())
+        assert rel_err(out.float().cpu().numpy(), ref.float().numpy()) < 8e-3

@@ -38,6 +38,8 @@ def _bf(x):
     (2, 128, 32, 3, 1, 1, 32, 24, True),       # halo kernel: two resident channel blocks, Cout < 64
     (1, 64, 48, 3, 1, 1, 16, 8, False),        # halo kernel: a single 8x16 tile, Cout = 48 (three 16-column chunks)
     (3, 64, 128, 3, 1, 1, 64, 64, True),       # halo kernel BN=128 (conv2_1 class), 96 tiles
+    (4, 32, 64, 1, 0, 1, 40, 40, True),        # Cin = 32 (MobileNet pw1): 64-channel TMA box zero-fills channels 32..63
+    (2, 96, 64, 3, 1, 1, 16, 16, False),       # Cin = 96: second channel block half out of bounds
     (2, 128, 256, 3, 1, 1, 32, 48, True),      # streamed halo kernel: two channel blocks, two 128-wide N tiles (conv3_1 class)
     (5, 128, 128, 3, 1, 1, 64, 96, False),     # streamed halo kernel: 120 units, both TMEM buffers and the 7-stage weight ring wrap
 ])
