@@ -286,7 +286,7 @@ def run_gpu(args, rank, world, local_rank):
     def timed(step_fn, steps, warmup):
         pipe['primed'] = -1
         with torch.cuda.stream(stream):
-            for i in range(warmup):
+            for i in range(max(warmup, 12)):               # W is a minimum: a few more replays let the clocks settle
                 step_fn(i)
             stream.synchronize()
             if world > 1:
@@ -295,7 +295,7 @@ def run_gpu(args, rank, world, local_rank):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for i in range(steps):
-                step_fn(warmup + i)
+                step_fn(max(warmup, 12) + i)
             stream.wait_stream(copy_stream)                     # e2e: the last step's D2H is inside the timed region
             e1.record(stream)
             stream.synchronize()
