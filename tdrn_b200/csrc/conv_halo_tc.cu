@@ -56,7 +56,7 @@ __device__ __forceinline__ void halo_epilogue_tile(const HaloP &p, uint32_t trow
                                            int b, int x, int y, int wl, int hl)
 {
     const bool valid = x < p.W && y < p.H;
-    for (int c0 = half * 32; c0 < (p.debug_skip_epilogue ? 0 : ncols); c0 += 64) {
+    for (int c0 = half * 32; c0 < (p.debug_skip_epilogue == 1 ? 0 : ncols); c0 += 64) {
         float v[32];
         tmem_ld32(trow + (uint32_t)c0, v);
         if (n0 + c0 >= p.Cout) continue;                     // warp-uniform
@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) conv_halo_stream_kernel(const _
                     for (int tap = 0; tap < 9; ++tap, ++jt) {
                         const uint32_t s = jt % HS_B_STAGES, ph = (jt / HS_B_STAGES) & 1u;
                         mbar_wait(&b_empty[s], ph ^ 1u);
+                        if (p.debug_skip_epilogue == 2 && (jt & 1u)) { mbar_arrive(&b_full[s]); continue; }   // timing experiment: half the weight traffic
                         mbar_expect_tx(&b_full[s], HS_B_BYTES);
                         tma_load_2d(sB + (size_t)s * HS_B_BYTES, &tmB, &b_full[s], (tap * p.cblocks + cb) * 64, n0);
                     }
@@ -428,7 +429,7 @@ int conv_halo_try(const tdrn_conv_desc *d, const void *in, const void *weight, c
     p.bias = bias; p.out = out; p.out_sb = d->out_sb; p.out_sp = d->out_sp;
     p.relu = d->relu; p.out_f32 = d->out_dtype == TDRN_F32; p.pool = d->pool2x2;
     p.out_w = p.pool ? d->W / 2 : d->W;
-    { static const bool dbg = getenv("TDRN_HALO_DEBUG") != nullptr; p.debug_skip_epilogue = dbg; }
+    { static const int dbg = getenv("TDRN_HALO_DEBUG") ? atoi(getenv("TDRN_HALO_DEBUG")) : 0; p.debug_skip_epilogue = dbg; }
     if (!g_halo_sms) {
         int dev = 0;
         TDRN_CUDA(cudaGetDevice(&dev));
