@@ -216,7 +216,9 @@ def run_gpu(args, rank, world, local_rank):
         arm_loc, _, loc, conf = net(x)
         return det.forward(loc, conf, priors, arm_loc_data=arm_loc)
 
-    stream = torch.cuda.Stream(dev)
+    # the critical path (trunk -> FPN chain -> level-0 head -> Detect) runs on this stream; the forked ARM / TCB / small-level
+    # branches run on default-priority side streams, so give the main stream scheduling priority over them
+    stream = torch.cuda.Stream(dev, priority=int(os.environ.get('TDRN_BENCH_PRIO', '-1')))
     torch.cuda.synchronize()
     with torch.cuda.stream(stream), torch.no_grad():
         for i in range(3):                      # eager warm-up: packs weights, sizes workspaces, loads kernels

@@ -70,6 +70,7 @@ struct TcConvP {
     // ragged-tail tiles: when H = qh*bh + rr (rr > 0) with full-width single-image boxes, the rr leftover rows of g2
     // consecutive images are batched into one tile (second tensor map, box (64, bw, rr, g2)); nA = #regular tiles
     int nA, qh, rr, g2; uint32_t a_bytes2;
+    int l2_prefetch;             // producer prefetches its first weight slice into L2 (few-tile layers)
     uint32_t b_bytes;            // bytes one B box deposits (min(BN, n_pad16)*128)
     const float *bias; const void *res; void *out;
     long long out_sb, out_sp; int out_w;
@@ -135,6 +136,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            // The weights of the small-map layers are cold in L2 every step (1 GB of activations went through it since
+            // their last use) and each CTA streams them through a ring that only holds a few k-blocks: prefetch this
+            // CTA's first weight slice into L2 now, all boxes at once.
+            if (p.l2_prefetch && unit0 < total_tiles) {
+                const int n0p = (unit0 / m_units) * BN + (CL == 2 ? cr * (int)(p.b_bytes >> 8) : 0);
+                for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_l2_2d(&tmB, kb * 64, n0p);
+            }
             uint32_t it = 0;                                   // running k-block counter across tiles
             for (int tile = unit0; tile < total_tiles; tile += unit_step) {
                 const int mt = (tile % m_units) * CL + cr, nt = tile / m_units;
@@ -504,6 +512,10 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         p.b_bytes = b_rows * 128u;
         int rc = make_tmap_bf16(&tmB, weight, 2, dims, str, box, nullptr);
         if (rc) return rc;
+    }
+    {   // opt-in experiment (TDRN_L2_PREFETCH=1): measured slower on B200 (3.13 vs 3.06 ms per step), so it stays off
+        static const bool pf = getenv("TDRN_L2_PREFETCH") != nullptr;
+        p.l2_prefetch = pf && p.m_tiles * p.n_tiles <= 2 * g_num_sms;
     }
     cudaStream_t st = as_stream(stream);
     if (BN == 256) return launch_tc<256>(tmA, tmA2, tmB, p, use_cluster, st);

@@ -62,6 +62,13 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *m, uin
                  ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// Ask L2 to fetch a 2-D box (no shared-memory destination, no completion to wait for): used to pull a layer's whole
+// weight slice out of HBM up front, so that the latency the smem ring later sees is L2's, not DRAM's.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *m, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)m), "r"(c0), "r"(c1) : "memory");
+}
+
 // B-operand box delivered to the same shared-memory offset of every CTA in `mask` (thread-block cluster); each
 // destination CTA's mbarrier at the same offset receives the complete_tx.
 __device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, uint16_t mask)
