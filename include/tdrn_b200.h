@@ -187,6 +187,18 @@ int tdrn_deform_head(const tdrn_deform_head_desc *d, const void *feat, const flo
                      const void *weight, const float *offsets2, const void *weight2,
                      float *loc_out, float *conf_out, tdrn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (next row) Result scatter of the evaluation drivers: evaluate.py:469-483, evaluate_coco.py:140-159
+ * (per image and class: masked_select(score > 0), boxes * (w,h,w,h), .cpu()).  One call for the whole batch:
+ *   det [B,C,top_k,5] (Detect output), wh [B,2] = original (width, height) of every image (device, fp32)
+ *   -> out_rows [n,7] = (image, class, x1*w, y1*h, x2*w, y2*h, score), ordered by image, class, rank;
+ *      *count = n on the device (rows beyond max_rows are counted but not written).  Class 0 is skipped.
+ * workspace >= tdrn_collect_workspace_bytes(B, C).
+ * ------------------------------------------------------------------------------------------ */
+size_t tdrn_collect_workspace_bytes(int B, int C);
+int tdrn_collect_detections(const float *det, const float *wh, int B, int C, int top_k, float *out_rows, int max_rows,
+                            int *count, void *workspace, size_t workspace_bytes, tdrn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -139,3 +139,33 @@ def test_detect_coco512_shape():
     boxes = ops.decode(loc.cuda(), pri.cuda(), None).cpu().numpy()
     ref = C.detect(boxes, conf.numpy(), np.array([512.] * 4, np.float32), Cn, 100, 0.01, 0.45)
     assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_collect_detections_matches_eval_loop():
+    """tdrn_collect_detections == the reference's per-image / per-class masked_select + scale + hstack (evaluate.py:469-483),
+    bit for bit, including empty segments, a non-prefix mask and the row cap."""
+    from oracle.eval_ref import all_boxes_ref
+    from tdrn_b200.utils.results import collect_detections, to_all_boxes
+    g = torch.Generator().manual_seed(5)
+    B, C, K = 5, 7, 40
+    det = torch.zeros(B, C, K, 5)
+    for b in range(B):
+        for c in range(C):
+            n = int(torch.randint(0, K + 1, (1,), generator=g)) if (b + c) % 3 else 0
+            det[b, c, :n, 0] = torch.rand(n, generator=g).sort(descending=True)[0] + 0.01
+            det[b, c, :n, 1:] = torch.rand(n, 4, generator=g)
+    det[2, 3, 5, 0] = 0.0                                            # a hole: the mask is not a prefix
+    det[:, 0] = torch.rand(B, K, 5, generator=g)                     # background rows must be ignored
+    sizes = [(500, 375), (353, 500), (1280, 720), (320, 320), (64, 48)]
+    ref = all_boxes_ref(det, sizes)
+    rows, n = collect_detections(det.cuda(), sizes)
+    got = to_all_boxes(rows, B, C)
+    assert n == sum(len(ref[c][b]) for c in range(C) for b in range(B)) == rows.shape[0]
+    for c in range(C):
+        for b in range(B):
+            if len(ref[c][b]) == 0:
+                assert len(got[c][b]) == 0
+            else:
+                assert np.array_equal(got[c][b], ref[c][b]), (c, b)
+    capped, n2 = collect_detections(det.cuda(), sizes, max_rows=17)
+    assert n2 == n and capped.shape[0] == 17 and torch.equal(capped, rows[:17])
