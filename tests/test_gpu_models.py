@@ -181,3 +181,52 @@ def test_end_to_end_detections_fp32(golden):
     assert np.abs(det[0, 1:, :top, 0] - ref[0, 1:, :top, 0]).max() < 1e-4
     agree = np.abs(det[0, 1:, :top, 1:] - ref[0, 1:, :top, 1:]).max(-1) < 1e-3
     assert agree.mean() > 0.97
+
+
+def test_tdrn_stream_follows_the_reference_loop():
+    """TDRNStream (tdrn_b200/utils/tdrn_stream.py) == the loop of evaluate_trn.py:434-467 restated with the oracle's
+    functional nets: key frames at the start of a video and every `interval` frames, cached offsets in between, the
+    (loosened) key-frame regression as the ARM stage of Detect.  fp32 path: boxes/scores of every frame within 1e-4."""
+    from oracle import model_ref as M, detect_ref as D
+    from oracle.make_golden import SEED_W, make_input
+    from tdrn_b200.model import ssd4scale_vgg as S
+    from tdrn_b200.layers.functions import Detect, PriorBox
+    from tdrn_b200.data import mb_cfg
+    from tdrn_b200.utils.tdrn_stream import TDRNStream
+    from tdrn_b200 import ops
+    C, interval, loose = 31, 3, 0.9
+    sd_s = M.make_state_dict(M.param_spec_ssd4scale_vgg(C, bn=True, deform=False), SEED_W)
+    sd_t = M.make_state_dict(M.param_spec_ssd4scale_vgg(C, bn=True, deform=True), SEED_W + 1)
+    static = S.build_net('test', 320, C, bn=True, deform=False)
+    temporal = S.build_net('test', 320, C, bn=True, deform=True)
+    static.load_state_dict(sd_s); temporal.load_state_dict(sd_t)
+    static = static.eval().cuda().set_precision('fp32')
+    temporal = temporal.eval().cuda().set_precision('fp32')
+    pri = PriorBox(mb_cfg['VOC_320']).forward()
+    stream = TDRNStream(static, temporal, Detect(C, 0, 200, 0.01, 0.45), pri.cuda(), interval=interval, loose=loose)
+    frames = [make_input(1, 320, seed=40 + i) for i in range(5)]
+    videos = ['a', 'a', 'a', 'a', 'b']                       # key frames: 0 (new video), 3 (interval), 4 (new video)
+    # --- oracle loop ---
+    pre, cur, offs, ref_loc, s_out, expect_keys, keys = None, 0, [], [], None, [0, 3, 4], []
+    for i, (x, v) in enumerate(zip(frames, videos)):
+        with torch.no_grad():
+            if v != pre or cur % interval == 0:
+                keys.append(i)
+                s_out = list(M.ssd4scale_vgg_forward(sd_s, x, C, bn=True, deform=False, ret_loc=True))
+                s_out[0] = s_out[0] * loose
+                ref_loc, offs = s_out[2], []
+                if v != pre:
+                    pre, cur = v, 0
+            out = M.ssd4scale_vgg_forward(sd_t, x, C, bn=True, deform=True, ref_loc=ref_loc, offset_list=offs, ret_off=not offs)
+            if len(out) == 3:
+                offs, ref_loc = out[2], []
+            cur += 1
+            was_key = stream.is_key_frame(v)
+            det = stream.step(x.cuda(), v)
+        assert was_key == (i in expect_keys)
+        # same decoded boxes (two-stage decode against the loosened key-frame regression) and scores, frame by frame
+        boxes_ref = D.decode(out[0][0], D.center_size(D.decode(s_out[0][0], pri, [0.1, 0.2])), [0.1, 0.2])
+        boxes = ops.decode(stream.net(x.cuda(), ref_loc=[], offset_list=stream.offset_list)[0], pri.cuda(), stream.static_out[0])
+        assert rel_err(boxes[0].cpu().numpy(), boxes_ref.numpy()) < 1e-4
+        assert det.shape == (1, C, 200, 5) and float(det[0, 1:, 0, 0].min()) > 0.01
+    assert keys == expect_keys
