@@ -196,57 +196,71 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform_head_kernel(const __grid
         const char *fbytes = (const char *)p.feat;
         const uint32_t cin2 = (uint32_t)p.Cin * 2u, row2 = (uint32_t)p.W * cin2;
         uint32_t s = 0, ph = 1;                                  // ring stage and the parity empty_bar[s] must have passed
-        for (int head = 0; head < 2; ++head) {
-            const int taps = p.taps[head];
-            const uint32_t gstep = (uint32_t)p.dg * 16u;
-            for (int cb = 0; cb < (taps ? cblocks : 0); ++cb) {
-                const int g = cb / blocks_per_group;
-                uint32_t goff = (uint32_t)((head ? p.taps[0] * p.dg : 0) + g) * 16u;
-                const uint32_t lane_off = (uint32_t)(cb << 7) + (uint32_t)(chunk << 4);
-                for (int tap = 0; tap < taps; ++tap, goff += gstep) {
-                    uint4 cv[2][4];                      // 2 rows x 4 corners: 8 independent 16-byte loads in flight
-                    float f[2][4];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        uint32_t e0, e1, e2, e3;
-                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3) : "r"((i ? geo_row1 : geo_row0) + goff));
-                        const uint32_t oa = (e0 & 0x3fffffffu) + lane_off;
-                        const uint32_t dxb = (uint32_t)((int32_t)(e0 << 1) >> 31) & cin2;
-                        const uint32_t dyb = (uint32_t)((int32_t)e0 >> 31) & row2;
-                        const uint32_t oc = oa + dyb;
-                        cv[i][0] = __ldg((const uint4 *)(fbytes + oa));
-                        cv[i][1] = __ldg((const uint4 *)(fbytes + (oa + dxb)));
-                        cv[i][2] = __ldg((const uint4 *)(fbytes + oc));
-                        cv[i][3] = __ldg((const uint4 *)(fbytes + (oc + dxb)));
-                        const float hh = __uint_as_float(e1), lh = __uint_as_float(e2), lw = __uint_as_float(e3), hw = 1.f - lw;
-                        f[i][0] = hh * hw; f[i][1] = hh * lw; f[i][2] = lh * hw; f[i][3] = lh * lw;      // .cu:47 (x inside flag)
-                    }
-                    mbar_wait(&empty_bar[s], ph);
-                    const uint32_t sa = tiles_s + s * (uint32_t)Cfg::STAGE_BYTES;
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        uint32_t o0, o1, o2, o3;                             // .cu:49, two channels per 32-bit lane
-                        if (F2) {
-                            const uint64_t w1 = pair_of(f[i][0], f[i][0]), w2 = pair_of(f[i][1], f[i][1]);
-                            const uint64_t w3 = pair_of(f[i][2], f[i][2]), w4 = pair_of(f[i][3], f[i][3]);
-                            o0 = blend2(cv[i][0].x, cv[i][1].x, cv[i][2].x, cv[i][3].x, w1, w2, w3, w4);
-                            o1 = blend2(cv[i][0].y, cv[i][1].y, cv[i][2].y, cv[i][3].y, w1, w2, w3, w4);
-                            o2 = blend2(cv[i][0].z, cv[i][1].z, cv[i][2].z, cv[i][3].z, w1, w2, w3, w4);
-                            o3 = blend2(cv[i][0].w, cv[i][1].w, cv[i][2].w, cv[i][3].w, w1, w2, w3, w4);
-                        } else {
-                            o0 = blend2s(cv[i][0].x, cv[i][1].x, cv[i][2].x, cv[i][3].x, f[i][0], f[i][1], f[i][2], f[i][3]);
-                            o1 = blend2s(cv[i][0].y, cv[i][1].y, cv[i][2].y, cv[i][3].y, f[i][0], f[i][1], f[i][2], f[i][3]);
-                            o2 = blend2s(cv[i][0].z, cv[i][1].z, cv[i][2].z, cv[i][3].z, f[i][0], f[i][1], f[i][2], f[i][3]);
-                            o3 = blend2s(cv[i][0].w, cv[i][1].w, cv[i][2].w, cv[i][3].w, f[i][0], f[i][1], f[i][2], f[i][3]);
-                        }
-                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sa + (i ? st_off1 : st_off0)), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
-                    }
-                    fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_bar[s]);
-                    if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
-                }
+        // Flat walk over the k-blocks (head, channel block, tap).  The corner loads of row-item i of the NEXT k-block are
+        // issued right after item i of the current k-block has been blended (same registers, no double buffer), so
+        // their L1/L2 latency overlaps the other item's blend, the fence/arrive and the ring wait instead of being
+        // paid in full at the top of every k-block.
+        const int taps0 = p.taps[0], taps1 = p.taps[1];
+        const uint32_t gstep = (uint32_t)p.dg * 16u;
+        const uint32_t ghead1 = (uint32_t)(taps0 * p.dg) * 16u;
+        int head = 0, cb = 0, tap = 0;
+        uint32_t goff = 0u, lane_off = (uint32_t)(chunk << 4);
+        bool valid = true;
+        auto advance = [&]() {                                    // -> (goff, lane_off) of the next k-block, or valid = false
+            const int taps = head ? taps1 : taps0;
+            if (++tap < taps) { goff += gstep; return; }
+            tap = 0;
+            if (++cb == cblocks) { cb = 0; ++head; if (head == 2 || taps1 == 0) { valid = false; return; } }
+            goff = (head ? ghead1 : 0u) + (uint32_t)(cb / blocks_per_group) * 16u;
+            lane_off = (uint32_t)(cb << 7) + (uint32_t)(chunk << 4);
+        };
+        uint4 cv[2][4];                                           // 2 rows x 4 corners: 8 independent 16-byte loads in flight
+        float f[2][4];
+        auto load_item = [&](int i) {
+            uint32_t e0, e1, e2, e3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3) : "r"((i ? geo_row1 : geo_row0) + goff));
+            const uint32_t oa = (e0 & 0x3fffffffu) + lane_off;
+            const uint32_t dxb = (uint32_t)((int32_t)(e0 << 1) >> 31) & cin2;
+            const uint32_t dyb = (uint32_t)((int32_t)e0 >> 31) & row2;
+            const uint32_t oc = oa + dyb;
+            cv[i][0] = __ldg((const uint4 *)(fbytes + oa));
+            cv[i][1] = __ldg((const uint4 *)(fbytes + (oa + dxb)));
+            cv[i][2] = __ldg((const uint4 *)(fbytes + oc));
+            cv[i][3] = __ldg((const uint4 *)(fbytes + (oc + dxb)));
+            const float hh = __uint_as_float(e1), lh = __uint_as_float(e2), lw = __uint_as_float(e3), hw = 1.f - lw;
+            f[i][0] = hh * hw; f[i][1] = hh * lw; f[i][2] = lh * hw; f[i][3] = lh * lw;      // .cu:47 (x inside flag)
+        };
+        auto blend_item = [&](int i, uint32_t sa) {
+            uint32_t o0, o1, o2, o3;                             // .cu:49, two channels per 32-bit lane
+            if (F2) {
+                const uint64_t w1 = pair_of(f[i][0], f[i][0]), w2 = pair_of(f[i][1], f[i][1]);
+                const uint64_t w3 = pair_of(f[i][2], f[i][2]), w4 = pair_of(f[i][3], f[i][3]);
+                o0 = blend2(cv[i][0].x, cv[i][1].x, cv[i][2].x, cv[i][3].x, w1, w2, w3, w4);
+                o1 = blend2(cv[i][0].y, cv[i][1].y, cv[i][2].y, cv[i][3].y, w1, w2, w3, w4);
+                o2 = blend2(cv[i][0].z, cv[i][1].z, cv[i][2].z, cv[i][3].z, w1, w2, w3, w4);
+                o3 = blend2(cv[i][0].w, cv[i][1].w, cv[i][2].w, cv[i][3].w, w1, w2, w3, w4);
+            } else {
+                o0 = blend2s(cv[i][0].x, cv[i][1].x, cv[i][2].x, cv[i][3].x, f[i][0], f[i][1], f[i][2], f[i][3]);
+                o1 = blend2s(cv[i][0].y, cv[i][1].y, cv[i][2].y, cv[i][3].y, f[i][0], f[i][1], f[i][2], f[i][3]);
+                o2 = blend2s(cv[i][0].z, cv[i][1].z, cv[i][2].z, cv[i][3].z, f[i][0], f[i][1], f[i][2], f[i][3]);
+                o3 = blend2s(cv[i][0].w, cv[i][1].w, cv[i][2].w, cv[i][3].w, f[i][0], f[i][1], f[i][2], f[i][3]);
             }
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sa + (i ? st_off1 : st_off0)), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+        };
+        load_item(0);
+        load_item(1);
+        while (valid) {
+            mbar_wait(&empty_bar[s], ph);
+            const uint32_t sa = tiles_s + s * (uint32_t)Cfg::STAGE_BYTES;
+            advance();                                            // (goff, lane_off) now describe the NEXT k-block
+            blend_item(0, sa);
+            if (valid) load_item(0);
+            blend_item(1, sa);
+            if (valid) load_item(1);
+            fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[s]);
+            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1u; }
         }
     } else if (warp == DF_PRODUCER_WARPS) {
         // ===================== weight (B operand) TMA producer =====================
