@@ -199,6 +199,9 @@ def run_gpu(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     if world > 1:
+        # stdout carries ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION in this image) goes to stdout too
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
 
     net = build_synthetic_net().to(dev).set_precision(args.precision)
