@@ -37,13 +37,14 @@ DETECT_KW = dict(top_k=200, conf_thresh=0.01, nms_thresh=0.45)      # scripts/ba
 GFLOP_PER_FRAME = 77.466                                           # SURVEY.md 8d (multihead, conv + deform)
 
 
-def config_dict(n_gpus):
+def config_dict(n_gpus, inflight=2):
     return {'workload': 'DualRefineDet-VGGBN 320x320 VOC-21 batch %d per GPU, multihead deformable ODM, '
                         'net(x)+Detect(top_k 200, conf 0.01, nms 0.45)' % BATCH,
             'global_batch': BATCH * n_gpus, 'per_gpu_batch': BATCH, 'input': '[B,3,320,320] fp32 N(0,1)',
             'weights': 'seeded random init, randomised BN statistics (tdrn_b200.utils.synthetic.randomize_ seed 0)',
             'parallelism': 'dp%d (frames sharded by batch, weights replicated)' % n_gpus,
-            'l2': 'rotating 4 distinct input batches (157 MB) and >1 GB of per-step activations exceed the 126 MB L2'}
+            'l2': 'rotating 4 distinct input batches (157 MB) and >1 GB of per-step activations exceed the 126 MB L2',
+            'pipelining': 'CUDA-graph replay, %d step(s) in flight (with 2, step i+1 trunk overlaps the latency-bound tail of step i)' % inflight}
 
 
 def peaks():
@@ -199,10 +200,19 @@ def run_gpu(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     if world > 1:
-        # stdout carries ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION in this image) goes to stdout too
-        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
-        dist.init_process_group('nccl', device_id=dev)
+        # stdout carries ONE JSON line, but NCCL printf()s its version banner to stdout when the communicator is created:
+        # point fd 1 at stderr while the process group (and its communicator, via the first collective) comes up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     net = build_synthetic_net().to(dev).set_precision(args.precision)
     det = Detect(NUM_CLASSES, 0, DETECT_KW['top_k'], DETECT_KW['conf_thresh'], DETECT_KW['nms_thresh'])
@@ -211,58 +221,77 @@ def run_gpu(args, rank, world, local_rank):
     n_in = 4
     host_x = [make_frames(BATCH, SIZE, seed=100 + rank * n_in + i).pin_memory() for i in range(n_in)]
     dev_x = [h.to(dev) for h in host_x]
-    static_x = torch.empty_like(dev_x[0])
     host_out = torch.empty(BATCH, NUM_CLASSES, DETECT_KW['top_k'], 5).pin_memory()
-    gathered = torch.empty(world * BATCH, NUM_CLASSES, DETECT_KW['top_k'], 5, device=dev) if world > 1 else None
-
     def hot_path(x):
         arm_loc, _, loc, conf = net(x)
         return det.forward(loc, conf, priors, arm_loc_data=arm_loc)
 
-    # the critical path (trunk -> FPN chain -> level-0 head -> Detect) runs on this stream; the forked ARM / TCB / small-level
-    # branches run on default-priority side streams, so give the main stream scheduling priority over them
-    stream = torch.cuda.Stream(dev, priority=int(os.environ.get('TDRN_BENCH_PRIO', '-1')))
+    # Two steps are kept in flight on two streams / graph instances (a serving loop would do the same): the tail of a
+    # step (FPN chain, small pyramid levels, NMS) is latency-bound and leaves SMs idle that the next step's trunk can
+    # use.  A "step" is still one pass over one batch of 32 frames; K steps are timed; --inflight 1 gives the strictly
+    # serial number (about 5 % slower).
+    n_fl = 1 if args.no_graph else max(1, args.inflight)
+    streams = [torch.cuda.Stream(dev) for _ in range(n_fl)]
+    stream = streams[0]
+    static_xs = [torch.empty_like(dev_x[0]) for _ in range(n_fl)]
+    graphs, static_outs = [], []
     torch.cuda.synchronize()
     with torch.cuda.stream(stream), torch.no_grad():
         for i in range(3):                      # eager warm-up: packs weights, sizes workspaces, loads kernels
-            out = hot_path(dev_x[i % n_in])
+            hot_path(dev_x[i % n_in])
         stream.synchronize()
         l0 = _lib.launch_count()
         hot_path(dev_x[0])
         launches_per_step = _lib.launch_count() - l0
         stream.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        static_x.copy_(dev_x[0])
-        with torch.cuda.graph(graph, stream=stream):
-            static_out = hot_path(static_x)
-    stream.synchronize()
+    for k in range(n_fl):
+        with torch.cuda.stream(streams[k]), torch.no_grad():
+            static_xs[k].copy_(dev_x[0])
+            if k:
+                hot_path(static_xs[k])          # eager once on this stream: its own Detect workspace exists before capture
+                streams[k].synchronize()
+            if args.no_graph:
+                graphs.append(None)
+                static_outs.append(hot_path(static_xs[k]))
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=streams[k]):
+                    static_outs.append(hot_path(static_xs[k]))
+                graphs.append(g)
+        streams[k].synchronize()
+    gathered = [torch.empty(world * BATCH, NUM_CLASSES, DETECT_KW['top_k'], 5, device=dev) for _ in range(n_fl)] if world > 1 else None
 
-    def replay():
+    def replay(k):
         if args.no_graph:
             with torch.no_grad():
-                static_out.copy_(hot_path(static_x))
+                static_outs[k].copy_(hot_path(static_xs[k]))
         else:
-            graph.replay()
+            graphs[k].replay()
 
     def step_device(i):
-        static_x.copy_(dev_x[i % n_in], non_blocking=True)      # device->device: the frames are already in HBM
-        replay()
-        if world > 1:
-            gather_detections(static_out, out=gathered)
+        k = i % n_fl
+        with torch.cuda.stream(streams[k]):
+            static_xs[k].copy_(dev_x[i % n_in], non_blocking=True)      # device->device: the frames are already in HBM
+            replay(k)
+            if world > 1:
+                gather_detections(static_outs[k], out=gathered[k])
 
     # e2e: software-pipelined like a production feeder -- the pinned-host -> device copy of step i+1 runs on a copy
     # stream while step i computes; every step still pays its own H2D (39 MB) and D2H (2.7 MB) inside the timed
     # region, they just overlap with the previous / next step's kernels instead of serialising with them.
-    copy_stream = torch.cuda.Stream(dev)
-    staging = [torch.empty_like(dev_x[0]) for _ in range(2)]
-    staged_ev = [torch.cuda.Event() for _ in range(2)]       # H2D into staging[j] finished
-    consumed_ev = [torch.cuda.Event() for _ in range(2)]     # staging[j] copied into the graph's input
-    out_ready, out_copied = torch.cuda.Event(), torch.cuda.Event()
-    dev_out = torch.empty_like(static_out)
+    copy_stream = torch.cuda.Stream(dev)                      # host -> device feeder
+    d2h_stream = torch.cuda.Stream(dev)                       # detections -> host (own stream: a D2H waiting for step i
+                                                              # must not hold back the H2D of step i+2)
+    n_st = n_fl + 1
+    staging = [torch.empty_like(dev_x[0]) for _ in range(n_st)]
+    staged_ev = [torch.cuda.Event() for _ in range(n_st)]     # H2D into staging[j] finished
+    consumed_ev = [torch.cuda.Event() for _ in range(n_st)]   # staging[j] copied into a graph's input
+    out_ready = [torch.cuda.Event() for _ in range(n_fl)]
+    out_copied = [torch.cuda.Event() for _ in range(n_fl)]
     pipe = {'primed': -1}
 
     def prefetch(i):
-        j = i % 2
+        j = i % n_st
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed_ev[j])
             staging[j].copy_(host_x[i % n_in], non_blocking=True)
@@ -270,43 +299,52 @@ def run_gpu(args, rank, world, local_rank):
         pipe['primed'] = i
 
     def step_e2e(i):
-        if pipe['primed'] != i:
+        if pipe['primed'] < i:
             prefetch(i)
-        j = i % 2
-        stream.wait_event(staged_ev[j])
-        static_x.copy_(staging[j], non_blocking=True)           # 39 MB device->device, ~15 us
-        consumed_ev[j].record(stream)
-        prefetch(i + 1)                                         # next step's H2D overlaps this step's kernels
-        replay()
-        if world > 1:
-            gather_detections(static_out, out=gathered)
-        stream.wait_event(out_copied)                           # previous D2H has drained dev_out
-        dev_out.copy_(static_out, non_blocking=True)
-        out_ready.record(stream)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(out_ready)
-            host_out.copy_(dev_out, non_blocking=True)          # detections -> pinned host
-            out_copied.record(copy_stream)
+        k, j = i % n_fl, i % n_st
+        st = streams[k]
+        with torch.cuda.stream(st):
+            st.wait_event(staged_ev[j])
+            st.wait_event(out_copied[k])                            # this slot's previous detections have left the device
+            static_xs[k].copy_(staging[j], non_blocking=True)       # 39 MB device->device, ~15 us
+            consumed_ev[j].record(st)
+            prefetch(i + 1)                                         # next step's H2D overlaps this step's kernels
+            replay(k)
+            src = static_outs[k]
+            if world > 1:
+                gather_detections(static_outs[k], out=gathered[k])
+            out_ready[k].record(st)
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(out_ready[k])
+            host_out.copy_(src, non_blocking=True)                  # detections -> pinned host
+            out_copied[k].record(d2h_stream)
 
     def timed(step_fn, steps, warmup):
         pipe['primed'] = -1
-        with torch.cuda.stream(stream):
-            for i in range(max(warmup, 12)):               # W is a minimum: a few more replays let the clocks settle
-                step_fn(i)
-            stream.synchronize()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for i in range(steps):
-                step_fn(max(warmup, 12) + i)
-            stream.wait_stream(copy_stream)                     # e2e: the last step's D2H is inside the timed region
-            e1.record(stream)
-            stream.synchronize()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
+        w = max(warmup, 12)                                # W is a minimum: a few more replays let the clocks settle
+        for i in range(w):
+            step_fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for st in streams[1:]:
+            st.wait_event(e0)
+        copy_stream.wait_event(e0)
+        d2h_stream.wait_event(e0)
+        for i in range(steps):
+            step_fn(w + i)
+        for st in streams[1:]:
+            stream.wait_stream(st)
+        stream.wait_stream(copy_stream)
+        stream.wait_stream(d2h_stream)                      # e2e: the last step's D2H is inside the timed region
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device=dev)
@@ -319,6 +357,18 @@ def run_gpu(args, rank, world, local_rank):
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
     sampler.end()
     clocks = sampler.stop() if rank == 0 else None          # sampled every 20 ms across both timed legs
+
+    # ---- overlapped replay must give what a serial eager pass gives (bit for bit: every kernel is deterministic) ----
+    inflight_ok = None
+    if not args.no_graph:
+        for i in range(2 * n_fl):
+            step_device(i)                                  # slot k ends up holding the detections of dev_x[(2*n_fl - n_fl + k) % n_in]
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream), torch.no_grad():
+            inflight_ok = all(bool(torch.equal(static_outs[k], hot_path(dev_x[(n_fl + k) % n_in]))) for k in range(n_fl))
+        torch.cuda.synchronize()
+        if not inflight_ok:
+            raise RuntimeError('bench: detections of overlapped graph replays differ from a serial eager pass')
 
     # ---- roofline leg: per-call CUDA events on the launching stream, eager (same kernels as the graph) ----
     roof = None
@@ -380,11 +430,12 @@ def run_gpu(args, rank, world, local_rank):
                              'cores + scalar C Detect/NMS), after 1 warm-up step'}
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic', 'config': config_dict(world),
+                'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic', 'config': config_dict(world, n_fl),
                 'e2e': {'value': e2e_v, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
-                        'h2d_bytes_per_step': int(static_x.numel() * 4), 'd2h_bytes_per_step': int(host_out.numel() * 4)},
+                        'h2d_bytes_per_step': int(static_xs[0].numel() * 4), 'd2h_bytes_per_step': int(host_out.numel() * 4)},
                 'gpu_launches': int(launches_per_step * args.steps),
                 'launches_per_step': int(launches_per_step),
+                'inflight_replay_matches_serial': inflight_ok,
                 'tflops_per_gpu_whole_step': GFLOP_PER_FRAME * BATCH / (ms_dev / args.steps),   # GFLOP / ms == TFLOP/s
                 'roofline': roof, 'kernel_breakdown': breakdown, 'cpu_baseline': cpu, 'clocks': clocks}
         print(json.dumps(line), flush=True)
@@ -400,6 +451,7 @@ def main():
     ap.add_argument('--impl', default='tdrn_b200', choices=['tdrn_b200', 'reference'])
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--inflight', type=int, default=2, help='steps kept in flight on separate streams / graph instances (1 = strictly serial)')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay (profiling)')
     ap.add_argument('--detail', action='store_true', help='print the per-layer CUDA-event breakdown to stderr')
     args = ap.parse_args()

@@ -316,7 +316,10 @@ _ws_cache = {}
 
 
 def _workspace(nbytes, device):
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    # one workspace per (device, stream): calls in flight on different streams (two graph instances replaying
+    # concurrently) must never share scratch memory
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
