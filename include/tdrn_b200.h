@@ -187,6 +187,18 @@ int tdrn_deform_head(const tdrn_deform_head_desc *d, const void *feat, const flo
                      const void *weight, const float *offsets2, const void *weight2,
                      float *loc_out, float *conf_out, tdrn_stream_t stream);
 
+/* "Project, then sample" form of the same head for narrow heads with one deformable group (12 + 3C much smaller
+ * than Cin): bilinear sampling commutes with the 1x1 channel contraction, so the caller first computes the per-tap
+ * projections with one dense GEMM (tdrn_conv2d_tc, 1x1, Cout = (kh*kh + kh2*kh2) * n_pad, bf16 out)
+ *   proj [B,H,W,taps,n_pad] bf16,  proj[b,y,x,t,o] = sum_c W_t[o,c] * feat[b,y,x,c]
+ * (t runs over the taps of head 1 then head 2, o over loc rows then conf rows, zero-padded to n_pad % 8 == 0),
+ * and this entry point samples them with the reference's sampler (deform_conv_cuda_kernel.cu:16-51,195-203),
+ * sums over taps, applies the softmax and writes loc_out / conf_out exactly like tdrn_deform_head.
+ * Replaces the same reference calls as tdrn_deform_head (deform_conv_cuda.c:98-213 for loc and conf). */
+int tdrn_deform_head_sample(const tdrn_deform_head_desc *d, const void *proj, int n_pad,
+                            const float *offsets, const float *offsets2, float *loc_out, float *conf_out,
+                            tdrn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * (next row) Result scatter of the evaluation drivers: evaluate.py:469-483, evaluate_coco.py:140-159
  * (per image and class: masked_select(score > 0), boxes * (w,h,w,h), .cpu()).  One call for the whole batch:

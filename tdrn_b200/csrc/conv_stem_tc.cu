@@ -34,15 +34,6 @@ constexpr int ST_PSTAGES = 4;            // input-patch ring depth (hides HBM la
 constexpr int ST_PATCH_BYTES = 4096;     // >= 3 ch x (bh+2) rows x (bw+8) cols x 4 B for the three tile shapes, 128B aligned
 constexpr int ST_SMEM = 2 * 16384 + 2 * 16384 + 8192 + ST_PSTAGES * ST_PATCH_BYTES + 256 + 1024;
 
-__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *src, int c0, int c1, int c2, int c3)
-{
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                 ::"l"((uint64_t)m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
 {
     uint32_t r;

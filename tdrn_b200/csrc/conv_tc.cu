@@ -71,6 +71,9 @@ struct TcConvP {
     // consecutive images are batched into one tile (second tensor map, box (64, bw, rr, g2)); nA = #regular tiles
     int nA, qh, rr, g2; uint32_t a_bytes2;
     int l2_prefetch;             // producer prefetches its first weight slice into L2 (few-tile layers)
+    int tma_out;                 // epilogue stages bf16 tiles in shared memory and writes them with TMA stores (plain NHWC output)
+    int b_resident;              // num_kb == STAGES: k-block kb always lands in stage kb, so the weight boxes of an N tile
+                                 // stay in shared memory across consecutive M tiles (CTAs walk contiguous tile ranges)
     uint32_t b_bytes;            // bytes one B box deposits (min(BN, n_pad16)*128)
     const float *bias; const void *res; void *out;
     long long out_sb, out_sp; int out_w;
@@ -83,7 +86,8 @@ template <int BN> struct TcCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;          // 4 / 6 / 8 stages for BN = 256 / 128 / 64
     static constexpr int TMEM_COLS = 2 * BN;                           // double-buffered accumulator
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;     // + slack for manual 1024B alignment
+    static constexpr int OUT_STAGE_BYTES = 128 * 128;                  // one [128 px][64 ch] bf16 box of the TMA-store epilogue
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * OUT_STAGE_BYTES + 1024;   // + slack for manual 1024B alignment
 };
 
 constexpr int TC_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
@@ -94,7 +98,9 @@ constexpr int TC_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 e
 template <int BN, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmA2,
-                                                                const __grid_constant__ CUtensorMap tmB, const TcConvP p)
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const __grid_constant__ CUtensorMap tmO,
+                                                                const __grid_constant__ CUtensorMap tmO2, const TcConvP p)
 {
     using Cfg = TcCfg<BN>;
     extern __shared__ uint8_t smem_dyn[];
@@ -115,6 +121,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int m_units = (p.m_tiles + CL - 1) / CL;
     const int total_tiles = m_units * p.n_tiles;
     const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
+    // tile walk: interleaved (tile = unit0, +unit_step, ...) or, with resident weights, one contiguous range per CTA so
+    // that its tiles share the N tile (tile = nt * m_units + mt)
+    const int tile_begin = p.b_resident ? (int)((long long)total_tiles * unit0 / unit_step) : unit0;
+    const int tile_end = p.b_resident ? (int)((long long)total_tiles * (unit0 + 1) / unit_step) : total_tiles;
+    const int tile_step = p.b_resident ? 1 : unit_step;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -144,7 +155,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_l2_2d(&tmB, kb * 64, n0p);
             }
             uint32_t it = 0;                                   // running k-block counter across tiles
-            for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+            int nt_in_smem = -1;                               // b_resident: N tile whose weight boxes sit in the stages
+            for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
                 const int mt = (tile % m_units) * CL + cr, nt = tile / m_units;
                 const bool tail = p.rr && mt >= p.nA;           // ragged-tail tile (leftover rows of g2 images)
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
@@ -154,6 +166,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const CUtensorMap *mapA = tail ? &tmA2 : &tmA;
                 const uint32_t a_bytes = tail ? p.a_bytes2 : p.a_bytes;
                 const int n0 = nt * BN;
+                const bool load_b = !(p.b_resident && nt == nt_in_smem);
+                nt_in_smem = nt;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % Cfg::STAGES;
                     const uint32_t ph = (it / Cfg::STAGES) & 1u;
@@ -161,9 +175,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     uint8_t *sa = tiles + s * Cfg::STAGE_BYTES;
                     const int tap = kb / cblocks, cb = kb - tap * cblocks;
                     const int tr = tap / p.kw, ts = tap - tr * p.kw;
-                    mbar_expect_tx(&full_bar[s], a_bytes + p.b_bytes);
+                    mbar_expect_tx(&full_bar[s], a_bytes + (load_b ? p.b_bytes : 0u));
                     tma_load_4d(sa, mapA, &full_bar[s], cb * 64, w0 + ts * p.dil, h0 + tr * p.dil, b0);
-                    if (CL == 2) {
+                    if (!load_b) {
+                        // this stage still holds k-block kb of the same N tile
+                    } else if (CL == 2) {
                         const uint32_t half_rows = p.b_bytes >> 8;           // (b_bytes / 128) / 2 rows of the weight box
                         tma_load_2d_mc(sa + Cfg::A_BYTES + cr * half_rows * 128u, &tmB, &full_bar[s], kb * 64,
                                        n0 + cr * (int)half_rows, (uint16_t)3);
@@ -178,7 +194,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             uint32_t it = 0, tcount = 0;
-            for (int tile = unit0; tile < total_tiles; tile += unit_step, ++tcount) {
+            for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
                 const int nt = tile / m_units;
                 const int n_eff = min(BN, n_pad16 - nt * BN);           // UMMA N (multiple of 16)
                 const uint32_t idesc = umma_idesc_bf16(128, n_eff);
@@ -211,11 +227,72 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // processed, so its global-memory latency overlaps the TMEM load / arithmetic / stores.
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const int r = quad * 32 + lane;
+        if (p.tma_out) {
+            // ---- plain NHWC bf16 output: TMEM -> bias/ReLU -> bf16 -> 128B-swizzled [128 px][64 ch] staging box -> TMA store.
+            // Whole 128-byte lines leave the SM (a per-thread store writes 32 bytes of 32 different lines), rows beyond the
+            // map / channels beyond Cout are clipped by TMA.  Two staging boxes: the store of column group g drains while
+            // group g+1 is converted.  Each warp converts 32 rows x 32 columns of the group.
+            uint8_t *stage_base = tiles + Cfg::STAGES * Cfg::STAGE_BYTES;
+            const bool leader = threadIdx.x == 64;
+            uint32_t tcount = 0, git = 0;
+            for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
+                const int mt = (tile % m_units) * CL + cr, nt = tile / m_units;
+                const bool tail = p.rr && mt >= p.nA;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+                const int x0 = tw * p.bw, y0 = tail ? p.qh * p.bh : th * p.bh, b0 = tail ? (mt - p.nA) * p.g2 : tn * p.bn;
+                const int n0 = nt * BN;
+                const int n_eff = min(BN, n_pad16 - n0);
+                const uint32_t buf = tcount & 1u;
+                mbar_wait(&tmem_full_bar[buf], (tcount >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
+                const int groups = (n_eff + 63) >> 6;
+                for (int g = 0; g < groups; ++g, ++git) {
+                    uint8_t *o = stage_base + (git & 1u) * Cfg::OUT_STAGE_BYTES;
+                    if (leader) bulk_wait_read<1>();                 // the store that last read this box has drained
+                    named_bar(1, 256);
+                    const int c0 = g * 64 + half * 32;
+                    if (c0 < n_eff) {                                // warp-uniform; columns >= n_eff are >= Cout: clipped
+                        float v[32];
+                        tmem_ld32(trow + (uint32_t)c0, v);
+                        const int n = n0 + c0;
+                        if (p.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (n + j < p.n_total) v[j] += __ldg(p.bias + n + j);
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 w;
+                            __nv_bfloat162 *wb = (__nv_bfloat162 *)&w;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) wb[j] = __floats2bfloat162_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
+                            *(uint4 *)(o + sw128_offset(r, half * 4 + q)) = w;
+                        }
+                    }
+                    if (g == groups - 1) {                           // all tcgen05.ld of this tile are complete
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+                    }
+                    fence_proxy_async_smem();
+                    named_bar(1, 256);
+                    if (leader) {
+                        tma_store_4d(tail ? &tmO2 : &tmO, o, n0 + g * 64, x0, y0, b0);
+                        bulk_commit();
+                    }
+                }
+            }
+            if (leader) bulk_wait_read<0>();
+        } else {
         const int wl = r % p.bw, hl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
         const int hl2 = p.rr ? (r / p.bw) % p.rr : 0, nl2 = p.rr ? r / (p.bw * p.rr) : 0;      // ragged-tail tiles
         const bool res_bf16 = p.res != nullptr && !p.out_f32;
         uint32_t tcount = 0;
-        for (int tile = unit0; tile < total_tiles; tile += unit_step, ++tcount) {
+        for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
             const int mt = (tile % m_units) * CL + cr, nt = tile / m_units;
             const bool tail = p.rr && mt >= p.nA;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
@@ -322,6 +399,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
+        }
     }
 
     tc_fence_before();
@@ -350,7 +428,8 @@ static void pick_box(int B, int H, int W, int max_w, int max_h, int &bw, int &bh
 static int g_num_sms = 0;
 
 template <int BN>
-static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmA2, const CUtensorMap &tmB, const TcConvP &p, bool use_cluster, cudaStream_t st)
+static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmA2, const CUtensorMap &tmB, const CUtensorMap &tmO,
+                     const CUtensorMap &tmO2, const TcConvP &p, bool use_cluster, cudaStream_t st)
 {
     using Cfg = TcCfg<BN>;
     if (!g_num_sms) {
@@ -379,13 +458,13 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmA2, const CUte
         const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
         const int clusters = units < max_clusters[slot] ? units : max_clusters[slot];
         cfg.gridDim = dim3(2 * clusters);
-        TDRN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 2>, tmA, tmA2, tmB, p));
+        TDRN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 2>, tmA, tmA2, tmB, tmO, tmO2, p));
         count_launch();
         return TDRN_OK;
     }
     TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const int total = p.m_tiles * p.n_tiles;
-    conv_tc_kernel<BN, 1><<<total < g_num_sms ? total : g_num_sms, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, p);
+    conv_tc_kernel<BN, 1><<<total < g_num_sms ? total : g_num_sms, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }
@@ -517,8 +596,33 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         static const bool pf = getenv("TDRN_L2_PREFETCH") != nullptr;
         p.l2_prefetch = pf && p.m_tiles * p.n_tiles <= 2 * g_num_sms;
     }
+    {   // wide 1x1 layers with few k-blocks (the per-tap projection of the deformable heads: Cin 256 -> 2720) are bound
+        // by operand traffic L2->SM, two thirds of it weight boxes that every M tile of an N tile re-reads: keep them
+        static const bool no_res = getenv("TDRN_NO_RESIDENT_B") != nullptr;
+        const int stages = (192 * 1024) / (128 * 128 + BN * 128);
+        p.b_resident = !no_res && !use_cluster && p.taps * (p.Cin >> 6) == stages && p.m_tiles * p.n_tiles >= 4 * g_num_sms;
+    }
+    CUtensorMap tmO = tmA, tmO2 = tmA;
+    {   // TMA-store epilogue: plain contiguous NHWC bf16 output (no pool / pixel shuffle / residual), 16-byte aligned rows
+        static const bool no_tma_out = getenv("TDRN_NO_TMA_STORE") != nullptr;
+        p.tma_out = !no_tma_out && !d->deconv2x2 && !p.pool && !p.out_f32 && !residual && d->Cout % 8 == 0 &&
+                    d->out_sp == d->Cout && d->out_sb == (long long)p.H * p.W * d->Cout && ((uintptr_t)out & 15) == 0;
+        if (p.tma_out) {
+            const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
+            const uint64_t str[3] = {(uint64_t)d->Cout * 2, (uint64_t)p.W * d->Cout * 2, (uint64_t)p.H * p.W * d->Cout * 2};
+            const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+            int rc = make_tmap_bf16(&tmO, out, 4, dims, str, box, nullptr);
+            if (rc) return rc;
+            tmO2 = tmO;
+            if (p.rr) {
+                const uint32_t box2[4] = {64, (uint32_t)p.bw, (uint32_t)p.rr, (uint32_t)p.g2};
+                rc = make_tmap_bf16(&tmO2, out, 4, dims, str, box2, nullptr);
+                if (rc) return rc;
+            }
+        }
+    }
     cudaStream_t st = as_stream(stream);
-    if (BN == 256) return launch_tc<256>(tmA, tmA2, tmB, p, use_cluster, st);
-    if (BN == 128) return launch_tc<128>(tmA, tmA2, tmB, p, use_cluster, st);
-    return launch_tc<64>(tmA, tmA2, tmB, p, use_cluster, st);
+    if (BN == 256) return launch_tc<256>(tmA, tmA2, tmB, tmO, tmO2, p, use_cluster, st);
+    if (BN == 128) return launch_tc<128>(tmA, tmA2, tmB, tmO, tmO2, p, use_cluster, st);
+    return launch_tc<64>(tmA, tmA2, tmB, tmO, tmO2, p, use_cluster, st);
 }

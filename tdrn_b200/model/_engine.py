@@ -364,9 +364,20 @@ class Engine(object):
         conf = torch.empty(B, P, num_classes, dtype=torch.float32, device=self.device)
         fused = self.use_tc and feats[0].dtype == torch.bfloat16 and all(f.shape[3] % 64 == 0 for f in feats)
 
+        # narrow head, one deformable group: project per tap on the tensor cores first, then sample the projections
+        # (3.4x fewer bilinear samples at VOC-21); wide heads / dg > 1 sample into the fused im2col tile instead
+        n_out8 = (12 + 3 * num_classes + 7) // 8 * 8
+        projected = (fused and dg == 1 and os.environ.get('TDRN_DEFORM_PATH', 'project') != 'im2col'
+                     and all(2 * n_out8 <= f.shape[3] for f in feats))
+
         def level(k):
             f = feats[k]
-            if fused:
+            if projected:
+                pc, n_pad = self.projected_head_weight(loc_name, conf_name, k, multihead)
+                ops.deform_head_projected(f, offs[k], pc, n_pad, num_classes, 3, 1, loc, conf, P, lv_off[k],
+                                          offsets2=offs2[k] if multihead else None,
+                                          kh2=5 if multihead else 0, pad2=2 if multihead else 0, softmax=softmax)
+            elif fused:
                 w1 = self.fused_head_weight(loc_name, conf_name, k)
                 w2 = self.fused_head_weight(loc_name + '_2', conf_name + '_2', k) if multihead else None
                 ops.deform_head(f, offs[k], w1, num_classes, dg, 3, 1, loc, conf, P, lv_off[k],
@@ -393,6 +404,18 @@ class Engine(object):
             wl = self.sd['%s.%d.weight' % (loc_name, k)].detach()
             wc = self.sd['%s.%d.weight' % (conf_name, k)].detach()
             w = ops.pack_deform_head_weight(torch.cat([wl, wc], 0), self.device)   # [N = 12 + 3C, Cin, kh, kw]
+            self.pk[key] = w
+        return w
+
+    def projected_head_weight(self, loc_name, conf_name, k, multihead):
+        """Per-tap projection weights (1x1 PackedConv, Cout = taps * n_pad) for tdrn_deform_head_sample."""
+        key = 'proj.%s.%s.%d.%d' % (loc_name, conf_name, k, int(multihead))
+        w = self.pk.get(key)
+        if w is None:
+            cat = lambda ln, cn: torch.cat([self.sd['%s.%d.weight' % (ln, k)].detach(),
+                                            self.sd['%s.%d.weight' % (cn, k)].detach()], 0)
+            w = ops.pack_deform_proj_weight(cat(loc_name, conf_name),
+                                            cat(loc_name + '_2', conf_name + '_2') if multihead else None, self.device)
             self.pk[key] = w
         return w
 

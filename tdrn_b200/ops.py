@@ -112,7 +112,7 @@ class PackedConv(object):
 
 
 def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_sb=None, out_sp=None,
-           offsets=None, dg=0, use_tc=False, in_shape=None, in_sb=0, pool=False):
+           offsets=None, dg=0, use_tc=False, in_shape=None, in_sb=0, pool=False, label=None, work=None):
     """out = act(conv(x) + bias (+ residual)).  ``out`` may be a view into a larger flat buffer, in which
     case out_sb/out_sp give the per-image and per-pixel strides (elements)."""
     if in_shape is not None:          # x is a strided view (e.g. one level of the flat [B,P,4] ARM output)
@@ -136,11 +136,11 @@ def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_
                  dil=pc.dil, relu=int(relu), deconv2x2=int(pc.deconv), dg=dg, in_dtype=_dt(x),
                  out_dtype=_dt(out), out_sb=out_sb, out_sp=out_sp, in_sb=in_sb, pool2x2=int(pool))
     L = _lib.lib()
-    flops = 2.0 * B * (H * W * 4 if pc.deconv else Ho * Wo * pc.kh * pc.kw) * Cin * pc.cout
+    flops = 2.0 * B * (H * W * 4 if pc.deconv else Ho * Wo * pc.kh * pc.kw) * Cin * pc.cout if work is None else work
     if use_tc:
         if pc.w_bf16 is None or x.dtype != torch.bfloat16 or dg:
             raise _lib.TdrnError('tcgen05 conv needs bf16 input, Cin %% 64 == 0 and no offsets')
-        with _Timed('conv_tc|%dx%d k%d d%d @%dx%d%s' % (Cin, pc.cout, pc.kh, pc.dil, H, W, ' deconv' if pc.deconv else ''), flops):
+        with _Timed(label or 'conv_tc|%dx%d k%d d%d @%dx%d%s' % (Cin, pc.cout, pc.kh, pc.dil, H, W, ' deconv' if pc.deconv else ''), flops):
             check(L.tdrn_conv2d_tc(ctypes.byref(d), ptr(x), ptr(pc.w_bf16), ptr(pc.bias), ptr(residual), ptr(out),
                                    stream_handle()), 'tdrn_conv2d_tc')
     else:
@@ -301,6 +301,57 @@ def deform_head(feat_nhwc, offsets, w_bf16, num_classes, dg, kh, pad, loc_out, c
     with _Timed('deform_head_tc|%d @%dx%d k%d+%d' % (Cin, H, W, kh, kh2), flops):
         check(_lib.lib().tdrn_deform_head(ctypes.byref(d), ptr(x), ptr(offsets), ptr(w_bf16), ptr(offsets2),
                                           ptr(w2_bf16), ptr(loc_out), ptr(conf_out), stream_handle()), 'tdrn_deform_head')
+
+
+def pack_deform_proj_weight(wcat, wcat2=None, device='cuda'):
+    """Per-tap projection weights of the "project, then sample" head (tdrn_deform_head_sample).
+
+    wcat [N, Cin, kh, kw] (loc rows then conf rows; wcat2: the optional second, 5x5, head) -> a 1x1 PackedConv with
+    Cout = taps * n_pad rows, row t * n_pad + o = W[o, :, tap t] (taps of head 1 first), n_pad = N up to a multiple of 8."""
+    ws = [wcat.detach().double().cpu()] + ([wcat2.detach().double().cpu()] if wcat2 is not None else [])
+    n, cin = ws[0].shape[:2]
+    n_pad = (n + 7) // 8 * 8
+    rows = []
+    for w in ws:
+        kh, kw = w.shape[2:]
+        blk = torch.zeros(kh * kw, n_pad, cin, dtype=torch.float64)
+        blk[:, :n] = w.permute(2, 3, 0, 1).reshape(kh * kw, n, cin)
+        rows.append(blk.reshape(kh * kw * n_pad, cin))
+    wp = torch.cat(rows, 0)
+    return PackedConv(wp.view(wp.shape[0], cin, 1, 1), device=device), n_pad
+
+
+def _deform_chunk_bytes():
+    import os
+    return int(float(os.environ.get('TDRN_DEFORM_CHUNK_MB', '1024')) * (1 << 20))
+
+
+def deform_head_projected(feat_nhwc, offsets, pc_proj, n_pad, num_classes, kh, pad, loc_out, conf_out, P, prior_off,
+                          offsets2=None, kh2=0, pad2=0, softmax=True):
+    """Same contract as deform_head (dg = 1) in two launches per image chunk: dense per-tap projection on tcgen05
+    (1x1 conv, bf16 out), then the bilinear sampler over the projections.  The batch is split into image chunks only
+    when the projection buffer would exceed TDRN_DEFORM_CHUNK_MB (default 1024 MB; 278 MB at b32 / 40x40 / VOC-21).
+    Measured on B200: L2-sized chunks (48 MB) lose more to per-launch tails than they gain in L2 residency."""
+    x = _cuda(feat_nhwc, 'feat')
+    B, H, W, Cin = x.shape
+    taps = kh * kh + kh2 * kh2
+    assert pc_proj.cout == taps * n_pad and pc_proj.cin == Cin
+    per_img = H * W * taps * n_pad * 2
+    nb = max(1, min(B, _deform_chunk_bytes() // per_img))
+    y = torch.empty(nb, H, W, taps * n_pad, dtype=torch.bfloat16, device=x.device)
+    flops = 2.0 * H * W * (12 + 3 * num_classes) * Cin * taps
+    L = _lib.lib()
+    for b0 in range(0, B, nb):
+        n = min(nb, B - b0)
+        conv2d(x[b0:b0 + n], pc_proj, use_tc=True, out=y[:n],
+               label='deform_head_tc|%d @%dx%d k%d+%d project' % (Cin, H, W, kh, kh2), work=flops * n)
+        d = DeformHeadDesc(B=n, H=H, W=W, Cin=Cin, num_classes=num_classes, dg=1, kh=kh, pad=pad, kh2=kh2, pad2=pad2,
+                           P=P, prior_off=prior_off, softmax=int(softmax))
+        with _Timed('deform_head_tc|%d @%dx%d k%d+%d sample' % (Cin, H, W, kh, kh2), 0.0):
+            check(L.tdrn_deform_head_sample(ctypes.byref(d), ptr(y), n_pad, ptr(offsets[b0:b0 + n]),
+                                            ptr(offsets2[b0:b0 + n]) if offsets2 is not None else None,
+                                            ptr(loc_out[b0:b0 + n]), ptr(conf_out[b0:b0 + n]), stream_handle()),
+                  'tdrn_deform_head_sample')
 
 
 def decode(loc, priors, arm_loc=None):

@@ -42,6 +42,7 @@ def _bf(x):
     (2, 96, 64, 3, 1, 1, 16, 16, False),       # Cin = 96: second channel block half out of bounds
     (2, 128, 256, 3, 1, 1, 32, 48, True),      # streamed halo kernel: two channel blocks, two 128-wide N tiles (conv3_1 class)
     (5, 128, 128, 3, 1, 1, 64, 96, False),     # streamed halo kernel: 120 units, both TMEM buffers and the 7-stage weight ring wrap
+    (16, 256, 600, 1, 0, 1, 40, 40, False),    # resident-weight mode (4 k-blocks = 4 stages, 600 tiles): contiguous tile ranges, 3 N tiles, last one 96 wide
 ])
 def test_conv_tc_vs_fp32(b, cin, cout, k, pad, dil, h, w, relu):
     from tdrn_b200 import ops
@@ -160,6 +161,61 @@ def test_deform_head_tc_vs_oracle(B, H, W, cin, C, dg, multihead):
                     softmax=True)
     sm = torch.softmax(conf[:, poff:poff + H * W * 3], -1)
     assert rel_err(conf2[:, poff:poff + H * W * 3].cpu().numpy(), sm.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize('B,H,W,cin,C,multihead,chunk_mb', [
+    (2, 10, 10, 256, 21, False, 48), (1, 40, 40, 256, 21, True, 48), (3, 5, 5, 256, 21, True, 48),
+    (5, 20, 20, 256, 21, True, 5),           # 2.2 MB of projections per image -> chunks of 2, 2, 1 images
+    (2, 13, 7, 256, 6, True, 48), (1, 16, 16, 512, 31, False, 48)])
+def test_deform_head_projected_vs_oracle(B, H, W, cin, C, multihead, chunk_mb, monkeypatch):
+    """Project-then-sample head (tdrn_conv2d_tc 1x1 per-tap projections + tdrn_deform_head_sample) against the
+    restated reference loop (deform_conv_cuda.c:157-193), and against the fused im2col head on the same inputs."""
+    from oracle import deform_conv_ref as R
+    from tdrn_b200 import ops
+    monkeypatch.setenv('TDRN_DEFORM_CHUNK_MB', str(chunk_mb))
+    g = torch.Generator().manual_seed(B * H + C + 1)
+    x = _bf(torch.randn(B, cin, H, W, generator=g))
+    wl = _bf(torch.randn(12, cin, 3, 3, generator=g) * 0.03)
+    wc = _bf(torch.randn(3 * C, cin, 3, 3, generator=g) * 0.03)
+    off = torch.randn(B, 18, H, W, generator=g) * 1.5
+    loc_ref = R.deform_conv_forward(x, off, wl, 1, 1, 1, 1)
+    conf_ref = R.deform_conv_forward(x, off, wc, 1, 1, 1, 1)
+    w1, w2, off2 = torch.cat([wl, wc], 0), None, None
+    if multihead:
+        wl2 = _bf(torch.randn(12, cin, 5, 5, generator=g) * 0.02)
+        wc2 = _bf(torch.randn(3 * C, cin, 5, 5, generator=g) * 0.02)
+        off2 = torch.randn(B, 50, H, W, generator=g) * 1.5
+        loc_ref = loc_ref + R.deform_conv_forward(x, off2, wl2, 1, 2, 1, 1)
+        conf_ref = conf_ref + R.deform_conv_forward(x, off2, wc2, 1, 2, 1, 1)
+        w2 = torch.cat([wl2, wc2], 0)
+    pc, n_pad = ops.pack_deform_proj_weight(w1, w2)
+    assert n_pad % 8 == 0 and pc.cout == (9 + (25 if multihead else 0)) * n_pad
+    P, poff = H * W * 3 + 11, 5
+    xb = _nhwc(x).cuda().to(torch.bfloat16)
+    kw = dict(offsets2=_nhwc(off2).cuda() if multihead else None, kh2=5 if multihead else 0, pad2=2 if multihead else 0)
+    loc = torch.zeros(B, P, 4, device='cuda')
+    conf = torch.zeros(B, P, C, device='cuda')
+    ops.deform_head_projected(xb, _nhwc(off).cuda(), pc, n_pad, C, 3, 1, loc, conf, P, poff, softmax=False, **kw)
+    torch.cuda.synchronize()
+    lr = loc_ref.permute(0, 2, 3, 1).reshape(B, H * W * 3, 4)
+    cr = conf_ref.permute(0, 2, 3, 1).reshape(B, H * W * 3, C)
+    # the per-tap projections are rounded to bf16 before they are sampled -> ~2^-9 relative per term
+    assert rel_err(loc[:, poff:poff + H * W * 3].cpu().numpy(), lr.numpy()) < 1e-2
+    assert rel_err(conf[:, poff:poff + H * W * 3].cpu().numpy(), cr.numpy()) < 1e-2
+    assert not loc[:, :poff].any() and not loc[:, poff + H * W * 3:].any()
+    assert not conf[:, :poff].any() and not conf[:, poff + H * W * 3:].any()
+    conf2 = torch.zeros(B, P, C, device='cuda')
+    ops.deform_head_projected(xb, _nhwc(off).cuda(), pc, n_pad, C, 3, 1, loc, conf2, P, poff, softmax=True, **kw)
+    sm = torch.softmax(conf[:, poff:poff + H * W * 3], -1)
+    assert rel_err(conf2[:, poff:poff + H * W * 3].cpu().numpy(), sm.cpu().numpy()) < 1e-5
+    # same head through the fused im2col kernel: two bf16 roundings of different quantities, both within tolerance
+    loc3 = torch.zeros(B, P, 4, device='cuda')
+    conf3 = torch.zeros(B, P, C, device='cuda')
+    pack = ops.pack_deform_head_weight
+    ops.deform_head(xb, _nhwc(off).cuda(), pack(w1), C, 1, 3, 1, loc3, conf3, P, poff,
+                    w2_bf16=pack(w2) if multihead else None, softmax=False, **kw)
+    assert rel_err(loc.cpu().numpy(), loc3.cpu().numpy()) < 1.5e-2
+    assert rel_err(conf.cpu().numpy(), conf3.cpu().numpy()) < 1.5e-2
 
 
 @pytest.mark.parametrize('b,h,w,relu', [
