@@ -15,7 +15,7 @@ OBJ_DIR = os.path.join(HERE, '_obj')
 LIB = os.path.join(HERE, 'libtdrn_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
-         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr'] + os.environ.get('TDRN_NVCC_EXTRA', '').split()
 
 
 def sources():

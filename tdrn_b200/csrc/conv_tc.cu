@@ -72,8 +72,9 @@ struct TcConvP {
     int nA, qh, rr, g2; uint32_t a_bytes2;
     int l2_prefetch;             // producer prefetches its first weight slice into L2 (few-tile layers)
     int tma_out;                 // epilogue stages bf16 tiles in shared memory and writes them with TMA stores (plain NHWC output)
-    int b_resident;              // num_kb == STAGES: k-block kb always lands in stage kb, so the weight boxes of an N tile
-                                 // stay in shared memory across consecutive M tiles (CTAs walk contiguous tile ranges)
+    int b_resident;              // few k-blocks (wide 1x1 layers): the weight boxes of an N tile live in their own shared-memory
+                                 // region and stay there across consecutive M tiles (CTAs walk contiguous tile ranges); the rest
+    int a_stages;                // of the 192 KB is a ring of a_stages activation boxes (16 KB each)
     uint32_t b_bytes;            // bytes one B box deposits (min(BN, n_pad16)*128)
     const float *bias; const void *res; void *out;
     long long out_sb, out_sp; int out_w;
@@ -95,7 +96,9 @@ constexpr int TC_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 e
 // CL = 2: the kernel runs as thread-block clusters of two CTAs that own two different M tiles of the SAME N tile and
 // walk the k-blocks in lock step; each CTA fetches half of every weight box and multicasts it into both CTAs'
 // shared memory, so the weight (B) traffic L2->SM per CTA is halved (the 40x40 / 20x20 layers are L2->SM bound).
-template <int BN, int CL>
+// RES: resident weight boxes (TcConvP::b_resident) -- a template parameter so that the ring arithmetic of the common
+// streamed case stays compile-time (the single MMA-issuing thread has ~500 cycles per k-block for everything it does).
+template <int BN, int CL, bool RES>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmA2,
                                                                 const __grid_constant__ CUtensorMap tmB,
@@ -104,8 +107,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 {
     using Cfg = TcCfg<BN>;
     extern __shared__ uint8_t smem_dyn[];
-    __shared__ __align__(8) uint64_t full_bar[Cfg::STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[Cfg::STAGES];
+    constexpr int MAX_STAGES = Cfg::STAGES > 8 ? Cfg::STAGES : 8;
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_s;
@@ -123,16 +127,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
     // tile walk: interleaved (tile = unit0, +unit_step, ...) or, with resident weights, one contiguous range per CTA so
     // that its tiles share the N tile (tile = nt * m_units + mt)
-    const int tile_begin = p.b_resident ? (int)((long long)total_tiles * unit0 / unit_step) : unit0;
-    const int tile_end = p.b_resident ? (int)((long long)total_tiles * (unit0 + 1) / unit_step) : total_tiles;
-    const int tile_step = p.b_resident ? 1 : unit_step;
+    const int tile_begin = RES ? (int)((long long)total_tiles * unit0 / unit_step) : unit0;
+    const int tile_end = RES ? (int)((long long)total_tiles * (unit0 + 1) / unit_step) : total_tiles;
+    const int tile_step = RES ? 1 : unit_step;
+    // shared-memory layout: ring of (A box | B box) stages, or -- resident weights -- num_kb B boxes followed by a ring of A boxes
+    const uint32_t n_stages = RES ? (uint32_t)p.a_stages : (uint32_t)Cfg::STAGES;
+    constexpr uint32_t a_stride = RES ? (uint32_t)Cfg::A_BYTES : (uint32_t)Cfg::STAGE_BYTES;
+    uint8_t *a_base = RES ? tiles + num_kb * Cfg::B_BYTES : tiles;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         if (p.rr) tma_prefetch_desc(&tmA2);
         tma_prefetch_desc(&tmB);
 #pragma unroll
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
 #pragma unroll
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
         fence_barrier_init();
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int n0p = (unit0 / m_units) * BN + (CL == 2 ? cr * (int)(p.b_bytes >> 8) : 0);
                 for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_l2_2d(&tmB, kb * 64, n0p);
             }
-            uint32_t it = 0;                                   // running k-block counter across tiles
+            uint32_t it = 0, s = 0, ph = 0;                    // running k-block counter across tiles; its ring stage and phase
             int nt_in_smem = -1;                               // b_resident: N tile whose weight boxes sit in the stages
             for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
                 const int mt = (tile % m_units) * CL + cr, nt = tile / m_units;
@@ -166,13 +174,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const CUtensorMap *mapA = tail ? &tmA2 : &tmA;
                 const uint32_t a_bytes = tail ? p.a_bytes2 : p.a_bytes;
                 const int n0 = nt * BN;
-                const bool load_b = !(p.b_resident && nt == nt_in_smem);
+                const bool load_b = !(RES && nt == nt_in_smem);
                 nt_in_smem = nt;
+                if (RES && load_b) {
+                    // new N tile: its weight boxes overwrite the resident region -> every MMA issued so far must have retired
+                    for (uint32_t k = it > n_stages ? it - n_stages : 0u; k < it; ++k)
+                        mbar_wait(&empty_bar[k % n_stages], (k / n_stages) & 1u);
+                }
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % Cfg::STAGES;
-                    const uint32_t ph = (it / Cfg::STAGES) & 1u;
                     mbar_wait(&empty_bar[s], ph ^ 1u);        // CL = 2: both CTAs' MMAs have released stage s
-                    uint8_t *sa = tiles + s * Cfg::STAGE_BYTES;
+                    uint8_t *sa = a_base + s * a_stride;
+                    uint8_t *sb = RES ? tiles + kb * Cfg::B_BYTES : sa + Cfg::A_BYTES;
                     const int tap = kb / cblocks, cb = kb - tap * cblocks;
                     const int tr = tap / p.kw, ts = tap - tr * p.kw;
                     mbar_expect_tx(&full_bar[s], a_bytes + (load_b ? p.b_bytes : 0u));
@@ -181,11 +193,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         // this stage still holds k-block kb of the same N tile
                     } else if (CL == 2) {
                         const uint32_t half_rows = p.b_bytes >> 8;           // (b_bytes / 128) / 2 rows of the weight box
-                        tma_load_2d_mc(sa + Cfg::A_BYTES + cr * half_rows * 128u, &tmB, &full_bar[s], kb * 64,
+                        tma_load_2d_mc(sb + cr * half_rows * 128u, &tmB, &full_bar[s], kb * 64,
                                        n0 + cr * (int)half_rows, (uint16_t)3);
                     } else {
-                        tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full_bar[s], kb * 64, n0);
+                        tma_load_2d(sb, &tmB, &full_bar[s], kb * 64, n0);
                     }
+                    if (++s == n_stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -193,7 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            uint32_t it = 0, tcount = 0;
+            uint32_t s = 0, ph = 0, tcount = 0;
             for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
                 const int nt = tile / m_units;
                 const int n_eff = min(BN, n_pad16 - nt * BN);           // UMMA N (multiple of 16)
@@ -202,19 +215,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 mbar_wait(&tmem_empty_bar[buf], ((tcount >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % Cfg::STAGES;
-                    const uint32_t ph = (it / Cfg::STAGES) & 1u;
+                for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+                    const uint32_t sa = smem_u32(a_base + s * a_stride);
                     const uint64_t adesc = umma_desc_sw128(sa);
-                    const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
+                    const uint64_t bdesc = umma_desc_sw128(RES ? smem_u32(tiles + kb * Cfg::B_BYTES) : sa + Cfg::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)      // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle atom
                         umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
                     if (CL == 2) umma_commit_mc(&empty_bar[s], (uint16_t)3);   // both producers multicast into this stage
                     else umma_commit(&empty_bar[s]);     // frees the smem stage when these MMAs retire
+                    if (++s == n_stages) { s = 0; ph ^= 1u; }
                 }
                 umma_commit(&tmem_full_bar[buf]);   // accumulator of this tile complete
             }
@@ -440,7 +452,7 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmA2, const CUte
     if (use_cluster) {
         static int max_clusters[3] = {0, 0, 0};
         const int slot = BN == 256 ? 2 : (BN == 128 ? 1 : 0);
-        TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         cudaLaunchConfig_t cfg = {};
         cfg.blockDim = dim3(TC_THREADS);
         cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
@@ -452,19 +464,25 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmA2, const CUte
         if (!max_clusters[slot]) {
             cfg.gridDim = dim3(g_num_sms);
             int n = 0;
-            TDRN_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BN, 2>, &cfg));
+            TDRN_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BN, 2, false>, &cfg));
             max_clusters[slot] = n > 0 ? n : 1;
         }
         const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
         const int clusters = units < max_clusters[slot] ? units : max_clusters[slot];
         cfg.gridDim = dim3(2 * clusters);
-        TDRN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 2>, tmA, tmA2, tmB, tmO, tmO2, p));
+        TDRN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 2, false>, tmA, tmA2, tmB, tmO, tmO2, p));
         count_launch();
         return TDRN_OK;
     }
-    TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const int total = p.m_tiles * p.n_tiles;
-    conv_tc_kernel<BN, 1><<<total < g_num_sms ? total : g_num_sms, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+    const int grid = total < g_num_sms ? total : g_num_sms;
+    if (p.b_resident) {
+        TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        conv_tc_kernel<BN, 1, true><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+    } else {
+        TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        conv_tc_kernel<BN, 1, false><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+    }
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }
@@ -596,11 +614,16 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         static const bool pf = getenv("TDRN_L2_PREFETCH") != nullptr;
         p.l2_prefetch = pf && p.m_tiles * p.n_tiles <= 2 * g_num_sms;
     }
-    {   // wide 1x1 layers with few k-blocks (the per-tap projection of the deformable heads: Cin 256 -> 2720) are bound
-        // by operand traffic L2->SM, two thirds of it weight boxes that every M tile of an N tile re-reads: keep them
+    {   // wide 1x1 layers with few k-blocks (the per-tap projection of the deformable heads: Cin 256 -> 2720; MobileNet's
+        // pointwise convs) are bound by operand traffic and by the depth of the TMA ring, not by the MMAs: keep the weight
+        // boxes of an N tile resident and give the rest of the ring to activation boxes.  Measured (b32, 256 -> 2720 @40x40):
+        // 0.131 ms without, 0.124 with resident weights, 0.096 with the TMA-store epilogue on top = cuBLAS (0.093) and 77 % of
+        // a pure 278 MB memset (0.074 ms: HBM write bandwidth is the bound); BN = 128 with a two-tile ring is slower (0.157)
         static const bool no_res = getenv("TDRN_NO_RESIDENT_B") != nullptr;
-        const int stages = (192 * 1024) / (128 * 128 + BN * 128);
-        p.b_resident = !no_res && !use_cluster && p.taps * (p.Cin >> 6) == stages && p.m_tiles * p.n_tiles >= 4 * g_num_sms;
+        const int num_kb = p.taps * (p.Cin >> 6);
+        const int ring_boxes = (192 * 1024 - num_kb * BN * 128) / (128 * 128);
+        p.b_resident = !no_res && !use_cluster && ring_boxes >= 4 && ring_boxes >= num_kb && p.m_tiles * p.n_tiles >= 4 * g_num_sms;
+        p.a_stages = ring_boxes < 8 ? ring_boxes : 8;
     }
     CUtensorMap tmO = tmA, tmO2 = tmA;
     {   // TMA-store epilogue: plain contiguous NHWC bf16 output (no pool / pixel shuffle / residual), 16-byte aligned rows
