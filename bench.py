@@ -411,25 +411,26 @@ def run_gpu(args, rank, world, local_rank):
             d = agg['detect']
             breakdown['detect']['achieved_gbs'] = d[0] / (d[1] * 1e-3) / 1e9
             breakdown['detect']['frac_of_hbm'] = breakdown['detect']['achieved_gbs'] / pk['hbm_gbs']
-            # regime T: trained-like scores -- background logit +6, so ~1-2 % of the priors pass conf_thresh --
-            # where Detect is bound by HBM traffic rather than by the IoU scan of 6 375 candidates per class (random init)
-            g = torch.Generator(device='cpu').manual_seed(7)
-            logits = torch.randn(BATCH * priors.shape[0], NUM_CLASSES, generator=g)
-            logits[:, 0] += 6.0
-            conf_t = torch.softmax(logits, 1).to(dev)
-            loc_t = torch.randn(BATCH, priors.shape[0], 4, generator=g).to(dev)
-            arm_t = (0.5 * torch.randn(BATCH, priors.shape[0], 4, generator=g)).to(dev)
-            with torch.cuda.stream(stream), torch.no_grad():
-                for _ in range(3):
-                    det.forward(loc_t, conf_t, priors, arm_loc_data=arm_t)
-                ops.prof_begin()
-                for _ in range(10):
-                    det.forward(loc_t, conf_t, priors, arm_loc_data=arm_t)
-                rec_t = ops.prof_end()
-            ms_t = sum(r[2] for r in rec_t) / len(rec_t)
-            breakdown['detect']['trained_like'] = {
-                'ms_per_step': ms_t, 'candidates_frac': float((conf_t[:, 1:] > DETECT_KW['conf_thresh']).float().mean().item()),
-                'achieved_gbs': rec_t[0][1] / (ms_t * 1e-3) / 1e9, 'frac_of_hbm': rec_t[0][1] / (ms_t * 1e-3) / 1e9 / pk['hbm_gbs']}
+            if not args.no_graph:          # (the ncu launch-list runs use --no-graph: keep their tail = one step)
+                # regime T: trained-like scores -- background logit +7.7, so ~1.5 % of the (prior, class) scores pass conf_thresh --
+                # where Detect is bound by HBM traffic rather than by the IoU scan of 6 375 candidates per class (random init)
+                g = torch.Generator(device='cpu').manual_seed(7)
+                logits = torch.randn(BATCH * priors.shape[0], NUM_CLASSES, generator=g)
+                logits[:, 0] += 7.7
+                conf_t = torch.softmax(logits, 1).to(dev)
+                loc_t = torch.randn(BATCH, priors.shape[0], 4, generator=g).to(dev)
+                arm_t = (0.5 * torch.randn(BATCH, priors.shape[0], 4, generator=g)).to(dev)
+                with torch.cuda.stream(stream), torch.no_grad():
+                    for _ in range(3):
+                        det.forward(loc_t, conf_t, priors, arm_loc_data=arm_t)
+                    ops.prof_begin()
+                    for _ in range(10):
+                        det.forward(loc_t, conf_t, priors, arm_loc_data=arm_t)
+                    rec_t = ops.prof_end()
+                ms_t = sum(r[2] for r in rec_t) / len(rec_t)
+                breakdown['detect']['trained_like'] = {
+                    'ms_per_step': ms_t, 'candidates_frac': float((conf_t[:, 1:] > DETECT_KW['conf_thresh']).float().mean().item()),
+                    'achieved_gbs': rec_t[0][1] / (ms_t * 1e-3) / 1e9, 'frac_of_hbm': rec_t[0][1] / (ms_t * 1e-3) / 1e9 / pk['hbm_gbs']}
         if 'deform_head_tc' in agg:
             d = agg['deform_head_tc']
             breakdown['deform_head_tc']['achieved_tflops'] = d[0] / (d[1] * 1e-3) / 1e12
