@@ -211,6 +211,17 @@ size_t tdrn_collect_workspace_bytes(int B, int C);
 int tdrn_collect_detections(const float *det, const float *wh, int B, int C, int top_k, float *out_rows, int max_rows,
                             int *count, void *workspace, size_t workspace_bytes, tdrn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (next row) Pre-processing of the evaluation / video drivers on the device:
+ *   base_transform (data/__init__.py:7-12): cv2.resize(image, (size, size)) [INTER_LINEAR, 8-bit fixed point],
+ *   .astype(float32), -= mean; then the callers' `img[:, :, (2,1,0)]` (data/voc0712.py:466-467; swap_rb = 1) and
+ *   HWC -> CHW (`permute(2,0,1)`, voc0712.py:468; test_video_trn.py:91 has no channel swap: swap_rb = 0).
+ *   frames [B,Hs,Ws,3] uint8 (device, cv2 channel order), mean3 = host float[3] in the order of the SOURCE channels
+ *   -> out [B,3,size,size] fp32 NCHW, the `x` that net(x) takes.
+ * ------------------------------------------------------------------------------------------ */
+int tdrn_preprocess(const unsigned char *frames, int B, int Hs, int Ws, int size, const float *mean3, int swap_rb,
+                    float *out, tdrn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,9 @@ relative to the upstream reference checkout):
   layers/box_utils.py:16-25,176-195, layers/functions/prior_box.py:33-64
 * ``model_ref``        -- functional PyTorch restatement of model/dualrefinedet_vggbn.py,
   model/dualrefinedet_mobilenet.py, model/refinedet_vgg.py, model/ssd4scale_vgg.py
+* ``preprocess_ref``   -- restatement of data/__init__.py:7-12 (base_transform) incl. OpenCV's 8-bit INTER_LINEAR
+  fixed-point resize (PARITY UNPINNED: OpenCV is not in this image; see the module header)
+* ``eval_ref``         -- restatement of the result scatter of evaluate.py:469-483
 * ``c/oracle.c``       -- plain-C restatement of the sampler, im2col+GEMM, decode and NMS
   (built into ``oracle/_build/liboracle.so`` by ``oracle/build.py``)
 * ``ref_shim``         -- imports the *real* reference Python in place from /root/reference

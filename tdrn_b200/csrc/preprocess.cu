@@ -1,0 +1,89 @@
+// preprocess.cu -- (next row) the step immediately before the hot path, on the device:
+//   base_transform (data/__init__.py:7-12):  x = cv2.resize(image, (size, size)).astype(float32); x -= mean
+//   + the callers' layout change: `img[:, :, (2, 1, 0)]` (data/voc0712.py:466-467, dataset drivers only) and
+//     `permute(2, 0, 1)` / `.unsqueeze(0).permute(0, 3, 1, 2)` (voc0712.py:468, test_video_trn.py:91).
+// Input: uint8 BGR frames [B,Hs,Ws,3] already in HBM (one H2D of the raw frames, 4 bytes per output value less than
+// shipping the float tensor); output: the network input x [B,3,S,S] fp32 NCHW -- the reference's own boundary, so the
+// result is directly comparable with the host path.
+//
+// cv2.resize(INTER_LINEAR) on 8-bit images is OpenCV's fixed-point bilinear (modules/imgproc/src/resize.cpp):
+//   per destination column:  fx = float((dx + 0.5) * scale_x - 0.5); sx = floor(fx); fx -= sx;
+//                            sx < 0 -> (sx, fx) = (0, 0);  sx >= Ws - 1 -> (sx, fx) = (Ws - 1, 0);
+//                            alpha = { round_half_even((1 - fx) * 2048), round_half_even(fx * 2048) }   (short)
+//   per destination row:     the same without the clamp of fy; the two source rows are clipped to [0, Hs - 1]
+//   horizontal pass (int):   r_k = src[row_k][sx] * alpha0 + src[row_k][sx + 1] * alpha1
+//   vertical pass:           dst = saturate_u8(( ((beta0 * (r_0 >> 4)) >> 16) + ((beta1 * (r_1 >> 4)) >> 16) + 2 ) >> 2)
+//   with scale = 1 / (double(dst) / double(src)).
+// Integer arithmetic throughout, so the kernel is bit-exact against the restatement in oracle/preprocess_ref.py.
+// HBM-bound: algorithmic bytes = B * (Hs*Ws*3 + 3*S*S*4).
+#include "common.cuh"
+
+namespace tdrn {
+
+struct PreP {
+    const uint8_t *src; float *out;
+    int B, Hs, Ws, S;
+    double scale_x, scale_y;
+    float mean[3];
+    int swap_rb;
+};
+
+__device__ __forceinline__ void axis_coef(int d, double scale, int n_src, bool clamp_frac, int &s, int &a0, int &a1)
+{
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    s = (int)floorf(f);
+    f -= (float)s;
+    if (clamp_frac) {
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= n_src - 1) { s = n_src - 1; f = 0.f; }
+    }
+    // saturate_cast<short>(v) = round-half-to-even, then clamp (values here are within [0, 2048])
+    a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+__global__ void __launch_bounds__(256) preprocess_kernel(const PreP p)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x >= p.S) return;
+    int sx, ax0, ax1, sy, by0, by1;
+    axis_coef(x, p.scale_x, p.Ws, true, sx, ax0, ax1);
+    axis_coef(y, p.scale_y, p.Hs, false, sy, by0, by1);
+    const int y0 = min(max(sy, 0), p.Hs - 1), y1 = min(max(sy + 1, 0), p.Hs - 1);
+    const int x1 = min(sx + 1, p.Ws - 1);                      // alpha1 == 0 whenever sx + 1 is out of range
+    const uint8_t *img = p.src + (size_t)b * p.Hs * p.Ws * 3;
+    const uint8_t *r0 = img + (size_t)y0 * p.Ws * 3, *r1 = img + (size_t)y1 * p.Ws * 3;
+    float *o = p.out + (size_t)b * 3 * p.S * p.S + (size_t)y * p.S + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int h0 = (int)r0[sx * 3 + c] * ax0 + (int)r0[x1 * 3 + c] * ax1;
+        const int h1 = (int)r1[sx * 3 + c] * ax0 + (int)r1[x1 * 3 + c] * ax1;
+        int v = (((by0 * (h0 >> 4)) >> 16) + ((by1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        v = min(max(v, 0), 255);
+        const int oc = p.swap_rb ? 2 - c : c;                  // the mean is subtracted in source (BGR) order, then swapped
+        o[(size_t)oc * p.S * p.S] = __fsub_rn((float)v, p.mean[c]);
+    }
+}
+
+}  // namespace tdrn
+
+using namespace tdrn;
+
+extern "C" int tdrn_preprocess(const unsigned char *frames, int B, int Hs, int Ws, int size, const float *mean3,
+                               int swap_rb, float *out, tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(frames && mean3 && out, "tdrn_preprocess: null argument");
+    TDRN_REQUIRE(B > 0 && Hs > 0 && Ws > 0 && size > 0, "tdrn_preprocess: bad shape (B=%d Hs=%d Ws=%d size=%d)", B, Hs, Ws, size);
+    TDRN_REQUIRE(Hs <= 32768 && Ws <= 32768 && size <= 32768 && B <= 65535, "tdrn_preprocess: dimension too large");
+    PreP p{};
+    p.src = frames; p.out = out; p.B = B; p.Hs = Hs; p.Ws = Ws; p.S = size;
+    p.scale_x = 1.0 / ((double)size / (double)Ws);             // cv::resize: inv_scale = dsize / ssize; scale = 1 / inv_scale
+    p.scale_y = 1.0 / ((double)size / (double)Hs);
+    p.mean[0] = mean3[0]; p.mean[1] = mean3[1]; p.mean[2] = mean3[2];
+    p.swap_rb = swap_rb;
+    dim3 grid((size + 255) / 256, size, B);
+    preprocess_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}

@@ -354,6 +354,22 @@ def deform_head_projected(feat_nhwc, offsets, pc_proj, n_pad, num_classes, kh, p
                   'tdrn_deform_head_sample')
 
 
+def preprocess(frames_u8, size, mean, swap_rb=False, out=None):
+    """[B,Hs,Ws,3] uint8 CUDA frames (cv2 channel order) -> [B,3,size,size] fp32 NCHW network input:
+    base_transform (data/__init__.py:7-12) + optional channel swap + HWC->CHW, one launch (tdrn_preprocess)."""
+    f = _cuda(frames_u8, 'frames')
+    if f.dtype != torch.uint8 or f.dim() != 4 or f.shape[3] != 3:
+        raise TypeError('frames must be a uint8 tensor [B,H,W,3]')
+    B, Hs, Ws, _ = f.shape
+    if out is None:
+        out = torch.empty(B, 3, size, size, dtype=torch.float32, device=f.device)
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    with _Timed('preprocess|%dx%d->%d' % (Hs, Ws, size), float(B * (Hs * Ws * 3 + 3 * size * size * 4))):
+        check(_lib.lib().tdrn_preprocess(ptr(f), B, Hs, Ws, int(size), m, int(bool(swap_rb)), ptr(out), stream_handle()),
+              'tdrn_preprocess')
+    return out
+
+
 def decode(loc, priors, arm_loc=None):
     loc, priors = _cuda(loc, 'loc').float(), _cuda(priors, 'priors').float()
     B, P, _ = loc.shape
