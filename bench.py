@@ -299,8 +299,8 @@ def run_gpu(args, rank, world, local_rank):
         pipe['primed'] = i
 
     def step_e2e(i):
-        if pipe['primed'] < i:
-            prefetch(i)
+        for q in range(pipe['primed'] + 1, i + 1):
+            prefetch(q)
         k, j = i % n_fl, i % n_st
         st = streams[k]
         with torch.cuda.stream(st):
@@ -308,7 +308,8 @@ def run_gpu(args, rank, world, local_rank):
             st.wait_event(out_copied[k])                            # this slot's previous detections have left the device
             static_xs[k].copy_(staging[j], non_blocking=True)       # 39 MB device->device, ~15 us
             consumed_ev[j].record(st)
-            prefetch(i + 1)                                         # next step's H2D overlaps this step's kernels
+            for q in range(pipe['primed'] + 1, i + n_fl + 1):      # the H2D of the next n_fl steps overlaps the kernels in flight
+                prefetch(q)                                         # (staging ring of n_fl + 1 buffers: step i - 1's is free again)
             replay(k)
             src = static_outs[k]
             if world > 1:
@@ -434,6 +435,15 @@ def run_gpu(args, rank, world, local_rank):
         if 'deform_head_tc' in agg:
             d = agg['deform_head_tc']
             breakdown['deform_head_tc']['achieved_tflops'] = d[0] / (d[1] * 1e-3) / 1e12
+            breakdown['deform_head_tc']['frac_of_tensor_peak'] = d[0] / (d[1] * 1e-3) / 1e12 / pk['bf16_tflops_sustained']
+            # the projection GEMM of pyramid level 0 writes B*1600*34*80 bf16 projections: HBM-write bound
+            pj = [v for k, v in detail.items() if k.startswith('deform_head_tc') and '@40x40' in k and k.endswith('project')]
+            if pj:
+                ms_pj = pj[0][1] / pj[0][2]
+                wr = BATCH * 1600 * 34 * 80 * 2
+                breakdown['deform_head_tc']['projection_level0'] = {
+                    'ms': ms_pj, 'bytes_written': wr, 'achieved_write_gbs': wr / (ms_pj * 1e-3) / 1e9,
+                    'note': 'pure 278 MB memset on this B200: 3750 GB/s (profiles/probe_gemm_bound.txt); cuBLAS on the same GEMM 0.093 ms'}
     if world > 1:
         dist.barrier()
 
