@@ -44,7 +44,8 @@ def config_dict(n_gpus, inflight=2):
             'weights': 'seeded random init, randomised BN statistics (tdrn_b200.utils.synthetic.randomize_ seed 0)',
             'parallelism': 'dp%d (frames sharded by batch, weights replicated)' % n_gpus,
             'l2': 'rotating 4 distinct input batches (157 MB) and >1 GB of per-step activations exceed the 126 MB L2',
-            'pipelining': 'CUDA-graph replay, %d step(s) in flight (with 2, step i+1 trunk overlaps the latency-bound tail of step i)' % inflight}
+            'pipelining': 'CUDA-graph replay (one instance per resident input batch), %d step(s) in flight (with 2, step i+1 trunk '
+                          'overlaps the latency-bound tail of step i)' % inflight}
 
 
 def peaks():
@@ -226,14 +227,17 @@ def run_gpu(args, rank, world, local_rank):
         arm_loc, _, loc, conf = net(x)
         return det.forward(loc, conf, priors, arm_loc_data=arm_loc)
 
-    # Two steps are kept in flight on two streams / graph instances (a serving loop would do the same): the tail of a
-    # step (FPN chain, small pyramid levels, NMS) is latency-bound and leaves SMs idle that the next step's trunk can
-    # use.  A "step" is still one pass over one batch of 32 frames; K steps are timed; --inflight 1 gives the strictly
-    # serial number (about 5 % slower).
+    # Two steps are kept in flight on two streams (a serving loop would do the same): the tail of a step (FPN chain,
+    # small pyramid levels, NMS) is latency-bound and leaves SMs idle that the next step's trunk can use.  A "step" is still
+    # one pass over one batch of 32 frames; K steps are timed; --inflight 1 gives the strictly serial number (~5 % slower).
+    # There is one captured graph instance per resident input batch (n_in = 4): instance q reads xs[q] in place, so the
+    # device leg moves no input bytes at all and the e2e leg's H2D lands directly in the graph's input (no staging copy
+    # that would queue behind the 1.5 ms H2D on a copy engine).  Step i runs instance i % 4 on stream i % 2.
     n_fl = 1 if args.no_graph else max(1, args.inflight)
+    n_slots = 1 if args.no_graph else max(n_in, n_fl + 2)
     streams = [torch.cuda.Stream(dev) for _ in range(n_fl)]
     stream = streams[0]
-    static_xs = [torch.empty_like(dev_x[0]) for _ in range(n_fl)]
+    xs = [dev_x[q % n_in].clone() for q in range(n_slots)]
     graphs, static_outs = [], []
     torch.cuda.synchronize()
     with torch.cuda.stream(stream), torch.no_grad():
@@ -244,81 +248,78 @@ def run_gpu(args, rank, world, local_rank):
         hot_path(dev_x[0])
         launches_per_step = _lib.launch_count() - l0
         stream.synchronize()
-    for k in range(n_fl):
+    for k in range(1, n_fl):
         with torch.cuda.stream(streams[k]), torch.no_grad():
-            static_xs[k].copy_(dev_x[0])
-            if k:
-                hot_path(static_xs[k])          # eager once on this stream: its own Detect workspace exists before capture
-                streams[k].synchronize()
+            hot_path(xs[0])                     # eager once on this stream: its own Detect workspace exists before capture
+        streams[k].synchronize()
+    for q in range(n_slots):
+        st = streams[q % n_fl]
+        with torch.cuda.stream(st), torch.no_grad():
             if args.no_graph:
                 graphs.append(None)
-                static_outs.append(hot_path(static_xs[k]))
+                static_outs.append(hot_path(xs[q]))
             else:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=streams[k]):
-                    static_outs.append(hot_path(static_xs[k]))
+                with torch.cuda.graph(g, stream=st):
+                    static_outs.append(hot_path(xs[q]))
                 graphs.append(g)
-        streams[k].synchronize()
-    gathered = [torch.empty(world * BATCH, NUM_CLASSES, DETECT_KW['top_k'], 5, device=dev) for _ in range(n_fl)] if world > 1 else None
+        st.synchronize()
+    gathered = [torch.empty(world * BATCH, NUM_CLASSES, DETECT_KW['top_k'], 5, device=dev) for _ in range(n_slots)] if world > 1 else None
 
-    def replay(k):
+    def replay(q):
         if args.no_graph:
             with torch.no_grad():
-                static_outs[k].copy_(hot_path(static_xs[k]))
+                static_outs[q].copy_(hot_path(xs[q]))
         else:
-            graphs[k].replay()
+            graphs[q].replay()
 
     def step_device(i):
-        k = i % n_fl
-        with torch.cuda.stream(streams[k]):
-            static_xs[k].copy_(dev_x[i % n_in], non_blocking=True)      # device->device: the frames are already in HBM
-            replay(k)
+        q = i % n_slots
+        with torch.cuda.stream(streams[i % n_fl]):
+            if n_slots < n_in:
+                xs[q].copy_(dev_x[i % n_in], non_blocking=True)         # eager profiling mode: one input buffer
+            replay(q)                                                   # the frames are already in HBM (xs[q])
             if world > 1:
-                gather_detections(static_outs[k], out=gathered[k])
+                gather_detections(static_outs[q], out=gathered[q])
 
-    # e2e: software-pipelined like a production feeder -- the pinned-host -> device copy of step i+1 runs on a copy
-    # stream while step i computes; every step still pays its own H2D (39 MB) and D2H (2.7 MB) inside the timed
-    # region, they just overlap with the previous / next step's kernels instead of serialising with them.
+    # e2e: software-pipelined like a production feeder -- the pinned-host -> device copy of step i + n_fl runs on a copy
+    # stream while steps i, i + 1 compute; every step still pays its own H2D (39 MB) and D2H (2.7 MB) inside the timed
+    # region, they just overlap with the neighbouring steps' kernels instead of serialising with them.
     copy_stream = torch.cuda.Stream(dev)                      # host -> device feeder
     d2h_stream = torch.cuda.Stream(dev)                       # detections -> host (own stream: a D2H waiting for step i
                                                               # must not hold back the H2D of step i+2)
-    n_st = n_fl + 1
-    staging = [torch.empty_like(dev_x[0]) for _ in range(n_st)]
-    staged_ev = [torch.cuda.Event() for _ in range(n_st)]     # H2D into staging[j] finished
-    consumed_ev = [torch.cuda.Event() for _ in range(n_st)]   # staging[j] copied into a graph's input
-    out_ready = [torch.cuda.Event() for _ in range(n_fl)]
-    out_copied = [torch.cuda.Event() for _ in range(n_fl)]
+    in_ready = [torch.cuda.Event() for _ in range(n_slots)]   # H2D into xs[q] finished
+    done_ev = [torch.cuda.Event() for _ in range(n_slots)]    # the step that read xs[q] / wrote static_outs[q] has finished
+    out_copied = [torch.cuda.Event() for _ in range(n_slots)]
     pipe = {'primed': -1}
 
     def prefetch(i):
-        j = i % n_st
+        q = i % n_slots
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed_ev[j])
-            staging[j].copy_(host_x[i % n_in], non_blocking=True)
-            staged_ev[j].record(copy_stream)
+            copy_stream.wait_event(done_ev[q])                # the previous user of this instance's input is done
+            xs[q].copy_(host_x[i % n_in], non_blocking=True)
+            in_ready[q].record(copy_stream)
         pipe['primed'] = i
 
     def step_e2e(i):
-        for q in range(pipe['primed'] + 1, i + 1):
-            prefetch(q)
-        k, j = i % n_fl, i % n_st
-        st = streams[k]
+        depth = min(n_fl, n_slots - 1)
+        for j in range(pipe['primed'] + 1, i + 1):
+            prefetch(j)
+        q = i % n_slots
+        st = streams[i % n_fl]
         with torch.cuda.stream(st):
-            st.wait_event(staged_ev[j])
-            st.wait_event(out_copied[k])                            # this slot's previous detections have left the device
-            static_xs[k].copy_(staging[j], non_blocking=True)       # 39 MB device->device, ~15 us
-            consumed_ev[j].record(st)
-            for q in range(pipe['primed'] + 1, i + n_fl + 1):      # the H2D of the next n_fl steps overlaps the kernels in flight
-                prefetch(q)                                         # (staging ring of n_fl + 1 buffers: step i - 1's is free again)
-            replay(k)
-            src = static_outs[k]
+            st.wait_event(in_ready[q])
+            st.wait_event(out_copied[q])                            # this instance's previous detections have left the device
+            replay(q)
             if world > 1:
-                gather_detections(static_outs[k], out=gathered[k])
-            out_ready[k].record(st)
+                gather_detections(static_outs[q], out=gathered[q])
+            done_ev[q].record(st)
+        for j in range(pipe['primed'] + 1, i + depth + 1):          # the H2D of the next steps overlaps the kernels in flight
+            prefetch(j)
         with torch.cuda.stream(d2h_stream):
-            d2h_stream.wait_event(out_ready[k])
-            host_out.copy_(src, non_blocking=True)                  # detections -> pinned host
-            out_copied[k].record(d2h_stream)
+            d2h_stream.wait_event(done_ev[q])
+            host_out.copy_(static_outs[q], non_blocking=True)       # detections -> pinned host
+            out_copied[q].record(d2h_stream)
 
     def timed(step_fn, steps, warmup):
         pipe['primed'] = -1
@@ -362,11 +363,11 @@ def run_gpu(args, rank, world, local_rank):
     # ---- overlapped replay must give what a serial eager pass gives (bit for bit: every kernel is deterministic) ----
     inflight_ok = None
     if not args.no_graph:
-        for i in range(2 * n_fl):
-            step_device(i)                                  # slot k ends up holding the detections of dev_x[(2*n_fl - n_fl + k) % n_in]
+        for i in range(2 * n_slots):
+            step_device(i)                                  # instance q ends up holding the detections of xs[q]
         torch.cuda.synchronize()
         with torch.cuda.stream(stream), torch.no_grad():
-            inflight_ok = all(bool(torch.equal(static_outs[k], hot_path(dev_x[(n_fl + k) % n_in]))) for k in range(n_fl))
+            inflight_ok = all(bool(torch.equal(static_outs[q], hot_path(xs[q]))) for q in range(n_slots))
         torch.cuda.synchronize()
         if not inflight_ok:
             raise RuntimeError('bench: detections of overlapped graph replays differ from a serial eager pass')
@@ -462,7 +463,7 @@ def run_gpu(args, rank, world, local_rank):
                 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic', 'config': config_dict(world, n_fl),
                 'e2e': {'value': e2e_v, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
-                        'h2d_bytes_per_step': int(static_xs[0].numel() * 4), 'd2h_bytes_per_step': int(host_out.numel() * 4)},
+                        'h2d_bytes_per_step': int(xs[0].numel() * 4), 'd2h_bytes_per_step': int(host_out.numel() * 4)},
                 'gpu_launches': int(launches_per_step * args.steps),
                 'launches_per_step': int(launches_per_step),
                 'inflight_replay_matches_serial': inflight_ok,
