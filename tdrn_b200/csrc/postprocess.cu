@@ -305,7 +305,9 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
                 if (ci < cnt) {
                     const float4 bx = cbox[ci];
                     const float ar = carea[ci];
-                    // (a group vote that stops all 8 sub-lanes at the first hit was measured slower: 0.276 vs 0.233 ms)
+                    // (a group vote that stops all 8 sub-lanes at the first hit was measured slower: 0.276 vs 0.233 ms; an
+                    // area-ratio pre-test -- ovr <= min(area)/max(area), so cross-level pairs cannot reach the threshold --
+                    // gave nothing either: the lanes of a warp diverge and the warp still pays for the full test)
                     for (unsigned q = l; q < kept_n && !sup; q += 8)        // vs boxes kept so far
                         sup = iou_ge(kbox[q], kar[q], bx, ar, p.thr_up);
 #pragma unroll
