@@ -71,6 +71,7 @@ struct TcConvP {
     // consecutive images are batched into one tile (second tensor map, box (64, bw, rr, g2)); nA = #regular tiles
     int nA, qh, rr, g2; uint32_t a_bytes2;
     int l2_prefetch;             // producer prefetches its first weight slice into L2 (few-tile layers)
+    int mt2;                     // work unit = two M tiles sharing every weight box (kernel template MT = 2)
     int tma_out;                 // epilogue stages bf16 tiles in shared memory and writes them with TMA stores (plain NHWC output)
     int b_resident;              // few k-blocks (wide 1x1 layers): the weight boxes of an N tile live in their own shared-memory
                                  // region and stay there across consecutive M tiles (CTAs walk contiguous tile ranges); the rest
@@ -81,12 +82,12 @@ struct TcConvP {
     int relu, deconv, out_f32, pool;
 };
 
-template <int BN> struct TcCfg {
+template <int BN, int MT = 1> struct TcCfg {
     static constexpr int A_BYTES = 128 * 128;
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;          // 4 / 6 / 8 stages for BN = 256 / 128 / 64
-    static constexpr int TMEM_COLS = 2 * BN;                           // double-buffered accumulator
+    static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;         // MT activation boxes (M tiles) share one weight box
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;          // 4 / 6 / 8 stages for BN = 256 / 128 / 64 (MT = 2, BN = 256: 3)
+    static constexpr int TMEM_COLS = 2 * BN;                           // MT = 1: double-buffered accumulator; MT = 2: two accumulators
     static constexpr int OUT_STAGE_BYTES = 128 * 128;                  // one [128 px][64 ch] bf16 box of the TMA-store epilogue
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * OUT_STAGE_BYTES + 1024;   // + slack for manual 1024B alignment
 };
@@ -98,14 +99,20 @@ constexpr int TC_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 e
 // shared memory, so the weight (B) traffic L2->SM per CTA is halved (the 40x40 / 20x20 layers are L2->SM bound).
 // RES: resident weight boxes (TcConvP::b_resident) -- a template parameter so that the ring arithmetic of the common
 // streamed case stays compile-time (the single MMA-issuing thread has ~500 cycles per k-block for everything it does).
-template <int BN, int CL, bool RES>
+// MT = 2: a work unit is TWO consecutive M tiles of one N tile: every weight box is multiplied with two activation boxes
+// (64 instead of 94 operand bytes per MMA cycle from L2, as in conv_halo_stream_kernel); the two accumulators fill TMEM, so
+// the epilogue of a unit is not overlapped with the next unit's main loop -- worth it for the long-K 3x3 layers on the
+// 40x40 / 20x20 maps (conv4_x, conv5_x, TCB), which are bound by operand delivery.  TMA-store epilogue only.
+template <int BN, int CL, bool RES, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmA2,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmO,
                                                                 const __grid_constant__ CUtensorMap tmO2, const TcConvP p)
 {
-    using Cfg = TcCfg<BN>;
+    static_assert(MT == 1 || (CL == 1 && !RES), "two-M-tile units: single CTA, streamed weights");
+    using Cfg = TcCfg<BN, MT>;
+    constexpr uint32_t NBUF = MT == 2 ? 1u : 2u;           // accumulator buffers a unit alternates between
     extern __shared__ uint8_t smem_dyn[];
     constexpr int MAX_STAGES = Cfg::STAGES > 8 ? Cfg::STAGES : 8;
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -122,7 +129,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // work unit = CL M tiles x one N tile; CTA `cr` of the cluster takes M tile mu*CL + cr (may be a dummy beyond
     // m_tiles: its A boxes are entirely out of bounds -> zeros, its epilogue stores nothing)
     const int cr = CL == 2 ? (int)cluster_ctarank() : 0;
-    const int m_units = (p.m_tiles + CL - 1) / CL;
+    const int m_units = (p.m_tiles + CL * MT - 1) / (CL * MT);
     const int total_tiles = m_units * p.n_tiles;
     const int unit0 = blockIdx.x / CL, unit_step = gridDim.x / CL;
     // tile walk: interleaved (tile = unit0, +unit_step, ...) or, with resident weights, one contiguous range per CTA so
@@ -165,14 +172,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             uint32_t it = 0, s = 0, ph = 0;                    // running k-block counter across tiles; its ring stage and phase
             int nt_in_smem = -1;                               // b_resident: N tile whose weight boxes sit in the stages
             for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-                const int mt = (tile % m_units) * CL + cr, nt = tile / m_units;
-                const bool tail = p.rr && mt >= p.nA;           // ragged-tail tile (leftover rows of g2 images)
-                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-                const int w0 = tw * p.bw * p.stride - p.pad;
-                const int h0 = (tail ? p.qh * p.bh : th * p.bh) * p.stride - p.pad;
-                const int b0 = tail ? (mt - p.nA) * p.g2 : tn * p.bn;
-                const CUtensorMap *mapA = tail ? &tmA2 : &tmA;
-                const uint32_t a_bytes = tail ? p.a_bytes2 : p.a_bytes;
+                const int nt = tile / m_units;
+                int w0[MT], h0[MT], b0[MT];
+                const CUtensorMap *mapA[MT];
+                uint32_t a_bytes = 0;
+                bool have[MT];
+#pragma unroll
+                for (int sub = 0; sub < MT; ++sub) {
+                    const int mt = (tile % m_units) * (CL * MT) + (MT == 2 ? sub : cr);
+                    have[sub] = MT == 1 || mt < p.m_tiles;          // an odd M tile count leaves the last unit half empty
+                    const bool tail = p.rr && mt >= p.nA;           // ragged-tail tile (leftover rows of g2 images)
+                    const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+                    w0[sub] = tw * p.bw * p.stride - p.pad;
+                    h0[sub] = (tail ? p.qh * p.bh : th * p.bh) * p.stride - p.pad;
+                    b0[sub] = tail ? (mt - p.nA) * p.g2 : tn * p.bn;
+                    mapA[sub] = tail ? &tmA2 : &tmA;
+                    if (have[sub]) a_bytes += tail ? p.a_bytes2 : p.a_bytes;
+                }
                 const int n0 = nt * BN;
                 const bool load_b = !(RES && nt == nt_in_smem);
                 nt_in_smem = nt;
@@ -184,11 +200,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     mbar_wait(&empty_bar[s], ph ^ 1u);        // CL = 2: both CTAs' MMAs have released stage s
                     uint8_t *sa = a_base + s * a_stride;
-                    uint8_t *sb = RES ? tiles + kb * Cfg::B_BYTES : sa + Cfg::A_BYTES;
+                    uint8_t *sb = RES ? tiles + kb * Cfg::B_BYTES : sa + MT * Cfg::A_BYTES;
                     const int tap = kb / cblocks, cb = kb - tap * cblocks;
                     const int tr = tap / p.kw, ts = tap - tr * p.kw;
                     mbar_expect_tx(&full_bar[s], a_bytes + (load_b ? p.b_bytes : 0u));
-                    tma_load_4d(sa, mapA, &full_bar[s], cb * 64, w0 + ts * p.dil, h0 + tr * p.dil, b0);
+#pragma unroll
+                    for (int sub = 0; sub < MT; ++sub)
+                        if (have[sub])
+                            tma_load_4d(sa + sub * Cfg::A_BYTES, mapA[sub], &full_bar[s], cb * 64, w0[sub] + ts * p.dil,
+                                        h0[sub] + tr * p.dil, b0[sub]);
                     if (!load_b) {
                         // this stage still holds k-block kb of the same N tile
                     } else if (CL == 2) {
@@ -211,19 +231,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int nt = tile / m_units;
                 const int n_eff = min(BN, n_pad16 - nt * BN);           // UMMA N (multiple of 16)
                 const uint32_t idesc = umma_idesc_bf16(128, n_eff);
-                const uint32_t buf = tcount & 1u;
-                mbar_wait(&tmem_empty_bar[buf], ((tcount >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
+                const uint32_t buf = tcount % NBUF;
+                mbar_wait(&tmem_empty_bar[buf], ((tcount / NBUF) & 1u) ^ 1u);   // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
+                const bool have1 = MT == 2 && (tile % m_units) * 2 + 1 < p.m_tiles;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(a_base + s * a_stride);
                     const uint64_t adesc = umma_desc_sw128(sa);
-                    const uint64_t bdesc = umma_desc_sw128(RES ? smem_u32(tiles + kb * Cfg::B_BYTES) : sa + Cfg::A_BYTES);
+                    const uint64_t bdesc = umma_desc_sw128(RES ? smem_u32(tiles + kb * Cfg::B_BYTES) : sa + MT * Cfg::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)      // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle atom
                         umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    if (have1) {                     // second M tile of the unit: same weight box, accumulator in the upper columns
+                        const uint64_t adesc1 = umma_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d_tmem + BN, adesc1 + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    }
                     if (CL == 2) umma_commit_mc(&empty_bar[s], (uint16_t)3);   // both producers multicast into this stage
                     else umma_commit(&empty_bar[s]);     // frees the smem stage when these MMAs retire
                     if (++s == n_stages) { s = 0; ph ^= 1u; }
@@ -248,53 +275,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const bool leader = threadIdx.x == 64;
             uint32_t tcount = 0, git = 0;
             for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
-                const int mt = (tile % m_units) * CL + cr, nt = tile / m_units;
-                const bool tail = p.rr && mt >= p.nA;
-                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-                const int x0 = tw * p.bw, y0 = tail ? p.qh * p.bh : th * p.bh, b0 = tail ? (mt - p.nA) * p.g2 : tn * p.bn;
+                const int nt = tile / m_units;
                 const int n0 = nt * BN;
                 const int n_eff = min(BN, n_pad16 - n0);
-                const uint32_t buf = tcount & 1u;
-                mbar_wait(&tmem_full_bar[buf], (tcount >> 1) & 1u);
+                const uint32_t buf = tcount % NBUF;
+                mbar_wait(&tmem_full_bar[buf], (tcount / NBUF) & 1u);
                 tc_fence_after();
-                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
                 const int groups = (n_eff + 63) >> 6;
-                for (int g = 0; g < groups; ++g, ++git) {
-                    uint8_t *o = stage_base + (git & 1u) * Cfg::OUT_STAGE_BYTES;
-                    if (leader) bulk_wait_read<1>();                 // the store that last read this box has drained
-                    named_bar(1, 256);
-                    const int c0 = g * 64 + half * 32;
-                    if (c0 < n_eff) {                                // warp-uniform; columns >= n_eff are >= Cout: clipped
-                        float v[32];
-                        tmem_ld32(trow + (uint32_t)c0, v);
-                        const int n = n0 + c0;
-                        if (p.bias) {
+                const int nsub = MT == 2 && (tile % m_units) * 2 + 1 < p.m_tiles ? 2 : 1;
+                for (int sub = 0; sub < nsub; ++sub) {
+                    const int mt = (tile % m_units) * (CL * MT) + (MT == 2 ? sub : cr);
+                    const bool tail = p.rr && mt >= p.nA;
+                    const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+                    const int x0 = tw * p.bw, y0 = tail ? p.qh * p.bh : th * p.bh, b0 = tail ? (mt - p.nA) * p.g2 : tn * p.bn;
+                    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (MT == 2 ? sub * BN : buf * BN);
+                    for (int g = 0; g < groups; ++g, ++git) {
+                        uint8_t *o = stage_base + (git & 1u) * Cfg::OUT_STAGE_BYTES;
+                        if (leader) bulk_wait_read<1>();                 // the store that last read this box has drained
+                        named_bar(1, 256);
+                        const int c0 = g * 64 + half * 32;
+                        if (c0 < n_eff) {                                // warp-uniform; columns >= n_eff are >= Cout: clipped
+                            float v[32];
+                            tmem_ld32(trow + (uint32_t)c0, v);
+                            const int n = n0 + c0;
+                            if (p.bias) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) if (n + j < p.n_total) v[j] += __ldg(p.bias + n + j);
+                                for (int j = 0; j < 32; ++j) if (n + j < p.n_total) v[j] += __ldg(p.bias + n + j);
+                            }
+                            if (p.relu) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 w;
+                                __nv_bfloat162 *wb = (__nv_bfloat162 *)&w;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) wb[j] = __floats2bfloat162_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
+                                *(uint4 *)(o + sw128_offset(r, half * 4 + q)) = w;
+                            }
                         }
-                        if (p.relu) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                        if (g == groups - 1 && sub == nsub - 1) {        // all tcgen05.ld of this unit are complete
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
                         }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint4 w;
-                            __nv_bfloat162 *wb = (__nv_bfloat162 *)&w;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) wb[j] = __floats2bfloat162_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
-                            *(uint4 *)(o + sw128_offset(r, half * 4 + q)) = w;
+                        fence_proxy_async_smem();
+                        named_bar(1, 256);
+                        if (leader) {
+                            tma_store_4d(tail ? &tmO2 : &tmO, o, n0 + g * 64, x0, y0, b0);
+                            bulk_commit();
                         }
-                    }
-                    if (g == groups - 1) {                           // all tcgen05.ld of this tile are complete
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-                    }
-                    fence_proxy_async_smem();
-                    named_bar(1, 256);
-                    if (leader) {
-                        tma_store_4d(tail ? &tmO2 : &tmO, o, n0 + g * 64, x0, y0, b0);
-                        bulk_commit();
                     }
                 }
             }
@@ -452,7 +483,7 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmA2, const CUte
     if (use_cluster) {
         static int max_clusters[3] = {0, 0, 0};
         const int slot = BN == 256 ? 2 : (BN == 128 ? 1 : 0);
-        TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         cudaLaunchConfig_t cfg = {};
         cfg.blockDim = dim3(TC_THREADS);
         cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
@@ -464,24 +495,34 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmA2, const CUte
         if (!max_clusters[slot]) {
             cfg.gridDim = dim3(g_num_sms);
             int n = 0;
-            TDRN_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BN, 2, false>, &cfg));
+            TDRN_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BN, 2, false, 1>, &cfg));
             max_clusters[slot] = n > 0 ? n : 1;
         }
         const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
         const int clusters = units < max_clusters[slot] ? units : max_clusters[slot];
         cfg.gridDim = dim3(2 * clusters);
-        TDRN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 2, false>, tmA, tmA2, tmB, tmO, tmO2, p));
+        TDRN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, 2, false, 1>, tmA, tmA2, tmB, tmO, tmO2, p));
         count_launch();
         return TDRN_OK;
+    }
+    if constexpr (BN == 256) {
+        if (p.mt2) {
+            using Cfg2 = TcCfg<256, 2>;
+            const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
+            TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256, 1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
+            conv_tc_kernel<256, 1, false, 2><<<units < g_num_sms ? units : g_num_sms, TC_THREADS, Cfg2::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+            TDRN_LAUNCH_CHECK();
+            return TDRN_OK;
+        }
     }
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < g_num_sms ? total : g_num_sms;
     if (p.b_resident) {
-        TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        conv_tc_kernel<BN, 1, true><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+        TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        conv_tc_kernel<BN, 1, true, 1><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
     } else {
-        TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        conv_tc_kernel<BN, 1, false><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+        TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        conv_tc_kernel<BN, 1, false, 1><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
     }
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
@@ -643,6 +684,12 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
                 if (rc) return rc;
             }
         }
+    }
+    {   // long-K layers with enough M tiles: pair two M tiles per weight box (see the kernel's MT parameter)
+        static const bool no_mt2 = getenv("TDRN_NO_MT2") != nullptr;
+        const int num_kb = p.taps * (p.Cin >> 6);
+        const int units2 = ((p.m_tiles + 1) / 2) * p.n_tiles;
+        p.mt2 = !no_mt2 && BN == 256 && p.tma_out && !p.b_resident && !use_cluster && num_kb >= 64 && units2 * 10 >= g_num_sms * 7;   // measured: K = 2304 (36 k-blocks) loses 5 %, K = 4608 gains 5-10 %
     }
     cudaStream_t st = as_stream(stream);
     if (BN == 256) return launch_tc<256>(tmA, tmA2, tmB, tmO, tmO2, p, use_cluster, st);

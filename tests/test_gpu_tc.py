@@ -42,6 +42,8 @@ def _bf(x):
     (2, 96, 64, 3, 1, 1, 16, 16, False),       # Cin = 96: second channel block half out of bounds
     (2, 128, 256, 3, 1, 1, 32, 48, True),      # streamed halo kernel: two channel blocks, two 128-wide N tiles (conv3_1 class)
     (5, 128, 128, 3, 1, 1, 64, 96, False),     # streamed halo kernel: 120 units, both TMEM buffers and the 7-stage weight ring wrap
+    (9, 512, 320, 3, 1, 1, 40, 40, True),      # two-M-tile units (MT=2): 121 M tiles (odd: last unit half empty), ragged-tail tiles, N tiles 256 + 64
+    (21, 512, 512, 3, 1, 1, 20, 20, False),    # MT=2 on 20x20 maps (conv5 class): 71 M tiles incl. tail tiles of 3 images
     (16, 256, 600, 1, 0, 1, 40, 40, False),    # resident-weight mode (4 k-blocks = 4 stages, 600 tiles): contiguous tile ranges, 3 N tiles, last one 96 wide
 ])
 def test_conv_tc_vs_fp32(b, cin, cout, k, pad, dil, h, w, relu):
