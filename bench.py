@@ -37,6 +37,11 @@ DETECT_KW = dict(top_k=200, conf_thresh=0.01, nms_thresh=0.45)      # scripts/ba
 GFLOP_PER_FRAME = 77.466                                           # SURVEY.md 8d (multihead, conv + deform)
 
 
+# diagnosis only (never set by the driver): TDRN_BENCH_E2E_SKIP=h2d,d2h drops those copies from the e2e leg to attribute its
+# gap to the device leg; a run with it set is not a valid e2e number and says so in its JSON line
+_DIAG_SKIP = [t for t in os.environ.get('TDRN_BENCH_E2E_SKIP', '').split(',') if t]
+
+
 def config_dict(n_gpus, inflight=2):
     return {'workload': 'DualRefineDet-VGGBN 320x320 VOC-21 batch %d per GPU, multihead deformable ODM, '
                         'net(x)+Detect(top_k 200, conf 0.01, nms 0.45)' % BATCH,
@@ -297,7 +302,8 @@ def run_gpu(args, rank, world, local_rank):
         q = i % n_slots
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(done_ev[q])                # the previous user of this instance's input is done
-            xs[q].copy_(host_x[i % n_in], non_blocking=True)
+            if 'h2d' not in _DIAG_SKIP:
+                xs[q].copy_(host_x[i % n_in], non_blocking=True)
             in_ready[q].record(copy_stream)
         pipe['primed'] = i
 
@@ -318,7 +324,8 @@ def run_gpu(args, rank, world, local_rank):
             prefetch(j)
         with torch.cuda.stream(d2h_stream):
             d2h_stream.wait_event(done_ev[q])
-            host_out.copy_(static_outs[q], non_blocking=True)       # detections -> pinned host
+            if 'd2h' not in _DIAG_SKIP:
+                host_out.copy_(static_outs[q], non_blocking=True)   # detections -> pinned host
             out_copied[q].record(d2h_stream)
 
     def timed(step_fn, steps, warmup):
@@ -467,6 +474,7 @@ def run_gpu(args, rank, world, local_rank):
                 'gpu_launches': int(launches_per_step * args.steps),
                 'launches_per_step': int(launches_per_step),
                 'inflight_replay_matches_serial': inflight_ok,
+                **({'INVALID_e2e_diagnosis_skip': _DIAG_SKIP} if _DIAG_SKIP else {}),
                 'tflops_per_gpu_whole_step': GFLOP_PER_FRAME * BATCH / (ms_dev / args.steps),   # GFLOP / ms == TFLOP/s
                 'roofline': roof, 'kernel_breakdown': breakdown, 'cpu_baseline': cpu, 'clocks': clocks}
         print(json.dumps(line), flush=True)
