@@ -150,6 +150,14 @@ int tdrn_maxpool2x2(const void *in, void *out, int B, int H, int W, int C, int c
 int tdrn_l2norm(const void *in, const float *weight, void *out, long long pixels, int C, int dtype,
                 tdrn_stream_t stream);
 
+/* VGG conv1_1 (3 -> 64, reads the reference's NCHW fp32 image) and conv1_2 (64 -> 64) + optional MaxPool2d(2,2) in one
+   kernel (model/networks.py:136-163, cfg entries 64, 64, 'M'; folded BN + ReLU after each conv): conv1_1's output -- the
+   largest activation of the network -- never reaches HBM.  w1 [27][64] fp32 (k = (i*3+j)*3 + c), w2 bf16 [64][9*64] K-major
+   (k = tap*64 + c, as for tdrn_conv2d_tc), out bf16 NHWC [B,H/2,W/2,64] (pool) or [B,H,W,64].  Needs W % 8 == 0 and
+   H % 16 == 0 (TDRN_EUNSUPPORTED otherwise: the caller uses tdrn_conv_first + tdrn_conv2d_tc, same results bit for bit). */
+int tdrn_conv_stem_pair(const float *x, const float *w1, const float *b1, const void *w2, const float *b2, void *out,
+                        int B, int H, int W, int relu1, int relu2, int pool, tdrn_stream_t stream);
+
 /* L2Norm and the MaxPool2d(2,2) of the SAME input in one pass (conv4_3 / conv5_3 feed both, model/
    dualrefinedet_vggbn.py:130-148): out_norm [B,H,W,C], out_pool [B,H/2,W/2,C].  bf16, C in {256,512,1024}, even H and W;
    TDRN_EUNSUPPORTED otherwise (caller uses tdrn_l2norm + tdrn_maxpool2x2). */

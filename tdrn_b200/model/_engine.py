@@ -172,6 +172,14 @@ class Engine(object):
 
         n_cfg = len(VGG_CFG)
         ci = 0
+        if (self.use_tc and self.act == torch.bfloat16 and VGG_CFG[:3] == [64, 64, 'M']
+                and os.environ.get('TDRN_NO_STEM_PAIR') is None):
+            # conv1_1 -> conv1_2 -> pool1 in one kernel: conv1_1's 419 MB (b32) output never reaches HBM
+            pc1 = self.packed('backbone.0', 1, 1, 1, 'backbone.1' if bn else None)
+            pc2 = self.packed('backbone.%d' % step, 1, 1, 1, 'backbone.%d' % (step + 1) if bn else None)
+            y = ops.conv_stem_pair(x_nchw, pc1, pc2, relu=True, pool=True)
+            if y is not None:
+                x, idx, ci = y, 2 * step + 1, 3
         while ci < n_cfg:
             v = VGG_CFG[ci]
             if idx == split43:

@@ -164,6 +164,24 @@ def conv_first(x_nchw, pc, relu, out_dtype):
     return out
 
 
+def conv_stem_pair(x_nchw, pc1, pc2, relu=True, pool=True):
+    """conv1_1 + conv1_2 (+ 2x2 max-pool) of the VGG trunk in one launch (tdrn_conv_stem_pair); returns None when the map
+    does not tile (the caller then runs the two layers separately -- identical results)."""
+    x = _cuda(x_nchw, 'input')
+    if x.dtype != torch.float32:
+        raise TypeError('network input must be float32 NCHW (reference boundary)')
+    B, C, H, W = x.shape
+    if (C != 3 or pc1.cout != 64 or pc2.cin != 64 or pc2.cout != 64 or pc2.w_bf16 is None or W % 8 or H % 16
+            or pc1.stride != 1 or pc2.stride != 1 or pc2.kh != 3 or pc2.pad != 1 or pc2.dil != 1):
+        return None
+    out = torch.empty(B, H // 2 if pool else H, W // 2 if pool else W, 64, dtype=torch.bfloat16, device=x.device)
+    flops = 2.0 * B * H * W * 64 * (27 + 9 * 64)
+    with _Timed('conv_tc|3x64+64x64 k3 stem pair @%dx%d' % (H, W), flops):
+        check(_lib.lib().tdrn_conv_stem_pair(ptr(x), ptr(pc1.w_f32), ptr(pc1.bias), ptr(pc2.w_bf16), ptr(pc2.bias), ptr(out),
+                                             B, H, W, int(relu), int(relu), int(pool), stream_handle()), 'tdrn_conv_stem_pair')
+    return out
+
+
 class PackedDw(object):
     """Depthwise 3x3 weights [C,1,3,3] (+BN) -> [9, C] fp32."""
 

@@ -243,3 +243,32 @@ def test_conv_stem_tc_vs_fp32(b, h, w, relu):
     assert out.shape == (b, h, w, 64) and out.dtype == torch.bfloat16
     tol = 4e-3 if (w % 16 == 0 and h % 2 == 0) else 8e-3      # the CUDA-core fallback multiplies un-rounded fp32 operands
     assert rel_err(_nchw(out.float()).cpu().numpy(), ref.numpy()) < tol
+
+
+@pytest.mark.parametrize('b,h,w,pool', [(2, 32, 32, True), (1, 16, 16, True), (3, 64, 48, False), (2, 48, 80, True),
+                                        (5, 320, 320, True)])    # 5 x 800 tiles: every CTA runs many tiles, all rings wrap
+def test_conv_stem_pair_is_bit_identical_to_the_two_kernel_path(b, h, w, pool):
+    """conv1_1 + conv1_2 (+pool) fused (tdrn_conv_stem_pair) against conv_stem_tc -> conv_halo_kernel and against fp32."""
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(b * h + w)
+    x = torch.randn(b, 3, h, w, generator=g)
+    w1 = torch.randn(64, 3, 3, 3, generator=g) * 0.2
+    b1 = torch.randn(64, generator=g) * 0.1
+    w2 = _bf(torch.randn(64, 64, 3, 3, generator=g) * 0.05)
+    b2 = torch.randn(64, generator=g) * 0.1
+    pc1 = ops.PackedConv(w1, b1, None, 1, 1, 1, device='cuda')
+    pc2 = ops.PackedConv(w2, b2, None, 1, 1, 1, device='cuda')
+    xc = x.cuda()
+    y1 = ops.conv_first(xc, pc1, True, torch.bfloat16)
+    ref2 = ops.conv2d(y1, pc2, relu=True, use_tc=True, pool=pool)
+    got = ops.conv_stem_pair(xc, pc1, pc2, relu=True, pool=pool)
+    torch.cuda.synchronize()
+    assert got is not None and got.shape == ref2.shape and got.dtype == torch.bfloat16
+    assert torch.equal(got, ref2)
+    # and against an fp32 reference computed from the same bf16-rounded operands of each stage
+    a1 = _bf(F.relu(F.conv2d(_bf(x), _bf(w1), b1, 1, 1)))
+    a2 = F.relu(F.conv2d(a1, w2, b2, 1, 1))
+    if pool:
+        a2 = F.max_pool2d(a2, 2, 2)
+    assert rel_err(_nchw(got.float()).cpu().numpy(), a2.numpy()) < 2e-2
+    assert ops.conv_stem_pair(torch.randn(1, 3, 20, 12).cuda(), pc1, pc2) is None      # does not tile: caller falls back
