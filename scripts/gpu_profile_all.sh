@@ -8,14 +8,14 @@ mkdir -p gpurun_out /tmp/prof
 tag=${1:-r01}
 B="python bench.py --steps 1 --warmup 3 --no-cpu --no-graph"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv $B > /tmp/prof/launches.log 2>&1
-python scripts/launch_summary.py gpurun_out/${tag}_launches.csv 62 > gpurun_out/${tag}_launches.txt
+python scripts/launch_summary.py gpurun_out/${tag}_launches.csv 61 > gpurun_out/${tag}_launches.txt
 run() { timeout 1500 ncu --set full --clock-control none $5 -k regex:$2 -s $3 -c $4 -o /tmp/prof/${tag}_$1 -f $B > /tmp/prof/ncu_$1.log 2>&1; tail -n 1 /tmp/prof/ncu_$1.log | cut -c1-120; python scripts/ncu_table.py /tmp/prof/${tag}_$1.ncu-rep > gpurun_out/${tag}_ncu_$1.txt; }
 # conv family = the 35 conv launches of the step: capture it with the deformable heads on their im2col path so that the
 # per-tap projection GEMMs (same kernel name, reported with the deformable head) stay out of the family's DRAM-traffic mean
-TDRN_DEFORM_PATH=im2col run conv   'conv_(tc|halo)'      35 35 ""
+TDRN_DEFORM_PATH=im2col run conv   'conv_(tc|halo|stem_pair)'      35 35 ""
 python scripts/ncu_traffic.py /tmp/prof/${tag}_conv.ncu-rep gpurun_out/${tag}_conv_traffic.json
 run sample 'deform_sample_kernel' 4 4 "--import-source on"
-run stem   'conv_stem_tc_kernel' 1 1 ""
+run stem   'conv_stem_pair_kernel' 1 1 "--import-source on"
 run post   '(nms_segment|decode_transpose|l2norm_pool)' 4 4 ""
 # projection GEMM + sampler of pyramid level 0 (b32, 40x40) on their own
 export LEVELS=40 CHUNKS=1024

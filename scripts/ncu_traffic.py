@@ -11,7 +11,7 @@ scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
 tot, n, table = 0.0, 0, []
 for r in rows[2:]:
     name = r[ix['Kernel Name']]
-    if 'conv_' not in name or 'simt' in name or 'stem' in name:
+    if 'conv_' not in name or 'simt' in name or 'conv_stem_tc' in name:
         continue
     rd = float(r[ix['dram__bytes_read.sum']].replace(',', '')) * scale[units[ix['dram__bytes_read.sum']]]
     wr = float(r[ix['dram__bytes_write.sum']].replace(',', '')) * scale[units[ix['dram__bytes_write.sum']]]
