@@ -239,7 +239,9 @@ def run_gpu(args, rank, world, local_rank):
     # device leg moves no input bytes at all and the e2e leg's H2D lands directly in the graph's input (no staging copy
     # that would queue behind the 1.5 ms H2D on a copy engine).  Step i runs instance i % 4 on stream i % 2.
     n_fl = 1 if args.no_graph else max(1, args.inflight)
-    n_slots = 1 if args.no_graph else max(n_in, n_fl + 2)
+    # instance q is captured on stream q % n_fl and must always replay there (its Detect workspace belongs to that stream, and
+    # consecutive uses of one instance must be stream-ordered): the instance count is a multiple of the stream count
+    n_slots = 1 if args.no_graph else n_fl * ((max(n_in, n_fl + 2) + n_fl - 1) // n_fl)
     streams = [torch.cuda.Stream(dev) for _ in range(n_fl)]
     stream = streams[0]
     xs = [dev_x[q % n_in].clone() for q in range(n_slots)]

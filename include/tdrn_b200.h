@@ -228,7 +228,21 @@ int tdrn_collect_detections(const float *det, const float *wh, int B, int C, int
  *   -> out [B,3,size,size] fp32 NCHW, the `x` that net(x) takes.
  * ------------------------------------------------------------------------------------------ */
 int tdrn_preprocess(const unsigned char *frames, int B, int Hs, int Ws, int size, const float *mean3, int swap_rb,
-                    float *out, tdrn_stream_t stream);
+                    int flip_lr /* cv2.flip(image, 1) first: multi_eval.py:541-544 */, float *out, tdrn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (next row) Merge step of multi-scale / flip testing: multi_eval.py:557-640 (gather the detections of the
+ * K passes per class: score > 0, un-flip, scale to pixels, per-scale size rule) + bbox_vote (multi_eval.py:453-494).
+ *   dets [K,C,top_k,5] = Detect outputs of the K passes of ONE image (device); flip[k] != 0: pass k saw the mirrored image;
+ *   rule[k] 0: keep boxes whose longer side (+1 convention) > rule_thr[k], 1: whose shorter side < rule_thr[k];
+ *   (w, h) original image size; vote_thresh 0.45f
+ *   -> out [C,max_out,5] rows (x1,y1,x2,y2,score) in pixels, in voting order; out_count[C] (rows beyond max_out are counted,
+ *      not written; K*top_k always suffices).  Class 0 is skipped.  NumPy float32 arithmetic order (oracle/multi_scale_ref.py).
+ * ------------------------------------------------------------------------------------------ */
+size_t tdrn_multiscale_vote_workspace_bytes(int K, int C, int top_k);
+int tdrn_multiscale_vote(const float *dets, const int *flip, const int *rule, const float *rule_thr, int K, int C, int top_k,
+                         float w, float h, float vote_thresh, float *out, int *out_count, int max_out, void *workspace,
+                         size_t workspace_bytes, tdrn_stream_t stream);
 
 #ifdef __cplusplus
 }

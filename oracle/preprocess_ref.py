@@ -59,11 +59,12 @@ def base_transform(image, size, mean):
     return x.astype(np.float32)
 
 
-def network_input(frames, size, mean, to_rgb):
-    """[B,H,W,3] uint8 -> [B,3,size,size] float32, as the drivers build it frame by frame."""
+def network_input(frames, size, mean, to_rgb, flip=False):
+    """[B,H,W,3] uint8 -> [B,3,size,size] float32, as the drivers build it frame by frame (flip: cv2.flip(im, 1) first,
+    multi_eval.py:541-544)."""
     out = []
     for f in frames:
-        x = base_transform(f, size, mean)
+        x = base_transform(f[:, ::-1] if flip else f, size, mean)
         if to_rgb:
             x = x[:, :, (2, 1, 0)]                                   # data/voc0712.py:466-467
         out.append(np.transpose(x, (2, 0, 1)))                       # .permute(2, 0, 1)

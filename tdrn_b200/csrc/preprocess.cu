@@ -25,7 +25,7 @@ struct PreP {
     int B, Hs, Ws, S;
     double scale_x, scale_y;
     float mean[3];
-    int swap_rb;
+    int swap_rb, flip_lr;
 };
 
 __device__ __forceinline__ void axis_coef(int d, double scale, int n_src, bool clamp_frac, int &s, int &a0, int &a1)
@@ -54,11 +54,13 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreP p)
     const int x1 = min(sx + 1, p.Ws - 1);                      // alpha1 == 0 whenever sx + 1 is out of range
     const uint8_t *img = p.src + (size_t)b * p.Hs * p.Ws * 3;
     const uint8_t *r0 = img + (size_t)y0 * p.Ws * 3, *r1 = img + (size_t)y1 * p.Ws * 3;
+    // cv2.flip(image, 1) before the resize (multi_eval.py:541-544): the resize of the mirrored image reads mirrored columns
+    const int cxa = p.flip_lr ? p.Ws - 1 - sx : sx, cxb = p.flip_lr ? p.Ws - 1 - x1 : x1;
     float *o = p.out + (size_t)b * 3 * p.S * p.S + (size_t)y * p.S + x;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const int h0 = (int)r0[sx * 3 + c] * ax0 + (int)r0[x1 * 3 + c] * ax1;
-        const int h1 = (int)r1[sx * 3 + c] * ax0 + (int)r1[x1 * 3 + c] * ax1;
+        const int h0 = (int)r0[cxa * 3 + c] * ax0 + (int)r0[cxb * 3 + c] * ax1;
+        const int h1 = (int)r1[cxa * 3 + c] * ax0 + (int)r1[cxb * 3 + c] * ax1;
         int v = (((by0 * (h0 >> 4)) >> 16) + ((by1 * (h1 >> 4)) >> 16) + 2) >> 2;
         v = min(max(v, 0), 255);
         const int oc = p.swap_rb ? 2 - c : c;                  // the mean is subtracted in source (BGR) order, then swapped
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreP p)
 using namespace tdrn;
 
 extern "C" int tdrn_preprocess(const unsigned char *frames, int B, int Hs, int Ws, int size, const float *mean3,
-                               int swap_rb, float *out, tdrn_stream_t stream)
+                               int swap_rb, int flip_lr, float *out, tdrn_stream_t stream)
 {
     TDRN_REQUIRE(frames && mean3 && out, "tdrn_preprocess: null argument");
     TDRN_REQUIRE(B > 0 && Hs > 0 && Ws > 0 && size > 0, "tdrn_preprocess: bad shape (B=%d Hs=%d Ws=%d size=%d)", B, Hs, Ws, size);
@@ -81,7 +83,7 @@ extern "C" int tdrn_preprocess(const unsigned char *frames, int B, int Hs, int W
     p.scale_x = 1.0 / ((double)size / (double)Ws);             // cv::resize: inv_scale = dsize / ssize; scale = 1 / inv_scale
     p.scale_y = 1.0 / ((double)size / (double)Hs);
     p.mean[0] = mean3[0]; p.mean[1] = mean3[1]; p.mean[2] = mean3[2];
-    p.swap_rb = swap_rb;
+    p.swap_rb = swap_rb; p.flip_lr = flip_lr;
     dim3 grid((size + 255) / 256, size, B);
     preprocess_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
     TDRN_LAUNCH_CHECK();

@@ -3,18 +3,18 @@ dictionaries (data/config.py) and base_transform / BaseTransform (data/__init__.
 import numpy as np
 import torch
 
-from .config import mb_cfg, VOC_320, VOC_512_RefineDet
+from .config import mb_cfg, multi_cfg, multi_cfg_512, multi_scale, VOC_320, VOC_512_RefineDet
 from .. import ops
 
 
-def preprocess_frames(frames, size, mean, to_rgb=False, device='cuda'):
+def preprocess_frames(frames, size, mean, to_rgb=False, device='cuda', flip=False):
     """Batch form used by a serving loop: uint8 frames [B,H,W,3] (numpy or torch, cv2 BGR order) -> the network input
     x [B,3,size,size] fp32 on the device, i.e. what the reference builds with base_transform(frame, size, mean),
     (optionally `img[:, :, (2, 1, 0)]`, data/voc0712.py:466-467) and `.permute(2, 0, 1)` per frame."""
     f = torch.as_tensor(np.ascontiguousarray(frames) if isinstance(frames, np.ndarray) else frames)
     if f.dim() == 3:
         f = f.unsqueeze(0)
-    return ops.preprocess(f.to(device, non_blocking=True), size, mean, swap_rb=to_rgb)
+    return ops.preprocess(f.to(device, non_blocking=True), size, mean, swap_rb=to_rgb, flip_lr=flip)
 
 
 def base_transform(image, size, mean):

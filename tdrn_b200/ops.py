@@ -372,7 +372,7 @@ def deform_head_projected(feat_nhwc, offsets, pc_proj, n_pad, num_classes, kh, p
                   'tdrn_deform_head_sample')
 
 
-def preprocess(frames_u8, size, mean, swap_rb=False, out=None):
+def preprocess(frames_u8, size, mean, swap_rb=False, out=None, flip_lr=False):
     """[B,Hs,Ws,3] uint8 CUDA frames (cv2 channel order) -> [B,3,size,size] fp32 NCHW network input:
     base_transform (data/__init__.py:7-12) + optional channel swap + HWC->CHW, one launch (tdrn_preprocess)."""
     f = _cuda(frames_u8, 'frames')
@@ -383,9 +383,31 @@ def preprocess(frames_u8, size, mean, swap_rb=False, out=None):
         out = torch.empty(B, 3, size, size, dtype=torch.float32, device=f.device)
     m = (ctypes.c_float * 3)(*[float(v) for v in mean])
     with _Timed('preprocess|%dx%d->%d' % (Hs, Ws, size), float(B * (Hs * Ws * 3 + 3 * size * size * 4))):
-        check(_lib.lib().tdrn_preprocess(ptr(f), B, Hs, Ws, int(size), m, int(bool(swap_rb)), ptr(out), stream_handle()),
+        check(_lib.lib().tdrn_preprocess(ptr(f), B, Hs, Ws, int(size), m, int(bool(swap_rb)), int(bool(flip_lr)), ptr(out),
+                                         stream_handle()),
               'tdrn_preprocess')
     return out
+
+
+def multiscale_vote(dets, flips, rules, rule_thrs, w, h, vote_thresh=0.45):
+    """dets [K,C,top_k,5] CUDA (Detect outputs of the K passes of one image) -> (rows [C,K*top_k,5], counts [C]) on the
+    device: per-class gather + bbox_vote of multi_eval.py:453-494,557-640 (tdrn_multiscale_vote)."""
+    d = _cuda(dets, 'dets').float()
+    K, C, top_k, five = d.shape
+    assert five == 5 and len(flips) == K and len(rules) == K and len(rule_thrs) == K
+    dev = d.device
+    fl = torch.tensor([int(v) for v in flips], dtype=torch.int32, device=dev)
+    ru = torch.tensor([int(v) for v in rules], dtype=torch.int32, device=dev)
+    rt = torch.tensor([float(v) for v in rule_thrs], dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    ws = torch.empty(L.tdrn_multiscale_vote_workspace_bytes(K, C, top_k), dtype=torch.uint8, device=dev)
+    out = torch.zeros(C, K * top_k, 5, dtype=torch.float32, device=dev)
+    cnt = torch.zeros(C, dtype=torch.int32, device=dev)
+    import numpy as np
+    check(L.tdrn_multiscale_vote(ptr(d), ptr(fl), ptr(ru), ptr(rt), K, C, top_k, ctypes.c_float(float(w)), ctypes.c_float(float(h)),
+                                 ctypes.c_float(float(np.float32(vote_thresh))), ptr(out), ptr(cnt), K * top_k, ptr(ws),
+                                 ctypes.c_size_t(ws.numel()), stream_handle()), 'tdrn_multiscale_vote')
+    return out, cnt
 
 
 def decode(loc, priors, arm_loc=None):

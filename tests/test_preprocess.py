@@ -67,14 +67,15 @@ def test_base_transform_and_layout():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('flip', [False, True])
 @pytest.mark.parametrize('b,h,w,size,rgb', [(3, 480, 640, 320, False), (2, 375, 500, 320, True), (1, 240, 352, 512, True),
                                             (2, 333, 77, 320, False), (1, 1080, 1920, 320, False), (4, 320, 320, 320, True),
                                             (1, 1, 1, 8, False), (2, 5, 300, 17, True)])
-def test_preprocess_kernel_bit_exact(b, h, w, size, rgb):
+def test_preprocess_kernel_bit_exact(b, h, w, size, rgb, flip):
     from tdrn_b200 import ops
     frames = _frames(b, max(h, 16), max(w, 16), b * h + w)[:, :h, :w].copy()
-    ref = P.network_input(frames, size, MEAN, to_rgb=rgb)
-    out = ops.preprocess(torch.from_numpy(frames).cuda(), size, MEAN, swap_rb=rgb)
+    ref = P.network_input(frames, size, MEAN, to_rgb=rgb, flip=flip)
+    out = ops.preprocess(torch.from_numpy(frames).cuda(), size, MEAN, swap_rb=rgb, flip_lr=flip)
     assert out.shape == ref.shape and out.dtype == torch.float32
     assert np.array_equal(out.cpu().numpy(), ref)
 
