@@ -76,7 +76,11 @@ class RefineSSD(DetectorBase):
         fp32 maps that replace the ARM-regressed offsets, to check the deformable heads in isolation."""
         E = self.engine()
         x = self._check_input(x)
-        arm_loc, offs, offs2, offs_nchw, odm_sources, P, lv = E.trunk_arm_tcb(x, self.bn, self.size, self.multihead)
+        if x.shape[2] != x.shape[3]:
+            raise ValueError('square inputs only (got %dx%d)' % (x.shape[2], x.shape[3]))
+        # fully convolutional like the reference's forward: the pyramid follows the INPUT size (multi-scale testing runs one
+        # module at several sizes, multi_eval.py:531-556), self.size is only the nominal training size
+        arm_loc, offs, offs2, offs_nchw, odm_sources, P, lv = E.trunk_arm_tcb(x, self.bn, int(x.shape[2]), self.multihead)
         if _offsets is not None:
             offs = [ops.nchw_f32_to_nhwc(o.float(), torch.float32) for o in _offsets[0]]
             offs2 = [ops.nchw_f32_to_nhwc(o.float(), torch.float32) for o in (_offsets[1] or [])]
