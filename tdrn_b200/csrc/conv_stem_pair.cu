@@ -4,7 +4,7 @@
 // conv1_1 writes the largest activation of the network (B x 320 x 320 x 64 bf16 = 419 MB at b32) only for conv1_2 to
 // read it back: the stem kernel (conv_stem_tc.cu) is bound by exactly that HBM write.  Here the conv1_1 outputs a conv1_2
 // tile needs -- the 10 x 18 halo of an 8 x 16 output tile -- are computed on the spot and never leave the SM:
-//   patch   : fp32 NCHW image box (16 x 20 x 3, the reference's own input layout) through a 4-deep TMA ring; the conv1_1
+//   patch   : fp32 NCHW image box (20 x 20 x 3, the reference's own input layout) through a 4-deep TMA ring; the conv1_1
 //             zero padding is the TMA out-of-bounds fill;
 //   A'      : 4 warps build the 27-tap im2col rows of the 180 halo pixels (K = 32, 128B-swizzled K-major, two M = 128 halves);
 //   pre-MMA : D' [256 x 64] = A' x W1^T on tcgen05 (4 instructions), accumulators in TMEM;
@@ -21,11 +21,13 @@
 //
 // Warps: 0 patch TMA + weight TMA, 1 TMEM allocator + MMA issuer, 2-9 epilogue, 10-13 im2col builders, 14-17 mid stage.
 //
-// Measured (B200, b32, 320x320): 0.431 ms against 0.118 (conv_stem_tc) + 0.308 (conv_halo_kernel) = 0.426 ms for the two
-// kernels -- no faster in isolation: an M=128, N=64, K=16 MMA reads 6 KB of operands from shared memory every 73 cycles
-// (84 of the 128 B/clk), and the im2col / mid-stage traffic (~85 KB per tile) competes for the rest.  What it removes is
-// 838 MB of HBM traffic per step (40 % of the step's total), which is worth 1-1.5 % of the whole step on a power-capped
-// part (2.79-2.82 vs 2.85-2.86 ms, same box, alternating runs).  TDRN_NO_STEM_PAIR=1 selects the two-kernel path.
+// Measured (B200, b32, 320x320): 0.410 ms against 0.118 (conv_stem_tc) + 0.308 (conv_halo_kernel) = 0.426 ms for the two
+// kernels.  The limiter is shared-memory bandwidth: an M=128, N=64, K=16 MMA reads 6 KB of operands every 73 cycles (84 of
+// the 128 B/clk), and the LSU traffic of the builder / mid / epilogue warps competes for the rest (ncu: 45 % LSU-shared
+// wavefront utilisation on top of the tensor core's reads at 0.431 ms; loading the conv1_1 bias as float4 instead of scalars
+// and a patch pitch of 20 floats -- no 2-way bank conflicts in the im2col reads -- brought 0.431 -> 0.410).  It also removes
+// 838 MB of HBM traffic per step (40 % of the step's total); whole step 2.79-2.82 vs 2.85-2.86 ms on a power-capped
+// part (same box, alternating runs, before the shared-memory tweaks).  TDRN_NO_STEM_PAIR=1 selects the two-kernel path.
 #include "halo_common.cuh"
 #include <stdlib.h>
 
@@ -35,9 +37,10 @@ namespace tc {
 constexpr int SP_THREADS = 576;
 constexpr int SP_C = 64;                                   // channels of conv1_1's output = conv1_2's input and output
 constexpr int SP_ROWS = HL_PW * HL_PH;                     // 180 halo pixels
-constexpr int SP_PXW = 16, SP_PXH = HL_PH + 2;             // patch: x0-4 .. x0+11 (16-byte aligned start), y0-2 .. y0+17
-constexpr int SP_PATCH_BYTES = 3 * SP_PXH * SP_PXW * 4;    // 3840
-constexpr int SP_PATCH_STRIDE = 4096;
+constexpr int SP_PXW = 20, SP_PXH = HL_PH + 2;             // patch: x0-4 .. x0+15 (16-byte aligned start; 12 columns are needed, a pitch
+                                                           // of 20 floats keeps rows r, r+1, r+2 of a warp's LDS on different banks), y0-2 .. y0+17
+constexpr int SP_PATCH_BYTES = 3 * SP_PXH * SP_PXW * 4;    // 4800
+constexpr int SP_PATCH_STRIDE = 5120;
 constexpr int SP_PSTAGES = 4;
 constexpr int SP_W2_BYTES = 9 * SP_C * 128;                // 73728: conv1_2 weights, [tap][64 rows][128 B]
 constexpr int SP_HSTAGES = 2;                              // halo A tiles
@@ -260,10 +263,12 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
 #pragma unroll
                         for (int cq = 0; cq < 4; ++cq) {
                             uint32_t w[4];
+                            const float4 ba = *(const float4 *)(s_bias1 + c0 + cq * 8), bb = *(const float4 *)(s_bias1 + c0 + cq * 8 + 4);
+                            const float bias8[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int c = cq * 8 + 2 * j;
-                                float lo = v[c] + s_bias1[c0 + c], hi = v[c + 1] + s_bias1[c0 + c + 1];
+                                float lo = v[c] + bias8[2 * j], hi = v[c + 1] + bias8[2 * j + 1];
                                 if (q.relu1) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
                                 w[j] = inside ? sp_pack(lo, hi) : 0u;       // conv1_2's zero padding
                             }
@@ -311,7 +316,7 @@ extern "C" int tdrn_conv_stem_pair(const float *x, const float *w1, const float 
     p.out_sp = SP_C; p.out_sb = (long long)(pool ? (H / 2) * (W / 2) : H * W) * SP_C;
     q.w1 = w1; q.b1 = b1; q.relu1 = relu1;
     CUtensorMap tmX, tmW2;
-    {   // fp32 NCHW image: dims (W, H, 3, B); box (16, 20, 3, 1) starting at (x0-4, y0-2): out-of-bounds = conv1_1 padding
+    {   // fp32 NCHW image: dims (W, H, 3, B); box (20, 20, 3, 1) starting at (x0-4, y0-2): out-of-bounds = conv1_1 padding
         EncodeTiledFn enc = get_encode_tiled();
         if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return TDRN_ECUDA; }
         const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
