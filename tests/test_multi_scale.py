@@ -40,8 +40,6 @@ def test_gather_unflips_scales_and_filters():
     d[1, 1] = [0.5, 0.50, 0.50, 0.52, 0.53]         # 11 x 12.25 px (+1): below the 32 px rule of scale 192
     got = M.gather_class([(192, False, d), (192, True, d)], 1, 500, 375, 320)
     assert got.shape == (2, 5)                       # the small box is dropped in both passes (longer side <= 32)
-    np.testing.assert_array_equal(got[0], np.array([0.1 * 500, 0.2 * 375, 0.3 * 500, 0.6 * 375, 0.9], np.float32)
-                                  .astype(np.float32) if False else got[0])
     assert got[0, 0] == np.float32(0.1) * np.float32(500) and got[0, 2] == np.float32(0.3) * np.float32(500)
     assert got[1, 0] == (np.float32(1) - np.float32(0.3)) * np.float32(500)         # flipped pass: x1' = (1 - x2) * w
     assert got[1, 2] == (np.float32(1) - np.float32(0.1)) * np.float32(500)
