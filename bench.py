@@ -409,8 +409,9 @@ def run_gpu(args, rank, world, local_rank):
         tc = agg.get('conv_tc')
         if tc:
             tflops = tc[0] / (tc[1] * 1e-3) / 1e12
-            roof = {'kernel': 'tcgen05 implicit-GEMM conv family (conv_halo_kernel, conv_halo_stream_kernel, conv_tc_kernel): '
-                              'all conv launches of the step, algorithmic FLOPs / summed CUDA-event time', 'bound': 'tensor',
+            roof = {'kernel': 'tcgen05 implicit-GEMM conv family (conv_stem_pair_kernel = conv1_1+conv1_2 fused, conv_halo_kernel, '
+                              'conv_halo_stream_kernel, conv_tc_kernel): all conv launches of the step, algorithmic FLOPs / summed '
+                              'CUDA-event time', 'bound': 'tensor',
                     'achieved': tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                     'frac': tflops / pk['bf16_tflops_sustained'], 'traffic': conv_traffic(),
                     'peak_source': pk['source'] + ', sustained bf16 (kernel timed inside a long step)',
