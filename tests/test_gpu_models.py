@@ -230,3 +230,22 @@ def test_tdrn_stream_follows_the_reference_loop():
         assert rel_err(boxes[0].cpu().numpy(), boxes_ref.numpy()) < 1e-4
         assert det.shape == (1, C, 200, 5) and float(det[0, 1:, 0, 0].min()) > 0.01
     assert keys == expect_keys
+
+
+@pytest.mark.parametrize('size,precision', [(192, 'fp32'), (192, 'bf16'), (448, 'bf16'), (704, 'bf16'), (704, 'fp32')])
+def test_other_input_sizes_vs_oracle(size, precision):
+    """The detector is fully convolutional (multi-scale testing runs ONE module at 192 ... 704 / 1216 pixels,
+    multi_eval.py:531-556): the pyramid, the prior layout and every kernel's tiling follow the input size."""
+    from oracle import model_ref as M
+    from oracle.make_golden import CASES, make_input
+    mod_name, spec_fn, build_kw, spec_kw, _ = CASES['drn_vgg320_multihead']
+    net, sd = _build(mod_name, spec_fn, build_kw, spec_kw, precision)
+    x = make_input(1, size, seed=size)
+    ref = M.drn_vgg_forward(sd, x, **spec_kw)
+    with torch.no_grad():
+        out = net(x.cuda())
+    P = 3 * sum((size // s) ** 2 for s in (8, 16, 32, 64))
+    assert tuple(out[0].shape) == (1, P, 4) and tuple(out[3].shape) == (P, 21)
+    assert rel_err(out[0].cpu().numpy(), ref[0].numpy()) < TOL[precision]
+    check_odm(out[2].cpu().numpy().reshape(-1, 4), ref[2].numpy().reshape(-1, 4), precision, 'odm_loc')
+    check_odm(out[3].cpu().numpy(), ref[3].numpy(), precision, 'conf')
