@@ -92,3 +92,81 @@ def test_product_nms_matches_reference_gpu_kernel(n, thresh):
     got = nms(dets, thresh)
     ora = nms_ref.cpu_nms(dets, thresh)
     assert [int(i) for i in ref] == [int(i) for i in got] == [int(i) for i in ora]
+
+
+def test_deform_head_vs_the_reference_kernels_speed_and_values():
+    """DeformConv head-to-head on the same B200 (BASELINE.json: "DeformConv % roofline"): the ODM head of pyramid level 0
+    at the bench shape (b32, 256 ch, 40x40, 3x3 loc/conf + 5x5 multihead, VOC-21) through
+      (a) the reference's own path: its unmodified CUDA im2col kernel per sample + fp32 cuBLAS GEMM, for loc, conf, loc_2,
+          conf_2 (deform_conv_cuda.c:157-193; 256 launches, replayed as ONE CUDA graph so that launch overhead is not held
+          against it), softmax by torch;
+      (b) tdrn_b200: per-tap projection GEMM + sampler (2 launches).
+    Values agree within the bf16 bar; the timings are written to gpurun_out/deform_vs_reference.txt."""
+    import os
+    from tdrn_b200 import ops
+    B, C, H, W, ncls = 32, 256, 40, 40, 21
+    g = torch.Generator().manual_seed(11)
+    bf = lambda t: t.to(torch.bfloat16).float()
+    x = bf(torch.randn(B, C, H, W, generator=g)).cuda()
+    off1 = (torch.randn(B, 18, H, W, generator=g) * 1.5).cuda()
+    off2 = (torch.randn(B, 50, H, W, generator=g) * 1.5).cuda()
+    wl, wc = bf(torch.randn(12, C, 3, 3, generator=g) * 0.03), bf(torch.randn(3 * ncls, C, 3, 3, generator=g) * 0.03)
+    wl2, wc2 = bf(torch.randn(12, C, 5, 5, generator=g) * 0.02), bf(torch.randn(3 * ncls, C, 5, 5, generator=g) * 0.02)
+    wl_c, wc_c, wl2_c, wc2_c = wl.cuda(), wc.cuda(), wl2.cuda(), wc2.cuda()
+
+    def reference_head():
+        loc = ref_native.deform_conv_forward(x, off1, wl_c, 1, 1, 1, 1) + ref_native.deform_conv_forward(x, off2, wl2_c, 1, 2, 1, 1)
+        conf = ref_native.deform_conv_forward(x, off1, wc_c, 1, 1, 1, 1) + ref_native.deform_conv_forward(x, off2, wc2_c, 1, 2, 1, 1)
+        loc = loc.permute(0, 2, 3, 1).reshape(B, -1, 4)                                # dualrefinedet_vggbn.py:186-189
+        conf = torch.softmax(conf.permute(0, 2, 3, 1).reshape(-1, ncls), 1)            # :196
+        return loc, conf
+
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    xb = nhwc(x).to(torch.bfloat16)
+    o1, o2 = nhwc(off1), nhwc(off2)
+    pc, n_pad = ops.pack_deform_proj_weight(torch.cat([wl, wc], 0), torch.cat([wl2, wc2], 0))
+    P = H * W * 3
+    loc_o = torch.zeros(B, P, 4, device='cuda')
+    conf_o = torch.zeros(B, P, ncls, device='cuda')
+
+    def ours():
+        ops.deform_head_projected(xb, o1, pc, n_pad, ncls, 3, 1, loc_o, conf_o, P, 0, offsets2=o2, kh2=5, pad2=2, softmax=True)
+
+    def timed(fn, graph):
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st), torch.no_grad():
+            for _ in range(2):
+                fn()
+            st.synchronize()
+            run = fn
+            if graph:
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=st):
+                    fn()
+                run = gr.replay
+            for _ in range(3):
+                run()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(10):
+                run()
+            e1.record(st)
+            st.synchronize()
+        return e0.elapsed_time(e1) / 10
+
+    loc_r, conf_r = reference_head()
+    ours()
+    torch.cuda.synchronize()
+    assert float((loc_o - loc_r).abs().max() / loc_r.abs().max()) < 2e-2
+    assert float((conf_o.view(-1, ncls) - conf_r).abs().max() / conf_r.abs().max()) < 2e-2
+    ms_ref = timed(reference_head, graph=True)
+    ms_ours = timed(ours, graph=True)
+    flops = 2.0 * B * H * W * 75 * C * 34
+    line = ('DeformConv head, level 0 of DualRefineDet-VGGBN-320 b32 (multihead, VOC-21), one B200:\n'
+            '  reference CUDA im2col kernel + fp32 cuBLAS GEMM (graph replay): %.3f ms  (%.1f TFLOP/s nominal)\n'
+            '  tdrn_b200 projection GEMM + sampler (graph replay):             %.3f ms  (%.1f TFLOP/s nominal)\n'
+            '  speed-up %.1fx\n' % (ms_ref, flops / ms_ref / 1e9, ms_ours, flops / ms_ours / 1e9, ms_ref / ms_ours))
+    os.makedirs('gpurun_out', exist_ok=True)
+    open('gpurun_out/deform_vs_reference.txt', 'w').write(line)
+    print(line)
+    assert ms_ours < ms_ref
