@@ -19,6 +19,8 @@ relative to the upstream reference checkout):
 * ``preprocess_ref``   -- restatement of data/__init__.py:7-12 (base_transform) incl. OpenCV's 8-bit INTER_LINEAR
   fixed-point resize (PARITY UNPINNED: OpenCV is not in this image; see the module header)
 * ``eval_ref``         -- restatement of the result scatter of evaluate.py:469-483
+* ``multi_scale_ref``  -- NumPy restatement of the multi-scale merge + bbox_vote (multi_eval.py:453-494,557-640);
+  bbox_vote pinned by ``make_golden_vote`` (runs the reference's own function source)
 * ``c/oracle.c``       -- plain-C restatement of the sampler, im2col+GEMM, decode and NMS
   (built into ``oracle/_build/liboracle.so`` by ``oracle/build.py``)
 * ``ref_shim``         -- imports the *real* reference Python in place from /root/reference

@@ -10,6 +10,10 @@ Everything is NumPy float32 arithmetic exactly as the reference performs it (the
   * `np.sum(acc[:, -1:])`          -> NumPy's pairwise sum over all members (n < 8: sequential from 0; n <= 128: 8 strided
                                       accumulators combined as ((0+1)+(2+3))+((4+5)+(6+7)), then the tail; larger n split in
                                       halves rounded down to a multiple of 8) -- pinned against np.sum in tests/test_multi_scale.py.
+Pin status: `bbox_vote` is PINNED against the reference's own function -- oracle/make_golden_vote.py executes the source of
+multi_eval.py:453-494 (extracted with `ast`; the module cannot be imported) on seeded detections and stores its outputs in
+tests/golden/bbox_vote.npz; restatement and device kernel reproduce them bit for bit.  The gathering loop (:557-640) is
+inline in `test_net` and cannot be run in isolation: restated only.
 Pinned where the reference leaves the order open: detections are visited by descending score, ties -> lower index
 (`argsort()[::-1]` of an unstable sort in the reference).
 

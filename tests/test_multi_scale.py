@@ -118,3 +118,37 @@ def test_multiscale_tester_end_to_end():
         assert np.array_equal(got[j], ref[j]), j
     with pytest.raises(ValueError):
         MultiScaleTester(net, det, 320, (104, 117, 123), scales=[300])
+
+
+def _vote_golden(golden):
+    g = golden('bbox_vote')
+    i = 0
+    while 'in_%d' % i in g:
+        yield g['in_%d' % i], g['out_%d' % i]
+        i += 1
+
+
+def test_bbox_vote_restatement_matches_the_reference_function(golden):
+    """tests/golden/bbox_vote.npz holds outputs of the reference's OWN bbox_vote (multi_eval.py:453-494, executed from its
+    source by oracle/make_golden_vote.py) on seeded detections, up to 2 800 boxes with ~50-member groups."""
+    n_cases = 0
+    for det, ref in _vote_golden(golden):
+        got = M.bbox_vote(det)
+        assert got.shape == ref.shape and np.array_equal(got.astype(np.float64), ref)
+        n_cases += 1
+    assert n_cases == 7
+
+
+@pytest.mark.gpu
+def test_multiscale_vote_kernel_matches_the_reference_function(golden):
+    """The device kernel against the same fixture: one pass, one class, identity scaling, a size rule that keeps everything."""
+    from tdrn_b200 import ops
+    for det, ref in _vote_golden(golden):
+        n = det.shape[0]
+        d = np.zeros((1, 2, n, 5), np.float32)
+        d[0, 1, :, 0] = det[:, 4]
+        d[0, 1, :, 1:] = det[:, :4]
+        rows, cnt = ops.multiscale_vote(torch.from_numpy(d).cuda(), [False], [0], [-1.0], 1, 1)
+        rows, cnt = rows.cpu().numpy(), cnt.cpu().numpy()
+        assert cnt[1] == ref.shape[0]
+        assert np.array_equal(rows[1, :cnt[1]].astype(np.float64), ref)
