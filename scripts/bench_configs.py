@@ -66,7 +66,7 @@ def mobilenet():
         a, _, l, c = net(x)
         return det.forward(l, c, pri, arm_loc_data=a)
     res = {'config': 'DualRefineDet-MobileNet 320x320 VOC-21, net+Detect'}
-    ms, p50, p99, _ = graph_time(f, frames(1, 320, 5).to(dev), iters=200)
+    ms, p50, p99, _ = graph_time(f, frames(1, 320, 5).to(dev), iters=1000)
     res['b1_latency_ms'] = {'mean': ms, 'p50': p50, 'p99': p99}
     ms, _, _, _ = graph_time(f, frames(64, 320, 6).to(dev))
     res['b64'] = {'ms_per_step': ms, 'frames_per_s': 64 / ms * 1e3}
