@@ -142,9 +142,9 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
     __shared__ unsigned long long keys[NMS_CAP];
     __shared__ unsigned hist[NMS_BINS];
     __shared__ unsigned part[NMS_THREADS];
-    __shared__ float4 cbox[NMS_CH];
-    __shared__ float carea[NMS_CH];
-    __shared__ int cidx[NMS_CH];
+    __shared__ float4 cbox2[2][NMS_CH];      // chunk boxes / areas / source indices, double-buffered: warp 1 fetches the next
+    __shared__ float carea2[2][NMS_CH];      // chunk while warp 0 resolves the current one
+    __shared__ int cidx2[2][NMS_CH];
     __shared__ unsigned csup[NMS_CH];        // suppressed by an earlier-kept box
     __shared__ unsigned crow[NMS_CH];        // bit j: candidate j (> i) overlaps candidate i
     __shared__ unsigned long long s_lo;
@@ -281,22 +281,28 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
         }
 
         // ---- 3. greedy NMS over the sorted batch, 32 candidates per chunk -----------------------------------------
-        for (unsigned c0 = 0; c0 < n_sel && kept_n < max_keep; c0 += NMS_CH) {
-            const int cnt = min(NMS_CH, (int)(n_sel - c0));
-            if (tid < cnt) {
-                const int src = (int)(0xffffffffu - (unsigned)(keys[c0 + tid] & 0xffffffffull));
-                float4 bx;
-                if (DETECT) {
-                    const float4 nb = p.boxes[(long long)b * p.P + src];
-                    bx = make_float4(__fmul_rn(nb.x, p.scale.x), __fmul_rn(nb.y, p.scale.y),
-                                     __fmul_rn(nb.z, p.scale.z), __fmul_rn(nb.w, p.scale.w));   // detection.py:59
-                } else {
-                    const float *d = p.dets + 5 * (long long)src;
-                    bx = make_float4(d[0], d[1], d[2], d[3]);
-                }
-                cbox[tid] = bx; carea[tid] = box_area(bx); cidx[tid] = src;
+        auto load_chunk = [&](unsigned c0, int buf, int t) {               // t = 0..31: candidate of the chunk
+            if (c0 + (unsigned)t >= n_sel) return;
+            const int src = (int)(0xffffffffu - (unsigned)(keys[c0 + t] & 0xffffffffull));
+            float4 bx;
+            if (DETECT) {
+                const float4 nb = p.boxes[(long long)b * p.P + src];
+                bx = make_float4(__fmul_rn(nb.x, p.scale.x), __fmul_rn(nb.y, p.scale.y),
+                                 __fmul_rn(nb.z, p.scale.z), __fmul_rn(nb.w, p.scale.w));   // detection.py:59
+            } else {
+                const float *d = p.dets + 5 * (long long)src;
+                bx = make_float4(d[0], d[1], d[2], d[3]);
             }
-            __syncthreads();
+            cbox2[buf][t] = bx; carea2[buf][t] = box_area(bx); cidx2[buf][t] = src;
+        };
+        if (tid < NMS_CH) load_chunk(0, 0, tid);
+        __syncthreads();
+        int cur = 0;
+        for (unsigned c0 = 0; c0 < n_sel && kept_n < max_keep; c0 += NMS_CH, cur ^= 1) {
+            const int cnt = min(NMS_CH, (int)(n_sel - c0));
+            const float4 *cbox = cbox2[cur];
+            const float *carea = carea2[cur];
+            const int *cidx = cidx2[cur];
             {
                 // thread (ci, l): candidate ci = tid / 8, sub-lane l = tid % 8
                 const int ci = tid >> 3, l = tid & 7;
@@ -323,14 +329,20 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
                 if (l == 0 && ci < NMS_CH) { csup[ci] = s; crow[ci] = row; }
             }
             __syncthreads();
+            if (warp == 1) load_chunk(c0 + NMS_CH, cur ^ 1, lane);          // next chunk's boxes, hidden behind the resolution
             if (warp == 0) {
                 const bool alive = lane < cnt && !csup[lane];
                 const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
                 const unsigned myrow = crow[lane];
-                unsigned removed = 0, keepmask = 0, k = kept_n;
-                for (int i = 0; i < cnt && k < max_keep; ++i) {              // uniform across the warp
+                // greedy resolution of the chunk in candidate order, visiting only the candidates that are still pending
+                // (typically a handful of the 32): the lowest pending one is kept and knocks out the later ones it overlaps
+                unsigned pending = alive_mask, keepmask = 0, k = kept_n;
+                while (pending && k < max_keep) {                            // uniform across the warp
+                    const int i = __ffs(pending) - 1;
                     const unsigned ri = __shfl_sync(0xffffffffu, myrow, i);
-                    if (((alive_mask >> i) & 1u) && !((removed >> i) & 1u)) { keepmask |= 1u << i; removed |= ri; ++k; }
+                    keepmask |= 1u << i;
+                    ++k;
+                    pending &= ~((1u << i) | ri);
                 }
                 if ((keepmask >> lane) & 1u) {
                     const unsigned pos = kept_n + __popc(keepmask & ((1u << lane) - 1u));
