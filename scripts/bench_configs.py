@@ -74,26 +74,28 @@ def mobilenet():
 
 
 def tdrn():
-    """One 16-frame clip, key-frame interval 4: static net on frames 0,4,8,12 (ret_loc), temporal net (dg = 8 deformable
-    heads, offsets from the key frame's regression) on all 16 frames, Detect with the key frame's arm_loc."""
+    """16-frame clips, key-frame interval 4: static net on frames 0,4,8,12 of every clip (ret_loc), temporal net (dg = 8
+    deformable heads, offsets from the key frame's regression) on all frames, Detect with the key frame's arm_loc.  One clip
+    per step (the latency configuration) and two clips per step (B = 32 temporal forwards: the throughput configuration)."""
     from tdrn_b200.model import ssd4scale_vgg as S
     C, T, K = 31, 16, 4
     stat = randomize_(S.build_net('test', 320, num_classes=C, bn=True, deform=False), 0).eval().to(dev)
     temp = randomize_(S.build_net('test', 320, num_classes=C, bn=True, deform=True), 1).eval().to(dev)
     pri = PriorBox(mb_cfg['VOC_320']).forward().to(dev)
     det = Detect(C, 0, 200, 0.01, 0.45)
-    x = frames(T, 320, 7).to(dev)
 
     def f(x):
-        keys = x[::K]                                             # 4 key frames
+        keys = x[::K]                                             # key frames (clips are stacked along the batch)
         s_loc, s_conf, loc_maps = stat(keys, ret_loc=True)
         ref = [m.repeat_interleave(K, 0) for m in loc_maps]       # every frame uses its key frame's regression
         out = temp(x, ref_loc=ref, ret_off=True)
         arm = s_loc.repeat_interleave(K, 0)
         return det.forward(out[0], out[1], pri, arm_loc_data=arm)
-    ms, _, _, _ = graph_time(f, x)
-    return {'config': 'TDRN VGGBN-320 VID-31, one 16-frame clip, key-frame interval 4 (4 static + 16 temporal forwards + Detect)',
-            'ms_per_clip': ms, 'frames_per_s_per_gpu': T / ms * 1e3, 'tflops': 1321.0 / ms}
+    res = {'config': 'TDRN VGGBN-320 VID-31, 16-frame clips, key-frame interval 4 (4 static + 16 temporal forwards + Detect per clip)'}
+    for clips in (1, 2):
+        ms, _, _, _ = graph_time(f, frames(T * clips, 320, 7).to(dev))
+        res['clips_per_step_%d' % clips] = {'ms_per_step': ms, 'frames_per_s_per_gpu': T * clips / ms * 1e3, 'tflops': 1321.0 * clips / ms}
+    return res
 
 
 if __name__ == '__main__':
