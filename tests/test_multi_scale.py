@@ -152,3 +152,26 @@ def test_multiscale_vote_kernel_matches_the_reference_function(golden):
         rows, cnt = rows.cpu().numpy(), cnt.cpu().numpy()
         assert cnt[1] == ref.shape[0]
         assert np.array_equal(rows[1, :cnt[1]].astype(np.float64), ref)
+
+
+@pytest.mark.skipif(not __import__('os').path.exists('/root/reference/data/config.py'),
+                    reason='reference checkout only exists in the build container')
+def test_multi_scale_prior_dicts_equal_the_reference_values():
+    """multi_cfg / multi_cfg_512 / multi_scale against the dict literals of data/config.py:139-261 and multi_eval.py:21-24
+    (read with `ast`: importing the reference's data package opens dataset files)."""
+    import ast
+    from tdrn_b200.data import config as C
+    ns = {}
+    for path, want in (('/root/reference/data/config.py', None), ('/root/reference/multi_eval.py', {'multi_scale'})):
+        for node in ast.parse(open(path).read()).body:
+            if isinstance(node, ast.Assign) and isinstance(node.value, ast.Dict):
+                name = node.targets[0].id if isinstance(node.targets[0], ast.Name) else None
+                if want is not None and name not in want:
+                    continue
+                try:
+                    exec(compile(ast.Module([node], []), path, 'exec'), ns)
+                except NameError:
+                    pass                                      # dicts that reference dataset constants: not needed here
+    assert ns['multi_cfg'] == C.multi_cfg and ns['multi_cfg_512'] == C.multi_cfg_512
+    assert ns['multi_scale'] == C.multi_scale
+    assert ns['VOC_320'] == C.VOC_320 and ns['VOC_512_RefineDet'] == C.VOC_512_RefineDet
