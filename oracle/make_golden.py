@@ -87,6 +87,26 @@ def tdrn_case(ns):
                 sd_checksum=np.float64(M.state_dict_checksum(sd_s) + M.state_dict_checksum(sd_t)))
 
 
+def tdrn_mobile_case(ns):
+    """The same key-frame step with the MobileNet TDRN pair (model/ssd4scale_mobile.py; evaluate_trn.py:537)."""
+    C = 31
+    sd_s = M.make_state_dict(M.param_spec_ssd4scale_mobile(C, deform=False), SEED_W)
+    sd_t = M.make_state_dict(M.param_spec_ssd4scale_mobile(C, deform=True), SEED_W + 1)
+    static = ns.ssd4scale_mobile.build_net('test', 320, C, deform=False)
+    temporal = ns.ssd4scale_mobile.build_net('test', 320, C, deform=True)
+    static.load_state_dict(sd_s, strict=True); temporal.load_state_dict(sd_t, strict=True)
+    static.eval(); temporal.eval()
+    x = make_input(1, 320)
+    with torch.no_grad():
+        s_out = static(x, ret_loc=True)
+        t_out = temporal(x, ref_loc=s_out[2], offset_list=[], ret_off=True)
+    st = 7
+    return dict(static_loc=s_out[0][0, ::st].numpy(), static_conf=s_out[1][::st].numpy(),
+                temporal_loc=t_out[0][0, ::st].numpy(), temporal_conf=t_out[1][::st].numpy(),
+                offset0=t_out[2][0][0, :, ::4, ::4].numpy(), stride=np.int64(st),
+                sd_checksum=np.float64(M.state_dict_checksum(sd_s) + M.state_dict_checksum(sd_t)))
+
+
 def syn_inputs(B=2, P=6375, C=21, seed=7):
     """Synthetic Detect inputs (regime T: background-dominated softmax), regenerated by the tests."""
     g = torch.Generator().manual_seed(seed)
@@ -128,20 +148,24 @@ def small_cases(ns):
     return rec
 
 
-def main():
+def main(only=()):
+    """``python -m oracle.make_golden [fixture ...]``: all fixtures, or only the named ones."""
     ns = ref_shim.load()
     os.makedirs(OUT, exist_ok=True)
-    for name in CASES:
-        rec = run_case(ns, name)
+    jobs = [(name, (lambda name=name: run_case(ns, name))) for name in CASES]
+    jobs += [('tdrn_vgg320_keyframe', lambda: tdrn_case(ns)), ('tdrn_mobile320_keyframe', lambda: tdrn_mobile_case(ns)),
+             ('small_cases', lambda: small_cases(ns))]
+    unknown = set(only) - set(n for n, _ in jobs)
+    if unknown:
+        raise SystemExit('unknown fixture(s): %s' % ', '.join(sorted(unknown)))
+    for name, fn in jobs:
+        if only and name not in only:
+            continue
+        rec = fn()
         np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
         print(name, {k: getattr(v, 'shape', v) for k, v in rec.items()})
-    rec = tdrn_case(ns)
-    np.savez_compressed(os.path.join(OUT, 'tdrn_vgg320_keyframe.npz'), **rec)
-    print('tdrn', {k: getattr(v, 'shape', v) for k, v in rec.items()})
-    rec = small_cases(ns)
-    np.savez_compressed(os.path.join(OUT, 'small_cases.npz'), **rec)
-    print('small', {k: getattr(v, 'shape', v) for k, v in rec.items()})
 
 
 if __name__ == '__main__':
-    main()
+    import sys
+    main(tuple(sys.argv[1:]))

@@ -222,6 +222,36 @@ def param_spec_ssd4scale_vgg(num_classes=31, c7_channel=1024, bn=True, deform=Fa
     return spec
 
 
+def param_spec_ssd4scale_mobile(num_classes=31, c7_channel=1024, deform=False):
+    """ssd4scale_mobile.py:19-82 (backbone as MOBILENET_DW with the last block 1024 -> c7_channel; heads keep bias
+    when plain, are bias-free ConvOffset2d with 8 deformable groups when ``deform``)."""
+    spec = []
+    spec.append(('backbone.0.0.weight', (32, 3, 3, 3), 'conv'))
+    _bn(spec, 'backbone.0.1', 32)
+    for n, (i, o, s) in enumerate(MOBILENET_DW):
+        _spec_conv_dw(spec, 'backbone.%d' % (n + 1), i, c7_channel if n == len(MOBILENET_DW) - 1 else o)
+    spec.append(('L2Norm_4_3.weight', (512,), 'l2norm10'))       # :40 (scale 10; the DualRefineDet variant uses 20)
+    spec.append(('L2Norm_5_3.weight', (1024,), 'l2norm8'))       # :41
+    for e, cin in enumerate((c7_channel, 512)):                  # :43-51
+        _conv(spec, 'extras.%d.0' % e, 256, cin, 1)
+        _bn(spec, 'extras.%d.1' % e, 256)
+        _spec_conv_dw(spec, 'extras.%d.3' % e, 256, 512)
+    src = [512, c7_channel, 512, 512]
+    if deform:                                                   # :52-71
+        for k in range(4):
+            _conv(spec, 'offset.%d' % k, 8 * 18, NUM_BOX * 4, 1, kind='offset_conv')
+        for k in range(4):
+            _conv(spec, 'arm_loc.%d' % k, NUM_BOX * 4, src[k], 3, False, 'deform')
+        for k in range(4):
+            _conv(spec, 'arm_conf.%d' % k, NUM_BOX * num_classes, src[k], 3, False, 'deform')
+    else:                                                        # :72-82
+        for k in range(4):
+            _conv(spec, 'arm_loc.%d' % k, NUM_BOX * 4, src[k], 3)
+        for k in range(4):
+            _conv(spec, 'arm_conf.%d' % k, NUM_BOX * num_classes, src[k], 3)
+    return spec
+
+
 def make_state_dict(spec, seed=0, offset_gain=1.5):
     """Deterministic random weights (CPU mt19937): He-uniform convs, randomised BN statistics so
     BN folding is exercised, xavier-uniform deformable weights (networks.py:727)."""
@@ -425,29 +455,61 @@ def ssd4scale_vgg_forward(sd, x, num_classes=31, c7_channel=1024, bn=True, defor
                           ref_loc=(), offset_list=(), ret_loc=False, ret_off=False, softmax=True):
     """ssd4scale_vgg.py:71-135."""
     with torch.no_grad():
+        offsets = None
         if deform:
             if not offset_list:
                 offsets = [_c(sd, 'offset.%d' % k, ref_loc[k]) for k in range(4)]   # :72-76
             else:
                 offsets = list(offset_list)
         src = _vgg_trunk(sd, x, bn, c7_channel)
-        locs, confs, loc_maps = [], [], []
-        for k in range(4):
-            if deform:
-                l = deform_conv_forward(src[k], offsets[k], sd['arm_loc.%d.weight' % k], 1, 1, 1, 8)
-                c = deform_conv_forward(src[k], offsets[k], sd['arm_conf.%d.weight' % k], 1, 1, 1, 8)
+        return _ssd4scale_heads(sd, src, x, num_classes, deform, offsets, ret_loc, ret_off, softmax)
+
+
+def _ssd4scale_heads(sd, src, x, num_classes, deform, offsets, ret_loc, ret_off, softmax):
+    """Head loop and output tuple shared by the two SSD4Scale variants (ssd4scale_vgg.py:104-135,
+    ssd4scale_mobile.py:108-140)."""
+    locs, confs, loc_maps = [], [], []
+    for k in range(4):
+        if deform:
+            l = deform_conv_forward(src[k], offsets[k], sd['arm_loc.%d.weight' % k], 1, 1, 1, 8)
+            c = deform_conv_forward(src[k], offsets[k], sd['arm_conf.%d.weight' % k], 1, 1, 1, 8)
+        else:
+            l = _c(sd, 'arm_loc.%d' % k, src[k], 1, 1)
+            c = _c(sd, 'arm_conf.%d' % k, src[k], 1, 1)
+            loc_maps.append(l)
+        locs.append(_flat(l)); confs.append(_flat(c))
+    loc = torch.cat(locs, 1)
+    conf = torch.cat(confs, 1).view(-1, num_classes)
+    if softmax:
+        conf = F.softmax(conf, dim=1)
+    out = [loc.view(x.size(0), -1, 4), conf]
+    if ret_loc:
+        out.append(loc_maps)
+    if ret_off:
+        out.append(offsets)
+    return tuple(out)
+
+
+def ssd4scale_mobile_forward(sd, x, num_classes=31, c7_channel=1024, deform=False,
+                             ref_loc=(), offset_list=(), ret_loc=False, ret_off=False, softmax=True):
+    """ssd4scale_mobile.py:86-140."""
+    with torch.no_grad():
+        offsets = None
+        if deform:
+            if not offset_list:
+                offsets = [_c(sd, 'offset.%d' % k, ref_loc[k]) for k in range(4)]   # :87-93
             else:
-                l = _c(sd, 'arm_loc.%d' % k, src[k], 1, 1)
-                c = _c(sd, 'arm_conf.%d' % k, src[k], 1, 1)
-                loc_maps.append(l)
-            locs.append(_flat(l)); confs.append(_flat(c))
-        loc = torch.cat(locs, 1)
-        conf = torch.cat(confs, 1).view(-1, num_classes)
-        if softmax:
-            conf = F.softmax(conf, dim=1)
-        out = [loc.view(x.size(0), -1, 4), conf]
-        if ret_loc:
-            out.append(loc_maps)
-        if ret_off:
-            out.append(offsets)
-        return tuple(out)
+                offsets = list(offset_list)
+        inp = x
+        x = F.relu(_b(sd, 'backbone.0.1', _c(sd, 'backbone.0.0', x, 2, 1)))
+        src = []
+        for n, (i, o, s) in enumerate(MOBILENET_DW):
+            if n + 1 == 12:                                                         # :101-103
+                src.append(l2norm(x, sd['L2Norm_4_3.weight']))
+            x = _conv_dw(sd, 'backbone.%d' % (n + 1), x, s)
+        src.append(l2norm(x, sd['L2Norm_5_3.weight']))                              # :104-106
+        for e in range(2):                                                          # :108-110
+            x = F.relu(_b(sd, 'extras.%d.1' % e, _c(sd, 'extras.%d.0' % e, x)))
+            x = _conv_dw(sd, 'extras.%d.3' % e, x, 2)
+            src.append(x)
+        return _ssd4scale_heads(sd, src, inp, num_classes, deform, offsets, ret_loc, ret_off, softmax)

@@ -74,6 +74,7 @@ def load():
         ns.drn_mobilenet = importlib.import_module('model.dualrefinedet_mobilenet')
         ns.refinedet_vgg = importlib.import_module('model.refinedet_vgg')
         ns.ssd4scale_vgg = importlib.import_module('model.ssd4scale_vgg')
+        ns.ssd4scale_mobile = importlib.import_module('model.ssd4scale_mobile')
         ns.layers = importlib.import_module('layers')
         ns.box_utils = importlib.import_module('layers.box_utils')
         ns.Detect = ns.layers.Detect

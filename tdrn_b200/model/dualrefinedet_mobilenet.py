@@ -18,6 +18,30 @@ DW_CFG = [(32, 64, 1), (64, 128, 2), (128, 128, 1), (128, 256, 1), (256, 256, 1)
           (512, 1024, 2), (1024, 1024, 1)]
 
 
+def _dw_block(E, name, x, stride):
+    """conv_dw (networks.py:736-745): depthwise 3x3+BN+ReLU then pointwise 1x1+BN+ReLU."""
+    x = ops.dwconv3x3(x, E.packed_dw(name + '.0', name + '.1', stride), relu=True)
+    return E.conv(name + '.3', x, bn=name + '.4', relu=True)
+
+
+def mobilenet_sources(E, x):
+    """The four ARM sources of the MobileNet trunk (dualrefinedet_mobilenet.py:139-152; the same loop in
+    ssd4scale_mobile.py:99-110): L2Norm of backbone[11]'s output (512 @ 40x40), L2Norm of the last block
+    (1024 @ 20x20), then the two 1x1 + conv_dw(s2) extras (512 @ 10x10, 512 @ 5x5).  NHWC."""
+    x = E.conv_first('backbone.0.0', x, 2, 'backbone.0.1')
+    arm_sources = []
+    for n, (i, o, s) in enumerate(DW_CFG):
+        if n + 1 == 12:
+            arm_sources.append(ops.l2norm(x, E.vec('L2Norm_4_3.weight')))
+        x = _dw_block(E, 'backbone.%d' % (n + 1), x, s)
+    arm_sources.append(ops.l2norm(x, E.vec('L2Norm_5_3.weight')))
+    for e in range(2):
+        x = E.conv('extras.%d.0' % e, x, bn='extras.%d.1' % e, relu=True)
+        x = _dw_block(E, 'extras.%d.3' % e, x, 2)
+        arm_sources.append(x)
+    return arm_sources
+
+
 class RefineSSD(DetectorBase):
     def __init__(self, size, num_classes=21, phase='train', def_groups=1, multihead=False):
         super(RefineSSD, self).__init__()
@@ -37,26 +61,10 @@ class RefineSSD(DetectorBase):
         if phase == 'test':
             self.softmax = nn.Softmax(dim=1)
 
-    def _dw_block(self, E, name, x, stride):
-        """conv_dw (networks.py:736-745): depthwise 3x3+BN+ReLU then pointwise 1x1+BN+ReLU."""
-        x = ops.dwconv3x3(x, E.packed_dw(name + '.0', name + '.1', stride), relu=True)
-        return E.conv(name + '.3', x, bn=name + '.4', relu=True)
-
     def forward(self, x, _offsets=None):
         """``_offsets``: test hook, see dualrefinedet_vggbn.RefineSSD.forward."""
         E = self.engine()
-        x = self._check_input(x)
-        x = E.conv_first('backbone.0.0', x, 2, 'backbone.0.1')
-        arm_sources = []
-        for n, (i, o, s) in enumerate(DW_CFG):
-            if n + 1 == 12:
-                arm_sources.append(ops.l2norm(x, E.vec('L2Norm_4_3.weight')))
-            x = self._dw_block(E, 'backbone.%d' % (n + 1), x, s)
-        arm_sources.append(ops.l2norm(x, E.vec('L2Norm_5_3.weight')))
-        for e in range(2):
-            x = E.conv('extras.%d.0' % e, x, bn='extras.%d.1' % e, relu=True)
-            x = self._dw_block(E, 'extras.%d.3' % e, x, 2)
-            arm_sources.append(x)
+        arm_sources = mobilenet_sources(E, self._check_input(x))
         P, lv = prior_layout(arm_sources)
         arm_loc, offs, offs2, odm_sources = E.arm_and_tcb(arm_sources, P, lv, self.multihead)
         if _offsets is not None:

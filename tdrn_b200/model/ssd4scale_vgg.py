@@ -18,15 +18,11 @@ from .networks import vgg, vgg_base, ConvOffset2d
 DF_GROUP = 8
 
 
-class SSD4Scale(DetectorBase):
-    def __init__(self, size, num_classes=21, phase='train', c7_channel=1024, bn=True, deform=False):
-        super(SSD4Scale, self).__init__()
-        self.num_classes, self.size, self.phase, self.bn, self.deform = num_classes, size, phase, bn, deform
-        self.backbone = nn.ModuleList(vgg(vgg_base['320'], 3, batch_norm=bn, pool5_ds=True, c7_channel=c7_channel))
-        self.L2Norm_4_3 = L2Norm(512, 10)
-        self.L2Norm_5_3 = L2Norm(512, 8)
-        add_vgg_extras(self, bn, c7_channel)
-        src = [512, 512, c7_channel, 512]
+class SSD4ScaleBase(DetectorBase):
+    """Head construction and ``forward`` shared by the VGG and MobileNet SSD4Scale nets; a subclass builds its
+    trunk and says how the four ARM sources come out of it (``_sources``)."""
+
+    def _add_heads(self, src, num_classes, deform):
         if deform:
             self.offset = _list(lambda k: nn.Conv2d(12, DF_GROUP * 18, kernel_size=1))
             self.arm_loc = _list(lambda k: ConvOffset2d(src[k], 12, 3, 1, 1, num_deformable_groups=DF_GROUP))
@@ -34,8 +30,11 @@ class SSD4Scale(DetectorBase):
         else:
             self.arm_loc = _list(lambda k: nn.Conv2d(src[k], 12, kernel_size=3, stride=1, padding=1))
             self.arm_conf = _list(lambda k: nn.Conv2d(src[k], 3 * num_classes, kernel_size=3, stride=1, padding=1))
-        if phase == 'test':
+        if self.phase == 'test':
             self.softmax = nn.Softmax(dim=1)
+
+    def _sources(self, E, x):
+        raise NotImplementedError
 
     def forward(self, x, ref_loc=list(), offset_list=list(), ret_loc=False, ret_off=False):
         E = self.engine()
@@ -47,7 +46,7 @@ class SSD4Scale(DetectorBase):
                                     out_dtype=torch.float32) for k, rl in enumerate(ref_loc)]
             else:
                 offs_nhwc = [ops.nchw_f32_to_nhwc(o.float(), torch.float32) for o in offset_list]
-        src = E.vgg_trunk(x, self.bn)
+        src = self._sources(E, x)
         P, lv = prior_layout(src)
         if self.deform:
             loc, conf = E.deform_heads(src, offs_nhwc, None, P, lv, self.num_classes, DF_GROUP, False,
@@ -66,6 +65,20 @@ class SSD4Scale(DetectorBase):
         if ret_off:
             out.append([ops.nhwc_to_nchw_f32(o) for o in offs_nhwc])
         return tuple(out)
+
+
+class SSD4Scale(SSD4ScaleBase):
+    def __init__(self, size, num_classes=21, phase='train', c7_channel=1024, bn=True, deform=False):
+        super(SSD4Scale, self).__init__()
+        self.num_classes, self.size, self.phase, self.bn, self.deform = num_classes, size, phase, bn, deform
+        self.backbone = nn.ModuleList(vgg(vgg_base['320'], 3, batch_norm=bn, pool5_ds=True, c7_channel=c7_channel))
+        self.L2Norm_4_3 = L2Norm(512, 10)
+        self.L2Norm_5_3 = L2Norm(512, 8)
+        add_vgg_extras(self, bn, c7_channel)
+        self._add_heads([512, 512, c7_channel, 512], num_classes, deform)
+
+    def _sources(self, E, x):
+        return E.vgg_trunk(x, self.bn)
 
 
 def build_net(phase, size=320, num_classes=21, c7_channel=1024, bn=False, deform=False):

@@ -78,7 +78,8 @@ def test_nms_wrapper_empty_input():
 
 def test_state_dict_surface_matches_reference_keys():
     from oracle import model_ref as M
-    from tdrn_b200.model import dualrefinedet_vggbn as V, dualrefinedet_mobilenet as MB, refinedet_vgg as R, ssd4scale_vgg as S
+    from tdrn_b200.model import (dualrefinedet_vggbn as V, dualrefinedet_mobilenet as MB, refinedet_vgg as R, ssd4scale_vgg as S,
+                                 ssd4scale_mobile as SM)
 
     def chk(net, spec):
         got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
@@ -91,6 +92,8 @@ def test_state_dict_surface_matches_reference_keys():
     chk(R.build_net('test', 320, 21, use_refine=True), M.param_spec_refinedet_vgg(21, True))
     chk(S.build_net('test', 320, 31, bn=True, deform=True), M.param_spec_ssd4scale_vgg(31, bn=True, deform=True))
     chk(S.build_net('test', 320, 31, bn=True, deform=False), M.param_spec_ssd4scale_vgg(31, bn=True, deform=False))
+    chk(SM.build_net('test', 320, 31, deform=True), M.param_spec_ssd4scale_mobile(31, deform=True))
+    chk(SM.build_net('test', 320, 31, deform=False), M.param_spec_ssd4scale_mobile(31, deform=False))
     assert V.build_net('test', 300) is None        # dualrefinedet_vggbn.py:218-220
     net = V.build_net('test', 320, 21)
     assert (net.size, net.num_classes, net.phase) == (320, 21, 'test')

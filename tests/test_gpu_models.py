@@ -137,6 +137,71 @@ def test_tdrn_keyframe_vs_reference_golden(golden, precision):
     assert len(t2) == 2 and rel_err(t2[0].cpu().numpy(), t[0].cpu().numpy()) < 1e-6
 
 
+def rows_off(out, ref, thr=TOL['bf16']):
+    """Fraction of rows whose max error exceeds ``thr`` x max|ref|."""
+    ref = np.asarray(ref, np.float64)
+    rows = np.abs(np.asarray(out, np.float64) - ref).reshape(len(ref), -1).max(1) / np.abs(ref).max()
+    return float((rows > thr).mean())
+
+
+@pytest.mark.xfail(strict=False, reason='written after this round\'s GPU budget was spent: not yet run on a B200 (the '
+                   'kernels underneath are the verified ones; only the composition is new).  Non-strict, so an '
+                   'unverified test cannot mask the verified suite under -x; an XPASS is the expected outcome.')
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_tdrn_mobile_keyframe_vs_reference_golden(golden, precision):
+    """MobileNet TDRN pair (model/ssd4scale_mobile.py, `evaluate_trn.py:537`): static net with ``ret_loc``, temporal
+    net with computed / cached / given offsets.  fp32 path: 1e-4 max-norm on everything.  bf16 path: this trunk stacks
+    27 bf16-rounded layers under random-init heads whose logits reach |60|, so the gate is the one of the DualRefineDet
+    MobileNet variant (relative L2 + fraction of rows beyond 2e-2; a CPU emulation of the bf16 roundings gives
+    L2 1.3-2.0e-2 and <= 1.3 % of the rows); end to end (offsets regressed from the bf16 static net) only the row
+    fraction is meaningful: the reference's sampler is discontinuous at the map border, the flipped taps change a
+    few rows by O(1) and dominate any norm (emulation: 1.8-2.8 % of the rows)."""
+    from oracle import model_ref as M
+    from oracle.make_golden import SEED_W, make_input
+    from tdrn_b200.model import ssd4scale_mobile as S
+    g = golden('tdrn_mobile320_keyframe')
+    sd_s = M.make_state_dict(M.param_spec_ssd4scale_mobile(31, deform=False), SEED_W)
+    sd_t = M.make_state_dict(M.param_spec_ssd4scale_mobile(31, deform=True), SEED_W + 1)
+    static = S.build_net('test', 320, 31, deform=False)
+    temporal = S.build_net('test', 320, 31, deform=True)
+    static.load_state_dict(sd_s); temporal.load_state_dict(sd_t)
+    static = static.eval().cuda().set_precision(precision)
+    temporal = temporal.eval().cuda().set_precision(precision)
+    x = make_input(1, 320).cuda()
+    with torch.no_grad():
+        s = static(x, ret_loc=True)
+        t = temporal(x, ref_loc=s[2], offset_list=[], ret_off=True)
+        t2 = temporal(x, ref_loc=[], offset_list=t[2])                 # cached offsets on non-key frames
+        s_ref = M.ssd4scale_mobile_forward(sd_s, x.cpu(), 31, deform=False, ret_loc=True)
+        t_ref = M.ssd4scale_mobile_forward(sd_t, x.cpu(), 31, deform=True, ref_loc=s_ref[2], ret_off=True)
+        t3 = temporal(x, ref_loc=[], offset_list=[o.cuda() for o in t_ref[2]])   # the oracle's fp32 offsets, given
+    torch.cuda.synchronize()
+    assert tuple(s[0].shape) == (1, 6375, 4) and tuple(s[1].shape) == (6375, 31)
+    assert [tuple(m.shape) for m in s[2]] == [(1, 12, 40, 40), (1, 12, 20, 20), (1, 12, 10, 10), (1, 12, 5, 5)]
+    assert [tuple(o.shape) for o in t[2]] == [(1, 144, 40, 40), (1, 144, 20, 20), (1, 144, 10, 10), (1, 144, 5, 5)]
+    assert len(t2) == 2 and rel_err(t2[0].cpu().numpy(), t[0].cpu().numpy()) < 1e-6
+    st = int(g['stride'])
+    if precision == 'fp32':
+        tol = TOL['fp32']
+        assert rel_err(t3[0].cpu().numpy(), t_ref[0].numpy()) < tol
+        assert rel_err(t3[1].cpu().numpy(), t_ref[1].numpy()) < tol
+        assert rel_err(s[0][0, ::st].cpu().numpy(), g['static_loc']) < tol
+        assert rel_err(s[1][::st].cpu().numpy(), g['static_conf']) < tol
+        assert rel_err(t[0][0, ::st].cpu().numpy(), g['temporal_loc']) < tol
+        assert rel_err(t[1][::st].cpu().numpy(), g['temporal_conf']) < tol
+        assert rel_err(t[2][0][0, :, ::4, ::4].cpu().numpy(), g['offset0']) < tol
+        for k in range(4):
+            assert rel_err(s[2][k].cpu().numpy(), s_ref[2][k].numpy()) < tol
+        return
+    check_odm(t3[0][0].cpu().numpy(), t_ref[0][0].numpy(), precision, 'temporal_loc, offsets given')
+    check_odm(t3[1].cpu().numpy(), t_ref[1].numpy(), precision, 'temporal_conf, offsets given')
+    check_odm(s[0][0, ::st].cpu().numpy(), g['static_loc'], precision, 'static_loc')
+    check_odm(s[1][::st].cpu().numpy(), g['static_conf'], precision, 'static_conf')
+    assert rel_err(t[2][0][0, :, ::4, ::4].cpu().numpy(), g['offset0']) < 4e-2
+    assert rows_off(t[0][0, ::st].cpu().numpy(), g['temporal_loc']) < 0.1
+    assert rows_off(t[1][::st].cpu().numpy(), g['temporal_conf']) < 0.1
+
+
 @pytest.mark.parametrize('name', ['drn_vgg320_multihead', 'drn_mobilenet320'])
 def test_bf16_heads_with_reference_offsets(name):
     """bf16 path with the ORACLE's fp32 offsets injected: backbone, FPN and the fused deformable heads meet

@@ -41,6 +41,29 @@ def test_tdrn_restatement_matches_reference_golden(golden):
     assert rel_err(t[2][0][0, :, ::4, ::4].numpy(), g['offset0']) < 1e-5
 
 
+def test_tdrn_mobile_restatement_matches_reference_golden(golden):
+    """MobileNet TDRN pair (model/ssd4scale_mobile.py): restatement vs the reference's own modules."""
+    g = golden('tdrn_mobile320_keyframe')
+    sd_s = M.make_state_dict(M.param_spec_ssd4scale_mobile(31, deform=False), SEED_W)
+    sd_t = M.make_state_dict(M.param_spec_ssd4scale_mobile(31, deform=True), SEED_W + 1)
+    chk = M.state_dict_checksum(sd_s) + M.state_dict_checksum(sd_t)
+    assert abs(chk - float(g['sd_checksum'])) < 1e-6 * float(g['sd_checksum']), 'weight RNG drifted'
+    x = make_input(1, 320)
+    s = M.ssd4scale_mobile_forward(sd_s, x, 31, deform=False, ret_loc=True)
+    t = M.ssd4scale_mobile_forward(sd_t, x, 31, deform=True, ref_loc=s[2], ret_off=True)
+    assert tuple(s[0].shape) == (1, 6375, 4) and tuple(s[1].shape) == (6375, 31)
+    assert [tuple(m.shape) for m in s[2]] == [(1, 12, 40, 40), (1, 12, 20, 20), (1, 12, 10, 10), (1, 12, 5, 5)]
+    st = int(g['stride'])
+    assert rel_err(s[0][0, ::st].numpy(), g['static_loc']) < 1e-5
+    assert rel_err(s[1][::st].numpy(), g['static_conf']) < 1e-5
+    assert rel_err(t[0][0, ::st].numpy(), g['temporal_loc']) < 1e-5
+    assert rel_err(t[1][::st].numpy(), g['temporal_conf']) < 1e-5
+    assert rel_err(t[2][0][0, :, ::4, ::4].numpy(), g['offset0']) < 1e-5
+    # cached offsets on non-key frames (evaluate_trn.py:460-462): same result as recomputing them
+    t2 = M.ssd4scale_mobile_forward(sd_t, x, 31, deform=True, offset_list=t[2])
+    assert len(t2) == 2 and torch.equal(t2[0], t[0]) and torch.equal(t2[1], t[1])
+
+
 def test_prior_box_bit_exact(golden):
     g = golden('small_cases')
     for name, cfg in (('VOC_320', D.VOC_320), ('VOC_512_RefineDet', D.VOC_512_RefineDet)):
