@@ -2,7 +2,7 @@
 record in DESIGN.md -- bench.py's JSON line stays on configs[1].  CUDA-graph replay, CUDA events, synthetic inputs
 resident in HBM, 20 timed replays after 5 warm-ups.
 
-    python scripts/bench_configs.py [coco512] [mobilenet] [tdrn]
+    python scripts/bench_configs.py [coco512] [mobilenet] [tdrn] [tdrn_mobile]
 """
 import json
 import os
@@ -73,14 +73,13 @@ def mobilenet():
     return res
 
 
-def tdrn():
+def _tdrn(S, kw, label, gflop_per_clip):
     """16-frame clips, key-frame interval 4: static net on frames 0,4,8,12 of every clip (ret_loc), temporal net (dg = 8
     deformable heads, offsets from the key frame's regression) on all frames, Detect with the key frame's arm_loc.  One clip
     per step (the latency configuration) and two clips per step (B = 32 temporal forwards: the throughput configuration)."""
-    from tdrn_b200.model import ssd4scale_vgg as S
     C, T, K = 31, 16, 4
-    stat = randomize_(S.build_net('test', 320, num_classes=C, bn=True, deform=False), 0).eval().to(dev)
-    temp = randomize_(S.build_net('test', 320, num_classes=C, bn=True, deform=True), 1).eval().to(dev)
+    stat = randomize_(S.build_net('test', 320, num_classes=C, deform=False, **kw), 0).eval().to(dev)
+    temp = randomize_(S.build_net('test', 320, num_classes=C, deform=True, **kw), 1).eval().to(dev)
     pri = PriorBox(mb_cfg['VOC_320']).forward().to(dev)
     det = Detect(C, 0, 200, 0.01, 0.45)
 
@@ -91,15 +90,28 @@ def tdrn():
         out = temp(x, ref_loc=ref, ret_off=True)
         arm = s_loc.repeat_interleave(K, 0)
         return det.forward(out[0], out[1], pri, arm_loc_data=arm)
-    res = {'config': 'TDRN VGGBN-320 VID-31, 16-frame clips, key-frame interval 4 (4 static + 16 temporal forwards + Detect per clip)'}
+    res = {'config': 'TDRN %s-320 VID-31, 16-frame clips, key-frame interval 4 (4 static + 16 temporal forwards + Detect per clip)' % label}
     for clips in (1, 2):
         ms, _, _, _ = graph_time(f, frames(T * clips, 320, 7).to(dev))
-        res['clips_per_step_%d' % clips] = {'ms_per_step': ms, 'frames_per_s_per_gpu': T * clips / ms * 1e3, 'tflops': 1321.0 * clips / ms}
+        res['clips_per_step_%d' % clips] = {'ms_per_step': ms, 'frames_per_s_per_gpu': T * clips / ms * 1e3}
+        if gflop_per_clip:
+            res['clips_per_step_%d' % clips]['tflops'] = gflop_per_clip * clips / ms
     return res
 
 
+def tdrn():
+    from tdrn_b200.model import ssd4scale_vgg as S
+    return _tdrn(S, dict(bn=True), 'VGGBN', 1321.0)
+
+
+def tdrn_mobile():
+    """The MobileNet TDRN pair (model/ssd4scale_mobile.py; `evaluate_trn.py:537`)."""
+    from tdrn_b200.model import ssd4scale_mobile as S
+    return _tdrn(S, {}, 'MobileNet', None)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['coco512', 'mobilenet', 'tdrn']
+    which = sys.argv[1:] or ['coco512', 'mobilenet', 'tdrn', 'tdrn_mobile']
     for w in which:
         try:
             print(json.dumps({w: globals()[w]()}), flush=True)

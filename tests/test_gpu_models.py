@@ -144,9 +144,6 @@ def rows_off(out, ref, thr=TOL['bf16']):
     return float((rows > thr).mean())
 
 
-@pytest.mark.xfail(strict=False, reason='written after this round\'s GPU budget was spent: not yet run on a B200 (the '
-                   'kernels underneath are the verified ones; only the composition is new).  Non-strict, so an '
-                   'unverified test cannot mask the verified suite under -x; an XPASS is the expected outcome.')
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_tdrn_mobile_keyframe_vs_reference_golden(golden, precision):
     """MobileNet TDRN pair (model/ssd4scale_mobile.py, `evaluate_trn.py:537`): static net with ``ret_loc``, temporal
