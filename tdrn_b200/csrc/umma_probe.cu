@@ -141,6 +141,165 @@ extern "C" int tdrn_debug_umma_rate(long long *cycles_dev, int grid, int n, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Second rate probe (development): is the 73-cycle floor of narrow-N MMAs the shared-memory read of the A operand?
+//   mode 0  SS  : A and B from shared memory (the case above, repeated as the reference point of the same run)
+//   mode 1  TS  : A from tensor memory ([taddr] operand), B from shared memory
+//   mode 2  CP  : tcgen05.cp.128x256b only (one K = 16 slice of a 128-row A tile, shared -> tensor memory)
+//   mode 3  CP+TS: every MMA preceded by the tcgen05.cp of its A slice into one of two tensor-memory slots
+//   mode 4  SS, cta_group::2: M = 256 over an SM pair (cluster of two CTAs, the leader issues), N = n
+// Values are not checked (operands are constant fills); only the issue rate is read.
+// ---------------------------------------------------------------------------------------------------------
+namespace tdrn {
+namespace tc {
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t s_desc)
+{
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(s_desc) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) umma_rate2_kernel(long long *cycles, int n, int iters, int nacc)
+{
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base;                        // 24 KB, as in umma_rate_kernel
+    uint8_t *sB = base + 24 * 1024;            // 256 x 128 B
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < (24 * 1024 + 32 * 1024) / 4; e += 128) ((uint32_t *)base)[e] = 0x3c003c00u;
+    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = umma_idesc_bf16(128, n);
+        const uint64_t ad = umma_desc_sw128(smem_u32(sA));
+        const uint64_t bd = umma_desc_sw128(smem_u32(sB));
+        const uint32_t a_tm = tmem_base + 448u;           // A slots: 8 columns (16 bf16) per K = 16 slice
+        if (MODE == 1) {                                   // give the TS MMAs defined A values
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tmem_cp_128x256b(a_tm + (uint32_t)(k * 8), ad + (uint64_t)(k * 2));
+        }
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const uint32_t d = tmem_base + (uint32_t)((i % nacc) * n);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (MODE == 0) umma_bf16(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, 1u);
+                else if (MODE == 1) umma_bf16_ts(d, a_tm + (uint32_t)(k * 8), bd + (uint64_t)(k * 2), idesc, 1u);
+                else if (MODE == 2) tmem_cp_128x256b(a_tm + (uint32_t)(k * 8), ad + (uint64_t)(k * 2));
+                else {                                     // slot alternates so that cp k+1 may run under MMA k
+                    const uint32_t slot = a_tm + (uint32_t)(((i * 4 + k) & 1) * 32 + k * 8);
+                    tmem_cp_128x256b(slot, ad + (uint64_t)(k * 2));
+                    umma_bf16_ts(d, slot, bd + (uint64_t)(k * 2), idesc, 1u);
+                }
+            }
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        cycles[blockIdx.x] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// cta_group::2: both CTAs of the pair allocate, the leader (cluster rank 0) issues M = 256 MMAs whose A descriptor
+// names the 128 rows each CTA holds at the same shared-memory offset and whose B descriptor names N/2 rows per CTA;
+// the commit is multicast to the barrier of both CTAs so that the peer stays resident until the MMAs have drained.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_cg2_kernel(long long *cycles, int n, int iters, int nacc)
+{
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base;
+    uint8_t *sB = base + 16 * 1024;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t rank = cluster_ctarank();
+    for (int e = tid; e < (16 * 1024 + 32 * 1024) / 4; e += 128) ((uint32_t *)base)[e] = 0x3c003c00u;
+    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    fence_proxy_async_smem();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        long long t0 = 0;
+        if (rank == 0) {
+            const uint32_t idesc = umma_idesc_bf16(256, n);
+            const uint64_t ad = umma_desc_sw128(smem_u32(sA));
+            const uint64_t bd = umma_desc_sw128(smem_u32(sB));
+            t0 = clock64();
+            for (int i = 0; i < iters; ++i) {
+                const uint32_t d = tmem_base + (uint32_t)((i % nacc) * n);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    asm volatile("{\n\t.reg .pred p;\n\t"
+                                 "setp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(d), "l"(ad + (uint64_t)(k * 2)), "l"(bd + (uint64_t)(k * 2)), "r"(idesc), "r"(1u) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                         ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+        }
+        mbar_wait(&bar, 0);
+        if (rank == 0) cycles[blockIdx.x >> 1] = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace tc
+}  // namespace tdrn
+
+extern "C" int tdrn_debug_umma_rate2(long long *cycles_dev, int grid, int n, int iters, int nacc, int mode)
+{
+    TDRN_REQUIRE(cycles_dev && grid > 0 && n >= 16 && n <= 256 && n % 16 == 0 && nacc >= 1 && nacc * n <= 448 && mode >= 0 && mode <= 4,
+                 "umma rate2: bad argument");
+    const int smem = 24 * 1024 + 32 * 1024 + 1024;
+    if (mode == 4) {
+        TDRN_REQUIRE(grid % 2 == 0, "umma rate2: cta_group::2 needs an even grid");
+        TDRN_CUDA(cudaFuncSetAttribute(tdrn::tc::umma_rate_cg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        tdrn::tc::umma_rate_cg2_kernel<<<grid, 128, smem>>>(cycles_dev, n, iters, nacc);
+    } else {
+#define TDRN_RATE2(M)                                                                                                        \
+    case M:                                                                                                                  \
+        TDRN_CUDA(cudaFuncSetAttribute(tdrn::tc::umma_rate2_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        tdrn::tc::umma_rate2_kernel<M><<<grid, 128, smem>>>(cycles_dev, n, iters, nacc);                                  \
+        break;
+        switch (mode) { TDRN_RATE2(0) TDRN_RATE2(1) TDRN_RATE2(2) TDRN_RATE2(3) }
+#undef TDRN_RATE2
+    }
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // TMA fp32 box probe (development): load one (pw, ph, 3, 1) box of an NCHW fp32 image at (cx, cy) and copy it out.
 // ---------------------------------------------------------------------------------------------------------
 namespace tdrn {
