@@ -2,7 +2,7 @@
 instruction (clock64) and chip TFLOP/s (CUDA events) for A from shared memory (SS), A from tensor memory (TS),
 tcgen05.cp alone, cp + TS interleaved, and SS with cta_group::2 (M = 256 over an SM pair).
 
-    python scripts/umma_rate2.py [modes...]       # default: 0 1 2 3 4 (4 = cta_group::2 runs last)
+    python scripts/umma_rate2.py [modes...]       # default: 0 1 2 3 5 6 4 (4 = cta_group::2 runs last)
 """
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,9 +10,10 @@ sys.path.insert(0, ROOT)
 import torch
 from tdrn_b200 import _lib
 L = _lib.lib()
-NAMES = {0: 'SS', 1: 'TS (A in TMEM)', 2: 'cp 128x256b only', 3: 'cp + TS', 4: 'SS cta_group::2 (M=256)'}
+NAMES = {0: 'SS', 1: 'TS (A in TMEM)', 2: 'cp 128x256b only', 3: 'cp + TS', 4: 'SS cta_group::2 (M=256)',
+         5: 'SS, descs per 4 MMAs', 6: 'SS, descs per MMA'}
 grid, iters = 148, 20000
-modes = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 4]
+modes = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 5, 6, 4]
 cyc = torch.zeros(grid, dtype=torch.int64, device='cuda')
 for mode in modes:
     for n in (64, 128, 256):

@@ -147,6 +147,8 @@ extern "C" int tdrn_debug_umma_rate(long long *cycles_dev, int grid, int n, int 
 //   mode 2  CP  : tcgen05.cp.128x256b only (one K = 16 slice of a 128-row A tile, shared -> tensor memory)
 //   mode 3  CP+TS: every MMA preceded by the tcgen05.cp of its A slice into one of two tensor-memory slots
 //   mode 4  SS, cta_group::2: M = 256 over an SM pair (cluster of two CTAs, the leader issues), N = n
+//   mode 5  SS, A and B descriptors recomputed once per group of 4 MMAs (what a k-block loop does)
+//   mode 6  SS, A and B descriptors recomputed before EVERY MMA (what the nine-tap halo loop does per tap, taken further)
 // Values are not checked (operands are constant fills); only the issue rate is read.
 // ---------------------------------------------------------------------------------------------------------
 namespace tdrn {
@@ -172,9 +174,9 @@ __global__ void __launch_bounds__(128, 1) umma_rate2_kernel(long long *cycles, i
     __shared__ uint32_t tmem_base_s;
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = base;                        // 24 KB, as in umma_rate_kernel
-    uint8_t *sB = base + 24 * 1024;            // 256 x 128 B
+    uint8_t *sB = base + 24 * 1024;            // 256 x 128 B (+ 4 KB: modes 5/6 shift the B start by up to 3 KB)
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int e = tid; e < (24 * 1024 + 32 * 1024) / 4; e += 128) ((uint32_t *)base)[e] = 0x3c003c00u;
+    for (int e = tid; e < (24 * 1024 + 36 * 1024) / 4; e += 128) ((uint32_t *)base)[e] = 0x3c003c00u;
     if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     fence_proxy_async_smem();
@@ -197,6 +199,12 @@ __global__ void __launch_bounds__(128, 1) umma_rate2_kernel(long long *cycles, i
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (MODE == 0) umma_bf16(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, 1u);
+                else if (MODE == 5 || MODE == 6) {
+                    const uint32_t j = MODE == 5 ? (uint32_t)i : (uint32_t)(i * 4 + k);
+                    const uint64_t ax = umma_desc_sw128(smem_u32(sA) + (j & 7u) * 128u);      // cheap, not hoistable
+                    const uint64_t bx = umma_desc_sw128(smem_u32(sB) + ((j >> 1) & 3u) * 1024u);
+                    umma_bf16(d, ax + (uint64_t)(k * 2), bx + (uint64_t)(k * 2), idesc, 1u);
+                }
                 else if (MODE == 1) umma_bf16_ts(d, a_tm + (uint32_t)(k * 8), bd + (uint64_t)(k * 2), idesc, 1u);
                 else if (MODE == 2) tmem_cp_128x256b(a_tm + (uint32_t)(k * 8), ad + (uint64_t)(k * 2));
                 else {                                     // slot alternates so that cp k+1 may run under MMA k
@@ -279,9 +287,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_cg
 
 extern "C" int tdrn_debug_umma_rate2(long long *cycles_dev, int grid, int n, int iters, int nacc, int mode)
 {
-    TDRN_REQUIRE(cycles_dev && grid > 0 && n >= 16 && n <= 256 && n % 16 == 0 && nacc >= 1 && nacc * n <= 448 && mode >= 0 && mode <= 4,
+    TDRN_REQUIRE(cycles_dev && grid > 0 && n >= 16 && n <= 256 && n % 16 == 0 && nacc >= 1 && nacc * n <= 448 && mode >= 0 && mode <= 6,
                  "umma rate2: bad argument");
-    const int smem = 24 * 1024 + 32 * 1024 + 1024;
+    const int smem = 24 * 1024 + 36 * 1024 + 1024;
     if (mode == 4) {
         TDRN_REQUIRE(grid % 2 == 0, "umma rate2: cta_group::2 needs an even grid");
         TDRN_CUDA(cudaFuncSetAttribute(tdrn::tc::umma_rate_cg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -292,7 +300,7 @@ extern "C" int tdrn_debug_umma_rate2(long long *cycles_dev, int grid, int n, int
         TDRN_CUDA(cudaFuncSetAttribute(tdrn::tc::umma_rate2_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
         tdrn::tc::umma_rate2_kernel<M><<<grid, 128, smem>>>(cycles_dev, n, iters, nacc);                                  \
         break;
-        switch (mode) { TDRN_RATE2(0) TDRN_RATE2(1) TDRN_RATE2(2) TDRN_RATE2(3) }
+        switch (mode) { TDRN_RATE2(0) TDRN_RATE2(1) TDRN_RATE2(2) TDRN_RATE2(3) TDRN_RATE2(5) TDRN_RATE2(6) }
 #undef TDRN_RATE2
     }
     TDRN_LAUNCH_CHECK();
