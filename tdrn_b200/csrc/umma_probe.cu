@@ -285,6 +285,148 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_cg
 }  // namespace tc
 }  // namespace tdrn
 
+// ---------------------------------------------------------------------------------------------------------
+// Third rate probe (development): the MMA rate next to OTHER shared-memory traffic.  Production N = 128 layers run at
+// ~1.35x the 71-cycle floor even with their epilogue compiled out; the tensor core alone reads A 4 KB + B 4 KB per
+// instruction = 115 of the 128 B/clk of shared-memory bandwidth, so the TMA writes of the next halo box (and any staged
+// epilogue) may be what stretches them.  cta_group::2 halves the B rows each SM reads (6 KB per instruction = 86 B/clk).
+// Warps 1..bg_warps stream 16-byte-per-lane loads (bg_kind 0) or stores (1) over an 8 KB region while thread 0 issues
+// the MMAs; `gap` idle cycles between batches of 8 throttle them.  Reports MMA cycles and background bytes per CTA.
+// ---------------------------------------------------------------------------------------------------------
+namespace tdrn {
+namespace tc {
+
+template <int CG>
+__device__ __forceinline__ void umma_rate_bg_body(long long *cycles, unsigned long long *bg_bytes, int n, int iters, int bg_warps,
+                                                  int bg_kind, int gap)
+{
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int stop;
+    __shared__ unsigned long long bg_total;
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base;                        // 16 KB (128 rows)
+    uint8_t *sB = base + 16 * 1024;            // 32 KB (256 rows)
+    uint8_t *sG = base + 48 * 1024;            // 8 KB of background traffic
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    for (int e = tid; e < (56 * 1024) / 4; e += 128) ((uint32_t *)base)[e] = 0x3c003c00u;
+    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); stop = 0; bg_total = 0ull; }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();
+    if (warp == 0) {
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            tmem_alloc(&tmem_base_s, 512);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        long long t0 = 0;
+        if (rank == 0) {
+            const uint32_t idesc = umma_idesc_bf16(CG == 2 ? 256 : 128, n);
+            const uint64_t ad = umma_desc_sw128(smem_u32(sA));
+            const uint64_t bd = umma_desc_sw128(smem_u32(sB));
+            t0 = clock64();
+            for (int i = 0; i < iters; ++i) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (CG == 2)
+                        asm volatile("{\n\t.reg .pred p;\n\t"
+                                     "setp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                     ::"r"(tmem_base), "l"(ad + (uint64_t)(k * 2)), "l"(bd + (uint64_t)(k * 2)), "r"(idesc), "r"(1u) : "memory");
+                    else
+                        umma_bf16(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, 1u);
+                }
+            }
+            if (CG == 2)
+                asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                             ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+            else
+                umma_commit(&bar);
+        }
+        mbar_wait(&bar, 0);
+        if (rank == 0) cycles[CG == 2 ? blockIdx.x >> 1 : blockIdx.x] = clock64() - t0;
+        *(volatile int *)&stop = 1;
+    } else if (warp >= 1 && warp <= bg_warps) {
+        // background traffic: 8 independent 16-byte accesses per lane per batch (4 KB per warp-batch), conflict-free
+        const uint32_t a0 = smem_u32(sG) + (uint32_t)lane * 16u;
+        unsigned long long batches = 0;
+        uint32_t x = 0;
+        while (*(volatile int *)&stop == 0) {
+            if (bg_kind == 0) {
+                uint32_t r[32];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(r[4 * u]), "=r"(r[4 * u + 1]), "=r"(r[4 * u + 2]), "=r"(r[4 * u + 3]) : "r"(a0 + (uint32_t)u * 512u) : "memory");
+#pragma unroll
+                for (int u = 0; u < 32; ++u) x ^= r[u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a0 + (uint32_t)u * 512u), "r"(x) : "memory");
+                x += 1u;
+            }
+            ++batches;
+            if (gap > 0) { const long long t = clock64(); while (clock64() - t < gap) { } }
+        }
+        if (x == 0x12345678u) sG[0] = 1;           // keep the loads alive
+        if (lane == 0) atomicAdd(&bg_total, batches * 4096ull);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) bg_bytes[blockIdx.x] = bg_total;
+    if (CG == 2) cluster_sync_all();
+    if (warp == 0) {
+        tc_fence_after();
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else tmem_dealloc(tmem_base, 512);
+    }
+}
+
+__global__ void __launch_bounds__(128, 1) umma_rate_bg1_kernel(long long *cycles, unsigned long long *bg_bytes, int n, int iters,
+                                                               int bg_warps, int bg_kind, int gap)
+{
+    umma_rate_bg_body<1>(cycles, bg_bytes, n, iters, bg_warps, bg_kind, gap);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_bg2_kernel(long long *cycles, unsigned long long *bg_bytes,
+                                                                                          int n, int iters, int bg_warps, int bg_kind, int gap)
+{
+    umma_rate_bg_body<2>(cycles, bg_bytes, n, iters, bg_warps, bg_kind, gap);
+}
+
+}  // namespace tc
+}  // namespace tdrn
+
+// cycles_dev: one entry per issuing CTA (grid, or grid / 2 with cta_group 2); bg_bytes_dev: one entry per CTA.
+extern "C" int tdrn_debug_umma_rate_bg(long long *cycles_dev, unsigned long long *bg_bytes_dev, int grid, int n, int iters, int cta_group,
+                                       int bg_warps, int bg_kind, int gap)
+{
+    TDRN_REQUIRE(cycles_dev && bg_bytes_dev && grid > 0 && n >= 16 && n <= 256 && n % 16 == 0 && (cta_group == 1 || cta_group == 2) &&
+                 bg_warps >= 0 && bg_warps <= 3 && (bg_kind == 0 || bg_kind == 1) && gap >= 0, "umma rate bg: bad argument");
+    const int smem = 56 * 1024 + 1024;
+    if (cta_group == 2) {
+        TDRN_REQUIRE(grid % 2 == 0, "umma rate bg: cta_group::2 needs an even grid");
+        TDRN_CUDA(cudaFuncSetAttribute(tdrn::tc::umma_rate_bg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        tdrn::tc::umma_rate_bg2_kernel<<<grid, 128, smem>>>(cycles_dev, bg_bytes_dev, n, iters, bg_warps, bg_kind, gap);
+    } else {
+        TDRN_CUDA(cudaFuncSetAttribute(tdrn::tc::umma_rate_bg1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        tdrn::tc::umma_rate_bg1_kernel<<<grid, 128, smem>>>(cycles_dev, bg_bytes_dev, n, iters, bg_warps, bg_kind, gap);
+    }
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
 extern "C" int tdrn_debug_umma_rate2(long long *cycles_dev, int grid, int n, int iters, int nacc, int mode)
 {
     TDRN_REQUIRE(cycles_dev && grid > 0 && n >= 16 && n <= 256 && n % 16 == 0 && nacc >= 1 && nacc * n <= 448 && mode >= 0 && mode <= 6,
