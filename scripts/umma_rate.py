@@ -1,4 +1,5 @@
-"""tcgen05.mma sustained rate for narrow tiles (tdrn_debug_umma_rate): cycles per K=16 MMA (clock64) and
+"""SUPERSEDED by scripts/umma_rate_bg.py (this probe's 73-cycle rows are its own issue loop, see profiles/probe_umma_rate.txt).
+tcgen05.mma sustained rate for narrow tiles (tdrn_debug_umma_rate): cycles per K=16 MMA (clock64) and
 TFLOP/s over the whole chip (CUDA events) for N in 64/128/256, 1 or 2 accumulators, aligned or row-shifted A."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,4 +1,6 @@
-"""Where does the 73-cycle floor of narrow-N tcgen05.mma come from (tdrn_debug_umma_rate2)?  Cycles per K = 16
+"""SUPERSEDED by scripts/umma_rate_bg.py: the MMA rows of this probe are limited by its own issue loop (run-time `i % nacc`
+per group of four MMAs), not by the hardware -- see profiles/probe_umma_rate2.txt.  Original question:
+where does the 73-cycle floor of narrow-N tcgen05.mma come from (tdrn_debug_umma_rate2)?  Cycles per K = 16
 instruction (clock64) and chip TFLOP/s (CUDA events) for A from shared memory (SS), A from tensor memory (TS),
 tcgen05.cp alone, cp + TS interleaved, and SS with cta_group::2 (M = 256 over an SM pair).
 

@@ -1,9 +1,13 @@
-"""tcgen05.mma issue rate next to other shared-memory traffic (tdrn_debug_umma_rate_bg): does the shared-memory
-bandwidth the tensor core needs for its operands (A 4 KB + B N x 32 B per K = 16 instruction) explain why the N = 128
-layers run at ~1.35x the 71-cycle floor, and does cta_group::2 (each SM reads half of B) relieve it?
-Not run yet (written after the round-1 GPU budget was spent): first experiment of the next round.
+"""tcgen05.mma issue rate with the descriptors resident in uniform registers (tdrn_debug_umma_rate_bg), next to other
+shared-memory traffic, with cta_group 1 or 2, and with the row-shifted / 1280-byte-strided A views of the halo-tile kernels.
 
-    python scripts/umma_rate_bg.py
+First run (r01f, `profiles/probe_umma_rate_bg.txt`, aligned A only): 48.0 cycles per N = 64 instruction and 64.0 per N = 128
+-- the tensor core reads its operands at exactly 128 B/clk -- so the "71-73 cycle floor" of scripts/umma_rate.py /
+umma_rate2.py was their own issue loop (a run-time `i % nacc` per iteration), not the hardware.  The A-view sweep at the
+end of this script has NOT run yet: it asks whether the production halo kernels' 84 / 96-100 cycles per MMA (N = 64 / 128,
+epilogue skipped) are the shifted A views reading at half rate (4 KB at 64 B/clk + B would give 80 / 96).
+
+    python scripts/umma_rate_bg.py [views]        # "views": only the A-view sweep
 """
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,21 +18,34 @@ L = _lib.lib()
 grid, iters = 148, 20000
 cyc = torch.zeros(grid, dtype=torch.int64, device='cuda')
 bgb = torch.zeros(grid, dtype=torch.int64, device='cuda')
-for n in (64, 128, 256):
+
+
+def run(n, cg, warps=0, kind=0, gap=0, shift=0, sbo=1024):
+    cyc.zero_(); bgb.zero_()
+    for rep in range(2):
+        _lib.check(L.tdrn_debug_umma_rate_bg(ctypes.c_void_p(cyc.data_ptr()), ctypes.c_void_p(bgb.data_ptr()), grid, n, iters,
+                                             cg, warps, kind, gap, shift, sbo), 'rate_bg')
+        torch.cuda.synchronize()
+    c = cyc[:grid // cg].float().mean().item()
+    return c / (iters * 4), bgb.float().mean().item() / max(c, 1.0)
+
+
+if 'views' not in sys.argv[1:]:
+    for n in (64, 128, 256):
+        for cg in (1, 2):
+            for kind in (0, 1):
+                for warps, gap in ((0, 0), (1, 256), (1, 0), (2, 0), (3, 0)):
+                    if warps == 0 and kind == 1:
+                        continue
+                    per, bg = run(n, cg, warps, kind, gap)
+                    tc = (4096 + n * 32 // cg) / per                 # operand bytes each SM's tensor core reads per clock
+                    print('N=%3d cta_group::%d  background %s x%d warps gap %3d: %6.1f cycles per MMA  tensor-core reads %5.1f B/clk/SM  '
+                          'background %5.1f B/clk/SM' % (n, cg, ('loads ', 'stores')[kind], warps, gap, per, tc, bg), flush=True)
+
+# A views of the halo kernels: tap (r, s) of the 8 x 16 tile starts r * 10 + s rows in, 8-row groups 1280 bytes apart
+# (conv_halo_kernel); the 16 x 16 super-tile of conv_halo_stream_kernel uses an 18-pixel pitch: shift r * 18 + s, SBO 2304.
+for n in (64, 128):
     for cg in (1, 2):
-        for kind in (0, 1):
-            for warps, gap in ((0, 0), (1, 256), (1, 0), (2, 0), (3, 0)):
-                if warps == 0 and kind == 1:
-                    continue
-                cyc.zero_(); bgb.zero_()
-                for rep in range(2):
-                    _lib.check(L.tdrn_debug_umma_rate_bg(ctypes.c_void_p(cyc.data_ptr()), ctypes.c_void_p(bgb.data_ptr()), grid, n, iters,
-                                                         cg, warps, kind, gap), 'rate_bg')
-                    torch.cuda.synchronize()
-                units = grid // cg
-                c = cyc[:units].float().mean().item()
-                per = c / (iters * 4)
-                bg = bgb.float().mean().item() / max(c, 1.0)
-                tc = (4096 + n * 32 // cg) / per                 # operand bytes each SM's tensor core reads per clock
-                print('N=%3d cta_group::%d  background %s x%d warps gap %3d: %6.1f cycles per MMA  tensor-core reads %5.1f B/clk/SM  '
-                      'background %5.1f B/clk/SM' % (n, cg, ('loads ', 'stores')[kind], warps, gap, per, tc, bg), flush=True)
+        for shift, sbo in ((0, 1024), (8, 1024), (1, 1024), (11, 1024), (0, 1280), (1, 1280), (10, 1280), (22, 1280)):
+            per, _ = run(n, cg, shift=shift, sbo=sbo)
+            print('N=%3d cta_group::%d  A start +%2d rows, SBO %4d B: %6.1f cycles per MMA' % (n, cg, shift, sbo, per), flush=True)

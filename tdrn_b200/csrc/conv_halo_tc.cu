@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_c
 // conv3_1 128->256 @80^2).  A work unit is a 16 x 16 pixel super-tile (two 8 x 16 M tiles side by side, ONE 18 x 18
 // halo box, tile 1's descriptors start 8 rows further) times one 128-wide N tile: each weight k-block (16 KB)
 // fetched from L2 feeds 2 x 4 MMAs, so the L2->SM traffic per MMA is 2.5x lower than conv_tc.cu's and the main
-// loop is MMA-issue bound (73 cycles per M=128, N=128, K=16 instruction) instead of L2 bound.
+// loop is no longer L2 bound (measured r01f: ~98 cycles per M=128, N=128, K=16 instruction against a hardware cost of 64;
+// DESIGN.md section 4 lists what is suspected).
 // TMEM: 2 tiles x 128 columns, double buffered = all 512 columns.
 // Warps: 0 A-halo TMA, 1 MMA, 2-9 epilogue, 10 weight TMA.
 // ---------------------------------------------------------------------------------------------------------

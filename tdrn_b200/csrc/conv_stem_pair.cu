@@ -22,8 +22,8 @@
 // Warps: 0 patch TMA + weight TMA, 1 TMEM allocator + MMA issuer, 2-9 epilogue, 10-13 im2col builders, 14-17 mid stage.
 //
 // Measured (B200, b32, 320x320): 0.410 ms against 0.118 (conv_stem_tc) + 0.308 (conv_halo_kernel) = 0.426 ms for the two
-// kernels.  The limiter is shared-memory bandwidth: an M=128, N=64, K=16 MMA reads 6 KB of operands every 73 cycles (84 of
-// the 128 B/clk), and the LSU traffic of the builder / mid / epilogue warps competes for the rest (ncu: 45 % LSU-shared
+// kernels.  The limiter is shared-memory bandwidth: an M=128, N=64, K=16 MMA reads 6 KB of operands (48 cycles at the 128 B/clk the
+// tensor core gets from shared memory, r01f probe; "73 cycles" in earlier notes was a probe artefact), and the LSU traffic of the builder / mid / epilogue warps competes for the rest (ncu: 45 % LSU-shared
 // wavefront utilisation on top of the tensor core's reads at 0.431 ms; loading the conv1_1 bias as float4 instead of scalars
 // and a patch pitch of 20 floats -- no 2-way bank conflicts in the im2col reads -- brought 0.431 -> 0.410).  It also removes
 // 838 MB of HBM traffic per step (40 % of the step's total); whole step 2.79-2.82 vs 2.85-2.86 ms on a power-capped

@@ -6,7 +6,7 @@
 // Smem rows (128 B = 64 bf16) are filled in the layout TMA SWIZZLE_128B produces (16-byte chunk c of absolute
 // row R stored at chunk position c ^ (R & 7)); value = R (mode 0) or k (mode 1).  B = 64x64 identity, so
 // D[m][n] = A[m][n] and the output reveals the (row, column) every A element was fetched from.
-#include "tc_common.cuh"
+#include "halo_common.cuh"
 
 namespace tdrn {
 namespace tc {
@@ -141,7 +141,9 @@ extern "C" int tdrn_debug_umma_rate(long long *cycles_dev, int grid, int n, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Second rate probe (development): is the 73-cycle floor of narrow-N MMAs the shared-memory read of the A operand?
+// Second rate probe (development): is the 73-cycle cost of narrow-N MMAs the shared-memory read of the A operand?
+// (Superseded: the 71-73 cycles of this probe and of umma_rate_kernel are their own issue loops -- the run-time `i % nacc`
+// per group of four MMAs -- see umma_rate_bg below, which measures 48 / 64 / 128 cycles at N = 64 / 128 / 256.)
 //   mode 0  SS  : A and B from shared memory (the case above, repeated as the reference point of the same run)
 //   mode 1  TS  : A from tensor memory ([taddr] operand), B from shared memory
 //   mode 2  CP  : tcgen05.cp.128x256b only (one K = 16 slice of a 128-row A tile, shared -> tensor memory)
@@ -286,8 +288,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_cg
 }  // namespace tdrn
 
 // ---------------------------------------------------------------------------------------------------------
-// Third rate probe (development): the MMA rate next to OTHER shared-memory traffic.  Production N = 128 layers run at
-// ~1.35x the 71-cycle floor even with their epilogue compiled out; the tensor core alone reads A 4 KB + B 4 KB per
+// Third rate probe (development): the MMA rate with loop-invariant descriptors, next to OTHER shared-memory traffic, and
+// with the halo kernels' shifted A views.  Production N = 128 layers run at ~100 cycles per MMA even with their epilogue compiled out; the tensor core alone reads A 4 KB + B 4 KB per
 // instruction = 115 of the 128 B/clk of shared-memory bandwidth, so the TMA writes of the next halo box (and any staged
 // epilogue) may be what stretches them.  cta_group::2 halves the B rows each SM reads (6 KB per instruction = 86 B/clk).
 // Warps 1..bg_warps stream 16-byte-per-lane loads (bg_kind 0) or stores (1) over an 8 KB region while thread 0 issues
@@ -298,7 +300,7 @@ namespace tc {
 
 template <int CG>
 __device__ __forceinline__ void umma_rate_bg_body(long long *cycles, unsigned long long *bg_bytes, int n, int iters, int bg_warps,
-                                                  int bg_kind, int gap)
+                                                  int bg_kind, int gap, int a_shift_rows, int a_sbo_bytes)
 {
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t bar;
@@ -306,12 +308,12 @@ __device__ __forceinline__ void umma_rate_bg_body(long long *cycles, unsigned lo
     __shared__ int stop;
     __shared__ unsigned long long bg_total;
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    uint8_t *sA = base;                        // 16 KB (128 rows)
-    uint8_t *sB = base + 16 * 1024;            // 32 KB (256 rows)
-    uint8_t *sG = base + 48 * 1024;            // 8 KB of background traffic
+    uint8_t *sA = base;                        // 24 KB (128 rows at up to 1280 B per 8-row group + a start shift)
+    uint8_t *sB = base + 24 * 1024;            // 32 KB (256 rows)
+    uint8_t *sG = base + 56 * 1024;            // 8 KB of background traffic
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
-    for (int e = tid; e < (56 * 1024) / 4; e += 128) ((uint32_t *)base)[e] = 0x3c003c00u;
+    for (int e = tid; e < (64 * 1024) / 4; e += 128) ((uint32_t *)base)[e] = 0x3c003c00u;
     if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); stop = 0; bg_total = 0ull; }
     fence_proxy_async_smem();
     __syncthreads();
@@ -333,10 +335,11 @@ __device__ __forceinline__ void umma_rate_bg_body(long long *cycles, unsigned lo
         long long t0 = 0;
         if (rank == 0) {
             const uint32_t idesc = umma_idesc_bf16(CG == 2 ? 256 : 128, n);
-            const uint64_t ad = umma_desc_sw128(smem_u32(sA));
+            // the halo-tile kernels' A view: start shifted by whole 128-byte rows, 8-row groups a_sbo_bytes apart
+            const uint64_t ad = umma_desc_sw128_sbo(smem_u32(sA) + (uint32_t)a_shift_rows * 128u, (uint32_t)a_sbo_bytes);
             const uint64_t bd = umma_desc_sw128(smem_u32(sB));
             t0 = clock64();
-            for (int i = 0; i < iters; ++i) {
+            for (int i = 0; i < iters; ++i) {      // no per-iteration arithmetic: descriptors stay in uniform registers
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (CG == 2)
@@ -395,33 +398,38 @@ __device__ __forceinline__ void umma_rate_bg_body(long long *cycles, unsigned lo
 }
 
 __global__ void __launch_bounds__(128, 1) umma_rate_bg1_kernel(long long *cycles, unsigned long long *bg_bytes, int n, int iters,
-                                                               int bg_warps, int bg_kind, int gap)
+                                                               int bg_warps, int bg_kind, int gap, int a_shift_rows, int a_sbo_bytes)
 {
-    umma_rate_bg_body<1>(cycles, bg_bytes, n, iters, bg_warps, bg_kind, gap);
+    umma_rate_bg_body<1>(cycles, bg_bytes, n, iters, bg_warps, bg_kind, gap, a_shift_rows, a_sbo_bytes);
 }
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_bg2_kernel(long long *cycles, unsigned long long *bg_bytes,
-                                                                                          int n, int iters, int bg_warps, int bg_kind, int gap)
+                                                                                          int n, int iters, int bg_warps, int bg_kind, int gap,
+                                                                                          int a_shift_rows, int a_sbo_bytes)
 {
-    umma_rate_bg_body<2>(cycles, bg_bytes, n, iters, bg_warps, bg_kind, gap);
+    umma_rate_bg_body<2>(cycles, bg_bytes, n, iters, bg_warps, bg_kind, gap, a_shift_rows, a_sbo_bytes);
 }
 
 }  // namespace tc
 }  // namespace tdrn
 
 // cycles_dev: one entry per issuing CTA (grid, or grid / 2 with cta_group 2); bg_bytes_dev: one entry per CTA.
+// a_shift_rows / a_sbo_bytes: the A descriptor starts that many 128-byte rows into the tile and steps a_sbo_bytes between
+// 8-row groups (0 / 1024 = the aligned case; the halo kernels use shifts of r * 10 + s rows and 1280 or 2304 bytes).
 extern "C" int tdrn_debug_umma_rate_bg(long long *cycles_dev, unsigned long long *bg_bytes_dev, int grid, int n, int iters, int cta_group,
-                                       int bg_warps, int bg_kind, int gap)
+                                       int bg_warps, int bg_kind, int gap, int a_shift_rows, int a_sbo_bytes)
 {
+    TDRN_REQUIRE(a_shift_rows >= 0 && a_sbo_bytes >= 1024 && a_sbo_bytes % 16 == 0 &&
+                 a_shift_rows * 128 + 15 * a_sbo_bytes + 1024 <= 24 * 1024, "umma rate bg: A view leaves the 24 KB tile");
     TDRN_REQUIRE(cycles_dev && bg_bytes_dev && grid > 0 && n >= 16 && n <= 256 && n % 16 == 0 && (cta_group == 1 || cta_group == 2) &&
                  bg_warps >= 0 && bg_warps <= 3 && (bg_kind == 0 || bg_kind == 1) && gap >= 0, "umma rate bg: bad argument");
-    const int smem = 56 * 1024 + 1024;
+    const int smem = 64 * 1024 + 1024;
     if (cta_group == 2) {
         TDRN_REQUIRE(grid % 2 == 0, "umma rate bg: cta_group::2 needs an even grid");
         TDRN_CUDA(cudaFuncSetAttribute(tdrn::tc::umma_rate_bg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        tdrn::tc::umma_rate_bg2_kernel<<<grid, 128, smem>>>(cycles_dev, bg_bytes_dev, n, iters, bg_warps, bg_kind, gap);
+        tdrn::tc::umma_rate_bg2_kernel<<<grid, 128, smem>>>(cycles_dev, bg_bytes_dev, n, iters, bg_warps, bg_kind, gap, a_shift_rows, a_sbo_bytes);
     } else {
         TDRN_CUDA(cudaFuncSetAttribute(tdrn::tc::umma_rate_bg1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        tdrn::tc::umma_rate_bg1_kernel<<<grid, 128, smem>>>(cycles_dev, bg_bytes_dev, n, iters, bg_warps, bg_kind, gap);
+        tdrn::tc::umma_rate_bg1_kernel<<<grid, 128, smem>>>(cycles_dev, bg_bytes_dev, n, iters, bg_warps, bg_kind, gap, a_shift_rows, a_sbo_bytes);
     }
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
