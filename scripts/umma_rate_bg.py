@@ -49,3 +49,18 @@ for n in (64, 128):
         for shift, sbo in ((0, 1024), (8, 1024), (1, 1024), (11, 1024), (0, 1280), (1, 1280), (10, 1280), (22, 1280)):
             per, _ = run(n, cg, shift=shift, sbo=sbo)
             print('N=%3d cta_group::%d  A start +%2d rows, SBO %4d B: %6.1f cycles per MMA' % (n, cg, shift, sbo, per), flush=True)
+
+# The issue pattern of conv_halo_kernel (9 taps x 4 MMAs per tile, one weight block per tap, halo views of A) without TMA and
+# without an epilogue: halo views vs aligned views, with and without the TMEM double-buffer handshake (tdrn_debug_umma_rate_halo).
+tiles = 2000
+for n in (64, 128):
+    for aligned in (0, 1):
+        for handshake in (0, 1):
+            cyc.zero_()
+            for rep in range(2):
+                _lib.check(L.tdrn_debug_umma_rate_halo(ctypes.c_void_p(cyc.data_ptr()), grid, n, tiles, aligned, handshake), 'rate_halo')
+                torch.cuda.synchronize()
+            per = cyc.float().mean().item() / (tiles * 36)
+            print('halo pattern N=%3d  %s A views, %s: %6.1f cycles per MMA' %
+                  (n, ('halo (shifted, SBO 1280)', 'aligned (SBO 1024)      ')[aligned],
+                   ('no handshake        ', 'TMEM double-buffer handshake')[handshake], per), flush=True)

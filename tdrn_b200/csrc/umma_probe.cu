@@ -435,6 +435,96 @@ extern "C" int tdrn_debug_umma_rate_bg(long long *cycles_dev, unsigned long long
     return TDRN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fourth rate probe (development): the issue pattern of conv_halo_kernel without TMA and without an epilogue.
+// Per "tile": nine taps x four K = 16 MMAs; tap (r, s) reads the A tile through the halo view (start (r * 10 + s) rows in,
+// 8-row groups 1280 bytes apart) or, with `aligned`, through the nearest 1024-byte-aligned view with SBO 1024 (different
+// data, same volume); every tap has its own n x 128-byte weight block, as the resident-weight kernel has.
+// handshake = 1 adds the production kernel's TMEM double-buffer protocol (tcgen05.commit per tile to t_full, a consumer warp
+// that waits for it and arrives on t_empty, the issuer waiting for t_empty before it re-uses an accumulator).
+// Answers: does the pattern itself reach 48 / 64 cycles per MMA, and if not, is it the views or the protocol?
+// ---------------------------------------------------------------------------------------------------------
+namespace tdrn {
+namespace tc {
+
+__global__ void __launch_bounds__(128, 1) umma_rate_halo_kernel(long long *cycles, int n, int tiles, int aligned, int handshake)
+{
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t t_full[2], t_empty[2], done_bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    const uint32_t w_bytes = 9u * (uint32_t)n * 128u;
+    uint8_t *sW = base;
+    uint8_t *sA = base + w_bytes;                       // two halo tiles, HL_A_STRIDE apart
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (uint32_t e = tid; e < (w_bytes + 2u * HL_A_STRIDE) / 4u; e += 128) ((uint32_t *)base)[e] = 0x3c003c00u;
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], 1); }
+        mbar_init(&done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = umma_idesc_bf16(128, n);
+        const uint32_t sW_u = smem_u32(sW), sA_u = smem_u32(sA);
+        const uint32_t kb_bytes = (uint32_t)n * 128u;
+        const long long t0 = clock64();
+        for (int tile = 0; tile < tiles; ++tile) {
+            const uint32_t buf = (uint32_t)tile & 1u;
+            if (handshake) { mbar_wait(&t_empty[buf], (((uint32_t)tile >> 1) & 1u) ^ 1u); tc_fence_after(); }
+            const uint32_t d_tmem = tmem_base + buf * (uint32_t)n;
+            const uint32_t a0 = sA_u + buf * (uint32_t)HL_A_STRIDE;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int tr = tap / 3, ts = tap - tr * 3;
+                const uint32_t row = (uint32_t)(tr * HL_PW + ts);
+                const uint64_t adesc = aligned ? umma_desc_sw128_sbo(a0 + (row & ~7u) * 128u, 1024u)
+                                               : umma_desc_sw128_sbo(a0 + row * 128u, HL_PW * 128u);
+                const uint64_t bdesc = umma_desc_sw128(sW_u + (uint32_t)tap * kb_bytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (tap | k) != 0);
+            }
+            if (handshake) umma_commit(&t_full[buf]);
+        }
+        umma_commit(&done_bar);
+        mbar_wait(&done_bar, 0);
+        cycles[blockIdx.x] = clock64() - t0;
+    } else if (warp == 1 && handshake) {
+        // stands in for the epilogue: wait for the accumulator, hand it back at once
+        for (int tile = 0; tile < tiles; ++tile) {
+            const uint32_t buf = (uint32_t)tile & 1u;
+            mbar_wait(&t_full[buf], ((uint32_t)tile >> 1) & 1u);
+            tc_fence_after();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace tc
+}  // namespace tdrn
+
+extern "C" int tdrn_debug_umma_rate_halo(long long *cycles_dev, int grid, int n, int tiles, int aligned, int handshake)
+{
+    TDRN_REQUIRE(cycles_dev && grid > 0 && (n == 64 || n == 128) && tiles > 0, "umma rate halo: bad argument");
+    const int smem = 9 * n * 128 + 2 * tdrn::tc::HL_A_STRIDE + 1024;
+    TDRN_CUDA(cudaFuncSetAttribute(tdrn::tc::umma_rate_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tdrn::tc::umma_rate_halo_kernel<<<grid, 128, smem>>>(cycles_dev, n, tiles, aligned ? 1 : 0, handshake ? 1 : 0);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
 extern "C" int tdrn_debug_umma_rate2(long long *cycles_dev, int grid, int n, int iters, int nacc, int mode)
 {
     TDRN_REQUIRE(cycles_dev && grid > 0 && n >= 16 && n <= 256 && n % 16 == 0 && nacc >= 1 && nacc * n <= 448 && mode >= 0 && mode <= 6,
