@@ -39,7 +39,8 @@ path.  Pins used instead:
     zero + im2col + SGEMM and is restated in oracle/ref_native.deform_conv_forward.
   * NMS: the reference's GPU kernel utils/nms/nms_kernel.cu (`_nms`) is compiled and run the same
     way (IoU +1 convention, bitmask reduction); the Cython CPU variant that Detect actually calls
-    (cpu_nms.pyx, suppress at ovr >= thresh instead of >) cannot be built under Cython 3 /
-    NumPy 2 -- for that one comparison operator the status is "parity unpinned"; it is restated
-    line by line and cross-checked against the importable utils/nms/py_cpu_nms.py.
+    (cpu_nms.pyx, suppress at ovr >= thresh instead of >) is built by oracle/build_ref_nms.py from a
+    temporary copy with two removed NumPy dtype names respelled (np.int_t / np.int -> np.intp_t /
+    np.intp) and nothing else changed; the restatements are compared with it in
+    tests/test_ref_cython_nms.py and the reference's Detect runs with it in oracle/ref_shim.py.
 """

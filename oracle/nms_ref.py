@@ -9,8 +9,9 @@ NumPy's introsort.  Both this oracle and the CUDA kernel use "descending score, 
 original index first", i.e. ``np.argsort(-scores, kind='stable')``.  For distinct scores this is
 identical to the reference.
 
-Parity status: *unpinned* against the compiled Cython module (it does not build under
-Cython 3 / NumPy 2 / Python 3.12); cross-checked in tests against the reference's importable
+Parity status: pinned against the reference's own compiled Cython module (oracle/build_ref_nms.py builds
+cpu_nms.pyx through a two-token dtype respelling; tests/test_ref_cython_nms.py compares keep lists, the
+pair-exactly-on-the-threshold case included) and cross-checked against the reference's importable
 utils/nms/py_cpu_nms.py (identical except at ovr == thresh exactly).
 """
 import numpy as np

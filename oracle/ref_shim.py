@@ -7,7 +7,8 @@ absent) and by oracle/make_golden.py to generate tests/golden/*.npz.
 
 Nothing is copied: the reference files are executed where they lie.  Six shims are needed to
 run 2018 PyTorch-0.4 code under torch 2.x on CPU:
-  1. utils.nms.cpu_nms      -> oracle.nms_ref.cpu_nms (Cython source does not build)
+  1. utils.nms.cpu_nms      -> the reference's own cpu_nms.pyx built by oracle/build_ref_nms.py (two dtype tokens
+                               respelled for NumPy 2); oracle.nms_ref.cpu_nms only if that build is impossible
   2. utils.nms.gpu_nms      -> stub (needs a GPU; not on the Detect path)
   3. utils._ext.deform_conv -> stub module (import at model/networks.py:8)
   4. torch.cuda.FloatTensor -> CPU fp32 tensor factory (default arg at detection.py:25)
@@ -45,7 +46,14 @@ def load():
             raise RuntimeError('module %r already imported from elsewhere' % name)
 
     m = types.ModuleType('utils.nms.cpu_nms')
-    m.cpu_nms = lambda dets, thresh: nms_ref.cpu_nms(dets, thresh)
+    real = None
+    try:                                                # the reference's own Cython NMS, when oracle/build_ref_nms.py built it
+        from . import build_ref_nms
+        build_ref_nms.build()
+        real = build_ref_nms.load()
+    except Exception:                                   # no Cython / no compiler: fall back to the restatement
+        real = None
+    m.cpu_nms = real.cpu_nms if real is not None else (lambda dets, thresh: nms_ref.cpu_nms(dets, thresh))
     m.cpu_soft_nms = None
     sys.modules['utils.nms.cpu_nms'] = m
     m = types.ModuleType('utils.nms.gpu_nms')
@@ -82,6 +90,7 @@ def load():
         ns.L2Norm = ns.layers.L2Norm
         ns.py_cpu_nms = importlib.import_module('utils.nms.py_cpu_nms').py_cpu_nms
         ns.nms_wrapper = importlib.import_module('utils.nms_wrapper')
+        ns.cpu_nms_is_reference_build = real is not None
     finally:
         sys.path.remove(REFERENCE_ROOT)
     _loaded = ns

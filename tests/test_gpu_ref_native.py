@@ -9,7 +9,8 @@ oracle/build_ref.py into oracle/_ref/libtdrn_ref_native.so (built in the contain
     non-zero pattern of the border rules (.cu:195-203, :25-37) must match exactly.
   * deformable conv forward: product tdrn_deform_conv_forward (fp32) vs reference im2col + fp32 GEMM, 1e-4.
   * NMS: reference GPU `_nms` (suppress when IoU > thresh) vs product tdrn_nms (IoU >= thresh, the CPU rule
-    Detect uses): identical keep lists whenever no pair sits exactly on the threshold.
+    Detect uses): identical keep lists whenever no pair sits exactly on the threshold; and product tdrn_nms vs the
+    reference's own compiled Cython cpu_nms (oracle/build_ref_nms.py), pair exactly on the threshold included.
 """
 import numpy as np
 import pytest
@@ -92,6 +93,21 @@ def test_product_nms_matches_reference_gpu_kernel(n, thresh):
     got = nms(dets, thresh)
     ora = nms_ref.cpu_nms(dets, thresh)
     assert [int(i) for i in ref] == [int(i) for i in got] == [int(i) for i in ora]
+
+
+@pytest.mark.parametrize('n,thresh', [(1, 0.45), (2, 0.45), (257, 0.3), (1000, 0.45), (3000, 0.6), (6375, 0.45)])
+def test_product_nms_matches_reference_cython_nms(n, thresh):
+    """tdrn_nms (through utils.nms_wrapper.nms) == the reference's own compiled cpu_nms.pyx -- the function Detect calls --
+    built by oracle/build_ref_nms.py; includes a pair exactly on the threshold (`>=` suppresses, cpu_nms.pyx:65)."""
+    from oracle import build_ref_nms
+    mod = build_ref_nms.load()
+    if mod is None:
+        pytest.skip('oracle/_ref/cpu_nms*.so not built (needs /root/reference + Cython)')
+    from tdrn_b200.utils.nms_wrapper import nms
+    dets = _boxes(n, 100 + n)
+    assert [int(i) for i in nms(dets, thresh)] == [int(i) for i in mod.cpu_nms(dets, thresh)]
+    edge = np.array([[0, 0, 9, 9, 0.9], [0, 0, 9, 19, 0.8], [100, 100, 120, 130, 0.7]], np.float32)   # IoU(0, 1) == 0.5
+    assert [int(i) for i in nms(edge, 0.5)] == [int(i) for i in mod.cpu_nms(edge, 0.5)] == [0, 2]
 
 
 def test_deform_head_vs_the_reference_kernels_speed_and_values():

@@ -53,3 +53,34 @@ def test_reference_state_dict_keys_are_the_spec():
         got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
         exp = {n: tuple(s) for n, s, _ in spec}
         assert got == exp, type(net).__name__
+
+
+@pytest.mark.parametrize('seed,P,C,top_k,conf_t,nms_t,use_arm,bias', [
+    (11, 6375, 21, 200, 0.01, 0.45, True, 4.0),     # trained-like scores on the VOC_320 priors (the canonical thresholds)
+    (12, 6375, 21, 50, 0.05, 0.30, False, 4.0),     # no ARM stage, other thresholds
+    (13, 700, 6, 200, 0.01, 0.45, True, 0.0),       # every prior of every class is a candidate (random-init regime)
+    (14, 300, 4, 20, 0.01, 0.45, True, 0.0),        # top_k smaller than the kept list: the early exit of the product
+])
+def test_detect_restatements_follow_the_reference_live(seed, P, C, top_k, conf_t, nms_t, use_arm, bias):
+    """The reference's own Detect.forward (detection.py:25-70, run live) == the Python restatement == the C restatement,
+    bit for bit, on inputs no fixture holds."""
+    import torch
+    from oracle import detect_ref as D, c_oracle as Cc
+    ns = ref_shim.load()
+    g = torch.Generator().manual_seed(seed)
+    pri = ns.PriorBox(D.VOC_320).forward()
+    if P != pri.shape[0]:
+        pri = pri[torch.randperm(pri.shape[0], generator=g)[:P]].contiguous()
+    B = 2
+    loc = torch.randn(B, P, 4, generator=g)
+    arm = torch.randn(B, P, 4, generator=g) * 0.5 if use_arm else None
+    logits = torch.randn(B * P, C, generator=g) * 2
+    logits[:, 0] += bias
+    conf = torch.softmax(logits, 1)
+    ref = ns.Detect(C, 0, top_k, conf_t, nms_t).forward(loc, conf, pri, arm_loc_data=arm).numpy()
+    got = D.detect(loc, conf, pri, arm, None, C, top_k, conf_t, nms_t).numpy()
+    assert np.array_equal(got, ref)
+    boxes = torch.stack([D.decode_two_stage(loc[i], pri, arm[i] if use_arm else None) for i in range(B)]).numpy()
+    got_c = Cc.detect(boxes, conf.numpy(), np.array([320.] * 4, np.float32), C, top_k, conf_t, nms_t)
+    assert np.array_equal(got_c, ref)
+    assert (ref[:, 1:, :, 0] > 0).any()
