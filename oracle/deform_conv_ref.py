@@ -14,9 +14,10 @@ Semantics that differ from torchvision.ops.deform_conv2d:
   * when floor(h) >= H-1 the row is clamped to H-1 with lh = 0 (.cu:25-30), same for w (.cu:32-37),
     i.e. points in [H-1, H) replicate the last row/column.
 
-Parity status for this function: *unpinned* against the native CUDA build (it cannot be
-compiled or run here); cross-checked in tests against F.conv2d (zero offsets), torchvision
-(interior points) and the scalar C restatement in oracle/c/oracle.c.
+Parity status for this function: pinned on the GPU box against the reference's OWN CUDA kernel file, compiled
+unmodified by oracle/build_ref.py and run in tests/test_gpu_ref_native.py (im2col columns within 4 ulp -- the
+reference is built with -fmad=true -- and identical zero patterns for the border rules); on CPU it is cross-checked
+against F.conv2d (zero offsets), torchvision (interior points) and the scalar C restatement in oracle/c/oracle.c.
 """
 import torch
 

@@ -4,13 +4,16 @@
     img[:, :, (2, 1, 0)] + permute(2,0,1)  reference data/voc0712.py:466-468 (dataset drivers),
                                            test_video_trn.py:89-91 (video: no channel swap)
 
-PARITY UNPINNED: `cv2.resize` lives in OpenCV, a third-party dependency of the reference that is not pinned by it
-(README: "OpenCV") and is not installed in this image, and the reference ships no fixture for this step.  The resize
-below restates OpenCV's published 8-bit INTER_LINEAR algorithm (modules/imgproc/src/resize.cpp of OpenCV 3.x / 4.x:
-`resizeGeneric_` coefficient set-up, `HResizeLinear<uchar,int,short,2048>`, `VResizeLinear<uchar,int,short,
-FixedPtCast<int,uchar,22>>`; the IPP path is not taken for 8-bit linear unless IPP "not exact" mode is enabled).
-Cross-checks available here (tests/test_oracle.py): identity when sizes match, exact 2x2 box average at scale 2, and
-agreement within one grey level with torch's float bilinear interpolation (same half-pixel coordinate mapping).
+Parity: PINNED against real OpenCV.  `cv2.resize` lives in OpenCV, a third-party dependency the reference does not pin
+(README: "OpenCV"); this image carries OpenCV 4.13.0, and the restatement is bit-identical to it: the reference's own
+`base_transform` source executed with that cv2 produced tests/golden/base_transform.npz (oracle/make_golden_preprocess.py),
+and tests/test_preprocess.py also compares live with cv2.resize (twelve shapes incl. 1x1 and 5x300 sources, up- and
+down-scaling, flipped) wherever cv2 imports.  The resize below restates OpenCV's 8-bit INTER_LINEAR algorithm
+(modules/imgproc/src/resize.cpp of OpenCV 3.x / 4.x: `resizeGeneric_` coefficient set-up,
+`HResizeLinear<uchar,int,short,2048>`, `VResizeLinear<uchar,int,short, FixedPtCast<int,uchar,22>>`) -- integer
+arithmetic, so the result does not depend on the CPU or on SIMD dispatch.
+Further cross-checks (tests/test_preprocess.py): identity when sizes match, exact 2x2 box average at scale 2, and agreement
+within one grey level with torch's float bilinear interpolation (same half-pixel coordinate mapping).
 """
 import numpy as np
 

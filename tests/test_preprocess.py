@@ -1,7 +1,8 @@
 """Pre-processing in front of the hot path: the restated cv2 fixed-point resize / base_transform
 (oracle/preprocess_ref.py) against independent cross-checks on CPU, and tdrn_preprocess against it on the GPU.
-cv2 is not installed here and the reference ships no fixture for this step: the oracle's parity is unpinned (see its
-header); what IS pinned is that the kernel and the restatement agree bit for bit."""
+The reference ships no fixture for this step and pins no OpenCV version; the pin is the reference's own `base_transform`
+source executed with the OpenCV of this image (4.13.0): tests/golden/base_transform.npz (oracle/make_golden_preprocess.py),
+plus live comparisons with cv2 where it is importable.  The kernel and the restatement agree bit for bit."""
 import numpy as np
 import pytest
 import torch
@@ -65,6 +66,57 @@ def test_base_transform_and_layout():
     y = P.network_input(frames, 32, MEAN, to_rgb=False)
     assert np.array_equal(y[1, 0], r[:, :, 0] - 104)
 
+
+def _golden_cases(golden):
+    g = golden('base_transform')
+    mean = g['mean']
+    i = 0
+    while 'in_%d' % i in g.files:
+        yield g['in_%d' % i], g['res_%d' % i].astype(np.float32) - mean, mean
+        i += 1
+
+
+def test_restatement_matches_the_reference_base_transform_golden(golden):
+    """oracle/preprocess_ref.base_transform == the reference's base_transform (data/__init__.py:7-12) run with real cv2."""
+    n = 0
+    for img, ref, mean in _golden_cases(golden):
+        got = P.base_transform(img, ref.shape[0], mean)
+        assert got.dtype == np.float32 and np.array_equal(got, ref)
+        n += 1
+    assert n == 8
+
+
+@pytest.mark.parametrize('h,w,size', [(480, 640, 320), (375, 500, 320), (240, 352, 512), (333, 77, 320), (1080, 1920, 320),
+                                      (320, 320, 320), (100, 100, 704), (720, 1280, 192), (321, 319, 320), (1, 1, 8), (5, 300, 17)])
+def test_restatement_matches_cv2_live(h, w, size):
+    """Bit-exact against cv2.resize (default INTER_LINEAR) of whatever OpenCV is installed; skipped where there is none."""
+    cv2 = pytest.importorskip('cv2')
+    img = _frames(1, max(h, 16), max(w, 16), 3 * h + w)[0, :h, :w].copy()
+    assert np.array_equal(P.cv2_resize_linear_u8(img, size), cv2.resize(img, (size, size)).reshape(size, size, 3))
+    flipped = cv2.flip(img, 1).reshape(img.shape)                     # multi_eval.py:541-544
+    assert np.array_equal(P.cv2_resize_linear_u8(img[:, ::-1], size), cv2.resize(flipped, (size, size)).reshape(size, size, 3))
+
+
+def test_reference_base_transform_source_live():
+    """Build container only: the reference's own function source + cv2 vs the restatement, on frames no fixture holds."""
+    import os
+    pytest.importorskip('cv2')
+    from oracle import make_golden_preprocess as G
+    if not os.path.exists(G.REF):
+        pytest.skip('reference checkout not present (GPU box)')
+    fn = G.reference_base_transform()
+    for seed, (h, w, size) in enumerate([(480, 640, 320), (375, 500, 512), (300, 300, 300)]):
+        img = _frames(1, h, w, 70 + seed)[0]
+        assert np.array_equal(fn(img.copy(), size, np.array(MEAN, dtype=np.float32)), P.base_transform(img, size, MEAN))
+
+
+@pytest.mark.gpu
+def test_preprocess_kernel_matches_the_reference_base_transform_golden(golden):
+    """tdrn_preprocess == the reference's base_transform run with real cv2 (committed fixture), bit for bit."""
+    from tdrn_b200.data import base_transform
+    for img, ref, mean in _golden_cases(golden):
+        got = base_transform(img, ref.shape[0], tuple(float(m) for m in mean))
+        assert got.shape == ref.shape and got.dtype == np.float32 and np.array_equal(got, ref)
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('flip', [False, True])
