@@ -13,7 +13,9 @@ Everything is NumPy float32 arithmetic exactly as the reference performs it (the
 Pin status: `bbox_vote` is PINNED against the reference's own function -- oracle/make_golden_vote.py executes the source of
 multi_eval.py:453-494 (extracted with `ast`; the module cannot be imported) on seeded detections and stores its outputs in
 tests/golden/bbox_vote.npz; restatement and device kernel reproduce them bit for bit.  The gathering loop (:557-640) is
-inline in `test_net` and cannot be run in isolation: restated only.
+inline in `test_net`; tests/test_oracle_vs_reference.py executes the source of the WHOLE `test_net` (with real cv2, the
+reference's PriorBox / Detect / Cython NMS and a stand-in network) at base size 512 and `multi_scale_merge` reproduces every
+voted box of every class and image bit for bit (build container only).
 Pinned where the reference leaves the order open: detections are visited by descending score, ties -> lower index
 (`argsort()[::-1]` of an unstable sort in the reference).
 

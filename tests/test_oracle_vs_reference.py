@@ -84,3 +84,115 @@ def test_detect_restatements_follow_the_reference_live(seed, P, C, top_k, conf_t
     got_c = Cc.detect(boxes, conf.numpy(), np.array([320.] * 4, np.float32), C, top_k, conf_t, nms_t)
     assert np.array_equal(got_c, ref)
     assert (ref[:, 1:, :, 0] > 0).any()
+
+
+def _reference_functions(path, names, ns):
+    """Execute the named top-level function definitions of a reference file (which cannot be imported as a module:
+    multi_eval.py parses the command line and opens datasets at import time) in the namespace `ns`."""
+    import ast
+    tree = ast.parse(open(path).read())
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert sorted(f.name for f in fns) == sorted(names)
+    exec(compile(ast.Module(fns, []), path, 'exec'), ns)
+    return ns
+
+
+@pytest.mark.filterwarnings('ignore::DeprecationWarning')         # np.row_stack inside the reference's bbox_vote
+def test_multi_scale_merge_follows_the_reference_test_net_live(tmp_path):
+    """The reference's own `test_net` (multi_eval.py:496-655: multi-scale PriorBoxes, base_transform + cv2.flip per pass,
+    Detect per pass, per-class gather with un-flip / pixel scaling / size rules, bbox_vote) executed from its source at base
+    size 512 (scales 320, 512, 640, 1216 x {plain, flipped}) with real cv2, the reference's PriorBox / Detect / Cython NMS and
+    a stand-in network, against oracle/multi_scale_ref.multi_scale_merge fed with the same Detect outputs: every voted box
+    of every class of every image, bit for bit.  (Base size 320 cannot be pinned this way: the reference's size-rule table
+    names '320_706' where its scale list says 704, and its loop then pairs boxes with a stale index array.)"""
+    import ast
+    import os
+    import pickle
+    import types
+    import torch
+    cv2 = pytest.importorskip('cv2')
+    from oracle import multi_scale_ref as MS, make_golden_preprocess as GP
+    ns_ref = ref_shim.load()
+    REF = os.path.join(ref_shim.REFERENCE_ROOT, 'multi_eval.py')
+    cfg = {}
+    for node in ast.parse(open(os.path.join(ref_shim.REFERENCE_ROOT, 'data', 'config.py')).read()).body:
+        if isinstance(node, ast.Assign) and isinstance(node.value, ast.Dict):
+            try:
+                exec(compile(ast.Module([node], []), 'config.py', 'exec'), cfg)
+            except NameError:
+                pass
+    C, TOP_K, N_IMG = 3, 25, 12                      # test_net's FPS line divides by the time of images 11.. : needs > 11 images
+    rng = np.random.RandomState(5)
+    images = [np.clip(rng.randn(60 + 7 * i, 90 + 5 * i, 3) * 40 + 120, 0, 255).astype(np.uint8) for i in range(N_IMG)]
+
+    class Dataset(object):
+        def __len__(self):
+            return N_IMG
+
+        def pull_image(self, i):
+            return images[i]
+
+    class Timer(object):
+        def tic(self):
+            self.t = 0.0
+
+        def toc(self, average=True):
+            return 1.0
+
+    calls = {'n': 0}
+
+    def net(x):                                      # stand-in network: seeded outputs of the right shape for this scale
+        s = x.shape[-1]
+        P = 3 * sum(((s // st) + (1 if s % st else 0)) ** 2 for st in (8, 16, 32, 64))
+        g = torch.Generator().manual_seed(1000 + calls['n'])
+        calls['n'] += 1
+        loc = torch.randn(1, P, 4, generator=g) * 0.5
+        arm = torch.randn(1, P, 4, generator=g) * 0.3
+        logits = torch.randn(P, C, generator=g) * 2
+        logits[:, 0] += 8.5
+        return arm, None, loc, torch.softmax(logits, 1)
+
+    recorded = []
+    ref_detect = ns_ref.Detect(C, 0, TOP_K, 0.01, 0.45)
+
+    class Detector(object):
+        def forward(self, loc, conf, priors, arm_loc_data=None):
+            assert priors.shape[0] == loc.shape[1], (priors.shape, loc.shape)
+            out = ref_detect.forward(loc, conf, priors, arm_loc_data=arm_loc_data)
+            recorded.append(out.clone().numpy())
+            return out
+
+    captured = {}
+
+    def get_output_dir(name, phase):
+        d = os.path.join(str(tmp_path), str(abs(hash((name, phase)))))
+        os.makedirs(d, exist_ok=True)
+        return d
+
+    ns = {'np': np, 'torch': torch, 'os': os, 'cv2': cv2, 'pickle': pickle, 'labelmap': ('a', 'b'), 'Timer': Timer,
+          'get_output_dir': get_output_dir, 'pkl_dir': str(tmp_path), 'device': torch.device('cpu'),
+          'args': types.SimpleNamespace(iteration='0', dataset_name='x', set_file_name='y', backbone='RefineDet_VGG', refine=True),
+          'multi_scale': {'320': [192, 320, 384, 448, 512, 576, 704], '512': [320, 512, 640, 1216]},
+          'multi_cfg': cfg['multi_cfg_512'], 'ssd_dim': 512, 'PriorBox': ns_ref.PriorBox,
+          'base_transform': GP.reference_base_transform(), 'dataset_mean': (104, 117, 123),
+          'evaluate_detections': lambda all_boxes, output_dir, dataset, FPS=None: captured.update(all_boxes=all_boxes),
+          'print': lambda *a, **k: None}
+    _reference_functions(REF, ['test_net', 'bbox_vote'], ns)
+    ns['test_net'](str(tmp_path), net, Dataset(), None, TOP_K, Detector(), None)
+    all_boxes = captured['all_boxes']
+    assert len(recorded) == N_IMG * 8
+    n_rows = 0
+    for i in range(N_IMG):
+        h, w, _ = images[i].shape
+        passes = [(scale, flip, recorded[i * 8 + k * 2 + flip][0]) for k, scale in enumerate([320, 512, 640, 1216]) for flip in (0, 1)]
+        mine = MS.multi_scale_merge(passes, C, w, h, 512)
+        for j in range(1, C):
+            ref = all_boxes[j][i]
+            if isinstance(ref, list) and not ref:
+                assert mine[j].shape[0] == 0
+                continue
+            assert np.asarray(ref).dtype == np.float32 or np.asarray(ref).dtype == np.float64
+            assert mine[j].shape == np.asarray(ref).shape, (i, j)
+            assert np.array_equal(mine[j].astype(np.float64), np.asarray(ref, dtype=np.float64)), (i, j)
+            n_rows += mine[j].shape[0]
+    assert n_rows > 30                               # the comparison is not vacuous
