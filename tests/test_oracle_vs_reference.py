@@ -196,3 +196,130 @@ def test_multi_scale_merge_follows_the_reference_test_net_live(tmp_path):
             assert np.array_equal(mine[j].astype(np.float64), np.asarray(ref, dtype=np.float64)), (i, j)
             n_rows += mine[j].shape[0]
     assert n_rows > 30                               # the comparison is not vacuous
+
+
+def test_tdrn_stream_and_result_scatter_follow_the_reference_test_net_live(tmp_path):
+    """The reference's own video evaluation loop (evaluate_trn.py `test_net`, :416-516) executed from its source -- key-frame
+    scheduling per video and per `interval`, the in-place `loose` scaling of the static regression, the offset cache
+    (`ref_loc` consumed once, `offset_list` re-used until the next key frame), Detect with the static net's regression as ARM
+    stage, and the per-class result scatter -- against the PRODUCT's host logic tdrn_b200.utils.tdrn_stream.TDRNStream (pure
+    Python: it runs here on CPU tensors with stand-in networks) and oracle.eval_ref.all_boxes_ref: the same calls with the
+    same arguments in the same order, the same detections, the same all_boxes, bit for bit."""
+    import os
+    import pickle
+    import types
+    import torch
+    from oracle import eval_ref
+    from tdrn_b200.utils.tdrn_stream import TDRNStream
+    ns_ref = ref_shim.load()
+    REF = os.path.join(ref_shim.REFERENCE_ROOT, 'evaluate_trn.py')
+    C, TOP_K, P, INTERVAL, LOOSE = 4, 30, 300, 4, 0.5
+    videos = ['vidA'] * 9 + ['vidB'] * 6                       # 15 frames (> 11: the FPS lines), key frames 0,4,8 | 9,13
+    sizes = [(320 + 3 * i, 240 + 2 * i) for i in range(len(videos))]           # (w, h)
+    g0 = torch.Generator().manual_seed(3)
+    pri = ns_ref.PriorBox(dict(feature_maps=[10], min_dim=320, steps=[32], min_sizes=[64], max_sizes=[], aspect_ratios=[[2]],
+                               variance=[0.1, 0.2], clip=True, flip=True, name='test')).forward()
+    assert pri.shape[0] == P
+
+    def frame_tensor(i):
+        return torch.full((3, 8, 8), float(i))
+
+    def seeded(i, salt, *shape):
+        return torch.randn(*shape, generator=torch.Generator().manual_seed(10000 * salt + i))
+
+    def make_fakes(log):
+        def static_net(x, ret_loc=False):
+            i = int(x[0, 0, 0, 0])
+            log.append(('static', i, bool(ret_loc)))
+            out = [seeded(i, 1, 1, P, 4) * 0.4, torch.softmax(seeded(i, 2, P, C), 1)]
+            if ret_loc:
+                out.append([seeded(i, 3, 1, 12, 10, 10), seeded(i, 4, 1, 12, 5, 5)])
+            return tuple(out)
+
+        def net(x, ref_loc=list(), offset_list=list(), ret_loc=False, ret_off=False):
+            i = int(x[0, 0, 0, 0])
+            log.append(('net', i, [float(t.sum()) for t in ref_loc], [float(t.sum()) for t in offset_list], bool(ret_off)))
+            logits = seeded(i, 5, P, C) * 2
+            logits[:, 0] += 3.0
+            out = [seeded(i, 6, 1, P, 4) * 0.5, torch.softmax(logits, 1)]
+            if ret_off:
+                out.append([seeded(i, 7, 1, 144, 10, 10), seeded(i, 8, 1, 144, 5, 5)])
+            return tuple(out)
+        return static_net, net
+
+    class Dataset(object):
+        def __len__(self):
+            return len(videos)
+
+        def pull_transformed_image(self, i):
+            return frame_tensor(i), sizes[i][1], sizes[i][0]     # im, h, w
+
+        def pull_img_id(self, i):
+            return ('root', '%s/%06d' % (videos[i], i))
+
+    class Timer(object):
+        def tic(self):
+            pass
+
+        def toc(self, average=True):
+            return 1.0
+
+    class RecordingDetect(object):
+        def __init__(self, log):
+            self.det, self.log, self.outs = ns_ref.Detect(C, 0, TOP_K, 0.01, 0.45), log, []
+
+        def forward(self, loc, conf, priors, arm_loc_data=None):
+            self.log.append(('detect', float(loc.sum()), float(arm_loc_data.sum())))
+            out = self.det.forward(loc, conf, priors, arm_loc_data=arm_loc_data)
+            self.outs.append(out.clone())
+            return out
+
+    # --- the reference loop, from its own source
+    ref_log, captured = [], {}
+    s_net, t_net = make_fakes(ref_log)
+    ref_detect = RecordingDetect(ref_log)
+
+    def get_output_dir(name, phase):
+        d = os.path.join(str(tmp_path), 'out')
+        os.makedirs(d, exist_ok=True)
+        return d
+
+    import numpy
+    ns = {'np': numpy, 'torch': torch, 'os': os, 'pickle': pickle, 'labelmap': ('a', 'b', 'c'), 'Timer': Timer,
+          'get_output_dir': get_output_dir, 'pkl_dir': str(tmp_path), 'device': torch.device('cpu'), 'iteration': '0',
+          'args': types.SimpleNamespace(dataset_name='x', set_file_name='y', interval=INTERVAL, display=False, deform=True,
+                                        loose=LOOSE),
+          'evaluate_detections': lambda all_boxes, output_dir, dataset, FPS=None: captured.update(all_boxes=all_boxes),
+          'print': lambda *a, **k: None}
+    _reference_functions(REF, ['test_net'], ns)
+    ns['test_net'](str(tmp_path), t_net, Dataset(), ref_detect, pri, static_net=s_net)
+
+    # --- the product's host logic on the same stand-ins
+    my_log = []
+    s_net2, t_net2 = make_fakes(my_log)
+    my_detect = RecordingDetect(my_log)
+    stream = TDRNStream(s_net2, t_net2, my_detect, pri, interval=INTERVAL, loose=LOOSE, deform=True)
+    ds = Dataset()
+    mine = []
+    for i in range(len(videos)):
+        im, h, w = ds.pull_transformed_image(i)
+        mine.append(stream.step(im.unsqueeze(0), ds.pull_img_id(i)[1].split('/')[0]).clone())
+
+    assert my_log == ref_log
+    assert [e[1] for e in ref_log if e[0] == 'static'] == [0, 4, 8, 9, 13]          # key frames: per video, every `interval`
+    assert len(ref_detect.outs) == len(mine) == len(videos)
+    for a, b in zip(ref_detect.outs, mine):
+        assert torch.equal(a, b)
+    # result scatter (the same lines in evaluate.py:469-483 and evaluate_coco.py:140-159)
+    ref_boxes = captured['all_boxes']
+    mine_boxes = eval_ref.all_boxes_ref(torch.cat(mine, 0), sizes)
+    n = 0
+    for j in range(1, C):
+        for i in range(len(videos)):
+            r, m = ref_boxes[j][i], mine_boxes[j][i]
+            if isinstance(r, list) and not r:
+                assert isinstance(m, list) and not m
+                continue
+            assert np.asarray(r).dtype == np.float32 and np.array_equal(np.asarray(r), np.asarray(m)), (j, i)
+            n += len(r)
+    assert n > 100
