@@ -43,4 +43,9 @@ path.  Pins used instead:
     temporary copy with two removed NumPy dtype names respelled (np.int_t / np.int -> np.intp_t /
     np.intp) and nothing else changed; the restatements are compared with it in
     tests/test_ref_cython_nms.py and the reference's Detect runs with it in oracle/ref_shim.py.
+  * Pre-processing: the reference's own base_transform source executed with the real cv2 of this image
+    (oracle/make_golden_preprocess.py -> tests/golden/base_transform.npz) + live cv2.resize comparisons.
+  * Drivers around the path (multi-scale merge, TDRN video loop, result scatter): the reference's own
+    `test_net` functions of multi_eval.py / evaluate_trn.py executed from their source with stand-in
+    networks (tests/test_oracle_vs_reference.py, build container only).
 """
