@@ -15,12 +15,14 @@ relative to the upstream reference checkout):
 * ``detect_ref``       -- restatement of layers/functions/detection.py:25-70 and
   layers/box_utils.py:16-25,176-195, layers/functions/prior_box.py:33-64
 * ``model_ref``        -- functional PyTorch restatement of model/dualrefinedet_vggbn.py,
-  model/dualrefinedet_mobilenet.py, model/refinedet_vgg.py, model/ssd4scale_vgg.py
+  model/dualrefinedet_mobilenet.py, model/refinedet_vgg.py, model/ssd4scale_vgg.py, model/ssd4scale_mobile.py
 * ``preprocess_ref``   -- restatement of data/__init__.py:7-12 (base_transform) incl. OpenCV's 8-bit INTER_LINEAR
-  fixed-point resize (PARITY UNPINNED: OpenCV is not in this image; see the module header)
-* ``eval_ref``         -- restatement of the result scatter of evaluate.py:469-483
+  fixed-point resize (pinned against the OpenCV 4.13.0 of this image; see the module header)
+* ``eval_ref``         -- restatement of the result scatter of evaluate.py:469-483 (pinned against evaluate_trn.py's
+  test_net run from its source)
 * ``multi_scale_ref``  -- NumPy restatement of the multi-scale merge + bbox_vote (multi_eval.py:453-494,557-640);
-  bbox_vote pinned by ``make_golden_vote`` (runs the reference's own function source)
+  bbox_vote pinned by ``make_golden_vote`` (runs the reference's own function source), the whole merge by running
+  multi_eval.py's test_net from its source (tests/test_oracle_vs_reference.py)
 * ``c/oracle.c``       -- plain-C restatement of the sampler, im2col+GEMM, decode and NMS
   (built into ``oracle/_build/liboracle.so`` by ``oracle/build.py``)
 * ``ref_shim``         -- imports the *real* reference Python in place from /root/reference
