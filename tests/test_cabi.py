@@ -125,3 +125,18 @@ def test_level_sizes_and_prior_count():
     from tdrn_b200.model._engine import level_sizes
     assert level_sizes(320) == [40, 20, 10, 5] and level_sizes(512) == [64, 32, 16, 8]
     assert 3 * sum(s * s for s in level_sizes(320)) == 6375
+
+
+def test_integration_md_python_stubs_are_valid_python_and_name_real_exports():
+    """Every ```python block of INTEGRATION.md compiles, and every tdrn_* symbol it binds is exported by the library."""
+    src = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    blocks = re.findall(r"```python\n(.*?)```", src, re.S)
+    assert len(blocks) >= 5
+    from tdrn_b200 import _lib
+    L = _lib.lib()
+    for code in blocks:
+        compile(code, 'INTEGRATION.md', 'exec')
+        for sym in set(re.findall(r'_L\.(tdrn_[a-z0-9_]+)', code)):
+            assert hasattr(L, sym), sym
+    # pointers are never passed as bare integers (ctypes would truncate them to a C int)
+    assert '.ctypes.data,' not in src and '.ctypes.data)' not in src
