@@ -216,7 +216,6 @@ def test_tdrn_stream_and_result_scatter_follow_the_reference_test_net_live(tmp_p
     C, TOP_K, P, INTERVAL, LOOSE = 4, 30, 300, 4, 0.5
     videos = ['vidA'] * 9 + ['vidB'] * 6                       # 15 frames (> 11: the FPS lines), key frames 0,4,8 | 9,13
     sizes = [(320 + 3 * i, 240 + 2 * i) for i in range(len(videos))]           # (w, h)
-    g0 = torch.Generator().manual_seed(3)
     pri = ns_ref.PriorBox(dict(feature_maps=[10], min_dim=320, steps=[32], min_sizes=[64], max_sizes=[], aspect_ratios=[[2]],
                                variance=[0.1, 0.2], clip=True, flip=True, name='test')).forward()
     assert pri.shape[0] == P
