@@ -41,12 +41,13 @@ long long tdrn_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * A5  PriorBox.forward        layers/functions/prior_box.py:33-64  (host, float64 -> fp32)
- * ars is [n_levels][4] (unused entries ignored), n_ar[k] = len(aspect_ratios[k]);
+ * ars is [n_levels][4] (unused entries ignored), n_ar[k] = len(aspect_ratios[k]); sizes and aspect ratios are doubles:
+ * the reference takes any Python number (SSD-512's min_sizes are 35.84, 76.8, ...; MOT_300's aspect ratios 0.5, 1/3, 0.25);
  * max_sizes_host may be NULL (cfg['max_sizes'] == []).  out_host may be NULL to query *num_priors.
  * ------------------------------------------------------------------------------------------ */
 int tdrn_prior_box(int image_size, int n_levels, const int *feature_maps_host, const int *steps_host,
-                   const int *min_sizes_host, const int *max_sizes_host, const int *n_ar_host,
-                   const int *ars_host, int flip, int clip, float *out_host, int *num_priors);
+                   const double *min_sizes_host, const double *max_sizes_host, const int *n_ar_host,
+                   const double *ars_host, int flip, int clip, float *out_host, int *num_priors);
 
 /* ------------------------------------------------------------------------------------------
  * A3  deform_conv_forward_cuda   utils/deformconv/deform_conv_cuda.h:1-7, deform_conv_cuda.c:98-213

@@ -220,8 +220,8 @@ int oracle_detect(const float *boxes, const float *conf, const float *scale, int
 /* ---- PriorBox: prior_box.py:33-64 (float64 arithmetic, one fp32 conversion, clamp) -----------
  * Boxes per cell: [s,s], (if n_max) [sqrt(s*s'),..], per ar: [s*sqrt(ar), s/sqrt(ar)], flip.  Returns P. */
 int oracle_prior_box(int image_size, int n_levels, const int *feature_maps, const int *steps,
-                     const int *min_sizes, const int *max_sizes /* or NULL */,
-                     const int *n_ar, const int *ars /* [n_levels][4] */, int flip, int clip, float *out)
+                     const double *min_sizes, const double *max_sizes /* or NULL */,
+                     const int *n_ar, const double *ars /* [n_levels][4] */, int flip, int clip, float *out)
 {
     int n = 0;
     for (int k = 0; k < n_levels; ++k) {
@@ -230,15 +230,15 @@ int oracle_prior_box(int image_size, int n_levels, const int *feature_maps, cons
             for (int j = 0; j < f; ++j) {
                 double f_k = (double)image_size / steps[k];
                 double cx = (j + 0.5) / f_k, cy = (i + 0.5) / f_k;
-                double s_k = (double)min_sizes[k] / image_size;
+                double s_k = min_sizes[k] / image_size;
                 double b[16][2]; int nb = 0;
                 b[nb][0] = s_k; b[nb][1] = s_k; nb++;
                 if (max_sizes) {
-                    double sp = sqrt(s_k * ((double)max_sizes[k] / image_size));
+                    double sp = sqrt(s_k * (max_sizes[k] / image_size));
                     b[nb][0] = sp; b[nb][1] = sp; nb++;
                 }
                 for (int a = 0; a < n_ar[k]; ++a) {
-                    double r = sqrt((double)ars[k * 4 + a]);
+                    double r = sqrt(ars[k * 4 + a]);
                     b[nb][0] = s_k * r; b[nb][1] = s_k / r; nb++;
                     if (flip) { b[nb][0] = s_k / r; b[nb][1] = s_k * r; nb++; }
                 }

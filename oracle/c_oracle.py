@@ -81,13 +81,14 @@ def detect(boxes, conf, scale, num_classes, top_k, conf_thresh, nms_thresh):
 def prior_box(cfg):
     n = len(cfg['feature_maps'])
     ia = lambda v: (ctypes.c_int * len(v))(*v)
+    da = lambda v: (ctypes.c_double * len(v))(*[float(t) for t in v])
     ars = []
     for a in cfg['aspect_ratios']:
         ars += list(a) + [0] * (4 - len(a))
     n_ar = [len(a) for a in cfg['aspect_ratios']]
-    mx = ia(cfg['max_sizes']) if len(cfg['max_sizes']) else None
-    args = (cfg['min_dim'], n, ia(cfg['feature_maps']), ia(cfg['steps']), ia(cfg['min_sizes']), mx,
-            ia(n_ar), ia(ars), int(bool(cfg['flip'])), int(bool(cfg['clip'])))
+    mx = da(cfg['max_sizes']) if len(cfg['max_sizes']) else None
+    args = (cfg['min_dim'], n, ia(cfg['feature_maps']), ia(cfg['steps']), da(cfg['min_sizes']), mx,
+            ia(n_ar), da(ars), int(bool(cfg['flip'])), int(bool(cfg['clip'])))
     p = lib().oracle_prior_box(*args, None)
     out = np.empty((p, 4), np.float32)
     lib().oracle_prior_box(*args, _fp(out))

@@ -32,7 +32,7 @@ extern "C" long long tdrn_launch_count(void) { return g_launches.load(std::memor
 // (IEEE double) and converts the whole list to fp32 once (torch.Tensor(mean), :61), then clamps
 // (:62-63).  Same operations, same order, in C double -> bit-identical fp32 output.
 extern "C" int tdrn_prior_box(int image_size, int n_levels, const int *feature_maps, const int *steps,
-                              const int *min_sizes, const int *max_sizes, const int *n_ar, const int *ars,
+                              const double *min_sizes, const double *max_sizes, const int *n_ar, const double *ars,
                               int flip, int clip, float *out, int *num_priors)
 {
     TDRN_REQUIRE(image_size > 0 && n_levels > 0 && feature_maps && steps && min_sizes && n_ar && ars && num_priors,
@@ -42,16 +42,16 @@ extern "C" int tdrn_prior_box(int image_size, int n_levels, const int *feature_m
         TDRN_REQUIRE(feature_maps[k] > 0 && steps[k] > 0 && n_ar[k] >= 0 && n_ar[k] <= 4, "tdrn_prior_box: bad level %d", k);
         const int f = feature_maps[k];
         const double f_k = (double)image_size / (double)steps[k];           // :39
-        const double s_k = (double)min_sizes[k] / (double)image_size;       // :46
+        const double s_k = min_sizes[k] / (double)image_size;               // :46
         double bw[10], bh[10];
         int nb = 0;
         bw[nb] = s_k; bh[nb] = s_k; ++nb;                                   // :47
         if (max_sizes) {                                                    // :51-53
-            const double sp = sqrt(s_k * ((double)max_sizes[k] / (double)image_size));
+            const double sp = sqrt(s_k * (max_sizes[k] / (double)image_size));
             bw[nb] = sp; bh[nb] = sp; ++nb;
         }
         for (int a = 0; a < n_ar[k]; ++a) {                                 // :56-59
-            const double r = sqrt((double)ars[k * 4 + a]);
+            const double r = sqrt(ars[k * 4 + a]);
             bw[nb] = s_k * r; bh[nb] = s_k / r; ++nb;
             if (flip) { bw[nb] = s_k / r; bh[nb] = s_k * r; ++nb; }
         }

@@ -12,7 +12,33 @@ VOC_512_RefineDet = {
     'variance': [0.1, 0.2], 'clip': True, 'flip': True, 'name': 'VOC_512_RefineDet',
 }
 
-mb_cfg = {'VOC_320': VOC_320, 'VOC_512_RefineDet': VOC_512_RefineDet}
+
+def _ssd_prior_cfg(name, size, min_sizes, max_sizes, aspect_ratios, flip=True):
+    """The SSD / RFB-style dictionaries of data/config.py:5-55,83-137 (six levels at 300, seven at 512, with max_sizes)."""
+    n = len(min_sizes)
+    steps = [8, 16, 32, 64, 100, 300] if size == 300 else [8, 16, 32, 64, 128, 256, 512]
+    fmaps = [38, 19, 10, 5, 3, 1] if size == 300 else [64, 32, 16, 8, 4, 2, 1]
+    assert n == len(steps) == len(max_sizes) == len(aspect_ratios)
+    return {'feature_maps': fmaps, 'min_dim': size, 'steps': steps, 'min_sizes': min_sizes, 'max_sizes': max_sizes,
+            'aspect_ratios': aspect_ratios, 'variance': [0.1, 0.2], 'clip': True, 'flip': flip, 'name': name}
+
+
+_S300 = ([30, 60, 111, 162, 213, 264], [60, 111, 162, 213, 264, 315])
+VOC_300 = _ssd_prior_cfg('VOC_300', 300, *_S300, [[2], [2, 3], [2, 3], [2, 3], [2], [2]])
+VOC_300_RFB = _ssd_prior_cfg('VOC_300_RFB', 300, *_S300, [[2, 3], [2, 3], [2, 3], [2, 3], [2], [2]])
+MOT_300 = _ssd_prior_cfg('MOT_300', 300, *_S300, [[1 / 2, 1 / 3, 1 / 4]] * 6, flip=False)
+COCO_300 = _ssd_prior_cfg('COCO_300', 300, [21, 45, 99, 153, 207, 261], [45, 99, 153, 207, 261, 315],
+                          [[2, 3], [2, 3], [2, 3], [2, 3], [2], [2]])
+_AR512 = [[2, 3], [2, 3], [2, 3], [2, 3], [2, 3], [2], [2]]
+VOC_512 = _ssd_prior_cfg('VOC_512', 512, [35.84, 76.8, 153.6, 230.4, 307.2, 384.0, 460.8],
+                         [76.8, 153.6, 230.4, 307.2, 384.0, 460.8, 537.6], _AR512)
+COCO_512 = _ssd_prior_cfg('COCO_512', 512, [20.48, 51.2, 133.12, 215.04, 296.96, 378.88, 460.8],
+                          [51.2, 133.12, 215.04, 296.96, 378.88, 460.8, 542.72], _AR512)
+
+# data/config.py:257-258: every dictionary the reference's `mb_cfg` holds (the hot-path models use VOC_320 and
+# VOC_512_RefineDet; the SSD / RFB entries are here so that `from data import mb_cfg` keeps working unchanged)
+mb_cfg = {'VOC_300': VOC_300, 'VOC_300_RFB': VOC_300_RFB, 'VOC_320': VOC_320, 'VOC_512': VOC_512, 'MOT_300': MOT_300,
+          'COCO_300': COCO_300, 'COCO_512': COCO_512, 'VOC_512_RefineDet': VOC_512_RefineDet}
 
 
 def _refinedet_prior_cfg(size, name):

@@ -472,17 +472,21 @@ def prior_box(cfg):
     """PriorBox.forward via the C ABI (host) -> CPU fp32 tensor [P,4]."""
     n = len(cfg['feature_maps'])
     ia = lambda v: (ctypes.c_int * len(v))(*[int(t) for t in v])
+    da = lambda v: (ctypes.c_double * len(v))(*[float(t) for t in v])       # sizes / ratios may be fractional (SSD-512, MOT_300)
+    for name in ('feature_maps', 'steps'):
+        if any(int(t) != t for t in cfg[name]):
+            raise ValueError('%s must be integers' % name)
     ars, n_ar = [], []
     for a in cfg['aspect_ratios']:
         if len(a) > 4:
             raise ValueError('at most 4 aspect ratios per level are supported')
-        ars += [int(t) for t in a] + [0] * (4 - len(a))
+        ars += [float(t) for t in a] + [0.0] * (4 - len(a))
         n_ar.append(len(a))
-    mx = ia(cfg['max_sizes']) if len(cfg['max_sizes']) else None
+    mx = da(cfg['max_sizes']) if len(cfg['max_sizes']) else None
     num = ctypes.c_int(0)
     L = _lib.lib()
-    args = (int(cfg['min_dim']), n, ia(cfg['feature_maps']), ia(cfg['steps']), ia(cfg['min_sizes']), mx, ia(n_ar),
-            ia(ars), int(bool(cfg['flip'])), int(bool(cfg['clip'])))
+    args = (int(cfg['min_dim']), n, ia(cfg['feature_maps']), ia(cfg['steps']), da(cfg['min_sizes']), mx, ia(n_ar),
+            da(ars), int(bool(cfg['flip'])), int(bool(cfg['clip'])))
     check(L.tdrn_prior_box(*args, None, ctypes.byref(num)), 'tdrn_prior_box')
     out = torch.empty(num.value, 4, dtype=torch.float32)
     check(L.tdrn_prior_box(*args, ptr(out), ctypes.byref(num)), 'tdrn_prior_box')

@@ -41,6 +41,20 @@ def test_prior_box_cabi_bit_exact(golden):
         PriorBox(cfg)
 
 
+def test_prior_box_every_mb_cfg_entry_matches_oracle():
+    """All eight dictionaries of mb_cfg (fractional min_sizes: VOC_512 / COCO_512; fractional aspect ratios, flip off:
+    MOT_300) through tdrn_prior_box vs the Python restatement (itself pinned live against the reference's PriorBox)."""
+    from oracle import detect_ref as D
+    from tdrn_b200.layers.functions import PriorBox
+    from tdrn_b200.data import mb_cfg
+    want = {'VOC_300': 8732, 'VOC_300_RFB': 11620, 'VOC_320': 6375, 'VOC_512': 32756, 'MOT_300': 9700, 'COCO_300': 11620,
+            'COCO_512': 32756, 'VOC_512_RefineDet': 16320}
+    assert set(mb_cfg) == set(want)
+    for name, cfg in mb_cfg.items():
+        got = PriorBox(cfg).forward().numpy()
+        assert got.shape == (want[name], 4) and np.array_equal(got, D.prior_box(cfg).numpy()), name
+
+
 def test_prior_box_with_max_sizes_matches_oracle():
     from oracle import detect_ref as D
     from tdrn_b200.layers.functions import PriorBox

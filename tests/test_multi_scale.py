@@ -175,3 +175,4 @@ def test_multi_scale_prior_dicts_equal_the_reference_values():
     assert ns['multi_cfg'] == C.multi_cfg and ns['multi_cfg_512'] == C.multi_cfg_512
     assert ns['multi_scale'] == C.multi_scale
     assert ns['VOC_320'] == C.VOC_320 and ns['VOC_512_RefineDet'] == C.VOC_512_RefineDet
+    assert ns['mb_cfg'] == C.mb_cfg and list(ns['mb_cfg']) == list(C.mb_cfg)      # data/config.py:257-258, every entry

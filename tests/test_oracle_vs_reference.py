@@ -322,3 +322,28 @@ def test_tdrn_stream_and_result_scatter_follow_the_reference_test_net_live(tmp_p
             assert np.asarray(r).dtype == np.float32 and np.array_equal(np.asarray(r), np.asarray(m)), (j, i)
             n += len(r)
     assert n > 100
+
+
+def test_prior_box_product_and_oracles_equal_the_reference_for_every_config():
+    """Every prior-box dictionary of the reference's data/config.py (SSD-300/512 with max_sizes and fractional min_sizes,
+    MOT_300 with fractional aspect ratios and flip off, the RefineDet and multi-scale ones) through the reference's own
+    PriorBox.forward vs the product's host entry point tdrn_prior_box and both oracle restatements: bit-exact."""
+    import ast
+    import os
+    from oracle import detect_ref as D, c_oracle as Cc
+    from tdrn_b200.layers.functions import PriorBox
+    ns = ref_shim.load()
+    cfg = {}
+    for node in ast.parse(open(os.path.join(ref_shim.REFERENCE_ROOT, 'data', 'config.py')).read()).body:
+        if isinstance(node, ast.Assign) and isinstance(node.value, ast.Dict):
+            try:
+                exec(compile(ast.Module([node], []), 'config.py', 'exec'), cfg)
+            except NameError:
+                pass
+    names = [k for k, c in cfg.items() if isinstance(c, dict) and 'feature_maps' in c]
+    assert len(names) >= 17
+    for name in names:
+        ref = ns.PriorBox(cfg[name]).forward().numpy()
+        assert np.array_equal(PriorBox(cfg[name]).forward().numpy(), ref), name
+        assert np.array_equal(D.prior_box(cfg[name]).numpy(), ref), name
+        assert np.array_equal(Cc.prior_box(cfg[name]), ref), name
