@@ -347,3 +347,42 @@ def test_prior_box_product_and_oracles_equal_the_reference_for_every_config():
         assert np.array_equal(PriorBox(cfg[name]).forward().numpy(), ref), name
         assert np.array_equal(D.prior_box(cfg[name]).numpy(), ref), name
         assert np.array_equal(Cc.prior_box(cfg[name]), ref), name
+
+
+def test_public_signatures_equal_the_reference():
+    """Parameter names, order, kinds and defaults of the drop-in surface against the reference's own definitions
+    (inspect.signature on both): build_net / __init__ / forward of the five detector modules, Detect, PriorBox, nms,
+    ConvOffset2d, conv_dw, vgg.  Allowed differences: the `_offsets` test hook appended to the two DualRefineDet forwards, and
+    Detect.forward's `scale` default (None here, resolved to the reference's [320, 320, 320, 320] at call time)."""
+    import importlib
+    import inspect
+    ns = ref_shim.load()
+    from tdrn_b200.layers.functions import Detect, PriorBox
+    from tdrn_b200.model import networks as N
+    from tdrn_b200.utils.nms_wrapper import nms
+    pairs = []
+    for refmod, mine in (('drn_vgg', 'dualrefinedet_vggbn'), ('drn_mobilenet', 'dualrefinedet_mobilenet'),
+                         ('refinedet_vgg', 'refinedet_vgg'), ('ssd4scale_vgg', 'ssd4scale_vgg'), ('ssd4scale_mobile', 'ssd4scale_mobile')):
+        r, m = getattr(ns, refmod), importlib.import_module('tdrn_b200.model.' + mine)
+        pairs.append((mine + '.build_net', r.build_net, m.build_net))
+        for c in [c for c in vars(r).values() if inspect.isclass(c) and c.__module__ == r.__name__]:
+            cm = getattr(m, c.__name__)                              # same class name
+            pairs.append((mine + '.' + c.__name__ + '.__init__', c.__init__, cm.__init__))
+            pairs.append((mine + '.' + c.__name__ + '.forward', c.forward, cm.forward))
+    pairs += [('Detect.__init__', ns.Detect.__init__, Detect.__init__), ('Detect.forward', ns.Detect.forward, Detect.forward),
+              ('PriorBox.__init__', ns.PriorBox.__init__, PriorBox.__init__), ('PriorBox.forward', ns.PriorBox.forward, PriorBox.forward),
+              ('nms', ns.nms_wrapper.nms, nms), ('ConvOffset2d.__init__', ns.networks.ConvOffset2d.__init__, N.ConvOffset2d.__init__),
+              ('ConvOffset2d.forward', ns.networks.ConvOffset2d.forward, N.ConvOffset2d.forward),
+              ('conv_dw', ns.networks.conv_dw, N.conv_dw), ('vgg', ns.networks.vgg, N.vgg)]
+    assert len(pairs) >= 24
+    for name, a, b in pairs:
+        pa = list(inspect.signature(a).parameters.values())
+        pb = list(inspect.signature(b).parameters.values())
+        if name.endswith('RefineSSD.forward') and pb and pb[-1].name == '_offsets':
+            pb = pb[:-1]
+        assert [(p.name, p.kind) for p in pa] == [(p.name, p.kind) for p in pb], name
+        for x, y in zip(pa, pb):
+            if name == 'Detect.forward' and x.name == 'scale':
+                assert y.default is None and [float(v) for v in x.default] == [320.0] * 4
+                continue
+            assert repr(x.default) == repr(y.default), (name, x.name)
