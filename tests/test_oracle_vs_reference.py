@@ -386,3 +386,40 @@ def test_public_signatures_equal_the_reference():
                 assert y.default is None and [float(v) for v in x.default] == [320.0] * 4
                 continue
             assert repr(x.default) == repr(y.default), (name, x.name)
+
+
+def test_state_dict_surface_equals_the_reference_over_constructor_arguments():
+    """Parameter / buffer names and shapes of every detector module against the reference's own modules over a sweep of
+    constructor arguments (size, classes, c7_channel, def_groups, bn, multihead, use_refine, deform).  Names and shapes must be
+    identical; the ORDER of the FPN containers differs (the reference registers trans_layers / up_layers / latent_layers after
+    the heads, here they follow last_layer_trans) -- irrelevant to load_state_dict, which matches by name."""
+    import contextlib
+    import importlib
+    import io
+    ns = ref_shim.load()
+    combos = {
+        ('drn_vgg', 'dualrefinedet_vggbn'): [dict(size=s, num_classes=c, c7_channel=c7, def_groups=dg, bn=bn, multihead=mh)
+                                             for (s, c, c7, dg, bn, mh) in [(320, 21, 1024, 1, True, True), (512, 81, 1024, 1, True, False),
+                                                                            (320, 21, 512, 2, False, True), (512, 31, 1024, 4, False, False)]],
+        ('drn_mobilenet', 'dualrefinedet_mobilenet'): [dict(size=s, num_classes=c, def_groups=dg, multihead=mh)
+                                                       for (s, c, dg, mh) in [(320, 21, 1, False), (512, 31, 4, True)]],
+        ('refinedet_vgg', 'refinedet_vgg'): [dict(size=320, num_classes=c, use_refine=ur, c7_channel=c7, bn=bn, multihead=mh)
+                                             for (c, ur, c7, bn, mh) in [(21, True, 1024, False, False), (81, False, 1024, True, True),
+                                                                         (21, True, 512, True, True)]],
+        ('ssd4scale_vgg', 'ssd4scale_vgg'): [dict(size=320, num_classes=c, c7_channel=c7, bn=bn, deform=d)
+                                             for (c, c7, bn, d) in [(31, 1024, True, True), (31, 1024, True, False), (21, 512, False, True)]],
+        ('ssd4scale_mobile', 'ssd4scale_mobile'): [dict(size=320, num_classes=31, c7_channel=1024, deform=d) for d in (False, True)],
+    }
+    n = 0
+    for (refmod, mine), lst in combos.items():
+        r, m = getattr(ns, refmod), importlib.import_module('tdrn_b200.model.' + mine)
+        for kw in lst:
+            with contextlib.redirect_stdout(io.StringIO()):
+                a, b = r.build_net('test', **kw), m.build_net('test', **kw)
+            sa = {k: tuple(v.shape) for k, v in a.state_dict().items()}
+            sb = {k: tuple(v.shape) for k, v in b.state_dict().items()}
+            assert sa == sb, (mine, kw)
+            moved = {'trans_layers', 'up_layers', 'latent_layers'}
+            assert [k for k in sa if k.split('.')[0] not in moved] == [k for k in sb if k.split('.')[0] not in moved], (mine, kw)
+            n += 1
+    assert n == 14
