@@ -80,6 +80,10 @@ def test_detect_restatements_follow_the_reference_live(seed, P, C, top_k, conf_t
     ref = ns.Detect(C, 0, top_k, conf_t, nms_t).forward(loc, conf, pri, arm_loc_data=arm).numpy()
     got = D.detect(loc, conf, pri, arm, None, C, top_k, conf_t, nms_t).numpy()
     assert np.array_equal(got, ref)
+    # the evaluation drivers pass the image size as NMS scale (evaluate.py:463: scale=[w, h, w, h])
+    sc = torch.tensor([500., 375., 500., 375.])
+    ref_s = ns.Detect(C, 0, top_k, conf_t, nms_t).forward(loc, conf, pri, arm_loc_data=arm, scale=sc).numpy()
+    assert np.array_equal(D.detect(loc, conf, pri, arm, sc, C, top_k, conf_t, nms_t).numpy(), ref_s)
     boxes = torch.stack([D.decode_two_stage(loc[i], pri, arm[i] if use_arm else None) for i in range(B)]).numpy()
     got_c = Cc.detect(boxes, conf.numpy(), np.array([320.] * 4, np.float32), C, top_k, conf_t, nms_t)
     assert np.array_equal(got_c, ref)
