@@ -16,6 +16,16 @@
 #include "halo_common.cuh"
 #include <stdlib.h>
 
+// Compile-time experiments for the main loops (all OFF in the shipped build: the code below is then removed by the
+// preprocessor; build with e.g. TDRN_NVCC_EXTRA="-DTDRN_HALO_PREFETCH=6" python -m tdrn_b200.build --force):
+//   TDRN_HALO_PREFETCH=k   the A producer asks L2 for the halo box of the tile k grid-strides ahead (no correctness effect):
+//                          tests whether the issuer waits for HBM latency with only 2-4 stages in flight;
+//   TDRN_HALO_NO_A_LOADS   the A producer signals `a_full` without loading anything (TIMING ONLY, results are garbage):
+//                          what the loop costs when the operand is always there;
+//   TDRN_HALO_ALIGNED_A    every tap reads the nearest 1024-byte-aligned view with SBO 1024 (TIMING ONLY): do the shifted /
+//                          1280-byte-strided views of the halo tile read slower than aligned ones?
+// DESIGN.md section 4 ("What one narrow MMA really costs") says why these three.
+
 namespace tdrn {
 namespace tc {
 
@@ -64,8 +74,21 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_c
                 for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
                     const uint32_t s = it % (uint32_t)p.stages, ph = (it / (uint32_t)p.stages) & 1u;
                     mbar_wait(&a_empty[s], ph ^ 1u);
+#ifdef TDRN_HALO_NO_A_LOADS
+                    mbar_arrive(&a_full[s]);
+#else
                     mbar_expect_tx(&a_full[s], HL_A_BYTES);
                     tma_load_4d(sA + (size_t)s * HL_A_STRIDE, &tmA, &a_full[s], cb * 64, x0, y0, b);
+#endif
+#if defined(TDRN_HALO_PREFETCH) && TDRN_HALO_PREFETCH > 0
+                    {
+                        const int tp = tile + TDRN_HALO_PREFETCH * (int)gridDim.x;
+                        if (tp < p.total) {
+                            const int bp = tp / tiles_per_img, rp = tp - bp * tiles_per_img;
+                            tma_prefetch_l2_4d(&tmA, cb * 64, (rp % p.tiles_w) * HL_BW - 1, (rp / p.tiles_w) * HL_BH - 1, bp);
+                        }
+                    }
+#endif
                 }
             }
         }
@@ -91,7 +114,11 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_c
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int tr = tap / 3, ts = tap - tr * 3;
+#ifdef TDRN_HALO_ALIGNED_A
+                        const uint64_t adesc = umma_desc_sw128_sbo(a0 + ((uint32_t)(tr * HL_PW + ts) & ~7u) * 128u, 1024u);
+#else
                         const uint64_t adesc = umma_desc_sw128_sbo(a0 + (uint32_t)(tr * HL_PW + ts) * 128u, HL_PW * 128u);
+#endif
                         const uint64_t bdesc = umma_desc_sw128(sW_u + (uint32_t)(tap * p.cblocks + cb) * kb_bytes);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
@@ -201,8 +228,22 @@ __global__ void __launch_bounds__(HS_THREADS, 1) conv_halo_stream_kernel(const _
                 for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
                     const uint32_t s = it % HS_A_STAGES, ph = (it / HS_A_STAGES) & 1u;
                     mbar_wait(&a_empty[s], ph ^ 1u);
+#ifdef TDRN_HALO_NO_A_LOADS
+                    mbar_arrive(&a_full[s]);
+#else
                     mbar_expect_tx(&a_full[s], HS_A_BYTES);
                     tma_load_4d(sA + (size_t)s * HS_A_STRIDE, &tmA, &a_full[s], cb * 64, x0, y0, b);
+#endif
+#if defined(TDRN_HALO_PREFETCH) && TDRN_HALO_PREFETCH > 0
+                    if (cb == 0) {                                       // every channel block of the unit TDRN_HALO_PREFETCH strides ahead
+                        const int up = unit + TDRN_HALO_PREFETCH * (int)gridDim.x;
+                        if (up < total) {
+                            const int mp = up % m_units, bp = mp / units_per_img, rp = mp - bp * units_per_img;
+                            for (int c = 0; c < p.cblocks; ++c)
+                                tma_prefetch_l2_4d(&tmA, c * 64, (rp % pairs_w) * (2 * HL_BW) - 1, (rp / pairs_w) * HL_BH - 1, bp);
+                        }
+                    }
+#endif
                 }
             }
         }

@@ -79,6 +79,12 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *m, int c0,
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)m), "r"(c0), "r"(c1) : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap *m, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"((uint64_t)m), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // B-operand box delivered to the same shared-memory offset of every CTA in `mask` (thread-block cluster); each
 // destination CTA's mbarrier at the same offset receives the complete_tx.
 __device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, uint16_t mask)
