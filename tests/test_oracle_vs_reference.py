@@ -427,3 +427,41 @@ def test_state_dict_surface_equals_the_reference_over_constructor_arguments():
             assert [k for k in sa if k.split('.')[0] not in moved] == [k for k in sb if k.split('.')[0] not in moved], (mine, kw)
             n += 1
     assert n == 14
+
+
+@pytest.mark.parametrize('mod,kw,size', [
+    ('drn_vgg', dict(num_classes=21, c7_channel=512, def_groups=2, bn=False, multihead=True), 320),
+    ('drn_vgg', dict(num_classes=31, c7_channel=1024, def_groups=4, bn=True, multihead=False), 192),
+    ('drn_mobilenet', dict(num_classes=31, def_groups=4, multihead=True), 320),
+    ('refinedet_vgg', dict(num_classes=21, use_refine=False, c7_channel=1024, bn=True, multihead=True), 320),
+    ('refinedet_vgg', dict(num_classes=81, use_refine=True, c7_channel=512, bn=False, multihead=False), 448),
+])
+def test_model_restatements_follow_the_reference_modules_beyond_the_fixtures(mod, kw, size):
+    """The functional restatements in oracle/model_ref.py (what the -m gpu tests compare the kernels with at other sizes,
+    group counts and head configurations) against the reference's own modules run live: constructor arguments and input
+    sizes no committed fixture covers (deformable groups 2 / 4, c7_channel 512, no BN, COCO-81, 192 / 448-pixel inputs)."""
+    import contextlib
+    import io
+    import torch
+    from oracle import model_ref as M
+    from oracle.make_golden import make_input
+    ns = ref_shim.load()
+    spec_fn, fwd = {'drn_vgg': (M.param_spec_drn_vgg, M.drn_vgg_forward), 'drn_mobilenet': (M.param_spec_drn_mobilenet, M.drn_mobilenet_forward),
+                    'refinedet_vgg': (M.param_spec_refinedet_vgg, M.refinedet_vgg_forward)}[mod]
+    sd = M.make_state_dict(spec_fn(**kw), 3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = getattr(ns, mod).build_net('test', 320, **kw)           # the modules are fully convolutional: any input size runs
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    x = make_input(1, size, seed=4)
+    with torch.no_grad():
+        ref = net(x)
+    out = fwd(sd, x, **kw)
+    assert len(out) == len(ref)
+    for k, (a, b) in enumerate(zip(out, ref)):
+        if b is None:                       # slot 1 of the MobileNet / RefineDet outputs (the restatement keeps the offsets there)
+            continue
+        if isinstance(b, (list, tuple)):
+            assert len(a) == len(b) and all(torch.equal(p, q) for p, q in zip(a, b)), k
+        else:
+            assert torch.equal(a, b), k
