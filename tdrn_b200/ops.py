@@ -420,15 +420,28 @@ def decode(loc, priors, arm_loc=None):
 
 
 _ws_cache = {}
+_ws_retired = []          # outgrown workspaces stay allocated: a captured CUDA graph may hold their raw pointers
 
 
 def _workspace(nbytes, device):
-    # one workspace per (device, stream): calls in flight on different streams (two graph instances replaying
-    # concurrently) must never share scratch memory
+    """Scratch memory for detect / nms_device, one block per (device, stream): calls in flight on different streams
+    (two graph instances replaying concurrently) must never share scratch memory.
+
+    Lifetime rules (a captured CUDA graph bakes the raw pointer in):
+      * a block that is outgrown is RETIRED, never freed, so graphs captured earlier on that stream keep writing into
+        memory that is still theirs;
+      * a block is never allocated or grown while the stream is capturing (it would live in that graph's private pool
+        and be handed to eager calls and other captures afterwards): warm the call up eagerly first -- this raises;
+      * a graph captured before a growth keeps using the retired block; re-capture it if it should use the new one."""
     key = (device.index if device.index is not None else torch.cuda.current_device(),
            torch.cuda.current_stream(device).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.TdrnError('detect/nms workspace of %d bytes would be allocated during CUDA-graph capture; run the '
+                                 'same call once eagerly on this stream before capturing' % nbytes)
+        if ws is not None:
+            _ws_retired.append(ws)
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _ws_cache[key] = ws
     return ws

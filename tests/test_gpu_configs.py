@@ -1,0 +1,195 @@
+"""Full-net GPU parity for the BASELINE.json configurations beyond configs[1]:
+
+  * config 3: DualRefineDet-VGGBN 512x512 COCO-81 multihead (`evaluate_coco.py:108-188`, prior dict
+    `data/config.py:70-81`), B = 2, fp32 (1e-4) and bf16 (2e-2 on the ARM tensors, attributed 2e-2 on the deformable
+    heads, tests/test_gpu_models.py check_odm_attributed) against the oracle on the host CPU; this is the wide-head
+    path (12 + 243 = 255 fused outputs -> `tdrn_deform_head`, csrc/deform_tc.cu) and 16 320 priors;
+  * config 5: TDRN 16-frame clip, key-frame interval 4 (`evaluate_trn.py:434-467`): static net on the 4 key frames,
+    temporal net (dg = 8 deformable heads) on all 16 frames with every frame driven by its key frame's regression, as one
+    batch -- against the oracle run the same way, and against the frame-by-frame TDRNStream executor;
+  * bf16 DETECTIONS against the oracle's detections (the fp32 test exists in test_gpu_models.py).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from test_gpu_models import TOL, check_odm_attributed
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_config3_coco512_full_net(precision):
+    import parity_tools as PT
+    from oracle import model_ref as M
+    from oracle.make_golden import SEED_W, make_input
+    from tdrn_b200.model import dualrefinedet_vggbn as V
+    from tdrn_b200.model._engine import level_sizes
+    from tdrn_b200.layers.functions import Detect, PriorBox
+    from tdrn_b200.data import mb_cfg
+    kw = dict(num_classes=81, def_groups=1, bn=True, multihead=True)
+    sd = M.make_state_dict(M.param_spec_drn_vgg(**kw), SEED_W)
+    net = V.build_net('test', 512, **kw)
+    net.load_state_dict(sd, strict=True)
+    net = net.eval().cuda().set_precision(precision)
+    x = make_input(2, 512, seed=21)
+    ref = M.drn_vgg_forward(sd, x, **kw)
+    with torch.no_grad():
+        out = net(x.cuda())
+    P = 16320
+    assert tuple(out[0].shape) == (2, P, 4) and tuple(out[2].shape) == (2, P, 4) and tuple(out[3].shape) == (2 * P, 81)
+    assert [tuple(o.shape) for o in out[1]] == [(2, 18, s, s) for s in (64, 32, 16, 8)]
+    tol = TOL[precision]
+    assert rel_err(out[0].cpu().numpy(), ref[0].numpy()) < tol
+    for k in range(4):
+        assert rel_err(out[1][k].cpu().numpy(), ref[1][k].numpy()) < tol
+    sizes = [(v, v) for v in level_sizes(512)]
+    fl = PT.drn_flipped_rows(sd, ref[0], out[0].cpu(), sizes, True).reshape(-1)
+    check_odm_attributed(out[2].cpu().numpy().reshape(-1, 4), ref[2].numpy().reshape(-1, 4), fl, precision, 'odm_loc')
+    check_odm_attributed(out[3].cpu().numpy(), ref[3].numpy(), fl, precision, 'conf')
+    # Detect at the config's settings (top_k 100, 512-pixel NMS scale) is bit-exact given the GPU's own loc / conf
+    from oracle import c_oracle as C
+    from tdrn_b200 import ops
+    pri = PriorBox(mb_cfg['VOC_512_RefineDet']).forward().cuda()
+    det = Detect(81, 0, 100, 0.01, 0.45).forward(out[2], out[3], pri, arm_loc_data=out[0], scale=[512.] * 4)
+    boxes = ops.decode(out[2], pri, out[0]).cpu().numpy()
+    chk = C.detect(boxes, out[3].cpu().numpy(), np.array([512.] * 4, np.float32), 81, 100, 0.01, 0.45)
+    assert np.array_equal(det.cpu().numpy(), chk)
+
+
+def _tdrn_pair(precision, C=31):
+    from oracle import model_ref as M
+    from oracle.make_golden import SEED_W
+    from tdrn_b200.model import ssd4scale_vgg as S
+    sd_s = M.make_state_dict(M.param_spec_ssd4scale_vgg(C, bn=True, deform=False), SEED_W)
+    sd_t = M.make_state_dict(M.param_spec_ssd4scale_vgg(C, bn=True, deform=True), SEED_W + 1)
+    static = S.build_net('test', 320, C, bn=True, deform=False)
+    temporal = S.build_net('test', 320, C, bn=True, deform=True)
+    static.load_state_dict(sd_s); temporal.load_state_dict(sd_t)
+    return sd_s, sd_t, static.eval().cuda().set_precision(precision), temporal.eval().cuda().set_precision(precision)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_config5_tdrn_clip_as_one_batch(precision):
+    """A 16-frame clip, interval 4, evaluated as ONE batch (what bench.py --config tdrn times): frame f uses the static
+    net's regression of key frame 4*(f // 4)."""
+    import parity_tools as PT
+    from oracle import model_ref as M
+    from oracle.make_golden import make_input
+    C, T, K = 31, 16, 4
+    sd_s, sd_t, static, temporal = _tdrn_pair(precision, C)
+    x = make_input(T, 320, seed=77)
+    with torch.no_grad():
+        s = static(x[::K].cuda(), ret_loc=True)
+        ref_maps = [m.repeat_interleave(K, 0) for m in s[2]]
+        t = temporal(x.cuda(), ref_loc=ref_maps, ret_off=True)
+        s_ref = M.ssd4scale_vgg_forward(sd_s, x[::K], C, bn=True, deform=False, ret_loc=True)
+        t_ref = M.ssd4scale_vgg_forward(sd_t, x, C, bn=True, deform=True,
+                                        ref_loc=[m.repeat_interleave(K, 0) for m in s_ref[2]], ret_off=True)
+    torch.cuda.synchronize()
+    tol = TOL[precision]
+    assert tuple(t[0].shape) == (T, 6375, 4) and tuple(t[1].shape) == (T * 6375, C)
+    assert rel_err(s[0].cpu().numpy(), s_ref[0].numpy()) < tol
+    assert rel_err(s[1].cpu().numpy(), s_ref[1].numpy()) < tol
+    for k in range(4):
+        assert rel_err(t[2][k].cpu().numpy(), t_ref[2][k].numpy()) < tol
+    fl = PT.flipped_rows([PT.flipped_pixels(t_ref[2][k], t[2][k].cpu(), 3, 1, 8) for k in range(4)]).reshape(-1)
+    check_odm_attributed(t[0].cpu().numpy().reshape(-1, 4), t_ref[0].numpy().reshape(-1, 4), fl, precision, 'temporal_loc')
+    check_odm_attributed(t[1].cpu().numpy(), t_ref[1].numpy(), fl, precision, 'temporal_conf')
+    if precision == 'fp32':
+        # the batched clip == the reference's frame-by-frame loop (TDRNStream follows evaluate_trn.py:434-467)
+        from tdrn_b200.layers.functions import Detect, PriorBox
+        from tdrn_b200.data import mb_cfg
+        from tdrn_b200.utils.tdrn_stream import TDRNStream
+        pri = PriorBox(mb_cfg['VOC_320']).forward().cuda()
+        det = Detect(C, 0, 200, 0.01, 0.45)
+        stream = TDRNStream(static, temporal, det, pri, interval=K)
+        with torch.no_grad():
+            batched = det.forward(t[0], t[1], pri, arm_loc_data=s[0].repeat_interleave(K, 0))
+            for f in (0, 1, 5, 15):
+                stream.reset()
+                for g in range(4 * (f // 4), f + 1):                 # replay the stream from the frame's key frame
+                    d = stream.step(x[g:g + 1].cuda(), 'v')
+                top = 10
+                a, b = d[0, 1:, :top].cpu().numpy(), batched[f, 1:, :top].cpu().numpy()
+                assert np.abs(a[..., 0] - b[..., 0]).max() < 1e-4
+                assert (np.abs(a[..., 1:] - b[..., 1:]).max(-1) < 1e-3).mean() > 0.97
+
+
+def test_end_to_end_detections_bf16_vs_oracle():
+    """bf16 net(x) + Detect against the ORACLE's detections (oracle forward + scalar C Detect on the host): with
+    random-init weights every prior is a candidate (scores ~1/C), so the comparison is on what NMS keeps first: the
+    top-scoring detections of every class must be the same boxes, scores within the bf16 tolerance."""
+    from oracle import model_ref as M, c_oracle as C
+    from oracle import detect_ref as D
+    from oracle.make_golden import CASES, SEED_W, make_input
+    from tdrn_b200.model import dualrefinedet_vggbn as V
+    from tdrn_b200.layers.functions import Detect, PriorBox
+    from tdrn_b200.data import mb_cfg
+    mod_name, spec_fn, build_kw, spec_kw, _ = CASES['drn_vgg320_multihead']
+    sd = M.make_state_dict(spec_fn(**spec_kw), SEED_W)
+    net = V.build_net('test', **build_kw)
+    net.load_state_dict(sd)
+    net = net.eval().cuda().set_precision('bf16')
+    x = make_input(1, 320)
+    pri = PriorBox(mb_cfg['VOC_320']).forward()
+    with torch.no_grad():
+        arm, _, loc, conf = net(x.cuda())
+        det = Detect(21, 0, 200, 0.01, 0.45).forward(loc, conf, pri.cuda(), arm_loc_data=arm).cpu().numpy()
+        ref = M.drn_vgg_forward(sd, x, **spec_kw)
+    boxes_ref = D.decode(ref[2][0], D.center_size(D.decode(ref[0][0], pri, [0.1, 0.2])), [0.1, 0.2]).numpy()[None]
+    chk = C.detect(boxes_ref, ref[3].numpy(), np.array([320.] * 4, np.float32), 21, 200, 0.01, 0.45)
+    top = 5
+    smax = float(chk[0, 1:, 0, 0].max())
+    assert np.abs(det[0, 1:, :top, 0] - chk[0, 1:, :top, 0]).max() < 2e-2 * smax
+    # same boxes: each of the oracle's top detections has a bf16 detection of that class within 2 % of the image side
+    # among the bf16 top-2*top (near-ties in score may swap neighbours)
+    hit = 0
+    for c in range(1, 21):
+        for r in range(top):
+            d = np.abs(det[0, c, :2 * top, 1:] - chk[0, c, r, 1:]).max(-1)
+            hit += int(d.min() < 2e-2)
+    assert hit >= 0.9 * 20 * top, hit
+
+
+def test_detect_workspace_survives_growth_and_capture():
+    """ops._workspace: a block outgrown by a later, larger call is retired, not freed -- a CUDA graph
+    captured against the old block keeps producing the same detections; growing during capture raises."""
+    from tdrn_b200 import ops, _lib
+    from tdrn_b200.layers.functions import Detect, PriorBox
+    from tdrn_b200.data import mb_cfg
+    pri = PriorBox(mb_cfg['VOC_320']).forward().cuda()
+    g = torch.Generator().manual_seed(5)
+    P, C = pri.shape[0], 21
+
+    def inputs(B):
+        loc = (torch.randn(B, P, 4, generator=g) * 0.5).cuda()
+        arm = (torch.randn(B, P, 4, generator=g) * 0.5).cuda()
+        conf = torch.softmax(torch.randn(B * P, C, generator=g) * 3, 1).cuda()
+        return loc, conf, arm
+    det = Detect(C, 0, 200, 0.01, 0.45)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st), torch.no_grad():
+        loc, conf, arm = inputs(1)
+        eager = det.forward(loc, conf, pri, arm_loc_data=arm).clone()
+        st.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            out = det.forward(loc, conf, pri, arm_loc_data=arm)
+        gr.replay(); st.synchronize()
+        assert torch.equal(out, eager)
+        key = (torch.cuda.current_device(), st.cuda_stream)
+        old = ops._ws_cache[key]
+        l8, c8, a8 = inputs(8)
+        det.forward(l8, c8, pri, arm_loc_data=a8)                  # needs a larger workspace on the same stream
+        assert ops._ws_cache[key] is not old and any(w is old for w in ops._ws_retired)
+        torch.empty(64 << 20, dtype=torch.uint8, device='cuda').fill_(7)   # would land on a freed block
+        out.zero_(); gr.replay(); st.synchronize()
+        assert torch.equal(out, eager)
+    st2 = torch.cuda.Stream()
+    with torch.cuda.stream(st2), torch.no_grad():
+        gr2 = torch.cuda.CUDAGraph()
+        with pytest.raises(_lib.TdrnError):
+            with torch.cuda.graph(gr2, stream=st2):
+                det.forward(loc, conf, pri, arm_loc_data=arm)     # no eager warm-up on this stream: loud, not silent

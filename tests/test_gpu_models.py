@@ -18,20 +18,30 @@ def l2_err(a, b):
 
 
 def check_odm(out, ref, precision, what, l2_tol=5e-2, row_frac=0.05):
-    """Deformable-head outputs of the END-TO-END chain.  fp32 path: max-norm relative error < 1e-4.
-    bf16 path: the 2e-2 max-norm bar is enforced with the offsets given (test_bf16_heads_with_reference_
-    offsets, test_tdrn_*: every kernel on the path, the heads included, is inside it); end to end the
-    check is relative L2 < 5e-2 with < 5 % of the rows off by more than 2e-2.  Reason: the reference's
-    sampler is DISCONTINUOUS at the map border (deform_conv_cuda_kernel.cu:195: a tap at h = -0.001
-    contributes 0, at h = +0.001 the full row-0 value), so the ~7e-3 bf16 error of the ARM regression that
-    produces the offsets flips a handful of border taps; an fp32 perturbation of the same size does the
-    same to the oracle itself (DESIGN.md "bf16 tolerance")."""
+    """LOOSE gate, kept only for the MobileNet trunks (known deviation): relative L2 and the
+    fraction of rows beyond 2e-2.  The VGG detectors use check_odm_attributed below."""
     if precision == 'fp32':
         assert rel_err(out, ref) < TOL['fp32'], what
         return
     assert l2_err(out, ref) < l2_tol, (what, l2_err(out, ref))
     rows = np.abs(np.asarray(out, np.float64) - ref).reshape(len(ref), -1).max(1) / np.abs(ref).max()
     assert (rows > TOL['bf16']).mean() < row_frac, (what, float((rows > TOL['bf16']).mean()))
+
+
+def check_odm_attributed(out, ref, flipped, precision, what):
+    """Deformable-head outputs of the END-TO-END chain.  fp32 path: max-norm relative error < 1e-4.
+    bf16 path: the north_star's 2e-2 max-norm bound on EVERY ROW WHOSE SAMPLING TAPS KEPT THEIR SIDE of the map edge, and
+    every row beyond 2e-2 must have a tap that the bf16 rounding of the ARM regression moved across the edge: the
+    reference's sampler is discontinuous there (deform_conv_cuda_kernel.cu:195: a tap at h = -0.001 contributes 0, at
+    h = +0.001 the full row-0 value).  `flipped` comes from tests/parity_tools (taps recomputed from both sides'
+    offsets).  The CPU control (tests/test_bf16_control.py) shows the oracle itself doing the same under a perturbation of
+    its ARM regression of the size the B200 shows; measured on the B200 (profiles/r02a_bf16_attribution.txt):
+    148 / 12 750 rows beyond 2e-2, all 148 with a flipped tap, 1.45e-2 max over the other rows."""
+    import parity_tools as PT
+    if precision == 'fp32':
+        assert rel_err(out, ref) < TOL['fp32'], what
+        return
+    PT.assert_attributed(out, ref, flipped, TOL['bf16'], what)
 
 
 def _build(mod_name, spec_fn, build_kw, spec_kw, precision):
@@ -69,13 +79,23 @@ def test_detector_vs_reference_golden(golden, name, precision):
     if mod_name == 'refinedet_vgg':            # plain-conv ODM heads: continuous, max-norm holds in bf16 too
         assert rel_err(odm_loc[0, ::stride].cpu().numpy(), g['odm_loc']) < tol
         assert rel_err(conf[::stride].cpu().numpy(), g['conf']) < tol
-    else:
+    elif mod_name == 'drn_mobilenet':
         # KNOWN DEVIATION: the MobileNet variant stacks 27 bf16-rounded layers (every depthwise and
         # pointwise output is stored in bf16) and lands at ~3e-2 even with exact offsets, above the 2e-2 the
         # north_star quotes; its fp32 path meets 1e-4.  The looser bound keeps the regression visible.
-        kw = dict(l2_tol=1e-1, row_frac=0.2) if mod_name == 'drn_mobilenet' else {}
+        kw = dict(l2_tol=1e-1, row_frac=0.2)
         check_odm(odm_loc[0, ::stride].cpu().numpy(), g['odm_loc'], precision, 'odm_loc', **kw)
         check_odm(conf[::stride].cpu().numpy(), g['conf'], precision, 'conf', **kw)
+    else:
+        # the golden arrays are the reference's own outputs; the ARM regression of the reference is rebuilt by the
+        # (bit-identical, tests/test_oracle.py) restatement to name the rows whose taps changed side
+        import parity_tools as PT
+        ref = M.drn_vgg_forward(sd, x.cpu(), **spec_kw)
+        assert np.array_equal(ref[0][0, ::stride].numpy(), g['arm_loc'])
+        sizes = [(s, s) for s in (40, 20, 10, 5)]
+        fl = PT.drn_flipped_rows(sd, ref[0], arm_loc.cpu(), sizes, spec_kw['multihead'])[0][::stride]
+        check_odm_attributed(odm_loc[0, ::stride].cpu().numpy(), g['odm_loc'], fl, precision, 'odm_loc')
+        check_odm_attributed(conf[::stride].cpu().numpy(), g['conf'], fl, precision, 'conf')
     if name == 'drn_vgg320_multihead':
         assert rel_err(out[1][0][0].cpu().numpy(), g['offset0']) < tol
         assert rel_err(out[1][3][0].cpu().numpy(), g['offset3']) < tol
@@ -97,8 +117,10 @@ def test_batch_consistency_and_oracle_b3(precision):
         out1 = net(x[1:2].cuda())
     tol = TOL[precision]
     assert rel_err(out[0].cpu().numpy(), ref[0].numpy()) < tol
-    check_odm(out[2].cpu().numpy().reshape(-1, 4), ref[2].numpy().reshape(-1, 4), precision, 'odm_loc')
-    check_odm(out[3].cpu().numpy(), ref[3].numpy(), precision, 'conf')
+    import parity_tools as PT
+    fl = PT.drn_flipped_rows(sd, ref[0], out[0].cpu(), [(s, s) for s in (40, 20, 10, 5)], spec_kw['multihead']).reshape(-1)
+    check_odm_attributed(out[2].cpu().numpy().reshape(-1, 4), ref[2].numpy().reshape(-1, 4), fl, precision, 'odm_loc')
+    check_odm_attributed(out[3].cpu().numpy(), ref[3].numpy(), fl, precision, 'conf')
     # frames are independent: image 1 alone == image 1 inside the batch (bit-exact, same kernels/tiles order per pixel)
     assert rel_err(out1[2][0].cpu().numpy(), out[2][1].cpu().numpy()) < 1e-6 if precision == 'fp32' else True
 
@@ -131,8 +153,12 @@ def test_tdrn_keyframe_vs_reference_golden(golden, precision):
     tol = TOL[precision]
     assert rel_err(s[0][0, ::st].cpu().numpy(), g['static_loc']) < tol
     assert rel_err(s[1][::st].cpu().numpy(), g['static_conf']) < tol
-    check_odm(t[0][0, ::st].cpu().numpy(), g['temporal_loc'], precision, 'temporal_loc')
-    check_odm(t[1][::st].cpu().numpy(), g['temporal_conf'], precision, 'temporal_conf')
+    # end to end (offsets regressed from the bf16 static net): rows whose dg = 8 taps changed side are named from the two
+    # sides' offset maps (ret_off), every other row is held to 2e-2
+    import parity_tools as PT
+    fl = PT.flipped_rows([PT.flipped_pixels(t_ref[2][k], t[2][k].cpu(), 3, 1, 8) for k in range(4)])[0][::st]
+    check_odm_attributed(t[0][0, ::st].cpu().numpy(), g['temporal_loc'], fl, precision, 'temporal_loc')
+    check_odm_attributed(t[1][::st].cpu().numpy(), g['temporal_conf'], fl, precision, 'temporal_conf')
     assert rel_err(t[2][0][0, :, ::4, ::4].cpu().numpy(), g['offset0']) < tol
     assert len(t2) == 2 and rel_err(t2[0].cpu().numpy(), t[0].cpu().numpy()) < 1e-6
 
@@ -309,5 +335,9 @@ def test_other_input_sizes_vs_oracle(size, precision):
     P = 3 * sum((size // s) ** 2 for s in (8, 16, 32, 64))
     assert tuple(out[0].shape) == (1, P, 4) and tuple(out[3].shape) == (P, 21)
     assert rel_err(out[0].cpu().numpy(), ref[0].numpy()) < TOL[precision]
-    check_odm(out[2].cpu().numpy().reshape(-1, 4), ref[2].numpy().reshape(-1, 4), precision, 'odm_loc')
-    check_odm(out[3].cpu().numpy(), ref[3].numpy(), precision, 'conf')
+    import parity_tools as PT
+    from tdrn_b200.model._engine import level_sizes
+    sizes = [(v, v) for v in level_sizes(size)]
+    fl = PT.drn_flipped_rows(sd, ref[0], out[0].cpu(), sizes, spec_kw['multihead']).reshape(-1)
+    check_odm_attributed(out[2].cpu().numpy().reshape(-1, 4), ref[2].numpy().reshape(-1, 4), fl, precision, 'odm_loc')
+    check_odm_attributed(out[3].cpu().numpy(), ref[3].numpy(), fl, precision, 'conf')
