@@ -1,23 +1,29 @@
 // postprocess.cu -- two-stage box decode, per-class candidate selection, sort, greedy NMS, top-k.
 //
 // Replaces the Python loops of Detect.forward (layers/functions/detection.py:25-70: B x (C-1)
-// device->host round trips + single-core Cython NMS, utils/nms/cpu_nms.pyx:17-68) with two kernels:
+// device->host round trips + single-core Cython NMS, utils/nms/cpu_nms.pyx:17-68) with three kernels:
 //
-//   decode_transpose_kernel : boxes[B,P,4] = decode(loc, center_size(decode(arm_loc, priors)))
-//                             (layers/box_utils.py:176-195, :16-25) and scoresT[B,C,P] (class-major
-//                             copy of conf so every (image, class) segment is one coalesced row).
-//   nms_segment_kernel      : one CTA per (image, class) segment.  Greedy NMS only ever consumes the
-//                             highest-scoring candidates until top_k boxes are kept (SURVEY.md 8a
-//                             "Exactness note for A8"), so instead of sorting all P candidates the
-//                             kernel works in descending score BATCHES:
+//   detect_front_kernel : ONE pass over [B,P,(4 + 4 + C)]: boxes[B,P,4] = decode(loc, center_size(decode(arm_loc,
+//                         priors))) (layers/box_utils.py:176-195, :16-25) and, for every (prior, class >= 1) with
+//                         score > conf_thresh (strict, detection.py:53), a 64-bit key (score bits << 32 | ~prior) appended
+//                         to the (image, class) segment's candidate list (warp-aggregated atomics).  The lists are
+//                         what everything downstream reads: no class-major copy of the scores is made.
+//   nms_warp_kernel     : segments with <= NMS_WCAP candidates (every segment of a trained detector: ~1 % of the
+//                         priors pass the threshold): one WARP per segment, four per CTA -- bitonic sort of the keys in
+//                         shared memory, greedy NMS with lane = candidate, output rows and zero fill.
+//   nms_segment_kernel  : larger segments (random-init scores: all P priors pass), one CTA per segment.  Greedy NMS
+//                         only ever consumes the highest-scoring candidates until top_k boxes are kept (SURVEY.md 8a
+//                         "Exactness note for A8"), so instead of sorting all candidates the kernel works in descending
+//                         score BATCHES:
 //       1. radix-select (12/12/8/8.. bit digits, shared-memory histograms) the cut-off such that
 //          the next <= 1024 candidates in (score desc, index asc) order are selected;
-//       2. bitonic-sort that batch on 64-bit (score, ~index) keys in shared memory;
+//       2. bitonic-sort that batch on the 64-bit keys in shared memory;
 //       3. greedy NMS in chunks of 32: 8 lanes per candidate scan the kept list, a 32x32
 //          suppression matrix resolves the chunk with warp shuffles;
 //       4. stop when top_k boxes are kept or the candidates are exhausted, else next batch.
 //     The visiting order is exactly the reference's (descending score, pinned tie rule), so the
-//     result is identical to a full sort + full scan.
+//     result is identical to a full sort + full scan.  (Both NMS kernels are launched over all segments; a segment
+//     that belongs to the other one costs an immediate exit.)
 //
 // Bit-exactness: every fp32 operation of the reference's IoU (cpu_nms.pyx:24,57-65) and of decode
 // is issued with explicit round-to-nearest intrinsics in the reference's order so that nvcc cannot
@@ -33,6 +39,8 @@ constexpr int NMS_CAP = 1024;              // candidates sorted per batch
 constexpr int NMS_KSEL = 512;              // every batch holds at least min(KSEL, remaining) candidates
 constexpr int NMS_BINS = 4096;             // histogram bins (12-bit digit)
 constexpr int NMS_CH = 32;                 // candidates per greedy chunk
+constexpr int NMS_WCAP = 512;              // largest segment nms_warp_kernel takes (one warp per segment)
+constexpr int NMS_WARPS = 4;               // segments per CTA of nms_warp_kernel
 
 __device__ __forceinline__ float4 decode_box(float4 l, float4 p)
 {
@@ -56,35 +64,68 @@ __device__ __forceinline__ float4 center_size_box(float4 b)
 
 constexpr int DEC_TP = 128;   // priors per CTA
 
-// grid (ceil(P/DEC_TP), B).  scoresT may be NULL (plain tdrn_decode).
-__global__ void __launch_bounds__(256) decode_transpose_kernel(const float4 *__restrict__ loc, const float4 *__restrict__ priors,
-                                                               const float4 *__restrict__ arm_loc, const float *__restrict__ conf,
-                                                               float4 *__restrict__ boxes, float *__restrict__ scoresT, int P, int C)
+// order-preserving fp32 -> u32 (handles negative scores in standalone mode)
+__device__ __forceinline__ unsigned score_key(float s)
+{
+    const unsigned u = __float_as_uint(s);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_score(unsigned long long c)   // inverse of score_key for the key's upper half
+{
+    const unsigned k = (unsigned)(c >> 32);
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// grid (ceil(P/DEC_TP), B).  conf == NULL: plain tdrn_decode (boxes only).
+// cand [B*C][P] u64 candidate keys per (image, class) segment, cnt [B*C] their number (zeroed by the caller).
+__global__ void __launch_bounds__(256) detect_front_kernel(const float4 *__restrict__ loc, const float4 *__restrict__ priors,
+                                                           const float4 *__restrict__ arm_loc, const float *__restrict__ conf,
+                                                           float4 *__restrict__ boxes, unsigned long long *__restrict__ cand,
+                                                           unsigned *__restrict__ cnt, int P, int C, float conf_thresh)
 {
     extern __shared__ float s_conf[];          // [DEC_TP * C]
     const int b = blockIdx.y, p0 = blockIdx.x * DEC_TP;
     const int np = min(DEC_TP, P - p0);
+    if (conf) {                                // issue the score tile's loads first: the decode below overlaps them
+        const float *src = conf + ((long long)b * P + p0) * C;
+        if ((((uintptr_t)src) & 15) == 0 && ((np * C) & 3) == 0) {
+            for (int i = threadIdx.x; i < (np * C) >> 2; i += blockDim.x) ((float4 *)s_conf)[i] = ((const float4 *)src)[i];
+        } else {
+            for (int i = threadIdx.x; i < np * C; i += blockDim.x) s_conf[i] = src[i];
+        }
+    }
     if (threadIdx.x < np) {
         const int p = p0 + threadIdx.x;
         float4 prior = priors[p];
         if (arm_loc) prior = center_size_box(decode_box(arm_loc[(long long)b * P + p], prior));
         boxes[(long long)b * P + p] = decode_box(loc[(long long)b * P + p], prior);
     }
-    if (scoresT) {
-        const float *src = conf + ((long long)b * P + p0) * C;
-        for (int i = threadIdx.x; i < np * C; i += blockDim.x) s_conf[i] = src[i];
-        __syncthreads();
-        for (int i = threadIdx.x; i < np * (C - 1); i += blockDim.x) {
-            const int cl = 1 + i / np, pl = i - (cl - 1) * np;
-            scoresT[((long long)b * C + cl) * P + p0 + pl] = s_conf[pl * C + cl];
-        }
+    if (!conf) return;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    // item i = (class cl, prior pl) with the prior fastest: a warp looks at 32 consecutive priors of one class
+    // (DEC_TP is a multiple of 32 and np is padded up to it, so a warp never straddles two classes)
+    for (int i = threadIdx.x; i < DEC_TP * (C - 1); i += blockDim.x) {
+        const int cl = 1 + i / DEC_TP, pl = i - (cl - 1) * DEC_TP;
+        const float sc = pl < np ? s_conf[pl * C + cl] : 0.f;
+        const bool take = pl < np && sc > conf_thresh;                     // strict fp32 compare, detection.py:53
+        const unsigned ballot = __ballot_sync(0xffffffffu, take);
+        if (ballot == 0u) continue;                                        // warp-uniform
+        const int seg = b * C + cl;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&cnt[seg], (unsigned)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (take)
+            cand[(long long)seg * P + base + __popc(ballot & ((1u << lane) - 1u))] =
+                ((unsigned long long)score_key(sc) << 32) | (unsigned)(0xffffffffu - (unsigned)(p0 + pl));
     }
 }
 
 struct NmsP {
     // detect mode
     const float4 *boxes;      // [B,P,4] normalised
-    const float *scoresT;     // [B,C,P]
+    const unsigned long long *cand;   // [B*C][P] candidate keys (detect_front_kernel)
+    const unsigned *cnt;      // [B*C]
     float *out;               // [B,C,top_k,5]
     int P, C, top_k;
     float conf_thresh;
@@ -126,13 +167,6 @@ __device__ __forceinline__ float box_area(float4 b)
     return __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
 }
 
-// order-preserving fp32 -> u32 (handles negative scores in standalone mode)
-__device__ __forceinline__ unsigned score_key(float s)
-{
-    const unsigned u = __float_as_uint(s);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
 // One CTA per segment.  DETECT: grid (C, B); class 0 only zero-fills.  Standalone: grid (1).
 template <bool DETECT>
 __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
@@ -154,17 +188,15 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int cl = 0, b = 0;
     float *out_seg = nullptr;
-    const float *sc = nullptr;
+    const unsigned long long *cand = nullptr;
     int n_in;
     if (DETECT) {
         cl = blockIdx.x; b = blockIdx.y;
+        if (cl == 0) return;                                       // background row: zero-filled by nms_warp_kernel
+        n_in = (int)p.cnt[b * p.C + cl];
+        if (n_in <= NMS_WCAP) return;                              // small segment: nms_warp_kernel's
         out_seg = p.out + ((long long)b * p.C + cl) * p.top_k * 5;
-        if (cl == 0) {                                             // background row stays zero (detection.py:37,52)
-            for (int i = tid; i < p.top_k * 5; i += NMS_THREADS) out_seg[i] = 0.f;
-            return;
-        }
-        sc = p.scoresT + ((long long)b * p.C + cl) * p.P;
-        n_in = p.P;
+        cand = p.cand + (long long)(b * p.C + cl) * p.P;
     } else {
         n_in = p.n;
     }
@@ -175,9 +207,13 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
 
     // composite key of element i, or 0 if it is not a candidate / not below the current bound
     auto key_of = [&](int i, unsigned long long hi_incl) -> unsigned long long {
-        const float s = DETECT ? sc[i] : p.dets[5 * (long long)i + 4];
-        if (DETECT && !(s > p.conf_thresh)) return 0ull;           // strict fp32 compare, detection.py:53
-        const unsigned long long c = ((unsigned long long)score_key(s) << 32) | (unsigned)(0xffffffffu - (unsigned)i);
+        unsigned long long c;
+        if (DETECT) {
+            c = cand[i];                                            // already thresholded and keyed by detect_front_kernel
+        } else {
+            const float s = p.dets[5 * (long long)i + 4];
+            c = ((unsigned long long)score_key(s) << 32) | (unsigned)(0xffffffffu - (unsigned)i);
+        }
         return c <= hi_incl ? c : 0ull;
     };
 
@@ -351,7 +387,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
                     if (DETECT) {
                         const float4 nb = p.boxes[(long long)b * p.P + cidx[lane]];
                         float *o = out_seg + pos * 5;                       // detection.py:61-63
-                        o[0] = sc[cidx[lane]]; o[1] = nb.x; o[2] = nb.y; o[3] = nb.z; o[4] = nb.w;
+                        o[0] = key_score(keys[c0 + lane]); o[1] = nb.x; o[2] = nb.y; o[3] = nb.z; o[4] = nb.w;
                     } else {
                         p.keep[pos] = cidx[lane];
                     }
@@ -374,6 +410,77 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
     }
 }
 
+// One WARP per (image, class) segment with at most NMS_WCAP candidates (grid = ceil(B*C / NMS_WARPS), also zero-fills the
+// background rows).  Shared memory per warp: keys[NMS_WCAP] u64, kept boxes float4[kc], kept areas float[kc] with
+// kc = min(top_k, NMS_WCAP).  Same visiting order and the same fp32 IoU as nms_segment_kernel.
+__global__ void __launch_bounds__(NMS_WARPS * 32) nms_warp_kernel(const NmsP p, int n_seg, int kc)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = blockIdx.x * NMS_WARPS + warp;
+    if (seg >= n_seg) return;
+    const int b = seg / p.C, cl = seg - b * p.C;
+    const int n = cl == 0 ? 0 : (int)p.cnt[seg];
+    if (n > NMS_WCAP) return;                                       // nms_segment_kernel's
+    unsigned char *mine = smem_raw + (size_t)warp * ((size_t)NMS_WCAP * 8 + (size_t)kc * 20);
+    unsigned long long *keys = (unsigned long long *)mine;
+    float4 *kbox = (float4 *)(mine + (size_t)NMS_WCAP * 8);
+    float *kar = (float *)(kbox + kc);
+    float *out_seg = p.out + (long long)seg * p.top_k * 5;
+    const unsigned max_keep = (unsigned)p.max_keep;
+    unsigned kept_n = 0;
+    if (n > 0) {
+        const unsigned long long *cand = p.cand + (long long)seg * p.P;
+        int n_pad = 32;
+        while (n_pad < n) n_pad <<= 1;
+        for (int i = lane; i < n_pad; i += 32) keys[i] = i < n ? cand[i] : 0ull;
+        __syncwarp();
+        for (int k = 2; k <= n_pad; k <<= 1) {                      // bitonic sort, descending (score desc, prior asc)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = lane; t < (n_pad >> 1); t += 32) {
+                    const int lo_i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int hi_i = lo_i | j;
+                    const unsigned long long a = keys[lo_i], c = keys[hi_i];
+                    const bool desc = (lo_i & k) == 0;
+                    if (desc ? (a < c) : (a > c)) { keys[lo_i] = c; keys[hi_i] = a; }
+                }
+                __syncwarp();
+            }
+        }
+        const float4 *boxes = p.boxes + (long long)b * p.P;
+        for (int c0 = 0; c0 < n && kept_n < max_keep; c0 += 32) {
+            const bool valid = c0 + lane < n;
+            const unsigned long long key = valid ? keys[c0 + lane] : 0ull;
+            const int src = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
+            const float4 nb = valid ? boxes[src] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 bx = make_float4(__fmul_rn(nb.x, p.scale.x), __fmul_rn(nb.y, p.scale.y),
+                                          __fmul_rn(nb.z, p.scale.z), __fmul_rn(nb.w, p.scale.w));   // detection.py:59
+            const float ar = box_area(bx);
+            bool sup = !valid;
+            for (unsigned q = 0; q < kept_n; ++q)                   // lane = candidate, the kept box is a broadcast read
+                if (!sup) sup = iou_ge(kbox[q], kar[q], bx, ar, p.thr_up);
+            unsigned pending = __ballot_sync(0xffffffffu, !sup);
+            while (pending && kept_n < max_keep) {                  // uniform: the lowest pending candidate is kept
+                const int i = __ffs(pending) - 1;
+                const float4 bi = make_float4(__shfl_sync(0xffffffffu, bx.x, i), __shfl_sync(0xffffffffu, bx.y, i),
+                                              __shfl_sync(0xffffffffu, bx.z, i), __shfl_sync(0xffffffffu, bx.w, i));
+                const float ai = __shfl_sync(0xffffffffu, ar, i);
+                if (lane == i) {
+                    kbox[kept_n] = bx; kar[kept_n] = ar;
+                    float *o = out_seg + kept_n * 5;                // detection.py:61-63
+                    o[0] = key_score(key); o[1] = nb.x; o[2] = nb.y; o[3] = nb.z; o[4] = nb.w;
+                }
+                pending &= ~(1u << i);
+                const bool hit = ((pending >> lane) & 1u) && iou_ge(bi, ai, bx, ar, p.thr_up);
+                pending &= ~__ballot_sync(0xffffffffu, hit);
+                ++kept_n;
+            }
+            __syncwarp();
+        }
+    }
+    for (int i = kept_n * 5 + lane; i < p.top_k * 5; i += 32) out_seg[i] = 0.f;
+}
+
 static float thresh_up(double t)
 {
     float f = (float)t;
@@ -391,16 +498,18 @@ extern "C" int tdrn_decode(const float *loc, const float *priors, const float *a
 {
     TDRN_REQUIRE(loc && priors && boxes && B > 0 && P > 0, "tdrn_decode: bad argument");
     dim3 grid(ceil_div(P, DEC_TP), B);
-    decode_transpose_kernel<<<grid, 256, 0, as_stream(stream)>>>((const float4 *)loc, (const float4 *)priors, (const float4 *)arm_loc,
-                                                                 nullptr, (float4 *)boxes, nullptr, P, 0);
+    detect_front_kernel<<<grid, 256, 0, as_stream(stream)>>>((const float4 *)loc, (const float4 *)priors, (const float4 *)arm_loc,
+                                                             nullptr, (float4 *)boxes, nullptr, nullptr, P, 0, 0.f);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }
 
+// workspace: decoded boxes [B,P,4] f32 | candidate counts [B*C] u32 | candidate keys [B*C][P] u64
 extern "C" size_t tdrn_detect_workspace_bytes(int B, int P, int C, int top_k)
 {
     (void)top_k;
-    return align_up((size_t)B * P * 4 * sizeof(float), 256) + align_up((size_t)B * C * P * sizeof(float), 256);
+    return align_up((size_t)B * P * 4 * sizeof(float), 256) + align_up((size_t)B * C * sizeof(unsigned), 256) +
+           align_up((size_t)B * C * P * sizeof(unsigned long long), 256);
 }
 
 extern "C" int tdrn_detect(const float *loc, const float *conf, const float *priors, const float *arm_loc,
@@ -415,23 +524,36 @@ extern "C" int tdrn_detect(const float *loc, const float *conf, const float *pri
         return TDRN_EWORKSPACE;
     }
     cudaStream_t st = as_stream(stream);
-    float *boxes = (float *)workspace;
-    float *scoresT = (float *)((char *)workspace + align_up((size_t)B * P * 4 * sizeof(float), 256));
+    char *w = (char *)workspace;
+    float *boxes = (float *)w;
+    w += align_up((size_t)B * P * 4 * sizeof(float), 256);
+    unsigned *cnt = (unsigned *)w;
+    w += align_up((size_t)B * C * sizeof(unsigned), 256);
+    unsigned long long *cand = (unsigned long long *)w;
 
     const size_t dec_smem = (size_t)DEC_TP * C * sizeof(float);
     TDRN_REQUIRE(dec_smem <= 200 * 1024, "tdrn_detect: too many classes (%d)", C);
     if (dec_smem > 48 * 1024)
-        TDRN_CUDA(cudaFuncSetAttribute(decode_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));
+        TDRN_CUDA(cudaFuncSetAttribute(detect_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));
+    TDRN_CUDA(cudaMemsetAsync(cnt, 0, (size_t)B * C * sizeof(unsigned), st));
     dim3 dgrid(ceil_div(P, DEC_TP), B);
-    decode_transpose_kernel<<<dgrid, 256, dec_smem, st>>>((const float4 *)loc, (const float4 *)priors, (const float4 *)arm_loc,
-                                                           conf, (float4 *)boxes, scoresT, P, C);
+    detect_front_kernel<<<dgrid, 256, dec_smem, st>>>((const float4 *)loc, (const float4 *)priors, (const float4 *)arm_loc,
+                                                       conf, (float4 *)boxes, cand, cnt, P, C, conf_thresh);
     TDRN_LAUNCH_CHECK();
 
     NmsP p{};
-    p.boxes = (const float4 *)boxes; p.scoresT = scoresT; p.out = out; p.P = P; p.C = C; p.top_k = top_k;
+    p.boxes = (const float4 *)boxes; p.cand = cand; p.cnt = cnt; p.out = out; p.P = P; p.C = C; p.top_k = top_k;
     p.conf_thresh = conf_thresh;
     p.scale = make_float4(scale_host[0], scale_host[1], scale_host[2], scale_host[3]);
     p.max_keep = top_k; p.kept_cap = top_k; p.thr_up = thresh_up(nms_thresh);
+    // small segments: one warp each
+    const int kc = top_k < NMS_WCAP ? top_k : NMS_WCAP;
+    const size_t wsmem = (size_t)NMS_WARPS * ((size_t)NMS_WCAP * 8 + (size_t)kc * 20);
+    if (wsmem > 48 * 1024)
+        TDRN_CUDA(cudaFuncSetAttribute(nms_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+    nms_warp_kernel<<<ceil_div(B * C, NMS_WARPS), NMS_WARPS * 32, wsmem, st>>>(p, B * C, kc);
+    TDRN_LAUNCH_CHECK();
+    // large segments: one CTA each
     const size_t smem = (size_t)top_k * 5 * sizeof(float);
     TDRN_REQUIRE(smem <= 150 * 1024, "tdrn_detect: top_k=%d exceeds the shared-memory kept-list capacity", top_k);
     if (smem > 16 * 1024)

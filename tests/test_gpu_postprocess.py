@@ -169,3 +169,51 @@ def test_collect_detections_matches_eval_loop():
                 assert np.array_equal(got[c][b], ref[c][b]), (c, b)
     capped, n2 = collect_detections(det.cuda(), sizes, max_rows=17)
     assert n2 == n and capped.shape[0] == 17 and torch.equal(capped, rows[:17])
+
+
+def _detect_vs_oracle(loc, conf, arm, Cn, top_k=200, conf_t=0.01, nms_t=0.45):
+    from oracle import c_oracle as C
+    from tdrn_b200 import ops
+    from tdrn_b200.layers.functions import Detect, PriorBox
+    from tdrn_b200.data import mb_cfg
+    pri = PriorBox(mb_cfg['VOC_320']).forward()
+    out = Detect(Cn, 0, top_k, conf_t, nms_t).forward(loc.cuda(), conf.cuda(), pri.cuda(), arm_loc_data=arm.cuda())
+    boxes = ops.decode(loc.cuda(), pri.cuda(), arm.cuda()).cpu().numpy()
+    ref = C.detect(boxes, conf.numpy(), np.array([320.] * 4, np.float32), Cn, top_k, conf_t, nms_t)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    return out
+
+
+def test_detect_trained_like_regime_warp_path():
+    """Regime T: background logit +7, ~1-2 % of the (prior, class) scores pass the threshold -> every segment
+    is a small one and goes through the one-warp-per-segment kernel (nms_warp_kernel)."""
+    g = torch.Generator().manual_seed(31)
+    P, Cn, B = 6375, 21, 4
+    loc = torch.randn(B, P, 4, generator=g) * 0.5
+    arm = torch.randn(B, P, 4, generator=g) * 0.5
+    logits = torch.randn(B * P, Cn, generator=g) * 2
+    logits[:, 0] += 7
+    conf = torch.softmax(logits, 1)
+    n_cand = (conf.view(B, P, Cn)[:, :, 1:] > 0.01).sum(1)
+    assert 0 < int(n_cand.max()) <= 512 and float(n_cand.float().mean()) > 20
+    out = _detect_vs_oracle(loc, conf, arm, Cn)
+    assert (out[:, 1:, 0, 0] > 0).any()
+    _detect_vs_oracle(loc, conf, arm, Cn, top_k=7, conf_t=0.02, nms_t=0.3)     # early exit at top_k inside a chunk
+
+
+def test_detect_segment_sizes_around_the_warp_kernel_limit():
+    """Segments with exactly 0, 1, 31, 32, 33, 511, 512 (warp kernel) and 513, 1025 (CTA kernel) candidates in ONE call, with
+    ties in the scores (pinned rule: lower prior index first)."""
+    g = torch.Generator().manual_seed(32)
+    P, Cn, B = 6375, 11, 1
+    loc = torch.randn(B, P, 4, generator=g) * 0.3
+    arm = torch.randn(B, P, 4, generator=g) * 0.3
+    conf = torch.full((B * P, Cn), 0.001)
+    sizes = [0, 1, 31, 32, 33, 511, 512, 513, 1025, 200]
+    for cl, n in enumerate(sizes, start=1):
+        idx = torch.randperm(P, generator=g)[:n]
+        sc = 0.02 + 0.9 * torch.rand(n, generator=g)
+        sc = torch.round(sc * 64) / 64 if cl == 10 else sc                # class 10: heavy ties
+        conf[idx, cl] = sc
+    _detect_vs_oracle(loc, conf, arm, Cn)
+    _detect_vs_oracle(loc, conf, arm, Cn, top_k=600)                       # kept list longer than a chunk, > 512 rows
