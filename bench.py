@@ -1,19 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- frames/s of the DualRefineDet-VGGBN-320 inference hot path (net(x) + Detect) on N B200s.
+"""bench.py -- frames/s of the DualRefineDet / TDRN inference hot path (net(x) + Detect) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config vgg320|coco512|mobilenet|tdrn]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1: one rank per GPU)
 
-A "step" is one pass of the hot path over one batch of 32 synthetic frames per GPU (BASELINE.json
-configs[1]): conv backbone + ARM/ODM heads (deformable, multihead as scripts/batch_eval.sh ships it),
-softmax, two-stage decode, per-class NMS, top-k.  Frames shard by batch across ranks (weak scaling, no
-collective inside the compute path; one NCCL all_gather of the fixed-size detection buffers per step).
+Default workload (BASELINE.json configs[1], the one the metric is quoted on): a "step" is one pass of the hot path over one
+batch of 32 synthetic frames per GPU: conv backbone + ARM/ODM heads (deformable, multihead as scripts/batch_eval.sh
+ships it), softmax, two-stage decode, per-class NMS, top-k.  Frames shard by batch across ranks (weak scaling, no
+collective inside the compute path; one NCCL all_gather of the fixed-size detection buffers per step, issued on its own
+stream so that no rank's kernels ever wait for another rank).  `--config` selects the other BASELINE.json configurations
+(3: 512x512 COCO-81 b16 per GPU, `evaluate_coco.py:108-188`; 4: MobileNet b64 throughput + b1 latency from uint8 frames,
+`test_video.py:104-115`; 5: TDRN 16-frame clips sharded across ranks, `evaluate_trn.py:434-467`) with the same JSON schema.
 
 One JSON line on stdout (rank 0).  `value` = frames/s with inputs resident in HBM (CUDA-graph replay);
-`e2e` = the same through the public API with HOST buffers (pinned H2D of the frames + D2H of the
-detections inside the timed region); `roofline` = the tcgen05 implicit-GEMM conv kernel (dominant),
-algorithmic FLOPs / CUDA-event time; `cpu_baseline` = the oracle port of the reference's CPU path timed
-on this box's host cores.  `--impl reference` times only that CPU path.
+`e2e` = the same through the public API with HOST buffers: pinned uint8 frames -> H2D -> base_transform on the device
+(tdrn_preprocess) -> net -> Detect -> D2H of the detections, all inside the timed region (`--ingest fp32` feeds
+pre-transformed fp32 frames as round 1 did); `sustained` = the device leg replayed for >= 2 s (power-steady figure);
+`roofline` = the tcgen05 implicit-GEMM conv family (dominant), algorithmic FLOPs / CUDA-event time; `cpu_baseline` = the
+oracle port of the reference's CPU path timed on this box's host cores.  `--impl reference` times only that CPU path.
 """
 import argparse
 import json
@@ -27,30 +31,170 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = 'frames/sec DualRefineDet-VGGBN-320 b32'
 UNIT = 'frames/s'
-BATCH = 32
-SIZE = 320
-NUM_CLASSES = 21
-MODEL_KW = dict(num_classes=NUM_CLASSES, def_groups=1, bn=True, multihead=True)
-DETECT_KW = dict(top_k=200, conf_thresh=0.01, nms_thresh=0.45)      # scripts/batch_eval.sh:2-4
-GFLOP_PER_FRAME = 77.466                                           # SURVEY.md 8d (multihead, conv + deform)
-
+MEANS = (104.0, 117.0, 123.0)                                       # data/config.py: VOC / COCO BGR means
 
 # diagnosis only (never set by the driver): TDRN_BENCH_E2E_SKIP=h2d,d2h drops those copies from the e2e leg to attribute its
 # gap to the device leg; a run with it set is not a valid e2e number and says so in its JSON line
 _DIAG_SKIP = [t for t in os.environ.get('TDRN_BENCH_E2E_SKIP', '').split(',') if t]
 
 
-def config_dict(n_gpus, inflight=2):
-    return {'workload': 'DualRefineDet-VGGBN 320x320 VOC-21 batch %d per GPU, multihead deformable ODM, '
-                        'net(x)+Detect(top_k 200, conf 0.01, nms 0.45)' % BATCH,
-            'global_batch': BATCH * n_gpus, 'per_gpu_batch': BATCH, 'input': '[B,3,320,320] fp32 N(0,1)',
-            'weights': 'seeded random init, randomised BN statistics (tdrn_b200.utils.synthetic.randomize_ seed 0)',
-            'parallelism': 'dp%d (frames sharded by batch, weights replicated)' % n_gpus,
-            'l2': 'rotating 4 distinct input batches (157 MB) and >1 GB of per-step activations exceed the 126 MB L2',
-            'pipelining': 'CUDA-graph replay (one instance per resident input batch), %d step(s) in flight (with 2, step i+1 trunk '
-                          'overlaps the latency-bound tail of step i)' % inflight}
+# ------------------------------------------------------------------------------------------------------
+# workloads (BASELINE.json configs)
+# ------------------------------------------------------------------------------------------------------
+class Workload(object):
+    """One BASELINE.json configuration: the nets, Detect settings, the per-step batch and the algorithmic work."""
+    key = 'vgg320'
+    metric = 'frames/sec DualRefineDet-VGGBN-320 b32'
+    title = 'DualRefineDet-VGGBN 320x320 VOC-21 batch 32 per GPU, multihead deformable ODM'
+    batch, size, num_classes = 32, 320, 21
+    model_kw = dict(num_classes=21, def_groups=1, bn=True, multihead=True)
+    detect_kw = dict(top_k=200, conf_thresh=0.01, nms_thresh=0.45)  # scripts/batch_eval.sh:2-4
+    prior_cfg = 'VOC_320'
+    gflop_per_frame = 77.466                                        # SURVEY.md 8d (multihead, conv + deform)
+    unit_name = 'frames'
+    cpu_frames_per_step = 1
+
+    def build_modules(self):
+        from tdrn_b200.model import dualrefinedet_vggbn as V
+        from tdrn_b200.utils.synthetic import randomize_
+        return [randomize_(V.build_net('test', self.size, **self.model_kw), seed=0).eval()]
+
+    def setup(self, dev, precision):
+        from tdrn_b200.layers.functions import Detect, PriorBox
+        from tdrn_b200.data import mb_cfg
+        self.nets = [m.to(dev).set_precision(precision) for m in self.build_modules()]
+        self.det = Detect(self.num_classes, 0, self.detect_kw['top_k'], self.detect_kw['conf_thresh'], self.detect_kw['nms_thresh'])
+        self.priors = PriorBox(mb_cfg[self.prior_cfg]).forward().to(dev)
+        self.scale = [float(self.size)] * 4
+
+    def hot_path(self, x):
+        arm_loc, _, loc, conf = self.nets[0](x)
+        return self.det.forward(loc, conf, self.priors, arm_loc_data=arm_loc, scale=self.scale)
+
+    def net_outputs(self, x):                                       # (arm_loc, loc, conf) for the Detect micro-benchmarks
+        arm_loc, _, loc, conf = self.nets[0](x)
+        return arm_loc, loc, conf
+
+    def describe(self, n_gpus, inflight, ingest):
+        s = self.size
+        return {'workload': '%s, net(x)+Detect(top_k %d, conf %.2f, nms %.2f)' % (
+                    self.title, self.detect_kw['top_k'], self.detect_kw['conf_thresh'], self.detect_kw['nms_thresh']),
+                'global_batch': self.batch * n_gpus, 'per_gpu_batch': self.batch,
+                'input': '[B,3,%d,%d] fp32 N(0,1) resident in HBM (device leg); e2e leg: %s' % (
+                    s, s, 'pinned uint8 [B,%d,%d,3] frames -> H2D -> base_transform on the device' % (s, s)
+                    if ingest == 'u8' else 'pinned fp32 [B,3,%d,%d] frames -> H2D' % (s, s)),
+                'weights': 'seeded random init, randomised BN statistics (tdrn_b200.utils.synthetic.randomize_ seed 0)',
+                'parallelism': 'dp%d (%s sharded across ranks, weights replicated)' % (n_gpus, self.unit_name),
+                'l2': 'rotating 4 distinct input batches and >1 GB of per-step activations exceed the 126 MB L2',
+                'pipelining': 'CUDA-graph replay (one instance per resident input batch), %d step(s) in flight (with 2, step i+1 '
+                              'trunk overlaps the latency-bound tail of step i)' % inflight}
+
+    # ---- CPU reference arm: the oracle port of the reference's own CPU implementation of this workload ----
+    def cpu_setup(self):
+        import torch
+        from oracle import detect_ref as D
+        self.cpu_sd = [{k: v.detach().cpu() for k, v in m.state_dict().items()} for m in self.build_modules()]
+        self.cpu_priors = D.prior_box(getattr(D, self.prior_cfg))
+        torch.set_num_threads(os.cpu_count() or 1)
+
+    def cpu_forward(self, x):
+        from oracle import model_ref as M
+        arm_loc, _, loc, conf = M.drn_vgg_forward(self.cpu_sd[0], x, **self.model_kw)
+        return arm_loc, loc, conf
+
+    def cpu_step(self, x):
+        """x [b,3,S,S] -> detections; torch CPU convs on all cores, Detect on one core like the reference."""
+        import numpy as np
+        from oracle import c_oracle as C
+        arm_loc, loc, conf = self.cpu_forward(x)
+        boxes = C.decode(loc.numpy(), self.cpu_priors.numpy(), arm_loc.numpy())
+        return C.detect(boxes, conf.numpy(), np.array([float(self.size)] * 4, np.float32), self.num_classes,
+                        self.detect_kw['top_k'], self.detect_kw['conf_thresh'], self.detect_kw['nms_thresh'])
+
+
+class Coco512(Workload):
+    """configs[2]: evaluate_coco.py:108-188 with the 512 prior dictionary (data/config.py:70-81)."""
+    key = 'coco512'
+    metric = 'frames/sec DualRefineDet-VGGBN-512 COCO-81 b16'
+    title = 'DualRefineDet-VGGBN 512x512 COCO-81 batch 16 per GPU, multihead deformable ODM'
+    batch, size, num_classes = 16, 512, 81
+    model_kw = dict(num_classes=81, def_groups=1, bn=True, multihead=True)
+    detect_kw = dict(top_k=100, conf_thresh=0.01, nms_thresh=0.45)  # evaluate_coco.py:30 default top_k
+    prior_cfg = 'VOC_512_RefineDet'
+    gflop_per_frame = 215.360
+
+
+class MobileNet(Workload):
+    """configs[3]: DualRefineDet-MobileNet, batch-64 throughput (the JSON line) + batch-1 latency from uint8 frames."""
+    key = 'mobilenet'
+    metric = 'frames/sec DualRefineDet-MobileNet-320 b64'
+    title = 'DualRefineDet-MobileNet 320x320 VOC-21 batch 64 per GPU (throughput; batch-1 latency in `latency_b1`)'
+    batch, size, num_classes = 64, 320, 21
+    model_kw = dict(num_classes=21, def_groups=1, multihead=False)
+    gflop_per_frame = 20.297
+
+    def build_modules(self):
+        from tdrn_b200.model import dualrefinedet_mobilenet as Mb
+        from tdrn_b200.utils.synthetic import randomize_
+        return [randomize_(Mb.build_net('test', self.size, **self.model_kw), seed=0).eval()]
+
+    def cpu_forward(self, x):
+        from oracle import model_ref as M
+        arm_loc, _, loc, conf = M.drn_mobilenet_forward(self.cpu_sd[0], x, **self.model_kw)
+        return arm_loc, loc, conf
+
+
+class Tdrn(Workload):
+    """configs[4]: TDRN = static SSD4Scale on key frames + temporal SSD4Scale (dg = 8 deformable heads driven by the key
+    frame's regression) on every frame, evaluate_trn.py:434-467.  A step is CLIPS 16-frame clips per GPU, key-frame
+    interval 4: 4 static + 16 temporal forwards + Detect per clip.  Clips (never frames: a clip's frames share the
+    key-frame state) are assigned to ranks by tdrn_b200.utils.shard.shard_clips."""
+    key = 'tdrn'
+    CLIPS, T, K = 2, 16, 4
+    metric = 'frames/sec TDRN-VGGBN-320 VID-31 16-frame clips'
+    title = ('TDRN (SSD4Scale static + temporal, VGG-BN) 320x320 ImageNet-VID-31, 2 clips x 16 frames per GPU per step, '
+             'key-frame interval 4')
+    batch, size, num_classes = 32, 320, 31
+    model_kw = dict(bn=True)
+    gflop_per_frame = 1321.0 / 16
+    unit_name = 'clips'
+    cpu_frames_per_step = 4                                           # one key frame + the three frames it governs
+
+    def build_modules(self):
+        from tdrn_b200.model import ssd4scale_vgg as S
+        from tdrn_b200.utils.synthetic import randomize_
+        return [randomize_(S.build_net('test', self.size, num_classes=self.num_classes, deform=False, **self.model_kw), 0).eval(),
+                randomize_(S.build_net('test', self.size, num_classes=self.num_classes, deform=True, **self.model_kw), 1).eval()]
+
+    def _forward(self, x):
+        K = self.K
+        s_loc, s_conf, loc_maps = self.nets[0](x[::K], ret_loc=True)       # key frames (clips are stacked along the batch)
+        ref = [m.repeat_interleave(K, 0) for m in loc_maps]               # every frame uses its key frame's regression
+        out = self.nets[1](x, ref_loc=ref, ret_off=True)
+        return s_loc.repeat_interleave(K, 0), out[0], out[1]
+
+    def hot_path(self, x):
+        arm, loc, conf = self._forward(x)
+        return self.det.forward(loc, conf, self.priors, arm_loc_data=arm, scale=self.scale)
+
+    def net_outputs(self, x):
+        return self._forward(x)
+
+    def cpu_forward(self, x):
+        from oracle import model_ref as M
+        K, C = self.K, self.num_classes
+        s = M.ssd4scale_vgg_forward(self.cpu_sd[0], x[::K], C, bn=True, deform=False, ret_loc=True)
+        t = M.ssd4scale_vgg_forward(self.cpu_sd[1], x, C, bn=True, deform=True, ref_loc=[m.repeat_interleave(K, 0) for m in s[2]])
+        return s[0].repeat_interleave(K, 0), t[0], t[1]
+
+
+WORKLOADS = {w.key: w for w in (Workload, Coco512, MobileNet, Tdrn)}
+
+
+def build_synthetic_net():
+    """The default workload's module (scripts/ and tests use it)."""
+    return Workload().build_modules()[0]
 
 
 def peaks():
@@ -62,70 +206,86 @@ def peaks():
     return {'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'hbm_gbs': 6650.0, 'source': 'fallback (B200_PROFILING.md)'}
 
 
+def graph_replay_ms(fn, stream, iters=20, warmup=3):
+    """Milliseconds per call of ``fn`` replayed as a CUDA graph on ``stream`` (events around ``iters`` replays)."""
+    import torch
+    with torch.cuda.stream(stream), torch.no_grad():
+        for _ in range(warmup):
+            fn()
+        stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            fn()
+        for _ in range(warmup):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            g.replay()
+        e1.record(stream)
+        stream.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def csrc_sha():
+    """Short hash of the conv kernels' sources: ties profiles/conv_traffic.json to the build it was measured on."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, 'tdrn_b200', 'csrc')
+    for f in sorted(os.listdir(d)):
+        if f.startswith(('conv_', 'tc_common', 'halo_common')):
+            h.update(open(os.path.join(d, f), 'rb').read())
+    return h.hexdigest()[:12]
+
+
 def conv_traffic():
-    """DRAM bytes per launch of the conv family from the committed ncu --set full capture (profiles/conv_traffic.json,
-    written by scripts/ncu_traffic.py from the .ncu-rep of the same bench command); None when no capture is committed."""
+    """(DRAM bytes per launch of the conv family, where it comes from): the ncu --set full capture of THIS build's bench
+    command (profiles/conv_traffic.json, written by scripts/ncu_traffic.py with the hash of the kernel sources it was taken
+    on).  A capture of other sources is reported as None -- never a stale number."""
     path = os.path.join(ROOT, 'profiles', 'conv_traffic.json')
     if not os.path.exists(path):
-        return None
+        return None, 'no ncu capture committed'
     try:
-        return json.load(open(path))['dram_bytes_per_launch']
-    except Exception:
-        return None
+        rec = json.load(open(path))
+        sha = csrc_sha()
+        if rec.get('csrc_sha') != sha:
+            return None, 'the committed capture is of kernel sources %s, this build is %s (re-run scripts/gpu_profile_conv.sh)' % (
+                rec.get('csrc_sha'), sha)
+        return rec['dram_bytes_per_launch'], 'ncu --set full of this build (profiles/conv_traffic.json, csrc %s)' % sha
+    except Exception as e:  # noqa: BLE001
+        return None, 'unreadable capture: %r' % (e,)
 
 
 # ------------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port of the reference's own CPU implementation)
 # ------------------------------------------------------------------------------------------------------
-class CpuReference(object):
-    def __init__(self):
-        import torch
-        from oracle import model_ref as M, detect_ref as D
-        self.torch, self.M, self.D = torch, M, D
-        self.cores = os.cpu_count() or 1
-        torch.set_num_threads(self.cores)
-        self.sd = {k: v.detach().cpu() for k, v in build_synthetic_net().state_dict().items()}   # same weights as the GPU arm
-        self.priors = D.prior_box(D.VOC_320)
-
-    def step(self, x):
-        """x [b,3,320,320] -> detections; torch CPU convs on all cores, Detect on one core like the reference."""
-        import numpy as np
-        from oracle import c_oracle as C
-        arm_loc, _, loc, conf = self.M.drn_vgg_forward(self.sd, x, **MODEL_KW)
-        boxes = C.decode(loc.numpy(), self.priors.numpy(), arm_loc.numpy())
-        return C.detect(boxes, conf.numpy(), np.array([320.] * 4, np.float32), NUM_CLASSES, DETECT_KW['top_k'],
-                        DETECT_KW['conf_thresh'], DETECT_KW['nms_thresh'])
-
-    def run(self, steps, warmup, frames_per_step=1):
-        from tdrn_b200.utils.synthetic import frames
-        x = frames(frames_per_step, SIZE, seed=11)
-        for _ in range(warmup):
-            self.step(x)
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            self.step(x)
-        dt = time.perf_counter() - t0
-        return frames_per_step * steps / dt, dt / steps * 1e3
-
-
-def build_synthetic_net():
-    from tdrn_b200.model import dualrefinedet_vggbn as V
-    from tdrn_b200.utils.synthetic import randomize_
-    return randomize_(V.build_net('test', SIZE, **MODEL_KW), seed=0).eval()
+def cpu_run(wl, steps, warmup):
+    from tdrn_b200.utils.synthetic import frames
+    wl.cpu_setup()
+    n = wl.cpu_frames_per_step
+    x = frames(n, wl.size, seed=11)
+    for _ in range(warmup):
+        wl.cpu_step(x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        wl.cpu_step(x)
+    dt = time.perf_counter() - t0
+    return n * steps / dt, dt / steps * 1e3
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    ref = CpuReference()
-    fps, ms = ref.run(args.steps, args.warmup, 1)
-    line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+    wl = WORKLOADS[args.config]()
+    fps, ms = cpu_run(wl, args.steps, args.warmup)
+    cores = os.cpu_count() or 1
+    line = {'impl': 'reference', 'metric': wl.metric, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic', 'config': config_dict(args.gpus),
-            'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': ref.cores, 'kind': 'port',
-                             'sample': '1 frame per step through the oracle port (torch CPU convs on all cores + '
+            'dtype': 'f32', 'data': 'synthetic', 'config': wl.describe(args.gpus, args.inflight, args.ingest),
+            'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': '%d frame(s) per step through the oracle port (torch CPU convs on all cores + '
                                        'scalar C Detect/NMS on one core, as the reference runs it); frames/s is '
-                                       'batch-independent on CPU'},
+                                       'batch-independent on CPU' % wl.cpu_frames_per_step},
             'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -163,29 +323,34 @@ class ClockSampler(object):
     def end(self):
         self.t1 = time.perf_counter()
 
-    def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.05)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.03]
-        window = 'timed legs'
-        if not rows and self.rows and self.t0 is not None:     # bracket shorter than one poll: closest samples
-            mid = 0.5 * (self.t0 + self.t1)
-            rows = [r for t, r in sorted(self.rows, key=lambda tr: abs(tr[0] - mid))[:3]]
-            window = 'closest to the timed legs'
+    def window(self, t0, t1, name):
+        rows = [r for t, r in list(self.rows) if t0 <= t <= t1 + 0.03]
+        window = name
+        if not rows and self.rows:                             # bracket shorter than one poll: closest samples
+            mid = 0.5 * (t0 + t1)
+            rows = [r for t, r in sorted(list(self.rows), key=lambda tr: abs(tr[0] - mid))[:3]]
+            window = 'closest to the ' + name
         sm, mx, pw, reasons = [], None, [], set()
         for r in rows:
             try:
                 sm.append(float(r[0])); mx = float(r[1]); pw.append(float(r[2]))
             except Exception:
                 continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+            for rname, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
                 if v.lower().startswith('active'):
-                    reasons.add(name)
+                    reasons.add(rname)
         sm.sort()
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'power_w_max': max(pw) if pw else None,
                 'reasons': sorted(reasons), 'samples': len(sm), 'window': window}
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.05)
+        self.proc.terminate()
+        if self.t0 is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no timed region']}
+        return self.window(self.t0, self.t1, 'timed legs')
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -196,12 +361,21 @@ def run_gpu(args, rank, world, local_rank):
     import torch.distributed as dist
     from tdrn_b200 import ops, _lib
     from tdrn_b200.utils.synthetic import frames as make_frames
-    from tdrn_b200.layers.functions import Detect, PriorBox
-    from tdrn_b200.data import mb_cfg
-    from tdrn_b200.utils.shard import gather_detections
+    from tdrn_b200.utils.shard import shard_clips
 
+    wl = WORKLOADS[args.config]()
+    BATCH, SIZE, NUM_CLASSES, TOP_K = wl.batch, wl.size, wl.num_classes, wl.detect_kw['top_k']
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    if world > 1:
+        # one host thread per rank feeds its GPU; give every rank its own cores so that the feeders of a box do not migrate
+        # over each other (all eight GPUs of this pool report the same CPU affinity / NUMA node)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]) or set(cores))
+        except Exception:
+            pass
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -220,24 +394,36 @@ def run_gpu(args, rank, world, local_rank):
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
 
-    net = build_synthetic_net().to(dev).set_precision(args.precision)
-    det = Detect(NUM_CLASSES, 0, DETECT_KW['top_k'], DETECT_KW['conf_thresh'], DETECT_KW['nms_thresh'])
-    priors = PriorBox(mb_cfg['VOC_320']).forward().to(dev)
+    wl.setup(dev, args.precision)
 
+    # ---- this rank's units (frames, or whole clips for TDRN) and its inputs -----------------------------------------
     n_in = 4
-    host_x = [make_frames(BATCH, SIZE, seed=100 + rank * n_in + i).pin_memory() for i in range(n_in)]
-    dev_x = [h.to(dev) for h in host_x]
-    host_out = torch.empty(BATCH, NUM_CLASSES, DETECT_KW['top_k'], 5).pin_memory()
+    if wl.key == 'tdrn':
+        clip_ids, _ = shard_clips([wl.T] * (wl.CLIPS * world), rank, world)      # global clip list -> this rank's clips
+        assert len(clip_ids) == wl.CLIPS
+        host_f32 = [torch.cat([make_frames(wl.T, SIZE, seed=1000 * i + c) for c in clip_ids], 0).pin_memory() for i in range(n_in)]
+    else:
+        host_f32 = [make_frames(BATCH, SIZE, seed=100 + rank * n_in + i).pin_memory() for i in range(n_in)]
+    dev_x = [h.to(dev) for h in host_f32]
+    # uint8 frames as a camera / decoder delivers them (cv2 layout [B,H,W,3]); source size = network size, so base_transform
+    # is the mean subtraction + HWC->CHW + the (identity-size) fixed-point resize the reference always runs
+    gen = torch.Generator().manual_seed(7 + rank)
+    host_u8 = [torch.randint(0, 256, (BATCH, SIZE, SIZE, 3), dtype=torch.uint8, generator=gen).pin_memory() for _ in range(n_in)]
+    host_out = torch.empty(BATCH, NUM_CLASSES, TOP_K, 5).pin_memory()
+
     def hot_path(x):
-        arm_loc, _, loc, conf = net(x)
-        return det.forward(loc, conf, priors, arm_loc_data=arm_loc)
+        return wl.hot_path(x)
+
+    def hot_path_u8(u8, x_buf):
+        ops.preprocess(u8, SIZE, MEANS, out=x_buf)              # base_transform on the device (data/__init__.py:7-12)
+        return wl.hot_path(x_buf)
 
     # Two steps are kept in flight on two streams (a serving loop would do the same): the tail of a step (FPN chain,
     # small pyramid levels, NMS) is latency-bound and leaves SMs idle that the next step's trunk can use.  A "step" is still
-    # one pass over one batch of 32 frames; K steps are timed; --inflight 1 gives the strictly serial number (~5 % slower).
+    # one pass over one batch; K steps are timed; --inflight 1 gives the strictly serial number.
     # There is one captured graph instance per resident input batch (n_in = 4): instance q reads xs[q] in place, so the
     # device leg moves no input bytes at all and the e2e leg's H2D lands directly in the graph's input (no staging copy
-    # that would queue behind the 1.5 ms H2D on a copy engine).  Step i runs instance i % 4 on stream i % 2.
+    # that would queue behind the H2D on a copy engine).  Step i runs instance i % 4 on stream i % 2.
     n_fl = 1 if args.no_graph else max(1, args.inflight)
     # instance q is captured on stream q % n_fl and must always replay there (its Detect workspace belongs to that stream, and
     # consecutive uses of one instance must be stream-ordered): the instance count is a multiple of the stream count
@@ -245,7 +431,9 @@ def run_gpu(args, rank, world, local_rank):
     streams = [torch.cuda.Stream(dev) for _ in range(n_fl)]
     stream = streams[0]
     xs = [dev_x[q % n_in].clone() for q in range(n_slots)]
-    graphs, static_outs = [], []
+    use_u8 = args.ingest == 'u8' and not args.no_graph          # (eager profiling mode keeps the fp32 ingest)
+    xs_u8 = [host_u8[q % n_in].to(dev) for q in range(n_slots)] if use_u8 else None
+    graphs, static_outs, graphs_u8, static_outs_u8 = [], [], [], []
     torch.cuda.synchronize()
     with torch.cuda.stream(stream), torch.no_grad():
         for i in range(3):                      # eager warm-up: packs weights, sizes workspaces, loads kernels
@@ -270,42 +458,76 @@ def run_gpu(args, rank, world, local_rank):
                 with torch.cuda.graph(g, stream=st):
                     static_outs.append(hot_path(xs[q]))
                 graphs.append(g)
+                if use_u8:                      # the e2e leg's instance: base_transform of the uint8 frames in front
+                    hot_path_u8(xs_u8[q], xs[q])
+                    st.synchronize()
+                    g8 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g8, stream=st):
+                        static_outs_u8.append(hot_path_u8(xs_u8[q], xs[q]))
+                    graphs_u8.append(g8)
         st.synchronize()
-    gathered = [torch.empty(world * BATCH, NUM_CLASSES, DETECT_KW['top_k'], 5, device=dev) for _ in range(n_slots)] if world > 1 else None
+    for q in range(n_slots):                     # the u8 warm-up overwrote xs[q]: restore the resident fp32 frames
+        xs[q].copy_(dev_x[q % n_in])
+    torch.cuda.synchronize()
 
-    def replay(q):
+    # ---- end-of-step gather of the fixed-size detection buffers (the path's only exchange) ---------------------------
+    # Issued asynchronously behind an event: the compute streams never wait for a collective, i.e. for another rank; an
+    # instance's buffer is only reused n_slots steps later, after its gather has completed.
+    do_gather = world > 1 and not args.no_gather
+    gathered = [torch.empty(world * BATCH, NUM_CLASSES, TOP_K, 5, device=dev) for _ in range(n_slots)] if do_gather else None
+    gather_stream = torch.cuda.Stream(dev) if do_gather else None
+    gather_work = [None] * n_slots
+    step_done = [torch.cuda.Event() for _ in range(n_slots)]
+
+    def gather_async(q, src, st):
+        step_done[q].record(st)
+        with torch.cuda.stream(gather_stream):
+            gather_stream.wait_event(step_done[q])
+            gather_work[q] = dist.all_gather_into_tensor(gathered[q], src, async_op=True)
+
+    def wait_gather(q):
+        if gather_work[q] is not None:
+            gather_work[q].wait()                # the CURRENT stream waits for the gather that last read this instance's output
+            gather_work[q] = None
+
+    def replay(q, u8=False):
         if args.no_graph:
             with torch.no_grad():
                 static_outs[q].copy_(hot_path(xs[q]))
         else:
-            graphs[q].replay()
+            (graphs_u8 if u8 else graphs)[q].replay()
 
     def step_device(i):
         q = i % n_slots
-        with torch.cuda.stream(streams[i % n_fl]):
+        st = streams[i % n_fl]
+        with torch.cuda.stream(st):
             if n_slots < n_in:
                 xs[q].copy_(dev_x[i % n_in], non_blocking=True)         # eager profiling mode: one input buffer
+            if do_gather:
+                wait_gather(q)
             replay(q)                                                   # the frames are already in HBM (xs[q])
-            if world > 1:
-                gather_detections(static_outs[q], out=gathered[q])
+            if do_gather:
+                gather_async(q, static_outs[q], st)
 
     # e2e: software-pipelined like a production feeder -- the pinned-host -> device copy of step i + n_fl runs on a copy
-    # stream while steps i, i + 1 compute; every step still pays its own H2D (39 MB) and D2H (2.7 MB) inside the timed
-    # region, they just overlap with the neighbouring steps' kernels instead of serialising with them.
+    # stream while steps i, i + 1 compute; every step still pays its own H2D and D2H inside the timed region, they just
+    # overlap with the neighbouring steps' kernels instead of serialising with them.
     copy_stream = torch.cuda.Stream(dev)                      # host -> device feeder
     d2h_stream = torch.cuda.Stream(dev)                       # detections -> host (own stream: a D2H waiting for step i
                                                               # must not hold back the H2D of step i+2)
-    in_ready = [torch.cuda.Event() for _ in range(n_slots)]   # H2D into xs[q] finished
-    done_ev = [torch.cuda.Event() for _ in range(n_slots)]    # the step that read xs[q] / wrote static_outs[q] has finished
+    in_ready = [torch.cuda.Event() for _ in range(n_slots)]   # H2D into the instance's input finished
+    done_ev = [torch.cuda.Event() for _ in range(n_slots)]    # the step that read the input / wrote the output has finished
     out_copied = [torch.cuda.Event() for _ in range(n_slots)]
     pipe = {'primed': -1}
+    e2e_dst, e2e_host = (xs_u8, host_u8) if use_u8 else (xs, host_f32)
+    e2e_outs = static_outs_u8 if use_u8 else static_outs
 
     def prefetch(i):
         q = i % n_slots
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(done_ev[q])                # the previous user of this instance's input is done
             if 'h2d' not in _DIAG_SKIP:
-                xs[q].copy_(host_x[i % n_in], non_blocking=True)
+                e2e_dst[q].copy_(e2e_host[i % n_in], non_blocking=True)
             in_ready[q].record(copy_stream)
         pipe['primed'] = i
 
@@ -318,19 +540,22 @@ def run_gpu(args, rank, world, local_rank):
         with torch.cuda.stream(st):
             st.wait_event(in_ready[q])
             st.wait_event(out_copied[q])                            # this instance's previous detections have left the device
-            replay(q)
-            if world > 1:
-                gather_detections(static_outs[q], out=gathered[q])
+            if do_gather:
+                wait_gather(q)
+            replay(q, u8=use_u8)
+            if do_gather:
+                gather_async(q, e2e_outs[q], st)
             done_ev[q].record(st)
         for j in range(pipe['primed'] + 1, i + depth + 1):          # the H2D of the next steps overlaps the kernels in flight
             prefetch(j)
         with torch.cuda.stream(d2h_stream):
             d2h_stream.wait_event(done_ev[q])
             if 'd2h' not in _DIAG_SKIP:
-                host_out.copy_(static_outs[q], non_blocking=True)   # detections -> pinned host
+                host_out.copy_(e2e_outs[q], non_blocking=True)      # detections -> pinned host
             out_copied[q].record(d2h_stream)
 
     def timed(step_fn, steps, warmup):
+        """-> (ms over the timed steps, MAX over ranks; every rank's own ms)."""
         pipe['primed'] = -1
         w = max(warmup, 12)                                # W is a minimum: a few more replays let the clocks settle
         for i in range(w):
@@ -351,22 +576,40 @@ def run_gpu(args, rank, world, local_rank):
             stream.wait_stream(st)
         stream.wait_stream(copy_stream)
         stream.wait_stream(d2h_stream)                      # e2e: the last step's D2H is inside the timed region
+        if do_gather:
+            with torch.cuda.stream(stream):
+                for q in range(n_slots):                    # ... and so is every gather
+                    wait_gather(q)
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        mine = e0.elapsed_time(e1)
+        per_rank = [mine]
         if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+            t = torch.zeros(world, device=dev)
+            t[rank] = mine
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            per_rank = [float(v) for v in t.tolist()]
+        return max(per_rank), per_rank
 
     sampler.begin()
-    ms_dev = timed(step_device, args.steps, args.warmup)
-    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    ms_dev, per_rank_dev = timed(step_device, args.steps, args.warmup)
+    ms_e2e, per_rank_e2e = timed(step_e2e, args.steps, args.warmup)
     sampler.end()
+
+    # ---- sustained leg: the device leg replayed for >= 2 s (the 20-step region above is ~55 ms: not power-steady) --------
+    sustained = None
+    if args.sustain > 0 and not args.no_graph:
+        n_sus = max(args.steps, int(args.sustain * 1e3 / max(ms_dev / args.steps, 1e-3)) + 1)
+        t_s0 = time.perf_counter()
+        ms_sus, _ = timed(step_device, n_sus, args.warmup)
+        t_s1 = time.perf_counter()
+        sustained = {'value': BATCH * world * n_sus / (ms_sus * 1e-3), 'unit': UNIT, 'ms_per_step': ms_sus / n_sus, 'steps': n_sus,
+                     'seconds': ms_sus * 1e-3}
+        if rank == 0 and sampler.proc is not None:
+            sustained['clocks'] = sampler.window(t_s0, t_s1, 'sustained leg')
     clocks = sampler.stop() if rank == 0 else None          # sampled every 20 ms across both timed legs
 
     # ---- overlapped replay must give what a serial eager pass gives (bit for bit: every kernel is deterministic) ----
@@ -377,24 +620,55 @@ def run_gpu(args, rank, world, local_rank):
         torch.cuda.synchronize()
         with torch.cuda.stream(stream), torch.no_grad():
             inflight_ok = all(bool(torch.equal(static_outs[q], hot_path(xs[q]))) for q in range(n_slots))
+            if do_gather:                                   # and the gathered buffer holds this rank's rows at its offset
+                for q in range(n_slots):
+                    wait_gather(q)
+                inflight_ok = inflight_ok and bool(torch.equal(gathered[0][rank * BATCH:(rank + 1) * BATCH], static_outs[0]))
         torch.cuda.synchronize()
         if not inflight_ok:       # reported in the JSON line (inflight_replay_matches_serial: false), never silently dropped
             sys.stderr.write('bench: WARNING detections of overlapped graph replays differ from a serial eager pass\n')
 
+    # ---- batch-1 latency (config 4): uint8 frame -> base_transform -> net -> Detect, one CUDA-graph replay per frame ------
+    latency = None
+    if rank == 0 and wl.key == 'mobilenet' and not args.no_graph:
+        u1 = host_u8[0][:1].to(dev)
+        x1 = torch.empty(1, 3, SIZE, SIZE, device=dev)
+        with torch.cuda.stream(stream), torch.no_grad():
+            for _ in range(3):
+                hot_path_u8(u1, x1)
+            stream.synchronize()
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1, stream=stream):
+                hot_path_u8(u1, x1)
+            ts = []
+            for i in range(1000 + 20):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); g1.replay(); e1.record(stream)
+                stream.synchronize()
+                if i >= 20:
+                    ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        latency = {'ms_p50': ts[len(ts) // 2], 'ms_p99': ts[int(len(ts) * 0.99)], 'ms_mean': sum(ts) / len(ts), 'replays': len(ts),
+                   'includes': 'tdrn_preprocess (base_transform from a resident uint8 frame) + net + Detect, one graph replay per '
+                               'frame, CUDA events around each replay'}
+
     # ---- roofline leg: per-call CUDA events on the launching stream, eager (same kernels as the graph) ----
-    roof = None
+    roof, breakdown = None, None
     if rank == 0:
         # per-kernel timing needs the kernels serialised on one stream: switch the engine's fork/join branches
         # off for this leg only (the timed legs above run the multi-stream graph)
-        net.engine().multi_stream = False
+        n_prof = max(2, min(args.steps, 5))
+        for m in wl.nets:
+            m.engine().multi_stream = False
         with torch.cuda.stream(stream), torch.no_grad():
             hot_path(dev_x[1])
             stream.synchronize()
             ops.prof_begin()
-            for i in range(max(2, min(args.steps, 5))):
+            for i in range(n_prof):
                 hot_path(dev_x[i % n_in])
             rec = ops.prof_end()
-        net.engine().multi_stream = True
+        for m in wl.nets:
+            m.engine().multi_stream = True
         agg, detail = {}, {}
         for label, work, ms in rec:
             a = agg.setdefault(label.split('|')[0], [0.0, 0.0, 0])
@@ -409,52 +683,50 @@ def run_gpu(args, rank, world, local_rank):
         tc = agg.get('conv_tc')
         if tc:
             tflops = tc[0] / (tc[1] * 1e-3) / 1e12
+            traffic, traffic_src = conv_traffic() if wl.key == 'vgg320' else (None, 'captured for the default workload only')
             roof = {'kernel': 'tcgen05 implicit-GEMM conv family (conv_stem_pair_kernel = conv1_1+conv1_2 fused, conv_halo_kernel, '
                               'conv_halo_stream_kernel, conv_tc_kernel): all conv launches of the step, algorithmic FLOPs / summed '
                               'CUDA-event time', 'bound': 'tensor',
                     'achieved': tflops, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                    'frac': tflops / pk['bf16_tflops_sustained'], 'traffic': conv_traffic(),
+                    'frac': tflops / pk['bf16_tflops_sustained'], 'traffic': traffic, 'traffic_source': traffic_src,
                     'peak_source': pk['source'] + ', sustained bf16 (kernel timed inside a long step)',
-                    'launches_per_step': tc[2] // max(2, min(args.steps, 5)),
+                    'launches_per_step': tc[2] // n_prof,
                     'avg_launch_ms': tc[1] / tc[2], 'share_of_step': tc[1] / tot_ms}
-        breakdown = {k: {'ms_per_step': v[1] / max(2, min(args.steps, 5)), 'launches': v[2] // max(2, min(args.steps, 5)),
-                         'work_per_step': v[0] / max(2, min(args.steps, 5))} for k, v in agg.items()}
+        breakdown = {k: {'ms_per_step': v[1] / n_prof, 'launches': v[2] // n_prof, 'work_per_step': v[0] / n_prof} for k, v in agg.items()}
         if 'detect' in agg:
             d = agg['detect']
             breakdown['detect']['achieved_gbs'] = d[0] / (d[1] * 1e-3) / 1e9
             breakdown['detect']['frac_of_hbm'] = breakdown['detect']['achieved_gbs'] / pk['hbm_gbs']
             if not args.no_graph:          # (the ncu launch-list runs use --no-graph: keep their tail = one step)
-                # regime T: trained-like scores -- background logit +7.7, so ~1.5 % of the (prior, class) scores pass conf_thresh --
-                # where Detect is bound by HBM traffic rather than by the IoU scan of 6 375 candidates per class (random init)
+                # Both regimes timed as CUDA-graph replays (the way the step runs Detect: a memset + two short kernels; eager
+                # launches would let the events see the host's launch overhead).
+                # regime R: the bench workload's own scores (random init: every prior passes conf_thresh for every class)
+                P = wl.priors.shape[0]
+                bytes_alg = float(BATCH * (P * (16 * 2 + NUM_CLASSES * 4) + NUM_CLASSES * TOP_K * 20) + P * 16)
+                with torch.cuda.stream(stream), torch.no_grad():
+                    a_r, l_r, c_r = wl.net_outputs(dev_x[0])
+                ms_r = graph_replay_ms(lambda: wl.det.forward(l_r, c_r, wl.priors, arm_loc_data=a_r, scale=wl.scale), stream, iters=20)
+                breakdown['detect']['random_init'] = {
+                    'ms_per_step': ms_r, 'candidates_frac': float((c_r[:, 1:] > wl.detect_kw['conf_thresh']).float().mean().item()),
+                    'achieved_gbs': bytes_alg / (ms_r * 1e-3) / 1e9, 'frac_of_hbm': bytes_alg / (ms_r * 1e-3) / 1e9 / pk['hbm_gbs'],
+                    'timing': 'CUDA-graph replay, 20 replays between two events'}
+                # regime T: trained-like scores -- background logit +7.7, so ~1.2 % of the (prior, class) scores pass
+                # conf_thresh -- where Detect is bound by HBM traffic rather than by the IoU scan of P candidates per class
                 g = torch.Generator(device='cpu').manual_seed(7)
-                logits = torch.randn(BATCH * priors.shape[0], NUM_CLASSES, generator=g)
+                logits = torch.randn(BATCH * P, NUM_CLASSES, generator=g)
                 logits[:, 0] += 7.7
                 conf_t = torch.softmax(logits, 1).to(dev)
-                loc_t = torch.randn(BATCH, priors.shape[0], 4, generator=g).to(dev)
-                arm_t = (0.5 * torch.randn(BATCH, priors.shape[0], 4, generator=g)).to(dev)
-                with torch.cuda.stream(stream), torch.no_grad():
-                    for _ in range(3):
-                        det.forward(loc_t, conf_t, priors, arm_loc_data=arm_t)
-                    ops.prof_begin()
-                    for _ in range(10):
-                        det.forward(loc_t, conf_t, priors, arm_loc_data=arm_t)
-                    rec_t = ops.prof_end()
-                ms_t = sum(r[2] for r in rec_t) / len(rec_t)
+                loc_t = torch.randn(BATCH, P, 4, generator=g).to(dev)
+                arm_t = (0.5 * torch.randn(BATCH, P, 4, generator=g)).to(dev)
+                ms_t = graph_replay_ms(lambda: wl.det.forward(loc_t, conf_t, wl.priors, arm_loc_data=arm_t, scale=wl.scale), stream, iters=20)
                 breakdown['detect']['trained_like'] = {
-                    'ms_per_step': ms_t, 'candidates_frac': float((conf_t[:, 1:] > DETECT_KW['conf_thresh']).float().mean().item()),
-                    'achieved_gbs': rec_t[0][1] / (ms_t * 1e-3) / 1e9, 'frac_of_hbm': rec_t[0][1] / (ms_t * 1e-3) / 1e9 / pk['hbm_gbs']}
+                    'ms_per_step': ms_t, 'candidates_frac': float((conf_t[:, 1:] > wl.detect_kw['conf_thresh']).float().mean().item()),
+                    'achieved_gbs': bytes_alg / (ms_t * 1e-3) / 1e9, 'frac_of_hbm': bytes_alg / (ms_t * 1e-3) / 1e9 / pk['hbm_gbs'],
+                    'algorithmic_bytes': bytes_alg, 'timing': 'CUDA-graph replay, 20 replays between two events'}
         if 'deform_head_tc' in agg:
             d = agg['deform_head_tc']
             breakdown['deform_head_tc']['achieved_tflops'] = d[0] / (d[1] * 1e-3) / 1e12
             breakdown['deform_head_tc']['frac_of_tensor_peak'] = d[0] / (d[1] * 1e-3) / 1e12 / pk['bf16_tflops_sustained']
-            # the projection GEMM of pyramid level 0 writes B*1600*34*80 bf16 projections: HBM-write bound
-            pj = [v for k, v in detail.items() if k.startswith('deform_head_tc') and '@40x40' in k and k.endswith('project')]
-            if pj:
-                ms_pj = pj[0][1] / pj[0][2]
-                wr = BATCH * 1600 * 34 * 80 * 2
-                breakdown['deform_head_tc']['projection_level0'] = {
-                    'ms': ms_pj, 'bytes_written': wr, 'achieved_write_gbs': wr / (ms_pj * 1e-3) / 1e9,
-                    'note': 'pure 278 MB memset on this B200: 3750 GB/s (profiles/probe_gemm_bound.txt); cuBLAS on the same GEMM 0.093 ms'}
     if world > 1:
         dist.barrier()
 
@@ -464,21 +736,32 @@ def run_gpu(args, rank, world, local_rank):
         e2e_v = frames / (ms_e2e * 1e-3)
         cpu = None
         if world == 1 and not args.no_cpu:
-            ref = CpuReference()
-            fps, _ = ref.run(steps=6, warmup=1, frames_per_step=2)
-            cpu = {'value': fps, 'unit': UNIT, 'cores': ref.cores, 'kind': 'port',
-                   'sample': '6 steps x 2 frames of the same workload through the oracle port (torch CPU convs on all '
-                             'cores + scalar C Detect/NMS), after 1 warm-up step'}
-        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            cpu_wl = WORKLOADS[args.config]()
+            n_cpu = max(1, (3 if wl.key == 'coco512' else 12) // cpu_wl.cpu_frames_per_step)
+            fps, _ = cpu_run(cpu_wl, steps=n_cpu, warmup=1)
+            cpu = {'value': fps, 'unit': UNIT, 'cores': os.cpu_count() or 1, 'kind': 'port',
+                   'sample': '%d steps x %d frame(s) of the same workload through the oracle port (torch CPU convs on all '
+                             'cores + scalar C Detect/NMS), after 1 warm-up step' % (n_cpu, cpu_wl.cpu_frames_per_step)}
+        h2d = int(e2e_dst[0].numel() * e2e_dst[0].element_size())
+        line = {'metric': wl.metric, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic', 'config': config_dict(world, n_fl),
+                'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+                'config': wl.describe(world, n_fl, 'u8' if use_u8 else 'fp32'),
                 'e2e': {'value': e2e_v, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
-                        'h2d_bytes_per_step': int(xs[0].numel() * 4), 'd2h_bytes_per_step': int(host_out.numel() * 4)},
+                        'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(host_out.numel() * 4),
+                        'ingest': ('uint8 frames [B,%d,%d,3] + base_transform on the device (tdrn_preprocess) inside the timed region'
+                                   % (SIZE, SIZE)) if use_u8 else 'fp32 frames [B,3,%d,%d], pre-transformed on the host' % (SIZE, SIZE)},
+                'sustained': sustained,
+                'per_rank_ms_per_step': {'device': [v / args.steps for v in per_rank_dev], 'e2e': [v / args.steps for v in per_rank_e2e]},
+                'gather': ('all_gather_into_tensor of [%d,%d,%d,5] fp32 per rank per step, asynchronous behind an event (no compute '
+                           'stream waits for it)' % (BATCH, NUM_CLASSES, TOP_K))
+                          if do_gather else ('none (single rank)' if world == 1 else 'disabled (--no-gather)'),
                 'gpu_launches': int(launches_per_step * args.steps),
                 'launches_per_step': int(launches_per_step),
                 'inflight_replay_matches_serial': inflight_ok,
                 **({'INVALID_e2e_diagnosis_skip': _DIAG_SKIP} if _DIAG_SKIP else {}),
-                'tflops_per_gpu_whole_step': GFLOP_PER_FRAME * BATCH / (ms_dev / args.steps),   # GFLOP / ms == TFLOP/s
+                **({'latency_b1': latency} if latency else {}),
+                'tflops_per_gpu_whole_step': wl.gflop_per_frame * BATCH / (ms_dev / args.steps),   # GFLOP / ms == TFLOP/s
                 'roofline': roof, 'kernel_breakdown': breakdown, 'cpu_baseline': cpu, 'clocks': clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -491,7 +774,12 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='tdrn_b200', choices=['tdrn_b200', 'reference'])
+    ap.add_argument('--config', default='vgg320', choices=sorted(WORKLOADS), help='BASELINE.json configuration (default: configs[1])')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--ingest', default='u8', choices=['u8', 'fp32'], help='what the e2e leg copies from the host: uint8 frames '
+                    '(base_transform runs on the device) or pre-transformed fp32 frames')
+    ap.add_argument('--sustain', type=float, default=2.0, help='seconds of extra device-leg replays for the `sustained` figure (0 = skip)')
+    ap.add_argument('--no-gather', action='store_true', help='N > 1: skip the end-of-step all_gather (attributes the scaling gap)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--inflight', type=int, default=2, help='steps kept in flight on separate streams / graph instances (1 = strictly serial)')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay (profiling)')

@@ -1,20 +1,20 @@
 // postprocess.cu -- two-stage box decode, per-class candidate selection, sort, greedy NMS, top-k.
 //
 // Replaces the Python loops of Detect.forward (layers/functions/detection.py:25-70: B x (C-1)
-// device->host round trips + single-core Cython NMS, utils/nms/cpu_nms.pyx:17-68) with three kernels:
+// device->host round trips + single-core Cython NMS, utils/nms/cpu_nms.pyx:17-68) with two kernels:
 //
 //   detect_front_kernel : ONE pass over [B,P,(4 + 4 + C)]: boxes[B,P,4] = decode(loc, center_size(decode(arm_loc,
 //                         priors))) (layers/box_utils.py:176-195, :16-25) and, for every (prior, class >= 1) with
 //                         score > conf_thresh (strict, detection.py:53), a 64-bit key (score bits << 32 | ~prior) appended
 //                         to the (image, class) segment's candidate list (warp-aggregated atomics).  The lists are
 //                         what everything downstream reads: no class-major copy of the scores is made.
-//   nms_warp_kernel     : segments with <= NMS_WCAP candidates (every segment of a trained detector: ~1 % of the
-//                         priors pass the threshold): one WARP per segment, four per CTA -- bitonic sort of the keys in
-//                         shared memory, greedy NMS with lane = candidate, output rows and zero fill.
-//   nms_segment_kernel  : larger segments (random-init scores: all P priors pass), one CTA per segment.  Greedy NMS
-//                         only ever consumes the highest-scoring candidates until top_k boxes are kept (SURVEY.md 8a
-//                         "Exactness note for A8"), so instead of sorting all candidates the kernel works in descending
-//                         score BATCHES:
+//   nms_segment_kernel  : one CTA per (image, class) segment, two paths:
+//     small (<= NMS_WCAP candidates -- every segment of a trained detector, ~1 % of the priors pass the threshold):
+//       sort the keys, gather the boxes once, all-pairs suppression bit matrix with the whole CTA, one warp walks the
+//       candidates in score order over the bit rows (nms_small_path);
+//     large (random-init scores: all P priors pass): greedy NMS only ever consumes the highest-scoring candidates until
+//       top_k boxes are kept (SURVEY.md 8a "Exactness note for A8"), so instead of sorting all candidates the kernel
+//       works in descending score BATCHES:
 //       1. radix-select (12/12/8/8.. bit digits, shared-memory histograms) the cut-off such that
 //          the next <= 1024 candidates in (score desc, index asc) order are selected;
 //       2. bitonic-sort that batch on the 64-bit keys in shared memory;
@@ -22,8 +22,7 @@
 //          suppression matrix resolves the chunk with warp shuffles;
 //       4. stop when top_k boxes are kept or the candidates are exhausted, else next batch.
 //     The visiting order is exactly the reference's (descending score, pinned tie rule), so the
-//     result is identical to a full sort + full scan.  (Both NMS kernels are launched over all segments; a segment
-//     that belongs to the other one costs an immediate exit.)
+//     result is identical to a full sort + full scan.
 //
 // Bit-exactness: every fp32 operation of the reference's IoU (cpu_nms.pyx:24,57-65) and of decode
 // is issued with explicit round-to-nearest intrinsics in the reference's order so that nvcc cannot
@@ -39,8 +38,7 @@ constexpr int NMS_CAP = 1024;              // candidates sorted per batch
 constexpr int NMS_KSEL = 512;              // every batch holds at least min(KSEL, remaining) candidates
 constexpr int NMS_BINS = 4096;             // histogram bins (12-bit digit)
 constexpr int NMS_CH = 32;                 // candidates per greedy chunk
-constexpr int NMS_WCAP = 512;              // largest segment nms_warp_kernel takes (one warp per segment)
-constexpr int NMS_WARPS = 4;               // segments per CTA of nms_warp_kernel
+constexpr int NMS_WCAP = 256;              // segments up to this size take the all-pairs path (nms_small_path)
 
 __device__ __forceinline__ float4 decode_box(float4 l, float4 p)
 {
@@ -167,6 +165,93 @@ __device__ __forceinline__ float box_area(float4 b)
     return __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
 }
 
+// Small segment (n <= NMS_WCAP candidates; every segment of a trained detector, where ~1 % of the priors pass the
+// threshold): no selection rounds and no serial scan of a kept list.  The CTA sorts the n keys, gathers the n boxes once,
+// computes the upper triangle of the n x n suppression matrix with all 256 threads (independent IoU tests: the latency
+// of one does not wait for the previous one), and warp 0 then walks the candidates in score order over the bit rows.
+// Same visiting order, same fp32 IoU and the same early exit at top_k as the batch path below.
+// keys [>= NMS_WCAP], scratch [>= 13 KB, 16-byte aligned], klist [>= NMS_WCAP] are shared-memory regions of the caller.
+__device__ __forceinline__ void nms_small_path(const NmsP &p, int b, int seg, int n, float *out_seg, unsigned long long *keys,
+                                               unsigned char *scratch, unsigned *klist, unsigned *s_kept)
+{
+    constexpr int MW = NMS_WCAP / 32;                               // words per matrix row
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4 *sbox = (float4 *)scratch;                               // [NMS_WCAP] boxes in NMS (pixel) units
+    float *sarea = (float *)(scratch + NMS_WCAP * 16);              // [NMS_WCAP]
+    unsigned *M = (unsigned *)(scratch + NMS_WCAP * 20);            // [NMS_WCAP][MW]: bit j of row i = candidate j (> i) overlaps i
+    const unsigned long long *cand = p.cand + (long long)seg * p.P;
+    const float4 *boxes = p.boxes + (long long)b * p.P;
+    int n_pad = 32;
+    while (n_pad < n) n_pad <<= 1;
+    const int nw = (n + 31) >> 5;
+    for (int i = tid; i < n_pad; i += NMS_THREADS) keys[i] = i < n ? cand[i] : 0ull;
+    __syncthreads();
+    for (int k = 2; k <= n_pad; k <<= 1) {                          // bitonic sort, descending (score desc, prior asc)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (n_pad >> 1); t += NMS_THREADS) {
+                const int lo_i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi_i = lo_i | j;
+                const unsigned long long a = keys[lo_i], c = keys[hi_i];
+                const bool desc = (lo_i & k) == 0;
+                if (desc ? (a < c) : (a > c)) { keys[lo_i] = c; keys[hi_i] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < n; i += NMS_THREADS) {
+        const float4 nb = boxes[(int)(0xffffffffu - (unsigned)(keys[i] & 0xffffffffull))];
+        const float4 bx = make_float4(__fmul_rn(nb.x, p.scale.x), __fmul_rn(nb.y, p.scale.y),
+                                      __fmul_rn(nb.z, p.scale.z), __fmul_rn(nb.w, p.scale.w));   // detection.py:59
+        sbox[i] = bx; sarea[i] = box_area(bx);
+    }
+    __syncthreads();
+    for (int item = tid; item < n * nw; item += NMS_THREADS) {      // item = (candidate i, word w of its row)
+        const int i = item / nw, w = item - i * nw;
+        unsigned bits = 0u;
+        if (w >= (i >> 5)) {
+            const float4 bi = sbox[i];
+            const float ai = sarea[i];
+            const int j0 = w << 5;
+#pragma unroll 4
+            for (int jj = 0; jj < 32; ++jj) {
+                const int j = j0 + jj;
+                if (j > i && j < n && iou_ge(bi, ai, sbox[j], sarea[j], p.thr_up)) bits |= 1u << jj;
+            }
+        }
+        M[i * MW + w] = bits;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned max_keep = (unsigned)p.max_keep;
+        unsigned removed = 0u, kept_n = 0u;                         // lane l holds word l of the suppressed set
+        for (int w = 0; w < nw && kept_n < max_keep; ++w) {
+            const unsigned r = __shfl_sync(0xffffffffu, removed, w);
+            const unsigned valid = (w == nw - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
+            unsigned alive = ~r & valid, keepmask = 0u;
+            while (alive && kept_n < max_keep) {                    // uniform: the lowest pending candidate of the word is kept
+                const int i = __ffs(alive) - 1;
+                keepmask |= 1u << i;
+                if (lane == 0) klist[kept_n] = (unsigned)((w << 5) + i);
+                ++kept_n;
+                alive &= ~(M[((w << 5) + i) * MW + w] | (1u << i));
+            }
+            if (lane > w && lane < nw) {                            // the kept candidates' rows knock out later words
+                for (unsigned km = keepmask; km; km &= km - 1u) removed |= M[((w << 5) + __ffs(km) - 1) * MW + lane];
+            }
+        }
+        if (lane == 0) *s_kept = kept_n;
+    }
+    __syncthreads();
+    const unsigned kept_n = *s_kept;
+    for (unsigned r = tid; r < kept_n; r += NMS_THREADS) {          // detection.py:61-63
+        const unsigned long long key = keys[klist[r]];
+        const float4 nb = boxes[(int)(0xffffffffu - (unsigned)(key & 0xffffffffull))];
+        float *o = out_seg + r * 5;
+        o[0] = key_score(key); o[1] = nb.x; o[2] = nb.y; o[3] = nb.z; o[4] = nb.w;
+    }
+    for (int i = kept_n * 5 + tid; i < p.top_k * 5; i += NMS_THREADS) out_seg[i] = 0.f;
+}
+
 // One CTA per segment.  DETECT: grid (C, B); class 0 only zero-fills.  Standalone: grid (1).
 template <bool DETECT>
 __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
@@ -174,7 +259,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *kept_s = (float *)smem_raw;                                      // DETECT: [5][kept_cap]
     __shared__ unsigned long long keys[NMS_CAP];
-    __shared__ unsigned hist[NMS_BINS];
+    __shared__ __align__(16) unsigned hist[NMS_BINS];
     __shared__ unsigned part[NMS_THREADS];
     __shared__ float4 cbox2[2][NMS_CH];      // chunk boxes / areas / source indices, double-buffered: warp 1 fetches the next
     __shared__ float carea2[2][NMS_CH];      // chunk while warp 0 resolves the current one
@@ -192,10 +277,16 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
     int n_in;
     if (DETECT) {
         cl = blockIdx.x; b = blockIdx.y;
-        if (cl == 0) return;                                       // background row: zero-filled by nms_warp_kernel
-        n_in = (int)p.cnt[b * p.C + cl];
-        if (n_in <= NMS_WCAP) return;                              // small segment: nms_warp_kernel's
         out_seg = p.out + ((long long)b * p.C + cl) * p.top_k * 5;
+        if (cl == 0) {                                             // background row stays zero (detection.py:37,52)
+            for (int i = tid; i < p.top_k * 5; i += NMS_THREADS) out_seg[i] = 0.f;
+            return;
+        }
+        n_in = (int)p.cnt[b * p.C + cl];
+        if (n_in <= NMS_WCAP) {                                    // uniform across the CTA
+            nms_small_path(p, b, b * p.C + cl, n_in, out_seg, keys, (unsigned char *)hist, part, &s_kept);
+            return;
+        }
         cand = p.cand + (long long)(b * p.C + cl) * p.P;
     } else {
         n_in = p.n;
@@ -410,77 +501,6 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
     }
 }
 
-// One WARP per (image, class) segment with at most NMS_WCAP candidates (grid = ceil(B*C / NMS_WARPS), also zero-fills the
-// background rows).  Shared memory per warp: keys[NMS_WCAP] u64, kept boxes float4[kc], kept areas float[kc] with
-// kc = min(top_k, NMS_WCAP).  Same visiting order and the same fp32 IoU as nms_segment_kernel.
-__global__ void __launch_bounds__(NMS_WARPS * 32) nms_warp_kernel(const NmsP p, int n_seg, int kc)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int seg = blockIdx.x * NMS_WARPS + warp;
-    if (seg >= n_seg) return;
-    const int b = seg / p.C, cl = seg - b * p.C;
-    const int n = cl == 0 ? 0 : (int)p.cnt[seg];
-    if (n > NMS_WCAP) return;                                       // nms_segment_kernel's
-    unsigned char *mine = smem_raw + (size_t)warp * ((size_t)NMS_WCAP * 8 + (size_t)kc * 20);
-    unsigned long long *keys = (unsigned long long *)mine;
-    float4 *kbox = (float4 *)(mine + (size_t)NMS_WCAP * 8);
-    float *kar = (float *)(kbox + kc);
-    float *out_seg = p.out + (long long)seg * p.top_k * 5;
-    const unsigned max_keep = (unsigned)p.max_keep;
-    unsigned kept_n = 0;
-    if (n > 0) {
-        const unsigned long long *cand = p.cand + (long long)seg * p.P;
-        int n_pad = 32;
-        while (n_pad < n) n_pad <<= 1;
-        for (int i = lane; i < n_pad; i += 32) keys[i] = i < n ? cand[i] : 0ull;
-        __syncwarp();
-        for (int k = 2; k <= n_pad; k <<= 1) {                      // bitonic sort, descending (score desc, prior asc)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = lane; t < (n_pad >> 1); t += 32) {
-                    const int lo_i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    const int hi_i = lo_i | j;
-                    const unsigned long long a = keys[lo_i], c = keys[hi_i];
-                    const bool desc = (lo_i & k) == 0;
-                    if (desc ? (a < c) : (a > c)) { keys[lo_i] = c; keys[hi_i] = a; }
-                }
-                __syncwarp();
-            }
-        }
-        const float4 *boxes = p.boxes + (long long)b * p.P;
-        for (int c0 = 0; c0 < n && kept_n < max_keep; c0 += 32) {
-            const bool valid = c0 + lane < n;
-            const unsigned long long key = valid ? keys[c0 + lane] : 0ull;
-            const int src = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
-            const float4 nb = valid ? boxes[src] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 bx = make_float4(__fmul_rn(nb.x, p.scale.x), __fmul_rn(nb.y, p.scale.y),
-                                          __fmul_rn(nb.z, p.scale.z), __fmul_rn(nb.w, p.scale.w));   // detection.py:59
-            const float ar = box_area(bx);
-            bool sup = !valid;
-            for (unsigned q = 0; q < kept_n; ++q)                   // lane = candidate, the kept box is a broadcast read
-                if (!sup) sup = iou_ge(kbox[q], kar[q], bx, ar, p.thr_up);
-            unsigned pending = __ballot_sync(0xffffffffu, !sup);
-            while (pending && kept_n < max_keep) {                  // uniform: the lowest pending candidate is kept
-                const int i = __ffs(pending) - 1;
-                const float4 bi = make_float4(__shfl_sync(0xffffffffu, bx.x, i), __shfl_sync(0xffffffffu, bx.y, i),
-                                              __shfl_sync(0xffffffffu, bx.z, i), __shfl_sync(0xffffffffu, bx.w, i));
-                const float ai = __shfl_sync(0xffffffffu, ar, i);
-                if (lane == i) {
-                    kbox[kept_n] = bx; kar[kept_n] = ar;
-                    float *o = out_seg + kept_n * 5;                // detection.py:61-63
-                    o[0] = key_score(key); o[1] = nb.x; o[2] = nb.y; o[3] = nb.z; o[4] = nb.w;
-                }
-                pending &= ~(1u << i);
-                const bool hit = ((pending >> lane) & 1u) && iou_ge(bi, ai, bx, ar, p.thr_up);
-                pending &= ~__ballot_sync(0xffffffffu, hit);
-                ++kept_n;
-            }
-            __syncwarp();
-        }
-    }
-    for (int i = kept_n * 5 + lane; i < p.top_k * 5; i += 32) out_seg[i] = 0.f;
-}
-
 static float thresh_up(double t)
 {
     float f = (float)t;
@@ -546,14 +566,7 @@ extern "C" int tdrn_detect(const float *loc, const float *conf, const float *pri
     p.conf_thresh = conf_thresh;
     p.scale = make_float4(scale_host[0], scale_host[1], scale_host[2], scale_host[3]);
     p.max_keep = top_k; p.kept_cap = top_k; p.thr_up = thresh_up(nms_thresh);
-    // small segments: one warp each
-    const int kc = top_k < NMS_WCAP ? top_k : NMS_WCAP;
-    const size_t wsmem = (size_t)NMS_WARPS * ((size_t)NMS_WCAP * 8 + (size_t)kc * 20);
-    if (wsmem > 48 * 1024)
-        TDRN_CUDA(cudaFuncSetAttribute(nms_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-    nms_warp_kernel<<<ceil_div(B * C, NMS_WARPS), NMS_WARPS * 32, wsmem, st>>>(p, B * C, kc);
-    TDRN_LAUNCH_CHECK();
-    // large segments: one CTA each
+    // one CTA per (image, class) segment: all-pairs path for small segments, selection batches for large ones
     const size_t smem = (size_t)top_k * 5 * sizeof(float);
     TDRN_REQUIRE(smem <= 150 * 1024, "tdrn_detect: top_k=%d exceeds the shared-memory kept-list capacity", top_k);
     if (smem > 16 * 1024)

@@ -123,3 +123,44 @@ def assert_attributed(out, ref, flipped, tol, what, max_flipped_frac=0.03):
     assert rep['n_beyond_flipped'] == rep['n_beyond'], (what, rep)
     assert rep['n_flipped'] <= max_flipped_frac * rep['rows'], (what, rep)
     return rep
+
+
+def drn_reference_bundle(sd, x, arm_loc_out, num_classes, multihead, sizes, dg=1, bn=True):
+    """Everything the bf16 end-to-end gate of a DualRefineDet-VGG needs, from ONE oracle pass on the host:
+    the oracle's outputs, the rows whose taps changed side under the product's ARM regression `arm_loc_out`, and the
+    oracle's ODM heads evaluated on its own fp32 features but WITH THE PRODUCT'S OFFSETS (`*_given`): the product is
+    held to the north_star's 2e-2 on every row against those (same sampling positions on both sides)."""
+    from oracle import model_ref as M
+    import torch.nn.functional as F
+    with torch.no_grad():
+        src = M._vgg_trunk(sd, x, bn)
+        odm = M._fpn(sd, src)
+        loc_a = [M._c(sd, 'arm_loc.%d' % k, src[k], 1, 1) for k in range(4)]
+        o1 = [M._c(sd, 'offset.%d' % k, loc_a[k]) for k in range(4)]
+        o2 = [M._c(sd, 'offset2.%d' % k, loc_a[k]) for k in range(4)] if multihead else None
+        l_ref, c_ref = odm_heads_from_offsets(sd, odm, o1, o2, num_classes, dg)
+        maps_g = arm_maps_from_flat(torch.as_tensor(arm_loc_out).float().cpu(), sizes)
+        g1 = [F.conv2d(maps_g[k], sd['offset.%d.weight' % k], sd.get('offset.%d.bias' % k)) for k in range(4)]
+        g2 = [F.conv2d(maps_g[k], sd['offset2.%d.weight' % k], sd.get('offset2.%d.bias' % k)) for k in range(4)] if multihead else None
+        l_giv, c_giv = odm_heads_from_offsets(sd, odm, g1, g2, num_classes, dg)
+    b = x.shape[0]
+    fl = [flipped_pixels(o1[k], g1[k], 3, 1, dg) | (flipped_pixels(o2[k], g2[k], 5, 2, dg) if multihead else False) for k in range(4)]
+    arm_ref = torch.cat([m.permute(0, 2, 3, 1).reshape(b, -1) for m in loc_a], 1).view(b, -1, 4)
+    return dict(arm_loc=arm_ref, offsets=o1, odm_loc=l_ref, conf=c_ref, flipped=flipped_rows(fl),
+                odm_loc_given=l_giv, conf_given=c_giv)
+
+
+def assert_bf16_gate(out, ref, flipped, tol, what, out_given=None, max_flipped_frac=0.03, slack=1.5, min_explained=0.97):
+    """The bf16 end-to-end gate on a deformable-head tensor.
+      (A) `out_given` (oracle heads fed the product's own offsets): max-norm relative error < tol on EVERY row;
+      (B) against the pure oracle: every row whose taps kept their side within slack * tol (measured: <= 2.1e-2, i.e. the
+          (A) error plus the oracle's own continuous response to the offset perturbation), at least `min_explained` of the rows
+          beyond tol have a tap that changed side of the map edge, and such rows are rare."""
+    rep = split_report(out, ref, flipped, tol)
+    if out_given is not None:
+        e = row_errors(out, out_given)
+        assert float(e.max()) < tol, (what, 'vs the oracle heads fed the product offsets', float(e.max()))
+    assert rep['max_other'] < slack * tol, (what, rep)
+    assert rep['n_beyond_flipped'] >= min_explained * rep['n_beyond'], (what, rep)
+    assert rep['n_flipped'] <= max_flipped_frac * rep['rows'], (what, rep)
+    return rep
