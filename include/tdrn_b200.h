@@ -118,6 +118,12 @@ typedef struct tdrn_conv_desc {
     int pool2x2;               /* 1: fuse the following MaxPool2d(2,2) (vgg() 'M'/'C', networks.py:141-143) into
                                   the epilogue; output is [B,Ho/2,Wo/2,Cout]. tdrn_conv2d_tc only, needs
                                   Wo % 16 == 0 and Ho % 8 == 0                                             */
+    int split3;                /* 1 (tdrn_conv2d_tc only): fp32-accurate tensor-core mode.  `in` is the SPLIT tensor
+                                  [B,H,W,2*Cin] bf16 written by tdrn_split_bf16 (per pixel: Cin high parts, then Cin low
+                                  parts, x = hi + lo to 16 mantissa bits); `weight` is packed [Cout_pad][kh*kw][3*Cin] =
+                                  (W_hi | W_lo | W_hi).  The kernel accumulates hi*W_hi + hi*W_lo + lo*W_hi in fp32
+                                  (the reference's convs are fp32, model/networks.py:136-163; the dropped lo*lo term is
+                                  2^-18 relative).  Needs Cin % 64 == 0.                                      */
 } tdrn_conv_desc;
 
 /* fp32-accurate SIMT implicit GEMM (also bf16 in/out with fp32 accumulate). bias/residual may be NULL;
@@ -170,6 +176,10 @@ int tdrn_softmax(const float *in, float *out, long long rows, int C, tdrn_stream
 
 /* NHWC (dtype) -> NCHW fp32 (to hand offset maps back in the reference layout) and the reverse. */
 int tdrn_nhwc_to_nchw_f32(const void *in, float *out, int B, int H, int W, int C, int dtype, tdrn_stream_t stream);
+
+/* fp32 NHWC activations [pixels][C] -> the split operand of the fp32-accurate tensor-core convs (tdrn_conv_desc.split3):
+   out [pixels][2*C] bf16, out[p][c] = bf16(x), out[p][C + c] = bf16(x - float(out[p][c])).  C % 8 == 0. */
+int tdrn_split_bf16(const float *in, void *out, long long pixels, int C, tdrn_stream_t stream);
 int tdrn_nchw_f32_to_nhwc(const float *in, void *out, int B, int C, int H, int W, int dtype, tdrn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ class TdrnError(RuntimeError):
 class ConvDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in
                 ('B', 'H', 'W', 'Cin', 'Cout', 'kh', 'kw', 'stride', 'pad', 'dil', 'relu', 'deconv2x2', 'dg',
-                 'in_dtype', 'out_dtype')] + [('out_sb', ctypes.c_longlong), ('out_sp', ctypes.c_longlong), ('in_sb', ctypes.c_longlong), ('pool2x2', ctypes.c_int)]
+                 'in_dtype', 'out_dtype')] + [('out_sb', ctypes.c_longlong), ('out_sp', ctypes.c_longlong), ('in_sb', ctypes.c_longlong), ('pool2x2', ctypes.c_int), ('split3', ctypes.c_int)]
 
 
 class DeformHeadDesc(ctypes.Structure):
@@ -33,7 +33,7 @@ EXPORTS = [
     'tdrn_last_error', 'tdrn_version', 'tdrn_launch_count', 'tdrn_prior_box', 'tdrn_deform_conv_forward',
     'tdrn_nms_workspace_bytes', 'tdrn_nms', 'tdrn_nms_host', 'tdrn_decode', 'tdrn_detect_workspace_bytes',
     'tdrn_detect', 'tdrn_conv2d', 'tdrn_conv2d_tc', 'tdrn_dwconv3x3', 'tdrn_conv_first', 'tdrn_conv_stem_pair', 'tdrn_maxpool2x2',
-    'tdrn_l2norm', 'tdrn_l2norm_pool2x2', 'tdrn_softmax', 'tdrn_nhwc_to_nchw_f32', 'tdrn_nchw_f32_to_nhwc', 'tdrn_deform_head', 'tdrn_deform_head_sample', 'tdrn_collect_workspace_bytes', 'tdrn_collect_detections', 'tdrn_preprocess', 'tdrn_multiscale_vote_workspace_bytes', 'tdrn_multiscale_vote',
+    'tdrn_l2norm', 'tdrn_l2norm_pool2x2', 'tdrn_softmax', 'tdrn_nhwc_to_nchw_f32', 'tdrn_nchw_f32_to_nhwc', 'tdrn_split_bf16', 'tdrn_deform_head', 'tdrn_deform_head_sample', 'tdrn_collect_workspace_bytes', 'tdrn_collect_detections', 'tdrn_preprocess', 'tdrn_multiscale_vote_workspace_bytes', 'tdrn_multiscale_vote',
 ]
 
 

@@ -77,6 +77,9 @@ struct TcConvP {
                                  // region and stay there across consecutive M tiles (CTAs walk contiguous tile ranges); the rest
     int a_stages;                // of the 192 KB is a ring of a_stages activation boxes (16 KB each)
     uint32_t b_bytes;            // bytes one B box deposits (min(BN, n_pad16)*128)
+    int split_cb;                // > 0: fp32-accurate mode (tdrn_conv_desc.split3) with split_cb real channel blocks: the K loop runs
+                                 // over 3*split_cb blocks per tap -- (hi, W_hi), (hi, W_lo), (lo, W_hi) -- and the activation
+                                 // tensor holds [hi | lo], so A block cb is read at channel block (cb < 2*split_cb ? cb % split_cb : cb - split_cb)
     const float *bias; const void *res; void *out;
     long long out_sb, out_sp; int out_w;
     int relu, deconv, out_f32, pool;
@@ -203,11 +206,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     uint8_t *sb = RES ? tiles + kb * Cfg::B_BYTES : sa + MT * Cfg::A_BYTES;
                     const int tap = kb / cblocks, cb = kb - tap * cblocks;
                     const int tr = tap / p.kw, ts = tap - tr * p.kw;
+                    const int a_cb = p.split_cb ? (cb < 2 * p.split_cb ? cb % p.split_cb : cb - p.split_cb) : cb;
                     mbar_expect_tx(&full_bar[s], a_bytes + (load_b ? p.b_bytes : 0u));
 #pragma unroll
                     for (int sub = 0; sub < MT; ++sub)
                         if (have[sub])
-                            tma_load_4d(sa + sub * Cfg::A_BYTES, mapA[sub], &full_bar[s], cb * 64, w0[sub] + ts * p.dil,
+                            tma_load_4d(sa + sub * Cfg::A_BYTES, mapA[sub], &full_bar[s], a_cb * 64, w0[sub] + ts * p.dil,
                                         h0[sub] + tr * p.dil, b0[sub]);
                     if (!load_b) {
                         // this stage still holds k-block kb of the same N tile
@@ -551,9 +555,10 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
                   d->in_dtype, d->Cin, d->stride, d->dg);
         return TDRN_EUNSUPPORTED;
     }
+    TDRN_REQUIRE(!d->split3 || d->Cin % 64 == 0, "tdrn_conv2d_tc: split3 needs Cin %% 64 == 0 (got %d)", d->Cin);
     {   // narrow high-resolution 3x3 layers: halo tile + resident weights (conv_halo_tc.cu)
         static const bool no_halo = getenv("TDRN_NO_HALO") != nullptr;
-        if (!no_halo) {
+        if (!no_halo && !d->split3) {
             const int rc = conv_halo_try(d, in, weight, bias, residual, out, as_stream(stream));
             if (rc != TDRN_EUNSUPPORTED) return rc;
         }
@@ -567,6 +572,8 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     TDRN_REQUIRE(p.H > 0 && p.W > 0, "convolution input is too small (output would be %dx%d)", p.H, p.W);
     // p.Cin is padded to 64: the k-block count and the weight K use it, the activation tensor map uses the real Cin
     p.B = d->B; p.Cin = (d->Cin + 63) & ~63; p.Cout = d->Cout; p.n_total = d->deconv2x2 ? 4 * d->Cout : d->Cout;
+    const int cin_mem = d->split3 ? 2 * d->Cin : d->Cin;        // channels of the activation tensor in memory ([hi | lo] when split)
+    if (d->split3) { p.split_cb = d->Cin >> 6; p.Cin = 3 * d->Cin; }
     p.kw = kw; p.taps = kh * kw; p.pad = pad; p.dil = dil; p.stride = stride;
     p.bias = bias; p.res = residual; p.out = out;
     p.out_sb = d->out_sb; p.out_sp = d->out_sp;
@@ -621,8 +628,8 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     CUtensorMap tmA, tmA2, tmB;
     bool use_cluster = false;
     {
-        const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
-        const uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+        const uint64_t dims[4] = {(uint64_t)cin_mem, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        const uint64_t str[3] = {(uint64_t)cin_mem * 2, (uint64_t)d->W * cin_mem * 2, (uint64_t)d->H * d->W * cin_mem * 2};
         // with element stride s TMA loads ceil(box / s) elements: box = n * s loads exactly n
         const uint32_t box[4] = {64, (uint32_t)(p.bw * stride), (uint32_t)(p.bh * stride), (uint32_t)p.bn};
         const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};

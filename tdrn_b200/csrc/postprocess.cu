@@ -99,22 +99,38 @@ __global__ void __launch_bounds__(256) detect_front_kernel(const float4 *__restr
         boxes[(long long)b * P + p] = decode_box(loc[(long long)b * P + p], prior);
     }
     if (!conf) return;
+    // Candidate compaction with ONE global atomic per (CTA, class): pass 1 counts the CTA's candidates of every class in
+    // shared memory, the first C-1 threads then reserve the CTA's range in every segment list at once (one round trip to
+    // L2 for the whole CTA), pass 2 repeats the ballots and writes the keys at range base + rank inside the CTA.
+    unsigned *s_cnt = (unsigned *)(s_conf + DEC_TP * C);   // [C] candidates of class cl in this tile
+    unsigned *s_pos = s_cnt + C;                           // [C] running rank inside the CTA (pass 2)
+    unsigned *s_base = s_pos + C;                          // [C] start of the CTA's range in the segment list
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_cnt[i] = 0u;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     // item i = (class cl, prior pl) with the prior fastest: a warp looks at 32 consecutive priors of one class
-    // (DEC_TP is a multiple of 32 and np is padded up to it, so a warp never straddles two classes)
+    // (DEC_TP is a multiple of 32 and the tile is padded up to it, so a warp never straddles two classes)
+    for (int i = threadIdx.x; i < DEC_TP * (C - 1); i += blockDim.x) {
+        const int cl = 1 + i / DEC_TP, pl = i - (cl - 1) * DEC_TP;
+        const bool take = pl < np && s_conf[pl * C + cl] > conf_thresh;    // strict fp32 compare, detection.py:53
+        const unsigned ballot = __ballot_sync(0xffffffffu, take);
+        if (lane == 0 && ballot) atomicAdd(&s_cnt[cl], (unsigned)__popc(ballot));
+    }
+    __syncthreads();
+    for (int cl = 1 + threadIdx.x; cl < C; cl += blockDim.x)
+        s_base[cl] = s_cnt[cl] ? atomicAdd(&cnt[b * C + cl], s_cnt[cl]) : 0u;
+    __syncthreads();
     for (int i = threadIdx.x; i < DEC_TP * (C - 1); i += blockDim.x) {
         const int cl = 1 + i / DEC_TP, pl = i - (cl - 1) * DEC_TP;
         const float sc = pl < np ? s_conf[pl * C + cl] : 0.f;
-        const bool take = pl < np && sc > conf_thresh;                     // strict fp32 compare, detection.py:53
+        const bool take = pl < np && sc > conf_thresh;
         const unsigned ballot = __ballot_sync(0xffffffffu, take);
         if (ballot == 0u) continue;                                        // warp-uniform
-        const int seg = b * C + cl;
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&cnt[seg], (unsigned)__popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, 0);
+        unsigned off = 0;
+        if (lane == 0) off = atomicAdd(&s_pos[cl], (unsigned)__popc(ballot));
+        off = __shfl_sync(0xffffffffu, off, 0);
         if (take)
-            cand[(long long)seg * P + base + __popc(ballot & ((1u << lane) - 1u))] =
+            cand[(long long)(b * C + cl) * P + s_base[cl] + off + __popc(ballot & ((1u << lane) - 1u))] =
                 ((unsigned long long)score_key(sc) << 32) | (unsigned)(0xffffffffu - (unsigned)(p0 + pl));
     }
 }
@@ -551,7 +567,7 @@ extern "C" int tdrn_detect(const float *loc, const float *conf, const float *pri
     w += align_up((size_t)B * C * sizeof(unsigned), 256);
     unsigned long long *cand = (unsigned long long *)w;
 
-    const size_t dec_smem = (size_t)DEC_TP * C * sizeof(float);
+    const size_t dec_smem = (size_t)DEC_TP * C * sizeof(float) + 3 * (size_t)C * sizeof(unsigned);
     TDRN_REQUIRE(dec_smem <= 200 * 1024, "tdrn_detect: too many classes (%d)", C);
     if (dec_smem > 48 * 1024)
         TDRN_CUDA(cudaFuncSetAttribute(detect_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));

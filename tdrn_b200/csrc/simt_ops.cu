@@ -713,3 +713,39 @@ extern "C" int tdrn_nchw_f32_to_nhwc(const float *in, void *out, int B, int C, i
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 -> (hi | lo) bf16 split: the A operand of the fp32-accurate tensor-core convs (conv_tc.cu, split3).
+// One thread = 8 channels of one pixel: two float4 loads, one 16-byte store of the high parts at [p][c0..], one of
+// the low parts at [p][C + c0..].
+// ---------------------------------------------------------------------------------------------------------
+namespace tdrn {
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float4 *__restrict__ in, uint4 *__restrict__ out, long long pixels, int C8)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pixels * C8) return;
+    const long long p = i / C8;
+    const int c8 = (int)(i - p * C8);
+    const float4 a = in[2 * i], b = in[2 * i + 1];
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 hi, lo;
+    __nv_bfloat162 *h2 = (__nv_bfloat162 *)&hi, *l2 = (__nv_bfloat162 *)&lo;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+        h2[j] = __halves2bfloat162(h0, h1);
+        l2[j] = __floats2bfloat162_rn(__fsub_rn(v[2 * j], __bfloat162float(h0)), __fsub_rn(v[2 * j + 1], __bfloat162float(h1)));
+    }
+    out[p * (2 * C8) + c8] = hi;
+    out[p * (2 * C8) + C8 + c8] = lo;
+}
+}  // namespace tdrn
+
+extern "C" int tdrn_split_bf16(const float *in, void *out, long long pixels, int C, tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(in && out && pixels > 0 && C > 0 && C % 8 == 0, "tdrn_split_bf16: bad argument (C %% 8 == 0 required, got %d)", C);
+    const long long n = pixels * (C / 8);
+    tdrn::split_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, tdrn::as_stream(stream)>>>((const float4 *)in, (uint4 *)out, pixels, C / 8);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}

@@ -40,6 +40,10 @@ class Engine(object):
         self.precision = precision
         self.act = torch.bfloat16 if precision == 'bf16' else torch.float32
         self.use_tc = precision == 'bf16' and os.environ.get('TDRN_DISABLE_TC', '0') != '1'
+        # fp32 path: dense convs with Cin % 64 == 0 run on the tensor cores too, as three bf16 products per fp32 product
+        # (x = hi + lo, w = hi + lo; hi*hi + hi*lo + lo*hi with fp32 accumulation: 16 mantissa bits per operand, 1-2e-5
+        # relative on the detector outputs against the 1e-4 bar); TDRN_FP32_SIMT=1 keeps every conv on the CUDA cores
+        self.use_x3 = precision == 'fp32' and os.environ.get('TDRN_FP32_SIMT', '0') != '1'
         self.sd = {k: v for k, v in module.state_dict().items()}
         p = next(module.parameters())
         if not p.is_cuda:
@@ -61,7 +65,7 @@ class Engine(object):
         if pc is None:
             pc = ops.PackedConv(self.sd[name + '.weight'], self.sd.get(name + '.bias'),
                                 self._bn(bn) if bn else None, stride, pad, dil, deconv, self.device,
-                                want_bf16=self.precision == 'bf16')
+                                want_bf16=self.precision == 'bf16', want_x3=self.use_x3)
             self.pk[name] = pc
         return pc
 
@@ -142,6 +146,22 @@ class Engine(object):
         use_tc = (self.use_tc and pc.w_bf16 is not None and x.dtype == torch.bfloat16
                   and not kw.get('dg') and kw.get('in_shape') is None and (stride in (1, 2) or deconv))
         ceil_mode = kw.pop('ceil_mode', False)
+        if (self.use_x3 and pc.w_x3 is not None and x.dtype == torch.float32 and not kw.get('dg') and kw.get('in_shape') is None
+                and (stride in (1, 2) or deconv)):
+            xs = getattr(x, '_tdrn_split', None)              # one split per activation tensor, shared by all its consumers
+            if xs is None:
+                xs = ops.split_bf16(x)
+                try:
+                    x._tdrn_split = xs
+                except Exception:
+                    pass
+            kw.setdefault('out_dtype', torch.float32)
+            if kw.pop('pool', False):
+                H, W = x.shape[1], x.shape[2]
+                if stride == 1 and 2 * pad == dil * (pc.kh - 1) and W % 16 == 0 and H % 8 == 0:
+                    return ops.conv2d(xs, pc, relu=relu, use_tc=True, pool=True, split3=True, **kw)
+                return ops.maxpool2x2(ops.conv2d(xs, pc, relu=relu, use_tc=True, split3=True, **kw), ceil_mode)
+            return ops.conv2d(xs, pc, relu=relu, use_tc=True, split3=True, **kw)
         if kw.pop('pool', False):
             # MaxPool2d(2,2) after the conv: fused into the tcgen05 epilogue when the map tiles as 16x8 boxes
             H, W = x.shape[1], x.shape[2]

@@ -74,11 +74,12 @@ class PackedConv(object):
 
     w_f32  [kh*kw*Cin, Cout] fp32 (tap-major, then cin)      -> tdrn_conv2d (SIMT, fp32 accumulate)
     w_bf16 [Cout_pad, kh*kw*Cin_pad] bf16, K-major           -> tdrn_conv2d_tc (tcgen05); Cin_pad = Cin up to 64
+    w_x3   [Cout_pad, kh*kw*3*Cin] bf16 (W_hi | W_lo | W_hi)  -> tdrn_conv2d_tc with split3 (fp32-accurate tensor-core path)
     deconv (ConvTranspose2d k2 s2, weight [Cin,Cout,2,2]): w_f32 [Cin, 4*Cout] with n = (i*2+j)*Cout+co
     """
 
     def __init__(self, weight, bias=None, bn=None, stride=1, pad=0, dil=1, deconv=False, device='cuda',
-                 want_bf16=True):
+                 want_bf16=True, want_x3=False):
         w = weight.detach().double().cpu()
         b = bias.detach().double().cpu() if bias is not None else None
         self.deconv = deconv
@@ -101,6 +102,19 @@ class PackedConv(object):
             wk = w.permute(0, 2, 3, 1).reshape(self.cout, self.kh * self.kw * self.cin)
         self.bias = b.float().contiguous().to(device) if b is not None else None
         self.w_bf16 = None
+        self.w_x3 = None
+        if want_x3 and self.cin % 64 == 0:
+            # fp32-accurate tensor-core mode (tdrn_conv_desc.split3): [rows_pad][taps][W_hi | W_lo | W_hi] bf16, where the fp32
+            # weight (BN folded in float64, rounded to fp32 like the reference's parameters) is hi + lo to 16 mantissa bits
+            rows = wk.shape[0]
+            rows_pad = (rows + 15) // 16 * 16
+            taps = wk.shape[1] // self.cin
+            w32 = wk.float().reshape(rows, taps, self.cin)
+            hi = w32.to(torch.bfloat16)
+            lo = (w32 - hi.float()).to(torch.bfloat16)
+            wp = torch.zeros(rows_pad, taps, 3 * self.cin, dtype=torch.bfloat16)
+            wp[:rows] = torch.cat([hi, lo, hi], 2)
+            self.w_x3 = wp.reshape(rows_pad, taps * 3 * self.cin).contiguous().to(device)
         if want_bf16 and self.cin % 8 == 0 and self.cin >= 16:
             rows = wk.shape[0]
             rows_pad = (rows + 15) // 16 * 16
@@ -111,8 +125,19 @@ class PackedConv(object):
             self.w_bf16 = wp.reshape(rows_pad, taps * cin_pad).to(torch.bfloat16).contiguous().to(device)
 
 
+def split_bf16(x_nhwc):
+    """fp32 NHWC [B,H,W,C] -> the split operand [B,H,W,2C] bf16 (hi | lo) of the fp32-accurate tensor-core convs."""
+    x = _cuda(x_nhwc, 'input')
+    assert x.dtype == torch.float32
+    C = x.shape[-1]
+    out = torch.empty(x.shape[:-1] + (2 * C,), dtype=torch.bfloat16, device=x.device)
+    with _Timed('aux|split %d' % C, float(x.numel() * 8)):
+        check(_lib.lib().tdrn_split_bf16(ptr(x), ptr(out), ctypes.c_longlong(x.numel() // C), C, stream_handle()), 'tdrn_split_bf16')
+    return out
+
+
 def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_sb=None, out_sp=None,
-           offsets=None, dg=0, use_tc=False, in_shape=None, in_sb=0, pool=False, label=None, work=None):
+           offsets=None, dg=0, use_tc=False, in_shape=None, in_sb=0, pool=False, label=None, work=None, split3=False):
     """out = act(conv(x) + bias (+ residual)).  ``out`` may be a view into a larger flat buffer, in which
     case out_sb/out_sp give the per-image and per-pixel strides (elements)."""
     if in_shape is not None:          # x is a strided view (e.g. one level of the flat [B,P,4] ARM output)
@@ -121,6 +146,8 @@ def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_
     else:
         x = _cuda(x_nhwc, 'input')
         B, H, W, Cin = x.shape
+        if split3:
+            Cin //= 2                                # x is the split tensor [B,H,W,2*Cin]
     assert Cin == pc.cin, (Cin, pc.cin)
     if pc.deconv:
         Ho, Wo = 2 * H, 2 * W
@@ -134,14 +161,16 @@ def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_
         out_sb, out_sp = Hs * Ws * pc.cout, pc.cout
     d = ConvDesc(B=B, H=H, W=W, Cin=Cin, Cout=pc.cout, kh=pc.kh, kw=pc.kw, stride=pc.stride, pad=pc.pad,
                  dil=pc.dil, relu=int(relu), deconv2x2=int(pc.deconv), dg=dg, in_dtype=_dt(x),
-                 out_dtype=_dt(out), out_sb=out_sb, out_sp=out_sp, in_sb=in_sb, pool2x2=int(pool))
+                 out_dtype=_dt(out), out_sb=out_sb, out_sp=out_sp, in_sb=in_sb, pool2x2=int(pool), split3=int(split3))
     L = _lib.lib()
     flops = 2.0 * B * (H * W * 4 if pc.deconv else Ho * Wo * pc.kh * pc.kw) * Cin * pc.cout if work is None else work
     if use_tc:
-        if pc.w_bf16 is None or x.dtype != torch.bfloat16 or dg:
+        wt = pc.w_x3 if split3 else pc.w_bf16
+        if wt is None or x.dtype != torch.bfloat16 or dg:
             raise _lib.TdrnError('tcgen05 conv needs bf16 input, Cin %% 64 == 0 and no offsets')
-        with _Timed(label or 'conv_tc|%dx%d k%d d%d @%dx%d%s' % (Cin, pc.cout, pc.kh, pc.dil, H, W, ' deconv' if pc.deconv else ''), flops):
-            check(L.tdrn_conv2d_tc(ctypes.byref(d), ptr(x), ptr(pc.w_bf16), ptr(pc.bias), ptr(residual), ptr(out),
+        with _Timed(label or '%s|%dx%d k%d d%d @%dx%d%s' % ('conv_tc_x3' if split3 else 'conv_tc', Cin, pc.cout, pc.kh, pc.dil, H, W,
+                                                            ' deconv' if pc.deconv else ''), flops):
+            check(L.tdrn_conv2d_tc(ctypes.byref(d), ptr(x), ptr(wt), ptr(pc.bias), ptr(residual), ptr(out),
                                    stream_handle()), 'tdrn_conv2d_tc')
     else:
         with _Timed('%s|%dx%d k%d s%d @%dx%d' % ('deform_simt' if dg else 'conv_simt', Cin, pc.cout, pc.kh, pc.stride, H, W), flops):

@@ -272,3 +272,60 @@ def test_conv_stem_pair_is_bit_identical_to_the_two_kernel_path(b, h, w, pool):
         a2 = F.max_pool2d(a2, 2, 2)
     assert rel_err(_nchw(got.float()).cpu().numpy(), a2.numpy()) < 2e-2
     assert ops.conv_stem_pair(torch.randn(1, 3, 20, 12).cuda(), pc1, pc2) is None      # does not tile: caller falls back
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fp32-accurate tensor-core path (tdrn_conv_desc.split3): x = hi + lo, w = hi + lo (bf16 each),
+# hi*W_hi + hi*W_lo + lo*W_hi accumulated in fp32 on tcgen05.  Inputs here are full fp32 (NOT pre-rounded).
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('b,cin,cout,k,stride,pad,dil,h,w,relu,pool', [
+    (2, 64, 64, 3, 1, 1, 1, 32, 32, True, False),        # conv1_2 class
+    (2, 64, 64, 3, 1, 1, 1, 32, 32, True, True),         # + fused 2x2 max-pool, fp32 output
+    (1, 256, 512, 3, 1, 1, 1, 40, 40, True, False),      # conv4 class, ragged-tail tiles, 36 x 3 k-blocks
+    (3, 512, 1024, 3, 1, 6, 6, 10, 10, True, False),     # conv6: dilation 6
+    (3, 1024, 256, 1, 1, 0, 1, 10, 10, True, False),     # 1x1
+    (3, 256, 512, 3, 2, 1, 1, 10, 10, True, False),      # extras.3: stride 2
+    (2, 512, 12, 3, 1, 1, 1, 20, 20, False, False),      # ARM head: Cout = 12
+    (16, 256, 600, 1, 1, 0, 1, 40, 40, False, False),    # many tiles, several N tiles
+])
+def test_conv_tc_split3_fp32_accuracy(b, cin, cout, k, stride, pad, dil, h, w, relu, pool):
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(cin + cout + k + h)
+    x = torch.randn(b, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv2d(x.double(), wt.double(), bias.double(), stride, pad, dil)
+    if relu:
+        ref = F.relu(ref)
+    if pool:
+        ref = F.max_pool2d(ref, 2, 2)
+    pc = ops.PackedConv(wt, bias, None, stride, pad, dil, device='cuda', want_bf16=False, want_x3=True)
+    xs = ops.split_bf16(_nhwc(x).cuda())
+    hi, lo = xs[..., :cin].float(), xs[..., cin:].float()
+    assert torch.equal(hi, _nhwc(x).cuda().to(torch.bfloat16).float())
+    assert float(((hi + lo) - _nhwc(x).cuda()).abs().max()) <= 2.0 ** -16 * float(x.abs().max())   # 16 mantissa bits
+    out = ops.conv2d(xs, pc, relu=relu, out_dtype=torch.float32, use_tc=True, split3=True, pool=pool)
+    torch.cuda.synchronize()
+    assert out.dtype == torch.float32
+    # a single fp32 conv on cuDNN / oneDNN is itself ~1e-6 from the float64 result; the split costs ~1e-5
+    assert rel_err(_nchw(out).cpu().numpy(), ref.numpy()) < 2e-5
+    # same layer through plain bf16 operands: two orders of magnitude further away (the test would notice a missing lo term)
+    pc16 = ops.PackedConv(wt, bias, None, stride, pad, dil, device='cuda')
+    out16 = ops.conv2d(_nhwc(x).cuda().to(torch.bfloat16), pc16, relu=relu, out_dtype=torch.float32, use_tc=True, pool=pool)
+    assert rel_err(_nchw(out16).cpu().numpy(), ref.numpy()) > 2e-4
+
+
+def test_conv_tc_split3_deconv_residual():
+    """ConvTranspose2d k2 s2 + residual + ReLU (`relu(up(x) + t)`, dualrefinedet_vggbn.py:177) on the fp32-accurate path."""
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    B, C, H, W = 3, 256, 10, 10
+    x = torch.randn(B, C, H, W, generator=g)
+    wt = torch.randn(C, C, 2, 2, generator=g) * 0.05
+    bias = torch.randn(C, generator=g) * 0.1
+    t = torch.randn(B, C, 2 * H, 2 * W, generator=g)
+    ref = F.relu(F.conv_transpose2d(x.double(), wt.double(), bias.double(), 2, 0) + t.double())
+    pc = ops.PackedConv(wt, bias, None, deconv=True, device='cuda', want_bf16=False, want_x3=True)
+    out = ops.conv2d(ops.split_bf16(_nhwc(x).cuda()), pc, relu=True, residual=_nhwc(t).cuda(), out_dtype=torch.float32,
+                     use_tc=True, split3=True)
+    assert rel_err(_nchw(out).cpu().numpy(), ref.numpy()) < 2e-5
