@@ -74,6 +74,14 @@ int tdrn_nms(const float *dets, int n, double thresh, int max_keep, int *keep, i
              void *workspace, size_t workspace_bytes, tdrn_stream_t stream);
 int tdrn_nms_host(int *keep_out_host, int *num_out_host, const float *dets_host, int boxes_num,
                   int boxes_dim, double thresh, int device_id);
+/* The same two entry points with the suppression rule explicit.  rule 0: `ovr >= thresh`, threshold compared as a double
+   (utils/nms/cpu_nms.pyx:65: what Detect and nms(..., force_cpu=True) run); rule 1: `ovr > (float)thresh` (the reference's
+   GPU kernel, utils/nms/nms_kernel.cu:71: what nms(dets, thresh) runs with the default force_cpu=False).  The two differ
+   only for a pair whose IoU equals the threshold exactly. */
+int tdrn_nms_rule(const float *dets, int n, double thresh, int rule, int max_keep, int *keep, int *num_keep,
+                  void *workspace, size_t workspace_bytes, tdrn_stream_t stream);
+int tdrn_nms_host_rule(int *keep_out_host, int *num_out_host, const float *dets_host, int boxes_num,
+                       int boxes_dim, double thresh, int device_id, int rule);
 
 /* ------------------------------------------------------------------------------------------
  * A6  decode / center_size   layers/box_utils.py:176-195, :16-25 as applied by

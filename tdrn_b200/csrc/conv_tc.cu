@@ -106,7 +106,13 @@ constexpr int TC_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 e
 // (64 instead of 94 operand bytes per MMA cycle from L2, as in conv_halo_stream_kernel); the two accumulators fill TMEM, so
 // the epilogue of a unit is not overlapped with the next unit's main loop -- worth it for the long-K 3x3 layers on the
 // 40x40 / 20x20 maps (conv4_x, conv5_x, TCB), which are bound by operand delivery.  TMA-store epilogue only.
-template <int BN, int CL, bool RES, int MT>
+// SPLIT (fp32-accurate mode, tdrn_conv_desc.split3): the tensor core adds every K = 16 step into the fp32 accumulator with
+// truncation, so an accumulator that takes all 3 * K/16 steps of a long-K layer drifts by ~1e-5 per layer (measured: 1.3e-4
+// over the 17 stacked layers, above the 1e-4 bar).  The big products (hi * W_hi) are therefore spread round-robin over
+// NACC = 512 / BN - 1 accumulators (3 at BN = 128, 7 at BN = 64: each takes 1/NACC of the steps), the two small products
+// (hi * W_lo, lo * W_hi: 2^-8 of the magnitude, their truncation does not matter) share one more, and the epilogue adds the
+// accumulators in fp32 registers.  All 512 TMEM columns belong to one tile: no accumulator double-buffering in this mode.
+template <int BN, int CL, bool RES, int MT, bool SPLIT = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmA2,
                                                                 const __grid_constant__ CUtensorMap tmB,
@@ -114,8 +120,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap tmO2, const TcConvP p)
 {
     static_assert(MT == 1 || (CL == 1 && !RES), "two-M-tile units: single CTA, streamed weights");
+    static_assert(!SPLIT || (BN <= 128 && CL == 1 && !RES && MT == 1), "split mode: BN <= 128, single CTA, streamed weights");
     using Cfg = TcCfg<BN, MT>;
-    constexpr uint32_t NBUF = MT == 2 ? 1u : 2u;           // accumulator buffers a unit alternates between
+    constexpr uint32_t NBUF = (MT == 2 || SPLIT) ? 1u : 2u;           // accumulator buffers a unit alternates between
+    constexpr int NACC = SPLIT ? 512 / BN - 1 : 1;                    // split mode: accumulators of the hi * W_hi products
+    constexpr int TMEM_COLS = SPLIT ? 512 : Cfg::TMEM_COLS;
     extern __shared__ uint8_t smem_dyn[];
     constexpr int MAX_STAGES = Cfg::STAGES > 8 ? Cfg::STAGES : 8;
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -155,7 +164,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
+    if (warp == 1) tmem_alloc(&tmem_base_s, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     if (CL == 2) cluster_sync_all();          // the peer's barriers are initialised before anything is multicast at them
@@ -240,15 +249,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
                 const bool have1 = MT == 2 && (tile % m_units) * 2 + 1 < p.m_tiles;
+                uint32_t hh = 0, touched = 0;        // split mode: running count of hi * W_hi blocks, accumulators already written
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(a_base + s * a_stride);
                     const uint64_t adesc = umma_desc_sw128(sa);
                     const uint64_t bdesc = umma_desc_sw128(RES ? smem_u32(tiles + kb * Cfg::B_BYTES) : sa + MT * Cfg::A_BYTES);
+                    uint32_t d_acc = d_tmem, fresh = kb == 0 ? 1u : 0u;
+                    if (SPLIT) {
+                        const int cb = kb % cblocks;                          // block inside the tap: [hi*W_hi | hi*W_lo | lo*W_hi]
+                        const uint32_t a = cb < p.split_cb ? (hh++ % (uint32_t)NACC) : (uint32_t)NACC;
+                        d_acc = tmem_base + a * BN;
+                        fresh = ((touched >> a) & 1u) ^ 1u;
+                        touched |= 1u << a;
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; ++k)      // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle atom
-                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                        umma_bf16(d_acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (fresh == 0u) || k != 0);
                     if (have1) {                     // second M tile of the unit: same weight box, accumulator in the upper columns
                         const uint64_t adesc1 = umma_desc_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
@@ -366,8 +384,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 rn[0] = rp[0]; rn[1] = rp[1];
             };
             prefetch_res(half * 16);
-            const uint32_t buf = tcount & 1u;
-            mbar_wait(&tmem_full_bar[buf], (tcount >> 1) & 1u);
+            const uint32_t buf = tcount % NBUF;
+            mbar_wait(&tmem_full_bar[buf], (tcount / NBUF) & 1u);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
             for (int c0 = half * 16; c0 < n_eff; c0 += 32) {
@@ -375,6 +393,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 prefetch_res(c0 + 32);
                 float v[16];
                 tmem_ld16(trow + (uint32_t)c0, v);
+                if (SPLIT) {                                         // + the other hi * W_hi accumulators in use + the small-product one
+                    const int n_hh = p.taps * p.split_cb;
+                    const int used = n_hh < NACC ? n_hh : NACC;
+                    for (int a = 1; a <= NACC; ++a) {
+                        if (a >= used && a != NACC) continue;
+                        float u[16];
+                        tmem_ld16(trow + (uint32_t)(a * BN + c0), u);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += u[j];
+                    }
+                }
                 const int n = n0 + c0;
                 if (n >= p.n_total) continue;                       // warp-uniform
                 const int co = p.deconv ? n % p.Cout : n;
@@ -452,7 +481,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     tc_fence_before();
     __syncthreads();
     if (CL == 2) cluster_sync_all();          // no CTA leaves while its peer can still signal its barriers
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // Pick the A box (bw, bh, bn), bw*bh*bn <= 128, maximising useful rows; bn > 1 only when one image's
@@ -521,6 +550,14 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmA2, const CUte
     }
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < g_num_sms ? total : g_num_sms;
+    if constexpr (BN <= 128) {
+        if (p.split_cb) {
+            TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+            conv_tc_kernel<BN, 1, false, 1, true><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+            TDRN_LAUNCH_CHECK();
+            return TDRN_OK;
+        }
+    }
     if (p.b_resident) {
         TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         conv_tc_kernel<BN, 1, true, 1><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
@@ -613,7 +650,7 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     }
 
     const int n_pad16 = (p.n_total + 15) & ~15;
-    int BN = n_pad16 > 128 ? 256 : (n_pad16 > 64 ? 128 : 64);
+    int BN = n_pad16 > 128 && !d->split3 ? 256 : (n_pad16 > 64 ? 128 : 64);     // split mode: several accumulators per tile, BN <= 128
     // Small maps (the 10x10 / 5x5 pyramid levels, M <= 3200 rows at b32) yield a handful of 128-row tiles: with the
     // widest N tile only 7..25 SMs would stream the whole weight tensor.  Narrower N tiles put 2-4x more SMs to
     // work (the A re-reads this costs are tiny at these sizes).
@@ -652,7 +689,7 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         // Measured on B200 (profiles/r01b_*): no gain -- these layers are bound by tile fill and wave quantisation, not by
         // L2->SM weight traffic -- so the cluster path is opt-in (TDRN_CLUSTER=1) and kept as a tested option.
         static const bool want_cluster = getenv("TDRN_CLUSTER") != nullptr;
-        use_cluster = want_cluster && p.m_tiles >= 2 && (b_rows % 16u) == 0;
+        use_cluster = want_cluster && !d->split3 && p.m_tiles >= 2 && (b_rows % 16u) == 0;
         const uint32_t box[2] = {64, use_cluster ? b_rows / 2 : b_rows};
         p.b_bytes = b_rows * 128u;
         int rc = make_tmap_bf16(&tmB, weight, 2, dims, str, box, nullptr);
@@ -670,13 +707,13 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         static const bool no_res = getenv("TDRN_NO_RESIDENT_B") != nullptr;
         const int num_kb = p.taps * (p.Cin >> 6);
         const int ring_boxes = (192 * 1024 - num_kb * BN * 128) / (128 * 128);
-        p.b_resident = !no_res && !use_cluster && ring_boxes >= 4 && ring_boxes >= num_kb && p.m_tiles * p.n_tiles >= 4 * g_num_sms;
+        p.b_resident = !no_res && !d->split3 && !use_cluster && ring_boxes >= 4 && ring_boxes >= num_kb && p.m_tiles * p.n_tiles >= 4 * g_num_sms;
         p.a_stages = ring_boxes < 8 ? ring_boxes : 8;
     }
     CUtensorMap tmO = tmA, tmO2 = tmA;
     {   // TMA-store epilogue: plain contiguous NHWC bf16 output (no pool / pixel shuffle / residual), 16-byte aligned rows
         static const bool no_tma_out = getenv("TDRN_NO_TMA_STORE") != nullptr;
-        p.tma_out = !no_tma_out && !d->deconv2x2 && !p.pool && !p.out_f32 && !residual && d->Cout % 8 == 0 &&
+        p.tma_out = !no_tma_out && !d->split3 && !d->deconv2x2 && !p.pool && !p.out_f32 && !residual && d->Cout % 8 == 0 &&
                     d->out_sp == d->Cout && d->out_sb == (long long)p.H * p.W * d->Cout && ((uintptr_t)out & 15) == 0;
         if (p.tma_out) {
             const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};

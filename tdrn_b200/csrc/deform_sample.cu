@@ -133,10 +133,15 @@ __global__ void __launch_bounds__(DS_MAX_WARPS * 32, 2) deform_sample_kernel(con
             const uint32_t oa = (e.x & 0x3fffffffu) + usub;
             const uint32_t dxs = (uint32_t)((int32_t)(e.x << 1) >> 31) & px_stride;
             const uint32_t oc = oa + ((uint32_t)((int32_t)e.x >> 31) & row_stride);
-            const uint4 v1 = __ldg(yb + oa);
-            const uint4 v2 = __ldg(yb + (oa + dxs));
-            const uint4 v3 = __ldg(yb + oc);
-            const uint4 v4 = __ldg(yb + (oc + dxs));
+            // a sample outside the map (deform_conv_cuda_kernel.cu:195) and the padding taps are null entries (all weights 0,
+            // hh = 1 - lh > 0 for every real one): their loads are predicated off, so that they contribute exactly 0 as in the
+            // reference even if the projection they would have pointed at (Y[0]) holds an Inf / NaN
+            const bool real = e.y != 0u;
+            const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+            const uint4 v1 = real ? __ldg(yb + oa) : zero4;
+            const uint4 v2 = real ? __ldg(yb + (oa + dxs)) : zero4;
+            const uint4 v3 = real ? __ldg(yb + oc) : zero4;
+            const uint4 v4 = real ? __ldg(yb + (oc + dxs)) : zero4;
             const float hh = __uint_as_float(e.y), lh = __uint_as_float(e.z), lw = __uint_as_float(e.w), hw = 1.f - lw;
             s_acc(acc, v1, hh * hw);                                                          // .cu:47-49
             s_acc(acc, v2, hh * lw);

@@ -594,10 +594,18 @@ extern "C" int tdrn_detect(const float *loc, const float *conf, const float *pri
 
 extern "C" size_t tdrn_nms_workspace_bytes(int n) { return align_up((size_t)(n > 0 ? n : 1) * 5 * sizeof(float), 256); }
 
-extern "C" int tdrn_nms(const float *dets, int n, double thresh, int max_keep, int *keep, int *num_keep,
-                        void *workspace, size_t workspace_bytes, tdrn_stream_t stream)
+// rule 0: suppress when ovr >= thresh, thresh compared as a double (cpu_nms.pyx:65, what Detect uses);
+// rule 1: suppress when ovr > (float)thresh (the reference's GPU kernel, nms_kernel.cu:71, what nms() runs with force_cpu=False).
+// Both become `ovr >= t` for a float t: the smallest float >= thresh, or the float after (float)thresh.
+static float rule_threshold(double thresh, int rule)
 {
-    TDRN_REQUIRE(keep && num_keep && n >= 0, "tdrn_nms: bad argument");
+    return rule == 1 ? nextafterf((float)thresh, INFINITY) : thresh_up(thresh);
+}
+
+extern "C" int tdrn_nms_rule(const float *dets, int n, double thresh, int rule, int max_keep, int *keep, int *num_keep,
+                             void *workspace, size_t workspace_bytes, tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(keep && num_keep && n >= 0 && (rule == 0 || rule == 1), "tdrn_nms: bad argument");
     cudaStream_t st = as_stream(stream);
     if (n == 0) {                                                      // nms_wrapper.py:26-27
         TDRN_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int), st));
@@ -610,17 +618,23 @@ extern "C" int tdrn_nms(const float *dets, int n, double thresh, int max_keep, i
     }
     NmsP p{};
     p.dets = dets; p.n = n; p.keep = keep; p.num_keep = num_keep; p.kept_ws = (float *)workspace;
-    p.max_keep = max_keep; p.kept_cap = n; p.thr_up = thresh_up(thresh);
+    p.max_keep = max_keep; p.kept_cap = n; p.thr_up = rule_threshold(thresh, rule);
     nms_segment_kernel<false><<<1, NMS_THREADS, 0, st>>>(p);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }
 
+extern "C" int tdrn_nms(const float *dets, int n, double thresh, int max_keep, int *keep, int *num_keep,
+                        void *workspace, size_t workspace_bytes, tdrn_stream_t stream)
+{
+    return tdrn_nms_rule(dets, n, thresh, 0, max_keep, keep, num_keep, workspace, workspace_bytes, stream);
+}
+
 // Host-pointer, synchronous variant with the argument order of the reference's `_nms`
 // (utils/nms/gpu_nms.hpp:1-2), except that the input need not be pre-sorted and the threshold rule
 // is the CPU one Detect uses.
-extern "C" int tdrn_nms_host(int *keep_out, int *num_out, const float *dets_host, int boxes_num, int boxes_dim,
-                             double thresh, int device_id)
+extern "C" int tdrn_nms_host_rule(int *keep_out, int *num_out, const float *dets_host, int boxes_num, int boxes_dim,
+                                  double thresh, int device_id, int rule)
 {
     TDRN_REQUIRE(keep_out && num_out && boxes_num >= 0, "tdrn_nms_host: bad argument");
     TDRN_REQUIRE(boxes_dim == 5, "tdrn_nms_host: boxes_dim must be 5");
@@ -640,7 +654,7 @@ extern "C" int tdrn_nms_host(int *keep_out, int *num_out, const float *dets_host
     if (rc == TDRN_OK && (e = cudaMemcpy(d_dets, dets_host, sizeof(float) * 5 * boxes_num, cudaMemcpyHostToDevice)) != cudaSuccess) {
         set_error("tdrn_nms_host: H2D failed: %s", cudaGetErrorString(e)); rc = TDRN_ECUDA;
     }
-    if (rc == TDRN_OK) rc = tdrn_nms(d_dets, boxes_num, thresh, 0, d_keep + 1, d_keep, d_ws, ws, nullptr);
+    if (rc == TDRN_OK) rc = tdrn_nms_rule(d_dets, boxes_num, thresh, rule, 0, d_keep + 1, d_keep, d_ws, ws, nullptr);
     if (rc == TDRN_OK) {
         if ((e = cudaMemcpy(num_out, d_keep, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess ||
             (e = cudaMemcpy(keep_out, d_keep + 1, sizeof(int) * (*num_out), cudaMemcpyDeviceToHost)) != cudaSuccess) {
@@ -649,4 +663,10 @@ extern "C" int tdrn_nms_host(int *keep_out, int *num_out, const float *dets_host
     }
     cudaFree(d_dets); cudaFree(d_keep); cudaFree(d_ws);
     return rc;
+}
+
+extern "C" int tdrn_nms_host(int *keep_out, int *num_out, const float *dets_host, int boxes_num, int boxes_dim,
+                             double thresh, int device_id)
+{
+    return tdrn_nms_host_rule(keep_out, num_out, dets_host, boxes_num, boxes_dim, thresh, device_id, 0);
 }

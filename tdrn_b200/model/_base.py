@@ -18,6 +18,7 @@ class DetectorBase(nn.Module):
         super(DetectorBase, self).__init__()
         self.precision = os.environ.get('TDRN_PRECISION', 'bf16')
         self._engine = None
+        self._engine_stamp = None
 
     def set_precision(self, precision):
         self.precision = precision
@@ -26,6 +27,7 @@ class DetectorBase(nn.Module):
 
     def _invalidate(self):
         self._engine = None
+        self.__dict__['_stamp_tensors'] = None
 
     def load_state_dict(self, *a, **k):
         r = super(DetectorBase, self).load_state_dict(*a, **k)
@@ -46,12 +48,49 @@ class DetectorBase(nn.Module):
         else:
             print('Sorry only .pth and .pkl files supported.')
 
+    def _param_stamp(self):
+        """(data_ptr, in-place version counter) of every parameter and buffer: changes whenever a weight is rebound or
+        written in place (``p.copy_``, ``net.apply(init)``, optimizer / EMA steps, manual BN-statistics edits).  Writes through
+        ``p.data`` bypass PyTorch's version counters and cannot be seen: call ``net.refresh()`` after those."""
+        ts = self.__dict__.get('_stamp_tensors')
+        if ts is None:                               # (the module walk is the expensive part: cached until _invalidate)
+            ts = self.__dict__['_stamp_tensors'] = list(self.parameters()) + list(self.buffers())
+        return tuple((t.data_ptr(), t._version) for t in ts)
+
+    def refresh(self):
+        """Drop the packed (BN-folded, bf16 / split) weights; they are rebuilt from the current parameters at the next call."""
+        self._invalidate()
+        return self
+
     def engine(self):
         if self.phase != 'test':
             raise NotImplementedError("tdrn_b200 implements inference only (phase='test')")
-        if self._engine is None or self._engine.precision != self.precision:
+        # The Engine holds BN-folded, re-packed copies of the weights.  They are rebuilt when the precision changes, after
+        # load_state_dict / .to(), and when any parameter or buffer was modified in place since they were packed.  (Captured
+        # CUDA graphs hold the old packed buffers: re-capture after changing weights.)
+        stamp = self._param_stamp()
+        if self._engine is None or self._engine.precision != self.precision or self._engine_stamp != stamp:
             self._engine = Engine(self, self.precision)
+            self._engine_stamp = stamp
         return self._engine
+
+    def __deepcopy__(self, memo):
+        return self._clone_without_engine(memo)
+
+    def _clone_without_engine(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == '_engine' else copy.deepcopy(v, memo)
+        return new
+
+    def _replicate_for_data_parallel(self):
+        # nn.DataParallel replicas are shallow copies: they must not share the device-0 executor
+        replica = super(DetectorBase, self)._replicate_for_data_parallel()
+        replica._engine = None
+        return replica
 
     @staticmethod
     def _check_input(x):

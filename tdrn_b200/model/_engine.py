@@ -390,7 +390,12 @@ class Engine(object):
         B = feats[0].shape[0]
         loc = torch.empty(B, P, 4, dtype=torch.float32, device=self.device)
         conf = torch.empty(B, P, num_classes, dtype=torch.float32, device=self.device)
-        fused = self.use_tc and feats[0].dtype == torch.bfloat16 and all(f.shape[3] % 64 == 0 for f in feats)
+        # tdrn_deform_head (csrc/deform_tc.cu) needs whole 64-channel blocks per deformable group and the fused loc||conf
+        # accumulator (12 + 3C columns, rounded up to 16) inside one 256-column TMEM tile; other shapes (e.g. def_groups = 8 on
+        # the 256-channel ODM maps, or more than 81 classes) take the SIMT deformable heads
+        n_out16 = (12 + 3 * num_classes + 15) // 16 * 16
+        fused = (self.use_tc and feats[0].dtype == torch.bfloat16 and n_out16 <= 256
+                 and all(f.shape[3] % 64 == 0 and (f.shape[3] // max(dg, 1)) % 64 == 0 for f in feats))
 
         # narrow head, one deformable group: project per tap on the tensor cores first, then sample the projections
         # (3.4x fewer bilinear samples at VOC-21); wide heads / dg > 1 sample into the fused im2col tile instead

@@ -32,13 +32,22 @@ def test_nms_dense_overlaps_ties_and_max_keep(golden):
     c = rng.randint(0, 5, size=3000)
     xy = c[:, None] * 60.0 + rng.rand(3000, 2) * 6
     dets = np.hstack([xy, xy + 40 + rng.rand(3000, 2) * 4, np.round(rng.rand(3000, 1), 2)]).astype(np.float32)
-    assert nms(dets, 0.45) == C.cpu_nms(dets, 0.45) == N.cpu_nms(dets, 0.45)
+    assert nms(dets, 0.45, force_cpu=True) == C.cpu_nms(dets, 0.45) == N.cpu_nms(dets, 0.45)
+    assert nms(dets, 0.45) == nms(dets, 0.45, force_cpu=True)          # no pair sits exactly on the threshold here
     # identical boxes with identical scores: only the lowest index survives
     d = np.tile(np.array([[5, 5, 50, 50, 0.5]], np.float32), (700, 1))
     assert nms(d, 0.45) == [0]
     # IoU exactly at the threshold is suppressed (>=, cpu_nms.pyx:65): boxes 0..9 and 5..14 (+1 convention) -> 5/15
     e = np.array([[0, 0, 9, 0, 0.9], [5, 0, 14, 0, 0.8]], np.float32)
-    assert nms(e, 1.0 / 3.0) == C.cpu_nms(e, 1.0 / 3.0)
+    assert nms(e, 1.0 / 3.0, force_cpu=True) == C.cpu_nms(e, 1.0 / 3.0)
+    # ... and kept by the reference's GPU rule (`>`, nms_kernel.cu:71), which nms() runs with the default force_cpu=False:
+    # IoU([0,0,9,9], [0,0,9,19]) == 0.5 exactly in fp32
+    edge = np.array([[0, 0, 9, 9, 0.9], [0, 0, 9, 19, 0.8], [100, 100, 120, 130, 0.7]], np.float32)
+    assert nms(edge, 0.5, force_cpu=True) == [0, 2] and nms(edge, 0.5) == [0, 1, 2]
+    # pinned tie rule (documented deviation, utils/nms_wrapper.py): equal scores are visited lower index first
+    tie = np.array([[0, 0, 10, 10, 0.5], [1, 1, 11, 11, 0.5], [50, 50, 60, 60, 0.5], [0, 0, 10, 10, 0.7]], np.float32)
+    assert nms(tie, 0.45) == [3, 2]                                     # box 3 (highest score) suppresses 0 and 1
+    assert nms(tie[:3], 0.45) == [0, 2] and nms(tie[:3], 0.45, force_cpu=True) == [0, 2]
     # golden from the reference's py_cpu_nms.py
     g = golden('small_cases')
     assert nms(g['nms_dets'], 0.45) == g['nms_keep_py_cpu_nms'].tolist()

@@ -93,6 +93,11 @@ def test_product_nms_matches_reference_gpu_kernel(n, thresh):
     got = nms(dets, thresh)
     ora = nms_ref.cpu_nms(dets, thresh)
     assert [int(i) for i in ref] == [int(i) for i in got] == [int(i) for i in ora]
+    # a pair exactly on the threshold: the reference's GPU kernel keeps it (`>`, nms_kernel.cu:71), and so does nms() with the
+    # default force_cpu=False; the CPU rule (`>=`) drops it
+    edge = np.array([[0, 0, 9, 9, 0.9], [0, 0, 9, 19, 0.8], [100, 100, 120, 130, 0.7]], np.float32)      # IoU(0, 1) == 0.5
+    assert [int(i) for i in ref_native.gpu_nms(edge, 0.5)] == nms(edge, 0.5) == [0, 1, 2]
+    assert nms(edge, 0.5, force_cpu=True) == [0, 2]
 
 
 @pytest.mark.parametrize('n,thresh', [(1, 0.45), (2, 0.45), (257, 0.3), (1000, 0.45), (3000, 0.6), (6375, 0.45)])
@@ -105,9 +110,9 @@ def test_product_nms_matches_reference_cython_nms(n, thresh):
         pytest.skip('oracle/_ref/cpu_nms*.so not built (needs /root/reference + Cython)')
     from tdrn_b200.utils.nms_wrapper import nms
     dets = _boxes(n, 100 + n)
-    assert [int(i) for i in nms(dets, thresh)] == [int(i) for i in mod.cpu_nms(dets, thresh)]
+    assert [int(i) for i in nms(dets, thresh, force_cpu=True)] == [int(i) for i in mod.cpu_nms(dets, thresh)]
     edge = np.array([[0, 0, 9, 9, 0.9], [0, 0, 9, 19, 0.8], [100, 100, 120, 130, 0.7]], np.float32)   # IoU(0, 1) == 0.5
-    assert [int(i) for i in nms(edge, 0.5)] == [int(i) for i in mod.cpu_nms(edge, 0.5)] == [0, 2]
+    assert [int(i) for i in nms(edge, 0.5, force_cpu=True)] == [int(i) for i in mod.cpu_nms(edge, 0.5)] == [0, 2]
 
 
 def test_deform_head_vs_the_reference_kernels_speed_and_values():
