@@ -109,7 +109,7 @@ constexpr int TC_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 e
 // SPLIT (fp32-accurate mode, tdrn_conv_desc.split3): the tensor core adds every K = 16 step into the fp32 accumulator with
 // truncation, so an accumulator that takes all 3 * K/16 steps of a long-K layer drifts by ~1e-5 per layer (measured: 1.3e-4
 // over the 17 stacked layers, above the 1e-4 bar).  The big products (hi * W_hi) are therefore spread round-robin over
-// NACC = 512 / BN - 1 accumulators (3 at BN = 128, 7 at BN = 64: each takes 1/NACC of the steps), the two small products
+// NACC = 3 accumulators (each takes a third of the steps; 3 + 1 accumulators of BN = 128 columns fill TMEM), the two small products
 // (hi * W_lo, lo * W_hi: 2^-8 of the magnitude, their truncation does not matter) share one more, and the epilogue adds the
 // accumulators in fp32 registers.  All 512 TMEM columns belong to one tile: no accumulator double-buffering in this mode.
 template <int BN, int CL, bool RES, int MT, bool SPLIT = false>
@@ -123,8 +123,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     static_assert(!SPLIT || (BN <= 128 && CL == 1 && !RES && MT == 1), "split mode: BN <= 128, single CTA, streamed weights");
     using Cfg = TcCfg<BN, MT>;
     constexpr uint32_t NBUF = (MT == 2 || SPLIT) ? 1u : 2u;           // accumulator buffers a unit alternates between
-    constexpr int NACC = SPLIT ? 512 / BN - 1 : 1;                    // split mode: accumulators of the hi * W_hi products
-    constexpr int TMEM_COLS = SPLIT ? 512 : Cfg::TMEM_COLS;
+    constexpr int NACC = SPLIT ? 3 : 1;                               // split mode: accumulators of the hi * W_hi products (the same
+                                                                      // number for every BN: results do not depend on the tile shape, i.e. on the batch size)
+    constexpr int TMEM_COLS = SPLIT ? (BN == 128 ? 512 : 256) : Cfg::TMEM_COLS;
     extern __shared__ uint8_t smem_dyn[];
     constexpr int MAX_STAGES = Cfg::STAGES > 8 ? Cfg::STAGES : 8;
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];

@@ -81,16 +81,26 @@ __global__ void __launch_bounds__(256) detect_front_kernel(const float4 *__restr
                                                            float4 *__restrict__ boxes, unsigned long long *__restrict__ cand,
                                                            unsigned *__restrict__ cnt, int P, int C, float conf_thresh)
 {
-    extern __shared__ float s_conf[];          // [DEC_TP * C]
+    extern __shared__ __align__(16) float s_raw[];  // [4 + DEC_TP * C] scores, then 3 * C counters
     const int b = blockIdx.y, p0 = blockIdx.x * DEC_TP;
     const int np = min(DEC_TP, P - p0);
+    float *s_conf = s_raw;
     if (conf) {                                // issue the score tile's loads first: the decode below overlaps them
+        // The tile starts (b * P + p0) * C floats into conf: rarely on a 16-byte boundary (C = 21).  The shared copy is placed
+        // at the SAME offset from a 16-byte boundary as the global tile, so that all but the first / last few elements move as
+        // aligned float4 (a scalar copy loop was 18 % of this kernel's stall samples and most of its instructions).
         const float *src = conf + ((long long)b * P + p0) * C;
-        if ((((uintptr_t)src) & 15) == 0 && ((np * C) & 3) == 0) {
-            for (int i = threadIdx.x; i < (np * C) >> 2; i += blockDim.x) ((float4 *)s_conf)[i] = ((const float4 *)src)[i];
-        } else {
-            for (int i = threadIdx.x; i < np * C; i += blockDim.x) s_conf[i] = src[i];
-        }
+        const int n = np * C;
+        const int k = (int)((((uintptr_t)src) >> 2) & 3);          // floats past a 16-byte boundary
+        const int head = min((4 - k) & 3, n);                      // scalar elements in front of the first aligned float4
+        s_conf = s_raw + k;
+        const int nv = (n - head) >> 2;
+        const float4 *src4 = (const float4 *)(src + head);
+        float4 *dst4 = (float4 *)(s_conf + head);
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) dst4[i] = __ldg(src4 + i);
+        if (threadIdx.x < head) s_conf[threadIdx.x] = src[threadIdx.x];
+        const int tail0 = head + 4 * nv;
+        if (threadIdx.x < n - tail0) s_conf[tail0 + threadIdx.x] = src[tail0 + threadIdx.x];
     }
     if (threadIdx.x < np) {
         const int p = p0 + threadIdx.x;
@@ -102,7 +112,7 @@ __global__ void __launch_bounds__(256) detect_front_kernel(const float4 *__restr
     // Candidate compaction with ONE global atomic per (CTA, class): pass 1 counts the CTA's candidates of every class in
     // shared memory, the first C-1 threads then reserve the CTA's range in every segment list at once (one round trip to
     // L2 for the whole CTA), pass 2 repeats the ballots and writes the keys at range base + rank inside the CTA.
-    unsigned *s_cnt = (unsigned *)(s_conf + DEC_TP * C);   // [C] candidates of class cl in this tile
+    unsigned *s_cnt = (unsigned *)(s_raw + 4 + DEC_TP * C);  // [C] candidates of class cl in this tile
     unsigned *s_pos = s_cnt + C;                           // [C] running rank inside the CTA (pass 2)
     unsigned *s_base = s_pos + C;                          // [C] start of the CTA's range in the segment list
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_cnt[i] = 0u;
@@ -197,23 +207,21 @@ __device__ __forceinline__ void nms_small_path(const NmsP &p, int b, int seg, in
     unsigned *M = (unsigned *)(scratch + NMS_WCAP * 20);            // [NMS_WCAP][MW]: bit j of row i = candidate j (> i) overlaps i
     const unsigned long long *cand = p.cand + (long long)seg * p.P;
     const float4 *boxes = p.boxes + (long long)b * p.P;
-    int n_pad = 32;
-    while (n_pad < n) n_pad <<= 1;
     const int nw = (n + 31) >> 5;
-    for (int i = tid; i < n_pad; i += NMS_THREADS) keys[i] = i < n ? cand[i] : 0ull;
+    // rank sort (n <= NMS_WCAP = NMS_THREADS): thread t owns candidate t; its position in (score desc, prior asc) order is
+    // the number of keys larger than its own (keys are distinct: they carry the prior index).  One pass of broadcast
+    // shared-memory reads and two barriers, against 28-36 barrier stages of a bitonic network.
+    unsigned long long *unsorted = keys + NMS_WCAP;                 // keys[] has NMS_CAP = 4 * NMS_WCAP slots
+    const unsigned long long mine = tid < n ? cand[tid] : 0ull;
+    if (tid < n) unsorted[tid] = mine;
     __syncthreads();
-    for (int k = 2; k <= n_pad; k <<= 1) {                          // bitonic sort, descending (score desc, prior asc)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (n_pad >> 1); t += NMS_THREADS) {
-                const int lo_i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int hi_i = lo_i | j;
-                const unsigned long long a = keys[lo_i], c = keys[hi_i];
-                const bool desc = (lo_i & k) == 0;
-                if (desc ? (a < c) : (a > c)) { keys[lo_i] = c; keys[hi_i] = a; }
-            }
-            __syncthreads();
-        }
+    if (tid < n) {
+        int rank = 0;
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) rank += unsorted[j] > mine ? 1 : 0;
+        keys[rank] = mine;
     }
+    __syncthreads();
     for (int i = tid; i < n; i += NMS_THREADS) {
         const float4 nb = boxes[(int)(0xffffffffu - (unsigned)(keys[i] & 0xffffffffull))];
         const float4 bx = make_float4(__fmul_rn(nb.x, p.scale.x), __fmul_rn(nb.y, p.scale.y),
@@ -228,11 +236,10 @@ __device__ __forceinline__ void nms_small_path(const NmsP &p, int b, int seg, in
             const float4 bi = sbox[i];
             const float ai = sarea[i];
             const int j0 = w << 5;
+            const int jlo = w == (i >> 5) ? (i & 31) + 1 : 0, jhi = min(32, n - j0);   // only candidates after i, inside the segment
 #pragma unroll 4
-            for (int jj = 0; jj < 32; ++jj) {
-                const int j = j0 + jj;
-                if (j > i && j < n && iou_ge(bi, ai, sbox[j], sarea[j], p.thr_up)) bits |= 1u << jj;
-            }
+            for (int jj = jlo; jj < jhi; ++jj)
+                if (iou_ge(bi, ai, sbox[j0 + jj], sarea[j0 + jj], p.thr_up)) bits |= 1u << jj;
         }
         M[i * MW + w] = bits;
     }
@@ -243,14 +250,15 @@ __device__ __forceinline__ void nms_small_path(const NmsP &p, int b, int seg, in
         for (int w = 0; w < nw && kept_n < max_keep; ++w) {
             const unsigned r = __shfl_sync(0xffffffffu, removed, w);
             const unsigned valid = (w == nw - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
+            const unsigned diag = M[((w << 5) + lane) * MW + w];    // lane l: which later candidates of this word overlap candidate l
             unsigned alive = ~r & valid, keepmask = 0u;
             while (alive && kept_n < max_keep) {                    // uniform: the lowest pending candidate of the word is kept
                 const int i = __ffs(alive) - 1;
                 keepmask |= 1u << i;
-                if (lane == 0) klist[kept_n] = (unsigned)((w << 5) + i);
                 ++kept_n;
-                alive &= ~(M[((w << 5) + i) * MW + w] | (1u << i));
+                alive &= ~(__shfl_sync(0xffffffffu, diag, i) | (1u << i));
             }
+            if ((keepmask >> lane) & 1u) klist[kept_n - __popc(keepmask >> lane)] = (unsigned)((w << 5) + lane);
             if (lane > w && lane < nw) {                            // the kept candidates' rows knock out later words
                 for (unsigned km = keepmask; km; km &= km - 1u) removed |= M[((w << 5) + __ffs(km) - 1) * MW + lane];
             }
@@ -270,7 +278,7 @@ __device__ __forceinline__ void nms_small_path(const NmsP &p, int b, int seg, in
 
 // One CTA per segment.  DETECT: grid (C, B); class 0 only zero-fills.  Standalone: grid (1).
 template <bool DETECT>
-__global__ void __launch_bounds__(NMS_THREADS) nms_segment_kernel(const NmsP p)
+__global__ void __launch_bounds__(NMS_THREADS, 5) nms_segment_kernel(const NmsP p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *kept_s = (float *)smem_raw;                                      // DETECT: [5][kept_cap]
@@ -567,7 +575,7 @@ extern "C" int tdrn_detect(const float *loc, const float *conf, const float *pri
     w += align_up((size_t)B * C * sizeof(unsigned), 256);
     unsigned long long *cand = (unsigned long long *)w;
 
-    const size_t dec_smem = (size_t)DEC_TP * C * sizeof(float) + 3 * (size_t)C * sizeof(unsigned);
+    const size_t dec_smem = (size_t)(4 + DEC_TP * C) * sizeof(float) + 3 * (size_t)C * sizeof(unsigned);
     TDRN_REQUIRE(dec_smem <= 200 * 1024, "tdrn_detect: too many classes (%d)", C);
     if (dec_smem > 48 * 1024)
         TDRN_CUDA(cudaFuncSetAttribute(detect_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));
@@ -587,6 +595,10 @@ extern "C" int tdrn_detect(const float *loc, const float *conf, const float *pri
     TDRN_REQUIRE(smem <= 150 * 1024, "tdrn_detect: top_k=%d exceeds the shared-memory kept-list capacity", top_k);
     if (smem > 16 * 1024)
         TDRN_CUDA(cudaFuncSetAttribute(nms_segment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {   // five 32 KB CTAs per SM (one wave for 672 segments at b32 / VOC-21) need the large shared-memory carve-out
+        static bool carve = false;
+        if (!carve) { cudaFuncSetAttribute(nms_segment_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve = true; }
+    }
     nms_segment_kernel<true><<<dim3(C, B), NMS_THREADS, smem, st>>>(p);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;

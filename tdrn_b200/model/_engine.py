@@ -43,7 +43,10 @@ class Engine(object):
         # fp32 path: dense convs with Cin % 64 == 0 run on the tensor cores too, as three bf16 products per fp32 product
         # (x = hi + lo, w = hi + lo; hi*hi + hi*lo + lo*hi with fp32 accumulation: 16 mantissa bits per operand, 1-2e-5
         # relative on the detector outputs against the 1e-4 bar); TDRN_FP32_SIMT=1 keeps every conv on the CUDA cores
-        self.use_x3 = precision == 'fp32' and os.environ.get('TDRN_FP32_SIMT', '0') != '1'
+        # (the MobileNet trunks amplify per-layer error ~3x more than VGG -- DESIGN.md section 5 -- and land at 1.4-2.9e-4 with the
+        # split products, above the 1e-4 bar: those modules set fp32_tensor_cores = False and keep the CUDA-core fp32 convs)
+        self.use_x3 = (precision == 'fp32' and os.environ.get('TDRN_FP32_SIMT', '0') != '1'
+                       and getattr(module, 'fp32_tensor_cores', True))
         self.sd = {k: v for k, v in module.state_dict().items()}
         p = next(module.parameters())
         if not p.is_cuda:

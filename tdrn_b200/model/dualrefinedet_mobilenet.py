@@ -43,6 +43,7 @@ def mobilenet_sources(E, x):
 
 
 class RefineSSD(DetectorBase):
+    fp32_tensor_cores = False      # fp32 precision keeps the CUDA-core convs on this trunk (see _engine.Engine.use_x3)
     def __init__(self, size, num_classes=21, phase='train', def_groups=1, multihead=False):
         super(RefineSSD, self).__init__()
         self.num_classes, self.size, self.phase = num_classes, size, phase

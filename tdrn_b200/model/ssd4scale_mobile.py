@@ -17,6 +17,7 @@ from .ssd4scale_vgg import SSD4ScaleBase
 
 
 class SSD4Scale_MobNet(SSD4ScaleBase):
+    fp32_tensor_cores = False      # fp32 precision keeps the CUDA-core convs on this trunk (see _engine.Engine.use_x3)
     def __init__(self, size, num_classes=21, phase='train', c7_channel=1024, deform=False):
         super(SSD4Scale_MobNet, self).__init__()
         self.num_classes, self.size, self.phase, self.deform = num_classes, size, phase, deform

@@ -166,3 +166,18 @@ def assert_bf16_gate(out, ref, flipped, tol, what, out_given=None, max_flipped_f
     assert rep['n_beyond_flipped'] >= min_explained * rep['n_beyond'], (what, rep)
     assert rep['n_flipped'] <= max_flipped_frac * rep['rows'], (what, rep)
     return rep
+
+
+def assert_fp32_gate(out, ref, flipped, tol, what, out_given=None, max_flipped_frac=2e-3):
+    """fp32 path on a deformable-head tensor.  The discontinuity of the reference's sampler at the map edge does not go
+    away with precision: among ~10^5 rows x 34..72 taps a tap can sit within the ~1e-5 that separates two fp32 evaluations
+    of the ARM regression from the edge (measured: 1 row of 30 855 at 704 x 704, a handful per TDRN clip).  So:
+      (A) against the oracle heads fed the product's own offsets: max-norm relative error < tol on EVERY row;
+      (B) against the pure oracle: < tol on every row whose taps kept their side; rows with a flipped tap <= 0.2 %."""
+    rep = split_report(out, ref, flipped, tol)
+    if out_given is not None:
+        e = row_errors(out, out_given)
+        assert float(e.max()) < tol, (what, 'vs the oracle heads fed the product offsets', float(e.max()))
+    assert rep['max_other'] < tol, (what, rep)
+    assert rep['n_flipped'] <= max(1, int(max_flipped_frac * rep['rows'])), (what, rep)
+    return rep

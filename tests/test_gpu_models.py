@@ -44,7 +44,9 @@ def check_odm_attributed(out, ref, flipped, precision, what, out_given=None, max
     regression of the size the B200 shows.  Numbers: profiles/r02_bf16_attribution.txt."""
     import parity_tools as PT
     if precision == 'fp32':
-        assert rel_err(out, ref) < TOL['fp32'], what
+        # 1e-4 on every row whose taps kept their side and, on every row, against the oracle heads fed the product's offsets
+        # (parity_tools.assert_fp32_gate: the discontinuity is there in fp32 too, it is just hit ~1000x less often)
+        PT.assert_fp32_gate(out, ref, flipped, TOL['fp32'], what, out_given=out_given)
         return
     PT.assert_bf16_gate(out, ref, flipped, TOL['bf16'], what, out_given=out_given, max_flipped_frac=max_flipped_frac)
 
@@ -142,7 +144,7 @@ def test_batch_consistency_and_oracle_b3(precision):
         out1 = net(x[1:2].cuda())
     check_drn_vgg(out, sd, x, spec_kw, precision, [(s, s) for s in (40, 20, 10, 5)])
     # frames are independent: image 1 alone == image 1 inside the batch (bit-exact, same kernels/tiles order per pixel)
-    assert rel_err(out1[2][0].cpu().numpy(), out[2][1].cpu().numpy()) < 1e-6 if precision == 'fp32' else True
+    assert torch.equal(out1[2][0], out[2][1]) and torch.equal(out1[0][0], out[0][1])
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
