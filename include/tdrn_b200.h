@@ -132,6 +132,10 @@ typedef struct tdrn_conv_desc {
                                   (W_hi | W_lo | W_hi).  The kernel accumulates hi*W_hi + hi*W_lo + lo*W_hi in fp32
                                   (the reference's convs are fp32, model/networks.py:136-163; the dropped lo*lo term is
                                   2^-18 relative).  Needs Cin % 64 == 0.                                      */
+    int split_out;             /* g > 0 (split3, bf16 out, out_sp == 2*Cout, g % 16 == 0, Cout % g == 0): the fp32 result is
+                                  written as (hi | lo) bf16 pairs in groups of g channels -- output channel n -> hi at
+                                  n + (n / g) * g, lo g further -- the projection tensor of the fp32-accurate deformable
+                                  heads (tdrn_deform_head_desc.split)                                           */
 } tdrn_conv_desc;
 
 /* fp32-accurate SIMT implicit GEMM (also bf16 in/out with fp32 accumulate). bias/residual may be NULL;
@@ -208,6 +212,9 @@ typedef struct tdrn_deform_head_desc {
     int kh2, pad2;             /* second head, kh2 == 0: absent                    */
     int P, prior_off;
     int softmax;
+    int split;                 /* tdrn_deform_head_sample only: 1 = the projections are (hi | lo) bf16 pairs,
+                                  proj [B,H,W,taps,2*g] with n_pad = 2*g, 12 + 3C <= g (fp32-accurate heads: both halves
+                                  are sampled and added in fp32 before the softmax)                             */
 } tdrn_deform_head_desc;
 
 int tdrn_deform_head(const tdrn_deform_head_desc *d, const void *feat, const float *offsets,

@@ -19,12 +19,12 @@ class TdrnError(RuntimeError):
 class ConvDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in
                 ('B', 'H', 'W', 'Cin', 'Cout', 'kh', 'kw', 'stride', 'pad', 'dil', 'relu', 'deconv2x2', 'dg',
-                 'in_dtype', 'out_dtype')] + [('out_sb', ctypes.c_longlong), ('out_sp', ctypes.c_longlong), ('in_sb', ctypes.c_longlong), ('pool2x2', ctypes.c_int), ('split3', ctypes.c_int)]
+                 'in_dtype', 'out_dtype')] + [('out_sb', ctypes.c_longlong), ('out_sp', ctypes.c_longlong), ('in_sb', ctypes.c_longlong), ('pool2x2', ctypes.c_int), ('split3', ctypes.c_int), ('split_out', ctypes.c_int)]
 
 
 class DeformHeadDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in
-                ('B', 'H', 'W', 'Cin', 'num_classes', 'dg', 'kh', 'pad', 'kh2', 'pad2', 'P', 'prior_off', 'softmax')]
+                ('B', 'H', 'W', 'Cin', 'num_classes', 'dg', 'kh', 'pad', 'kh2', 'pad2', 'P', 'prior_off', 'softmax', 'split')]
 
 
 _lib = None

@@ -77,6 +77,7 @@ struct TcConvP {
                                  // region and stay there across consecutive M tiles (CTAs walk contiguous tile ranges); the rest
     int a_stages;                // of the 192 KB is a ring of a_stages activation boxes (16 KB each)
     uint32_t b_bytes;            // bytes one B box deposits (min(BN, n_pad16)*128)
+    int split_g;                 // > 0: output written as (hi | lo) bf16 pairs in groups of split_g channels (tdrn_conv_desc.split_out)
     int split_cb;                // > 0: fp32-accurate mode (tdrn_conv_desc.split3) with split_cb real channel blocks: the K loop runs
                                  // over 3*split_cb blocks per tap -- (hi, W_hi), (hi, W_lo), (lo, W_hi) -- and the activation
                                  // tensor holds [hi | lo], so A block cb is read at channel block (cb < 2*split_cb ? cb % split_cb : cb - split_cb)
@@ -373,6 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 int co = n, oy = y, ox = x;
                 if (p.deconv) { const int ij = n / p.Cout; co = n - ij * p.Cout; oy = 2 * y + (ij >> 1); ox = 2 * x + (ij & 1); }
                 else if (p.pool) { oy = y >> 1; ox = x >> 1; }
+                if (p.split_g) co = n + (n / p.split_g) * p.split_g;       // high halves; the low halves sit split_g further
                 return (long long)b * p.out_sb + ((long long)oy * p.out_w + ox) * p.out_sp + co;
             };
             uint4 rn[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
@@ -459,7 +461,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
-                    if (vec) {
+                    if (vec && p.split_g) {                           // (hi | lo) pair: x = hi + lo to 16 mantissa bits
+                        uint4 q[2], ql[2];
+                        __nv_bfloat16 *qb = (__nv_bfloat16 *)q, *lb = (__nv_bfloat16 *)ql;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            qb[j] = __float2bfloat16_rn(v[j]);
+                            lb[j] = __float2bfloat16_rn(__fsub_rn(v[j], __bfloat162float(qb[j])));
+                        }
+                        ((uint4 *)op)[0] = q[0]; ((uint4 *)op)[1] = q[1];
+                        ((uint4 *)(op + p.split_g))[0] = ql[0]; ((uint4 *)(op + p.split_g))[1] = ql[1];
+                    } else if (vec) {
                         uint4 q[2];
                         __nv_bfloat162 *qb = (__nv_bfloat162 *)q;
 #pragma unroll
@@ -594,6 +606,9 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         return TDRN_EUNSUPPORTED;
     }
     TDRN_REQUIRE(!d->split3 || d->Cin % 64 == 0, "tdrn_conv2d_tc: split3 needs Cin %% 64 == 0 (got %d)", d->Cin);
+    TDRN_REQUIRE(!d->split_out || (d->split3 && d->out_dtype == TDRN_BF16 && d->split_out % 16 == 0 && d->Cout % d->split_out == 0 &&
+                                   d->out_sp == 2ll * d->Cout && !d->deconv2x2 && !d->pool2x2 && !residual && ((uintptr_t)out & 15) == 0),
+                 "tdrn_conv2d_tc: split_out needs split3, bf16 out, g %% 16 == 0, Cout %% g == 0, out_sp == 2*Cout, plain conv");
     {   // narrow high-resolution 3x3 layers: halo tile + resident weights (conv_halo_tc.cu)
         static const bool no_halo = getenv("TDRN_NO_HALO") != nullptr;
         if (!no_halo && !d->split3) {
@@ -611,7 +626,7 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     // p.Cin is padded to 64: the k-block count and the weight K use it, the activation tensor map uses the real Cin
     p.B = d->B; p.Cin = (d->Cin + 63) & ~63; p.Cout = d->Cout; p.n_total = d->deconv2x2 ? 4 * d->Cout : d->Cout;
     const int cin_mem = d->split3 ? 2 * d->Cin : d->Cin;        // channels of the activation tensor in memory ([hi | lo] when split)
-    if (d->split3) { p.split_cb = d->Cin >> 6; p.Cin = 3 * d->Cin; }
+    if (d->split3) { p.split_cb = d->Cin >> 6; p.Cin = 3 * d->Cin; p.split_g = d->split_out; }
     p.kw = kw; p.taps = kh * kw; p.pad = pad; p.dil = dil; p.stride = stride;
     p.bias = bias; p.res = residual; p.out = out;
     p.out_sb = d->out_sb; p.out_sp = d->out_sp;

@@ -31,6 +31,7 @@ struct SampleP {
     int taps_pad;                    // taps_total rounded up to even (padding entry: weight 0)
     int TW, TH, tiles_w, tiles_h, slots;
     int n_total, C, P, prior_off, softmax;
+    int merge_g;                     // > 0: the projections are (hi | lo) pairs, columns [g, 2g) are added to [0, g) before the softmax
     float *loc_out, *conf_out;
 };
 
@@ -165,6 +166,13 @@ __global__ void __launch_bounds__(DS_MAX_WARPS * 32, 2) deform_sample_kernel(con
     }
     __syncthreads();
     const int C = p.C;
+    if (p.merge_g) {                              // fp32-accurate heads: sampled high halves + sampled low halves
+        for (int e = threadIdx.x; e < p.slots * p.merge_g; e += blockDim.x) {
+            const int r = e / p.merge_g, c = e - r * p.merge_g;
+            stg[r * lds + c] += stg[r * lds + p.merge_g + c];
+        }
+        __syncthreads();
+    }
     if (p.softmax) {
         for (int q = threadIdx.x; q < p.slots * 3; q += blockDim.x) {
             const int r = q / 3, a = q - r * 3;
@@ -209,6 +217,11 @@ extern "C" int tdrn_deform_head_sample(const tdrn_deform_head_desc *d, const voi
     TDRN_REQUIRE(d->kh2 == 0 || (2 * d->pad2 == d->kh2 - 1 && offsets2), "tdrn_deform_head_sample: bad second head");
     SampleP p{};
     p.n_total = 12 + 3 * d->num_classes;
+    if (d->split && (n_pad % 16 != 0 || n_pad / 2 < p.n_total)) {
+        set_error("tdrn_deform_head_sample: split projections need n_pad = 2*g with 12+3*C <= g (got C=%d n_pad=%d)", d->num_classes, n_pad);
+        return TDRN_EUNSUPPORTED;
+    }
+    p.merge_g = d->split ? n_pad / 2 : 0;
     if (d->dg != 1 || n_pad % 8 != 0 || n_pad < p.n_total || n_pad > 256) {
         set_error("tdrn_deform_head_sample: needs one deformable group and 12+3*C <= n_pad <= 256, n_pad %% 8 == 0 "
                   "(got dg=%d C=%d n_pad=%d)", d->dg, d->num_classes, n_pad);

@@ -229,19 +229,23 @@ __device__ __forceinline__ void nms_small_path(const NmsP &p, int b, int seg, in
         sbox[i] = bx; sarea[i] = box_area(bx);
     }
     __syncthreads();
-    for (int item = tid; item < n * nw; item += NMS_THREADS) {      // item = (candidate i, word w of its row)
-        const int i = item / nw, w = item - i * nw;
-        unsigned bits = 0u;
-        if (w >= (i >> 5)) {
+    // one warp per (candidate i, word w >= i / 32 of its row): lane jj tests the pair (i, 32 w + jj), the ballot IS the word
+    {
+        int item = warp;                                            // items enumerate (i, w) with w >= i >> 5, row-major
+        for (int i = 0; i < n; ++i) {
+            const int w0 = i >> 5;
+            const int cnt_i = nw - w0;
+            if (item >= cnt_i) { item -= cnt_i; continue; }
             const float4 bi = sbox[i];
             const float ai = sarea[i];
-            const int j0 = w << 5;
-            const int jlo = w == (i >> 5) ? (i & 31) + 1 : 0, jhi = min(32, n - j0);   // only candidates after i, inside the segment
-#pragma unroll 4
-            for (int jj = jlo; jj < jhi; ++jj)
-                if (iou_ge(bi, ai, sbox[j0 + jj], sarea[j0 + jj], p.thr_up)) bits |= 1u << jj;
+            for (; item < cnt_i; item += NMS_THREADS / 32) {
+                const int w = w0 + item, j = (w << 5) + lane;
+                const bool hit = j > i && j < n && iou_ge(bi, ai, sbox[j], sarea[j], p.thr_up);
+                const unsigned bits = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) M[i * MW + w] = bits;
+            }
+            item -= cnt_i;
         }
-        M[i * MW + w] = bits;
     }
     __syncthreads();
     if (warp == 0) {

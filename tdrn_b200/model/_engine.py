@@ -406,13 +406,20 @@ class Engine(object):
         projected = (fused and dg == 1 and os.environ.get('TDRN_DEFORM_PATH', 'project') != 'im2col'
                      and all(2 * n_out8 <= f.shape[3] for f in feats))
 
+        # fp32 path: the same "project, then sample" head with the projection GEMM in split precision and the projections kept
+        # as (hi | lo) bf16 pairs (both halves sampled, added in fp32): replaces the CUDA-core deformable convs (24 ms of a
+        # 28 ms fp32 step at b32) when the head is narrow enough (12 + 3C <= 128)
+        projected_x3 = (self.use_x3 and dg == 1 and feats[0].dtype == torch.float32 and n_out16 <= 128
+                        and all(f.shape[3] % 64 == 0 for f in feats) and os.environ.get('TDRN_DEFORM_PATH', 'project') == 'project')
+
         def level(k):
             f = feats[k]
-            if projected:
-                pc, n_pad = self.projected_head_weight(loc_name, conf_name, k, multihead)
+            if projected or projected_x3:
+                pc, n_pad = self.projected_head_weight(loc_name, conf_name, k, multihead, x3=projected_x3)
                 ops.deform_head_projected(f, offs[k], pc, n_pad, num_classes, 3, 1, loc, conf, P, lv_off[k],
                                           offsets2=offs2[k] if multihead else None,
-                                          kh2=5 if multihead else 0, pad2=2 if multihead else 0, softmax=softmax)
+                                          kh2=5 if multihead else 0, pad2=2 if multihead else 0, softmax=softmax,
+                                          split=projected_x3)
             elif fused:
                 w1 = self.fused_head_weight(loc_name, conf_name, k)
                 w2 = self.fused_head_weight(loc_name + '_2', conf_name + '_2', k) if multihead else None
@@ -428,7 +435,7 @@ class Engine(object):
 
         self.parallel([(lambda k=k: level(k)) for k in range(len(feats))])
         conf2d = conf.view(B * P, num_classes)
-        if softmax and not fused:
+        if softmax and not fused and not projected_x3:
             ops.softmax_rows(conf2d, out=conf2d)
         return loc, conf2d
 
@@ -443,15 +450,15 @@ class Engine(object):
             self.pk[key] = w
         return w
 
-    def projected_head_weight(self, loc_name, conf_name, k, multihead):
+    def projected_head_weight(self, loc_name, conf_name, k, multihead, x3=False):
         """Per-tap projection weights (1x1 PackedConv, Cout = taps * n_pad) for tdrn_deform_head_sample."""
-        key = 'proj.%s.%s.%d.%d' % (loc_name, conf_name, k, int(multihead))
+        key = 'proj.%s.%s.%d.%d.%d' % (loc_name, conf_name, k, int(multihead), int(x3))
         w = self.pk.get(key)
         if w is None:
             cat = lambda ln, cn: torch.cat([self.sd['%s.%d.weight' % (ln, k)].detach(),
                                             self.sd['%s.%d.weight' % (cn, k)].detach()], 0)
             w = ops.pack_deform_proj_weight(cat(loc_name, conf_name),
-                                            cat(loc_name + '_2', conf_name + '_2') if multihead else None, self.device)
+                                            cat(loc_name + '_2', conf_name + '_2') if multihead else None, self.device, x3=x3)
             self.pk[key] = w
         return w
 

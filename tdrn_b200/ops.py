@@ -137,7 +137,8 @@ def split_bf16(x_nhwc):
 
 
 def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_sb=None, out_sp=None,
-           offsets=None, dg=0, use_tc=False, in_shape=None, in_sb=0, pool=False, label=None, work=None, split3=False):
+           offsets=None, dg=0, use_tc=False, in_shape=None, in_sb=0, pool=False, label=None, work=None, split3=False,
+           split_out=0):
     """out = act(conv(x) + bias (+ residual)).  ``out`` may be a view into a larger flat buffer, in which
     case out_sb/out_sp give the per-image and per-pixel strides (elements)."""
     if in_shape is not None:          # x is a strided view (e.g. one level of the flat [B,P,4] ARM output)
@@ -161,7 +162,7 @@ def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_
         out_sb, out_sp = Hs * Ws * pc.cout, pc.cout
     d = ConvDesc(B=B, H=H, W=W, Cin=Cin, Cout=pc.cout, kh=pc.kh, kw=pc.kw, stride=pc.stride, pad=pc.pad,
                  dil=pc.dil, relu=int(relu), deconv2x2=int(pc.deconv), dg=dg, in_dtype=_dt(x),
-                 out_dtype=_dt(out), out_sb=out_sb, out_sp=out_sp, in_sb=in_sb, pool2x2=int(pool), split3=int(split3))
+                 out_dtype=_dt(out), out_sb=out_sb, out_sp=out_sp, in_sb=in_sb, pool2x2=int(pool), split3=int(split3), split_out=int(split_out))
     L = _lib.lib()
     flops = 2.0 * B * (H * W * 4 if pc.deconv else Ho * Wo * pc.kh * pc.kw) * Cin * pc.cout if work is None else work
     if use_tc:
@@ -350,14 +351,14 @@ def deform_head(feat_nhwc, offsets, w_bf16, num_classes, dg, kh, pad, loc_out, c
                                           ptr(w2_bf16), ptr(loc_out), ptr(conf_out), stream_handle()), 'tdrn_deform_head')
 
 
-def pack_deform_proj_weight(wcat, wcat2=None, device='cuda'):
+def pack_deform_proj_weight(wcat, wcat2=None, device='cuda', x3=False):
     """Per-tap projection weights of the "project, then sample" head (tdrn_deform_head_sample).
 
     wcat [N, Cin, kh, kw] (loc rows then conf rows; wcat2: the optional second, 5x5, head) -> a 1x1 PackedConv with
     Cout = taps * n_pad rows, row t * n_pad + o = W[o, :, tap t] (taps of head 1 first), n_pad = N up to a multiple of 8."""
     ws = [wcat.detach().double().cpu()] + ([wcat2.detach().double().cpu()] if wcat2 is not None else [])
     n, cin = ws[0].shape[:2]
-    n_pad = (n + 7) // 8 * 8
+    n_pad = (n + 15) // 16 * 16 if x3 else (n + 7) // 8 * 8     # x3 (fp32-accurate heads): groups of g = n_pad (hi | lo) channels
     rows = []
     for w in ws:
         kh, kw = w.shape[2:]
@@ -365,7 +366,7 @@ def pack_deform_proj_weight(wcat, wcat2=None, device='cuda'):
         blk[:, :n] = w.permute(2, 3, 0, 1).reshape(kh * kw, n, cin)
         rows.append(blk.reshape(kh * kw * n_pad, cin))
     wp = torch.cat(rows, 0)
-    return PackedConv(wp.view(wp.shape[0], cin, 1, 1), device=device), n_pad
+    return PackedConv(wp.view(wp.shape[0], cin, 1, 1), device=device, want_bf16=not x3, want_x3=x3), n_pad
 
 
 def _deform_chunk_bytes():
@@ -374,7 +375,7 @@ def _deform_chunk_bytes():
 
 
 def deform_head_projected(feat_nhwc, offsets, pc_proj, n_pad, num_classes, kh, pad, loc_out, conf_out, P, prior_off,
-                          offsets2=None, kh2=0, pad2=0, softmax=True):
+                          offsets2=None, kh2=0, pad2=0, softmax=True, split=False):
     """Same contract as deform_head (dg = 1) in two launches per image chunk: dense per-tap projection on tcgen05
     (1x1 conv, bf16 out), then the bilinear sampler over the projections.  The batch is split into image chunks only
     when the projection buffer would exceed TDRN_DEFORM_CHUNK_MB (default 1024 MB; 278 MB at b32 / 40x40 / VOC-21).
@@ -383,19 +384,27 @@ def deform_head_projected(feat_nhwc, offsets, pc_proj, n_pad, num_classes, kh, p
     B, H, W, Cin = x.shape
     taps = kh * kh + kh2 * kh2
     assert pc_proj.cout == taps * n_pad and pc_proj.cin == Cin
-    per_img = H * W * taps * n_pad * 2
+    # split (fp32-accurate heads): x fp32 -> (hi | lo) operand, x3 GEMM, projections stored as (hi | lo) pairs per tap
+    width = 2 * n_pad if split else n_pad
+    per_img = H * W * taps * width * 2
     nb = max(1, min(B, _deform_chunk_bytes() // per_img))
-    y = torch.empty(nb, H, W, taps * n_pad, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(nb, H, W, taps * width, dtype=torch.bfloat16, device=x.device)
     flops = 2.0 * H * W * (12 + 3 * num_classes) * Cin * taps
     L = _lib.lib()
+    xin = split_bf16(x) if split else x
+    tag = 'deform_head_x3' if split else 'deform_head_tc'
     for b0 in range(0, B, nb):
         n = min(nb, B - b0)
-        conv2d(x[b0:b0 + n], pc_proj, use_tc=True, out=y[:n],
-               label='deform_head_tc|%d @%dx%d k%d+%d project' % (Cin, H, W, kh, kh2), work=flops * n)
+        if split:
+            conv2d(xin[b0:b0 + n], pc_proj, use_tc=True, out=y[:n], split3=True, split_out=n_pad, out_sb=H * W * taps * width,
+                   out_sp=taps * width, label='%s|%d @%dx%d k%d+%d project' % (tag, Cin, H, W, kh, kh2), work=flops * n)
+        else:
+            conv2d(xin[b0:b0 + n], pc_proj, use_tc=True, out=y[:n],
+                   label='%s|%d @%dx%d k%d+%d project' % (tag, Cin, H, W, kh, kh2), work=flops * n)
         d = DeformHeadDesc(B=n, H=H, W=W, Cin=Cin, num_classes=num_classes, dg=1, kh=kh, pad=pad, kh2=kh2, pad2=pad2,
-                           P=P, prior_off=prior_off, softmax=int(softmax))
-        with _Timed('deform_head_tc|%d @%dx%d k%d+%d sample' % (Cin, H, W, kh, kh2), 0.0):
-            check(L.tdrn_deform_head_sample(ctypes.byref(d), ptr(y), n_pad, ptr(offsets[b0:b0 + n]),
+                           P=P, prior_off=prior_off, softmax=int(softmax), split=int(split))
+        with _Timed('%s|%d @%dx%d k%d+%d sample' % (tag, Cin, H, W, kh, kh2), 0.0):
+            check(L.tdrn_deform_head_sample(ctypes.byref(d), ptr(y), width, ptr(offsets[b0:b0 + n]),
                                             ptr(offsets2[b0:b0 + n]) if offsets2 is not None else None,
                                             ptr(loc_out[b0:b0 + n]), ptr(conf_out[b0:b0 + n]), stream_handle()),
                   'tdrn_deform_head_sample')
