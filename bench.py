@@ -652,7 +652,7 @@ def run_gpu(args, rank, world, local_rank):
                    'includes': 'tdrn_preprocess (base_transform from a resident uint8 frame) + net + Detect, one graph replay per '
                                'frame, CUDA events around each replay'}
 
-    # ---- roofline leg: per-call CUDA events on the launching stream, eager (same kernels as the graph) ----
+    # ---- roofline leg: CUDA events around every kernel call on the launching stream (same kernels as the timed graphs) ----
     roof, breakdown = None, None
     if rank == 0:
         # per-kernel timing needs the kernels serialised on one stream: switch the engine's fork/join branches
@@ -663,10 +663,26 @@ def run_gpu(args, rank, world, local_rank):
         with torch.cuda.stream(stream), torch.no_grad():
             hot_path(dev_x[1])
             stream.synchronize()
-            ops.prof_begin()
-            for i in range(n_prof):
-                hot_path(dev_x[i % n_in])
-            rec = ops.prof_end()
+            if args.no_graph:
+                ops.prof_begin()
+                for i in range(n_prof):
+                    hot_path(dev_x[i % n_in])
+                rec = ops.prof_end()
+            else:
+                # the serialised step captured as ONE graph with an event-record node on both sides of every kernel: the
+                # events see the kernels' own time inside a replay, not the host's launch overhead between two eager calls
+                gp = torch.cuda.CUDAGraph()
+                ops.prof_begin()
+                with torch.cuda.graph(gp, stream=stream):
+                    hot_path(dev_x[1])
+                raw = ops.prof_take()
+                gp.replay()
+                stream.synchronize()
+                rec = []
+                for _ in range(n_prof):
+                    gp.replay()
+                    stream.synchronize()
+                    rec += [(label, work, e0.elapsed_time(e1)) for (label, work, e0, e1) in raw]
         for m in wl.nets:
             m.engine().multi_stream = True
         agg, detail = {}, {}

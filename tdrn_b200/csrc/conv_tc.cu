@@ -77,6 +77,7 @@ struct TcConvP {
                                  // region and stay there across consecutive M tiles (CTAs walk contiguous tile ranges); the rest
     int a_stages;                // of the 192 KB is a ring of a_stages activation boxes (16 KB each)
     uint32_t b_bytes;            // bytes one B box deposits (min(BN, n_pad16)*128)
+    int split_nacc;              // split mode: accumulators the hi * W_hi products are spread over (1 or 3)
     int split_g;                 // > 0: output written as (hi | lo) bf16 pairs in groups of split_g channels (tdrn_conv_desc.split_out)
     int split_cb;                // > 0: fp32-accurate mode (tdrn_conv_desc.split3) with split_cb real channel blocks: the K loop runs
                                  // over 3*split_cb blocks per tap -- (hi, W_hi), (hi, W_lo), (lo, W_hi) -- and the activation
@@ -113,7 +114,7 @@ constexpr int TC_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 e
 // NACC = 3 accumulators (each takes a third of the steps; 3 + 1 accumulators of BN = 128 columns fill TMEM), the two small products
 // (hi * W_lo, lo * W_hi: 2^-8 of the magnitude, their truncation does not matter) share one more, and the epilogue adds the
 // accumulators in fp32 registers.  All 512 TMEM columns belong to one tile: no accumulator double-buffering in this mode.
-template <int BN, int CL, bool RES, int MT, bool SPLIT = false>
+template <int BN, int CL, bool RES, int MT, int SPLIT = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmA2,
                                                                 const __grid_constant__ CUtensorMap tmB,
@@ -121,12 +122,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap tmO2, const TcConvP p)
 {
     static_assert(MT == 1 || (CL == 1 && !RES), "two-M-tile units: single CTA, streamed weights");
-    static_assert(!SPLIT || (BN <= 128 && CL == 1 && !RES && MT == 1), "split mode: BN <= 128, single CTA, streamed weights");
+    static_assert(!SPLIT || ((SPLIT + 1) * BN <= 512 && CL == 1 && !RES && MT == 1), "split mode: SPLIT + 1 accumulators of BN columns, single CTA, streamed weights");
     using Cfg = TcCfg<BN, MT>;
     constexpr uint32_t NBUF = (MT == 2 || SPLIT) ? 1u : 2u;           // accumulator buffers a unit alternates between
-    constexpr int NACC = SPLIT ? 3 : 1;                               // split mode: accumulators of the hi * W_hi products (the same
-                                                                      // number for every BN: results do not depend on the tile shape, i.e. on the batch size)
-    constexpr int TMEM_COLS = SPLIT ? (BN == 128 ? 512 : 256) : Cfg::TMEM_COLS;
+    constexpr int NACC = SPLIT ? SPLIT : 1;                           // split mode: accumulators of the hi * W_hi products (the host picks
+                                                                      // ONE value for all tile shapes: results must not depend on BN, i.e. on the batch size)
+    constexpr int TMEM_COLS = SPLIT ? ((SPLIT + 1) * BN > 256 ? 512 : ((SPLIT + 1) * BN > 128 ? 256 : 128)) : Cfg::TMEM_COLS;
     extern __shared__ uint8_t smem_dyn[];
     constexpr int MAX_STAGES = Cfg::STAGES > 8 ? Cfg::STAGES : 8;
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -563,13 +564,19 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmA2, const CUte
     }
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < g_num_sms ? total : g_num_sms;
-    if constexpr (BN <= 128) {
-        if (p.split_cb) {
-            TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-            conv_tc_kernel<BN, 1, false, 1, true><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
-            TDRN_LAUNCH_CHECK();
-            return TDRN_OK;
+    if (p.split_cb) {
+        if constexpr (BN <= 128) {
+            if (p.split_nacc == 3) {
+                TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, false, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+                conv_tc_kernel<BN, 1, false, 1, 3><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+                TDRN_LAUNCH_CHECK();
+                return TDRN_OK;
+            }
         }
+        TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, false, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        conv_tc_kernel<BN, 1, false, 1, 1><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+        TDRN_LAUNCH_CHECK();
+        return TDRN_OK;
     }
     if (p.b_resident) {
         TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -666,7 +673,12 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     }
 
     const int n_pad16 = (p.n_total + 15) & ~15;
-    int BN = n_pad16 > 128 && !d->split3 ? 256 : (n_pad16 > 64 ? 128 : 64);     // split mode: several accumulators per tile, BN <= 128
+    // split mode: 1 + 1 accumulators (any BN) or, with TDRN_X3_NACC=3, 3 + 1 (BN <= 128).  Measured on B200 (b32, worst case over the
+    // test-suite): one accumulator for everything 1.3e-4, 1 + 1: see DESIGN.md, 3 + 1: < 5e-5 at twice the time (BN <= 128 doubles
+    // the operand traffic of the wide layers)
+    static const int x3_nacc = getenv("TDRN_X3_NACC") ? atoi(getenv("TDRN_X3_NACC")) : 1;
+    if (d->split3) p.split_nacc = x3_nacc == 3 ? 3 : 1;
+    int BN = n_pad16 > 128 && !(d->split3 && p.split_nacc == 3) ? 256 : (n_pad16 > 64 ? 128 : 64);
     // Small maps (the 10x10 / 5x5 pyramid levels, M <= 3200 rows at b32) yield a handful of 128-row tiles: with the
     // widest N tile only 7..25 SMs would stream the whole weight tensor.  Narrower N tiles put 2-4x more SMs to
     // work (the A re-reads this costs are tiny at these sizes).
