@@ -663,26 +663,14 @@ def run_gpu(args, rank, world, local_rank):
         with torch.cuda.stream(stream), torch.no_grad():
             hot_path(dev_x[1])
             stream.synchronize()
-            if args.no_graph:
-                ops.prof_begin()
-                for i in range(n_prof):
-                    hot_path(dev_x[i % n_in])
-                rec = ops.prof_end()
-            else:
-                # the serialised step captured as ONE graph with an event-record node on both sides of every kernel: the
-                # events see the kernels' own time inside a replay, not the host's launch overhead between two eager calls
-                gp = torch.cuda.CUDAGraph()
-                ops.prof_begin()
-                with torch.cuda.graph(gp, stream=stream):
-                    hot_path(dev_x[1])
-                raw = ops.prof_take()
-                gp.replay()
-                stream.synchronize()
-                rec = []
-                for _ in range(n_prof):
-                    gp.replay()
-                    stream.synchronize()
-                    rec += [(label, work, e0.elapsed_time(e1)) for (label, work, e0, e1) in raw]
+            # eager calls, one pair of events per kernel call.  (Measured r02j: event-record nodes inside one captured graph
+            # -- ops.prof_take() -- cost MORE per kernel than the host's launch overhead does here (conv family 2.67 vs 2.59 ms):
+            # every node edge of a graph is ~1-2 us, which is what bounds the sub-20-us launches of the small pyramid levels in
+            # both forms; the ncu launch list under profiles/ is the kernel-only cross-check.)
+            ops.prof_begin()
+            for i in range(n_prof):
+                hot_path(dev_x[i % n_in])
+            rec = ops.prof_end()
         for m in wl.nets:
             m.engine().multi_stream = True
         agg, detail = {}, {}

@@ -673,11 +673,12 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     }
 
     const int n_pad16 = (p.n_total + 15) & ~15;
-    // split mode: 1 + 1 accumulators (any BN) or, with TDRN_X3_NACC=3, 3 + 1 (BN <= 128).  Measured on B200 (b32, worst case over the
-    // test-suite): one accumulator for everything 1.3e-4, 1 + 1: see DESIGN.md, 3 + 1: < 5e-5 at twice the time (BN <= 128 doubles
-    // the operand traffic of the wide layers)
-    static const int x3_nacc = getenv("TDRN_X3_NACC") ? atoi(getenv("TDRN_X3_NACC")) : 1;
-    if (d->split3) p.split_nacc = x3_nacc == 3 ? 3 : 1;
+    // split mode: 3 + 1 accumulators (BN <= 128) or, with TDRN_X3_NACC=1, 1 + 1 (any BN).  Measured on B200 (b32 step / worst
+    // max-norm error over the test-suite, bar 1e-4): one accumulator for everything 23.0 ms / 1.3e-4; 1 + 1: 13.3 ms / 1.2e-4
+    // (one 704 x 704 case above the bar); 3 + 1: 17.2 ms / every case below the bar -- the default.  BN <= 128 doubles the operand
+    // traffic of the wide layers, which is what the extra 4 ms are.
+    static const int x3_nacc = getenv("TDRN_X3_NACC") ? atoi(getenv("TDRN_X3_NACC")) : 3;
+    if (d->split3) p.split_nacc = x3_nacc == 1 ? 1 : 3;
     int BN = n_pad16 > 128 && !(d->split3 && p.split_nacc == 3) ? 256 : (n_pad16 > 64 ? 128 : 64);
     // Small maps (the 10x10 / 5x5 pyramid levels, M <= 3200 rows at b32) yield a handful of 128-row tiles: with the
     // widest N tile only 7..25 SMs would stream the whole weight tensor.  Narrower N tiles put 2-4x more SMs to
