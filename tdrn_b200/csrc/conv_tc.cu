@@ -77,6 +77,7 @@ struct TcConvP {
                                  // region and stay there across consecutive M tiles (CTAs walk contiguous tile ranges); the rest
     int a_stages;                // of the 192 KB is a ring of a_stages activation boxes (16 KB each)
     uint32_t b_bytes;            // bytes one B box deposits (min(BN, n_pad16)*128)
+    int splitk;                  // > 1: K is split over a thread-block cluster of this many CTAs (conv_splitk_kernel)
     int split_nacc;              // split mode: accumulators the hi * W_hi products are spread over (1 or 3)
     int split_g;                 // > 0: output written as (hi | lo) bf16 pairs in groups of split_g channels (tdrn_conv_desc.split_out)
     int split_cb;                // > 0: fp32-accurate mode (tdrn_conv_desc.split3) with split_cb real channel blocks: the K loop runs
@@ -498,6 +499,223 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Split-K variant for the small pyramid levels (10x10 / 5x5 maps at 320, 16x16 / 8x8 at 512: M = B * H * W is a few
+// thousand rows, so a layer has 7..100 output tiles for 148 SMs while its K loop is 36..144 k-blocks long; measured r01:
+// arm_loc.2 1024 -> 12 @10x10 runs 144 k-blocks on 25 SMs, 0.39 us per k-block = the latency of eight TMA boxes in flight,
+// 12 TFLOP/s).  The k-blocks of ONE output tile are split over a thread-block cluster of S CTAs (S SMs pull operands for
+// the tile); every CTA accumulates its K slice in its own TMEM, ranks 1..S-1 park the fp32 partial tile in their shared
+// memory, and rank 0 adds them through distributed shared memory (ld.shared::cluster) in rank order -- deterministic --
+// before the usual epilogue.  S depends on the layer's shape only (never on the batch size): results stay bit-identical
+// across batch sizes.  BN = 64 (these layers are small: more N tiles = more SMs at work).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SK_BN = 64;
+constexpr int SK_STAGES = 8;
+constexpr int SK_STAGE_BYTES = 128 * 128 + SK_BN * 128;              // one A box + one B box
+constexpr int SK_SMEM_BYTES = SK_STAGES * SK_STAGE_BYTES + 1024;
+
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_splitk_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const __grid_constant__ CUtensorMap tmA2,
+                                                                    const __grid_constant__ CUtensorMap tmB, const TcConvP p)
+{
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[SK_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[SK_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    uint8_t *tiles = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.splitk;
+    const int rank = (int)cluster_ctarank();
+    const int unit = blockIdx.x / S;                       // output tile: unit = nt * m_tiles + mt
+    const int nt = unit / p.m_tiles, mt = unit - nt * p.m_tiles;
+    const int n_pad16 = (p.n_total + 15) & ~15;
+    const int cblocks = p.Cin >> 6;
+    const int num_kb = p.taps * cblocks;
+    const int kb0 = (int)((long long)num_kb * rank / S), kb1 = (int)((long long)num_kb * (rank + 1) / S);
+    const int n0 = nt * SK_BN;
+    const int n_eff = min(SK_BN, n_pad16 - n0);
+
+    const bool tail = p.rr && mt >= p.nA;                  // ragged-tail tile (leftover rows of g2 images)
+    const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        if (p.rr) tma_prefetch_desc(&tmA2);
+        tma_prefetch_desc(&tmB);
+#pragma unroll
+        for (int s = 0; s < SK_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, SK_BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===================== TMA producer: k-blocks kb0 .. kb1-1 of this tile =====================
+        if (lane == 0) {
+            const int w0 = tw * p.bw * p.stride - p.pad;
+            const int h0 = (tail ? p.qh * p.bh : th * p.bh) * p.stride - p.pad;
+            const int b0 = tail ? (mt - p.nA) * p.g2 : tn * p.bn;
+            const CUtensorMap *mapA = tail ? &tmA2 : &tmA;
+            const uint32_t a_bytes = tail ? p.a_bytes2 : p.a_bytes;
+            uint32_t s = 0, ph = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t *sa = tiles + s * SK_STAGE_BYTES;
+                const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                const int tr = tap / p.kw, ts = tap - tr * p.kw;
+                mbar_expect_tx(&full_bar[s], a_bytes + p.b_bytes);
+                tma_load_4d(sa, mapA, &full_bar[s], cb * 64, w0 + ts * p.dil, h0 + tr * p.dil, b0);
+                tma_load_2d(sa + 128 * 128, &tmB, &full_bar[s], kb * 64, n0);
+                if (++s == SK_STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, n_eff);
+            uint32_t s = 0, ph = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(tiles + s * SK_STAGE_BYTES);
+                const uint64_t adesc = umma_desc_sw128(sa);
+                const uint64_t bdesc = umma_desc_sw128(sa + 128 * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb > kb0) || k != 0);
+                umma_commit(&empty_bar[s]);
+                if (++s == SK_STAGES) { s = 0; ph ^= 1u; }
+            }
+            umma_commit(&tmem_full_bar);
+        }
+        __syncwarp();
+    }
+
+    // ===================== partial tiles: TMEM -> registers (-> shared memory on ranks 1..S-1) =====================
+    // Two warps per TMEM lane quadrant; each takes two of the four 16-column chunks.  Partial layout in shared memory
+    // (the TMA ring is idle by then): [chunk 0..3][row 0..127][16 floats] so that a warp's read of one chunk is 2 KB contiguous.
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int r = quad * 32 + lane;
+    float v[2][16];
+    float *partial = (float *)tiles;
+    if (warp >= 2) {
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int c0 = half * 16 + i * 32;
+            if (c0 < n_eff) tmem_ld16(trow + (uint32_t)c0, v[i]);
+        }
+        if (rank != 0) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int c0 = half * 16 + i * 32;
+                if (c0 < n_eff) {
+                    float4 *dst = (float4 *)(partial + ((c0 >> 4) * 128 + r) * 16);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[i][4 * q], v[i][4 * q + 1], v[i][4 * q + 2], v[i][4 * q + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                                   // every rank's partial tile is visible cluster-wide
+    if (rank == 0 && warp >= 2) {
+        const uint32_t local = smem_u32(partial);
+        for (int rr = 1; rr < S; ++rr) {                  // fixed order: deterministic sum
+            const uint32_t remote = mapa_shared(local, (uint32_t)rr);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int c0 = half * 16 + i * 32;
+                if (c0 < n_eff) {
+                    const uint32_t a = remote + (uint32_t)(((c0 >> 4) * 128 + r) * 64);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 u = ld_dsmem_f4(a + q * 16);
+                        v[i][4 * q] += u.x; v[i][4 * q + 1] += u.y; v[i][4 * q + 2] += u.z; v[i][4 * q + 3] += u.w;
+                    }
+                }
+            }
+        }
+    }
+    cluster_sync_all();                                   // nobody leaves (and frees its shared memory) while rank 0 reads
+
+    if (rank == 0 && warp >= 2) {
+        // ===================== epilogue (rank 0): bias / residual / ReLU / pixel shuffle / store =====================
+        const int wl = r % p.bw, hl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+        const int hl2 = p.rr ? (r / p.bw) % p.rr : 0, nl2 = p.rr ? r / (p.bw * p.rr) : 0;
+        const int x = tw * p.bw + wl;
+        const int y = tail ? p.qh * p.bh + hl2 : th * p.bh + hl;
+        const int b = tail ? (mt - p.nA) * p.g2 + nl2 : tn * p.bn + nl;
+        const bool valid = (tail ? nl2 < p.g2 : nl < p.bn) && x < p.W && y < p.H && b < p.B;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int c0 = half * 16 + i * 32;
+            const int n = n0 + c0;
+            if (c0 >= n_eff || n >= p.n_total || !valid) continue;
+            const int nv = min(16, p.n_total - n);
+            int co = n, oy = y, ox = x;
+            if (p.deconv) { const int ij = n / p.Cout; co = n - ij * p.Cout; oy = 2 * y + (ij >> 1); ox = 2 * x + (ij & 1); }
+            const long long o = (long long)b * p.out_sb + ((long long)oy * p.out_w + ox) * p.out_sp + co;
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) if (j < nv) v[i][j] += __ldg(p.bias + co + j);
+            }
+            if (p.out_f32) {
+                float *op = (float *)p.out + o;
+                if (p.res) { const float *rp = (const float *)p.res + o;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (j < nv) v[i][j] += rp[j]; }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) if (j < nv) op[j] = p.relu ? fmaxf(v[i][j], 0.f) : v[i][j];
+            } else {
+                __nv_bfloat16 *op = (__nv_bfloat16 *)p.out + o;
+                if (p.res) { const __nv_bfloat16 *rp = (const __nv_bfloat16 *)p.res + o;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (j < nv) v[i][j] += __bfloat162float(rp[j]); }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[i][j] = fmaxf(v[i][j], 0.f);
+                }
+                if (nv == 16 && ((o & 7) == 0)) {
+                    uint4 q[2];
+                    __nv_bfloat162 *qb = (__nv_bfloat162 *)q;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) qb[j] = __floats2bfloat162_rn(v[i][2 * j], v[i][2 * j + 1]);
+                    ((uint4 *)op)[0] = q[0]; ((uint4 *)op)[1] = q[1];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (j < nv) op[j] = __float2bfloat16_rn(v[i][j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, SK_BN); }
+}
+
 // Pick the A box (bw, bh, bn), bw*bh*bn <= 128, maximising useful rows; bn > 1 only when one image's
 // whole map fits (the 10x10 and 5x5 pyramid levels).  Ties -> wider rows.
 static void pick_box(int B, int H, int W, int max_w, int max_h, int &bw, int &bh, int &bn)
@@ -691,6 +909,18 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     while (BN > 64 && p.m_tiles * ((n_pad16 + BN - 1) / BN) * 2 <= g_num_sms) BN >>= 1;
     p.n_tiles = (n_pad16 + BN - 1) / BN;
 
+    {   // small maps with a long K loop: split K over a cluster (conv_splitk_kernel).  S is a function of the LAYER's shape only.
+        static const bool no_splitk = getenv("TDRN_NO_SPLITK") != nullptr;
+        const int num_kb = p.taps * (p.Cin >> 6);
+        const int n_tiles64 = (n_pad16 + SK_BN - 1) / SK_BN;
+        int S = 1;
+        if (!no_splitk && !d->split3 && !p.pool && p.H * p.W <= 256 && num_kb >= 16) {
+            S = 8;
+            while (S > 1 && (num_kb / S < 8 || n_tiles64 * S > 16)) S >>= 1;
+        }
+        p.splitk = S;
+        if (S > 1) { BN = SK_BN; p.n_tiles = n_tiles64; }
+    }
     CUtensorMap tmA, tmA2, tmB;
     bool use_cluster = false;
     {
@@ -718,7 +948,7 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         // Measured on B200 (profiles/r01b_*): no gain -- these layers are bound by tile fill and wave quantisation, not by
         // L2->SM weight traffic -- so the cluster path is opt-in (TDRN_CLUSTER=1) and kept as a tested option.
         static const bool want_cluster = getenv("TDRN_CLUSTER") != nullptr;
-        use_cluster = want_cluster && !d->split3 && p.m_tiles >= 2 && (b_rows % 16u) == 0;
+        use_cluster = want_cluster && !d->split3 && p.splitk == 1 && p.m_tiles >= 2 && (b_rows % 16u) == 0;
         const uint32_t box[2] = {64, use_cluster ? b_rows / 2 : b_rows};
         p.b_bytes = b_rows * 128u;
         int rc = make_tmap_bf16(&tmB, weight, 2, dims, str, box, nullptr);
@@ -736,13 +966,13 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         static const bool no_res = getenv("TDRN_NO_RESIDENT_B") != nullptr;
         const int num_kb = p.taps * (p.Cin >> 6);
         const int ring_boxes = (192 * 1024 - num_kb * BN * 128) / (128 * 128);
-        p.b_resident = !no_res && !d->split3 && !use_cluster && ring_boxes >= 4 && ring_boxes >= num_kb && p.m_tiles * p.n_tiles >= 4 * g_num_sms;
+        p.b_resident = !no_res && !d->split3 && p.splitk == 1 && !use_cluster && ring_boxes >= 4 && ring_boxes >= num_kb && p.m_tiles * p.n_tiles >= 4 * g_num_sms;
         p.a_stages = ring_boxes < 8 ? ring_boxes : 8;
     }
     CUtensorMap tmO = tmA, tmO2 = tmA;
     {   // TMA-store epilogue: plain contiguous NHWC bf16 output (no pool / pixel shuffle / residual), 16-byte aligned rows
         static const bool no_tma_out = getenv("TDRN_NO_TMA_STORE") != nullptr;
-        p.tma_out = !no_tma_out && !d->split3 && !d->deconv2x2 && !p.pool && !p.out_f32 && !residual && d->Cout % 8 == 0 &&
+        p.tma_out = !no_tma_out && !d->split3 && p.splitk == 1 && !d->deconv2x2 && !p.pool && !p.out_f32 && !residual && d->Cout % 8 == 0 &&
                     d->out_sp == d->Cout && d->out_sb == (long long)p.H * p.W * d->Cout && ((uintptr_t)out & 15) == 0;
         if (p.tma_out) {
             const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
@@ -765,6 +995,21 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         p.mt2 = !no_mt2 && BN == 256 && p.tma_out && !p.b_resident && !use_cluster && num_kb >= 64 && units2 * 10 >= g_num_sms * 7;   // measured: K = 2304 (36 k-blocks) loses 5 %, K = 4608 gains 5-10 %
     }
     cudaStream_t st = as_stream(stream);
+    if (p.splitk > 1) {
+        TDRN_CUDA(cudaFuncSetAttribute(conv_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(p.m_tiles * p.n_tiles * p.splitk));
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = SK_SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.splitk; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        TDRN_CUDA(cudaLaunchKernelEx(&cfg, conv_splitk_kernel, tmA, tmA2, tmB, p));
+        count_launch();
+        return TDRN_OK;
+    }
     if (BN == 256) return launch_tc<256>(tmA, tmA2, tmB, tmO, tmO2, p, use_cluster, st);
     if (BN == 128) return launch_tc<128>(tmA, tmA2, tmB, tmO, tmO2, p, use_cluster, st);
     return launch_tc<64>(tmA, tmA2, tmB, tmO, tmO2, p, use_cluster, st);

@@ -329,3 +329,34 @@ def test_conv_tc_split3_deconv_residual():
     out = ops.conv2d(ops.split_bf16(_nhwc(x).cuda()), pc, relu=True, residual=_nhwc(t).cuda(), out_dtype=torch.float32,
                      use_tc=True, split3=True)
     assert rel_err(_nchw(out).cpu().numpy(), ref.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize('b,cin,cout,k,stride,pad,h,w,relu', [
+    (8, 1024, 12, 3, 1, 1, 10, 10, False),      # arm_loc.2: 144 k-blocks over a cluster of 8, one N tile
+    (8, 1024, 256, 3, 1, 1, 10, 10, True),      # trans_layers.2.0: cluster of 4 x 4 N tiles
+    (9, 512, 256, 3, 1, 1, 5, 5, True),         # last_layer_trans.0: 5 images per tile, cluster of 4
+    (2, 256, 256, 3, 1, 1, 16, 16, True),       # 16x16 maps (512-pixel input): two tiles per image
+    (3, 256, 512, 3, 2, 1, 10, 10, True),       # extras.3: stride 2, cluster of 2
+    (1, 1024, 256, 1, 1, 0, 10, 10, True),      # a single tile (batch 1): 16 k-blocks over 2 CTAs
+])
+def test_conv_splitk_cluster(b, cin, cout, k, stride, pad, h, w, relu):
+    """Small maps: K split over a thread-block cluster, partial tiles summed through distributed shared memory
+    (conv_splitk_kernel).  Same reference and tolerance as the plain kernel; the result of an image must not depend on
+    the batch it is in (the cluster size is a function of the layer's shape only)."""
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(cin + cout + k + b)
+    x = _bf(torch.randn(b, cin, h, w, generator=g))
+    wt = _bf(torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5)
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv2d(x, wt, bias, stride, pad)
+    if relu:
+        ref = F.relu(ref)
+    pc = ops.PackedConv(wt, bias, None, stride, pad, 1, device='cuda')
+    xg = _nhwc(x).cuda().to(torch.bfloat16)
+    out = ops.conv2d(xg, pc, relu=relu, out_dtype=torch.float32, use_tc=True)
+    torch.cuda.synchronize()
+    assert rel_err(_nchw(out).cpu().numpy(), ref.numpy()) < 2e-5
+    out16 = ops.conv2d(xg, pc, relu=relu, use_tc=True)
+    assert rel_err(_nchw(out16.float()).cpu().numpy(), ref.numpy()) < 6e-3
+    one = ops.conv2d(xg[b - 1:b].contiguous(), pc, relu=relu, out_dtype=torch.float32, use_tc=True)
+    assert torch.equal(one[0], out[b - 1])
