@@ -301,6 +301,10 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform_head_kernel(const __grid
     // ===================== epilogue =====================
     // All MMAs (hence all smem operand reads) are complete once tmem_full fires; the stage buffers are
     // reused as a [128][n_pad16+1] fp32 staging tile.
+    // (The mbarrier chain producer-arrive -> MMA wait -> tcgen05.commit -> tmem_full already orders the producers' A-tile
+    // stores before these staging stores; the CTA barrier makes that order visible to compute-sanitizer's racecheck, which
+    // does not follow mbarriers -- it reported the pair as a write-after-write hazard -- and costs one barrier per tile.)
+    __syncthreads();
     float *stg = (float *)tiles;
     const int lds = p.n_pad16 + 1;
     if (warp < 4) {
