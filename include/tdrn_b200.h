@@ -189,6 +189,20 @@ int tdrn_softmax(const float *in, float *out, long long rows, int C, tdrn_stream
 /* NHWC (dtype) -> NCHW fp32 (to hand offset maps back in the reference layout) and the reverse. */
 int tdrn_nhwc_to_nchw_f32(const void *in, float *out, int B, int H, int W, int C, int dtype, tdrn_stream_t stream);
 
+/* The `offset.k` / `offset2.k` 1x1 convs (12 -> 18*dg and 12 -> 50*dg) of all pyramid levels in one launch
+   (model/dualrefinedet_vggbn.py:160-164, model/ssd4scale_vgg.py:72-76: `self.offset[k](arm_loc_k)`): arm_loc is the flattened
+   ARM regression [B,P,4] (level k: prior_off + (y*W+x)*3 + a), w1 [c1][12] / w2 [c2][12] fp32 row-major (the reference's
+   [Cout,12,1,1] weights as they lie), b1 / b2 may be NULL; out1 [B,H,W,c1], out2 [B,H,W,c2] NHWC fp32 (what the deformable
+   heads read), out1_nchw [B,c1,H,W] or NULL (the maps the reference's forward returns).  c2 == 0: no second head. */
+#define TDRN_MAX_OFFSET_LEVELS 6
+typedef struct tdrn_offset_level {
+    int H, W, prior_off;
+    const float *w1, *b1, *w2, *b2;
+    float *out1, *out2, *out1_nchw;
+} tdrn_offset_level;
+int tdrn_offset_convs(const float *arm_loc, int B, int P, int n_levels, const tdrn_offset_level *levels, int c1, int c2,
+                      tdrn_stream_t stream);
+
 /* fp32 NHWC activations [pixels][C] -> the split operand of the fp32-accurate tensor-core convs (tdrn_conv_desc.split3):
    out [pixels][2*C] bf16, out[p][c] = bf16(x), out[p][C + c] = bf16(x - float(out[p][c])).  C % 8 == 0. */
 int tdrn_split_bf16(const float *in, void *out, long long pixels, int C, tdrn_stream_t stream);

@@ -913,10 +913,13 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         static const bool no_splitk = getenv("TDRN_NO_SPLITK") != nullptr;
         const int num_kb = p.taps * (p.Cin >> 6);
         const int n_tiles64 = (n_pad16 + SK_BN - 1) / SK_BN;
+        // Measured r02l (b32): splitting pays where the cluster grid still fits one wave of 148 SMs -- the Cout <= 64 heads on the
+        // 10x10 / 16x16 maps (arm_loc.2: 0.063 -> 0.043 ms) and everything on the 5x5 / 8x8 maps (512 -> 256: 0.038 -> 0.023) -- and
+        // loses where it does not (256 -> 256 @10x10 as 400 one-tile CTAs: 0.024 -> 0.056).  The rule may only look at the layer.
         int S = 1;
-        if (!no_splitk && !d->split3 && !p.pool && p.H * p.W <= 256 && num_kb >= 16) {
-            S = 8;
-            while (S > 1 && (num_kb / S < 8 || n_tiles64 * S > 16)) S >>= 1;
+        if (!no_splitk && !d->split3 && !p.pool && num_kb >= 16) {
+            if (p.H * p.W <= 64) { S = 8; while (S > 1 && (num_kb / S < 8 || n_tiles64 * S > 16)) S >>= 1; }
+            else if (p.H * p.W <= 256 && n_tiles64 == 1) { S = 8; while (S > 1 && num_kb / S < 8) S >>= 1; }
         }
         p.splitk = S;
         if (S > 1) { BN = SK_BN; p.n_tiles = n_tiles64; }

@@ -749,3 +749,73 @@ extern "C" int tdrn_split_bf16(const float *in, void *out, long long pixels, int
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// offset / offset2 1x1 convs of all pyramid levels in ONE launch (dualrefinedet_vggbn.py:160-164, ssd4scale_vgg.py:72-76):
+// per pixel a 12-vector (the ARM regression of its three anchors, read straight out of the flattened [B,P,4] tensor) times
+// a [c1 | c2] x 12 matrix + bias -> NHWC fp32 offset maps for the deformable heads and, for the first head, the NCHW copy
+// the reference returns.  Replaces 8 conv launches + 4 layout copies per step (each a few microseconds of work on its own
+// branch stream).  One thread per (image, pixel, output channel).
+// ---------------------------------------------------------------------------------------------------------
+namespace tdrn {
+struct OffsetLevels {
+    int n, c1, c2, B, P;
+    int H[TDRN_MAX_OFFSET_LEVELS], W[TDRN_MAX_OFFSET_LEVELS], prior_off[TDRN_MAX_OFFSET_LEVELS];
+    long long first[TDRN_MAX_OFFSET_LEVELS + 1];           // running (pixel, channel) work-item offsets per image
+    const float *w1[TDRN_MAX_OFFSET_LEVELS], *b1[TDRN_MAX_OFFSET_LEVELS], *w2[TDRN_MAX_OFFSET_LEVELS], *b2[TDRN_MAX_OFFSET_LEVELS];
+    float *o1[TDRN_MAX_OFFSET_LEVELS], *o2[TDRN_MAX_OFFSET_LEVELS], *o1_nchw[TDRN_MAX_OFFSET_LEVELS];
+};
+
+__global__ void __launch_bounds__(256) offset_convs_kernel(const float *__restrict__ arm_loc, const OffsetLevels L)
+{
+    const long long per_img = L.first[L.n];
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per_img * L.B) return;
+    const int b = (int)(t / per_img);
+    const long long i = t - (long long)b * per_img;
+    int k = 0;
+    while (k + 1 < L.n && i >= L.first[k + 1]) ++k;
+    const int cc = L.c1 + L.c2;
+    const long long j = i - L.first[k];
+    const int pix = (int)(j / cc), ch = (int)(j - (long long)pix * cc);
+    const float *a = arm_loc + ((long long)b * L.P + L.prior_off[k] + (long long)pix * 3) * 4;       // 12 consecutive floats
+    const bool second = ch >= L.c1;
+    const int co = second ? ch - L.c1 : ch;
+    const float *w = (second ? L.w2[k] : L.w1[k]) + co * 12;
+    const float *bias = second ? L.b2[k] : L.b1[k];
+    float acc = bias ? bias[co] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 12; ++c) acc = fmaf(a[c], w[c], acc);
+    const int HW = L.H[k] * L.W[k];
+    if (second) {
+        L.o2[k][((long long)b * HW + pix) * L.c2 + co] = acc;
+    } else {
+        L.o1[k][((long long)b * HW + pix) * L.c1 + co] = acc;
+        if (L.o1_nchw[k]) L.o1_nchw[k][((long long)b * L.c1 + co) * HW + pix] = acc;
+    }
+}
+}  // namespace tdrn
+
+extern "C" int tdrn_offset_convs(const float *arm_loc, int B, int P, int n_levels, const tdrn_offset_level *lv, int c1, int c2,
+                                 tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(arm_loc && lv && B > 0 && P > 0 && n_levels > 0 && n_levels <= TDRN_MAX_OFFSET_LEVELS && c1 > 0 && c2 >= 0,
+                 "tdrn_offset_convs: bad argument");
+    tdrn::OffsetLevels L{};
+    L.n = n_levels; L.c1 = c1; L.c2 = c2; L.B = B; L.P = P;
+    long long run = 0;
+    for (int k = 0; k < n_levels; ++k) {
+        TDRN_REQUIRE(lv[k].H > 0 && lv[k].W > 0 && lv[k].w1 && lv[k].out1 && (c2 == 0 || (lv[k].w2 && lv[k].out2)) &&
+                     lv[k].prior_off >= 0 && lv[k].prior_off + 3ll * lv[k].H * lv[k].W <= P, "tdrn_offset_convs: bad level %d", k);
+        L.H[k] = lv[k].H; L.W[k] = lv[k].W; L.prior_off[k] = lv[k].prior_off;
+        L.w1[k] = lv[k].w1; L.b1[k] = lv[k].b1; L.w2[k] = lv[k].w2; L.b2[k] = lv[k].b2;
+        L.o1[k] = lv[k].out1; L.o2[k] = lv[k].out2; L.o1_nchw[k] = lv[k].out1_nchw;
+        L.first[k] = run;
+        run += (long long)lv[k].H * lv[k].W * (c1 + c2);
+    }
+    L.first[n_levels] = run;
+    const long long total = run * B;
+    tdrn::offset_convs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, tdrn::as_stream(stream)>>>(arm_loc, L);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}

@@ -291,27 +291,36 @@ class Engine(object):
         return self.conv(name, x, 1, pad, out=view, out_sb=P * per_prior, out_sp=cout,
                          residual=view if residual else None, offsets=offsets, dg=dg)
 
+    def offset_maps(self, arm_loc, sizes, lv_off, multihead, want_nchw):
+        """`offset.k` / `offset2.k` 1x1 convs of every level on the flattened ARM regression, one launch
+        (dualrefinedet_vggbn.py:160-164).  -> offsets NHWC, offsets2 NHWC (or []), offsets NCHW (or None)."""
+        key = 'offset_w.%d' % int(multihead)
+        w = self.pk.get(key)
+        if w is None:
+            n = len(sizes)
+            f = lambda name: self.sd[name].detach().float().reshape(self.sd[name].shape[0], -1).contiguous().to(self.device)
+            b = lambda name: (self.sd[name].detach().float().contiguous().to(self.device) if name in self.sd else None)
+            w = ([f('offset.%d.weight' % k) for k in range(n)], [b('offset.%d.bias' % k) for k in range(n)],
+                 [f('offset2.%d.weight' % k) for k in range(n)] if multihead else None,
+                 [b('offset2.%d.bias' % k) for k in range(n)] if multihead else None)
+            self.pk[key] = w
+        b1 = w[1] if all(t is not None for t in w[1]) else None
+        b2 = w[3] if (multihead and all(t is not None for t in w[3])) else None
+        return ops.offset_convs(arm_loc, sizes, lv_off, w[0], b1, w[2], b2, want_nchw=want_nchw)
+
     def arm_heads(self, arm_sources, P, lv_off, multihead, with_offsets=True):
         """arm_loc + 1x1 offset convs: dualrefinedet_vggbn.py:154-165."""
         B = arm_sources[0].shape[0]
         arm_loc = torch.empty(B, P, 4, dtype=torch.float32, device=self.device)
 
         def level(k):
-            a = arm_sources[k]
-            self.head_into('arm_loc.%d' % k, a, arm_loc, 4, lv_off[k], P)
-            o = o2 = None
-            if with_offsets:
-                H, W = a.shape[1], a.shape[2]
-                view = arm_loc.view(B, P * 4)[:, lv_off[k] * 4:]
-                kw = dict(in_shape=(B, H, W, 12), in_sb=P * 4, out_dtype=torch.float32)
-                o = self.conv('offset.%d' % k, view, **kw)
-                if multihead:
-                    o2 = self.conv('offset2.%d' % k, view, **kw)
-            return o, o2
+            self.head_into('arm_loc.%d' % k, arm_sources[k], arm_loc, 4, lv_off[k], P)
 
-        res = self.parallel([(lambda k=k: level(k)) for k in range(len(arm_sources))])
-        offs = [r[0] for r in res] if with_offsets else []
-        offs2 = [r[1] for r in res] if with_offsets and multihead else []
+        self.parallel([(lambda k=k: level(k)) for k in range(len(arm_sources))])
+        if not with_offsets:
+            return arm_loc, [], []
+        sizes = [(a.shape[1], a.shape[2]) for a in arm_sources]
+        offs, offs2, _ = self.offset_maps(arm_loc, sizes, lv_off, multihead, want_nchw=False)
         return arm_loc, offs, offs2
 
     def arm_and_tcb(self, arm_sources, P, lv_off, multihead):
@@ -321,22 +330,16 @@ class Engine(object):
         arm_loc = torch.empty(B, P, 4, dtype=torch.float32, device=self.device)
 
         def level(k):
-            a = arm_sources[k]
-            self.head_into('arm_loc.%d' % k, a, arm_loc, 4, lv_off[k], P)
-            H, W = a.shape[1], a.shape[2]
-            view = arm_loc.view(B, P * 4)[:, lv_off[k] * 4:]
-            kw = dict(in_shape=(B, H, W, 12), in_sb=P * 4, out_dtype=torch.float32)
-            o = self.conv('offset.%d' % k, view, **kw)
-            o2 = self.conv('offset2.%d' % k, view, **kw) if multihead else None
-            return o, o2
+            self.head_into('arm_loc.%d' % k, arm_sources[k], arm_loc, 4, lv_off[k], P)
 
         fns = [lambda: self.last_trans(arm_sources[3])]
         fns += [(lambda k=k: self.trans_branch(arm_sources[k], k)) for k in range(3)]
         fns += [(lambda k=k: level(k)) for k in range(4)]
         res = self.parallel(fns)
-        x, trans, lv = res[0], res[1:4], res[4:8]
+        x, trans = res[0], res[1:4]
+        offs, offs2, _ = self.offset_maps(arm_loc, [(a.shape[1], a.shape[2]) for a in arm_sources], lv_off, multihead, False)
         odm = self.fpn_topdown(x, [x], trans)
-        return arm_loc, [r[0] for r in lv], ([r[1] for r in lv] if multihead else []), odm
+        return arm_loc, offs, offs2, odm
 
     def trunk_arm_tcb(self, x_nchw, bn, size, multihead, want_nchw_offsets=True):
         """VGG trunk with the ARM heads (+1x1 offset convs) and the TCB transfer branches forked the moment their
@@ -354,13 +357,6 @@ class Engine(object):
 
         def level(k, a):
             self.head_into('arm_loc.%d' % k, a, arm_loc, 4, lv_off[k], P)
-            H, W = a.shape[1], a.shape[2]
-            view = arm_loc.view(B, P * 4)[:, lv_off[k] * 4:]
-            kw = dict(in_shape=(B, H, W, 12), in_sb=P * 4, out_dtype=torch.float32)
-            o = self.conv('offset.%d' % k, view, **kw)
-            o2 = self.conv('offset2.%d' % k, view, **kw) if multihead else None
-            on = ops.nhwc_to_nchw_f32(o) if want_nchw_offsets else None      # the reference returns NCHW offset maps
-            return o, o2, on
 
         def on_source(k, a):
             assert a.shape[1] == sizes[k], (a.shape, sizes)
@@ -383,9 +379,11 @@ class Engine(object):
             x = self.conv('latent_layers.%d' % k, u, 1, 1, relu=True)
             odm.append(x)
         odm.reverse()
-        lv = [self.join(handles['arm', k]) for k in range(4)]
-        return (arm_loc, [r[0] for r in lv], [r[1] for r in lv] if multihead else [],
-                [r[2] for r in lv] if want_nchw_offsets else None, odm, P, lv_off)
+        for k in range(4):
+            self.join(handles['arm', k])
+        # the 1x1 offset convs of all four levels (+ the NCHW maps the reference returns) in one launch, once every ARM head is in
+        offs, offs2, offs_nchw = self.offset_maps(arm_loc, [(sd, sd) for sd in sizes], lv_off, multihead, want_nchw_offsets)
+        return arm_loc, offs, offs2, offs_nchw, odm, P, lv_off
 
     def deform_heads(self, feats, offs, offs2, P, lv_off, num_classes, dg, multihead, loc_name='odm_loc',
                      conf_name='odm_conf', softmax=True):

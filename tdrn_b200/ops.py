@@ -8,7 +8,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import F32, BF16, ConvDesc, DeformHeadDesc, check, ptr, stream_handle
+from ._lib import F32, BF16, ConvDesc, DeformHeadDesc, OffsetLevel, check, ptr, stream_handle
 
 BN_EPS = 1e-5
 
@@ -311,6 +311,31 @@ def nchw_f32_to_nhwc(x_nchw, dtype):
     check(_lib.lib().tdrn_nchw_f32_to_nhwc(ptr(x), ptr(out), B, C, H, W, _dt(out), stream_handle()),
           'tdrn_nchw_f32_to_nhwc')
     return out
+
+
+def offset_convs(arm_loc, sizes, lv_off, w1, b1, w2=None, b2=None, want_nchw=True):
+    """All levels' `offset.k` (and `offset2.k`) 1x1 convs on the flattened ARM regression [B,P,4] in one launch.
+    sizes [(H, W)], lv_off [prior offset], w1/w2 lists of [c,12] fp32 CUDA tensors, b1/b2 lists of [c] or None.
+    -> (offsets NHWC fp32 list, offsets2 NHWC list (or []), offsets NCHW list (or None))"""
+    arm = _cuda(arm_loc, 'arm_loc')
+    assert arm.dtype == torch.float32
+    B, P, _ = arm.shape
+    n = len(sizes)
+    c1 = w1[0].shape[0]
+    c2 = w2[0].shape[0] if w2 else 0
+    o1 = [torch.empty(B, h, w, c1, dtype=torch.float32, device=arm.device) for h, w in sizes]
+    o2 = [torch.empty(B, h, w, c2, dtype=torch.float32, device=arm.device) for h, w in sizes] if c2 else []
+    on = [torch.empty(B, c1, h, w, dtype=torch.float32, device=arm.device) for h, w in sizes] if want_nchw else None
+    pv = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    lv = (OffsetLevel * n)()
+    for k, (h, w) in enumerate(sizes):
+        lv[k] = OffsetLevel(H=h, W=w, prior_off=int(lv_off[k]), w1=pv(w1[k]), b1=pv(b1[k] if b1 else None),
+                            w2=pv(w2[k] if c2 else None), b2=pv(b2[k] if (c2 and b2) else None),
+                            out1=pv(o1[k]), out2=pv(o2[k] if c2 else None), out1_nchw=pv(on[k] if want_nchw else None))
+    work = 2.0 * B * sum(h * w for h, w in sizes) * 12 * (c1 + c2)
+    with _Timed('conv_simt|offset convs, %d levels 12x%d+%d' % (n, c1, c2), work):
+        check(_lib.lib().tdrn_offset_convs(ptr(arm), B, P, n, lv, c1, c2, stream_handle()), 'tdrn_offset_convs')
+    return o1, o2, on
 
 
 def deform_conv_nchw(input, offset, weight, stride, pad, dil, dg):
