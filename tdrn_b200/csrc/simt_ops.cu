@@ -766,32 +766,40 @@ struct OffsetLevels {
     float *o1[TDRN_MAX_OFFSET_LEVELS], *o2[TDRN_MAX_OFFSET_LEVELS], *o1_nchw[TDRN_MAX_OFFSET_LEVELS];
 };
 
+constexpr int OFF_PX = 64;      // pixels per block
+
+// grid (blocks of all levels, B); a block owns OFF_PX pixels of one level of one image: the level's [c1 + c2] x 12 weights,
+// biases and the block's 12-vectors are staged in shared memory once, then one (pixel, channel) output per thread and step.
 __global__ void __launch_bounds__(256) offset_convs_kernel(const float *__restrict__ arm_loc, const OffsetLevels L)
 {
-    const long long per_img = L.first[L.n];
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= per_img * L.B) return;
-    const int b = (int)(t / per_img);
-    const long long i = t - (long long)b * per_img;
+    extern __shared__ float off_smem[];            // w [cc][12] | bias [cc] | arm [OFF_PX][12]
+    const int b = blockIdx.y;
     int k = 0;
-    while (k + 1 < L.n && i >= L.first[k + 1]) ++k;
+    while (k + 1 < L.n && (long long)blockIdx.x >= L.first[k + 1]) ++k;      // first[] = running block counts here
     const int cc = L.c1 + L.c2;
-    const long long j = i - L.first[k];
-    const int pix = (int)(j / cc), ch = (int)(j - (long long)pix * cc);
-    const float *a = arm_loc + ((long long)b * L.P + L.prior_off[k] + (long long)pix * 3) * 4;       // 12 consecutive floats
-    const bool second = ch >= L.c1;
-    const int co = second ? ch - L.c1 : ch;
-    const float *w = (second ? L.w2[k] : L.w1[k]) + co * 12;
-    const float *bias = second ? L.b2[k] : L.b1[k];
-    float acc = bias ? bias[co] : 0.f;
-#pragma unroll
-    for (int c = 0; c < 12; ++c) acc = fmaf(a[c], w[c], acc);
     const int HW = L.H[k] * L.W[k];
-    if (second) {
-        L.o2[k][((long long)b * HW + pix) * L.c2 + co] = acc;
-    } else {
-        L.o1[k][((long long)b * HW + pix) * L.c1 + co] = acc;
-        if (L.o1_nchw[k]) L.o1_nchw[k][((long long)b * L.c1 + co) * HW + pix] = acc;
+    const int pix0 = (int)(blockIdx.x - L.first[k]) * OFF_PX;
+    const int npx = min(OFF_PX, HW - pix0);
+    float *w = off_smem, *bias = w + cc * 12, *arm = bias + cc;
+    for (int i = threadIdx.x; i < cc * 12; i += blockDim.x) w[i] = i < L.c1 * 12 ? L.w1[k][i] : L.w2[k][i - L.c1 * 12];
+    for (int i = threadIdx.x; i < cc; i += blockDim.x)
+        bias[i] = i < L.c1 ? (L.b1[k] ? L.b1[k][i] : 0.f) : (L.b2[k] ? L.b2[k][i - L.c1] : 0.f);
+    const float *a = arm_loc + ((long long)b * L.P + L.prior_off[k] + (long long)pix0 * 3) * 4;     // npx * 12 consecutive floats
+    for (int i = threadIdx.x; i < npx * 12; i += blockDim.x) arm[i] = a[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < npx * cc; i += blockDim.x) {
+        const int px = i / cc, ch = i - px * cc;
+        const float *av = arm + px * 12, *wv = w + ch * 12;
+        float acc = bias[ch];
+#pragma unroll
+        for (int c = 0; c < 12; ++c) acc = fmaf(av[c], wv[c], acc);
+        const int pix = pix0 + px;
+        if (ch >= L.c1) {
+            L.o2[k][((long long)b * HW + pix) * L.c2 + (ch - L.c1)] = acc;
+        } else {
+            L.o1[k][((long long)b * HW + pix) * L.c1 + ch] = acc;
+            if (L.o1_nchw[k]) L.o1_nchw[k][((long long)b * L.c1 + ch) * HW + pix] = acc;
+        }
     }
 }
 }  // namespace tdrn
@@ -811,11 +819,12 @@ extern "C" int tdrn_offset_convs(const float *arm_loc, int B, int P, int n_level
         L.w1[k] = lv[k].w1; L.b1[k] = lv[k].b1; L.w2[k] = lv[k].w2; L.b2[k] = lv[k].b2;
         L.o1[k] = lv[k].out1; L.o2[k] = lv[k].out2; L.o1_nchw[k] = lv[k].out1_nchw;
         L.first[k] = run;
-        run += (long long)lv[k].H * lv[k].W * (c1 + c2);
+        run += ((long long)lv[k].H * lv[k].W + tdrn::OFF_PX - 1) / tdrn::OFF_PX;      // blocks of this level
     }
     L.first[n_levels] = run;
-    const long long total = run * B;
-    tdrn::offset_convs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, tdrn::as_stream(stream)>>>(arm_loc, L);
+    const size_t smem = (size_t)((c1 + c2) * 13 + tdrn::OFF_PX * 12) * sizeof(float);
+    TDRN_REQUIRE(smem <= 48 * 1024, "tdrn_offset_convs: too many offset channels (%d + %d)", c1, c2);
+    tdrn::offset_convs_kernel<<<dim3((unsigned)run, (unsigned)B), 256, smem, tdrn::as_stream(stream)>>>(arm_loc, L);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }

@@ -371,6 +371,14 @@ class Engine(object):
         else:
             for k, a in enumerate(self.vgg_trunk(x_nchw, bn)):
                 on_source(k, a)
+        def offsets_branch():
+            # the 1x1 offset convs of all four levels (+ the NCHW maps the reference returns) in one launch, once every ARM head is
+            # in -- on a side stream, under the FPN top-down chain
+            for k in range(4):
+                self.join(handles['arm', k])
+            return self.offset_maps(arm_loc, [(sd, sd) for sd in sizes], lv_off, multihead, want_nchw_offsets)
+
+        h_off = self.spawn(offsets_branch)
         x = self.join(handles['last'])
         odm = [x]
         for k in range(3):
@@ -379,10 +387,7 @@ class Engine(object):
             x = self.conv('latent_layers.%d' % k, u, 1, 1, relu=True)
             odm.append(x)
         odm.reverse()
-        for k in range(4):
-            self.join(handles['arm', k])
-        # the 1x1 offset convs of all four levels (+ the NCHW maps the reference returns) in one launch, once every ARM head is in
-        offs, offs2, offs_nchw = self.offset_maps(arm_loc, [(sd, sd) for sd in sizes], lv_off, multihead, want_nchw_offsets)
+        offs, offs2, offs_nchw = self.join(h_off)
         return arm_loc, offs, offs2, offs_nchw, odm, P, lv_off
 
     def deform_heads(self, feats, offs, offs2, P, lv_off, num_classes, dg, multihead, loc_name='odm_loc',
