@@ -361,7 +361,7 @@ def run_gpu(args, rank, world, local_rank):
     import torch.distributed as dist
     from tdrn_b200 import ops, _lib
     from tdrn_b200.utils.synthetic import frames as make_frames
-    from tdrn_b200.utils.shard import shard_clips
+    from tdrn_b200.utils.shard import shard_clips, AsyncGather
 
     wl = WORKLOADS[args.config]()
     BATCH, SIZE, NUM_CLASSES, TOP_K = wl.batch, wl.size, wl.num_classes, wl.detect_kw['top_k']
@@ -474,21 +474,13 @@ def run_gpu(args, rank, world, local_rank):
     # Issued asynchronously behind an event: the compute streams never wait for a collective, i.e. for another rank; an
     # instance's buffer is only reused n_slots steps later, after its gather has completed.
     do_gather = world > 1 and not args.no_gather
-    gathered = [torch.empty(world * BATCH, NUM_CLASSES, TOP_K, 5, device=dev) for _ in range(n_slots)] if do_gather else None
-    gather_stream = torch.cuda.Stream(dev) if do_gather else None
-    gather_work = [None] * n_slots
-    step_done = [torch.cuda.Event() for _ in range(n_slots)]
+    ag = AsyncGather(n_slots, (BATCH, NUM_CLASSES, TOP_K, 5), device=dev) if do_gather else None
 
     def gather_async(q, src, st):
-        step_done[q].record(st)
-        with torch.cuda.stream(gather_stream):
-            gather_stream.wait_event(step_done[q])
-            gather_work[q] = dist.all_gather_into_tensor(gathered[q], src, async_op=True)
+        ag.issue(q, src, producer_stream=st)
 
     def wait_gather(q):
-        if gather_work[q] is not None:
-            gather_work[q].wait()                # the CURRENT stream waits for the gather that last read this instance's output
-            gather_work[q] = None
+        ag.wait(q)                               # the CURRENT stream waits for the gather that last read this instance's output
 
     def replay(q, u8=False):
         if args.no_graph:
@@ -623,7 +615,7 @@ def run_gpu(args, rank, world, local_rank):
             if do_gather:                                   # and the gathered buffer holds this rank's rows at its offset
                 for q in range(n_slots):
                     wait_gather(q)
-                inflight_ok = inflight_ok and bool(torch.equal(gathered[0][rank * BATCH:(rank + 1) * BATCH], static_outs[0]))
+                inflight_ok = inflight_ok and bool(torch.equal(ag.out[0][rank * BATCH:(rank + 1) * BATCH], static_outs[0]))
         torch.cuda.synchronize()
         if not inflight_ok:       # reported in the JSON line (inflight_replay_matches_serial: false), never silently dropped
             sys.stderr.write('bench: WARNING detections of overlapped graph replays differ from a serial eager pass\n')

@@ -15,6 +15,7 @@
 // quadrant; bias, ReLU, optional fused 2x2 max-pool by warp shuffles, bf16/fp32 store); TMEM accumulator double-buffered.
 #include "halo_common.cuh"
 #include <stdlib.h>
+#include <stdio.h>
 
 // Compile-time experiments for the main loops (all OFF in the shipped build: the code below is then removed by the
 // preprocessor; build with e.g. TDRN_NVCC_EXTRA="-DTDRN_HALO_PREFETCH=6" python -m tdrn_b200.build --force):
@@ -101,14 +102,18 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_c
             tc_fence_after();
             const uint32_t sW_u = smem_u32(sW), sA_u = smem_u32(sA);
             uint32_t it = 0, tcount = 0;
+            long long c_te = 0, c_af = 0, c_start = p.dbg ? clock64() : 0, c_mark = c_start;    // TDRN_HALO_TIMING buckets
             for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++tcount) {
                 const uint32_t buf = tcount & 1u;
                 mbar_wait(&t_empty[buf], ((tcount >> 1) & 1u) ^ 1u);
+                if (p.dbg) { const long long c = clock64(); c_te += c - c_mark; c_mark = c; }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
                 for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
                     const uint32_t s = it % (uint32_t)p.stages, ph = (it / (uint32_t)p.stages) & 1u;
+                    if (p.dbg) c_mark = clock64();
                     mbar_wait(&a_full[s], ph);
+                    if (p.dbg) { const long long c = clock64(); c_af += c - c_mark; c_mark = c; }
                     tc_fence_after();
                     const uint32_t a0 = sA_u + s * (uint32_t)HL_A_STRIDE;
 #pragma unroll
@@ -127,6 +132,12 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_c
                     umma_commit(&a_empty[s]);
                 }
                 umma_commit(&t_full[buf]);
+                if (p.dbg) c_mark = clock64();
+            }
+            if (p.dbg) {
+                const long long tot = clock64() - c_start;
+                p.dbg[blockIdx.x * 5 + 0] = tot; p.dbg[blockIdx.x * 5 + 1] = c_te; p.dbg[blockIdx.x * 5 + 2] = c_af;
+                p.dbg[blockIdx.x * 5 + 3] = tot - c_te - c_af; p.dbg[blockIdx.x * 5 + 4] = tcount;
             }
         }
         __syncwarp();
@@ -401,6 +412,23 @@ int conv_halo_try(const tdrn_conv_desc *d, const void *in, const void *weight, c
         return TDRN_OK;
     }
     const size_t smem = 1024 + (size_t)p.w_bytes + (size_t)stages * HL_A_STRIDE;
+    static const bool timing = getenv("TDRN_HALO_TIMING") != nullptr;        // development aid: where does the MMA issuer's time go?
+    if (timing) {
+        static long long *dbg = nullptr;
+        if (!dbg) TDRN_CUDA(cudaMalloc(&dbg, 148 * 5 * sizeof(long long)));
+        TDRN_CUDA(cudaMemsetAsync(dbg, 0, 148 * 5 * sizeof(long long), st));
+        p.dbg = dbg;
+        int rc = p.n_pad16 > 64 ? launch_halo<128>(tmA, tmB, p, smem, st) : launch_halo<64>(tmA, tmB, p, smem, st);
+        long long h[148 * 5];
+        TDRN_CUDA(cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+        TDRN_CUDA(cudaStreamSynchronize(st));
+        double t[5] = {0, 0, 0, 0, 0};
+        for (int i = 0; i < 148; ++i) for (int j = 0; j < 5; ++j) t[j] += (double)h[i * 5 + j] / 148.0;
+        fprintf(stderr, "halo timing Cin %d Cout %d @%dx%d: MMA-issuer cycles per tile: total %.0f = waiting for the epilogue (t_empty) %.0f + "
+                        "waiting for the halo box (a_full) %.0f + issuing %.0f  (%.0f tiles per CTA, %d MMAs per tile)\n", p.Cin, p.Cout, p.H, p.W,
+                t[0] / t[4], t[1] / t[4], t[2] / t[4], t[3] / t[4], t[4], 36 * p.cblocks);
+        return rc;
+    }
     return p.n_pad16 > 64 ? launch_halo<128>(tmA, tmB, p, smem, st) : launch_halo<64>(tmA, tmB, p, smem, st);
 }
 

@@ -910,7 +910,12 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     p.n_tiles = (n_pad16 + BN - 1) / BN;
 
     {   // small maps with a long K loop: split K over a cluster (conv_splitk_kernel).  S is a function of the LAYER's shape only.
-        static const bool no_splitk = getenv("TDRN_NO_SPLITK") != nullptr;
+        // OPT-IN (TDRN_SPLITK=1, read per call so that tests can switch it).  Measured r02n (b32, two steps in flight): the summed
+        // conv time drops (2.662 -> 2.616 ms) but the STEP gets slower (2.728 -> 2.780 ms), and batch-1 MobileNet latency too (0.531
+        // -> 0.567 ms): a cluster launch costs ~3 us more than a plain one and its 8 CTAs need 8 free SMs of one GPC at once, which
+        // stalls behind the persistent trunk kernels of the other step in flight.
+        const char *sk_env = getenv("TDRN_SPLITK");
+        const bool no_splitk = !(sk_env && sk_env[0] == '1');
         const int num_kb = p.taps * (p.Cin >> 6);
         const int n_tiles64 = (n_pad16 + SK_BN - 1) / SK_BN;
         // Measured r02l (b32): splitting pays where the cluster grid still fits one wave of 148 SMs -- the Cout <= 64 heads on the

@@ -23,6 +23,7 @@ struct HaloP {
     long long out_sb, out_sp; int out_w;
     int relu, out_f32, pool;
     int debug_skip_epilogue;     // timing experiments only (TDRN_HALO_DEBUG=1): results are NOT written
+    long long *dbg;              // TDRN_HALO_TIMING=1: per CTA {cycles total, waiting for t_empty, waiting for a_full, issuing, tiles}
 };
 
 // SWIZZLE_128B K-major descriptor with an arbitrary (16-byte aligned) start and stride between 8-row groups.
@@ -37,16 +38,45 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
     return d;
 }
 
+// bias / ReLU / (pool) / store of one 32-column chunk held in v[]
+__device__ __forceinline__ void halo_epilogue_chunk(const HaloP &p, float (&v)[32], const float *s_bias, int n0, int c0,
+                                                    int b, int x, int y, int wl, int hl, bool valid);
+
 // Epilogue of one 128-pixel tile: accumulator columns [0, ncols) at `trow` are output channels n0 .. n0+ncols-1.
-// `half` selects which of the two warps of this TMEM lane quadrant handles a 32-column chunk.
+// `half` selects which of the two warps of this TMEM lane quadrant handles a 32-column chunk.  A warp's chunks (one at
+// ncols = 64, two at 128) are LOADED TOGETHER before the single tcgen05.wait::ld: next to running MMAs a tcgen05.ld takes
+// several hundred cycles (ncu r02n, conv2_1: LDTM + the first use of its result = 26 % of all stall samples, the epilogue
+// took longer than the tile's MMAs), and back-to-back load -> wait -> process pairs paid that latency twice per tile.
 __device__ __forceinline__ void halo_epilogue_tile(const HaloP &p, uint32_t trow, const float *s_bias, int n0, int ncols, int half,
                                            int b, int x, int y, int wl, int hl)
 {
     const bool valid = x < p.W && y < p.H;
-    for (int c0 = half * 32; c0 < (p.debug_skip_epilogue == 1 ? 0 : ncols); c0 += 64) {
+    if (p.debug_skip_epilogue == 1) return;
+    const int ca = half * 32, cb2 = half * 32 + 64;
+    if (cb2 < ncols) {
+        uint32_t ra[32], rb[32];
+        tmem_ld32_issue(trow + (uint32_t)ca, ra);
+        tmem_ld32_issue(trow + (uint32_t)cb2, rb);
+        tmem_ld_wait32(ra);
+        tmem_ld_pin32(rb);
         float v[32];
-        tmem_ld32(trow + (uint32_t)c0, v);
-        if (n0 + c0 >= p.Cout) continue;                     // warp-uniform
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]);
+        if (n0 + ca < p.Cout) halo_epilogue_chunk(p, v, s_bias, n0, ca, b, x, y, wl, hl, valid);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[i]);
+        if (n0 + cb2 < p.Cout) halo_epilogue_chunk(p, v, s_bias, n0, cb2, b, x, y, wl, hl, valid);
+    } else if (ca < ncols) {
+        float v[32];
+        tmem_ld32(trow + (uint32_t)ca, v);
+        if (n0 + ca < p.Cout) halo_epilogue_chunk(p, v, s_bias, n0, ca, b, x, y, wl, hl, valid);
+    }
+}
+
+__device__ __forceinline__ void halo_epilogue_chunk(const HaloP &p, float (&v)[32], const float *s_bias, int n0, int c0,
+                                                    int b, int x, int y, int wl, int hl, bool valid)
+{
+    {
         const int nv = min(32, p.Cout - n0 - c0);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -70,7 +100,7 @@ __device__ __forceinline__ void halo_epilogue_tile(const HaloP &p, uint32_t trow
                     v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, HL_BW));
                 }
             }
-            if (!store) continue;
+            if (!store) return;
             float *op = (float *)p.out + o;
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (j < nv) op[j] = v[j];
@@ -92,7 +122,7 @@ __device__ __forceinline__ void halo_epilogue_tile(const HaloP &p, uint32_t trow
                     q[j] = *(const uint32_t *)&m;
                 }
             }
-            if (!store) continue;
+            if (!store) return;
             __nv_bfloat16 *op = (__nv_bfloat16 *)p.out + o;
             if (nv == 32 && ((o & 7) == 0)) {
 #pragma unroll

@@ -170,6 +170,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v)
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Asynchronous halves of tmem_ld32: issue the load of 32 columns, and -- after any number of issued loads -- ONE
+// tcgen05.wait::ld.  tmem_ld_wait32 names the 32 destination registers as read-write operands so that the compiler cannot
+// schedule a use of them ahead of the wait; tmem_ld_pin32 does the same for a second (third ...) set of registers that the
+// same wait covers (an empty asm placed right after the wait).
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+#define TDRN_RW32(r) "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), \
+                     "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), \
+                     "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), \
+                     "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : TDRN_RW32(r) : : "memory");
+}
+__device__ __forceinline__ void tmem_ld_pin32(uint32_t (&r)[32])
+{
+    asm volatile("" : TDRN_RW32(r) : : "memory");
+}
+
 // UMMA shared-memory descriptor, K-major operand tile stored as rows of 128 bytes (64 bf16) with the
 // 128-byte swizzle (8-row / 1024-byte atoms, what TMA SWIZZLE_128B writes).  cute::UMMA::SmemDescriptor:
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=1024>>4)

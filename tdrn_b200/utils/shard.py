@@ -68,3 +68,49 @@ def gather_detections(local, n_units=None, group=None, out=None):
     parts = [buf[r * m:r * m + sizes[r]] for r in range(world)]
     res = torch.cat(parts, 0)
     return res if out is None else out.copy_(res)
+
+
+class AsyncGather(object):
+    """End-of-step gather that never makes a compute stream wait for another rank.
+
+    One slot per in-flight step (a CUDA-graph instance, or simply a step index modulo ``n_slots``): ``issue(q, local)`` starts
+    an asynchronous all_gather of slot q's detection buffer into its own output tensor and returns at once; ``wait(q)`` --
+    called before slot q's buffers are written again, ``n_slots`` steps later -- makes the CURRENT stream wait for that
+    gather.  On CUDA the gather runs behind an event recorded on the producing stream (it starts when the step's kernels
+    are done, on NCCL's own stream); with gloo on the CPU (tests/test_shard.py) the same calls are plain async work handles.
+    A slow rank therefore delays only gathers, up to ``n_slots - 1`` steps, never the other ranks' kernels."""
+
+    def __init__(self, n_slots, local_shape, dtype=torch.float32, device=None, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        shape = (self.world * local_shape[0],) + tuple(local_shape[1:])
+        self.out = [torch.empty(shape, dtype=dtype, device=device) for _ in range(n_slots)]
+        self.work = [None] * n_slots
+        self.cuda = device is not None and torch.device(device).type == 'cuda'
+        self.stream = torch.cuda.Stream(device) if self.cuda and self.world > 1 else None
+        self.done = [torch.cuda.Event() for _ in range(n_slots)] if self.stream is not None else None
+
+    def issue(self, q, local, producer_stream=None):
+        if self.world == 1:
+            self.out[q].copy_(local)
+            return
+        if self.stream is not None:
+            st = producer_stream if producer_stream is not None else torch.cuda.current_stream()
+            self.done[q].record(st)
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(self.done[q])
+                self.work[q] = dist.all_gather_into_tensor(self.out[q], local, group=self.group, async_op=True)
+        else:
+            self.work[q] = dist.all_gather_into_tensor(self.out[q], local.contiguous(), group=self.group, async_op=True)
+
+    def wait(self, q):
+        """The current stream (CUDA) / the caller (CPU) waits for the gather that last read slot q's buffer."""
+        if self.work[q] is not None:
+            self.work[q].wait()
+            self.work[q] = None
+        return self.out[q]
+
+    def wait_all(self):
+        for q in range(len(self.work)):
+            self.wait(q)

@@ -339,11 +339,11 @@ def test_conv_tc_split3_deconv_residual():
     (3, 256, 512, 3, 2, 1, 10, 10, True),       # extras.3: stride 2, cluster of 2
     (1, 1024, 256, 1, 1, 0, 10, 10, True),      # a single tile (batch 1): 16 k-blocks over 2 CTAs
 ])
-def test_conv_splitk_cluster(b, cin, cout, k, stride, pad, h, w, relu):
+def test_conv_splitk_cluster(monkeypatch, b, cin, cout, k, stride, pad, h, w, relu):
     """Small maps: K split over a thread-block cluster, partial tiles summed through distributed shared memory
     (conv_splitk_kernel).  Same reference and tolerance as the plain kernel; the result of an image must not depend on
     the batch it is in (the cluster size is a function of the layer's shape only)."""
-    from tdrn_b200 import ops
+    from tdrn_b200 import ops, _lib
     g = torch.Generator().manual_seed(cin + cout + k + b)
     x = _bf(torch.randn(b, cin, h, w, generator=g))
     wt = _bf(torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5)
@@ -353,6 +353,7 @@ def test_conv_splitk_cluster(b, cin, cout, k, stride, pad, h, w, relu):
         ref = F.relu(ref)
     pc = ops.PackedConv(wt, bias, None, stride, pad, 1, device='cuda')
     xg = _nhwc(x).cuda().to(torch.bfloat16)
+    monkeypatch.setenv('TDRN_SPLITK', '1')                   # opt-in path (csrc/conv_tc.cu says why it is not the default)
     out = ops.conv2d(xg, pc, relu=relu, out_dtype=torch.float32, use_tc=True)
     torch.cuda.synchronize()
     assert rel_err(_nchw(out).cpu().numpy(), ref.numpy()) < 2e-5
@@ -360,3 +361,6 @@ def test_conv_splitk_cluster(b, cin, cout, k, stride, pad, h, w, relu):
     assert rel_err(_nchw(out16.float()).cpu().numpy(), ref.numpy()) < 6e-3
     one = ops.conv2d(xg[b - 1:b].contiguous(), pc, relu=relu, out_dtype=torch.float32, use_tc=True)
     assert torch.equal(one[0], out[b - 1])
+    monkeypatch.delenv('TDRN_SPLITK')
+    plain = ops.conv2d(xg, pc, relu=relu, out_dtype=torch.float32, use_tc=True)      # the default kernel: same values to fp32 rounding
+    assert rel_err(out.cpu().numpy(), plain.cpu().numpy()) < 1e-5

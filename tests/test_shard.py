@@ -80,3 +80,44 @@ def test_two_rank_gather_reassembles_the_batch(n_units):
         p.join(60)
         assert p.exitcode == 0
     assert res == [(0, True, 2.0), (1, True, 2.0)]
+
+
+def _async_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        n_slots, steps = 3, 7
+        ag = shard.AsyncGather(n_slots, (2, 3, 4, 5))
+        bufs = [torch.zeros(2, 3, 4, 5) for _ in range(n_slots)]
+        ok = True
+        for i in range(steps):
+            s = i % n_slots
+            prev = ag.wait(s)                              # the gather that read bufs[s] three steps ago is complete
+            if i >= n_slots:
+                exp = torch.cat([torch.full((2, 3, 4, 5), float(100 * r + i - n_slots)) for r in range(world)], 0)
+                ok = ok and torch.equal(prev, exp)
+            bufs[s].fill_(float(100 * rank + i))           # "the step": rewrite the slot's buffer
+            ag.issue(s, bufs[s])
+        ag.wait_all()
+        last = steps - 1
+        exp = torch.cat([torch.full((2, 3, 4, 5), float(100 * r + last)) for r in range(world)], 0)
+        ok = ok and torch.equal(ag.out[last % n_slots], exp)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_async_gather_slots():
+    """AsyncGather (what bench.py uses at N > 1): per-slot asynchronous all_gather, waited for only when the slot is reused."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_async_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
