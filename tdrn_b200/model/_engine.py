@@ -151,13 +151,24 @@ class Engine(object):
         ceil_mode = kw.pop('ceil_mode', False)
         if (self.use_x3 and pc.w_x3 is not None and x.dtype == torch.float32 and not kw.get('dg') and kw.get('in_shape') is None
                 and (stride in (1, 2) or deconv)):
-            xs = getattr(x, '_tdrn_split', None)              # one split per activation tensor, shared by all its consumers
-            if xs is None:
+            # one split per activation tensor, shared by all its consumers -- which may sit on different branch streams (an ARM
+            # source feeds its ARM head and its TCB branch): the split is made on the first consumer's stream and carries an
+            # event the others wait for
+            cur = torch.cuda.current_stream()
+            ent = getattr(x, '_tdrn_split', None)
+            if ent is None:
                 xs = ops.split_bf16(x)
+                ev = torch.cuda.Event()
+                ev.record(cur)
                 try:
-                    x._tdrn_split = xs
+                    x._tdrn_split = (xs, ev, cur)
                 except Exception:
                     pass
+            else:
+                xs, ev, st = ent
+                if st != cur:
+                    cur.wait_event(ev)
+                    xs.record_stream(cur)
             kw.setdefault('out_dtype', torch.float32)
             if kw.pop('pool', False):
                 H, W = x.shape[1], x.shape[2]
