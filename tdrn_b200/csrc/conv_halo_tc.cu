@@ -32,7 +32,8 @@ namespace tc {
 
 template <int BN>
 __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                  const __grid_constant__ CUtensorMap tmB, const HaloP p)
+                                                                  const __grid_constant__ CUtensorMap tmB,
+                                                                  const __grid_constant__ CUtensorMap tmO, const HaloP p)
 {
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t a_full[HL_MAX_STAGES], a_empty[HL_MAX_STAGES];
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_c
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     uint8_t *sW = base;                               // [9*cblocks][n_pad16 rows][128 B]
     uint8_t *sA = base + p.w_bytes;                   // stages x HL_A_STRIDE (w_bytes is a multiple of 2048)
+    uint8_t *sO = sA + (size_t)p.stages * HL_A_STRIDE;   // tma_out: two 16 KB staging boxes of the TMA-store epilogue
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
     const uint32_t kb_bytes = (uint32_t)p.n_pad16 * 128u;
@@ -149,18 +151,42 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_c
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const int r = quad * 32 + lane;
         const int wl = r & (HL_BW - 1), hl = r >> 3;
-        uint32_t tcount = 0;
+        uint32_t tcount = 0, git = 0;
+        const bool leader = threadIdx.x == 64;
+        if (p.tma_out) {
+            if (leader) tma_prefetch_desc(&tmO);
+            for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++tcount) {
+                const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+                const uint32_t buf = tcount & 1u;
+                mbar_wait(&t_full[buf], (tcount >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
+                halo_epilogue_tile_tma(p, &tmO, sO, git, leader, trow, s_bias, 0, p.n_pad16, quad, half, lane, b,
+                                       (rem % p.tiles_w) * HL_BW, (rem / p.tiles_w) * HL_BH, [&]() {
+                                           tc_fence_before();
+                                           __syncwarp();
+                                           if (lane == 0) mbar_arrive(&t_empty[buf]);
+                                       });
+            }
+            if (leader) bulk_wait_read<0>();
+        } else
         for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++tcount) {
             const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
             const int x = (rem % p.tiles_w) * HL_BW + wl, y = (rem / p.tiles_w) * HL_BH + hl;
             const uint32_t buf = tcount & 1u;
+            const long long e0 = p.dbg ? clock64() : 0;
             mbar_wait(&t_full[buf], (tcount >> 1) & 1u);
+            const long long e1 = p.dbg ? clock64() : 0;
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
             halo_epilogue_tile(p, trow, s_bias, 0, p.n_pad16, half, b, x, y, wl, hl);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[buf]);
+            if (p.dbg && lane == 0) {
+                atomicAdd((unsigned long long *)&p.dbg[148 * 5 + 16 + warp], (unsigned long long)(e1 - e0));             // waiting for the tile
+                atomicAdd((unsigned long long *)&p.dbg[148 * 5 + 32 + warp], (unsigned long long)(clock64() - e1));       // working on it
+            }
         }
     }
 
@@ -185,12 +211,13 @@ constexpr int HS_A_STRIDE = (HS_A_BYTES + 1023) & ~1023;  // 41984
 constexpr int HS_A_STAGES = 2;
 constexpr int HS_BN = 128;
 constexpr int HS_B_BYTES = HS_BN * 128;                   // 16 KB per (tap, channel block)
-constexpr int HS_B_STAGES = 7;
+constexpr int HS_B_STAGES = 6;                           // (7 before the TMA-store epilogue took 32 KB for its staging boxes)
 constexpr int HS_THREADS = 352;
-constexpr int HS_SMEM = 1024 + HS_A_STAGES * HS_A_STRIDE + HS_B_STAGES * HS_B_BYTES;
+constexpr int HS_SMEM = 1024 + HS_A_STAGES * HS_A_STRIDE + HS_B_STAGES * HS_B_BYTES + 2 * 128 * 128;
 
 __global__ void __launch_bounds__(HS_THREADS, 1) conv_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                         const __grid_constant__ CUtensorMap tmB, const HaloP p)
+                                                                         const __grid_constant__ CUtensorMap tmB,
+                                                                         const __grid_constant__ CUtensorMap tmO, const HaloP p)
 {
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t a_full[HS_A_STAGES], a_empty[HS_A_STAGES];
@@ -202,6 +229,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) conv_halo_stream_kernel(const _
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = base;
     uint8_t *sB = base + HS_A_STAGES * HS_A_STRIDE;
+    uint8_t *sO = sB + HS_B_STAGES * HS_B_BYTES;                  // two 16 KB staging boxes of the TMA-store epilogue
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pairs_w = p.tiles_w >> 1;                           // super-tiles per row
     const int units_per_img = pairs_w * p.tiles_h;
@@ -319,7 +347,31 @@ __global__ void __launch_bounds__(HS_THREADS, 1) conv_halo_stream_kernel(const _
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const int r = quad * 32 + lane;
         const int wl = r & (HL_BW - 1), hl = r >> 3;
-        uint32_t tcount = 0;
+        uint32_t tcount = 0, git = 0;
+        const bool leader = threadIdx.x == 64;
+        if (p.tma_out) {
+            if (leader) tma_prefetch_desc(&tmO);
+            for (int unit = blockIdx.x; unit < total; unit += gridDim.x, ++tcount) {
+                const int mu = unit % m_units, n0 = (unit / m_units) * HS_BN;
+                const int b = mu / units_per_img, rem = mu - b * units_per_img;
+                const int y0 = (rem / pairs_w) * HL_BH, x0 = (rem % pairs_w) * (2 * HL_BW);
+                const uint32_t buf = tcount & 1u;
+                mbar_wait(&t_full[buf], (tcount >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (2 * HS_BN) + mt * HS_BN;
+                    halo_epilogue_tile_tma(p, &tmO, sO, git, leader, trow, s_bias, n0, HS_BN, quad, half, lane, b, x0 + mt * HL_BW, y0, [&]() {
+                        if (mt == 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&t_empty[buf]);
+                        }
+                    });
+                }
+            }
+            if (leader) bulk_wait_read<0>();
+        } else
         for (int unit = blockIdx.x; unit < total; unit += gridDim.x, ++tcount) {
             const int mu = unit % m_units, n0 = (unit / m_units) * HS_BN;
             const int b = mu / units_per_img, rem = mu - b * units_per_img;
@@ -346,10 +398,10 @@ __global__ void __launch_bounds__(HS_THREADS, 1) conv_halo_stream_kernel(const _
 static int g_halo_sms = 0;
 
 template <int BN>
-static int launch_halo(const CUtensorMap &tmA, const CUtensorMap &tmB, const HaloP &p, size_t smem, cudaStream_t st)
+static int launch_halo(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmO, const HaloP &p, size_t smem, cudaStream_t st)
 {
     TDRN_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_halo_kernel<BN><<<p.total < g_halo_sms ? p.total : g_halo_sms, HL_THREADS, smem, st>>>(tmA, tmB, p);
+    conv_halo_kernel<BN><<<p.total < g_halo_sms ? p.total : g_halo_sms, HL_THREADS, smem, st>>>(tmA, tmB, tmO, p);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }
@@ -370,9 +422,15 @@ int conv_halo_try(const tdrn_conv_desc *d, const void *in, const void *weight, c
     p.H = d->H; p.W = d->W; p.B = d->B; p.Cin = d->Cin; p.cblocks = d->Cin / 64; p.Cout = d->Cout;
     p.n_pad16 = (d->Cout + 15) & ~15;
     p.w_bytes = 9u * (uint32_t)p.cblocks * (uint32_t)p.n_pad16 * 128u;
+    // TMA-store epilogue: plain contiguous NHWC bf16 output (pooled or not) on exactly tiled maps; costs 32 KB of staging boxes
+    static const bool no_tma_out = getenv("TDRN_NO_TMA_STORE") != nullptr;
+    const int Ho = d->pool2x2 ? d->H / 2 : d->H, Wo = d->pool2x2 ? d->W / 2 : d->W;
+    const bool tma_out = !no_tma_out && exact && d->out_dtype == TDRN_BF16 && d->Cout % 8 == 0 && d->out_sp == d->Cout &&
+                         d->out_sb == (long long)Ho * Wo * d->Cout && ((uintptr_t)out & 15) == 0;
+    const size_t stage_bytes = tma_out ? 2 * 128 * 128 : 0;
     const size_t budget = 225 * 1024;
     int stages = HL_MAX_STAGES;
-    while (stages >= 2 && 1024 + (size_t)p.w_bytes + (size_t)stages * HL_A_STRIDE > budget) --stages;
+    while (stages >= 2 && 1024 + (size_t)p.w_bytes + (size_t)stages * HL_A_STRIDE + stage_bytes > budget) --stages;
     const bool resident = stages >= 2 && d->Cout <= 128;
     // weights too large to stay resident: streamed variant (two M tiles per weight k-block), 128-wide N tiles
     const bool streamed = !resident && exact && d->Cout % HS_BN == 0 && d->Cout <= 512 && d->W % (2 * HL_BW) == 0 && !getenv("TDRN_NO_HALO_STREAM");
@@ -404,22 +462,31 @@ int conv_halo_try(const tdrn_conv_desc *d, const void *in, const void *weight, c
         int rc = make_tmap_bf16(&tmB, weight, 2, dims, str, box, nullptr);
         if (rc) return rc;
     }
+    p.tma_out = tma_out;
+    CUtensorMap tmO = tmA;
+    if (tma_out) {
+        const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)d->B};
+        const uint64_t str[3] = {(uint64_t)d->Cout * 2, (uint64_t)Wo * d->Cout * 2, (uint64_t)Ho * Wo * d->Cout * 2};
+        const uint32_t box[4] = {64, (uint32_t)(d->pool2x2 ? HL_BW / 2 : HL_BW), (uint32_t)(d->pool2x2 ? HL_BH / 2 : HL_BH), 1};
+        int rc = make_tmap_bf16(&tmO, out, 4, dims, str, box, nullptr);
+        if (rc) return rc;
+    }
     if (!resident) {
         const int total = (p.tiles_w / 2) * p.tiles_h * d->B * (p.n_pad16 / HS_BN);
         TDRN_CUDA(cudaFuncSetAttribute(conv_halo_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HS_SMEM));
-        conv_halo_stream_kernel<<<total < g_halo_sms ? total : g_halo_sms, HS_THREADS, HS_SMEM, st>>>(tmA, tmB, p);
+        conv_halo_stream_kernel<<<total < g_halo_sms ? total : g_halo_sms, HS_THREADS, HS_SMEM, st>>>(tmA, tmB, tmO, p);
         TDRN_LAUNCH_CHECK();
         return TDRN_OK;
     }
-    const size_t smem = 1024 + (size_t)p.w_bytes + (size_t)stages * HL_A_STRIDE;
+    const size_t smem = 1024 + (size_t)p.w_bytes + (size_t)stages * HL_A_STRIDE + stage_bytes;
     static const bool timing = getenv("TDRN_HALO_TIMING") != nullptr;        // development aid: where does the MMA issuer's time go?
     if (timing) {
         static long long *dbg = nullptr;
-        if (!dbg) TDRN_CUDA(cudaMalloc(&dbg, 148 * 5 * sizeof(long long)));
-        TDRN_CUDA(cudaMemsetAsync(dbg, 0, 148 * 5 * sizeof(long long), st));
+        if (!dbg) TDRN_CUDA(cudaMalloc(&dbg, (148 * 5 + 48) * sizeof(long long)));
+        TDRN_CUDA(cudaMemsetAsync(dbg, 0, (148 * 5 + 48) * sizeof(long long), st));
         p.dbg = dbg;
-        int rc = p.n_pad16 > 64 ? launch_halo<128>(tmA, tmB, p, smem, st) : launch_halo<64>(tmA, tmB, p, smem, st);
-        long long h[148 * 5];
+        int rc = p.n_pad16 > 64 ? launch_halo<128>(tmA, tmB, tmO, p, smem, st) : launch_halo<64>(tmA, tmB, tmO, p, smem, st);
+        long long h[148 * 5 + 48];
         TDRN_CUDA(cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
         TDRN_CUDA(cudaStreamSynchronize(st));
         double t[5] = {0, 0, 0, 0, 0};
@@ -427,9 +494,12 @@ int conv_halo_try(const tdrn_conv_desc *d, const void *in, const void *weight, c
         fprintf(stderr, "halo timing Cin %d Cout %d @%dx%d: MMA-issuer cycles per tile: total %.0f = waiting for the epilogue (t_empty) %.0f + "
                         "waiting for the halo box (a_full) %.0f + issuing %.0f  (%.0f tiles per CTA, %d MMAs per tile)\n", p.Cin, p.Cout, p.H, p.W,
                 t[0] / t[4], t[1] / t[4], t[2] / t[4], t[3] / t[4], t[4], 36 * p.cblocks);
+        const double tiles_all = t[4] * 148.0;
+        fprintf(stderr, "   epilogue warp 2, cycles per tile: waiting for the tile %.0f, working on it %.0f, of which tcgen05.ld x2 + wait %.0f\n",
+                (double)h[148 * 5 + 16 + 2] / tiles_all, (double)h[148 * 5 + 32 + 2] / tiles_all, (double)h[148 * 5 + 2] / tiles_all);
         return rc;
     }
-    return p.n_pad16 > 64 ? launch_halo<128>(tmA, tmB, p, smem, st) : launch_halo<64>(tmA, tmB, p, smem, st);
+    return p.n_pad16 > 64 ? launch_halo<128>(tmA, tmB, tmO, p, smem, st) : launch_halo<64>(tmA, tmB, tmO, p, smem, st);
 }
 
 }  // namespace tc

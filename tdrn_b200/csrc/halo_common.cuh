@@ -23,6 +23,7 @@ struct HaloP {
     long long out_sb, out_sp; int out_w;
     int relu, out_f32, pool;
     int debug_skip_epilogue;     // timing experiments only (TDRN_HALO_DEBUG=1): results are NOT written
+    int tma_out;                 // epilogue stages bf16 tiles in shared memory and stores them with TMA (plain NHWC bf16 output)
     long long *dbg;              // TDRN_HALO_TIMING=1: per CTA {cycles total, waiting for t_empty, waiting for a_full, issuing, tiles}
 };
 
@@ -55,10 +56,12 @@ __device__ __forceinline__ void halo_epilogue_tile(const HaloP &p, uint32_t trow
     const int ca = half * 32, cb2 = half * 32 + 64;
     if (cb2 < ncols) {
         uint32_t ra[32], rb[32];
+        const long long c0_ = p.dbg ? clock64() : 0;
         tmem_ld32_issue(trow + (uint32_t)ca, ra);
         tmem_ld32_issue(trow + (uint32_t)cb2, rb);
         tmem_ld_wait32(ra);
         tmem_ld_pin32(rb);
+        if (p.dbg && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&p.dbg[148 * 5 + (threadIdx.x >> 5)], (unsigned long long)(clock64() - c0_));
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]);
@@ -132,6 +135,82 @@ __device__ __forceinline__ void halo_epilogue_chunk(const HaloP &p, float (&v)[3
 #pragma unroll
                 for (int j = 0; j < 32; ++j) if (j < nv) op[j] = qb[j];
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-store epilogue of one 128-pixel tile (plain NHWC bf16 output, optional fused 2x2 max-pool).
+// Measured r02 (TDRN_HALO_TIMING, conv2_1): the register-store epilogue took ~3 900 cycles per tile against 2 300 for the
+// tile's MMAs, and not because of tcgen05.ld (40 cycles): a lane stores 16-byte pieces of ITS pixel, so every store
+// instruction touches 32 different 128-byte lines and the L1 pipeline spends ~32 cycles on it (64 such instructions per tile).
+// Here the eight epilogue warps convert their 32 rows x 32 columns of a 64-channel group into a 128B-swizzled
+// [rows][64 ch] staging box (16-byte shared stores, conflict-free) and one thread hands the box to TMA: whole lines leave the SM.
+//   stage: two staging boxes of 128 x 128 B (16 KB each), used alternately; `git` counts groups over the whole kernel.
+//   leader: the one thread that issues / waits for the bulk stores.  Barrier id 1 is shared by the 256 epilogue threads.
+// Pooled tiles: the 8 x 16 pixel tile becomes 4 x 8 = 32 rows; the caller's tensor map has box (64, 4, 8, 1).
+// `after_last_ld` is called by every warp right after its last tcgen05.ld of the tile (hands the accumulator back).
+// ---------------------------------------------------------------------------------------------------------
+template <typename F>
+__device__ __forceinline__ void halo_epilogue_tile_tma(const HaloP &p, const CUtensorMap *tmO, uint8_t *stage, uint32_t &git, bool leader,
+                                                       uint32_t trow, const float *s_bias, int n0, int ncols, int quad, int half, int lane,
+                                                       int b, int x0, int y0, F after_last_ld)
+{
+    const int r = quad * 32 + lane;
+    const int wl = r & (HL_BW - 1), hl = r >> 3;
+    const int groups = (ncols + 63) >> 6;
+    for (int g = 0; g < groups; ++g, ++git) {
+        uint8_t *o = stage + (git & 1u) * (128 * 128);
+        if (leader) bulk_wait_read<1>();                         // the store that last read this box has drained
+        named_bar(1, 256);
+        const int c0 = g * 64 + half * 32;
+        if (c0 < ncols) {                                        // warp-uniform
+            float v[32];
+            tmem_ld32(trow + (uint32_t)c0, v);
+            if (g == groups - 1) after_last_ld();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 bq = *(const float4 *)(s_bias + n0 + c0 + j);
+                v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
+            }
+            if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            uint32_t q[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                q[j] = *(const uint32_t *)&h2;
+            }
+            int row = r;
+            bool wr = true;
+            if (p.pool) {                                        // MaxPool2d(2,2): partners are lanes ^1 and ^8 (bf16 max commutes with rounding)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    uint32_t o1 = __shfl_xor_sync(0xffffffffu, q[j], 1);
+                    __nv_bfloat162 m = __hmax2(*(const __nv_bfloat162 *)&q[j], *(const __nv_bfloat162 *)&o1);
+                    uint32_t mw = *(const uint32_t *)&m;
+                    uint32_t o2 = __shfl_xor_sync(0xffffffffu, mw, HL_BW);
+                    m = __hmax2(m, *(const __nv_bfloat162 *)&o2);
+                    q[j] = *(const uint32_t *)&m;
+                }
+                wr = !(wl & 1) && !(hl & 1);
+                row = (hl >> 1) * (HL_BW / 2) + (wl >> 1);
+            }
+            if (wr) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    *(uint4 *)(o + sw128_offset(row, half * 4 + k)) = make_uint4(q[4 * k], q[4 * k + 1], q[4 * k + 2], q[4 * k + 3]);
+            }
+        } else if (g == groups - 1) {
+            after_last_ld();
+        }
+        fence_proxy_async_smem();
+        named_bar(1, 256);
+        if (leader) {
+            tma_store_4d(tmO, o, n0 + g * 64, p.pool ? x0 >> 1 : x0, p.pool ? y0 >> 1 : y0, b);
+            bulk_commit();
         }
     }
 }
