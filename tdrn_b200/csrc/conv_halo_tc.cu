@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_c
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(&w_bar, p.w_bytes);
             for (int kb = 0; kb < 9 * p.cblocks; ++kb) tma_load_2d(sW + (size_t)kb * kb_bytes, &tmB, &w_bar, kb * 64, 0);
             uint32_t it = 0;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_c
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, p.n_pad16);
             mbar_wait(&w_bar, 0);
             tc_fence_after();
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const __grid_c
                 mbar_wait(&t_full[buf], (tcount >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
-                halo_epilogue_tile_tma(p, &tmO, sO, git, leader, trow, s_bias, 0, p.n_pad16, quad, half, lane, b,
+                halo_epilogue_tile_tma(p, &tmO, sO, 128u * 128u, git, leader, trow, s_bias, 0, p.n_pad16, quad, half, lane, b,
                                        (rem % p.tiles_w) * HL_BW, (rem / p.tiles_w) * HL_BH, [&]() {
                                            tc_fence_before();
                                            __syncwarp();
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) conv_halo_stream_kernel(const _
 
     if (warp == 0) {
         // ===================== A (halo) TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;
             for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
                 const int mu = unit % m_units;
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) conv_halo_stream_kernel(const _
         __syncwarp();
     } else if (warp == 10) {
         // ===================== B (weight k-block) TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t jt = 0;
             for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
                 const int n0 = (unit / m_units) * HS_BN;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) conv_halo_stream_kernel(const _
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, HS_BN);
             const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
             uint32_t it = 0, jt = 0, tcount = 0;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) conv_halo_stream_kernel(const _
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (2 * HS_BN) + mt * HS_BN;
-                    halo_epilogue_tile_tma(p, &tmO, sO, git, leader, trow, s_bias, n0, HS_BN, quad, half, lane, b, x0 + mt * HL_BW, y0, [&]() {
+                    halo_epilogue_tile_tma(p, &tmO, sO, 128u * 128u, git, leader, trow, s_bias, n0, HS_BN, quad, half, lane, b, x0 + mt * HL_BW, y0, [&]() {
                         if (mt == 1) {
                             tc_fence_before();
                             __syncwarp();

@@ -45,7 +45,8 @@ constexpr int SP_PSTAGES = 4;
 constexpr int SP_W2_BYTES = 9 * SP_C * 128;                // 73728: conv1_2 weights, [tap][64 rows][128 B]
 constexpr int SP_HSTAGES = 2;                              // halo A tiles
 constexpr int SP_AP_BYTES = 2 * 16384;                     // one A' tile: two M = 128 halves of [128 rows][128 B]
-constexpr int SP_SMEM = 1024 + SP_W2_BYTES + SP_HSTAGES * HL_A_STRIDE + 2 * SP_AP_BYTES + 8192 + SP_PSTAGES * SP_PATCH_STRIDE;
+constexpr int SP_OUT_BYTES = 2 * 4096;                     // two staging boxes of the TMA-store epilogue (pooled tile: 32 rows x 128 B)
+constexpr int SP_SMEM = 1024 + SP_W2_BYTES + SP_HSTAGES * HL_A_STRIDE + 2 * SP_AP_BYTES + 8192 + SP_PSTAGES * SP_PATCH_STRIDE + SP_OUT_BYTES;
 constexpr int SP_TMEM_PRE = 128;                           // TMEM: main accumulators [0,128), D' slot s half h at 128 + s*128 + h*64
 
 struct StemPairP {
@@ -63,7 +64,8 @@ __device__ __forceinline__ uint32_t sp_pack(float lo, float hi)
 }
 
 __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __grid_constant__ CUtensorMap tmX,
-                                                                       const __grid_constant__ CUtensorMap tmW2, const StemPairP q)
+                                                                       const __grid_constant__ CUtensorMap tmW2,
+                                                                       const __grid_constant__ CUtensorMap tmO, const StemPairP q)
 {
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t p_full[SP_PSTAGES], p_empty[SP_PSTAGES];
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
     uint8_t *sAp = sH + SP_HSTAGES * HL_A_STRIDE;          // 2 slots x 2 halves x 16 KB
     uint8_t *sB1 = sAp + 2 * SP_AP_BYTES;                  // [64 rows][128 B]
     uint8_t *sP = sB1 + 8192;                              // patch ring
+    uint8_t *sO = sP + SP_PSTAGES * SP_PATCH_STRIDE;       // two 4 KB staging boxes of the TMA-store epilogue (pooled tiles)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
     const int n_my = blockIdx.x < p.total ? (p.total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // tiles of this CTA
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
 
     if (warp == 0) {
         // ===================== TMA producer: conv1_2 weights once, then one image patch per tile =====================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(&w_bar, SP_W2_BYTES);
             for (int tap = 0; tap < 9; ++tap) tma_load_2d(sW2 + tap * (SP_C * 128), &tmW2, &w_bar, tap * 64, 0);
             uint32_t it = 0;
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread): pre(0); { pre(it+1); main(it) } =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, SP_C);
             const uint64_t b1desc = umma_desc_sw128(smem_u32(sB1));
             const uint32_t sW_u = smem_u32(sW2), sH_u = smem_u32(sH), sAp_u = smem_u32(sAp);
@@ -181,7 +184,25 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const int r = quad * 32 + lane;
         const int wl = r & (HL_BW - 1), hl = r >> 3;
-        uint32_t it = 0;
+        uint32_t it = 0, git = 0;
+        const bool leader = tid == 64;
+        if (p.tma_out) {
+            if (leader) tma_prefetch_desc(&tmO);
+            for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++it) {
+                const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+                const uint32_t s = it & 1u;
+                mbar_wait(&t_full[s], (it >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + s * SP_C;
+                halo_epilogue_tile_tma(p, &tmO, sO, 4096u, git, leader, trow, s_bias, 0, SP_C, quad, half, lane, b,
+                                       (rem % p.tiles_w) * HL_BW, (rem / p.tiles_w) * HL_BH, [&]() {
+                                           tc_fence_before();
+                                           __syncwarp();
+                                           if (lane == 0) mbar_arrive(&t_empty[s]);
+                                       });
+            }
+            if (leader) bulk_wait_read<0>();
+        } else
         for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++it) {
             const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
             const int x = (rem % p.tiles_w) * HL_BW + wl, y = (rem / p.tiles_w) * HL_BH + hl;
@@ -336,6 +357,18 @@ extern "C" int tdrn_conv_stem_pair(const float *x, const float *w1, const float 
         int rc = make_tmap_bf16(&tmW2, w2, 2, dims, str, box, nullptr);
         if (rc) return rc;
     }
+    CUtensorMap tmO = tmW2;
+    {   // TMA-store epilogue for the pooled output (its staging boxes are 32 rows; the un-pooled form keeps register stores)
+        static const bool no_tma_out = getenv("TDRN_NO_TMA_STORE") != nullptr;
+        p.tma_out = !no_tma_out && pool && ((uintptr_t)out & 15) == 0;
+        if (p.tma_out) {
+            const uint64_t dims[4] = {(uint64_t)SP_C, (uint64_t)(W / 2), (uint64_t)(H / 2), (uint64_t)B};
+            const uint64_t str[3] = {(uint64_t)SP_C * 2, (uint64_t)(W / 2) * SP_C * 2, (uint64_t)(H / 2) * (W / 2) * SP_C * 2};
+            const uint32_t box[4] = {64, HL_BW / 2, HL_BH / 2, 1};
+            int rc = make_tmap_bf16(&tmO, out, 4, dims, str, box, nullptr);
+            if (rc) return rc;
+        }
+    }
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
@@ -343,7 +376,7 @@ extern "C" int tdrn_conv_stem_pair(const float *x, const float *w1, const float 
         TDRN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     TDRN_CUDA(cudaFuncSetAttribute(conv_stem_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
-    conv_stem_pair_kernel<<<p.total < num_sms ? p.total : num_sms, SP_THREADS, SP_SMEM, as_stream(stream)>>>(tmX, tmW2, q);
+    conv_stem_pair_kernel<<<p.total < num_sms ? p.total : num_sms, SP_THREADS, SP_SMEM, as_stream(stream)>>>(tmX, tmW2, tmO, q);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
         }
     } else if (warp == 4) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, ST_COUT);
             const uint64_t bdesc = umma_desc_sw128(smem_u32(sB));
             uint32_t it = 0;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
         __syncwarp();
     } else if (warp == 9) {
         // ===================== input-patch TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t patch_bytes = (uint32_t)(3 * PH * PW * 4);
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++it) {

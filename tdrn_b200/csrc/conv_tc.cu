@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             // The weights of the small-map layers are cold in L2 every step (1 GB of activations went through it since
             // their last use) and each CTA streams them through a ring that only holds a few k-blocks: prefetch this
             // CTA's first weight slice into L2 now, all boxes at once.
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t s = 0, ph = 0, tcount = 0;
             for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
                 const int nt = tile / m_units;
@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_splitk_kernel(const __grid
 
     if (warp == 0) {
         // ===================== TMA producer: k-blocks kb0 .. kb1-1 of this tile =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const int w0 = tw * p.bw * p.stride - p.pad;
             const int h0 = (tail ? p.qh * p.bh : th * p.bh) * p.stride - p.pad;
             const int b0 = tail ? (mt - p.nA) * p.g2 : tn * p.bn;
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_splitk_kernel(const __grid
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, n_eff);
             uint32_t s = 0, ph = 0;
             for (int kb = kb0; kb < kb1; ++kb) {

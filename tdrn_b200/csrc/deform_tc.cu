@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform_head_kernel(const __grid
         }
     } else if (warp == DF_PRODUCER_WARPS) {
         // ===================== weight (B operand) TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % p.stages;
                 const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deform_head_kernel(const __grid
         __syncwarp();
     } else {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, p.n_pad16);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % p.stages;

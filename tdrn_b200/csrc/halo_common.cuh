@@ -146,13 +146,15 @@ __device__ __forceinline__ void halo_epilogue_chunk(const HaloP &p, float (&v)[3
 // instruction touches 32 different 128-byte lines and the L1 pipeline spends ~32 cycles on it (64 such instructions per tile).
 // Here the eight epilogue warps convert their 32 rows x 32 columns of a 64-channel group into a 128B-swizzled
 // [rows][64 ch] staging box (16-byte shared stores, conflict-free) and one thread hands the box to TMA: whole lines leave the SM.
-//   stage: two staging boxes of 128 x 128 B (16 KB each), used alternately; `git` counts groups over the whole kernel.
+//   stage: two staging boxes `stage_stride` bytes apart (128 rows x 128 B = 16 KB; 4 KB is enough for pooled tiles), used
+//   alternately; `git` counts groups over the whole kernel.
 //   leader: the one thread that issues / waits for the bulk stores.  Barrier id 1 is shared by the 256 epilogue threads.
 // Pooled tiles: the 8 x 16 pixel tile becomes 4 x 8 = 32 rows; the caller's tensor map has box (64, 4, 8, 1).
 // `after_last_ld` is called by every warp right after its last tcgen05.ld of the tile (hands the accumulator back).
 // ---------------------------------------------------------------------------------------------------------
 template <typename F>
-__device__ __forceinline__ void halo_epilogue_tile_tma(const HaloP &p, const CUtensorMap *tmO, uint8_t *stage, uint32_t &git, bool leader,
+__device__ __forceinline__ void halo_epilogue_tile_tma(const HaloP &p, const CUtensorMap *tmO, uint8_t *stage, uint32_t stage_stride,
+                                                       uint32_t &git, bool leader,
                                                        uint32_t trow, const float *s_bias, int n0, int ncols, int quad, int half, int lane,
                                                        int b, int x0, int y0, F after_last_ld)
 {
@@ -160,7 +162,7 @@ __device__ __forceinline__ void halo_epilogue_tile_tma(const HaloP &p, const CUt
     const int wl = r & (HL_BW - 1), hl = r >> 3;
     const int groups = (ncols + 63) >> 6;
     for (int g = 0; g < groups; ++g, ++git) {
-        uint8_t *o = stage + (git & 1u) * (128 * 128);
+        uint8_t *o = stage + (git & 1u) * stage_stride;
         if (leader) bulk_wait_read<1>();                         // the store that last read this box has drained
         named_bar(1, 256);
         const int c0 = g * 64 + half * 32;

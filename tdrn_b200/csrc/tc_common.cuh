@@ -44,6 +44,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         if (spins > (1u << 26)) { printf("tdrn: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
 }
 
+// One thread of a CONVERGED warp (all 32 lanes must execute this): the single-thread roles -- TMA producer, tcgen05.mma
+// issuer -- are entered through it rather than through `lane == 0`.  ptxas knows that a branch on elect.sync's predicate
+// holds exactly one thread and emits every tcgen05.mma / cp.async.bulk.tensor of the branch as ONE instruction; behind a
+// plain `lane == 0` test it wraps each of them in an ELECT / PLOP3 / BRA.U.ANY loop (5 extra instructions per MMA,
+// measured r02: the halo kernels' issue loop took 78 cycles per N = 128 MMA against the tensor core's 64).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "elect.sync _|p, 0xffffffff;\n\t"
+                 "selp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA loads (tile mode) -> shared memory, completion on an mbarrier
 // ---------------------------------------------------------------------------------------------
