@@ -2,7 +2,7 @@ import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tdrn_b200 import _lib
-L = _lib.lib()
+L = _lib.probe_lib()
 B, H, W = 2, 8, 64
 pw, ph, cx, cy, b, rank, promo = [int(v) for v in sys.argv[1:8]]
 x = torch.arange(B * 3 * H * W, dtype=torch.float32).view(B, 3, H, W).cuda()

@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import torch
 from tdrn_b200 import _lib
 
-L = _lib.lib()
+L = _lib.probe_lib()
 out = torch.empty(128, 64, device='cuda')
 rows = 400
 

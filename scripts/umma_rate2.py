@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from tdrn_b200 import _lib
-L = _lib.lib()
+L = _lib.probe_lib()
 NAMES = {0: 'SS', 1: 'TS (A in TMEM)', 2: 'cp 128x256b only', 3: 'cp + TS', 4: 'SS cta_group::2 (M=256)',
          5: 'SS, descs per 4 MMAs', 6: 'SS, descs per MMA'}
 grid, iters = 148, 20000

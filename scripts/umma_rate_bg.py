@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from tdrn_b200 import _lib
-L = _lib.lib()
+L = _lib.probe_lib()
 grid, iters = 148, 20000
 cyc = torch.zeros(grid, dtype=torch.int64, device='cuda')
 bgb = torch.zeros(grid, dtype=torch.int64, device='cuda')

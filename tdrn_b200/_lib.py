@@ -76,3 +76,18 @@ def stream_handle():
 
 def launch_count():
     return int(lib().tdrn_launch_count())
+
+
+_probe = None
+
+
+def probe_lib():
+    """libtdrn_probe.so (development probes, csrc/probe/; built by `python -m tdrn_b200.build --probe`)."""
+    global _probe
+    if _probe is None:
+        lib()                                    # the probes link against the product library
+        path = os.path.join(os.path.dirname(LIB_PATH), 'libtdrn_probe.so')
+        if not os.path.exists(path):
+            raise TdrnError('%s not found: build it with `python -m tdrn_b200.build --probe`' % path)
+        _probe = ctypes.CDLL(path)
+    return _probe

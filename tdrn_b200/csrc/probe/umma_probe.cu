@@ -6,7 +6,7 @@
 // Smem rows (128 B = 64 bf16) are filled in the layout TMA SWIZZLE_128B produces (16-byte chunk c of absolute
 // row R stored at chunk position c ^ (R & 7)); value = R (mode 0) or k (mode 1).  B = 64x64 identity, so
 // D[m][n] = A[m][n] and the output reveals the (row, column) every A element was fetched from.
-#include "halo_common.cuh"
+#include "../halo_common.cuh"
 
 namespace tdrn {
 namespace tc {
