@@ -30,6 +30,7 @@
 // part (same box, alternating runs, before the shared-memory tweaks).  TDRN_NO_STEM_PAIR=1 selects the two-kernel path.
 #include "halo_common.cuh"
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace tdrn {
 namespace tc {
@@ -139,10 +140,15 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
             const uint32_t idesc = umma_idesc_bf16(128, SP_C);
             const uint64_t b1desc = umma_desc_sw128(smem_u32(sB1));
             const uint32_t sW_u = smem_u32(sW2), sH_u = smem_u32(sH), sAp_u = smem_u32(sAp);
+            long long c_ap = 0, c_pe = 0, c_te = 0, c_af = 0;            // TDRN_HALO_TIMING: what the issuer waits for
+            const long long c_start = p.dbg ? clock64() : 0;
             auto pre = [&](uint32_t it) {
                 const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
+                long long c0 = p.dbg ? clock64() : 0;
                 mbar_wait(&ap_full[s], ph);
+                if (p.dbg) { const long long c = clock64(); c_ap += c - c0; c0 = c; }
                 mbar_wait(&pre_empty[s], ph ^ 1u);
+                if (p.dbg) c_pe += clock64() - c0;
                 tc_fence_after();
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -160,8 +166,11 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
             for (uint32_t it = 0; it < (uint32_t)n_my; ++it) {
                 if (it + 1 < (uint32_t)n_my) pre(it + 1);
                 const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
+                long long c0 = p.dbg ? clock64() : 0;
                 mbar_wait(&t_empty[s], ph ^ 1u);
+                if (p.dbg) { const long long c = clock64(); c_te += c - c0; c0 = c; }
                 mbar_wait(&a_full[s], ph);
+                if (p.dbg) c_af += clock64() - c0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + s * SP_C;
                 const uint32_t a0 = sH_u + s * (uint32_t)HL_A_STRIDE;
@@ -176,6 +185,10 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
                 }
                 umma_commit(&a_empty[s]);
                 umma_commit(&t_full[s]);
+            }
+            if (p.dbg) {
+                long long *o = p.dbg + blockIdx.x * 6;
+                o[0] = clock64() - c_start; o[1] = c_ap; o[2] = c_pe; o[3] = c_te; o[4] = c_af; o[5] = n_my;
             }
         }
         __syncwarp();
@@ -279,8 +292,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
 #pragma unroll
                 for (int c0 = 0; c0 < SP_C; c0 += 32) {
                     float v[32];
-                    tmem_ld32(taddr + (uint32_t)c0, v);
-                    if (row < SP_ROWS) {
+                    tmem_ld32(taddr + (uint32_t)c0, v);      // (both halves in flight before one wait: measured r02, no change --
+                    if (row < SP_ROWS) {                     //  the mid stage is not bound by tcgen05.ld)
 #pragma unroll
                         for (int cq = 0; cq < 4; ++cq) {
                             uint32_t w[4];
@@ -376,6 +389,24 @@ extern "C" int tdrn_conv_stem_pair(const float *x, const float *w1, const float 
         TDRN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     TDRN_CUDA(cudaFuncSetAttribute(conv_stem_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM));
+    static const bool timing = getenv("TDRN_HALO_TIMING") != nullptr;        // development aid (see conv_halo_tc.cu)
+    if (timing) {
+        static long long *dbg = nullptr;
+        if (!dbg) TDRN_CUDA(cudaMalloc(&dbg, 148 * 6 * sizeof(long long)));
+        TDRN_CUDA(cudaMemsetAsync(dbg, 0, 148 * 6 * sizeof(long long), as_stream(stream)));
+        p.dbg = dbg;
+        conv_stem_pair_kernel<<<p.total < num_sms ? p.total : num_sms, SP_THREADS, SP_SMEM, as_stream(stream)>>>(tmX, tmW2, tmO, q);
+        TDRN_LAUNCH_CHECK();
+        long long h[148 * 6];
+        TDRN_CUDA(cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, as_stream(stream)));
+        TDRN_CUDA(cudaStreamSynchronize(as_stream(stream)));
+        double t[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 148; ++i) for (int j = 0; j < 6; ++j) t[j] += (double)h[i * 6 + j] / 148.0;
+        fprintf(stderr, "stem pair timing: MMA-issuer cycles per tile: total %.0f = waiting for the im2col rows (ap_full) %.0f + for the mid stage to "
+                        "drain D' (pre_empty) %.0f + for the epilogue (t_empty) %.0f + for the halo tile (a_full) %.0f + issuing %.0f  (%.0f tiles per CTA)\n",
+                t[0] / t[5], t[1] / t[5], t[2] / t[5], t[3] / t[5], t[4] / t[5], (t[0] - t[1] - t[2] - t[3] - t[4]) / t[5], t[5]);
+        return TDRN_OK;
+    }
     conv_stem_pair_kernel<<<p.total < num_sms ? p.total : num_sms, SP_THREADS, SP_SMEM, as_stream(stream)>>>(tmX, tmW2, tmO, q);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
