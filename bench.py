@@ -688,6 +688,31 @@ def run_gpu(args, rank, world, local_rank):
                     'peak_source': pk['source'] + ', sustained bf16 (kernel timed inside a long step)',
                     'launches_per_step': tc[2] // n_prof,
                     'avg_launch_ms': tc[1] / tc[2], 'share_of_step': tc[1] / tot_ms}
+        tx = agg.get('conv_tc_x3')
+        if tx and not tc:
+            # fp32-accurate path: every fp32 product is THREE bf16 tensor-core products (hi*hi + hi*lo + lo*hi), so the peak this
+            # family can reach in fp32-equivalent FLOPs is a third of the bf16 one; cuBLAS's TF32 GEMM rate (one pass, 10-bit
+            # mantissa, NOT accurate to 1e-4 over 17 stacked layers) is measured alongside for scale
+            tflops = tx[0] / (tx[1] * 1e-3) / 1e12
+            a = torch.randn(8192, 8192, device=dev); b = torch.randn(8192, 8192, device=dev)
+            old_tf32 = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True
+            for _ in range(3):
+                a @ b
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                a @ b
+            e1.record(); torch.cuda.synchronize()
+            tf32 = 10 * 2 * 8192.0 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+            torch.backends.cuda.matmul.allow_tf32 = old_tf32
+            roof = {'kernel': 'split-precision tcgen05 implicit-GEMM convs (conv_tc_kernel<.., SPLIT>: hi*W_hi over 3 TMEM accumulators + '
+                              'hi*W_lo + lo*W_hi): all conv launches of the step, fp32 algorithmic FLOPs / summed CUDA-event time',
+                    'bound': 'tensor', 'achieved': tflops, 'peak': pk['bf16_tflops_sustained'] / 3.0, 'unit': 'TFLOP/s (fp32-equivalent)',
+                    'frac': tflops / (pk['bf16_tflops_sustained'] / 3.0), 'traffic': None,
+                    'peak_source': pk['source'] + ', sustained bf16 / 3 (three bf16 products per fp32 product)',
+                    'tf32_cublas_tflops_measured_here': tf32, 'launches_per_step': tx[2] // n_prof, 'avg_launch_ms': tx[1] / tx[2],
+                    'share_of_step': tx[1] / tot_ms}
         breakdown = {k: {'ms_per_step': v[1] / n_prof, 'launches': v[2] // n_prof, 'work_per_step': v[0] / n_prof} for k, v in agg.items()}
         if 'detect' in agg:
             d = agg['detect']
