@@ -35,7 +35,7 @@
 namespace tdrn {
 namespace tc {
 
-constexpr int SP_THREADS = 576;
+constexpr int SP_THREADS = 704;                            // 22 warps: TMA, MMA, 8 epilogue, 4 im2col builders, 8 mid-stage
 constexpr int SP_C = 64;                                   // channels of conv1_1's output = conv1_2's input and output
 constexpr int SP_ROWS = HL_PW * HL_PH;                     // 180 halo pixels
 constexpr int SP_PXW = 20, SP_PXH = HL_PH + 2;             // patch: x0-4 .. x0+15 (16-byte aligned start; 12 columns are needed, a pitch
@@ -270,9 +270,12 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++it) build(it, tile);
     } else {
-        // ===================== mid stage (warps 14..17, 128 threads): D' -> bias/ReLU/mask -> bf16 halo tile =====================
-        const int bt = tid - 448;                          // 0..127
+        // ===================== mid stage (warps 14..21, 256 threads): D' -> bias/ReLU/mask -> bf16 halo tile =====================
+        // r02: eight warps instead of four -- two per TMEM lane quadrant, each takes one 32-column half of its rows.  The halo
+        // tile this stage produces is what the main MMAs waited for (1 230 of 4 184 cycles per tile, TDRN_HALO_TIMING).
+        const int bt = tid - 448;                          // 0..255
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
+        const int chalf = (warp - 14) >> 2;                // which 32-column half
         auto mid = [&](uint32_t it, int tile) {
             const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
             const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
@@ -289,8 +292,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + SP_TMEM_PRE + s * 128u + h * 64u;
                 const int hr = row / HL_PW, hc = row - hr * HL_PW;
                 const bool inside = row < SP_ROWS && (unsigned)(x0 + hc) < (unsigned)p.W && (unsigned)(y0 + hr) < (unsigned)p.H;
-#pragma unroll
-                for (int c0 = 0; c0 < SP_C; c0 += 32) {
+                {
+                    const int c0 = chalf * 32;
                     float v[32];
                     tmem_ld32(taddr + (uint32_t)c0, v);      // (both halves in flight before one wait: measured r02, no change --
                     if (row < SP_ROWS) {                     //  the mid stage is not bound by tcgen05.ld)
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
             }
             tc_fence_before();
             fence_proxy_async_smem();
-            named_bar(3, 128);                             // halo tile complete, D' slot s fully read
+            named_bar(3, 256);                             // halo tile complete, D' slot s fully read
             if (bt == 0) { mbar_arrive(&a_full[s]); mbar_arrive(&pre_empty[s]); }
         };
         uint32_t it = 0;
