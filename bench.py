@@ -644,6 +644,32 @@ def run_gpu(args, rank, world, local_rank):
                    'includes': 'tdrn_preprocess (base_transform from a resident uint8 frame) + net + Detect, one graph replay per '
                                'frame, CUDA events around each replay'}
 
+    # ---- per-frame video latency (config 5): the reference's batch-1 loop (test_video_trn.py:81-103) on uint8 frames ----
+    if rank == 0 and wl.key == 'tdrn' and not args.no_graph:
+        from tdrn_b200.utils.tdrn_stream import GraphedTDRNStream
+        gs = GraphedTDRNStream(wl.nets[0], wl.nets[1], wl.det, wl.priors, size=SIZE, interval=wl.K, mean=MEANS)
+        f1 = host_u8[0][:1].to(dev)
+        tk, to = [], []
+        with torch.no_grad():
+            for i in range(40 + 800):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                key = gs.is_key_frame('v')
+                with torch.cuda.stream(gs._stream):
+                    e0.record()
+                gs.step(f1, 'v')
+                with torch.cuda.stream(gs._stream):
+                    e1.record()
+                gs.synchronize()
+                if i >= 40:
+                    (tk if key else to).append(e0.elapsed_time(e1))
+        tk.sort(); to.sort()
+        q = lambda t, p: t[min(len(t) - 1, int(len(t) * p))]
+        latency = {'key_frame_ms_p50': q(tk, 0.5), 'key_frame_ms_p99': q(tk, 0.99), 'other_frame_ms_p50': q(to, 0.5), 'other_frame_ms_p99': q(to, 0.99),
+                   'mean_ms_per_frame': (sum(tk) + sum(to)) / (len(tk) + len(to)), 'frames': len(tk) + len(to), 'interval': wl.K,
+                   'includes': 'batch 1 from a resident uint8 frame: base_transform + (key frame: static net on a side stream || temporal '
+                               'trunk, offsets, heads | other frames: temporal net with cached offsets) + Detect; one CUDA-graph replay '
+                               'per frame (tdrn_b200.utils.tdrn_stream.GraphedTDRNStream), CUDA events around each replay'}
+
     # ---- roofline leg: CUDA events around every kernel call on the launching stream (same kernels as the timed graphs) ----
     roof, breakdown = None, None
     if rank == 0:
@@ -781,7 +807,7 @@ def run_gpu(args, rank, world, local_rank):
                 'launches_per_step': int(launches_per_step),
                 'inflight_replay_matches_serial': inflight_ok,
                 **({'INVALID_e2e_diagnosis_skip': _DIAG_SKIP} if _DIAG_SKIP else {}),
-                **({'latency_b1': latency} if latency else {}),
+                **({('latency_stream_b1' if wl.key == 'tdrn' else 'latency_b1'): latency} if latency else {}),
                 'tflops_per_gpu_whole_step': wl.gflop_per_frame * BATCH / (ms_dev / args.steps),   # GFLOP / ms == TFLOP/s
                 'roofline': roof, 'kernel_breakdown': breakdown, 'cpu_baseline': cpu, 'clocks': clocks}
         print(json.dumps(line), flush=True)

@@ -36,7 +36,12 @@ class SSD4ScaleBase(DetectorBase):
     def _sources(self, E, x):
         raise NotImplementedError
 
-    def forward(self, x, ref_loc=list(), offset_list=list(), ret_loc=False, ret_off=False):
+    def trunk(self, x):
+        """The four ARM sources of ``x`` alone (not part of the reference's surface): lets a streaming loop run the temporal net's
+        trunk next to the static net of the same key frame and hand the sources to ``forward(..., _sources=...)``."""
+        return self._sources(self.engine(), self._check_input(x))
+
+    def forward(self, x, ref_loc=list(), offset_list=list(), ret_loc=False, ret_off=False, _sources=None):
         E = self.engine()
         x = self._check_input(x)
         offs_nhwc = None
@@ -46,7 +51,7 @@ class SSD4ScaleBase(DetectorBase):
                                     out_dtype=torch.float32) for k, rl in enumerate(ref_loc)]
             else:
                 offs_nhwc = [ops.nchw_f32_to_nhwc(o.float(), torch.float32) for o in offset_list]
-        src = self._sources(E, x)
+        src = _sources if _sources is not None else self._sources(E, x)
         P, lv = prior_layout(src)
         if self.deform:
             loc, conf = E.deform_heads(src, offs_nhwc, None, P, lv, self.num_classes, DF_GROUP, False,

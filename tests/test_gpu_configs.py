@@ -192,3 +192,33 @@ def test_detect_workspace_survives_growth_and_capture():
         with pytest.raises(_lib.TdrnError):
             with torch.cuda.graph(gr2, stream=st2):
                 det.forward(loc, conf, pri, arm_loc_data=arm)     # no eager warm-up on this stream: loud, not silent
+
+
+def test_graphed_tdrn_stream_equals_the_eager_loop():
+    """GraphedTDRNStream (key-frame / other-frame CUDA graphs, static net on a side stream next to the temporal trunk) returns
+    what TDRNStream -- the call-by-call mirror of evaluate_trn.py:434-467 -- returns, frame by frame, bit for bit; also from
+    uint8 frames with base_transform inside the graphs."""
+    from tdrn_b200.layers.functions import Detect, PriorBox
+    from tdrn_b200.data import mb_cfg, preprocess_frames
+    from tdrn_b200.utils.tdrn_stream import TDRNStream, GraphedTDRNStream
+    C, interval, loose = 31, 3, 0.9
+    _, _, static, temporal = _tdrn_pair('bf16', C)
+    pri = PriorBox(mb_cfg['VOC_320']).forward().cuda()
+    det = Detect(C, 0, 200, 0.01, 0.45)
+    eager = TDRNStream(static, temporal, det, pri, interval=interval, loose=loose)
+    mean = (104.0, 117.0, 123.0)
+    graphed = GraphedTDRNStream(static, temporal, det, pri, size=320, interval=interval, loose=loose, mean=mean, frame_hw=(240, 352))
+    g = torch.Generator().manual_seed(3)
+    videos = ['a', 'a', 'a', 'a', 'b', 'b', 'b']                  # key frames: 0, 3 (interval), 4 (new video)
+    keys = []
+    for i, v in enumerate(videos):
+        frame = torch.randint(0, 256, (1, 240, 352, 3), dtype=torch.uint8, generator=g)
+        x = preprocess_frames(frame, 320, mean)
+        with torch.no_grad():
+            keys.append(graphed.is_key_frame(v))
+            assert eager.is_key_frame(v) == keys[-1]
+            a = eager.step(x, v)
+            b = graphed.step(frame.cuda(), v)
+        graphed.synchronize(); torch.cuda.synchronize()
+        assert torch.equal(a, b), i
+    assert keys == [True, False, False, True, True, False, False]
