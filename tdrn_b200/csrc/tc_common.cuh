@@ -40,8 +40,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 // Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+#ifdef TDRN_MBAR_BACKOFF
+        if (spins >= 4) __nanosleep(TDRN_MBAR_BACKOFF);      // experiment: waiting warps stop competing for issue slots / power
+#endif
         if (spins > (1u << 26)) { printf("tdrn: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+    }
 }
 
 // One thread of a CONVERGED warp (all 32 lanes must execute this): the single-thread roles -- TMA producer, tcgen05.mma
