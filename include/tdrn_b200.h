@@ -246,6 +246,12 @@ int tdrn_deform_head(const tdrn_deform_head_desc *d, const void *feat, const flo
 int tdrn_deform_head_sample(const tdrn_deform_head_desc *d, const void *proj, int n_pad,
                             const float *offsets, const float *offsets2, float *loc_out, float *conf_out,
                             tdrn_stream_t stream);
+/* The same for all pyramid levels of a detector in one launch (`for k in range(4): odm_loc[k](...), odm_conf[k](...)`,
+   dualrefinedet_vggbn.py:180-189): descs[k] / projs[k] / offsets[k] / offsets2[k] (offsets2 may be NULL) describe level k,
+   n_pad, loc_out [B,P,4] and conf_out [B,P,C] are shared (descs[k].prior_off places the level).  n_levels <= 6. */
+int tdrn_deform_head_sample_group(int n_levels, const tdrn_deform_head_desc *descs, const void *const *projs, int n_pad,
+                                  const float *const *offsets, const float *const *offsets2, float *loc_out, float *conf_out,
+                                  tdrn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (next row) Result scatter of the evaluation drivers: evaluate.py:469-483, evaluate_coco.py:140-159

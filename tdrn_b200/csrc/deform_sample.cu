@@ -64,12 +64,14 @@ __device__ __forceinline__ void s_acc(uint64_t (&acc)[4], const uint4 v, float w
 
 constexpr int DS_MAX_WARPS = 16;
 
-__global__ void __launch_bounds__(DS_MAX_WARPS * 32, 2) deform_sample_kernel(const SampleP p)
+// One CTA's patch of one pyramid level.  `block` = index of the patch inside the level; blockDim may be larger than the level
+// needs (grouped launch: the widest level decides): the extra warps own no pixel slot and only take part in the barriers.
+__device__ __forceinline__ void deform_sample_body(const SampleP &p, int block)
 {
     extern __shared__ uint4 ds_smem[];           // geometry [slots][taps_total], later the fp32 staging tile
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int HW = p.H * p.W;
-    int t = blockIdx.x;
+    int t = block;
     const int tb = t / (p.tiles_w * p.tiles_h);
     t -= tb * p.tiles_w * p.tiles_h;
     const int ty0 = (t / p.tiles_w) * p.TH, tx0 = (t % p.tiles_w) * p.TW;
@@ -203,19 +205,39 @@ __global__ void __launch_bounds__(DS_MAX_WARPS * 32, 2) deform_sample_kernel(con
     }
 }
 
+__global__ void __launch_bounds__(DS_MAX_WARPS * 32, 2) deform_sample_kernel(const SampleP p)
+{
+    deform_sample_body(p, (int)blockIdx.x);
+}
+
+// All pyramid levels of a detector in ONE launch (the 20x20 / 10x10 / 5x5 levels are a quarter of the pixels and, launched
+// on their own, 40 % of the summed sampler time: launch + tail latency of kernels that live ~20 us).
+struct SampleGroup {
+    int n;
+    int first[TDRN_MAX_OFFSET_LEVELS + 1];       // running CTA counts
+    SampleP lv[TDRN_MAX_OFFSET_LEVELS];
+};
+
+__global__ void __launch_bounds__(DS_MAX_WARPS * 32, 2) deform_sample_group_kernel(const __grid_constant__ SampleGroup g)
+{
+    int k = 0;
+    while (k + 1 < g.n && (int)blockIdx.x >= g.first[k + 1]) ++k;
+    deform_sample_body(g.lv[k], (int)blockIdx.x - g.first[k]);
+}
+
 }  // namespace tdrn
 
 using namespace tdrn;
 
-extern "C" int tdrn_deform_head_sample(const tdrn_deform_head_desc *d, const void *proj, int n_pad,
-                                       const float *offsets, const float *offsets2, float *loc_out, float *conf_out,
-                                       tdrn_stream_t stream)
+// Validates one level and fills its kernel parameters; nw = warps the level needs, smem = its dynamic shared memory.
+static int sample_setup(const tdrn_deform_head_desc *d, const void *proj, int n_pad, const float *offsets, const float *offsets2,
+                        float *loc_out, float *conf_out, SampleP &p, int &nw_out, size_t &smem_out)
 {
     TDRN_REQUIRE(d && proj && offsets && loc_out && conf_out, "tdrn_deform_head_sample: null argument");
     TDRN_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->num_classes > 0, "tdrn_deform_head_sample: bad shape");
     TDRN_REQUIRE(d->kh > 0 && 2 * d->pad == d->kh - 1, "tdrn_deform_head_sample: head 1 must be 'same' (2*pad == k-1)");
     TDRN_REQUIRE(d->kh2 == 0 || (2 * d->pad2 == d->kh2 - 1 && offsets2), "tdrn_deform_head_sample: bad second head");
-    SampleP p{};
+    p = SampleP{};
     p.n_total = 12 + 3 * d->num_classes;
     if (d->split && (n_pad % 16 != 0 || n_pad / 2 < p.n_total)) {
         set_error("tdrn_deform_head_sample: split projections need n_pad = 2*g with 12+3*C <= g (got C=%d n_pad=%d)", d->num_classes, n_pad);
@@ -256,9 +278,48 @@ extern "C" int tdrn_deform_head_sample(const tdrn_deform_head_desc *d, const voi
     p.taps_pad = (p.taps_total + 1) & ~1;                  // the tap loop is unrolled by two
     const size_t geo_bytes = (size_t)p.slots * p.taps_pad * 16;
     const size_t stg_bytes = (size_t)p.slots * (n_pad + 1) * 4;
-    const size_t smem = geo_bytes > stg_bytes ? geo_bytes : stg_bytes;
+    smem_out = geo_bytes > stg_bytes ? geo_bytes : stg_bytes;
+    nw_out = nw;
+    return TDRN_OK;
+}
+
+extern "C" int tdrn_deform_head_sample(const tdrn_deform_head_desc *d, const void *proj, int n_pad,
+                                       const float *offsets, const float *offsets2, float *loc_out, float *conf_out,
+                                       tdrn_stream_t stream)
+{
+    SampleP p;
+    int nw = 0;
+    size_t smem = 0;
+    const int rc = sample_setup(d, proj, n_pad, offsets, offsets2, loc_out, conf_out, p, nw, smem);
+    if (rc != TDRN_OK) return rc;
     TDRN_CUDA(cudaFuncSetAttribute(deform_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     deform_sample_kernel<<<d->B * p.tiles_w * p.tiles_h, nw * 32, smem, as_stream(stream)>>>(p);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
+extern "C" int tdrn_deform_head_sample_group(int n_levels, const tdrn_deform_head_desc *descs, const void *const *projs, int n_pad,
+                                             const float *const *offsets, const float *const *offsets2, float *loc_out, float *conf_out,
+                                             tdrn_stream_t stream)
+{
+    TDRN_REQUIRE(n_levels > 0 && n_levels <= TDRN_MAX_OFFSET_LEVELS && descs && projs && offsets, "tdrn_deform_head_sample_group: bad argument");
+    SampleGroup g{};
+    g.n = n_levels;
+    int nw_max = 0, run = 0;
+    size_t smem_max = 0;
+    for (int k = 0; k < n_levels; ++k) {
+        int nw = 0;
+        size_t smem = 0;
+        const int rc = sample_setup(&descs[k], projs[k], n_pad, offsets[k], offsets2 ? offsets2[k] : nullptr, loc_out, conf_out, g.lv[k], nw, smem);
+        if (rc != TDRN_OK) return rc;
+        g.first[k] = run;
+        run += descs[k].B * g.lv[k].tiles_w * g.lv[k].tiles_h;
+        nw_max = nw > nw_max ? nw : nw_max;
+        smem_max = smem > smem_max ? smem : smem_max;
+    }
+    g.first[n_levels] = run;
+    TDRN_CUDA(cudaFuncSetAttribute(deform_sample_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    deform_sample_group_kernel<<<run, nw_max * 32, smem_max, as_stream(stream)>>>(g);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }

@@ -447,7 +447,23 @@ class Engine(object):
                     self.head_into('%s_2.%d' % (loc_name, k), f, loc, 4, lv_off[k], P, 2, True, offs2[k], dg)
                     self.head_into('%s_2.%d' % (conf_name, k), f, conf, num_classes, lv_off[k], P, 2, True, offs2[k], dg)
 
-        self.parallel([(lambda k=k: level(k)) for k in range(len(feats))])
+        grouped = ((projected or projected_x3) and len(feats) <= 6 and os.environ.get('TDRN_DEFORM_GROUP', '1') != '0'
+                   and all(f.shape[0] * f.shape[1] * f.shape[2] * 34 * 2 * (2 * n_out16 if projected_x3 else n_out8) <= ops._deform_chunk_bytes()
+                           for f in feats))
+        if grouped:
+            # projections of the levels on parallel branches, then ONE sampler launch over all levels (the small levels are
+            # launch / tail bound on their own)
+            def project(k):
+                pc, n_pad = self.projected_head_weight(loc_name, conf_name, k, multihead, x3=projected_x3)
+                return ops.deform_project(feats[k], pc, n_pad, 3, 5 if multihead else 0, num_classes, split=projected_x3)
+
+            ys = self.parallel([(lambda k=k: project(k)) for k in range(len(feats))])
+            n_pad = self.projected_head_weight(loc_name, conf_name, 0, multihead, x3=projected_x3)[1]
+            ops.deform_sample_group(ys, [tuple(f.shape) for f in feats], n_pad, num_classes, 3, 1, offs, loc, conf, P, lv_off,
+                                    offsets2=offs2 if multihead else None, kh2=5 if multihead else 0,
+                                    pad2=2 if multihead else 0, softmax=softmax, split=projected_x3)
+        else:
+            self.parallel([(lambda k=k: level(k)) for k in range(len(feats))])
         conf2d = conf.view(B * P, num_classes)
         if softmax and not fused and not projected_x3:
             ops.softmax_rows(conf2d, out=conf2d)

@@ -446,6 +446,41 @@ def deform_head_projected(feat_nhwc, offsets, pc_proj, n_pad, num_classes, kh, p
                   'tdrn_deform_head_sample')
 
 
+def deform_project(feat_nhwc, pc_proj, n_pad, kh, kh2, num_classes, split=False):
+    """First half of deform_head_projected for a whole batch: the per-tap projections [B,H,W,taps*width] bf16."""
+    x = _cuda(feat_nhwc, 'feat')
+    B, H, W, Cin = x.shape
+    taps = kh * kh + kh2 * kh2
+    width = 2 * n_pad if split else n_pad
+    y = torch.empty(B, H, W, taps * width, dtype=torch.bfloat16, device=x.device)
+    flops = 2.0 * B * H * W * (12 + 3 * num_classes) * Cin * taps
+    tag = 'deform_head_x3' if split else 'deform_head_tc'
+    label = '%s|%d @%dx%d k%d+%d project' % (tag, Cin, H, W, kh, kh2)
+    if split:
+        conv2d(split_bf16(x), pc_proj, use_tc=True, out=y, split3=True, split_out=n_pad, out_sb=H * W * taps * width,
+               out_sp=taps * width, label=label, work=flops)
+    else:
+        conv2d(x, pc_proj, use_tc=True, out=y, label=label, work=flops)
+    return y
+
+
+def deform_sample_group(projs, shapes, n_pad, num_classes, kh, pad, offsets, loc_out, conf_out, P, prior_offs,
+                        offsets2=None, kh2=0, pad2=0, softmax=True, split=False):
+    """Second half for ALL pyramid levels in one launch (tdrn_deform_head_sample_group).  projs[k] from deform_project,
+    shapes[k] = (B, H, W, Cin) of level k's feature map."""
+    n = len(projs)
+    width = 2 * n_pad if split else n_pad
+    descs = (DeformHeadDesc * n)()
+    for k, (B, H, W, Cin) in enumerate(shapes):
+        descs[k] = DeformHeadDesc(B=B, H=H, W=W, Cin=Cin, num_classes=num_classes, dg=1, kh=kh, pad=pad, kh2=kh2, pad2=pad2,
+                                  P=P, prior_off=int(prior_offs[k]), softmax=int(softmax), split=int(split))
+    vp = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])
+    with _Timed('%s|all %d levels k%d+%d sample' % ('deform_head_x3' if split else 'deform_head_tc', n, kh, kh2), 0.0):
+        check(_lib.lib().tdrn_deform_head_sample_group(n, descs, vp(projs), width, vp(offsets),
+                                                       vp(offsets2) if offsets2 else None, ptr(loc_out), ptr(conf_out),
+                                                       stream_handle()), 'tdrn_deform_head_sample_group')
+
+
 def preprocess(frames_u8, size, mean, swap_rb=False, out=None, flip_lr=False):
     """[B,Hs,Ws,3] uint8 CUDA frames (cv2 channel order) -> [B,3,size,size] fp32 NCHW network input:
     base_transform (data/__init__.py:7-12) + optional channel swap + HWC->CHW, one launch (tdrn_preprocess)."""

@@ -220,6 +220,43 @@ def test_deform_head_projected_vs_oracle(B, H, W, cin, C, multihead, chunk_mb, m
     assert rel_err(conf.cpu().numpy(), conf3.cpu().numpy()) < 1.5e-2
 
 
+@pytest.mark.parametrize('multihead,split,softmax', [(False, False, True), (True, False, True), (True, True, False),
+                                                     (False, True, True)])
+def test_deform_sample_group_is_bit_identical_to_per_level(multihead, split, softmax):
+    """tdrn_deform_head_sample_group (all pyramid levels in one launch) writes exactly what the per-level launches write."""
+    from tdrn_b200 import ops
+    B, C, cin = 3, 21, 256
+    sizes = [(20, 24), (10, 12), (5, 6), (3, 3)]
+    g = torch.Generator().manual_seed(7 + multihead + 2 * split)
+    P = sum(h * w * 3 for h, w in sizes)
+    lv = [0]
+    for h, w in sizes:
+        lv.append(lv[-1] + h * w * 3)
+    feats, offs, offs2, packs = [], [], [], []
+    for h, w in sizes:
+        x = torch.randn(B, h, w, cin, generator=g).cuda()
+        feats.append(x if split else x.to(torch.bfloat16))
+        offs.append((torch.randn(B, h, w, 18, generator=g) * 1.5).cuda())
+        offs2.append((torch.randn(B, h, w, 50, generator=g) * 1.5).cuda())
+        w1 = torch.randn(12 + 3 * C, cin, 3, 3, generator=g) * 0.03
+        w2 = torch.randn(12 + 3 * C, cin, 5, 5, generator=g) * 0.02 if multihead else None
+        packs.append(ops.pack_deform_proj_weight(w1, w2, x3=split))
+    kw = dict(kh2=5 if multihead else 0, pad2=2 if multihead else 0, softmax=softmax, split=split)
+    loc_a = torch.zeros(B, P, 4, device='cuda')
+    conf_a = torch.zeros(B, P, C, device='cuda')
+    for k in range(len(sizes)):
+        ops.deform_head_projected(feats[k], offs[k], packs[k][0], packs[k][1], C, 3, 1, loc_a, conf_a, P, lv[k],
+                                  offsets2=offs2[k] if multihead else None, **kw)
+    loc_b = torch.zeros(B, P, 4, device='cuda')
+    conf_b = torch.zeros(B, P, C, device='cuda')
+    ys = [ops.deform_project(feats[k], packs[k][0], packs[k][1], 3, 5 if multihead else 0, C, split=split)
+          for k in range(len(sizes))]
+    ops.deform_sample_group(ys, [tuple(f.shape) for f in feats], packs[0][1], C, 3, 1, offs, loc_b, conf_b, P, lv[:-1],
+                            offsets2=offs2 if multihead else None, **kw)
+    torch.cuda.synchronize()
+    assert loc_a.abs().sum() > 0 and torch.equal(loc_a, loc_b) and torch.equal(conf_a, conf_b)
+
+
 @pytest.mark.parametrize('b,h,w,relu', [
     (2, 8, 64, True),          # 64x2 tiles, one tile row per image pair
     (3, 20, 96, True),         # 32x4 tiles
