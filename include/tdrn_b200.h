@@ -128,8 +128,8 @@ typedef struct tdrn_conv_desc {
                                   Wo % 16 == 0 and Ho % 8 == 0                                             */
     int split3;                /* 1 (tdrn_conv2d_tc only): fp32-accurate tensor-core mode.  `in` is the SPLIT tensor
                                   [B,H,W,2*Cin] bf16 written by tdrn_split_bf16 (per pixel: Cin high parts, then Cin low
-                                  parts, x = hi + lo to 16 mantissa bits); `weight` is packed [Cout_pad][kh*kw][3*Cin] =
-                                  (W_hi | W_lo | W_hi).  The kernel accumulates hi*W_hi + hi*W_lo + lo*W_hi in fp32
+                                  parts, x = hi + lo to 16 mantissa bits); `weight` is packed [Cout_pad][kh*kw][2*Cin] =
+                                  (W_hi | W_lo) per tap.  The kernel accumulates hi*W_hi + hi*W_lo + lo*W_hi in fp32
                                   (the reference's convs are fp32, model/networks.py:136-163; the dropped lo*lo term is
                                   2^-18 relative).  Needs Cin % 64 == 0.                                      */
     int split_out;             /* g > 0 (split3, bf16 out, out_sp == 2*Cout, g % 16 == 0, Cout % g == 0): the fp32 result is

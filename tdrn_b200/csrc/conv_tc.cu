@@ -80,12 +80,21 @@ struct TcConvP {
     int splitk;                  // > 1: K is split over a thread-block cluster of this many CTAs (conv_splitk_kernel)
     int split_nacc;              // split mode: accumulators the hi * W_hi products are spread over (1 or 3)
     int split_g;                 // > 0: output written as (hi | lo) bf16 pairs in groups of split_g channels (tdrn_conv_desc.split_out)
-    int split_cb;                // > 0: fp32-accurate mode (tdrn_conv_desc.split3) with split_cb real channel blocks: the K loop runs
-                                 // over 3*split_cb blocks per tap -- (hi, W_hi), (hi, W_lo), (lo, W_hi) -- and the activation
-                                 // tensor holds [hi | lo], so A block cb is read at channel block (cb < 2*split_cb ? cb % split_cb : cb - split_cb)
+    int split_cb;                // > 0: fp32-accurate mode (tdrn_conv_desc.split3) with split_cb channel blocks per tap: a ring stage holds
+                                 // FOUR boxes of one (tap, channel block) -- x_hi, x_lo, W_hi, W_lo; the activation tensor is [hi | lo],
+                                 // the weight K axis is taps x [W_hi | W_lo] -- and feeds three products: hi*W_hi, hi*W_lo, lo*W_hi
     const float *bias; const void *res; void *out;
     long long out_sb, out_sp; int out_w;
     int relu, deconv, out_f32, pool;
+};
+
+// split mode (fp32-accurate): ring stage = x_hi | x_lo | W_hi | W_lo boxes of one (tap, channel block); fp32 / (hi|lo) register-store epilogue
+template <int BN> struct TcSplitCfg {
+    static constexpr int A_BYTES = 128 * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (208 * 1024) / STAGE_BYTES;          // 2 / 3 / 4 stages for BN = 256 / 128 / 64
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
 };
 
 template <int BN, int MT = 1> struct TcCfg {
@@ -115,6 +124,9 @@ constexpr int TC_THREADS = 320;           // warp 0 TMA, warp 1 MMA, warps 2-9 e
 // NACC = 3 accumulators (each takes a third of the steps; 3 + 1 accumulators of BN = 128 columns fill TMEM), the two small products
 // (hi * W_lo, lo * W_hi: 2^-8 of the magnitude, their truncation does not matter) share one more, and the epilogue adds the
 // accumulators in fp32 registers.  All 512 TMEM columns belong to one tile: no accumulator double-buffering in this mode.
+// Operands: each (tap, channel block) brings x_hi, x_lo, W_hi, W_lo ONCE (64 KB at BN = 128) for its three products -- 85 bytes per
+// MMA cycle from L2 instead of the 128 of one (A, B) pair per product, which is what bound the first version (r02i: 560 TFLOP/s
+// of products on the 40x40 layers against 1 400 for the bf16 kernel).
 template <int BN, int CL, bool RES, int MT, int SPLIT = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmA2,
@@ -154,8 +166,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int tile_end = RES ? (int)((long long)total_tiles * (unit0 + 1) / unit_step) : total_tiles;
     const int tile_step = RES ? 1 : unit_step;
     // shared-memory layout: ring of (A box | B box) stages, or -- resident weights -- num_kb B boxes followed by a ring of A boxes
-    const uint32_t n_stages = RES ? (uint32_t)p.a_stages : (uint32_t)Cfg::STAGES;
-    constexpr uint32_t a_stride = RES ? (uint32_t)Cfg::A_BYTES : (uint32_t)Cfg::STAGE_BYTES;
+    const uint32_t n_stages = RES ? (uint32_t)p.a_stages : (SPLIT ? (uint32_t)TcSplitCfg<BN>::STAGES : (uint32_t)Cfg::STAGES);
+    constexpr uint32_t a_stride = RES ? (uint32_t)Cfg::A_BYTES : (SPLIT ? (uint32_t)TcSplitCfg<BN>::STAGE_BYTES : (uint32_t)Cfg::STAGE_BYTES);
     uint8_t *a_base = RES ? tiles + num_kb * Cfg::B_BYTES : tiles;
 
     if (threadIdx.x == 0) {
@@ -219,12 +231,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     uint8_t *sb = RES ? tiles + kb * Cfg::B_BYTES : sa + MT * Cfg::A_BYTES;
                     const int tap = kb / cblocks, cb = kb - tap * cblocks;
                     const int tr = tap / p.kw, ts = tap - tr * p.kw;
-                    const int a_cb = p.split_cb ? (cb < 2 * p.split_cb ? cb % p.split_cb : cb - p.split_cb) : cb;
+                    if (SPLIT) {
+                        // x_hi | x_lo | W_hi | W_lo of this (tap, channel block); weight column = (tap * 2 + half) * Cin + cb * 64
+                        mbar_expect_tx(&full_bar[s], 2u * a_bytes + 2u * p.b_bytes);
+                        tma_load_4d(sa, mapA[0], &full_bar[s], cb * 64, w0[0] + ts * p.dil, h0[0] + tr * p.dil, b0[0]);
+                        tma_load_4d(sa + Cfg::A_BYTES, mapA[0], &full_bar[s], (cblocks + cb) * 64, w0[0] + ts * p.dil, h0[0] + tr * p.dil, b0[0]);
+                        tma_load_2d(sa + 2 * Cfg::A_BYTES, &tmB, &full_bar[s], (2 * tap * cblocks + cb) * 64, n0);
+                        tma_load_2d(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &tmB, &full_bar[s], ((2 * tap + 1) * cblocks + cb) * 64, n0);
+                        if (++s == n_stages) { s = 0; ph ^= 1u; }
+                        continue;
+                    }
                     mbar_expect_tx(&full_bar[s], a_bytes + (load_b ? p.b_bytes : 0u));
 #pragma unroll
                     for (int sub = 0; sub < MT; ++sub)
                         if (have[sub])
-                            tma_load_4d(sa + sub * Cfg::A_BYTES, mapA[sub], &full_bar[s], a_cb * 64, w0[sub] + ts * p.dil,
+                            tma_load_4d(sa + sub * Cfg::A_BYTES, mapA[sub], &full_bar[s], cb * 64, w0[sub] + ts * p.dil,
                                         h0[sub] + tr * p.dil, b0[sub]);
                     if (!load_b) {
                         // this stage still holds k-block kb of the same N tile
@@ -253,24 +274,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
                 const bool have1 = MT == 2 && (tile % m_units) * 2 + 1 < p.m_tiles;
-                uint32_t hh = 0, touched = 0;        // split mode: running count of hi * W_hi blocks, accumulators already written
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(a_base + s * a_stride);
                     const uint64_t adesc = umma_desc_sw128(sa);
                     const uint64_t bdesc = umma_desc_sw128(RES ? smem_u32(tiles + kb * Cfg::B_BYTES) : sa + MT * Cfg::A_BYTES);
-                    uint32_t d_acc = d_tmem, fresh = kb == 0 ? 1u : 0u;
                     if (SPLIT) {
-                        const int cb = kb % cblocks;                          // block inside the tap: [hi*W_hi | hi*W_lo | lo*W_hi]
-                        const uint32_t a = cb < p.split_cb ? (hh++ % (uint32_t)NACC) : (uint32_t)NACC;
-                        d_acc = tmem_base + a * BN;
-                        fresh = ((touched >> a) & 1u) ^ 1u;
-                        touched |= 1u << a;
+                        // hi * W_hi -> accumulator kb % NACC (each takes a third of the truncating steps); hi * W_lo and lo * W_hi -> the last one
+                        const uint64_t alo = umma_desc_sw128(sa + Cfg::A_BYTES);
+                        const uint64_t bhi = umma_desc_sw128(sa + 2 * Cfg::A_BYTES), blo = umma_desc_sw128(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+                        const uint32_t a = (uint32_t)kb % (uint32_t)NACC;
+                        const uint32_t d_big = tmem_base + a * BN, d_small = tmem_base + (uint32_t)NACC * BN;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d_big, adesc + (uint64_t)(k * 2), bhi + (uint64_t)(k * 2), idesc, kb >= NACC || k != 0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d_small, adesc + (uint64_t)(k * 2), blo + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d_small, alo + (uint64_t)(k * 2), bhi + (uint64_t)(k * 2), idesc, true);
+                        umma_commit(&empty_bar[s]);
+                        if (++s == n_stages) { s = 0; ph ^= 1u; }
+                        continue;
                     }
 #pragma unroll
                     for (int k = 0; k < 4; ++k)      // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle atom
-                        umma_bf16(d_acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (fresh == 0u) || k != 0);
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
                     if (have1) {                     // second M tile of the unit: same weight box, accumulator in the upper columns
                         const uint64_t adesc1 = umma_desc_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
@@ -399,8 +430,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 float v[16];
                 tmem_ld16(trow + (uint32_t)c0, v);
                 if (SPLIT) {                                         // + the other hi * W_hi accumulators in use + the small-product one
-                    const int n_hh = p.taps * p.split_cb;
-                    const int used = n_hh < NACC ? n_hh : NACC;
+                    const int used = num_kb < NACC ? num_kb : NACC;
                     for (int a = 1; a <= NACC; ++a) {
                         if (a >= used && a != NACC) continue;
                         float u[16];
@@ -783,16 +813,17 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmA2, const CUte
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < g_num_sms ? total : g_num_sms;
     if (p.split_cb) {
+        constexpr int smem = TcSplitCfg<BN>::SMEM_BYTES;
         if constexpr (BN <= 128) {
             if (p.split_nacc == 3) {
-                TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, false, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-                conv_tc_kernel<BN, 1, false, 1, 3><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+                TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, false, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                conv_tc_kernel<BN, 1, false, 1, 3><<<grid, TC_THREADS, smem, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
                 TDRN_LAUNCH_CHECK();
                 return TDRN_OK;
             }
         }
-        TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, false, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        conv_tc_kernel<BN, 1, false, 1, 1><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+        TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, false, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        conv_tc_kernel<BN, 1, false, 1, 1><<<grid, TC_THREADS, smem, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
         TDRN_LAUNCH_CHECK();
         return TDRN_OK;
     }
@@ -851,7 +882,7 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     // p.Cin is padded to 64: the k-block count and the weight K use it, the activation tensor map uses the real Cin
     p.B = d->B; p.Cin = (d->Cin + 63) & ~63; p.Cout = d->Cout; p.n_total = d->deconv2x2 ? 4 * d->Cout : d->Cout;
     const int cin_mem = d->split3 ? 2 * d->Cin : d->Cin;        // channels of the activation tensor in memory ([hi | lo] when split)
-    if (d->split3) { p.split_cb = d->Cin >> 6; p.Cin = 3 * d->Cin; p.split_g = d->split_out; }
+    if (d->split3) { p.split_cb = d->Cin >> 6; p.split_g = d->split_out; }
     p.kw = kw; p.taps = kh * kw; p.pad = pad; p.dil = dil; p.stride = stride;
     p.bias = bias; p.res = residual; p.out = out;
     p.out_sb = d->out_sb; p.out_sp = d->out_sp;
@@ -947,7 +978,7 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         }
     }
     {
-        const uint64_t K = (uint64_t)p.taps * p.Cin;
+        const uint64_t K = (uint64_t)p.taps * p.Cin * (d->split3 ? 2 : 1);       // split mode: taps x [W_hi | W_lo]
         const uint64_t dims[2] = {K, (uint64_t)n_pad16};
         const uint64_t str[1] = {K * 2};
         const uint32_t b_rows = (uint32_t)(n_pad16 < BN ? n_pad16 : BN);

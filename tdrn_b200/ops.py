@@ -85,7 +85,7 @@ class PackedConv(object):
 
     w_f32  [kh*kw*Cin, Cout] fp32 (tap-major, then cin)      -> tdrn_conv2d (SIMT, fp32 accumulate)
     w_bf16 [Cout_pad, kh*kw*Cin_pad] bf16, K-major           -> tdrn_conv2d_tc (tcgen05); Cin_pad = Cin up to 64
-    w_x3   [Cout_pad, kh*kw*3*Cin] bf16 (W_hi | W_lo | W_hi)  -> tdrn_conv2d_tc with split3 (fp32-accurate tensor-core path)
+    w_x3   [Cout_pad, kh*kw*2*Cin] bf16 (W_hi | W_lo per tap)  -> tdrn_conv2d_tc with split3 (fp32-accurate tensor-core path)
     deconv (ConvTranspose2d k2 s2, weight [Cin,Cout,2,2]): w_f32 [Cin, 4*Cout] with n = (i*2+j)*Cout+co
     """
 
@@ -115,7 +115,7 @@ class PackedConv(object):
         self.w_bf16 = None
         self.w_x3 = None
         if want_x3 and self.cin % 64 == 0:
-            # fp32-accurate tensor-core mode (tdrn_conv_desc.split3): [rows_pad][taps][W_hi | W_lo | W_hi] bf16, where the fp32
+            # fp32-accurate tensor-core mode (tdrn_conv_desc.split3): [rows_pad][taps][W_hi | W_lo] bf16, where the fp32
             # weight (BN folded in float64, rounded to fp32 like the reference's parameters) is hi + lo to 16 mantissa bits
             rows = wk.shape[0]
             rows_pad = (rows + 15) // 16 * 16
@@ -123,9 +123,9 @@ class PackedConv(object):
             w32 = wk.float().reshape(rows, taps, self.cin)
             hi = w32.to(torch.bfloat16)
             lo = (w32 - hi.float()).to(torch.bfloat16)
-            wp = torch.zeros(rows_pad, taps, 3 * self.cin, dtype=torch.bfloat16)
-            wp[:rows] = torch.cat([hi, lo, hi], 2)
-            self.w_x3 = wp.reshape(rows_pad, taps * 3 * self.cin).contiguous().to(device)
+            wp = torch.zeros(rows_pad, taps, 2 * self.cin, dtype=torch.bfloat16)
+            wp[:rows] = torch.cat([hi, lo], 2)
+            self.w_x3 = wp.reshape(rows_pad, taps * 2 * self.cin).contiguous().to(device)
         if want_bf16 and self.cin % 8 == 0 and self.cin >= 16:
             rows = wk.shape[0]
             rows_pad = (rows + 15) // 16 * 16
