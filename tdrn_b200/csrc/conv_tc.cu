@@ -93,8 +93,9 @@ template <int BN> struct TcSplitCfg {
     static constexpr int A_BYTES = 128 * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = (208 * 1024) / STAGE_BYTES;          // 2 / 3 / 4 stages for BN = 256 / 128 / 64
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;          // 2 / 3 / 4 stages for BN = 256 / 128 / 64
+    static constexpr int OUT_STAGE_BYTES = 2 * 128 * 128;              // (hi box | lo box) of the TMA-store epilogue, [128 px][64 ch] bf16 each
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024;
 };
 
 template <int BN, int MT = 1> struct TcCfg {
@@ -137,10 +138,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     static_assert(MT == 1 || (CL == 1 && !RES), "two-M-tile units: single CTA, streamed weights");
     static_assert(!SPLIT || ((SPLIT + 1) * BN <= 512 && CL == 1 && !RES && MT == 1), "split mode: SPLIT + 1 accumulators of BN columns, single CTA, streamed weights");
     using Cfg = TcCfg<BN, MT>;
-    constexpr uint32_t NBUF = (MT == 2 || SPLIT) ? 1u : 2u;           // accumulator buffers a unit alternates between
     constexpr int NACC = SPLIT ? SPLIT : 1;                           // split mode: accumulators of the hi * W_hi products (the host picks
                                                                       // ONE value for all tile shapes: results must not depend on BN, i.e. on the batch size)
-    constexpr int TMEM_COLS = SPLIT ? ((SPLIT + 1) * BN > 256 ? 512 : ((SPLIT + 1) * BN > 128 ? 256 : 128)) : Cfg::TMEM_COLS;
+    constexpr uint32_t ACC_COLS = SPLIT ? (uint32_t)((SPLIT + 1) * BN) : (uint32_t)BN;     // TMEM columns of one tile's accumulator set
+    // accumulator sets a unit alternates between (the epilogue of tile i overlaps the main loop of tile i+1): two where TMEM
+    // holds them -- in split mode that is BN = 64 with 3 + 1 accumulators, BN <= 128 with 1 + 1
+    constexpr uint32_t NBUF = MT == 2 ? 1u : (SPLIT ? (2u * ACC_COLS <= 512u ? 2u : 1u) : 2u);
+    constexpr int TMEM_COLS = SPLIT ? (NBUF * ACC_COLS > 256 ? 512 : (NBUF * ACC_COLS > 128 ? 256 : 128)) : Cfg::TMEM_COLS;
     extern __shared__ uint8_t smem_dyn[];
     constexpr int MAX_STAGES = Cfg::STAGES > 8 ? Cfg::STAGES : 8;
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const uint32_t buf = tcount % NBUF;
                 mbar_wait(&tmem_empty_bar[buf], ((tcount / NBUF) & 1u) ^ 1u);   // epilogue drained this buffer
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * BN;
+                const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
                 const bool have1 = MT == 2 && (tile % m_units) * 2 + 1 < p.m_tiles;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[s], ph);
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         const uint64_t alo = umma_desc_sw128(sa + Cfg::A_BYTES);
                         const uint64_t bhi = umma_desc_sw128(sa + 2 * Cfg::A_BYTES), blo = umma_desc_sw128(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
                         const uint32_t a = (uint32_t)kb % (uint32_t)NACC;
-                        const uint32_t d_big = tmem_base + a * BN, d_small = tmem_base + (uint32_t)NACC * BN;
+                        const uint32_t d_big = d_tmem + a * BN, d_small = d_tmem + (uint32_t)NACC * BN;
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_bf16(d_big, adesc + (uint64_t)(k * 2), bhi + (uint64_t)(k * 2), idesc, kb >= NACC || k != 0);
@@ -323,7 +327,126 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // processed, so its global-memory latency overlaps the TMEM load / arithmetic / stores.
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const int r = quad * 32 + lane;
-        if (p.tma_out) {
+        if (SPLIT != 0 && p.tma_out) {
+            // ---- split mode, (hi | lo) bf16 output [B,Ho,Wo,2*Cout] (optionally 2x2 max-pooled): sum of the accumulators -> bias /
+            // ReLU / pool in fp32 -> hi = bf16(v), lo = bf16(v - hi) -> two 128B-swizzled staging boxes -> two TMA stores (channels
+            // n .. n+63 and Cout + n .. Cout + n+63).  Same arithmetic, in the same order, as the register-store path below.
+            // Unpooled tiles use one (hi | lo) box pair and wait for its previous store to be read out right before refilling it
+            // (the loads and the arithmetic of the group hide that); pooled tiles (32 rows) alternate between two pairs.
+            uint8_t *stage_base = tiles + TcSplitCfg<BN>::STAGES * TcSplitCfg<BN>::STAGE_BYTES;
+            const bool leader = threadIdx.x == 64;
+            const int used = num_kb < NACC ? num_kb : NACC;
+            const int wl = r % p.bw, hl = (r / p.bw) % p.bh;
+            const uint32_t box_bytes = p.pool ? 32u * 128u : 128u * 128u;
+            uint32_t tcount = 0, git = 0;
+            for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
+                const int mt = tile % m_units, nt = tile / m_units;
+                const int n0 = nt * BN;
+                const int n_eff = min(BN, n_pad16 - n0);
+                const uint32_t buf = tcount % NBUF;
+                mbar_wait(&tmem_full_bar[buf], (tcount / NBUF) & 1u);
+                tc_fence_after();
+                const int groups = (n_eff + 63) >> 6;
+                const bool tail = p.rr && mt >= p.nA;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+                const int x0 = tw * p.bw, y0 = tail ? p.qh * p.bh : th * p.bh, b0 = tail ? (mt - p.nA) * p.g2 : tn * p.bn;
+                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * ACC_COLS;
+                for (int g = 0; g < groups; ++g, ++git) {
+                    uint8_t *o = stage_base + (p.pool ? (git & 1u) * 2u * box_bytes : 0u);
+                    const int c0 = g * 64 + half * 32;
+                    const bool have = c0 < n_eff;                    // warp-uniform
+                    uint32_t qh[16], ql[16];
+                    if (have) {
+                        float v[32];
+                        {
+                            uint32_t ra[32], rb[32];
+                            tmem_ld32_issue(trow + (uint32_t)c0, ra);
+                            tmem_ld32_issue(trow + (uint32_t)((NACC == 1 ? 1 : 1) * BN + c0), rb);   // accumulator 1 (NACC = 1: the small-product one)
+                            tmem_ld_wait32(ra);
+                            tmem_ld_pin32(rb);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+                            if (NACC == 1 || used > 1) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rb[j]);
+                            }
+                        }
+                        if (NACC == 3) {
+                            uint32_t ra[32], rb[32];
+                            tmem_ld32_issue(trow + (uint32_t)(2 * BN + c0), ra);
+                            tmem_ld32_issue(trow + (uint32_t)(3 * BN + c0), rb);
+                            tmem_ld_wait32(ra);
+                            tmem_ld_pin32(rb);
+                            if (used > 2) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(ra[j]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rb[j]);
+                        }
+                        if (g == groups - 1) {                          // all tcgen05.ld of this tile are complete
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+                        }
+                        if (p.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 bq = __ldg((const float4 *)(p.bias + n0 + c0 + j));
+                                v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
+                            }
+                        }
+                        if (p.pool) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                                v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, p.bw));
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+                            const __nv_bfloat16 l0 = __float2bfloat16_rn(__fsub_rn(v[2 * j], __bfloat162float(h0)));
+                            const __nv_bfloat16 l1 = __float2bfloat16_rn(__fsub_rn(v[2 * j + 1], __bfloat162float(h1)));
+                            qh[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            ql[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                    } else if (g == groups - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+                    }
+                    if (leader) { if (p.pool) bulk_wait_read<1>(); else bulk_wait_read<0>(); }   // the stores that last read these boxes have drained
+                    named_bar(1, 256);
+                    if (have) {
+                        int row = r;
+                        bool wr = true;
+                        if (p.pool) { wr = !(wl & 1) && !(hl & 1); row = (hl >> 1) * (p.bw >> 1) + (wl >> 1); }
+                        if (wr) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                *(uint4 *)(o + sw128_offset(row, half * 4 + k)) = make_uint4(qh[4 * k], qh[4 * k + 1], qh[4 * k + 2], qh[4 * k + 3]);
+                                *(uint4 *)(o + box_bytes + sw128_offset(row, half * 4 + k)) = make_uint4(ql[4 * k], ql[4 * k + 1], ql[4 * k + 2], ql[4 * k + 3]);
+                            }
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    named_bar(1, 256);
+                    if (leader) {
+                        const CUtensorMap *m = tail ? &tmO2 : &tmO;
+                        const int xo = p.pool ? x0 >> 1 : x0, yo = p.pool ? y0 >> 1 : y0;
+                        tma_store_4d(m, o, n0 + g * 64, xo, yo, b0);
+                        tma_store_4d(m, o + box_bytes, p.Cout + n0 + g * 64, xo, yo, b0);
+                        bulk_commit();
+                    }
+                }
+            }
+            if (leader) bulk_wait_read<0>();
+        } else if (p.tma_out) {
             // ---- plain NHWC bf16 output: TMEM -> bias/ReLU -> bf16 -> 128B-swizzled [128 px][64 ch] staging box -> TMA store.
             // Whole 128-byte lines leave the SM (a per-thread store writes 32 bytes of 32 different lines), rows beyond the
             // map / channels beyond Cout are clipped by TMA.  Two staging boxes: the store of column group g drains while
@@ -423,7 +546,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t buf = tcount % NBUF;
             mbar_wait(&tmem_full_bar[buf], (tcount / NBUF) & 1u);
             tc_fence_after();
-            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * ACC_COLS;
             for (int c0 = half * 16; c0 < n_eff; c0 += 32) {
                 const uint4 rc[2] = {rn[0], rn[1]};
                 prefetch_res(c0 + 32);
@@ -863,8 +986,8 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     }
     TDRN_REQUIRE(!d->split3 || d->Cin % 64 == 0, "tdrn_conv2d_tc: split3 needs Cin %% 64 == 0 (got %d)", d->Cin);
     TDRN_REQUIRE(!d->split_out || (d->split3 && d->out_dtype == TDRN_BF16 && d->split_out % 16 == 0 && d->Cout % d->split_out == 0 &&
-                                   d->out_sp == 2ll * d->Cout && !d->deconv2x2 && !d->pool2x2 && !residual && ((uintptr_t)out & 15) == 0),
-                 "tdrn_conv2d_tc: split_out needs split3, bf16 out, g %% 16 == 0, Cout %% g == 0, out_sp == 2*Cout, plain conv");
+                                   d->out_sp == 2ll * d->Cout && !d->deconv2x2 && !residual && ((uintptr_t)out & 15) == 0),
+                 "tdrn_conv2d_tc: split_out needs split3, bf16 out, g %% 16 == 0, Cout %% g == 0, out_sp == 2*Cout, no deconv / residual");
     {   // narrow high-resolution 3x3 layers: halo tile + resident weights (conv_halo_tc.cu)
         static const bool no_halo = getenv("TDRN_NO_HALO") != nullptr;
         if (!no_halo && !d->split3) {
@@ -1013,7 +1136,24 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         static const bool no_tma_out = getenv("TDRN_NO_TMA_STORE") != nullptr;
         p.tma_out = !no_tma_out && !d->split3 && p.splitk == 1 && !d->deconv2x2 && !p.pool && !p.out_f32 && !residual && d->Cout % 8 == 0 &&
                     d->out_sp == d->Cout && d->out_sb == (long long)p.H * p.W * d->Cout && ((uintptr_t)out & 15) == 0;
-        if (p.tma_out) {
+        if (!no_tma_out && d->split3 && d->split_out == d->Cout && d->Cout % 64 == 0) {
+            // split mode writing the whole (hi | lo) operand of the next layer, [B,Ho,Wo,2*Cout] contiguous (optionally pooled)
+            const int Ho = p.pool ? p.H / 2 : p.H, Wo = p.pool ? p.W / 2 : p.W;
+            if (d->out_sb == (long long)Ho * Wo * 2 * d->Cout) {
+                p.tma_out = 1;
+                const uint64_t dims[4] = {(uint64_t)2 * d->Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)p.B};
+                const uint64_t str[3] = {(uint64_t)d->Cout * 4, (uint64_t)Wo * d->Cout * 4, (uint64_t)Ho * Wo * d->Cout * 4};
+                const uint32_t box[4] = {64, (uint32_t)(p.pool ? p.bw / 2 : p.bw), (uint32_t)(p.pool ? p.bh / 2 : p.bh), (uint32_t)p.bn};
+                int rc = make_tmap_bf16(&tmO, out, 4, dims, str, box, nullptr);
+                if (rc) return rc;
+                tmO2 = tmO;
+                if (p.rr) {
+                    const uint32_t box2[4] = {64, (uint32_t)p.bw, (uint32_t)p.rr, (uint32_t)p.g2};
+                    rc = make_tmap_bf16(&tmO2, out, 4, dims, str, box2, nullptr);
+                    if (rc) return rc;
+                }
+            }
+        } else if (p.tma_out) {
             const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
             const uint64_t str[3] = {(uint64_t)d->Cout * 2, (uint64_t)p.W * d->Cout * 2, (uint64_t)p.H * p.W * d->Cout * 2};
             const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
@@ -1031,7 +1171,7 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         static const bool no_mt2 = getenv("TDRN_NO_MT2") != nullptr;
         const int num_kb = p.taps * (p.Cin >> 6);
         const int units2 = ((p.m_tiles + 1) / 2) * p.n_tiles;
-        p.mt2 = !no_mt2 && BN == 256 && p.tma_out && !p.b_resident && !use_cluster && num_kb >= 64 && units2 * 10 >= g_num_sms * 7;   // measured: K = 2304 (36 k-blocks) loses 5 %, K = 4608 gains 5-10 %
+        p.mt2 = !no_mt2 && !d->split3 && BN == 256 && p.tma_out && !p.b_resident && !use_cluster && num_kb >= 64 && units2 * 10 >= g_num_sms * 7;   // measured: K = 2304 (36 k-blocks) loses 5 %, K = 4608 gains 5-10 %
     }
     cudaStream_t st = as_stream(stream);
     if (p.splitk > 1) {

@@ -33,6 +33,12 @@ def level_sizes(size):
     return [l0, l1, l2, l3]
 
 
+def _mark_split(t, kw):
+    if kw.get('split_out'):
+        t._tdrn_is_split = True
+    return t
+
+
 class Engine(object):
     def __init__(self, module, precision):
         if precision not in ('fp32', 'bf16'):
@@ -149,33 +155,27 @@ class Engine(object):
         use_tc = (self.use_tc and pc.w_bf16 is not None and x.dtype == torch.bfloat16
                   and not kw.get('dg') and kw.get('in_shape') is None and (stride in (1, 2) or deconv))
         ceil_mode = kw.pop('ceil_mode', False)
-        if (self.use_x3 and pc.w_x3 is not None and x.dtype == torch.float32 and not kw.get('dg') and kw.get('in_shape') is None
-                and (stride in (1, 2) or deconv)):
+        to_split = kw.pop('to_split', False)
+        is_split = getattr(x, '_tdrn_is_split', False)
+        if is_split and not (self.use_x3 and pc.w_x3 is not None):
+            raise RuntimeError('%s: a split (hi | lo) activation can only feed a split-precision tensor-core conv' % name)
+        if (self.use_x3 and pc.w_x3 is not None and (is_split or x.dtype == torch.float32) and not kw.get('dg')
+                and kw.get('in_shape') is None and (stride in (1, 2) or deconv)):
             # one split per activation tensor, shared by all its consumers -- which may sit on different branch streams (an ARM
             # source feeds its ARM head and its TCB branch): the split is made on the first consumer's stream and carries an
-            # event the others wait for
-            cur = torch.cuda.current_stream()
-            ent = getattr(x, '_tdrn_split', None)
-            if ent is None:
-                xs = ops.split_bf16(x)
-                ev = torch.cuda.Event()
-                ev.record(cur)
-                try:
-                    x._tdrn_split = (xs, ev, cur)
-                except Exception:
-                    pass
-            else:
-                xs, ev, st = ent
-                if st != cur:
-                    cur.wait_event(ev)
-                    xs.record_stream(cur)
+            # event the others wait for.  Layers whose output only feeds other split-precision convs (to_split=True) write the
+            # (hi | lo) operand themselves: no fp32 copy of it, no split kernel.
+            if to_split and not deconv and kw.get('residual') is None and kw.get('out') is None and pc.cout % 16 == 0:
+                kw['split_out'] = pc.cout
+            xs = self.split_of(x)
             kw.setdefault('out_dtype', torch.float32)
             if kw.pop('pool', False):
                 H, W = x.shape[1], x.shape[2]
                 if stride == 1 and 2 * pad == dil * (pc.kh - 1) and W % 16 == 0 and H % 8 == 0:
-                    return ops.conv2d(xs, pc, relu=relu, use_tc=True, pool=True, split3=True, **kw)
+                    return _mark_split(ops.conv2d(xs, pc, relu=relu, use_tc=True, pool=True, split3=True, **kw), kw)
+                kw.pop('split_out', None)
                 return ops.maxpool2x2(ops.conv2d(xs, pc, relu=relu, use_tc=True, split3=True, **kw), ceil_mode)
-            return ops.conv2d(xs, pc, relu=relu, use_tc=True, split3=True, **kw)
+            return _mark_split(ops.conv2d(xs, pc, relu=relu, use_tc=True, split3=True, **kw), kw)
         if kw.pop('pool', False):
             # MaxPool2d(2,2) after the conv: fused into the tcgen05 epilogue when the map tiles as 16x8 boxes
             H, W = x.shape[1], x.shape[2]
@@ -183,6 +183,27 @@ class Engine(object):
                 return ops.conv2d(x, pc, relu=relu, use_tc=True, pool=True, **kw)
             return ops.maxpool2x2(ops.conv2d(x, pc, relu=relu, use_tc=use_tc, **kw), ceil_mode)
         return ops.conv2d(x, pc, relu=relu, use_tc=use_tc, **kw)
+
+    def split_of(self, x):
+        """The (hi | lo) bf16 operand of fp32 activation ``x`` (made once, cached on the tensor with the event other streams wait for)."""
+        if getattr(x, '_tdrn_is_split', False):
+            return x
+        cur = torch.cuda.current_stream()
+        ent = getattr(x, '_tdrn_split', None)
+        if ent is None:
+            xs = ops.split_bf16(x)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            try:
+                x._tdrn_split = (xs, ev, cur)
+            except Exception:
+                pass
+            return xs
+        xs, ev, st = ent
+        if st != cur:
+            cur.wait_event(ev)
+            xs.record_stream(cur)
+        return xs
 
     def conv_first(self, name, x_nchw, stride, bn):
         pc = self.packed(name, stride, 1, 1, bn)
@@ -196,13 +217,14 @@ class Engine(object):
         idx, x = 0, None
         step = 3 if bn else 2
 
-        def conv_block(i, x, pad=1, dil=1, pool=None):
+        def conv_block(i, x, pad=1, dil=1, pool=None, to_split=False):
+            # to_split: the output feeds only the next trunk conv (fp32 path: written as the (hi | lo) operand, see conv())
             bnn = 'backbone.%d' % (i + 1) if bn else None
             if x is None:
                 return self.conv_first('backbone.%d' % i, x_nchw, 1, bnn)
             if pool is not None:
-                return self.conv('backbone.%d' % i, x, 1, pad, dil, bn=bnn, relu=True, pool=True, ceil_mode=pool)
-            return self.conv('backbone.%d' % i, x, 1, pad, dil, bn=bnn, relu=True)
+                return self.conv('backbone.%d' % i, x, 1, pad, dil, bn=bnn, relu=True, pool=True, ceil_mode=pool, to_split=to_split)
+            return self.conv('backbone.%d' % i, x, 1, pad, dil, bn=bnn, relu=True, to_split=to_split)
 
         n_cfg = len(VGG_CFG)
         ci = 0
@@ -235,11 +257,12 @@ class Engine(object):
                 nxt = VGG_CFG[ci + 1] if ci + 1 < n_cfg else None
                 # conv followed by a pool whose input nobody else needs (not conv4_3 -> L2Norm): fuse the pool
                 if x is not None and nxt in ('M', 'C') and idx + step != split43 and (nxt == 'M' or x.shape[1] % 2 == 0):
-                    x = conv_block(idx, x, pool=(nxt == 'C'))
+                    x = conv_block(idx, x, pool=(nxt == 'C'), to_split=True)
                     idx += step + 1
                     ci += 1
                 else:
-                    x = conv_block(idx, x)
+                    # conv4_3 / conv5_3 feed an L2Norm, a conv before an unfused pool feeds the pool kernel: those stay fp32
+                    x = conv_block(idx, x, to_split=isinstance(nxt, int) and idx + step not in (split43, split53))
                     idx += step
             ci += 1
         assert idx == split53
@@ -248,7 +271,7 @@ class Engine(object):
         if on_source:
             on_source(1, s1)
         idx += 1
-        x = conv_block(idx, x, 6, 6)                      # conv6: 3x3 dilation 6
+        x = conv_block(idx, x, 6, 6, to_split=True)       # conv6: 3x3 dilation 6
         idx += step
         x = conv_block(idx, x, 0, 1)                      # conv7: 1x1
         sources.append(x)
@@ -256,10 +279,10 @@ class Engine(object):
             on_source(2, x)
         if with_extras:
             if bn:
-                x = self.conv('extras.0', x, bn='extras.1', relu=True)
+                x = self.conv('extras.0', x, bn='extras.1', relu=True, to_split=True)
                 x = self.conv('extras.3', x, 2, 1, bn='extras.4', relu=True)
             else:
-                x = self.conv('extras.0', x, relu=True)
+                x = self.conv('extras.0', x, relu=True, to_split=True)
                 x = self.conv('extras.2', x, 2, 1, relu=True)
             sources.append(x)
             if on_source:
@@ -268,19 +291,17 @@ class Engine(object):
 
     # ---- TCB / FPN: dualrefinedet_vggbn.py:166-179 -------------------------------------------------
     def fpn(self, arm_sources):
-        x = self.conv('last_layer_trans.0', arm_sources[3], 1, 1, relu=True)
-        x = self.conv('last_layer_trans.2', x, 1, 1)
-        x = self.conv('last_layer_trans.3', x, 1, 1)
+        x = self.last_trans(arm_sources[3])
         odm = [x]
         return self.fpn_topdown(x, odm, [self.trans_branch(arm_sources[k], k) for k in range(3)])
 
     def last_trans(self, src3):
-        x = self.conv('last_layer_trans.0', src3, 1, 1, relu=True)
-        x = self.conv('last_layer_trans.2', x, 1, 1)
+        x = self.conv('last_layer_trans.0', src3, 1, 1, relu=True, to_split=True)
+        x = self.conv('last_layer_trans.2', x, 1, 1, to_split=True)
         return self.conv('last_layer_trans.3', x, 1, 1)
 
     def trans_branch(self, src, k):
-        t = self.conv('trans_layers.%d.0' % k, src, 1, 1, relu=True)
+        t = self.conv('trans_layers.%d.0' % k, src, 1, 1, relu=True, to_split=True)
         return self.conv('trans_layers.%d.2' % k, t, 1, 1)
 
     def fpn_topdown(self, x, odm, trans):
@@ -455,7 +476,8 @@ class Engine(object):
             # launch / tail bound on their own)
             def project(k):
                 pc, n_pad = self.projected_head_weight(loc_name, conf_name, k, multihead, x3=projected_x3)
-                return ops.deform_project(feats[k], pc, n_pad, 3, 5 if multihead else 0, num_classes, split=projected_x3)
+                return ops.deform_project(feats[k], pc, n_pad, 3, 5 if multihead else 0, num_classes, split=projected_x3,
+                                          xs=self.split_of(feats[k]) if projected_x3 else None)
 
             ys = self.parallel([(lambda k=k: project(k)) for k in range(len(feats))])
             n_pad = self.projected_head_weight(loc_name, conf_name, 0, multihead, x3=projected_x3)[1]

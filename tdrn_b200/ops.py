@@ -166,6 +166,10 @@ def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_
     else:
         Ho, Wo = conv_out(H, pc.kh, pc.stride, pc.pad, pc.dil), conv_out(W, pc.kw, pc.stride, pc.pad, pc.dil)
     Hs, Ws = (Ho // 2, Wo // 2) if pool else (Ho, Wo)        # stored map (after the fused 2x2 max-pool)
+    if out is None and split_out:
+        # the fp32 result leaves the kernel as the (hi | lo) bf16 operand of the next fp32-accurate conv: [B,Hs,Ws,2*Cout]
+        out = torch.empty(B, Hs, Ws, 2 * pc.cout, dtype=torch.bfloat16, device=x.device)
+        out_sb, out_sp = Hs * Ws * 2 * pc.cout, 2 * pc.cout
     if out is None:
         odt = out_dtype if out_dtype is not None else x.dtype
         out = torch.empty(B, Hs, Ws, pc.cout, dtype=odt, device=x.device)
@@ -446,8 +450,9 @@ def deform_head_projected(feat_nhwc, offsets, pc_proj, n_pad, num_classes, kh, p
                   'tdrn_deform_head_sample')
 
 
-def deform_project(feat_nhwc, pc_proj, n_pad, kh, kh2, num_classes, split=False):
-    """First half of deform_head_projected for a whole batch: the per-tap projections [B,H,W,taps*width] bf16."""
+def deform_project(feat_nhwc, pc_proj, n_pad, kh, kh2, num_classes, split=False, xs=None):
+    """First half of deform_head_projected for a whole batch: the per-tap projections [B,H,W,taps*width] bf16.
+    ``xs``: the (hi | lo) operand of ``feat_nhwc`` when the caller already has it (split mode)."""
     x = _cuda(feat_nhwc, 'feat')
     B, H, W, Cin = x.shape
     taps = kh * kh + kh2 * kh2
@@ -457,8 +462,8 @@ def deform_project(feat_nhwc, pc_proj, n_pad, kh, kh2, num_classes, split=False)
     tag = 'deform_head_x3' if split else 'deform_head_tc'
     label = '%s|%d @%dx%d k%d+%d project' % (tag, Cin, H, W, kh, kh2)
     if split:
-        conv2d(split_bf16(x), pc_proj, use_tc=True, out=y, split3=True, split_out=n_pad, out_sb=H * W * taps * width,
-               out_sp=taps * width, label=label, work=flops)
+        conv2d(xs if xs is not None else split_bf16(x), pc_proj, use_tc=True, out=y, split3=True, split_out=n_pad,
+               out_sb=H * W * taps * width, out_sp=taps * width, label=label, work=flops)
     else:
         conv2d(x, pc_proj, use_tc=True, out=y, label=label, work=flops)
     return y

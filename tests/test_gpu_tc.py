@@ -352,6 +352,34 @@ def test_conv_tc_split3_fp32_accuracy(b, cin, cout, k, stride, pad, dil, h, w, r
     assert rel_err(_nchw(out16).cpu().numpy(), ref.numpy()) > 2e-4
 
 
+@pytest.mark.parametrize('b,cin,cout,k,stride,pad,dil,h,w,relu,pool', [
+    (2, 64, 64, 3, 1, 1, 1, 32, 32, True, False),        # one 64-column group, double-buffered accumulator sets
+    (3, 64, 64, 3, 1, 1, 1, 32, 48, True, True),         # + fused pool: 32-row boxes
+    (2, 64, 128, 3, 1, 1, 1, 32, 32, True, False),       # two groups per tile
+    (2, 128, 128, 3, 1, 1, 1, 16, 32, True, True),
+    (1, 256, 512, 3, 1, 1, 1, 40, 40, True, False),      # ragged-tail tiles, four N tiles
+    (3, 512, 1024, 3, 1, 6, 6, 10, 10, True, False),     # conv6: several images per tile
+    (3, 256, 512, 3, 2, 1, 1, 10, 10, False, False),     # stride 2
+    (2, 256, 80, 1, 1, 0, 1, 20, 20, False, False),      # Cout % 64 != 0: register-store path of the same output format
+])
+def test_conv_tc_split3_writes_the_next_layers_operand(b, cin, cout, k, stride, pad, dil, h, w, relu, pool):
+    """split_out = Cout: the layer writes the (hi | lo) operand of the next fp32-accurate conv itself -- bit-identical to its
+    fp32 output passed through tdrn_split_bf16."""
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(cin + cout + k + h + 1)
+    x = torch.randn(b, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    pc = ops.PackedConv(wt, bias, None, stride, pad, dil, device='cuda', want_bf16=False, want_x3=True)
+    xs = ops.split_bf16(_nhwc(x).cuda())
+    want = ops.split_bf16(ops.conv2d(xs, pc, relu=relu, out_dtype=torch.float32, use_tc=True, split3=True, pool=pool))
+    for _ in range(2):
+        got = ops.conv2d(xs, pc, relu=relu, use_tc=True, split3=True, pool=pool, split_out=cout)
+        torch.cuda.synchronize()
+        assert got.dtype == torch.bfloat16 and got.shape == want.shape
+        assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+
+
 def test_conv_tc_split3_deconv_residual():
     """ConvTranspose2d k2 s2 + residual + ReLU (`relu(up(x) + t)`, dualrefinedet_vggbn.py:177) on the fp32-accurate path."""
     from tdrn_b200 import ops
