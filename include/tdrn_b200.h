@@ -31,6 +31,8 @@ extern "C" {
 
 #define TDRN_F32  0
 #define TDRN_BF16 1
+#define TDRN_BF16_SPLIT 2   /* out_dtype of tdrn_conv_first only: [.., 2*C] bf16, C high parts then C low parts (x = hi + lo to 16
+                               mantissa bits) -- the operand format of tdrn_conv2d_tc's split3 mode */
 
 typedef void *tdrn_stream_t;   /* cudaStream_t */
 
@@ -157,7 +159,9 @@ int tdrn_dwconv3x3(const void *in, const float *weight, const float *bias, void 
                    int C, int stride, int relu, int dtype, tdrn_stream_t stream);
 
 /* First conv (Cin=3) reading the reference's NCHW fp32 image directly, writing NHWC `out_dtype`.
-   weight packed [27][Cout] fp32 (tap-major, then cin). stride 1 (VGG conv1_1) or 2 (MobileNet). */
+   weight packed [27][Cout] fp32 (tap-major, then cin). stride 1 (VGG conv1_1) or 2 (MobileNet).
+   out_dtype TDRN_BF16_SPLIT (Cout = 64, stride 1, maps that tile as 64x2 / 32x4 / 16x8; TDRN_EUNSUPPORTED otherwise): the layer
+   runs on the tensor cores in split precision (x and w as hi + lo bf16 pairs, three products) and writes [B,H,W,128]. */
 int tdrn_conv_first(const float *x_nchw, const float *weight, const float *bias, void *out, int B, int H,
                     int W, int Cout, int stride, int relu, int out_dtype, tdrn_stream_t stream);
 

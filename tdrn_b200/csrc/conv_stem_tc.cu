@@ -13,6 +13,12 @@
 //   staging tile and ONE thread issues a TMA store (cp.async.bulk.tensor ... global <- shared) of the 16 KB box,
 //   so the NHWC output is written as full 128-byte lines.
 // Persistent grid (2 CTAs per SM), tile = bw x bh output pixels of one image (64x2, 32x4 or 16x8).
+//
+// SPLIT (fp32-accurate path, out_dtype TDRN_BF16_SPLIT): x = hi + lo and w = hi + lo to 16 mantissa bits each.  An A row is
+// [x_hi (k 0..31) | x_lo (k 0..31)] = K 64, B1 rows are [w_hi | w_hi], B2 rows [w_lo | -]:  A x B1 (four K = 16 steps) gives
+// x_hi*w_hi + x_lo*w_hi, the first half of A x B2 (two steps) adds x_hi*w_lo -- six accumulation steps into one accumulator
+// (nothing like the hundreds of a long-K layer, so no accumulator spreading is needed here).  The epilogue writes the
+// (hi | lo) operand of conv1_2, [B,H,W,128] bf16, as two TMA stores (channels 0..63 and 64..127).
 #include "tc_common.cuh"
 #include <stdlib.h>
 
@@ -32,7 +38,7 @@ constexpr int ST_THREADS = 320;          // warps 0-3 producers, 4 MMA, 5-8 epil
 constexpr int ST_COUT = 64;
 constexpr int ST_PSTAGES = 4;            // input-patch ring depth (hides HBM latency of the fp32 image reads)
 constexpr int ST_PATCH_BYTES = 4096;     // >= 3 ch x (bh+2) rows x (bw+8) cols x 4 B for the three tile shapes, 128B aligned
-constexpr int ST_SMEM = 2 * 16384 + 2 * 16384 + 8192 + ST_PSTAGES * ST_PATCH_BYTES + 256 + 1024;
+constexpr int ST_SMEM = 2 * 16384 + 2 * 16384 + 2 * 8192 + ST_PSTAGES * ST_PATCH_BYTES + 256 + 1024;
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
 {
@@ -41,6 +47,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
     return r;
 }
 
+// low parts of two fp32 values: bf16(v - bf16(v)), packed like pack_bf16x2
+__device__ __forceinline__ uint32_t split_lo2(float a, float b)
+{
+    const float ha = __bfloat162float(__float2bfloat16_rn(a)), hb = __bfloat162float(__float2bfloat16_rn(b));
+    return pack_bf16x2(__fsub_rn(a, ha), __fsub_rn(b, hb));
+}
+
+template <bool SPLIT>
 __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmO, const StemP p)
 {
     extern __shared__ uint8_t smem_dyn[];
@@ -50,9 +64,9 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
 
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = base;                                   // 2 x [128 rows][128 B]
-    uint8_t *sO = base + 2 * 16384;                       // 2 x [128 rows][128 B] output staging
-    uint8_t *sB = base + 4 * 16384;                       // [64 rows][128 B]
-    uint8_t *sP = base + 4 * 16384 + 8192;                // ST_PSTAGES x patch [3][bh+2][bw+8] fp32
+    uint8_t *sO = base + 2 * 16384;                       // 2 x [128 rows][128 B] output staging (SPLIT: the hi and the lo box of one tile)
+    uint8_t *sB = base + 4 * 16384;                       // [64 rows][128 B] (SPLIT: B1 = [w_hi | w_hi], then B2 = [w_lo | -])
+    uint8_t *sP = base + 4 * 16384 + 2 * 8192;            // ST_PSTAGES x patch [3][bh+2][bw+8] fp32
     float *sBias = (float *)(sP + ST_PSTAGES * ST_PATCH_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -78,6 +92,13 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
         uint4 q;
         q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
         *(uint4 *)(sB + sw128_offset(n, chunk)) = q;
+        if (SPLIT) {
+            *(uint4 *)(sB + sw128_offset(n, chunk + 4)) = q;
+            uint4 l;
+            l.x = split_lo2(v[0], v[1]); l.y = split_lo2(v[2], v[3]); l.z = split_lo2(v[4], v[5]); l.w = split_lo2(v[6], v[7]);
+            *(uint4 *)(sB + 8192 + sw128_offset(n, chunk)) = l;
+            *(uint4 *)(sB + 8192 + sw128_offset(n, chunk + 4)) = make_uint4(0, 0, 0, 0);
+        }
     }
     if (tid < ST_COUT) sBias[tid] = p.bias ? p.bias[tid] : 0.f;
     fence_proxy_async_smem();
@@ -96,7 +117,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
             mbar_wait(&p_full[ps], pph);
             mbar_wait(&a_empty[s], ((it >> 1) & 1u) ^ 1u);
             const float *P = (const float *)(sP + ps * ST_PATCH_BYTES);
-            uint32_t kw[16];
+            uint32_t kw[16], kl[16];
 #pragma unroll
             for (int k2 = 0; k2 < 16; ++k2) {
                 float v[2];
@@ -107,11 +128,15 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
                     else v[h] = 0.f;
                 }
                 kw[k2] = pack_bf16x2(v[0], v[1]);
+                if (SPLIT) kl[k2] = split_lo2(v[0], v[1]);
             }
             uint8_t *a = sA + s * 16384;
 #pragma unroll
-            for (int chunk = 0; chunk < 4; ++chunk)
+            for (int chunk = 0; chunk < 4; ++chunk) {
                 *(uint4 *)(a + sw128_offset(tid, chunk)) = make_uint4(kw[4 * chunk], kw[4 * chunk + 1], kw[4 * chunk + 2], kw[4 * chunk + 3]);
+                if (SPLIT)
+                    *(uint4 *)(a + sw128_offset(tid, chunk + 4)) = make_uint4(kl[4 * chunk], kl[4 * chunk + 1], kl[4 * chunk + 2], kl[4 * chunk + 3]);
+            }
             fence_proxy_async_smem();
             named_bar(1, 128);                                          // A tile complete, patch[ps] fully consumed
             if (tid == 0) { mbar_arrive(&a_full[s]); mbar_arrive(&p_empty[ps]); }
@@ -130,6 +155,13 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
                 const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * 16384));
                 umma_bf16(tmem_base + s * ST_COUT, adesc, bdesc, idesc, 0u);
                 umma_bf16(tmem_base + s * ST_COUT, adesc + 2, bdesc + 2, idesc, 1u);
+                if (SPLIT) {
+                    const uint64_t bdesc2 = umma_desc_sw128(smem_u32(sB + 8192));
+                    umma_bf16(tmem_base + s * ST_COUT, adesc + 4, bdesc + 4, idesc, 1u);      // x_lo * w_hi
+                    umma_bf16(tmem_base + s * ST_COUT, adesc + 6, bdesc + 6, idesc, 1u);
+                    umma_bf16(tmem_base + s * ST_COUT, adesc, bdesc2, idesc, 1u);             // x_hi * w_lo
+                    umma_bf16(tmem_base + s * ST_COUT, adesc + 2, bdesc2 + 2, idesc, 1u);
+                }
                 umma_commit(&a_empty[s]);
                 umma_commit(&t_full[s]);
             }
@@ -156,12 +188,12 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++it) {
             const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
-            if (et == 0) bulk_wait_read<1>();                            // the store that last read sO[s] has drained
+            if (et == 0) { if (SPLIT) bulk_wait_read<0>(); else bulk_wait_read<1>(); }   // the store that last read these boxes has drained
             named_bar(2, 128);
             mbar_wait(&t_full[s], ph);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + s * ST_COUT;
-            uint8_t *o = sO + s * 16384;
+            uint8_t *o = SPLIT ? sO : sO + s * 16384;
 #pragma unroll
             for (int c0 = 0; c0 < ST_COUT; c0 += 16) {
                 float v[16];
@@ -172,6 +204,12 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
                     make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
                 *(uint4 *)(o + sw128_offset(r, (c0 >> 3) + 1)) =
                     make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                if (SPLIT) {
+                    *(uint4 *)(o + 16384 + sw128_offset(r, c0 >> 3)) =
+                        make_uint4(split_lo2(v[0], v[1]), split_lo2(v[2], v[3]), split_lo2(v[4], v[5]), split_lo2(v[6], v[7]));
+                    *(uint4 *)(o + 16384 + sw128_offset(r, (c0 >> 3) + 1)) =
+                        make_uint4(split_lo2(v[8], v[9]), split_lo2(v[10], v[11]), split_lo2(v[12], v[13]), split_lo2(v[14], v[15]));
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -181,6 +219,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
             if (et == 0) {
                 const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
                 tma_store_4d(&tmO, o, 0, (rem % p.tiles_w) * p.bw, (rem / p.tiles_w) * p.bh, b);
+                if (SPLIT) tma_store_4d(&tmO, o + 16384, ST_COUT, (rem % p.tiles_w) * p.bw, (rem / p.tiles_w) * p.bh, b);
                 bulk_commit();
             }
         }
@@ -194,7 +233,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
 
 // -> TDRN_EUNSUPPORTED when the shape does not tile (caller falls back to the CUDA-core stem)
 int launch_conv_stem_tc(const float *x, const float *w, const float *bias, void *out, int B, int H, int W, int relu,
-                        cudaStream_t st)
+                        bool split, cudaStream_t st)
 {
     StemP p{};
     if (W % 64 == 0 && H % 2 == 0) { p.bw = 64; p.bh = 2; }
@@ -220,8 +259,9 @@ int launch_conv_stem_tc(const float *x, const float *w, const float *bias, void 
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (stem input) failed (CUresult %d)", (int)r); return TDRN_ECUDA; }
     }
     CUtensorMap tmO;
-    const uint64_t dims[4] = {ST_COUT, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    const uint64_t str[3] = {ST_COUT * 2, (uint64_t)W * ST_COUT * 2, (uint64_t)H * W * ST_COUT * 2};
+    const uint64_t oc = split ? 2 * ST_COUT : ST_COUT;               // channels per output pixel in memory
+    const uint64_t dims[4] = {oc, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {oc * 2, (uint64_t)W * oc * 2, (uint64_t)H * W * oc * 2};
     const uint32_t box[4] = {ST_COUT, (uint32_t)p.bw, (uint32_t)p.bh, 1};
     int rc = make_tmap_bf16(&tmO, out, 4, dims, str, box, nullptr);
     if (rc) return rc;
@@ -231,9 +271,14 @@ int launch_conv_stem_tc(const float *x, const float *w, const float *bias, void 
         TDRN_CUDA(cudaGetDevice(&dev));
         TDRN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    TDRN_CUDA(cudaFuncSetAttribute(conv_stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
     const int grid = p.total < 2 * num_sms ? p.total : 2 * num_sms;
-    conv_stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM, st>>>(tmX, tmO, p);
+    if (split) {
+        TDRN_CUDA(cudaFuncSetAttribute(conv_stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+        conv_stem_tc_kernel<true><<<grid, ST_THREADS, ST_SMEM, st>>>(tmX, tmO, p);
+    } else {
+        TDRN_CUDA(cudaFuncSetAttribute(conv_stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+        conv_stem_tc_kernel<false><<<grid, ST_THREADS, ST_SMEM, st>>>(tmX, tmO, p);
+    }
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }

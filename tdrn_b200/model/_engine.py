@@ -205,8 +205,13 @@ class Engine(object):
             xs.record_stream(cur)
         return xs
 
-    def conv_first(self, name, x_nchw, stride, bn):
+    def conv_first(self, name, x_nchw, stride, bn, to_split=False):
         pc = self.packed(name, stride, 1, 1, bn)
+        if to_split and self.use_x3 and ops.conv_first_split_ok(x_nchw, pc):
+            # fp32 path, VGG conv1_1: split-precision tensor-core stem writing conv1_2's (hi | lo) operand
+            y = ops.conv_first(x_nchw, pc, True, self.act, split=True)
+            y._tdrn_is_split = True
+            return y
         return ops.conv_first(x_nchw, pc, True, self.act)
 
     # ---- VGG trunk: vgg() model/networks.py:136-163 + extras, forward :130-153 --------------------
@@ -221,7 +226,7 @@ class Engine(object):
             # to_split: the output feeds only the next trunk conv (fp32 path: written as the (hi | lo) operand, see conv())
             bnn = 'backbone.%d' % (i + 1) if bn else None
             if x is None:
-                return self.conv_first('backbone.%d' % i, x_nchw, 1, bnn)
+                return self.conv_first('backbone.%d' % i, x_nchw, 1, bnn, to_split=to_split)
             if pool is not None:
                 return self.conv('backbone.%d' % i, x, 1, pad, dil, bn=bnn, relu=True, pool=True, ceil_mode=pool, to_split=to_split)
             return self.conv('backbone.%d' % i, x, 1, pad, dil, bn=bnn, relu=True, to_split=to_split)

@@ -195,13 +195,26 @@ def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_
     return out
 
 
-def conv_first(x_nchw, pc, relu, out_dtype):
+def conv_first_split_ok(x_nchw, pc):
+    """Can tdrn_conv_first write the (hi | lo) operand of the next fp32-accurate conv directly (TDRN_BF16_SPLIT)?"""
+    H, W = x_nchw.shape[2], x_nchw.shape[3]
+    tiles = (W % 64 == 0 and H % 2 == 0) or (W % 32 == 0 and H % 4 == 0) or (W % 16 == 0 and H % 8 == 0)
+    return pc.cout == 64 and pc.stride == 1 and tiles and x_nchw.data_ptr() % 16 == 0
+
+
+def conv_first(x_nchw, pc, relu, out_dtype, split=False):
     x = _cuda(x_nchw, 'input')
     if x.dtype != torch.float32:
         raise TypeError('network input must be float32 NCHW (reference boundary)')
     B, C, H, W = x.shape
     assert C == 3 and pc.kh == 3 and pc.pad == 1
     Ho, Wo = conv_out(H, 3, pc.stride, 1, 1), conv_out(W, 3, pc.stride, 1, 1)
+    if split:
+        out = torch.empty(B, Ho, Wo, 2 * pc.cout, dtype=torch.bfloat16, device=x.device)
+        with _Timed('conv_first_x3', 2.0 * B * Ho * Wo * 27 * pc.cout):
+            check(_lib.lib().tdrn_conv_first(ptr(x), ptr(pc.w_f32), ptr(pc.bias), ptr(out), B, H, W, pc.cout, pc.stride,
+                                             int(relu), 2, stream_handle()), 'tdrn_conv_first')
+        return out
     out = torch.empty(B, Ho, Wo, pc.cout, dtype=out_dtype, device=x.device)
     with _Timed('conv_first', 2.0 * B * Ho * Wo * 27 * pc.cout):
         check(_lib.lib().tdrn_conv_first(ptr(x), ptr(pc.w_f32), ptr(pc.bias), ptr(out), B, H, W, pc.cout, pc.stride,

@@ -282,6 +282,34 @@ def test_conv_stem_tc_vs_fp32(b, h, w, relu):
     assert rel_err(_nchw(out.float()).cpu().numpy(), ref.numpy()) < tol
 
 
+@pytest.mark.parametrize('b,h,w,relu', [(2, 16, 64, True), (3, 20, 96, True), (1, 24, 48, False), (5, 64, 128, True)])
+def test_conv_stem_split_precision(b, h, w, relu):
+    """conv1_1 on the tensor cores in split precision (out_dtype TDRN_BF16_SPLIT): fp32-accurate result, written as the
+    (hi | lo) operand of conv1_2 -- against a float64 conv, and bit-identical in format to tdrn_split_bf16 of its own value."""
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(b * 100 + h + w + 5)
+    x = torch.randn(b, 3, h, w, generator=g) * 60.0                  # mean-subtracted pixel range
+    wt = torch.randn(64, 3, 3, 3, generator=g) * 0.3
+    bias = torch.randn(64, generator=g)
+    ref = F.conv2d(x.double(), wt.double(), bias.double(), 1, 1)
+    if relu:
+        ref = F.relu(ref)
+    pc = ops.PackedConv(wt, bias, None, 1, 1, 1, device='cuda', want_bf16=False)
+    assert ops.conv_first_split_ok(x.cuda(), pc)
+    out = ops.conv_first(x.cuda(), pc, relu, torch.float32, split=True)
+    torch.cuda.synchronize()
+    assert out.shape == (b, h, w, 128) and out.dtype == torch.bfloat16
+    val = out[..., :64].float() + out[..., 64:].float()
+    assert rel_err(_nchw(val).cpu().numpy(), ref.numpy()) < 1e-5
+    # hi is the bf16 nearest to the value (re-splitting hi + lo gives hi back, except where lo rounded up to exactly half an ulp)
+    again = ops.split_bf16(val.contiguous())
+    assert float((again[..., :64].view(torch.int16) == out[..., :64].view(torch.int16)).float().mean()) > 0.999
+    assert bool(((out[..., :64].float() - val).abs() <= val.abs() * 2.0 ** -8).all())
+    # plain bf16 operands are two orders of magnitude further away
+    out16 = ops.conv_first(x.cuda(), pc, relu, torch.bfloat16)
+    assert rel_err(_nchw(out16.float()).cpu().numpy(), ref.numpy()) > 1e-3
+
+
 @pytest.mark.parametrize('b,h,w,pool', [(2, 32, 32, True), (1, 16, 16, True), (3, 64, 48, False), (2, 48, 80, True),
                                         (5, 320, 320, True)])    # 5 x 800 tiles: every CTA runs many tiles, all rings wrap
 def test_conv_stem_pair_is_bit_identical_to_the_two_kernel_path(b, h, w, pool):
