@@ -158,6 +158,20 @@ int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in_bf16, const void *wei
 int tdrn_dwconv3x3(const void *in, const float *weight, const float *bias, void *out, int B, int H, int W,
                    int C, int stride, int relu, int dtype, tdrn_stream_t stream);
 
+/* One conv_dw block of the MobileNet trunks (model/networks.py:736-745: Conv2d(inp, inp, 3, stride, 1, groups=inp) + BN + ReLU,
+   Conv2d(inp, oup, 1) + BN + ReLU; used by dualrefinedet_mobilenet.py:23-35 and ssd4scale_mobile.py) in one kernel: the
+   depthwise result is produced on the CUDA cores straight into the shared-memory operand of the pointwise tcgen05 GEMM and
+   never reaches HBM.  bf16 NHWC in [B,H,W,Cin] / out [B,Ho,Wo,Cout]; dw_weight [9][Cin] fp32 and dw_bias [Cin] (BN folded,
+   as for tdrn_dwconv3x3); pw_weight bf16 [Cout_pad16][Cin_pad64] K-major and pw_bias [Cout] (as for tdrn_conv2d_tc).
+   Bit-identical to tdrn_dwconv3x3 followed by tdrn_conv2d_tc.  Needs Cin % 8 == 0, Cout % 8 == 0, stride 1 or 2. */
+typedef struct {
+    int B, H, W, Cin, Cout;
+    int stride;                /* of the depthwise conv (pad 1) */
+    int relu_dw, relu_pw;
+} tdrn_dwpw_desc;
+int tdrn_conv_dwpw(const tdrn_dwpw_desc *d, const void *in_bf16, const float *dw_weight, const float *dw_bias,
+                   const void *pw_weight_bf16, const float *pw_bias, void *out_bf16, tdrn_stream_t stream);
+
 /* First conv (Cin=3) reading the reference's NCHW fp32 image directly, writing NHWC `out_dtype`.
    weight packed [27][Cout] fp32 (tap-major, then cin). stride 1 (VGG conv1_1) or 2 (MobileNet).
    out_dtype TDRN_BF16_SPLIT (Cout = 64, stride 1, maps that tile as 64x2 / 32x4 / 16x8; TDRN_EUNSUPPORTED otherwise): the layer

@@ -32,12 +32,16 @@ class DeformHeadDesc(ctypes.Structure):
                 ('B', 'H', 'W', 'Cin', 'num_classes', 'dg', 'kh', 'pad', 'kh2', 'pad2', 'P', 'prior_off', 'softmax', 'split')]
 
 
+class DwPwDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ('B', 'H', 'W', 'Cin', 'Cout', 'stride', 'relu_dw', 'relu_pw')]
+
+
 _lib = None
 
 EXPORTS = [
     'tdrn_last_error', 'tdrn_version', 'tdrn_launch_count', 'tdrn_prior_box', 'tdrn_deform_conv_forward',
     'tdrn_nms_workspace_bytes', 'tdrn_nms', 'tdrn_nms_host', 'tdrn_nms_rule', 'tdrn_nms_host_rule', 'tdrn_decode', 'tdrn_detect_workspace_bytes',
-    'tdrn_detect', 'tdrn_conv2d', 'tdrn_conv2d_tc', 'tdrn_dwconv3x3', 'tdrn_conv_first', 'tdrn_conv_stem_pair', 'tdrn_maxpool2x2',
+    'tdrn_detect', 'tdrn_conv2d', 'tdrn_conv2d_tc', 'tdrn_dwconv3x3', 'tdrn_conv_dwpw', 'tdrn_conv_first', 'tdrn_conv_stem_pair', 'tdrn_maxpool2x2',
     'tdrn_l2norm', 'tdrn_l2norm_pool2x2', 'tdrn_softmax', 'tdrn_nhwc_to_nchw_f32', 'tdrn_nchw_f32_to_nhwc', 'tdrn_split_bf16', 'tdrn_offset_convs', 'tdrn_deform_head', 'tdrn_deform_head_sample', 'tdrn_deform_head_sample_group', 'tdrn_collect_workspace_bytes', 'tdrn_collect_detections', 'tdrn_preprocess', 'tdrn_multiscale_vote_workspace_bytes', 'tdrn_multiscale_vote',
 ]
 

@@ -871,7 +871,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_splitk_kernel(const __grid
 
 // Pick the A box (bw, bh, bn), bw*bh*bn <= 128, maximising useful rows; bn > 1 only when one image's
 // whole map fits (the 10x10 and 5x5 pyramid levels).  Ties -> wider rows.
-static void pick_box(int B, int H, int W, int max_w, int max_h, int &bw, int &bh, int &bn)
+void pick_box(int B, int H, int W, int max_w, int max_h, int &bw, int &bh, int &bn)
 {
     double best = -1;
     bw = bh = bn = 1;

@@ -3,6 +3,8 @@
 ``build_net(phase, size, num_classes, def_groups, multihead)`` (:210-214); state-dict keys :19-121;
 forward outputs (:183-189): (arm_loc, None, odm_loc, softmax(conf)).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -20,7 +22,18 @@ DW_CFG = [(32, 64, 1), (64, 128, 2), (128, 128, 1), (128, 256, 1), (256, 256, 1)
 
 def _dw_block(E, name, x, stride):
     """conv_dw (networks.py:736-745): depthwise 3x3+BN+ReLU then pointwise 1x1+BN+ReLU."""
-    x = ops.dwconv3x3(x, E.packed_dw(name + '.0', name + '.1', stride), relu=True)
+    pd = E.packed_dw(name + '.0', name + '.1', stride)
+    if E.use_tc and x.dtype == torch.bfloat16 and stride == 1 and os.environ.get('TDRN_DWPW', '0') == '1':
+        # OPT-IN (TDRN_DWPW=1): both halves in one kernel, the depthwise output stays in shared memory (tdrn_conv_dwpw; same
+        # bits as the two kernels).  Measured on B200 (b64, scripts/dwpw_timing.py): slower than the two kernels on every layer
+        # (512 -> 512 @40x40: 0.232 ms against 0.081 + 0.073) -- the depthwise arithmetic (bf16 unpack + fp32 FMA, ~2 300 issue cycles
+        # per 64-channel block on 8 producer warps) is 4-5x the block's MMA time, so the fused CTA runs at CUDA-core speed with
+        # 10 of its 19 warps waiting, while the stand-alone depthwise kernel fills all four schedulers of every SM.  The accuracy
+        # argument for fusing does not hold either (scripts/mobilenet_bf16_emulation.py: the MMA operand is bf16 in both forms).
+        pc = E.packed(name + '.3', 1, 0, 1, name + '.4')
+        if pc.w_bf16 is not None and x.shape[3] % 8 == 0 and pc.cout % 8 == 0:
+            return ops.conv_dwpw(x, pd, pc)
+    x = ops.dwconv3x3(x, pd, relu=True)
     return E.conv(name + '.3', x, bn=name + '.4', relu=True)
 
 

@@ -265,6 +265,21 @@ def dwconv3x3(x_nhwc, pd, relu=True):
     return out
 
 
+def conv_dwpw(x_nhwc, pd, pc, relu_dw=True, relu_pw=True):
+    """One conv_dw block (depthwise 3x3 + pointwise 1x1, BN folded, ReLU after each) in one launch (tdrn_conv_dwpw):
+    bit-identical to dwconv3x3 followed by conv2d(use_tc=True), without the HBM round trip of the depthwise output."""
+    x = _cuda(x_nhwc, 'input')
+    B, H, W, C = x.shape
+    assert x.dtype == torch.bfloat16 and C == pd.c == pc.cin and pc.kh == 1 and pc.w_bf16 is not None
+    Ho, Wo = conv_out(H, 3, pd.stride, 1, 1), conv_out(W, 3, pd.stride, 1, 1)
+    out = torch.empty(B, Ho, Wo, pc.cout, dtype=torch.bfloat16, device=x.device)
+    d = _lib.DwPwDesc(B=B, H=H, W=W, Cin=C, Cout=pc.cout, stride=pd.stride, relu_dw=int(relu_dw), relu_pw=int(relu_pw))
+    with _Timed('conv_tc|dw3x3 s%d + %dx%d k1 @%dx%d' % (pd.stride, C, pc.cout, H, W), 2.0 * B * Ho * Wo * C * (pc.cout + 9)):
+        check(_lib.lib().tdrn_conv_dwpw(ctypes.byref(d), ptr(x), ptr(pd.w), ptr(pd.bias), ptr(pc.w_bf16), ptr(pc.bias), ptr(out),
+                                        stream_handle()), 'tdrn_conv_dwpw')
+    return out
+
+
 def maxpool2x2(x_nhwc, ceil_mode=False):
     x = _cuda(x_nhwc, 'input')
     B, H, W, C = x.shape
