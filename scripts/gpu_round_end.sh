@@ -10,7 +10,9 @@ bash scripts/gpu_profile_conv.sh ${tag} > /dev/null 2>&1
 python bench.py --steps 20 --warmup 5 --detail > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench_layers.txt
 python bench.py --steps 20 --warmup 5 --impl reference > gpurun_out/${tag}_bench_reference.json 2> /dev/null
 for c in coco512 mobilenet tdrn; do python bench.py --config $c --steps 20 --warmup 5 > gpurun_out/${tag}_bench_$c.json 2> /dev/null; done
-python bench.py --precision fp32 --steps 10 --warmup 3 --no-cpu --sustain 0 > gpurun_out/${tag}_bench_fp32.json 2> /dev/null
+python bench.py --precision fp32 --steps 10 --warmup 3 --no-cpu --sustain 0 --detail > gpurun_out/${tag}_bench_fp32.json 2> gpurun_out/${tag}_bench_fp32_layers.txt
+python bench.py --config mobilenet --steps 10 --warmup 3 --no-cpu --sustain 0 --detail > /dev/null 2> gpurun_out/${tag}_bench_mobilenet_layers.txt
+python scripts/dwpw_timing.py > gpurun_out/${tag}_dwpw_timing.txt 2>&1
 python scripts/bench_detect.py > gpurun_out/${tag}_bench_detect.txt 2>&1
 tail -n 4 gpurun_out/${tag}_pytest_gpu.txt; tail -n 6 gpurun_out/${tag}_smoke.txt; head -n 8 gpurun_out/${tag}_launches.txt
 python - <<PY

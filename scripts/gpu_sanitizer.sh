@@ -16,9 +16,9 @@ run() {  # $1 tool, rest: command
 run memcheck python -m pytest tests/test_gpu_tc.py tests/test_gpu_postprocess.py -m gpu -x -q
 run memcheck python scripts/sanitizer_forward.py 32
 run racecheck python -m pytest tests/test_gpu_postprocess.py -m gpu -x -q
-run racecheck python -m pytest tests/test_gpu_tc.py -m gpu -x -q -k "fused_maxpool or stride2 or split3 or deform_head"
+run racecheck python -m pytest tests/test_gpu_tc.py -m gpu -x -q -k "fused_maxpool or stride2 or split3 or deform_head or deform_sample_group or dwpw or stem_split"
 run racecheck python scripts/sanitizer_forward.py 4
 run synccheck python -m pytest tests/test_gpu_postprocess.py -m gpu -x -q
-run synccheck python -m pytest tests/test_gpu_tc.py -m gpu -x -q -k "fused_maxpool or stride2 or split3 or deform_head"
+run synccheck python -m pytest tests/test_gpu_tc.py -m gpu -x -q -k "fused_maxpool or stride2 or split3 or deform_head or deform_sample_group or dwpw or stem_split"
 run synccheck python scripts/sanitizer_forward.py 4
 cat $out
