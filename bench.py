@@ -227,14 +227,16 @@ def graph_replay_ms(fn, stream, iters=20, warmup=3):
     return e0.elapsed_time(e1) / iters
 
 
+CONV_FAMILY_SOURCES = ('conv_halo_tc.cu', 'conv_stem_pair.cu', 'conv_tc.cu', 'halo_common.cuh', 'tc_common.cuh')
+
+
 def csrc_sha():
     """Short hash of the conv kernels' sources: ties profiles/conv_traffic.json to the build it was measured on."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, 'tdrn_b200', 'csrc')
-    for f in sorted(os.listdir(d)):
-        if f.startswith(('conv_', 'tc_common', 'halo_common')):
-            h.update(open(os.path.join(d, f), 'rb').read())
+    for f in CONV_FAMILY_SOURCES:          # the kernels scripts/gpu_profile_conv.sh captures (regex conv_(tc|halo|stem_pair)) + their headers
+        h.update(open(os.path.join(d, f), 'rb').read())
     return h.hexdigest()[:12]
 
 

@@ -7,7 +7,7 @@ mkdir -p gpurun_out /tmp/prof
 tag=${1:-r01}
 B="python bench.py --steps 1 --warmup 3 --no-cpu --no-graph"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv $B > /tmp/prof/launches.log 2>&1
-python scripts/launch_summary.py gpurun_out/${tag}_launches.csv 48 > gpurun_out/${tag}_launches.txt
+python scripts/launch_summary.py gpurun_out/${tag}_launches.csv 45 > gpurun_out/${tag}_launches.txt
 run() { timeout 1500 ncu --set full --clock-control none $5 -k regex:$2 -s $3 -c $4 -o /tmp/prof/${tag}_$1 -f $B > /tmp/prof/ncu_$1.log 2>&1; tail -n 1 /tmp/prof/ncu_$1.log | cut -c1-120; python scripts/ncu_table.py /tmp/prof/${tag}_$1.ncu-rep > gpurun_out/${tag}_ncu_$1.txt; }
 TDRN_DEFORM_PATH=im2col run conv 'conv_(tc|halo|stem_pair)' 35 35 ""
 python scripts/ncu_traffic.py /tmp/prof/${tag}_conv.ncu-rep gpurun_out/${tag}_conv_traffic.json

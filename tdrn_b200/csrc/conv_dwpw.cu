@@ -4,8 +4,8 @@
 // The two-kernel path (tdrn_dwconv3x3, then tdrn_conv2d_tc) writes the depthwise output to HBM and reads it back:
 // 2 x B*Ho*Wo*Cin bf16 per block, as much as the block's own input + output.  Here the depthwise result never leaves the SM:
 //   warp 18: TMA of the input halo patch of a tile and channel block -- box (64 ch, bw + 2, bh + 2, bn) of the NHWC input, the
-//       conv zero padding is the out-of-bounds fill -- plus that block's 9 x 64 depthwise weights and 64 biases (bulk copies),
-//       3-stage ring (a first version read the input with global loads from the producer warps: 8 warps cannot keep enough
+//       conv zero padding is the out-of-bounds fill; 3-stage ring; the block's 9 x 64 depthwise weights and 64 biases are
+//       copied next to the patch by the producers themselves (a first version read the input with global loads from the producer warps: 8 warps cannot keep enough
 //       bytes in flight, it ran at 11 000 cycles per channel block instead of the ~1 100 the arithmetic needs);
 //   warps 10-17 (256 threads): depthwise 3x3 on the CUDA cores out of that patch (16-byte shared loads of 8 channels, fp32
 //       FMAs in the same order as dwconv3x3_bf16_kernel -> the same values), bias + ReLU, rounded to bf16 and written as the
@@ -17,7 +17,7 @@
 // Same operands, same accumulation order over K as the two-kernel path: the output is bit-identical to it (tested).
 //
 // MEASURED (B200, b64, scripts/dwpw_timing.py, profiles/r02y_dwpw_timing.txt): correct but SLOWER than the two kernels on every
-// MobileNet-320 layer (512 -> 512 @40x40: 0.232 ms against 0.081 + 0.073 ms), so the model keeps the two-kernel path and this one
+// MobileNet-320 layer (512 -> 512 @40x40: 0.249 ms against 0.081 + 0.074 ms), so the model keeps the two-kernel path and this one
 // is opt-in (TDRN_DWPW=1).  With the producers' arithmetic switched off the kernel takes 0.117 ms, with the epilogue off as well
 // 0.079 ms (= the pointwise GEMM's own L2 -> SM operand traffic: every 128-pixel tile re-reads the 512 KB weight matrix); the
 // depthwise arithmetic adds 0.115 ms: per 64-channel block a producer warp issues ~830 instructions (144 FFMA, ~150 unpack
@@ -75,11 +75,6 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v)
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 __device__ __forceinline__ unsigned long long dp_unpack(uint32_t a)      // two bf16 -> two fp32 (packed pair)
 {
@@ -267,12 +262,8 @@ __global__ void __launch_bounds__(DP_THREADS, 1) conv_dwpw_kernel(const __grid_c
                     const uint32_t ps = it % DP_P_STAGES, php = (it / DP_P_STAGES) & 1u;
                     mbar_wait(&p_empty[ps], php ^ 1u);
                     uint8_t *st = sP + (size_t)ps * DP_P_BYTES;
-                    const uint32_t wb = (uint32_t)min(64, p.Cin - kb * 64) * 4u;          // bytes of this block's channels per weight row
-                    mbar_expect_tx(&p_full[ps], patch_bytes + wb * (p.dw_b ? 10u : 9u));
+                    mbar_expect_tx(&p_full[ps], patch_bytes);
                     tma_load_4d(st, &tmX, &p_full[ps], kb * 64, x0 - 1, y0 - 1, b0);
-#pragma unroll
-                    for (int t = 0; t < 9; ++t) bulk_load_1d(st + DP_W_OFF + t * 256, p.dw_w + (size_t)t * p.Cin + kb * 64, wb, &p_full[ps]);
-                    if (p.dw_b) bulk_load_1d(st + DP_BIAS_OFF, p.dw_b + kb * 64, wb, &p_full[ps]);
                 }
             }
         }
@@ -298,7 +289,20 @@ __global__ void __launch_bounds__(DP_THREADS, 1) conv_dwpw_kernel(const __grid_c
                 const bool chan_ok = kb * 64 + cg * 8 < p.Cin;
                 const uint32_t st = smem_u32(sP) + ps * (uint32_t)DP_P_BYTES;
                 const uint32_t a = smem_u32(sA) + sa * (uint32_t)DP_A_BYTES;
-                mbar_wait(&p_full[ps], php);
+                {   // this block's 9 x 64 depthwise weights + 64 biases -> the stage (160 float4, one per thread; zeros beyond Cin)
+                    float4 wv = make_float4(0, 0, 0, 0);
+                    if (pt < 160) {
+                        const int row = pt >> 4, ch = kb * 64 + (pt & 15) * 4;
+                        if (ch < p.Cin) {
+                            if (row < 9) wv = __ldg((const float4 *)(p.dw_w + (size_t)row * p.Cin + ch));
+                            else if (p.dw_b) wv = __ldg((const float4 *)(p.dw_b + ch));
+                        }
+                    }
+                    mbar_wait(&p_full[ps], php);                 // the halo patch has landed (the weight load above overlaps the wait)
+                    if (pt < 160)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st + DP_W_OFF + pt * 16), "f"(wv.x), "f"(wv.y), "f"(wv.z), "f"(wv.w) : "memory");
+                    named_bar(2, 256);                           // all producers: weights visible; nobody is still in the previous block
+                }
                 float4 b0v = make_float4(0, 0, 0, 0), b1v = b0v;
                 if (chan_ok && p.dw_b) { b0v = lds128f(st + DP_BIAS_OFF + cg * 32); b1v = lds128f(st + DP_BIAS_OFF + cg * 32 + 16); }
 #pragma unroll 1

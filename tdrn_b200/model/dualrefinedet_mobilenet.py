@@ -26,7 +26,7 @@ def _dw_block(E, name, x, stride):
     if E.use_tc and x.dtype == torch.bfloat16 and stride == 1 and os.environ.get('TDRN_DWPW', '0') == '1':
         # OPT-IN (TDRN_DWPW=1): both halves in one kernel, the depthwise output stays in shared memory (tdrn_conv_dwpw; same
         # bits as the two kernels).  Measured on B200 (b64, scripts/dwpw_timing.py): slower than the two kernels on every layer
-        # (512 -> 512 @40x40: 0.232 ms against 0.081 + 0.073) -- the depthwise arithmetic (bf16 unpack + fp32 FMA, ~2 300 issue cycles
+        # (512 -> 512 @40x40: 0.249 ms against 0.081 + 0.074) -- the depthwise arithmetic (bf16 unpack + fp32 FMA, ~2 300 issue cycles
         # per 64-channel block on 8 producer warps) is 4-5x the block's MMA time, so the fused CTA runs at CUDA-core speed with
         # 10 of its 19 warps waiting, while the stand-alone depthwise kernel fills all four schedulers of every SM.  The accuracy
         # argument for fusing does not hold either (scripts/mobilenet_bf16_emulation.py: the MMA operand is bf16 in both forms).
