@@ -19,6 +19,10 @@
 // x_hi*w_hi + x_lo*w_hi, the first half of A x B2 (two steps) adds x_hi*w_lo -- six accumulation steps into one accumulator
 // (nothing like the hundreds of a long-K layer, so no accumulator spreading is needed here).  The epilogue writes the
 // (hi | lo) operand of conv1_2, [B,H,W,128] bf16, as two TMA stores (channels 0..63 and 64..127).
+//
+// S = 2, COUT = 32: the MobileNet stem (dualrefinedet_mobilenet.py:20, conv_bn(3, 32, 2)): the patch box covers
+// (bw*2 + 8) x (bh*2 + 1) input pixels, the im2col rows step two input pixels per output pixel, N = 32; the 64-byte output
+// rows are staged un-swizzled (their tensor map is SWIZZLE_NONE).  The CUDA-core stem took 0.29 ms of the 3.48 ms b64 step.
 #include "tc_common.cuh"
 #include <stdlib.h>
 
@@ -35,10 +39,10 @@ struct StemP {
 };
 
 constexpr int ST_THREADS = 320;          // warps 0-3 producers, 4 MMA, 5-8 epilogue, 9 patch TMA
-constexpr int ST_COUT = 64;
 constexpr int ST_PSTAGES = 4;            // input-patch ring depth (hides HBM latency of the fp32 image reads)
-constexpr int ST_PATCH_BYTES = 4096;     // >= 3 ch x (bh+2) rows x (bw+8) cols x 4 B for the three tile shapes, 128B aligned
-constexpr int ST_SMEM = 2 * 16384 + 2 * 16384 + 2 * 8192 + ST_PSTAGES * ST_PATCH_BYTES + 256 + 1024;
+// patch stage: >= 3 ch x ((bh-1)*S + 3) rows x (bw*S + 8) cols x 4 B for the three tile shapes (64x2, 32x4, 16x8), 128B aligned
+constexpr int st_patch_bytes(int S) { return S == 1 ? 4096 : 8192; }
+constexpr int st_smem(int S) { return 2 * 16384 + 2 * 16384 + 2 * 8192 + ST_PSTAGES * st_patch_bytes(S) + 256 + 1024; }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
 {
@@ -54,7 +58,7 @@ __device__ __forceinline__ uint32_t split_lo2(float a, float b)
     return pack_bf16x2(__fsub_rn(a, ha), __fsub_rn(b, hb));
 }
 
-template <bool SPLIT>
+template <bool SPLIT, int S, int ST_COUT>
 __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmO, const StemP p)
 {
     extern __shared__ uint8_t smem_dyn[];
@@ -66,11 +70,13 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
     uint8_t *sA = base;                                   // 2 x [128 rows][128 B]
     uint8_t *sO = base + 2 * 16384;                       // 2 x [128 rows][128 B] output staging (SPLIT: the hi and the lo box of one tile)
     uint8_t *sB = base + 4 * 16384;                       // [64 rows][128 B] (SPLIT: B1 = [w_hi | w_hi], then B2 = [w_lo | -])
-    uint8_t *sP = base + 4 * 16384 + 2 * 8192;            // ST_PSTAGES x patch [3][bh+2][bw+8] fp32
+    constexpr int ST_PATCH_BYTES = st_patch_bytes(S);
+    static_assert(!SPLIT || (S == 1 && ST_COUT == 64), "split precision: the VGG stem only");
+    uint8_t *sP = base + 4 * 16384 + 2 * 8192;            // ST_PSTAGES x patch [3][(bh-1)*S+3][bw*S+8] fp32
     float *sBias = (float *)(sP + ST_PSTAGES * ST_PATCH_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int PH = p.bh + 2, PW = p.pw;
+    const int PH = (p.bh - 1) * S + 3, PW = p.pw;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
 
     if (tid == 0) {
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int k = 2 * k2 + h;                           // compile-time after unrolling
-                    if (k < 27) { const int t = k / 3, c = k - t * 3, i = t / 3, j = t - i * 3; v[h] = P[(c * PH + hl + i) * PW + wl + j + 3]; }
+                    if (k < 27) { const int t = k / 3, c = k - t * 3, i = t / 3, j = t - i * 3; v[h] = P[(c * PH + hl * S + i) * PW + wl * S + j + 3]; }
                     else v[h] = 0.f;
                 }
                 kw[k2] = pack_bf16x2(v[0], v[1]);
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
                 const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
                 mbar_wait(&p_empty[ps], pph ^ 1u);
                 mbar_expect_tx(&p_full[ps], patch_bytes);
-                tma_load_4d(sP + ps * ST_PATCH_BYTES, &tmX, &p_full[ps], (rem % p.tiles_w) * p.bw - 4, (rem / p.tiles_w) * p.bh - 1, 0, b);
+                tma_load_4d(sP + ps * ST_PATCH_BYTES, &tmX, &p_full[ps], (rem % p.tiles_w) * p.bw * S - 4, (rem / p.tiles_w) * p.bh * S - 1, 0, b);
             }
         }
         __syncwarp();
@@ -200,9 +206,12 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
                 tmem_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { v[j] += sBias[c0 + j]; if (p.relu) v[j] = fmaxf(v[j], 0.f); }
-                *(uint4 *)(o + sw128_offset(r, c0 >> 3)) =
+                // COUT = 64: 128-byte rows, 128B swizzle; COUT = 32: 64-byte rows, no swizzle (tensor map SWIZZLE_NONE)
+                const uint32_t o0 = ST_COUT == 64 ? sw128_offset(r, c0 >> 3) : (uint32_t)(r * 64 + (c0 >> 3) * 16);
+                const uint32_t o1 = ST_COUT == 64 ? sw128_offset(r, (c0 >> 3) + 1) : o0 + 16u;
+                *(uint4 *)(o + o0) =
                     make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                *(uint4 *)(o + sw128_offset(r, (c0 >> 3) + 1)) =
+                *(uint4 *)(o + o1) =
                     make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
                 if (SPLIT) {
                     *(uint4 *)(o + 16384 + sw128_offset(r, c0 >> 3)) =
@@ -231,40 +240,65 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
     if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
+template <bool SPLIT, int S, int COUT>
+static int launch_stem(const CUtensorMap &tmX, const CUtensorMap &tmO, const StemP &p, int grid, cudaStream_t st)
+{
+    TDRN_CUDA(cudaFuncSetAttribute(conv_stem_tc_kernel<SPLIT, S, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, st_smem(S)));
+    conv_stem_tc_kernel<SPLIT, S, COUT><<<grid, ST_THREADS, st_smem(S), st>>>(tmX, tmO, p);
+    TDRN_LAUNCH_CHECK();
+    return TDRN_OK;
+}
+
+// stride 1 / Cout 64 (VGG conv1_1; split = the fp32-accurate form) or stride 2 / Cout 32 (MobileNet stem).
 // -> TDRN_EUNSUPPORTED when the shape does not tile (caller falls back to the CUDA-core stem)
 int launch_conv_stem_tc(const float *x, const float *w, const float *bias, void *out, int B, int H, int W, int relu,
-                        bool split, cudaStream_t st)
+                        bool split, int stride, int cout, cudaStream_t st)
 {
+    if (!((stride == 1 && cout == 64) || (stride == 2 && cout == 32 && !split))) return TDRN_EUNSUPPORTED;
+    const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+    if (stride == 2 && ((H | W) & 1)) return TDRN_EUNSUPPORTED;
     StemP p{};
-    if (W % 64 == 0 && H % 2 == 0) { p.bw = 64; p.bh = 2; }
-    else if (W % 32 == 0 && H % 4 == 0) { p.bw = 32; p.bh = 4; }
-    else if (W % 16 == 0 && H % 8 == 0) { p.bw = 16; p.bh = 8; }
+    if (Wo % 64 == 0 && Ho % 2 == 0) { p.bw = 64; p.bh = 2; }
+    else if (Wo % 32 == 0 && Ho % 4 == 0) { p.bw = 32; p.bh = 4; }
+    else if (Wo % 16 == 0 && Ho % 8 == 0) { p.bw = 16; p.bh = 8; }
     else return TDRN_EUNSUPPORTED;
     p.x = x; p.w = w; p.bias = bias; p.B = B; p.H = H; p.W = W; p.relu = relu;
-    p.tiles_w = W / p.bw; p.tiles_h = H / p.bh; p.total = p.tiles_w * p.tiles_h * B;
+    p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh; p.total = p.tiles_w * p.tiles_h * B;
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return TDRN_ECUDA; }
     CUtensorMap tmX;
-    {   // fp32 NCHW image: dims (W, H, 3, B); box (bw+8, bh+2, 3, 1) starting at (x0-4, y0-1): out-of-bounds = conv padding
-        EncodeTiledFn enc = get_encode_tiled();
-        if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return TDRN_ECUDA; }
+    {   // fp32 NCHW image: dims (W, H, 3, B); box (bw*S + 8, (bh-1)*S + 3, 3, 1) starting at (x0*S - 4, y0*S - 1): out-of-bounds = conv padding
         if ((W * 4) % 16 != 0 || ((uintptr_t)x & 15)) return TDRN_EUNSUPPORTED;
         const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
         const cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
-        p.pw = p.bw + 8;     // columns x0-4 .. x0+bw+3: TMA needs the innermost start coordinate 16-byte aligned (4 floats)
-        const cuuint32_t bdim[4] = {(cuuint32_t)p.pw, (cuuint32_t)(p.bh + 2), 3, 1};
+        p.pw = p.bw * stride + 8;   // columns x0*S-4 .. : TMA needs the innermost start coordinate 16-byte aligned (4 floats)
+        const int ph = (p.bh - 1) * stride + 3;
+        const cuuint32_t bdim[4] = {(cuuint32_t)p.pw, (cuuint32_t)ph, 3, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
-        if (3 * (p.bh + 2) * p.pw * 4 > ST_PATCH_BYTES) return TDRN_EUNSUPPORTED;
+        if (3 * ph * p.pw * 4 > st_patch_bytes(stride)) return TDRN_EUNSUPPORTED;
         CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(x), gdim, gstr, bdim, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (stem input) failed (CUresult %d)", (int)r); return TDRN_ECUDA; }
     }
     CUtensorMap tmO;
-    const uint64_t oc = split ? 2 * ST_COUT : ST_COUT;               // channels per output pixel in memory
-    const uint64_t dims[4] = {oc, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    const uint64_t str[3] = {oc * 2, (uint64_t)W * oc * 2, (uint64_t)H * W * oc * 2};
-    const uint32_t box[4] = {ST_COUT, (uint32_t)p.bw, (uint32_t)p.bh, 1};
-    int rc = make_tmap_bf16(&tmO, out, 4, dims, str, box, nullptr);
-    if (rc) return rc;
+    const uint64_t oc = split ? 2 * cout : cout;                     // channels per output pixel in memory
+    if (cout == 64) {
+        const uint64_t dims[4] = {oc, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+        const uint64_t str[3] = {oc * 2, (uint64_t)Wo * oc * 2, (uint64_t)Ho * Wo * oc * 2};
+        const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+        int rc = make_tmap_bf16(&tmO, out, 4, dims, str, box, nullptr);
+        if (rc) return rc;
+    } else {   // 32 channels = 64-byte rows: staged un-swizzled
+        if ((uintptr_t)out & 15) return TDRN_EUNSUPPORTED;
+        const cuuint64_t gdim[4] = {(cuuint64_t)oc, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B};
+        const cuuint64_t gstr[3] = {(cuuint64_t)oc * 2, (cuuint64_t)Wo * oc * 2, (cuuint64_t)Ho * Wo * oc * 2};
+        const cuuint32_t bdim[4] = {(cuuint32_t)cout, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (stem output) failed (CUresult %d)", (int)r); return TDRN_ECUDA; }
+    }
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
@@ -272,15 +306,9 @@ int launch_conv_stem_tc(const float *x, const float *w, const float *bias, void 
         TDRN_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const int grid = p.total < 2 * num_sms ? p.total : 2 * num_sms;
-    if (split) {
-        TDRN_CUDA(cudaFuncSetAttribute(conv_stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
-        conv_stem_tc_kernel<true><<<grid, ST_THREADS, ST_SMEM, st>>>(tmX, tmO, p);
-    } else {
-        TDRN_CUDA(cudaFuncSetAttribute(conv_stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
-        conv_stem_tc_kernel<false><<<grid, ST_THREADS, ST_SMEM, st>>>(tmX, tmO, p);
-    }
-    TDRN_LAUNCH_CHECK();
-    return TDRN_OK;
+    if (stride == 2) return launch_stem<false, 2, 32>(tmX, tmO, p, grid, st);
+    if (split) return launch_stem<true, 1, 64>(tmX, tmO, p, grid, st);
+    return launch_stem<false, 1, 64>(tmX, tmO, p, grid, st);
 }
 
 }  // namespace tc

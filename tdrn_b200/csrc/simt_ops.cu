@@ -205,7 +205,7 @@ static int launch_conv(const ConvP &p, int in_dtype, int out_dtype, cudaStream_t
 static int conv_out_dim(int in, int k, int stride, int pad, int dil) { return (in + 2 * pad - (dil * (k - 1) + 1)) / stride + 1; }
 
 namespace tc { int launch_conv_stem_tc(const float *x, const float *w, const float *bias, void *out, int B, int H, int W, int relu,
-                                       bool split, cudaStream_t st); }   // conv_stem_tc.cu
+                                       bool split, int stride, int cout, cudaStream_t st); }   // conv_stem_tc.cu
 int launch_conv_first(const float *x, const float *w, const float *bias, void *out, int B, int H, int W, int Cout,
                       int Ho, int Wo, int stride, int relu, int out_dtype, cudaStream_t st);   // conv_first.cu
 
@@ -564,10 +564,11 @@ extern "C" int tdrn_conv_first(const float *x, const float *weight, const float 
     TDRN_REQUIRE(stride == 1 || stride == 2, "tdrn_conv_first: stride must be 1 or 2");
     if (out_dtype == TDRN_BF16_SPLIT) {      // fp32-accurate path: (hi | lo) operand of conv1_2, tensor cores only
         if (Cout != 64 || stride != 1) { set_error("tdrn_conv_first: TDRN_BF16_SPLIT output needs Cout = 64, stride 1"); return TDRN_EUNSUPPORTED; }
-        return tc::launch_conv_stem_tc(x, weight, bias, out, B, H, W, relu, true, as_stream(stream));
+        return tc::launch_conv_stem_tc(x, weight, bias, out, B, H, W, relu, true, 1, 64, as_stream(stream));
     }
-    if (Cout == 64 && stride == 1 && out_dtype == TDRN_BF16 && !getenv("TDRN_STEM_SIMT")) {   // tcgen05 K=32 stem (conv_stem_tc.cu)
-        const int rc = tc::launch_conv_stem_tc(x, weight, bias, out, B, H, W, relu, false, as_stream(stream));
+    if (((Cout == 64 && stride == 1) || (Cout == 32 && stride == 2)) && out_dtype == TDRN_BF16 && !getenv("TDRN_STEM_SIMT")) {
+        // tcgen05 K = 32 stem (conv_stem_tc.cu): VGG conv1_1, MobileNet conv_bn(3, 32, 2)
+        const int rc = tc::launch_conv_stem_tc(x, weight, bias, out, B, H, W, relu, false, stride, Cout, as_stream(stream));
         if (rc != TDRN_EUNSUPPORTED) return rc;
     }
     if (Cout % 16 == 0 && Cout <= 64)            // register-tiled direct kernel (conv_first.cu)

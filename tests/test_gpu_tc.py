@@ -331,6 +331,32 @@ def test_conv_dwpw_refuses_stride_2():
         ops.conv_dwpw(torch.zeros(1, 16, 16, 64, dtype=torch.bfloat16, device='cuda'), pd, pc)
 
 
+@pytest.mark.parametrize('b,h,w,relu', [
+    (2, 32, 128, True),        # 16 x 64 output: 64x2 tiles
+    (3, 40, 192, True),        # 20 x 96 output: 32x4 tiles
+    (1, 48, 96, False),        # 24 x 48 output: 16x8 tiles, negative outputs kept
+    (4, 320, 320, True),       # the MobileNet-320 stem itself: 1 000 tiles per image batch > 2 x #SMs
+    (1, 20, 40, True),         # does not tile -> CUDA-core stem (same result contract)
+])
+def test_conv_stem_tc_stride2_mobilenet(b, h, w, relu):
+    """The MobileNet stem conv_bn(3, 32, 2) (dualrefinedet_mobilenet.py:20) on the tensor cores (csrc/conv_stem_tc.cu, S = 2,
+    COUT = 32): fp32 NCHW image in, NHWC bf16 out.  Reference: fp32 conv of the bf16-rounded image and weights."""
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(b * 100 + h + w + 2)
+    x = torch.randn(b, 3, h, w, generator=g)
+    wt = torch.randn(32, 3, 3, 3, generator=g) * 0.3
+    bias = torch.randn(32, generator=g)
+    ref = F.conv2d(_bf(x), _bf(wt), bias, 2, 1)
+    if relu:
+        ref = F.relu(ref)
+    pc = ops.PackedConv(wt, bias, None, 2, 1, 1, device='cuda', want_bf16=False)
+    out = ops.conv_first(x.cuda(), pc, relu, torch.bfloat16)
+    torch.cuda.synchronize()
+    assert out.shape == (b, h // 2, w // 2, 32) and out.dtype == torch.bfloat16
+    tiles = (w // 2) % 16 == 0 and (h // 2) % 2 == 0
+    assert rel_err(_nchw(out.float()).cpu().numpy(), ref.numpy()) < (4e-3 if tiles else 8e-3)
+
+
 @pytest.mark.parametrize('b,h,w,relu', [(2, 16, 64, True), (3, 20, 96, True), (1, 24, 48, False), (5, 64, 128, True)])
 def test_conv_stem_split_precision(b, h, w, relu):
     """conv1_1 on the tensor cores in split precision (out_dtype TDRN_BF16_SPLIT): fp32-accurate result, written as the
