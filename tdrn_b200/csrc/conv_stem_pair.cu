@@ -64,6 +64,14 @@ __device__ __forceinline__ uint32_t sp_pack(float lo, float hi)
     return r;
 }
 
+// max(x, 0) on a packed bf16 pair
+__device__ __forceinline__ uint32_t sp_relu2(uint32_t a)
+{
+    uint32_t r;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(0u));
+    return r;
+}
+
 __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                        const __grid_constant__ CUtensorMap tmW2,
                                                                        const __grid_constant__ CUtensorMap tmO, const StemPairP q)
@@ -231,24 +239,26 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
     } else if (warp < 14) {
         // ===================== im2col builders (warps 10..13, 128 threads) =====================
         const int bt = tid - 320;                          // 0..127
+        const uint32_t sP_u = smem_u32(sP), sAp_u = smem_u32(sAp);
         auto build = [&](uint32_t it, int tile) {
             const uint32_t s = it & 1u, ps = it % SP_PSTAGES;
             mbar_wait(&p_full[ps], (it / SP_PSTAGES) & 1u);
             mbar_wait(&ap_empty[s], ((it >> 1) & 1u) ^ 1u);
-            const float *P = (const float *)(sP + ps * SP_PATCH_STRIDE);
+            const uint32_t P_u = sP_u + ps * (uint32_t)SP_PATCH_STRIDE;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int row = h * 128 + bt;              // halo pixel index r * 10 + c
                 uint32_t kw[16];
                 if (row < SP_ROWS) {
                     const int hr = row / HL_PW, hc = row - hr * HL_PW;
+                    const uint32_t p0 = P_u + (uint32_t)((hr * SP_PXW + hc + 2) * 4);
 #pragma unroll
                     for (int k2 = 0; k2 < 16; ++k2) {
                         float v[2];
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int k = 2 * k2 + e;                       // compile-time after unrolling
-                            if (k < 27) { const int t = k / 3, c = k - t * 3, i = t / 3, j = t - i * 3; v[e] = P[(c * SP_PXH + hr + i) * SP_PXW + hc + j + 2]; }
+                            if (k < 27) { const int t = k / 3, c = k - t * 3, i = t / 3, j = t - i * 3; v[e] = lds_f32(p0 + (uint32_t)(((c * SP_PXH + i) * SP_PXW + j) * 4)); }
                             else v[e] = 0.f;
                         }
                         kw[k2] = sp_pack(v[0], v[1]);
@@ -257,10 +267,10 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
 #pragma unroll
                     for (int k2 = 0; k2 < 16; ++k2) kw[k2] = 0u;
                 }
-                uint8_t *a = sAp + (s * 2 + h) * 16384;
+                const uint32_t a = sAp_u + (uint32_t)((s * 2 + h) * 16384);
 #pragma unroll
                 for (int chunk = 0; chunk < 4; ++chunk)
-                    *(uint4 *)(a + sw128_offset(bt, chunk)) = make_uint4(kw[4 * chunk], kw[4 * chunk + 1], kw[4 * chunk + 2], kw[4 * chunk + 3]);
+                    sts128(a + sw128_offset(bt, chunk), kw[4 * chunk], kw[4 * chunk + 1], kw[4 * chunk + 2], kw[4 * chunk + 3]);
             }
             fence_proxy_async_smem();
             named_bar(2, 128);                             // A' complete, patch[ps] fully consumed
@@ -273,9 +283,19 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
         // ===================== mid stage (warps 14..21, 256 threads): D' -> bias/ReLU/mask -> bf16 halo tile =====================
         // r02: eight warps instead of four -- two per TMEM lane quadrant, each takes one 32-column half of its rows.  The halo
         // tile this stage produces is what the main MMAs waited for (1 230 of 4 184 cycles per tile, TDRN_HALO_TIMING).
+        // r02 (2nd pass): ncu source view -- 42 % of these warps' stall samples sat on the FADDs that consume the bias LDS.128
+        // (short scoreboard: next to the tensor core's operand streaming a shared-memory load takes hundreds of cycles) and the
+        // stage was never waiting for its input: it was the bottleneck of the kernel.  The bias of a warp's 32 columns now lives
+        // in registers, ReLU is one packed bf16x2 max after the cast (max commutes with the monotonic rounding), the halo tile
+        // is written with st.shared (the generic ST.E the compiler emitted for these pointers is gone).
         const int bt = tid - 448;                          // 0..255
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
         const int chalf = (warp - 14) >> 2;                // which 32-column half
+        const int c0 = chalf * 32;
+        const uint32_t sH_u = smem_u32(sH);
+        float bias_r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bias_r[j] = s_bias1[c0 + j];
         auto mid = [&](uint32_t it, int tile) {
             const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
             const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
@@ -284,7 +304,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
             mbar_wait(&pre_full[s], ph);
             mbar_wait(&a_empty[s], ph ^ 1u);
             tc_fence_after();
-            uint8_t *ht = sH + s * HL_A_STRIDE;
+            const uint32_t ht = sH_u + s * (uint32_t)HL_A_STRIDE;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (h * 128 + quad * 32 >= SP_ROWS) continue;              // warp-uniform: rows 192.. do not exist
@@ -292,25 +312,21 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_stem_pair_kernel(const __g
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + SP_TMEM_PRE + s * 128u + h * 64u;
                 const int hr = row / HL_PW, hc = row - hr * HL_PW;
                 const bool inside = row < SP_ROWS && (unsigned)(x0 + hc) < (unsigned)p.W && (unsigned)(y0 + hr) < (unsigned)p.H;
-                {
-                    const int c0 = chalf * 32;
-                    float v[32];
-                    tmem_ld32(taddr + (uint32_t)c0, v);      // (both halves in flight before one wait: measured r02, no change --
-                    if (row < SP_ROWS) {                     //  the mid stage is not bound by tcgen05.ld)
+                float v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+                if (row < SP_ROWS) {
 #pragma unroll
-                        for (int cq = 0; cq < 4; ++cq) {
-                            uint32_t w[4];
-                            const float4 ba = *(const float4 *)(s_bias1 + c0 + cq * 8), bb = *(const float4 *)(s_bias1 + c0 + cq * 8 + 4);
-                            const float bias8[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                    for (int cq = 0; cq < 4; ++cq) {
+                        uint32_t w[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int c = cq * 8 + 2 * j;
-                                float lo = v[c] + bias8[2 * j], hi = v[c + 1] + bias8[2 * j + 1];
-                                if (q.relu1) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-                                w[j] = inside ? sp_pack(lo, hi) : 0u;       // conv1_2's zero padding
-                            }
-                            *(uint4 *)(ht + sw128_offset(row, (c0 >> 3) + cq)) = make_uint4(w[0], w[1], w[2], w[3]);
+                        for (int j = 0; j < 4; ++j) {
+                            const int c = cq * 8 + 2 * j;
+                            w[j] = sp_pack(v[c] + bias_r[c], v[c + 1] + bias_r[c + 1]);
+                            if (q.relu1) w[j] = sp_relu2(w[j]);
                         }
+                        const uint32_t dst = ht + sw128_offset(row, (c0 >> 3) + cq);
+                        if (inside) sts128(dst, w[0], w[1], w[2], w[3]);
+                        else sts128(dst, 0u, 0u, 0u, 0u);                   // conv1_2's zero padding
                     }
                 }
             }

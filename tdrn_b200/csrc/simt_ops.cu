@@ -267,16 +267,14 @@ __global__ void __launch_bounds__(128) dwconv3x3_bf16_kernel(const uint4 *__rest
                                                              const float *__restrict__ bias, uint4 *__restrict__ out,
                                                              int B, int H, int W, int C, int Ho, int Wo, int relu)
 {
+    // grid (ceil(XS * CG / 128), Ho, B): one 32-bit division per thread (the flat 64-bit index of the first version cost three
+    // 64-bit divisions = ~200 of the kernel's ~1 000 instructions per thread, and the kernel is issue-bound: ncu r02z2)
     constexpr int XT = 4, NCOL = (XT - 1) * STRIDE + 3;
     const int CG = C >> 3, XS = (Wo + XT - 1) / XT;
-    const long long total = (long long)B * Ho * XS * CG;
-    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int cg = (int)(idx % CG);
-    long long t = idx / CG;
-    const int xs = (int)(t % XS); t /= XS;
-    const int y = (int)(t % Ho);
-    const int b = (int)(t / Ho);
+    const unsigned e = blockIdx.x * 128u + threadIdx.x;
+    if (e >= (unsigned)(XS * CG)) return;
+    const int xs = (int)(e / (unsigned)CG), cg = (int)(e - (unsigned)xs * (unsigned)CG);
+    const int y = blockIdx.y, b = blockIdx.z;
     const int x0 = xs * XT;
     unsigned long long acc[XT][4];
     {
@@ -324,8 +322,8 @@ __global__ void __launch_bounds__(128) dwconv3x3_bf16_kernel(const uint4 *__rest
         for (int q = 0; q < 4; ++q) {
             float lo, hi;
             asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[p][q]));
-            if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
             asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o[q]) : "f"(hi), "f"(lo));
+            if (relu) asm("max.bf16x2 %0, %0, %1;" : "+r"(o[q]) : "r"(0u));     // max commutes with the (monotonic) rounding
         }
         out[(((long long)b * Ho + y) * Wo + x) * CG + cg] = make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -620,8 +618,8 @@ extern "C" int tdrn_dwconv3x3(const void *in, const float *weight, const float *
     const int Ho = conv_out_dim(H, 3, stride, 1, 1), Wo = conv_out_dim(W, 3, stride, 1, 1);
     const long long total = (long long)B * Ho * Wo * C;
     if (dtype == TDRN_BF16 && C % 8 == 0 && (stride == 1 || stride == 2)) {
-        const long long threads = (long long)B * Ho * ((Wo + 3) / 4) * (C / 8);
-        const int grid = (int)((threads + 127) / 128);
+        TDRN_REQUIRE(Ho <= 65535 && B <= 65535, "tdrn_dwconv3x3: map too tall / batch too large for the grid");
+        const dim3 grid((unsigned)((((Wo + 3) / 4) * (C / 8) + 127) / 128), (unsigned)Ho, (unsigned)B);
         if (stride == 1)
             dwconv3x3_bf16_kernel<1><<<grid, 128, 0, as_stream(stream)>>>((const uint4 *)in, weight, bias, (uint4 *)out, B, H, W, C, Ho, Wo, relu);
         else

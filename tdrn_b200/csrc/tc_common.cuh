@@ -48,6 +48,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     }
 }
 
+// Explicit shared-window accesses by 32-bit address.  Pointers derived from the 1024-byte-aligned dynamic shared memory base go
+// through an integer round trip, after which the compiler no longer knows their address space and emits GENERIC LD.E / ST.E
+// (64-bit address arithmetic, longer latency); the hot per-tile loops of the stem-pair kernel use these instead.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // One thread of a CONVERGED warp (all 32 lanes must execute this): the single-thread roles -- TMA producer, tcgen05.mma
 // issuer -- are entered through it rather than through `lane == 0`.  ptxas knows that a branch on elect.sync's predicate
 // holds exactly one thread and emits every tcgen05.mma / cp.async.bulk.tensor of the branch as ONE instruction; behind a
