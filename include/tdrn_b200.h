@@ -33,6 +33,10 @@ extern "C" {
 #define TDRN_BF16 1
 #define TDRN_BF16_SPLIT 2   /* out_dtype of tdrn_conv_first only: [.., 2*C] bf16, C high parts then C low parts (x = hi + lo to 16
                                mantissa bits) -- the operand format of tdrn_conv2d_tc's split3 mode */
+#define TDRN_F16  3          /* IEEE half activations / weights (same tensor-core rate as bf16, 11 significand bits instead of 8): accepted by
+                               tdrn_conv_first (out), tdrn_dwconv3x3_io, tdrn_conv2d_tc (in_dtype: weights packed as half too; out_dtype) and
+                               tdrn_l2norm_io -- the MobileNet trunks (model/dualrefinedet_mobilenet.py:139-152), whose 27 stacked layers
+                               exceed the 2e-2 bar with bf16 storage.  Conversions to half saturate at +-65504. */
 
 typedef void *tdrn_stream_t;   /* cudaStream_t */
 
@@ -119,7 +123,7 @@ typedef struct tdrn_conv_desc {
     int deconv2x2;             /* 1: ConvTranspose2d k2 s2 (weight packed [Cin][4*Cout], n=(ij,co)) */
     int dg;                    /* >0: deformable conv with dg offset groups (offsets NHWC fp32
                                   [B,Ho,Wo,dg*2*kh*kw]); sampler = deform_conv_cuda_kernel.cu:16-51 */
-    int in_dtype, out_dtype;   /* TDRN_F32 / TDRN_BF16                                              */
+    int in_dtype, out_dtype;   /* TDRN_F32 / TDRN_BF16 (tdrn_conv2d_tc also: TDRN_F16, see above)    */
     /* output addressing (elements): out[b*out_sb + (y*Wo+x)*out_sp + co]; lets heads write straight
        into the NHWC-flattened [B,P,4] / [B,P,C] tensors the reference builds with permute+cat.    */
     long long out_sb, out_sp;
@@ -157,6 +161,9 @@ int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in_bf16, const void *wei
    weight packed [9][C] fp32. */
 int tdrn_dwconv3x3(const void *in, const float *weight, const float *bias, void *out, int B, int H, int W,
                    int C, int stride, int relu, int dtype, tdrn_stream_t stream);
+/* Same with separate input / output formats (TDRN_BF16 or TDRN_F16 each; C % 8 == 0, stride 1 or 2). */
+int tdrn_dwconv3x3_io(const void *in, const float *weight, const float *bias, void *out, int B, int H, int W,
+                      int C, int stride, int relu, int in_dtype, int out_dtype, tdrn_stream_t stream);
 
 /* One conv_dw block of the MobileNet trunks (model/networks.py:736-745: Conv2d(inp, inp, 3, stride, 1, groups=inp) + BN + ReLU,
    Conv2d(inp, oup, 1) + BN + ReLU; used by dualrefinedet_mobilenet.py:23-35 and ssd4scale_mobile.py) in one kernel: the
@@ -186,6 +193,10 @@ int tdrn_maxpool2x2(const void *in, void *out, int B, int H, int W, int C, int c
 /* L2Norm: out = weight[c] * x / (sqrt(sum_c x^2) + 1e-10), NHWC. */
 int tdrn_l2norm(const void *in, const float *weight, void *out, long long pixels, int C, int dtype,
                 tdrn_stream_t stream);
+/* Same with separate 16-bit input / output formats (TDRN_BF16 or TDRN_F16 each; C in {256, 512, 1024}, pixels % 4 == 0): the
+   L2Norm that hands a half-precision MobileNet source to the bf16 ARM heads / TCB. */
+int tdrn_l2norm_io(const void *in, const float *weight, void *out, long long pixels, int C, int in_dtype, int out_dtype,
+                   tdrn_stream_t stream);
 
 /* VGG conv1_1 (3 -> 64, reads the reference's NCHW fp32 image) and conv1_2 (64 -> 64) + optional MaxPool2d(2,2) in one
    kernel (model/networks.py:136-163, cfg entries 64, 64, 'M'; folded BN + ReLU after each conv): conv1_1's output -- the

@@ -406,20 +406,26 @@ def _conv_dw(sd, name, x, stride):
     return F.relu(_b(sd, name + '.4', _c(sd, name + '.3', x)))
 
 
+def _mobilenet_trunk(sd, x):
+    """The four ARM sources of the MobileNet trunk (dualrefinedet_mobilenet.py:139-152)."""
+    x = F.relu(_b(sd, 'backbone.0.1', _c(sd, 'backbone.0.0', x, 2, 1)))
+    arm_sources = []
+    for n, (i, o, s) in enumerate(MOBILENET_DW):
+        if n + 1 == 12:
+            arm_sources.append(l2norm(x, sd['L2Norm_4_3.weight']))
+        x = _conv_dw(sd, 'backbone.%d' % (n + 1), x, s)
+    arm_sources.append(l2norm(x, sd['L2Norm_5_3.weight']))
+    for e in range(2):
+        x = F.relu(_b(sd, 'extras.%d.1' % e, _c(sd, 'extras.%d.0' % e, x)))
+        x = _conv_dw(sd, 'extras.%d.3' % e, x, 2)
+        arm_sources.append(x)
+    return arm_sources
+
+
 def drn_mobilenet_forward(sd, x, num_classes=21, def_groups=1, multihead=False, softmax=True):
     """dualrefinedet_mobilenet.py:127-199; slot 1 of the reference output is None (:188)."""
     with torch.no_grad():
-        x = F.relu(_b(sd, 'backbone.0.1', _c(sd, 'backbone.0.0', x, 2, 1)))
-        arm_sources = []
-        for n, (i, o, s) in enumerate(MOBILENET_DW):
-            if n + 1 == 12:
-                arm_sources.append(l2norm(x, sd['L2Norm_4_3.weight']))
-            x = _conv_dw(sd, 'backbone.%d' % (n + 1), x, s)
-        arm_sources.append(l2norm(x, sd['L2Norm_5_3.weight']))
-        for e in range(2):
-            x = F.relu(_b(sd, 'extras.%d.1' % e, _c(sd, 'extras.%d.0' % e, x)))
-            x = _conv_dw(sd, 'extras.%d.3' % e, x, 2)
-            arm_sources.append(x)
+        arm_sources = _mobilenet_trunk(sd, x)
         odm_sources = _fpn(sd, arm_sources)
         return _drn_heads(sd, arm_sources, odm_sources, num_classes, def_groups, multihead, softmax)
 

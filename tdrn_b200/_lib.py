@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libtdrn_b200.so')
 
 F32, BF16 = 0, 1
+F16 = 3            # TDRN_F16: IEEE half activations / weights (MobileNet trunks)
 
 
 class TdrnError(RuntimeError):
@@ -41,8 +42,8 @@ _lib = None
 EXPORTS = [
     'tdrn_last_error', 'tdrn_version', 'tdrn_launch_count', 'tdrn_prior_box', 'tdrn_deform_conv_forward',
     'tdrn_nms_workspace_bytes', 'tdrn_nms', 'tdrn_nms_host', 'tdrn_nms_rule', 'tdrn_nms_host_rule', 'tdrn_decode', 'tdrn_detect_workspace_bytes',
-    'tdrn_detect', 'tdrn_conv2d', 'tdrn_conv2d_tc', 'tdrn_dwconv3x3', 'tdrn_conv_dwpw', 'tdrn_conv_first', 'tdrn_conv_stem_pair', 'tdrn_maxpool2x2',
-    'tdrn_l2norm', 'tdrn_l2norm_pool2x2', 'tdrn_softmax', 'tdrn_nhwc_to_nchw_f32', 'tdrn_nchw_f32_to_nhwc', 'tdrn_split_bf16', 'tdrn_offset_convs', 'tdrn_deform_head', 'tdrn_deform_head_sample', 'tdrn_deform_head_sample_group', 'tdrn_collect_workspace_bytes', 'tdrn_collect_detections', 'tdrn_preprocess', 'tdrn_multiscale_vote_workspace_bytes', 'tdrn_multiscale_vote',
+    'tdrn_detect', 'tdrn_conv2d', 'tdrn_conv2d_tc', 'tdrn_dwconv3x3', 'tdrn_dwconv3x3_io', 'tdrn_conv_dwpw', 'tdrn_conv_first', 'tdrn_conv_stem_pair', 'tdrn_maxpool2x2',
+    'tdrn_l2norm', 'tdrn_l2norm_io', 'tdrn_l2norm_pool2x2', 'tdrn_softmax', 'tdrn_nhwc_to_nchw_f32', 'tdrn_nchw_f32_to_nhwc', 'tdrn_split_bf16', 'tdrn_offset_convs', 'tdrn_deform_head', 'tdrn_deform_head_sample', 'tdrn_deform_head_sample_group', 'tdrn_collect_workspace_bytes', 'tdrn_collect_detections', 'tdrn_preprocess', 'tdrn_multiscale_vote_workspace_bytes', 'tdrn_multiscale_vote',
 ]
 
 

@@ -36,6 +36,7 @@ struct StemP {
     int B, H, W;
     int bw, bh, pw, tiles_w, tiles_h, total;   // pw = patch pitch (bw + halo, padded so that pw*4 B is TMA-legal)
     int relu;
+    int f16;               // operands (image, weights) and output as IEEE half instead of bf16 (TDRN_F16; not with SPLIT)
 };
 
 constexpr int ST_THREADS = 320;          // warps 0-3 producers, 4 MMA, 5-8 epilogue, 9 patch TMA
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
     float *sBias = (float *)(sP + ST_PSTAGES * ST_PATCH_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int f16 = SPLIT ? 0 : p.f16;
     const int PH = (p.bh - 1) * S + 3, PW = p.pw;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
 
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const int k = chunk * 8 + j; v[j] = k < 27 ? __ldg(p.w + k * ST_COUT + n) : 0.f; }
         uint4 q;
-        q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]); q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+        q.x = pack16x2(v[0], v[1], f16); q.y = pack16x2(v[2], v[3], f16); q.z = pack16x2(v[4], v[5], f16); q.w = pack16x2(v[6], v[7], f16);
         *(uint4 *)(sB + sw128_offset(n, chunk)) = q;
         if (SPLIT) {
             *(uint4 *)(sB + sw128_offset(n, chunk + 4)) = q;
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
                     if (k < 27) { const int t = k / 3, c = k - t * 3, i = t / 3, j = t - i * 3; v[h] = P[(c * PH + hl * S + i) * PW + wl * S + j + 3]; }
                     else v[h] = 0.f;
                 }
-                kw[k2] = pack_bf16x2(v[0], v[1]);
+                kw[k2] = pack16x2(v[0], v[1], f16);
                 if (SPLIT) kl[k2] = split_lo2(v[0], v[1]);
             }
             uint8_t *a = sA + s * 16384;
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
     } else if (warp == 4) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            const uint32_t idesc = umma_idesc_bf16(128, ST_COUT);
+            const uint32_t idesc = umma_idesc_16(128, ST_COUT, f16);
             const uint64_t bdesc = umma_desc_sw128(smem_u32(sB));
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x, ++it) {
@@ -210,9 +212,9 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
                 const uint32_t o0 = ST_COUT == 64 ? sw128_offset(r, c0 >> 3) : (uint32_t)(r * 64 + (c0 >> 3) * 16);
                 const uint32_t o1 = ST_COUT == 64 ? sw128_offset(r, (c0 >> 3) + 1) : o0 + 16u;
                 *(uint4 *)(o + o0) =
-                    make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                    make_uint4(pack16x2(v[0], v[1], f16), pack16x2(v[2], v[3], f16), pack16x2(v[4], v[5], f16), pack16x2(v[6], v[7], f16));
                 *(uint4 *)(o + o1) =
-                    make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                    make_uint4(pack16x2(v[8], v[9], f16), pack16x2(v[10], v[11], f16), pack16x2(v[12], v[13], f16), pack16x2(v[14], v[15], f16));
                 if (SPLIT) {
                     *(uint4 *)(o + 16384 + sw128_offset(r, c0 >> 3)) =
                         make_uint4(split_lo2(v[0], v[1]), split_lo2(v[2], v[3]), split_lo2(v[4], v[5]), split_lo2(v[6], v[7]));
@@ -252,9 +254,9 @@ static int launch_stem(const CUtensorMap &tmX, const CUtensorMap &tmO, const Ste
 // stride 1 / Cout 64 (VGG conv1_1; split = the fp32-accurate form) or stride 2 / Cout 32 (MobileNet stem).
 // -> TDRN_EUNSUPPORTED when the shape does not tile (caller falls back to the CUDA-core stem)
 int launch_conv_stem_tc(const float *x, const float *w, const float *bias, void *out, int B, int H, int W, int relu,
-                        bool split, int stride, int cout, cudaStream_t st)
+                        bool split, int stride, int cout, cudaStream_t st, bool f16)
 {
-    if (!((stride == 1 && cout == 64) || (stride == 2 && cout == 32 && !split))) return TDRN_EUNSUPPORTED;
+    if (!((stride == 1 && cout == 64) || (stride == 2 && cout == 32 && !split)) || (f16 && split)) return TDRN_EUNSUPPORTED;
     const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
     if (stride == 2 && ((H | W) & 1)) return TDRN_EUNSUPPORTED;
     StemP p{};
@@ -262,7 +264,7 @@ int launch_conv_stem_tc(const float *x, const float *w, const float *bias, void 
     else if (Wo % 32 == 0 && Ho % 4 == 0) { p.bw = 32; p.bh = 4; }
     else if (Wo % 16 == 0 && Ho % 8 == 0) { p.bw = 16; p.bh = 8; }
     else return TDRN_EUNSUPPORTED;
-    p.x = x; p.w = w; p.bias = bias; p.B = B; p.H = H; p.W = W; p.relu = relu;
+    p.x = x; p.w = w; p.bias = bias; p.B = B; p.H = H; p.W = W; p.relu = relu; p.f16 = f16 ? 1 : 0;
     p.tiles_w = Wo / p.bw; p.tiles_h = Ho / p.bh; p.total = p.tiles_w * p.tiles_h * B;
     EncodeTiledFn enc = get_encode_tiled();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return TDRN_ECUDA; }

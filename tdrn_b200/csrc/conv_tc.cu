@@ -86,6 +86,7 @@ struct TcConvP {
     const float *bias; const void *res; void *out;
     long long out_sb, out_sp; int out_w;
     int relu, deconv, out_f32, pool;
+    int f16_in, f16_out;         // TDRN_F16: operands (activations AND packed weights) / the 16-bit output are IEEE half instead of bf16
 };
 
 // split mode (fp32-accurate): ring stage = x_hi | x_lo | W_hi | W_lo boxes of one (tap, channel block); fp32 / (hi|lo) register-store epilogue
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
                 const int nt = tile / m_units;
                 const int n_eff = min(BN, n_pad16 - nt * BN);           // UMMA N (multiple of 16)
-                const uint32_t idesc = umma_idesc_bf16(128, n_eff);
+                const uint32_t idesc = umma_idesc_16(128, n_eff, p.f16_in);
                 const uint32_t buf = tcount % NBUF;
                 mbar_wait(&tmem_empty_bar[buf], ((tcount / NBUF) & 1u) ^ 1u);   // epilogue drained this buffer
                 tc_fence_after();
@@ -488,11 +489,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             }
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                uint4 w;
-                                __nv_bfloat162 *wb = (__nv_bfloat162 *)&w;
+                                uint32_t w[4];
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) wb[j] = __floats2bfloat162_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
-                                *(uint4 *)(o + sw128_offset(r, half * 4 + q)) = w;
+                                for (int j = 0; j < 4; ++j) w[j] = pack16x2(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1], p.f16_out);
+                                *(uint4 *)(o + sw128_offset(r, half * 4 + q)) = make_uint4(w[0], w[1], w[2], w[3]);
                             }
                         }
                         if (g == groups - 1 && sub == nsub - 1) {        // all tcgen05.ld of this unit are complete
@@ -627,14 +627,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         ((uint4 *)op)[0] = q[0]; ((uint4 *)op)[1] = q[1];
                         ((uint4 *)(op + p.split_g))[0] = ql[0]; ((uint4 *)(op + p.split_g))[1] = ql[1];
                     } else if (vec) {
-                        uint4 q[2];
-                        __nv_bfloat162 *qb = (__nv_bfloat162 *)q;
+                        uint32_t q[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) qb[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                        ((uint4 *)op)[0] = q[0]; ((uint4 *)op)[1] = q[1];
+                        for (int j = 0; j < 8; ++j) q[j] = pack16x2(v[2 * j], v[2 * j + 1], p.f16_out);
+                        ((uint4 *)op)[0] = make_uint4(q[0], q[1], q[2], q[3]); ((uint4 *)op)[1] = make_uint4(q[4], q[5], q[6], q[7]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) if (j < nv) op[j] = __float2bfloat16_rn(v[j]);
+                        for (int j = 0; j < 16; ++j) if (j < nv) ((uint16_t *)op)[j] = pack16(v[j], p.f16_out);
                     }
                 }
             }
@@ -978,7 +977,14 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     TDRN_REQUIRE(d && in && weight && out, "tdrn_conv2d_tc: null argument");
     // Cin that is a multiple of 8 but not of 64 (MobileNet's 32-channel stem output): the channel box still asks for 64
     // channels, TMA zero-fills the ones beyond Cin, and the packed weights carry zero rows for them (K padded per tap).
-    if (d->in_dtype != TDRN_BF16 || d->Cin % 8 != 0 || d->dg != 0 || d->in_sb != 0 ||
+    const bool f16_in = d->in_dtype == TDRN_F16, f16_out = d->out_dtype == TDRN_F16;
+    if (f16_in || f16_out) {     // half operands / output: the plain conv kernel only (what the MobileNet trunk's 1x1 convs need)
+        if (d->split3 || d->pool2x2 || d->deconv2x2 || residual || d->dg) {
+            set_error("tdrn_conv2d_tc: TDRN_F16 is not available with split3 / fused pool / deconv / residual");
+            return TDRN_EUNSUPPORTED;
+        }
+    }
+    if ((d->in_dtype != TDRN_BF16 && !f16_in) || d->Cin % 8 != 0 || d->dg != 0 || d->in_sb != 0 ||
         (!d->deconv2x2 && d->stride != 1 && d->stride != 2)) {
         set_error("tdrn_conv2d_tc: needs bf16 input, Cin %% 8 == 0, stride 1 or 2, no offsets (got dtype=%d Cin=%d stride=%d dg=%d)",
                   d->in_dtype, d->Cin, d->stride, d->dg);
@@ -990,7 +996,7 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
                  "tdrn_conv2d_tc: split_out needs split3, bf16 out, g %% 16 == 0, Cout %% g == 0, out_sp == 2*Cout, no deconv / residual");
     {   // narrow high-resolution 3x3 layers: halo tile + resident weights (conv_halo_tc.cu)
         static const bool no_halo = getenv("TDRN_NO_HALO") != nullptr;
-        if (!no_halo && !d->split3) {
+        if (!no_halo && !d->split3 && !f16_in && !f16_out) {
             const int rc = conv_halo_try(d, in, weight, bias, residual, out, as_stream(stream));
             if (rc != TDRN_EUNSUPPORTED) return rc;
         }
@@ -1010,6 +1016,7 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     p.bias = bias; p.res = residual; p.out = out;
     p.out_sb = d->out_sb; p.out_sp = d->out_sp;
     p.relu = d->relu; p.deconv = d->deconv2x2; p.out_f32 = d->out_dtype == TDRN_F32; p.pool = d->pool2x2;
+    p.f16_in = f16_in; p.f16_out = f16_out;
     TDRN_REQUIRE(!d->deconv2x2 || d->Cout % 16 == 0, "tdrn_conv2d_tc: deconv needs Cout %% 16 == 0");
     if (p.pool) {
         if (d->deconv2x2 || residual || p.W % 16 != 0 || p.H % 8 != 0) {
@@ -1076,7 +1083,7 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         // 10x10 / 16x16 maps (arm_loc.2: 0.063 -> 0.043 ms) and everything on the 5x5 / 8x8 maps (512 -> 256: 0.038 -> 0.023) -- and
         // loses where it does not (256 -> 256 @10x10 as 400 one-tile CTAs: 0.024 -> 0.056).  The rule may only look at the layer.
         int S = 1;
-        if (!no_splitk && !d->split3 && !p.pool && num_kb >= 16) {
+        if (!no_splitk && !d->split3 && !p.pool && num_kb >= 16 && !f16_in && !f16_out) {
             if (p.H * p.W <= 64) { S = 8; while (S > 1 && (num_kb / S < 8 || n_tiles64 * S > 16)) S >>= 1; }
             else if (p.H * p.W <= 256 && n_tiles64 == 1) { S = 8; while (S > 1 && num_kb / S < 8) S >>= 1; }
         }
@@ -1169,9 +1176,10 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
     }
     {   // long-K layers with enough M tiles: pair two M tiles per weight box (see the kernel's MT parameter)
         static const bool no_mt2 = getenv("TDRN_NO_MT2") != nullptr;
+        static const int mt2_min = getenv("TDRN_MT2_MIN") ? atoi(getenv("TDRN_MT2_MIN")) : 70;   // paired units per 100 SMs from which pairing pays
         const int num_kb = p.taps * (p.Cin >> 6);
         const int units2 = ((p.m_tiles + 1) / 2) * p.n_tiles;
-        p.mt2 = !no_mt2 && !d->split3 && BN == 256 && p.tma_out && !p.b_resident && !use_cluster && num_kb >= 64 && units2 * 10 >= g_num_sms * 7;   // measured: K = 2304 (36 k-blocks) loses 5 %, K = 4608 gains 5-10 %
+        p.mt2 = !no_mt2 && !d->split3 && BN == 256 && p.tma_out && !p.b_resident && !use_cluster && num_kb >= 64 && units2 * 100 >= g_num_sms * mt2_min;   // measured: K = 2304 (36 k-blocks) loses 5 %, K = 4608 gains 5-10 %
     }
     cudaStream_t st = as_stream(stream);
     if (p.splitk > 1) {

@@ -205,7 +205,7 @@ static int launch_conv(const ConvP &p, int in_dtype, int out_dtype, cudaStream_t
 static int conv_out_dim(int in, int k, int stride, int pad, int dil) { return (in + 2 * pad - (dil * (k - 1) + 1)) / stride + 1; }
 
 namespace tc { int launch_conv_stem_tc(const float *x, const float *w, const float *bias, void *out, int B, int H, int W, int relu,
-                                       bool split, int stride, int cout, cudaStream_t st); }   // conv_stem_tc.cu
+                                       bool split, int stride, int cout, cudaStream_t st, bool f16 = false); }   // conv_stem_tc.cu
 int launch_conv_first(const float *x, const float *w, const float *bias, void *out, int B, int H, int W, int Cout,
                       int Ho, int Wo, int stride, int relu, int out_dtype, cudaStream_t st);   // conv_first.cu
 
@@ -243,10 +243,16 @@ __global__ void dwconv3x3_kernel(const T *__restrict__ in, const float *__restri
 // bf16 fast path: a thread owns 8 channels (one 16-byte vector) of XT consecutive output pixels of a row, so every
 // input vector it loads feeds up to three outputs; consecutive threads take consecutive channel groups (coalesced
 // 16-byte accesses); packed fp32x2 FMAs.  HBM-bound by design (the scalar kernel above was ~30x off).
-__device__ __forceinline__ unsigned long long dw_unpack(uint32_t a)
+template <bool F16>
+__device__ __forceinline__ unsigned long long dw_unpack(uint32_t a)      // packed bf16 (or IEEE half) pair -> (lo, hi) fp32
 {
     unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a << 16), "r"(a & 0xffff0000u));
+    if (F16) {
+        asm("{\n\t.reg .b16 l, h;\n\t.reg .f32 fl, fh;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 fl, l;\n\tcvt.f32.f16 fh, h;\n\tmov.b64 %0, {fl, fh};\n\t}"
+            : "=l"(r) : "r"(a));
+    } else {
+        asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a << 16), "r"(a & 0xffff0000u));
+    }
     return r;
 }
 __device__ __forceinline__ unsigned long long dw_fma2(unsigned long long a, unsigned long long b, unsigned long long c)
@@ -262,7 +268,7 @@ __device__ __forceinline__ unsigned long long dw_pair(float lo, float hi)
     return r;
 }
 
-template <int STRIDE>
+template <int STRIDE, bool F16IN, bool F16OUT>
 __global__ void __launch_bounds__(128) dwconv3x3_bf16_kernel(const uint4 *__restrict__ in, const float *__restrict__ w,
                                                              const float *__restrict__ bias, uint4 *__restrict__ out,
                                                              int B, int H, int W, int C, int Ho, int Wo, int relu)
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(128) dwconv3x3_bf16_kernel(const uint4 *__rest
         }
 #pragma unroll
         for (int c = 0; c < NCOL; ++c) {
-            const unsigned long long u[4] = {dw_unpack(v[c].x), dw_unpack(v[c].y), dw_unpack(v[c].z), dw_unpack(v[c].w)};
+            const unsigned long long u[4] = {dw_unpack<F16IN>(v[c].x), dw_unpack<F16IN>(v[c].y), dw_unpack<F16IN>(v[c].z), dw_unpack<F16IN>(v[c].w)};
 #pragma unroll
             for (int p = 0; p < XT; ++p) {
                 const int j = c - p * STRIDE;                      // tap column of input column c for output p
@@ -322,10 +328,189 @@ __global__ void __launch_bounds__(128) dwconv3x3_bf16_kernel(const uint4 *__rest
         for (int q = 0; q < 4; ++q) {
             float lo, hi;
             asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[p][q]));
-            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o[q]) : "f"(hi), "f"(lo));
-            if (relu) asm("max.bf16x2 %0, %0, %1;" : "+r"(o[q]) : "r"(0u));     // max commutes with the (monotonic) rounding
+            if (F16OUT) {
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o[q]) : "f"(hi), "f"(lo));
+                if (relu) asm("max.f16x2 %0, %0, %1;" : "+r"(o[q]) : "r"(0u));
+            } else {
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o[q]) : "f"(hi), "f"(lo));
+                if (relu) asm("max.bf16x2 %0, %0, %1;" : "+r"(o[q]) : "r"(0u));     // max commutes with the (monotonic) rounding
+            }
         }
         out[(((long long)b * Ho + y) * Wo + x) * CG + cg] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// IEEE-half in and out (the MobileNet trunk's format, TDRN_F16): the nine taps are packed-half FMAs on the loaded vectors
+// themselves -- no unpacking, no 64-bit register pairs, half the FMA issue slots of the fp32x2 form above, which was issue-bound
+// (~1 000 instructions per thread for 32 outputs, 2.6 TB/s).  Weights and bias (fp32 in memory, as for the other kernels) are
+// rounded to half per thread; the accumulator is half: every FMA rounds to 11 significand bits.  CPU emulation of exactly this
+// arithmetic inside the whole detector: conf 1.36e-2 against 1.33e-2 with fp32 accumulation.  The result
+// is clamped to the largest finite half.
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t h2_pack(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+template <int STRIDE>
+__global__ void __launch_bounds__(128) dwconv3x3_half_kernel(const uint4 *__restrict__ in, const float *__restrict__ w,
+                                                             const float *__restrict__ bias, uint4 *__restrict__ out,
+                                                             int B, int H, int W, int C, int Ho, int Wo, int relu)
+{
+    constexpr int XT = 4, NCOL = (XT - 1) * STRIDE + 3;
+    const int CG = C >> 3, XS = (Wo + XT - 1) / XT;
+    const unsigned e = blockIdx.x * 128u + threadIdx.x;
+    if (e >= (unsigned)(XS * CG)) return;
+    const int xs = (int)(e / (unsigned)CG), cg = (int)(e - (unsigned)xs * (unsigned)CG);
+    const int y = blockIdx.y, b = blockIdx.z;
+    const int x0 = xs * XT;
+    uint32_t acc[XT][4];
+    {
+        const float4 b0 = bias ? __ldg((const float4 *)(bias + cg * 8)) : make_float4(0, 0, 0, 0);
+        const float4 b1 = bias ? __ldg((const float4 *)(bias + cg * 8 + 4)) : make_float4(0, 0, 0, 0);
+        const uint32_t bh[4] = {h2_pack(b0.x, b0.y), h2_pack(b0.z, b0.w), h2_pack(b1.x, b1.y), h2_pack(b1.z, b1.w)};
+#pragma unroll
+        for (int p = 0; p < XT; ++p)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[p][q] = bh[q];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int yy = y * STRIDE - 1 + i;
+        if (yy < 0 || yy >= H) continue;
+        uint32_t wt[3][4];                                        // this kernel row's 3 taps x 8 channels, packed half
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float4 w0 = __ldg((const float4 *)(w + (i * 3 + j) * C + cg * 8)), w1 = __ldg((const float4 *)(w + (i * 3 + j) * C + cg * 8 + 4));
+            wt[j][0] = h2_pack(w0.x, w0.y); wt[j][1] = h2_pack(w0.z, w0.w); wt[j][2] = h2_pack(w1.x, w1.y); wt[j][3] = h2_pack(w1.z, w1.w);
+        }
+        const uint4 *row = in + (((long long)b * H + yy) * W) * CG + cg;
+        uint4 v[NCOL];
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c) {
+            const int xx = x0 * STRIDE - 1 + c;
+            v[c] = (xx >= 0 && xx < W) ? __ldg(row + (long long)xx * CG) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c) {
+            const uint32_t u[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+            for (int p = 0; p < XT; ++p) {
+                const int j = c - p * STRIDE;                      // tap column of input column c for output p
+                if (j < 0 || j > 2) continue;                      // compile-time after unrolling
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[p][q] = h2_fma(wt[j][q], u[q], acc[p][q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < XT; ++p) {
+        const int x = x0 + p;
+        if (x >= Wo) break;
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            o[q] = acc[p][q];
+            if (relu) asm("max.f16x2 %0, %0, %1;" : "+r"(o[q]) : "r"(0u));
+            else asm("max.f16x2 %0, %0, %1;" : "+r"(o[q]) : "r"(0xfbfffbffu));       // -Inf -> -65504
+            asm("min.f16x2 %0, %0, %1;" : "+r"(o[q]) : "r"(0x7bff7bffu));               // +Inf -> 65504
+        }
+        out[(((long long)b * Ho + y) * Wo + x) * CG + cg] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// Stride-1 form for large batches: a thread walks YT consecutive output rows of its 4-pixel x 8-channel strip and keeps the
+// three input rows it needs in registers, so every input vector is loaded ONCE per thread (not once per output row), the
+// weights are converted once per thread, and the next input row is requested a whole output row ahead.  Four row buffers
+// rotate by name through a 4x unrolled loop (no register moves).
+template <int YT>
+__global__ void __launch_bounds__(128, 3) dwconv3x3_half_roll_kernel(const uint4 *__restrict__ in, const float *__restrict__ w,
+                                                                     const float *__restrict__ bias, uint4 *__restrict__ out,
+                                                                     int B, int H, int W, int C, int relu)
+{
+    constexpr int XT = 4, NCOL = XT + 2;
+    const int CG = C >> 3, XS = (W + XT - 1) / XT;                  // stride 1, pad 1: Ho = H, Wo = W
+    const unsigned e = blockIdx.x * 128u + threadIdx.x;
+    if (e >= (unsigned)(XS * CG)) return;
+    const int xs = (int)(e / (unsigned)CG), cg = (int)(e - (unsigned)xs * (unsigned)CG);
+    const int y_begin = blockIdx.y * YT, y_end = min(H, y_begin + YT), b = blockIdx.z;
+    const int x0 = xs * XT;
+    uint32_t wt[9][4], bh[4];
+    {
+        const float4 b0 = bias ? __ldg((const float4 *)(bias + cg * 8)) : make_float4(0, 0, 0, 0);
+        const float4 b1 = bias ? __ldg((const float4 *)(bias + cg * 8 + 4)) : make_float4(0, 0, 0, 0);
+        bh[0] = h2_pack(b0.x, b0.y); bh[1] = h2_pack(b0.z, b0.w); bh[2] = h2_pack(b1.x, b1.y); bh[3] = h2_pack(b1.z, b1.w);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float4 w0 = __ldg((const float4 *)(w + t * C + cg * 8)), w1 = __ldg((const float4 *)(w + t * C + cg * 8 + 4));
+            wt[t][0] = h2_pack(w0.x, w0.y); wt[t][1] = h2_pack(w0.z, w0.w); wt[t][2] = h2_pack(w1.x, w1.y); wt[t][3] = h2_pack(w1.z, w1.w);
+        }
+    }
+    bool cv[NCOL];                                                  // column inside the map?
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c) cv[c] = (unsigned)(x0 - 1 + c) < (unsigned)W;
+    const uint4 *col0 = in + ((long long)b * H * W + (x0 - 1)) * CG + cg;      // (image b, row 0, column x0 - 1)
+    const long long rstride = (long long)W * CG;
+    struct Row { uint4 v[NCOL]; };
+    auto load_row = [&](Row &r, int yy) {
+        const bool rv = (unsigned)yy < (unsigned)H;
+        const uint4 *row = col0 + (long long)yy * rstride;
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c) r.v[c] = (rv && cv[c]) ? __ldg(row + c * CG) : make_uint4(0, 0, 0, 0);
+    };
+    auto emit = [&](const Row &ra, const Row &rb, const Row &rc, int y) {      // output row y from input rows y-1, y, y+1
+        uint32_t acc[XT][4];
+#pragma unroll
+        for (int p = 0; p < XT; ++p)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[p][q] = bh[q];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const Row &r = i == 0 ? ra : (i == 1 ? rb : rc);
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c) {
+                const uint32_t u[4] = {r.v[c].x, r.v[c].y, r.v[c].z, r.v[c].w};
+#pragma unroll
+                for (int p = 0; p < XT; ++p) {
+                    const int j = c - p;
+                    if (j < 0 || j > 2) continue;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[p][q] = h2_fma(wt[i * 3 + j][q], u[q], acc[p][q]);
+                }
+            }
+        }
+        uint4 *orow = out + (((long long)b * H + y) * W + x0) * CG + cg;
+#pragma unroll
+        for (int p = 0; p < XT; ++p) {
+            if (x0 + p >= W) break;
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                o[q] = acc[p][q];
+                if (relu) asm("max.f16x2 %0, %0, %1;" : "+r"(o[q]) : "r"(0u));
+                else asm("max.f16x2 %0, %0, %1;" : "+r"(o[q]) : "r"(0xfbfffbffu));
+                asm("min.f16x2 %0, %0, %1;" : "+r"(o[q]) : "r"(0x7bff7bffu));
+            }
+            orow[p * CG] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    };
+    Row r0, r1, r2, r3;
+    load_row(r0, y_begin - 1); load_row(r1, y_begin); load_row(r2, y_begin + 1);
+    for (int y = y_begin; y < y_end; y += 4) {
+        load_row(r3, y + 2); emit(r0, r1, r2, y);
+        if (y + 1 >= y_end) break;
+        load_row(r0, y + 3); emit(r1, r2, r3, y + 1);
+        if (y + 2 >= y_end) break;
+        load_row(r1, y + 4); emit(r2, r3, r0, y + 2);
+        if (y + 3 >= y_end) break;
+        load_row(r2, y + 5); emit(r3, r0, r1, y + 3);
     }
 }
 
@@ -379,10 +564,19 @@ __global__ void l2norm_kernel(const T *__restrict__ in, const float *__restrict_
 // {L2Norm_5_3, pool5}; model/dualrefinedet_vggbn.py:130-148): x is read ONCE, both consumers' inputs are written.
 // bf16 NHWC, one warp per 2x2 window, 16-byte vector accesses (lane l owns channels v*256 + 8l .. +7).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void l2_unpack(uint32_t a, int f16, float &lo, float &hi)     // packed bf16 / IEEE half pair -> fp32
+{
+    if (f16) {
+        asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(a));
+    } else {
+        lo = __uint_as_float(a << 16); hi = __uint_as_float(a & 0xffff0000u);
+    }
+}
+
 template <int CV>
 __global__ void __launch_bounds__(256, 4) l2norm_pool_kernel(const uint4 *__restrict__ in, const float *__restrict__ weight,
                                                              uint4 *__restrict__ out_norm, uint4 *__restrict__ out_pool,
-                                                             int B, int H, int W)
+                                                             int B, int H, int W, int f16in = 0, int f16out = 0)
 {
     const int lane = threadIdx.x & 31;
     const int Ho = H >> 1, Wo = W >> 1;
@@ -406,7 +600,8 @@ __global__ void __launch_bounds__(256, 4) l2norm_pool_kernel(const uint4 *__rest
             const uint32_t w4[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float lo = __uint_as_float(w4[j] << 16), hi = __uint_as_float(w4[j] & 0xffff0000u);
+                float lo, hi;
+                l2_unpack(w4[j], f16in, lo, hi);
                 s = fmaf(lo, lo, s); s = fmaf(hi, hi, s);
             }
             if (q == 0) mx[v] = xv;
@@ -443,9 +638,11 @@ __global__ void __launch_bounds__(256, 4) l2norm_pool_kernel(const uint4 *__rest
             uint32_t o4[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float lo = __uint_as_float(w4[j] << 16), hi = __uint_as_float(w4[j] & 0xffff0000u);
-                const __nv_bfloat162 r = __floats2bfloat162_rn(wv[2 * j] * (lo * inv), wv[2 * j + 1] * (hi * inv));   // :19-20
-                o4[j] = *(const uint32_t *)&r;
+                float lo, hi;
+                l2_unpack(w4[j], f16in, lo, hi);
+                const float rl = wv[2 * j] * (lo * inv), rh = wv[2 * j + 1] * (hi * inv);                               // :19-20
+                if (f16out) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o4[j]) : "f"(rh), "f"(rl));
+                else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o4[j]) : "f"(rh), "f"(rl));
             }
             out_norm[e] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
         }
@@ -564,11 +761,12 @@ extern "C" int tdrn_conv_first(const float *x, const float *weight, const float 
         if (Cout != 64 || stride != 1) { set_error("tdrn_conv_first: TDRN_BF16_SPLIT output needs Cout = 64, stride 1"); return TDRN_EUNSUPPORTED; }
         return tc::launch_conv_stem_tc(x, weight, bias, out, B, H, W, relu, true, 1, 64, as_stream(stream));
     }
-    if (((Cout == 64 && stride == 1) || (Cout == 32 && stride == 2)) && out_dtype == TDRN_BF16 && !getenv("TDRN_STEM_SIMT")) {
-        // tcgen05 K = 32 stem (conv_stem_tc.cu): VGG conv1_1, MobileNet conv_bn(3, 32, 2)
-        const int rc = tc::launch_conv_stem_tc(x, weight, bias, out, B, H, W, relu, false, stride, Cout, as_stream(stream));
+    if (((Cout == 64 && stride == 1) || (Cout == 32 && stride == 2)) && (out_dtype == TDRN_BF16 || out_dtype == TDRN_F16) && !getenv("TDRN_STEM_SIMT")) {
+        // tcgen05 K = 32 stem (conv_stem_tc.cu): VGG conv1_1, MobileNet conv_bn(3, 32, 2); TDRN_F16: half operands and output
+        const int rc = tc::launch_conv_stem_tc(x, weight, bias, out, B, H, W, relu, false, stride, Cout, as_stream(stream), out_dtype == TDRN_F16);
         if (rc != TDRN_EUNSUPPORTED) return rc;
     }
+    if (out_dtype == TDRN_F16) { set_error("tdrn_conv_first: half output needs a map the tensor-core stem tiles"); return TDRN_EUNSUPPORTED; }
     if (Cout % 16 == 0 && Cout <= 64)            // register-tiled direct kernel (conv_first.cu)
         return launch_conv_first(x, weight, bias, out, B, H, W, Cout, conv_out_dim(H, 3, stride, 1, 1),
                                  conv_out_dim(W, 3, stride, 1, 1), stride, relu, out_dtype, as_stream(stream));
@@ -611,28 +809,60 @@ extern "C" int tdrn_deform_conv_forward(const float *input, const float *weight,
     return launch_conv(p, TDRN_F32, TDRN_F32, as_stream(stream));
 }
 
-extern "C" int tdrn_dwconv3x3(const void *in, const float *weight, const float *bias, void *out, int B, int H, int W,
-                              int C, int stride, int relu, int dtype, tdrn_stream_t stream)
+template <int STRIDE>
+static void launch_dw16(const void *in, const float *weight, const float *bias, void *out, int B, int H, int W, int C, int Ho, int Wo,
+                        int relu, bool f16in, bool f16out, cudaStream_t st)
+{
+    const dim3 grid((unsigned)((((Wo + 3) / 4) * (C / 8) + 127) / 128), (unsigned)Ho, (unsigned)B);
+#define TDRN_DW(FI, FO) dwconv3x3_bf16_kernel<STRIDE, FI, FO><<<grid, 128, 0, st>>>((const uint4 *)in, weight, bias, (uint4 *)out, B, H, W, C, Ho, Wo, relu)
+    static const bool f32acc = getenv("TDRN_DW_F32ACC") != nullptr;    // half in/out with fp32 accumulation (the form the packed-half kernel replaced)
+    if (f16in && f16out && !f32acc) {
+        static const bool no_roll = getenv("TDRN_DW_NOROLL") != nullptr;
+        constexpr int YT = 8;
+        const long long roll_blocks = (long long)grid.x * ((Ho + YT - 1) / YT) * B;
+        if (STRIDE == 1 && !no_roll && roll_blocks >= 1024) {          // enough CTAs to fill the GPU several times over: row-walking form
+            const dim3 g2(grid.x, (unsigned)((Ho + YT - 1) / YT), (unsigned)B);
+            dwconv3x3_half_roll_kernel<YT><<<g2, 128, 0, st>>>((const uint4 *)in, weight, bias, (uint4 *)out, B, H, W, C, relu);
+            return;
+        }
+        dwconv3x3_half_kernel<STRIDE><<<grid, 128, 0, st>>>((const uint4 *)in, weight, bias, (uint4 *)out, B, H, W, C, Ho, Wo, relu);
+        return;
+    }
+    if (f16in) { if (f16out) TDRN_DW(true, true); else TDRN_DW(true, false); }
+    else { if (f16out) TDRN_DW(false, true); else TDRN_DW(false, false); }
+#undef TDRN_DW
+}
+
+extern "C" int tdrn_dwconv3x3_io(const void *in, const float *weight, const float *bias, void *out, int B, int H, int W,
+                                 int C, int stride, int relu, int in_dtype, int out_dtype, tdrn_stream_t stream)
 {
     TDRN_REQUIRE(in && weight && out && B > 0 && H > 0 && W > 0 && C > 0, "tdrn_dwconv3x3: bad argument");
     const int Ho = conv_out_dim(H, 3, stride, 1, 1), Wo = conv_out_dim(W, 3, stride, 1, 1);
     const long long total = (long long)B * Ho * Wo * C;
-    if (dtype == TDRN_BF16 && C % 8 == 0 && (stride == 1 || stride == 2)) {
+    const bool in16 = in_dtype == TDRN_BF16 || in_dtype == TDRN_F16, out16 = out_dtype == TDRN_BF16 || out_dtype == TDRN_F16;
+    if (in16 && out16 && C % 8 == 0 && (stride == 1 || stride == 2)) {
         TDRN_REQUIRE(Ho <= 65535 && B <= 65535, "tdrn_dwconv3x3: map too tall / batch too large for the grid");
-        const dim3 grid((unsigned)((((Wo + 3) / 4) * (C / 8) + 127) / 128), (unsigned)Ho, (unsigned)B);
-        if (stride == 1)
-            dwconv3x3_bf16_kernel<1><<<grid, 128, 0, as_stream(stream)>>>((const uint4 *)in, weight, bias, (uint4 *)out, B, H, W, C, Ho, Wo, relu);
-        else
-            dwconv3x3_bf16_kernel<2><<<grid, 128, 0, as_stream(stream)>>>((const uint4 *)in, weight, bias, (uint4 *)out, B, H, W, C, Ho, Wo, relu);
+        if (stride == 1) launch_dw16<1>(in, weight, bias, out, B, H, W, C, Ho, Wo, relu, in_dtype == TDRN_F16, out_dtype == TDRN_F16, as_stream(stream));
+        else launch_dw16<2>(in, weight, bias, out, B, H, W, C, Ho, Wo, relu, in_dtype == TDRN_F16, out_dtype == TDRN_F16, as_stream(stream));
         TDRN_LAUNCH_CHECK();
         return TDRN_OK;
     }
-    if (dtype == TDRN_F32)
+    if (in_dtype != out_dtype || in_dtype == TDRN_F16) {
+        set_error("tdrn_dwconv3x3: half / mixed formats need C %% 8 == 0 and stride 1 or 2 (got C=%d stride=%d in=%d out=%d)", C, stride, in_dtype, out_dtype);
+        return TDRN_EUNSUPPORTED;
+    }
+    if (in_dtype == TDRN_F32)
         dwconv3x3_kernel<float><<<grid_1d(total, 256), 256, 0, as_stream(stream)>>>((const float *)in, weight, bias, (float *)out, B, H, W, C, Ho, Wo, stride, relu);
     else
         dwconv3x3_kernel<__nv_bfloat16><<<grid_1d(total, 256), 256, 0, as_stream(stream)>>>((const __nv_bfloat16 *)in, weight, bias, (__nv_bfloat16 *)out, B, H, W, C, Ho, Wo, stride, relu);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
+}
+
+extern "C" int tdrn_dwconv3x3(const void *in, const float *weight, const float *bias, void *out, int B, int H, int W,
+                              int C, int stride, int relu, int dtype, tdrn_stream_t stream)
+{
+    return tdrn_dwconv3x3_io(in, weight, bias, out, B, H, W, C, stride, relu, dtype, dtype, stream);
 }
 
 extern "C" int tdrn_maxpool2x2(const void *in, void *out, int B, int H, int W, int C, int ceil_mode, int dtype, tdrn_stream_t stream)
@@ -648,27 +878,40 @@ extern "C" int tdrn_maxpool2x2(const void *in, void *out, int B, int H, int W, i
     return TDRN_OK;
 }
 
-extern "C" int tdrn_l2norm(const void *in, const float *weight, void *out, long long pixels, int C, int dtype, tdrn_stream_t stream)
+extern "C" int tdrn_l2norm_io(const void *in, const float *weight, void *out, long long pixels, int C, int in_dtype, int out_dtype,
+                              tdrn_stream_t stream)
 {
     TDRN_REQUIRE(in && weight && out && pixels > 0 && C > 0, "tdrn_l2norm: bad argument");
-    if (dtype == TDRN_BF16 && (C == 256 || C == 512 || C == 1024) && pixels % 4 == 0 && pixels / 2 < (1LL << 30)) {
+    const bool in16 = in_dtype == TDRN_BF16 || in_dtype == TDRN_F16, out16 = out_dtype == TDRN_BF16 || out_dtype == TDRN_F16;
+    if (in16 && out16 && (C == 256 || C == 512 || C == 1024) && pixels % 4 == 0 && pixels / 2 < (1LL << 30)) {
         // vectorised path: the fused L2Norm+pool kernel without its pool output, 4 consecutive pixels per warp
         const int Wv = (int)(pixels / 2);
         const int g = (int)((pixels / 4 * 32 + 255) / 256);
+        const int fi = in_dtype == TDRN_F16, fo = out_dtype == TDRN_F16;
         cudaStream_t st = as_stream(stream);
-        if (C == 256) l2norm_pool_kernel<1><<<g, 256, 0, st>>>((const uint4 *)in, weight, (uint4 *)out, nullptr, 1, 2, Wv);
-        else if (C == 512) l2norm_pool_kernel<2><<<g, 256, 0, st>>>((const uint4 *)in, weight, (uint4 *)out, nullptr, 1, 2, Wv);
-        else l2norm_pool_kernel<4><<<g, 256, 0, st>>>((const uint4 *)in, weight, (uint4 *)out, nullptr, 1, 2, Wv);
+        if (C == 256) l2norm_pool_kernel<1><<<g, 256, 0, st>>>((const uint4 *)in, weight, (uint4 *)out, nullptr, 1, 2, Wv, fi, fo);
+        else if (C == 512) l2norm_pool_kernel<2><<<g, 256, 0, st>>>((const uint4 *)in, weight, (uint4 *)out, nullptr, 1, 2, Wv, fi, fo);
+        else l2norm_pool_kernel<4><<<g, 256, 0, st>>>((const uint4 *)in, weight, (uint4 *)out, nullptr, 1, 2, Wv, fi, fo);
         TDRN_LAUNCH_CHECK();
         return TDRN_OK;
     }
+    if (in_dtype != out_dtype || in_dtype == TDRN_F16) {
+        set_error("tdrn_l2norm: half / mixed formats need C in {256, 512, 1024} and pixels %% 4 == 0 (got C=%d pixels=%lld in=%d out=%d)",
+                  C, pixels, in_dtype, out_dtype);
+        return TDRN_EUNSUPPORTED;
+    }
     const int grid = grid_1d(pixels * 32, 256);
-    if (dtype == TDRN_F32)
+    if (in_dtype == TDRN_F32)
         l2norm_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float *)in, weight, (float *)out, pixels, C);
     else
         l2norm_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16 *)in, weight, (__nv_bfloat16 *)out, pixels, C);
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
+}
+
+extern "C" int tdrn_l2norm(const void *in, const float *weight, void *out, long long pixels, int C, int dtype, tdrn_stream_t stream)
+{
+    return tdrn_l2norm_io(in, weight, out, pixels, C, dtype, dtype, stream);
 }
 
 extern "C" int tdrn_l2norm_pool2x2(const void *in, const float *weight, void *out_norm, void *out_pool, int B, int H, int W,

@@ -253,6 +253,32 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N)
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 instruction descriptor with IEEE half (f16 = 1: format code 0) or bf16 (format code 1) operands.  The MobileNet trunk
+// runs on half operands (TDRN_F16: 11 significand bits against bf16's 8 at the same tensor-core rate; its 27 stacked layers land at
+// 3e-2 on the detector outputs with bf16 storage).
+__host__ __device__ __forceinline__ uint32_t umma_idesc_16(int M, int N, int f16)
+{
+    return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// two fp32 -> packed 16-bit pair (lo in the low half); half conversions saturate to the largest finite value
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int f16)
+{
+    uint32_t r;
+    if (f16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint16_t pack16(float v, int f16) { return (uint16_t)(pack16x2(v, 0.f, f16) & 0xffffu); }
+// packed 16-bit pair -> two fp32
+__device__ __forceinline__ void unpack16x2(uint32_t a, int f16, float &lo, float &hi)
+{
+    if (f16) {
+        asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(a));
+    } else {
+        lo = __uint_as_float(a << 16); hi = __uint_as_float(a & 0xffff0000u);
+    }
+}
+
 // Byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a [rows][128B] SWIZZLE_128B tile.
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk)
 {

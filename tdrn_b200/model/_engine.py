@@ -63,6 +63,10 @@ class Engine(object):
         self._side = []
         self._rr = 0
         self.early_fork = os.environ.get('TDRN_EARLY_FORK', '0') != '0'   # measured: forking under conv5_x steals SMs from the critical path
+        # MobileNet trunks in the 16-bit mode: IEEE half instead of bf16 for the trunk's activations and weights (same tensor-core
+        # rate, 11 significand bits instead of 8).  With bf16 storage the 27 stacked layers land at ~3e-2 on the detector outputs,
+        # above the 2e-2 bar; the sources leave the trunk as bf16 for the ARM heads / TCB / deformable heads.
+        self.half_trunk = self.use_tc and os.environ.get('TDRN_MOBILE_BF16', '0') != '1'
 
     # ---- weight packing -------------------------------------------------------------------------
     def _bn(self, name):
@@ -152,7 +156,7 @@ class Engine(object):
     # ---- operators ------------------------------------------------------------------------------
     def conv(self, name, x, stride=1, pad=0, dil=1, bn=None, relu=False, deconv=False, **kw):
         pc = self.packed(name, stride, pad, dil, bn, deconv)
-        use_tc = (self.use_tc and pc.w_bf16 is not None and x.dtype == torch.bfloat16
+        use_tc = (self.use_tc and pc.w_bf16 is not None and x.dtype in (torch.bfloat16, torch.float16)
                   and not kw.get('dg') and kw.get('in_shape') is None and (stride in (1, 2) or deconv))
         ceil_mode = kw.pop('ceil_mode', False)
         to_split = kw.pop('to_split', False)
@@ -205,8 +209,10 @@ class Engine(object):
             xs.record_stream(cur)
         return xs
 
-    def conv_first(self, name, x_nchw, stride, bn, to_split=False):
+    def conv_first(self, name, x_nchw, stride, bn, to_split=False, out_dtype=None):
         pc = self.packed(name, stride, 1, 1, bn)
+        if out_dtype is not None:
+            return ops.conv_first(x_nchw, pc, True, out_dtype)
         if to_split and self.use_x3 and ops.conv_first_split_ok(x_nchw, pc):
             # fp32 path, VGG conv1_1: split-precision tensor-core stem writing conv1_2's (hi | lo) operand
             y = ops.conv_first(x_nchw, pc, True, self.act, split=True)

@@ -20,8 +20,9 @@ DW_CFG = [(32, 64, 1), (64, 128, 2), (128, 128, 1), (128, 256, 1), (256, 256, 1)
           (512, 1024, 2), (1024, 1024, 1)]
 
 
-def _dw_block(E, name, x, stride):
-    """conv_dw (networks.py:736-745): depthwise 3x3+BN+ReLU then pointwise 1x1+BN+ReLU."""
+def _dw_block(E, name, x, stride, out_dtype=None):
+    """conv_dw (networks.py:736-745): depthwise 3x3+BN+ReLU then pointwise 1x1+BN+ReLU.  ``out_dtype``: format of the block's
+    output when it differs from the input's (the half-precision trunk hands its last source to the bf16 heads)."""
     pd = E.packed_dw(name + '.0', name + '.1', stride)
     if E.use_tc and x.dtype == torch.bfloat16 and stride == 1 and os.environ.get('TDRN_DWPW', '0') == '1':
         # OPT-IN (TDRN_DWPW=1): both halves in one kernel, the depthwise output stays in shared memory (tdrn_conv_dwpw; same
@@ -34,6 +35,8 @@ def _dw_block(E, name, x, stride):
         if pc.w_bf16 is not None and x.shape[3] % 8 == 0 and pc.cout % 8 == 0:
             return ops.conv_dwpw(x, pd, pc)
     x = ops.dwconv3x3(x, pd, relu=True)
+    if out_dtype is not None and out_dtype != x.dtype:
+        return E.conv(name + '.3', x, bn=name + '.4', relu=True, out_dtype=out_dtype)
     return E.conv(name + '.3', x, bn=name + '.4', relu=True)
 
 
@@ -41,16 +44,24 @@ def mobilenet_sources(E, x):
     """The four ARM sources of the MobileNet trunk (dualrefinedet_mobilenet.py:139-152; the same loop in
     ssd4scale_mobile.py:99-110): L2Norm of backbone[11]'s output (512 @ 40x40), L2Norm of the last block
     (1024 @ 20x20), then the two 1x1 + conv_dw(s2) extras (512 @ 10x10, 512 @ 5x5).  NHWC."""
-    x = E.conv_first('backbone.0.0', x, 2, 'backbone.0.1')
+    # 16-bit mode: the trunk (stem, 13 conv_dw blocks, the first extras block) computes and stores IEEE half -- activations AND
+    # weights -- and hands its four sources to the bf16 ARM heads / TCB as bf16: the two L2Norms convert, the first extras block's
+    # pointwise conv writes bf16, the second extras block is bf16 throughout.  (CPU emulation of exactly this plan: conf 1.3e-2
+    # against 3.0e-2 with bf16 storage, scripts/mobilenet_bf16_emulation.py.)  TDRN_MOBILE_BF16=1 keeps the bf16 trunk.
+    half = E.half_trunk and E.act == torch.bfloat16 and ops.conv_first_f16_ok(x)
+    if half:
+        x = E.conv_first('backbone.0.0', x, 2, 'backbone.0.1', out_dtype=torch.float16)
+    else:
+        x = E.conv_first('backbone.0.0', x, 2, 'backbone.0.1')
     arm_sources = []
     for n, (i, o, s) in enumerate(DW_CFG):
         if n + 1 == 12:
-            arm_sources.append(ops.l2norm(x, E.vec('L2Norm_4_3.weight')))
+            arm_sources.append(ops.l2norm(x, E.vec('L2Norm_4_3.weight'), out_dtype=E.act))
         x = _dw_block(E, 'backbone.%d' % (n + 1), x, s)
-    arm_sources.append(ops.l2norm(x, E.vec('L2Norm_5_3.weight')))
+    arm_sources.append(ops.l2norm(x, E.vec('L2Norm_5_3.weight'), out_dtype=E.act))
     for e in range(2):
         x = E.conv('extras.%d.0' % e, x, bn='extras.%d.1' % e, relu=True)
-        x = _dw_block(E, 'extras.%d.3' % e, x, 2)
+        x = _dw_block(E, 'extras.%d.3' % e, x, 2, out_dtype=E.act)
         arm_sources.append(x)
     return arm_sources
 

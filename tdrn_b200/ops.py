@@ -8,7 +8,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import F32, BF16, ConvDesc, DeformHeadDesc, OffsetLevel, check, ptr, stream_handle
+from ._lib import F32, BF16, F16, ConvDesc, DeformHeadDesc, OffsetLevel, check, ptr, stream_handle
 
 BN_EPS = 1e-5
 
@@ -63,6 +63,8 @@ def _dt(t):
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
+    if t.dtype == torch.float16:
+        return F16
     raise TypeError('unsupported dtype %s' % t.dtype)
 
 
@@ -85,12 +87,13 @@ class PackedConv(object):
 
     w_f32  [kh*kw*Cin, Cout] fp32 (tap-major, then cin)      -> tdrn_conv2d (SIMT, fp32 accumulate)
     w_bf16 [Cout_pad, kh*kw*Cin_pad] bf16, K-major           -> tdrn_conv2d_tc (tcgen05); Cin_pad = Cin up to 64
+    w_f16  the same packing in IEEE half (want_f16)           -> tdrn_conv2d_tc with in_dtype TDRN_F16
     w_x3   [Cout_pad, kh*kw*2*Cin] bf16 (W_hi | W_lo per tap)  -> tdrn_conv2d_tc with split3 (fp32-accurate tensor-core path)
     deconv (ConvTranspose2d k2 s2, weight [Cin,Cout,2,2]): w_f32 [Cin, 4*Cout] with n = (i*2+j)*Cout+co
     """
 
     def __init__(self, weight, bias=None, bn=None, stride=1, pad=0, dil=1, deconv=False, device='cuda',
-                 want_bf16=True, want_x3=False):
+                 want_bf16=True, want_x3=False, want_f16=False):
         w = weight.detach().double().cpu()
         b = bias.detach().double().cpu() if bias is not None else None
         self.deconv = deconv
@@ -113,6 +116,7 @@ class PackedConv(object):
             wk = w.permute(0, 2, 3, 1).reshape(self.cout, self.kh * self.kw * self.cin)
         self.bias = b.float().contiguous().to(device) if b is not None else None
         self.w_bf16 = None
+        self.w_f16 = None
         self.w_x3 = None
         if want_x3 and self.cin % 64 == 0:
             # fp32-accurate tensor-core mode (tdrn_conv_desc.split3): [rows_pad][taps][W_hi | W_lo] bf16, where the fp32
@@ -134,6 +138,30 @@ class PackedConv(object):
             wp = torch.zeros(rows_pad, taps, cin_pad, dtype=torch.float64)
             wp[:rows, :, :self.cin] = wk.reshape(rows, taps, self.cin)
             self.w_bf16 = wp.reshape(rows_pad, taps * cin_pad).to(torch.bfloat16).contiguous().to(device)
+            if want_f16:           # the same packing as IEEE half: operands of the TDRN_F16 convs (MobileNet trunk)
+                self.w_f16 = wp.reshape(rows_pad, taps * cin_pad).clamp(-65504.0, 65504.0).to(torch.float16).contiguous().to(device)
+
+
+def ensure_f16(pc):
+    """Half-packed weights of ``pc`` (PackedConv.w_f16), made on first use from the fp32 copy when the layer was packed without them."""
+    if pc.w_f16 is None and pc.w_bf16 is not None and not pc.deconv:
+        rows_pad, kpad = pc.w_bf16.shape
+        taps = pc.kh * pc.kw
+        cin_pad = kpad // taps
+        wp = torch.zeros(rows_pad, taps, cin_pad, dtype=torch.float32, device=pc.w_f32.device)
+        wp[:pc.cout, :, :pc.cin] = pc.w_f32.t().reshape(pc.cout, taps, pc.cin)
+        pc.w_f16 = wp.reshape(rows_pad, kpad).clamp(-65504.0, 65504.0).to(torch.float16).contiguous()
+    return pc.w_f16
+
+
+def conv_first_f16_ok(x_nchw, stride=2, cout=32):
+    """Does the tensor-core stem (the only one with half output) tile this image?  Mirrors launch_conv_stem_tc (conv_stem_tc.cu)."""
+    H, W = x_nchw.shape[2], x_nchw.shape[3]
+    if not ((stride == 2 and cout == 32 and H % 2 == 0 and W % 2 == 0) or (stride == 1 and cout == 64)):
+        return False
+    Ho, Wo = conv_out(H, 3, stride, 1, 1), conv_out(W, 3, stride, 1, 1)
+    tiles = (Wo % 64 == 0 and Ho % 2 == 0) or (Wo % 32 == 0 and Ho % 4 == 0) or (Wo % 16 == 0 and Ho % 8 == 0)
+    return tiles and W % 4 == 0 and x_nchw.data_ptr() % 16 == 0
 
 
 def split_bf16(x_nhwc):
@@ -181,9 +209,9 @@ def conv2d(x_nhwc, pc, relu=False, out=None, out_dtype=None, residual=None, out_
     L = _lib.lib()
     flops = 2.0 * B * (H * W * 4 if pc.deconv else Ho * Wo * pc.kh * pc.kw) * Cin * pc.cout if work is None else work
     if use_tc:
-        wt = pc.w_x3 if split3 else pc.w_bf16
-        if wt is None or x.dtype != torch.bfloat16 or dg:
-            raise _lib.TdrnError('tcgen05 conv needs bf16 input, Cin %% 64 == 0 and no offsets')
+        wt = pc.w_x3 if split3 else (ensure_f16(pc) if x.dtype == torch.float16 else pc.w_bf16)
+        if wt is None or x.dtype not in (torch.bfloat16, torch.float16) or dg:
+            raise _lib.TdrnError('tcgen05 conv needs bf16 (or half, with half-packed weights) input, Cin %% 8 == 0 and no offsets')
         with _Timed(label or '%s|%dx%d k%d d%d @%dx%d%s' % ('conv_tc_x3' if split3 else 'conv_tc', Cin, pc.cout, pc.kh, pc.dil, H, W,
                                                             ' deconv' if pc.deconv else ''), flops):
             check(L.tdrn_conv2d_tc(ctypes.byref(d), ptr(x), ptr(wt), ptr(pc.bias), ptr(residual), ptr(out),
@@ -254,14 +282,14 @@ class PackedDw(object):
         self.bias = (beta - mean * scale).float().contiguous().to(device)
 
 
-def dwconv3x3(x_nhwc, pd, relu=True):
+def dwconv3x3(x_nhwc, pd, relu=True, out_dtype=None):
     x = _cuda(x_nhwc, 'input')
     B, H, W, C = x.shape
     Ho, Wo = conv_out(H, 3, pd.stride, 1, 1), conv_out(W, 3, pd.stride, 1, 1)
-    out = torch.empty(B, Ho, Wo, C, dtype=x.dtype, device=x.device)
+    out = torch.empty(B, Ho, Wo, C, dtype=out_dtype or x.dtype, device=x.device)
     with _Timed('aux|dwconv3x3 %d s%d @%dx%d' % (C, pd.stride, H, W), float((x.numel() + out.numel()) * x.element_size())):
-        check(_lib.lib().tdrn_dwconv3x3(ptr(x), ptr(pd.w), ptr(pd.bias), ptr(out), B, H, W, C, pd.stride, int(relu),
-                                        _dt(x), stream_handle()), 'tdrn_dwconv3x3')
+        check(_lib.lib().tdrn_dwconv3x3_io(ptr(x), ptr(pd.w), ptr(pd.bias), ptr(out), B, H, W, C, pd.stride, int(relu),
+                                           _dt(x), _dt(out), stream_handle()), 'tdrn_dwconv3x3')
     return out
 
 
@@ -291,13 +319,13 @@ def maxpool2x2(x_nhwc, ceil_mode=False):
     return out
 
 
-def l2norm(x_nhwc, weight_f32):
+def l2norm(x_nhwc, weight_f32, out_dtype=None):
     x = _cuda(x_nhwc, 'input')
-    out = torch.empty_like(x)
+    out = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
     C = x.shape[-1]
     with _Timed('aux|l2norm %d' % C, float(2 * x.numel() * x.element_size())):
-        check(_lib.lib().tdrn_l2norm(ptr(x), ptr(weight_f32), ptr(out), ctypes.c_longlong(x.numel() // C), C, _dt(x),
-                                     stream_handle()), 'tdrn_l2norm')
+        check(_lib.lib().tdrn_l2norm_io(ptr(x), ptr(weight_f32), ptr(out), ctypes.c_longlong(x.numel() // C), C, _dt(x), _dt(out),
+                                        stream_handle()), 'tdrn_l2norm')
     return out
 
 

@@ -125,7 +125,7 @@ def assert_attributed(out, ref, flipped, tol, what, max_flipped_frac=0.03):
     return rep
 
 
-def drn_reference_bundle(sd, x, arm_loc_out, num_classes, multihead, sizes, dg=1, bn=True):
+def drn_reference_bundle(sd, x, arm_loc_out, num_classes, multihead, sizes, dg=1, bn=True, trunk=None):
     """Everything the bf16 end-to-end gate of a DualRefineDet-VGG needs, from ONE oracle pass on the host:
     the oracle's outputs, the rows whose taps changed side under the product's ARM regression `arm_loc_out`, and the
     oracle's ODM heads evaluated on its own fp32 features but WITH THE PRODUCT'S OFFSETS (`*_given`): the product is
@@ -133,7 +133,7 @@ def drn_reference_bundle(sd, x, arm_loc_out, num_classes, multihead, sizes, dg=1
     from oracle import model_ref as M
     import torch.nn.functional as F
     with torch.no_grad():
-        src = M._vgg_trunk(sd, x, bn)
+        src = trunk(sd, x) if trunk is not None else M._vgg_trunk(sd, x, bn)     # trunk: e.g. M._mobilenet_trunk
         odm = M._fpn(sd, src)
         loc_a = [M._c(sd, 'arm_loc.%d' % k, src[k], 1, 1) for k in range(4)]
         o1 = [M._c(sd, 'offset.%d' % k, loc_a[k]) for k in range(4)]

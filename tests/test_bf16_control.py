@@ -137,3 +137,88 @@ def test_tap_validity_matches_the_oracle_sampler():
         cpg = c // dg
         for ch in range(c):
             assert torch.equal(cols[ch] != 0, valid[ch // cpg])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# MobileNet variant (16-bit path = IEEE-half trunk + bf16 ARM heads / TCB / deformable heads): the same control.
+# The emulation below is the product's arithmetic plan (tdrn_b200/model/dualrefinedet_mobilenet.py:mobilenet_sources):
+# half image / weights / activations through the first extras block, packed-half FMAs in the depthwise convs (every FMA
+# rounded to half), bf16 where the sources leave the trunk, bf16 second extras block, bf16 ARM heads.
+# ---------------------------------------------------------------------------------------------------------------
+def _h(t):
+    return t.to(torch.float16).to(torch.float32)
+
+
+def _fold_nb(sd, conv, bn):
+    w = sd[conv + '.weight'].double()
+    g, b, m, v = [sd[bn + k].double() for k in ('.weight', '.bias', '.running_mean', '.running_var')]
+    s = g / torch.sqrt(v + M.BN_EPS)
+    cb = sd[conv + '.bias'].double() if conv + '.bias' in sd else 0.0
+    return (w * s.view(-1, 1, 1, 1)).float(), (b + (cb - m) * s).float()
+
+
+def _dw_packed_half(x, w, b, stride):
+    c = x.size(1)
+    xp = F.pad(x, (1, 1, 1, 1))
+    Ho, Wo = (x.shape[2] - 1) // stride + 1, (x.shape[3] - 1) // stride + 1
+    acc = _h(b).view(1, c, 1, 1).expand(x.size(0), c, Ho, Wo).clone()
+    wh = _h(w)
+    for i in range(3):
+        for j in range(3):
+            xt = xp[:, :, i:i + (Ho - 1) * stride + 1:stride, j:j + (Wo - 1) * stride + 1:stride]
+            acc = _h(acc + xt * wh[:, 0, i, j].view(1, c, 1, 1))          # fma.rn.f16x2: one rounding per tap
+    return F.relu(acc)
+
+
+def mobilenet_trunk_half_emulated(sd, x):
+    w, b = _fold_nb(sd, 'backbone.0.0', 'backbone.0.1')
+    x = _h(F.relu(F.conv2d(_h(x), _h(w), b, 2, 1)))
+    src = []
+
+    def conv_dw(name, x, stride, r, r_out, packed):
+        w, b = _fold_nb(sd, name + '.0', name + '.1')
+        x = _dw_packed_half(x, w, b, stride) if packed else r(F.relu(F.conv2d(x, w, b, stride, 1, 1, x.size(1))))
+        w, b = _fold_nb(sd, name + '.3', name + '.4')
+        return r_out(F.relu(F.conv2d(x, r(w), b)))
+
+    for n, (i, o, s) in enumerate(M.MOBILENET_DW):
+        if n + 1 == 12:
+            src.append(_bf(M.l2norm(x, sd['L2Norm_4_3.weight'])))
+        x = conv_dw('backbone.%d' % (n + 1), x, s, _h, _h, True)
+    src.append(_bf(M.l2norm(x, sd['L2Norm_5_3.weight'])))
+    w, b = _fold_nb(sd, 'extras.0.0', 'extras.0.1')
+    x = _h(F.relu(F.conv2d(x, _h(w), b)))
+    x = conv_dw('extras.0.3', x, 2, _h, _bf, True)
+    src.append(x)
+    w, b = _fold_nb(sd, 'extras.1.0', 'extras.1.1')
+    x = _bf(F.relu(F.conv2d(x, _bf(w), b)))
+    x = conv_dw('extras.1.3', x, 2, _bf, _bf, False)
+    src.append(x)
+    return src
+
+
+def test_mobilenet_half_trunk_control():
+    """(1) The half trunk keeps the ARM regression within 1e-2 of the oracle (a bf16 trunk: 2.5e-2).  (2) The oracle's OWN heads, fed
+    offsets regressed from that ARM regression, move by MORE than 2 x 2e-2 on rows whose taps did not change side: on this
+    variant the reference's response to an 8e-3 offset perturbation is steep (measured here: odm_loc 5-10e-2, conf 1.1-1.5e-1),
+    which is why the GPU gate of the MobileNet variant bounds the non-flipped rows by the size measured HERE and holds the
+    product to 2e-2 on every row only against the oracle heads fed the product's own offsets (parity_tools.assert_bf16_gate (A))."""
+    mod_name, spec_fn, build_kw, spec_kw, _ = CASES['drn_mobilenet320']
+    sd = M.make_state_dict(spec_fn(**spec_kw), SEED_W)
+    x = make_input(1, 320)
+    with torch.no_grad():
+        src = mobilenet_trunk_half_emulated(sd, x)
+        arm = [F.conv2d(_bf(src[k]), _bf(sd['arm_loc.%d.weight' % k]), None, 1, 1) for k in range(4)]
+        arm_flat = torch.cat([m.permute(0, 2, 3, 1).reshape(1, -1) for m in arm], 1).view(1, -1, 4)
+        R = PT.drn_reference_bundle(sd, x, arm_flat, 21, False, [(s, s) for s in (40, 20, 10, 5)], trunk=M._mobilenet_trunk)
+    e_arm = float((arm_flat - R['arm_loc']).abs().max() / R['arm_loc'].abs().max())
+    assert e_arm < 1e-2, e_arm
+    fl = R['flipped'].reshape(-1)
+    rep_l = PT.split_report(R['odm_loc_given'].reshape(-1, 4).numpy(), R['odm_loc'].reshape(-1, 4).numpy(), fl, TOL)
+    rep_c = PT.split_report(R['conf_given'].numpy(), R['conf'].numpy(), fl, TOL)
+    assert 4e-2 < rep_l['max_other'] < MOBILE_SLACK * TOL and 4e-2 < rep_c['max_other'] < MOBILE_SLACK * TOL, (rep_l, rep_c)
+    assert rep_l['n_beyond'] < 0.03 * rep_l['rows'] and rep_c['n_beyond'] < 0.03 * rep_c['rows'], (rep_l, rep_c)
+    assert rep_l['l2'] < 3e-2 and rep_c['l2'] < 3e-2
+
+
+MOBILE_SLACK = 10.0     # bound on the non-flipped rows of the MobileNet variant, in units of 2e-2 (the control above measures 2.8-7.6)

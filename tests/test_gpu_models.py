@@ -28,7 +28,7 @@ def check_odm(out, ref, precision, what, l2_tol=5e-2, row_frac=0.05):
     assert (rows > TOL['bf16']).mean() < row_frac, (what, float((rows > TOL['bf16']).mean()))
 
 
-def check_odm_attributed(out, ref, flipped, precision, what, out_given=None, max_flipped_frac=0.03):
+def check_odm_attributed(out, ref, flipped, precision, what, out_given=None, max_flipped_frac=0.03, slack=2.0, min_explained=0.85):
     """Deformable-head outputs of the END-TO-END chain.  fp32 path: max-norm relative error < 1e-4.
     bf16 path (tests/parity_tools.assert_bf16_gate):
       (A) against the oracle's heads evaluated on the oracle's own fp32 features WITH THE PRODUCT'S OFFSETS (`out_given`):
@@ -48,17 +48,21 @@ def check_odm_attributed(out, ref, flipped, precision, what, out_given=None, max
         # (parity_tools.assert_fp32_gate: the discontinuity is there in fp32 too, it is just hit ~1000x less often)
         PT.assert_fp32_gate(out, ref, flipped, TOL['fp32'], what, out_given=out_given)
         return
-    PT.assert_bf16_gate(out, ref, flipped, TOL['bf16'], what, out_given=out_given, max_flipped_frac=max_flipped_frac)
+    rep = PT.assert_bf16_gate(out, ref, flipped, TOL['bf16'], what, out_given=out_given, max_flipped_frac=max_flipped_frac, slack=slack,
+                              min_explained=min_explained)
+    if min_explained == 0.0:     # MobileNet variant: rows beyond 2e-2 are not all edge flips (tests/test_bf16_control.py): they must be rare
+        assert rep['n_beyond'] < 0.03 * rep['rows'] and rep['l2'] < 3e-2, (what, rep)
 
 
-def check_drn_vgg(out, sd, x, spec_kw, precision, sizes, stride=1, golden=None, max_flipped_frac=0.03):
+def check_drn_vgg(out, sd, x, spec_kw, precision, sizes, stride=1, golden=None, max_flipped_frac=0.03, trunk=None, slack=2.0,
+                  min_explained=0.85):
     """arm_loc / offsets / odm_loc / conf of a DualRefineDet-VGG forward against the oracle (and, when given, the
     reference's golden arrays, strided by `stride` rows)."""
     import parity_tools as PT
     tol = TOL[precision]
     b = x.shape[0]
-    R = PT.drn_reference_bundle(sd, x.cpu(), out[0], spec_kw['num_classes'], spec_kw['multihead'], sizes)
-    C = spec_kw['num_classes']
+    R = PT.drn_reference_bundle(sd, x.cpu(), out[0], spec_kw.get('num_classes', 21), spec_kw.get('multihead', False), sizes, trunk=trunk)
+    C = spec_kw.get('num_classes', 21)
     arm, loc, conf = out[0].cpu().numpy(), out[2].cpu().numpy(), out[3].cpu().numpy()
     assert rel_err(arm, R['arm_loc'].numpy()) < tol
     fl = R['flipped'].reshape(-1)
@@ -68,13 +72,13 @@ def check_drn_vgg(out, sd, x, spec_kw, precision, sizes, stride=1, golden=None, 
         assert rel_err(R['arm_loc'][0, ::stride].numpy(), golden['arm_loc']) < 1e-5      # restatement == reference (other CPU: ulps)
         assert rel_err(arm[0, ::stride], golden['arm_loc']) < tol
         check_odm_attributed(loc[0, ::stride], golden['odm_loc'], fl[::stride], precision, 'odm_loc vs golden',
-                             out_given=R['odm_loc_given'][0, ::stride].numpy(), max_flipped_frac=max_flipped_frac)
+                             out_given=R['odm_loc_given'][0, ::stride].numpy(), max_flipped_frac=max_flipped_frac, slack=slack, min_explained=min_explained)
         check_odm_attributed(conf[::stride], golden['conf'], fl[::stride], precision, 'conf vs golden',
-                             out_given=R['conf_given'][::stride].numpy(), max_flipped_frac=max_flipped_frac)
+                             out_given=R['conf_given'][::stride].numpy(), max_flipped_frac=max_flipped_frac, slack=slack, min_explained=min_explained)
     check_odm_attributed(rows4(loc), rows4(R['odm_loc'].numpy()), fl, precision, 'odm_loc', out_given=rows4(R['odm_loc_given'].numpy()),
-                         max_flipped_frac=max_flipped_frac)
+                         max_flipped_frac=max_flipped_frac, slack=slack, min_explained=min_explained)
     check_odm_attributed(conf, R['conf'].numpy(), fl, precision, 'conf', out_given=R['conf_given'].numpy(),
-                         max_flipped_frac=max_flipped_frac)
+                         max_flipped_frac=max_flipped_frac, slack=slack, min_explained=min_explained)
     return R
 
 
@@ -114,12 +118,16 @@ def test_detector_vs_reference_golden(golden, name, precision):
         assert rel_err(odm_loc[0, ::stride].cpu().numpy(), g['odm_loc']) < tol
         assert rel_err(conf[::stride].cpu().numpy(), g['conf']) < tol
     elif mod_name == 'drn_mobilenet':
-        # KNOWN DEVIATION: the MobileNet variant stacks 27 bf16-rounded layers (every depthwise and
-        # pointwise output is stored in bf16) and lands at ~3e-2 even with exact offsets, above the 2e-2 the
-        # north_star quotes; its fp32 path meets 1e-4.  The looser bound keeps the regression visible.
-        kw = dict(l2_tol=1e-1, row_frac=0.2)
-        check_odm(odm_loc[0, ::stride].cpu().numpy(), g['odm_loc'], precision, 'odm_loc', **kw)
-        check_odm(conf[::stride].cpu().numpy(), g['conf'], precision, 'conf', **kw)
+        # r02: the trunk of the 16-bit path runs in IEEE half (activations and weights; 27 bf16-rounded layers landed at ~3e-2
+        # even with exact offsets) and this variant now passes the SAME attributed gate as the VGG detectors
+        # -- part (A), 2e-2 on every row against the oracle heads fed the product's offsets, unchanged.  Part (B): on this variant the
+        # ORACLE's own heads move by 5-15e-2 on rows without a flipped tap when their offsets come from an ARM regression that is
+        # 8e-3 off (CPU control tests/test_bf16_control.py::test_mobilenet_half_trunk_control), so the non-flipped rows are bounded
+        # by that measured response (MOBILE_SLACK x 2e-2) and the rows beyond 2e-2 must be rare (< 3 %, relative L2 < 3e-2).
+        from oracle import model_ref as M2
+        from test_bf16_control import MOBILE_SLACK
+        check_drn_vgg(out, sd, x, spec_kw, precision, [(s, s) for s in (40, 20, 10, 5)], stride=stride, golden=g, trunk=M2._mobilenet_trunk,
+                      slack=MOBILE_SLACK, min_explained=0.0)
     else:
         # the golden arrays are the reference's own outputs; the oracle restatement (bit-identical to the reference in the
         # build container, tests/test_oracle_vs_reference.py) is re-run here to name the rows whose taps changed side
@@ -271,7 +279,7 @@ def test_bf16_heads_with_reference_offsets(name):
             src = M._vgg_trunk(sd, x, True)
             offs2 = [M._c(sd, 'offset2.%d' % k, M._c(sd, 'arm_loc.%d' % k, src[k], 1, 1)) for k in range(4)]
         out = net(x.cuda(), _offsets=([o.cuda() for o in offs], [o.cuda() for o in offs2] if offs2 else None))
-    tol = 4e-2 if mod_name == 'drn_mobilenet' else TOL['bf16']      # MobileNet bf16: known deviation, see above
+    tol = TOL['bf16']               # both variants: the MobileNet trunk computes in IEEE half (3.5e-2 with a bf16 trunk, 1.6e-2 now)
     assert rel_err(out[2].cpu().numpy(), ref[2].numpy()) < tol
     assert rel_err(out[3].cpu().numpy(), ref[3].numpy()) < tol
 

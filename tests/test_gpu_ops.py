@@ -182,3 +182,96 @@ def test_l2norm_bf16_vectorised():
         ref = (wt * (xf / (xf.pow(2).sum(3, keepdim=True).sqrt() + 1e-10))).to(torch.bfloat16)
         out = ops.l2norm(x.cuda(), wt.cuda())
         assert rel_err(out.float().cpu().numpy(), ref.float().numpy()) < 8e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# IEEE-half variants of the MobileNet trunk operators (TDRN_F16): stem, depthwise 3x3, pointwise 1x1, L2Norm.
+# References: fp32 torch on the half-rounded operands; tolerance = the output rounding of the output format.
+# ---------------------------------------------------------------------------------------------------------------
+def _h(x):
+    return x.to(torch.float16).float()
+
+
+@pytest.mark.parametrize('stride', [1, 2])
+@pytest.mark.parametrize('din,dout', [(torch.float16, torch.float16), (torch.bfloat16, torch.float16), (torch.float16, torch.bfloat16)])
+def test_dwconv3x3_half_formats(stride, din, dout):
+    from tdrn_b200 import ops
+    b, c, h, w = 2, 64, 18, 22
+    g = torch.Generator().manual_seed(c + h + stride)
+    x = torch.randn(b, c, h, w, generator=g).to(din)
+    wd = torch.randn(c, 1, 3, 3, generator=g)
+    bn = (torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g), torch.randn(c, generator=g), torch.rand(c, generator=g) + 0.5)
+    ref = F.relu(F.batch_norm(F.conv2d(x.float(), wd, None, stride, 1, 1, c), bn[2], bn[3], bn[0], bn[1], False, 0.0, 1e-5))
+    out = ops.dwconv3x3(x.permute(0, 2, 3, 1).contiguous().cuda(), ops.PackedDw(wd, bn, stride, 'cuda'), out_dtype=dout)
+    assert out.dtype == dout
+    # half -> half runs the packed-half kernel (nine FMAs rounded to half each): a few half ulps; the mixed forms accumulate in fp32
+    tol = 3e-3 if (din, dout) == (torch.float16, torch.float16) else (8e-4 if dout == torch.float16 else 6e-3)
+    assert rel_err(out.float().permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < tol
+    # same input format in and out == the plain entry point
+    if din == dout:
+        assert torch.equal(out, ops.dwconv3x3(x.permute(0, 2, 3, 1).contiguous().cuda(), ops.PackedDw(wd, bn, stride, 'cuda')))
+
+
+def test_dwconv3x3_half_saturates():
+    """Conversions to half saturate at the largest finite value instead of producing Inf."""
+    from tdrn_b200 import ops
+    c = 8
+    x = torch.full((1, 4, 4, c), 3.0e4, dtype=torch.float16)
+    wd = torch.ones(c, 1, 3, 3)
+    bn = (torch.ones(c), torch.zeros(c), torch.zeros(c), torch.ones(c))
+    out = ops.dwconv3x3(x.cuda(), ops.PackedDw(wd, bn, 1, 'cuda'))
+    assert bool(torch.isfinite(out).all()) and float(out.max()) == 65504.0
+
+
+@pytest.mark.parametrize('b,cin,cout,h,w,dout', [(2, 64, 128, 20, 20, torch.float16), (3, 32, 64, 16, 24, torch.float16),
+                                                 (2, 256, 512, 10, 10, torch.bfloat16), (1, 512, 512, 40, 40, torch.float16)])
+def test_conv1x1_tc_half_operands(b, cin, cout, h, w, dout):
+    """Pointwise conv of the half-precision trunk: half activations and half-packed weights on tcgen05 (kind::f16 with the
+    half format codes), fp32 accumulation, half or bf16 output."""
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = torch.randn(b, cin, h, w, generator=g).to(torch.float16)
+    wt = torch.randn(cout, cin, 1, 1, generator=g) * (cin ** -0.5)
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.relu(F.conv2d(x.float(), _h(wt), bias))
+    pc = ops.PackedConv(wt, bias, None, 1, 0, 1, device='cuda', want_f16=True)
+    out = ops.conv2d(x.permute(0, 2, 3, 1).contiguous().cuda(), pc, relu=True, use_tc=True, out_dtype=dout)
+    torch.cuda.synchronize()
+    assert out.dtype == dout and out.shape == (b, h, w, cout)
+    assert rel_err(out.float().permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < (8e-4 if dout == torch.float16 else 6e-3)
+    # weights packed lazily from the fp32 copy give the same half bits
+    pc2 = ops.PackedConv(wt, bias, None, 1, 0, 1, device='cuda')
+    assert pc2.w_f16 is None and torch.equal(ops.ensure_f16(pc2), pc.w_f16)
+
+
+@pytest.mark.parametrize('b,h,w', [(2, 32, 128), (1, 320, 320)])
+def test_conv_stem_half_output(b, h, w):
+    """MobileNet stem with half operands and output (tdrn_conv_first, out_dtype TDRN_F16)."""
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(b + h)
+    x = torch.randn(b, 3, h, w, generator=g) * 40.0          # pixel-scale inputs
+    wt = torch.randn(32, 3, 3, 3, generator=g) * 0.05
+    bias = torch.randn(32, generator=g)
+    ref = F.relu(F.conv2d(_h(x), _h(wt), bias, 2, 1))
+    pc = ops.PackedConv(wt, bias, None, 2, 1, 1, device='cuda', want_bf16=False)
+    assert ops.conv_first_f16_ok(x.cuda())
+    out = ops.conv_first(x.cuda(), pc, True, torch.float16)
+    torch.cuda.synchronize()
+    assert out.dtype == torch.float16 and out.shape == (b, h // 2, w // 2, 32)
+    assert rel_err(out.float().permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 8e-4
+    assert not ops.conv_first_f16_ok(torch.zeros(1, 3, 20, 40, device='cuda'))
+
+
+def test_l2norm_half_in_bf16_out():
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(78)
+    for c, px in ((512, 40), (1024, 12)):
+        x = (torch.randn(2, px, 2, c, generator=g) * 2).to(torch.float16)
+        wt = torch.rand(c, generator=g) * 20 + 1
+        xf = x.float()
+        ref = wt * (xf / (xf.pow(2).sum(3, keepdim=True).sqrt() + 1e-10))
+        out = ops.l2norm(x.cuda(), wt.cuda(), out_dtype=torch.bfloat16)
+        assert out.dtype == torch.bfloat16
+        assert rel_err(out.float().cpu().numpy(), ref.numpy()) < 6e-3
+        out16 = ops.l2norm(x.cuda(), wt.cuda())
+        assert out16.dtype == torch.float16 and rel_err(out16.float().cpu().numpy(), ref.numpy()) < 8e-4
