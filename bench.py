@@ -133,6 +133,9 @@ class MobileNet(Workload):
     batch, size, num_classes = 64, 320, 21
     model_kw = dict(num_classes=21, def_groups=1, multihead=False)
     gflop_per_frame = 20.297
+    # 16-bit mode of this variant: IEEE-half trunk (activations and weights), bf16 ARM heads / TCB / deformable heads; fp32 accumulation
+    # on the tensor cores, packed-half FMAs in the depthwise convs (TDRN_MOBILE_BF16=1: bf16 trunk, 3.5e-2 instead of 1.6e-2 on conf)
+    dtype_16 = 'bf16' if os.environ.get('TDRN_MOBILE_BF16', '0') == '1' else 'f16 (trunk) + bf16 (heads)'
 
     def build_modules(self):
         from tdrn_b200.model import dualrefinedet_mobilenet as Mb
@@ -794,7 +797,7 @@ def run_gpu(args, rank, world, local_rank):
         h2d = int(e2e_dst[0].numel() * e2e_dst[0].element_size())
         line = {'metric': wl.metric, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+                'dtype': getattr(wl, 'dtype_16', 'bf16') if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
                 'config': wl.describe(world, n_fl, 'u8' if use_u8 else 'fp32'),
                 'e2e': {'value': e2e_v, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
                         'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(host_out.numel() * 4),

@@ -5,6 +5,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+if len(sys.argv) > 2 and sys.argv[2] == 'mobilenet':       # the MobileNet variant (IEEE-half trunk); B >= 64 takes the row-walking depthwise form
+    wl = bench.MobileNet()
+    wl.setup(torch.device('cuda'), 'bf16')
+    x = torch.randn(B, 3, 320, 320, generator=torch.Generator().manual_seed(1)).cuda()
+    with torch.no_grad():
+        out = wl.hot_path(x)
+        torch.cuda.synchronize()
+    print('mobilenet (half trunk) b%d: %d detections' % (B, int((out[..., 0] > 0).sum())))
+    sys.exit(0)
 wl = bench.Workload()
 wl.setup(torch.device('cuda'), 'bf16')
 x = torch.randn(B, 3, 320, 320, generator=torch.Generator().manual_seed(1)).cuda()

@@ -23,6 +23,7 @@
 // fewer tiles than SMs (the 10x10 / 5x5 pyramid levels).
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace tdrn {
 namespace tc {
@@ -1182,6 +1183,13 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         p.mt2 = !no_mt2 && !d->split3 && BN == 256 && p.tma_out && !p.b_resident && !use_cluster && num_kb >= 64 && units2 * 100 >= g_num_sms * mt2_min;   // measured: K = 2304 (36 k-blocks) loses 5 %, K = 4608 gains 5-10 %
     }
     cudaStream_t st = as_stream(stream);
+    {   // development aid (TDRN_TC_VERBOSE=1): which tiling / variant a layer gets
+        static const bool verbose = getenv("TDRN_TC_VERBOSE") != nullptr;
+        if (verbose)
+            fprintf(stderr, "conv_tc %dx%d k%d @%dx%d b%d: box %dx%dx%d, m_tiles %d (tail rr %d g2 %d), BN %d x %d, kb %d, mt2 %d cluster %d resident %d tma_out %d splitk %d\n",
+                    d->Cin, d->Cout, kh, p.H, p.W, p.B, p.bw, p.bh, p.bn, p.m_tiles, p.rr, p.g2, BN, p.n_tiles, p.taps * (p.Cin >> 6), p.mt2,
+                    (int)use_cluster, p.b_resident, p.tma_out, p.splitk);
+    }
     if (p.splitk > 1) {
         TDRN_CUDA(cudaFuncSetAttribute(conv_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
         cudaLaunchConfig_t cfg = {};
