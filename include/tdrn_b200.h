@@ -257,7 +257,9 @@ typedef struct tdrn_deform_head_desc {
     int softmax;
     int split;                 /* tdrn_deform_head_sample only: 1 = the projections are (hi | lo) bf16 pairs,
                                   proj [B,H,W,taps,2*g] with n_pad = 2*g, 12 + 3C <= g (fp32-accurate heads: both halves
-                                  are sampled and added in fp32 before the softmax)                             */
+                                  are sampled and added in fp32 before the softmax);
+                                  2 = the projections are IEEE half (TDRN_F16 output of tdrn_conv2d_tc) instead of bf16:
+                                  same bytes, 11 instead of 8 significand bits in the sampled values                */
 } tdrn_deform_head_desc;
 
 int tdrn_deform_head(const tdrn_deform_head_desc *d, const void *feat, const float *offsets,

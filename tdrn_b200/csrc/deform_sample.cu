@@ -31,6 +31,7 @@ struct SampleP {
     int taps_pad;                    // taps_total rounded up to even (padding entry: weight 0)
     int TW, TH, tiles_w, tiles_h, slots;
     int n_total, C, P, prior_off, softmax;
+    int f16;                         // the projections are IEEE half instead of bf16 (tdrn_deform_head_desc.split & 2)
     int merge_g;                     // > 0: the projections are (hi | lo) pairs, columns [g, 2g) are added to [0, g) before the softmax
     float *loc_out, *conf_out;
 };
@@ -41,10 +42,16 @@ __device__ __forceinline__ uint64_t s_pair(float lo, float hi)
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
-__device__ __forceinline__ uint64_t s_unpack(uint32_t a)     // bf16x2 -> (lo, hi) fp32
+template <bool F16>
+__device__ __forceinline__ uint64_t s_unpack(uint32_t a)     // bf16x2 (or IEEE half x2) -> (lo, hi) fp32
 {
     uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a << 16), "r"(a & 0xffff0000u));
+    if (F16) {
+        asm("{\n\t.reg .b16 l, h;\n\t.reg .f32 fl, fh;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 fl, l;\n\tcvt.f32.f16 fh, h;\n\tmov.b64 %0, {fl, fh};\n\t}"
+            : "=l"(r) : "r"(a));
+    } else {
+        asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a << 16), "r"(a & 0xffff0000u));
+    }
     return r;
 }
 __device__ __forceinline__ uint64_t s_fma2(uint64_t a, uint64_t b, uint64_t c)
@@ -53,19 +60,21 @@ __device__ __forceinline__ uint64_t s_fma2(uint64_t a, uint64_t b, uint64_t c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+template <bool F16>
 __device__ __forceinline__ void s_acc(uint64_t (&acc)[4], const uint4 v, float w)
 {
     const uint64_t ww = s_pair(w, w);
-    acc[0] = s_fma2(ww, s_unpack(v.x), acc[0]);
-    acc[1] = s_fma2(ww, s_unpack(v.y), acc[1]);
-    acc[2] = s_fma2(ww, s_unpack(v.z), acc[2]);
-    acc[3] = s_fma2(ww, s_unpack(v.w), acc[3]);
+    acc[0] = s_fma2(ww, s_unpack<F16>(v.x), acc[0]);
+    acc[1] = s_fma2(ww, s_unpack<F16>(v.y), acc[1]);
+    acc[2] = s_fma2(ww, s_unpack<F16>(v.z), acc[2]);
+    acc[3] = s_fma2(ww, s_unpack<F16>(v.w), acc[3]);
 }
 
 constexpr int DS_MAX_WARPS = 16;
 
 // One CTA's patch of one pyramid level.  `block` = index of the patch inside the level; blockDim may be larger than the level
 // needs (grouped launch: the widest level decides): the extra warps own no pixel slot and only take part in the barriers.
+template <bool F16>
 __device__ __forceinline__ void deform_sample_body(const SampleP &p, int block)
 {
     extern __shared__ uint4 ds_smem[];           // geometry [slots][taps_total], later the fp32 staging tile
@@ -146,10 +155,10 @@ __device__ __forceinline__ void deform_sample_body(const SampleP &p, int block)
             const uint4 v3 = real ? __ldg(yb + oc) : zero4;
             const uint4 v4 = real ? __ldg(yb + (oc + dxs)) : zero4;
             const float hh = __uint_as_float(e.y), lh = __uint_as_float(e.z), lw = __uint_as_float(e.w), hw = 1.f - lw;
-            s_acc(acc, v1, hh * hw);                                                          // .cu:47-49
-            s_acc(acc, v2, hh * lw);
-            s_acc(acc, v3, lh * hw);
-            s_acc(acc, v4, lh * lw);
+            s_acc<F16>(acc, v1, hh * hw);                                                     // .cu:47-49
+            s_acc<F16>(acc, v2, hh * lw);
+            s_acc<F16>(acc, v3, lh * hw);
+            s_acc<F16>(acc, v4, lh * lw);
         }
     }
     __syncthreads();                              // every warp is done with the geometry: reuse it as the staging tile
@@ -205,9 +214,10 @@ __device__ __forceinline__ void deform_sample_body(const SampleP &p, int block)
     }
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(DS_MAX_WARPS * 32, 2) deform_sample_kernel(const SampleP p)
 {
-    deform_sample_body(p, (int)blockIdx.x);
+    deform_sample_body<F16>(p, (int)blockIdx.x);
 }
 
 // All pyramid levels of a detector in ONE launch (the 20x20 / 10x10 / 5x5 levels are a quarter of the pixels and, launched
@@ -218,11 +228,12 @@ struct SampleGroup {
     SampleP lv[TDRN_MAX_OFFSET_LEVELS];
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(DS_MAX_WARPS * 32, 2) deform_sample_group_kernel(const __grid_constant__ SampleGroup g)
 {
     int k = 0;
     while (k + 1 < g.n && (int)blockIdx.x >= g.first[k + 1]) ++k;
-    deform_sample_body(g.lv[k], (int)blockIdx.x - g.first[k]);
+    deform_sample_body<F16>(g.lv[k], (int)blockIdx.x - g.first[k]);
 }
 
 }  // namespace tdrn
@@ -239,11 +250,14 @@ static int sample_setup(const tdrn_deform_head_desc *d, const void *proj, int n_
     TDRN_REQUIRE(d->kh2 == 0 || (2 * d->pad2 == d->kh2 - 1 && offsets2), "tdrn_deform_head_sample: bad second head");
     p = SampleP{};
     p.n_total = 12 + 3 * d->num_classes;
-    if (d->split && (n_pad % 16 != 0 || n_pad / 2 < p.n_total)) {
+    const int split = d->split & 1;
+    TDRN_REQUIRE(d->split >= 0 && d->split <= 2, "tdrn_deform_head_sample: split is 0, 1 (hi | lo bf16 pairs) or 2 (IEEE-half projections)");
+    p.f16 = d->split == 2;
+    if (split && (n_pad % 16 != 0 || n_pad / 2 < p.n_total)) {
         set_error("tdrn_deform_head_sample: split projections need n_pad = 2*g with 12+3*C <= g (got C=%d n_pad=%d)", d->num_classes, n_pad);
         return TDRN_EUNSUPPORTED;
     }
-    p.merge_g = d->split ? n_pad / 2 : 0;
+    p.merge_g = split ? n_pad / 2 : 0;
     if (d->dg != 1 || n_pad % 8 != 0 || n_pad < p.n_total || n_pad > 256) {
         set_error("tdrn_deform_head_sample: needs one deformable group and 12+3*C <= n_pad <= 256, n_pad %% 8 == 0 "
                   "(got dg=%d C=%d n_pad=%d)", d->dg, d->num_classes, n_pad);
@@ -292,8 +306,13 @@ extern "C" int tdrn_deform_head_sample(const tdrn_deform_head_desc *d, const voi
     size_t smem = 0;
     const int rc = sample_setup(d, proj, n_pad, offsets, offsets2, loc_out, conf_out, p, nw, smem);
     if (rc != TDRN_OK) return rc;
-    TDRN_CUDA(cudaFuncSetAttribute(deform_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    deform_sample_kernel<<<d->B * p.tiles_w * p.tiles_h, nw * 32, smem, as_stream(stream)>>>(p);
+    if (p.f16) {
+        TDRN_CUDA(cudaFuncSetAttribute(deform_sample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        deform_sample_kernel<true><<<d->B * p.tiles_w * p.tiles_h, nw * 32, smem, as_stream(stream)>>>(p);
+    } else {
+        TDRN_CUDA(cudaFuncSetAttribute(deform_sample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        deform_sample_kernel<false><<<d->B * p.tiles_w * p.tiles_h, nw * 32, smem, as_stream(stream)>>>(p);
+    }
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }
@@ -318,8 +337,15 @@ extern "C" int tdrn_deform_head_sample_group(int n_levels, const tdrn_deform_hea
         smem_max = smem > smem_max ? smem : smem_max;
     }
     g.first[n_levels] = run;
-    TDRN_CUDA(cudaFuncSetAttribute(deform_sample_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    deform_sample_group_kernel<<<run, nw_max * 32, smem_max, as_stream(stream)>>>(g);
+    for (int k = 1; k < n_levels; ++k)
+        TDRN_REQUIRE(g.lv[k].f16 == g.lv[0].f16, "tdrn_deform_head_sample_group: all levels must use the same projection format");
+    if (g.lv[0].f16) {
+        TDRN_CUDA(cudaFuncSetAttribute(deform_sample_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        deform_sample_group_kernel<true><<<run, nw_max * 32, smem_max, as_stream(stream)>>>(g);
+    } else {
+        TDRN_CUDA(cudaFuncSetAttribute(deform_sample_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        deform_sample_group_kernel<false><<<run, nw_max * 32, smem_max, as_stream(stream)>>>(g);
+    }
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }

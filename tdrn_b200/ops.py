@@ -470,6 +470,15 @@ def _deform_chunk_bytes():
     return int(float(os.environ.get('TDRN_DEFORM_CHUNK_MB', '1024')) * (1 << 20))
 
 
+def half_projections():
+    """OPT-IN (TDRN_PROJ_F16=1): store the per-tap projections of the 16-bit deformable heads as IEEE half instead of bf16 (same
+    bytes; tdrn_deform_head_desc.split = 2).  Measured on B200 with the oracle's offsets given (scripts/mobile_half_check.py,
+    profiles/r03i_half_check.txt): no gain -- VGG conf 8.2e-3 (bf16) / 8.8e-3 (half), MobileNet 1.60e-2 / 1.69e-2: the rounding of
+    the projections averages out over the 34 x 4 sampled values of a row, the error of the heads comes from their bf16 inputs."""
+    import os
+    return os.environ.get('TDRN_PROJ_F16', '0') == '1'
+
+
 def deform_head_projected(feat_nhwc, offsets, pc_proj, n_pad, num_classes, kh, pad, loc_out, conf_out, P, prior_off,
                           offsets2=None, kh2=0, pad2=0, softmax=True, split=False):
     """Same contract as deform_head (dg = 1) in two launches per image chunk: dense per-tap projection on tcgen05
@@ -484,7 +493,8 @@ def deform_head_projected(feat_nhwc, offsets, pc_proj, n_pad, num_classes, kh, p
     width = 2 * n_pad if split else n_pad
     per_img = H * W * taps * width * 2
     nb = max(1, min(B, _deform_chunk_bytes() // per_img))
-    y = torch.empty(nb, H, W, taps * width, dtype=torch.bfloat16, device=x.device)
+    half = not split and half_projections()
+    y = torch.empty(nb, H, W, taps * width, dtype=torch.float16 if half else torch.bfloat16, device=x.device)
     flops = 2.0 * H * W * (12 + 3 * num_classes) * Cin * taps
     L = _lib.lib()
     xin = split_bf16(x) if split else x
@@ -498,7 +508,7 @@ def deform_head_projected(feat_nhwc, offsets, pc_proj, n_pad, num_classes, kh, p
             conv2d(xin[b0:b0 + n], pc_proj, use_tc=True, out=y[:n],
                    label='%s|%d @%dx%d k%d+%d project' % (tag, Cin, H, W, kh, kh2), work=flops * n)
         d = DeformHeadDesc(B=n, H=H, W=W, Cin=Cin, num_classes=num_classes, dg=1, kh=kh, pad=pad, kh2=kh2, pad2=pad2,
-                           P=P, prior_off=prior_off, softmax=int(softmax), split=int(split))
+                           P=P, prior_off=prior_off, softmax=int(softmax), split=2 if half else int(split))
         with _Timed('%s|%d @%dx%d k%d+%d sample' % (tag, Cin, H, W, kh, kh2), 0.0):
             check(L.tdrn_deform_head_sample(ctypes.byref(d), ptr(y), width, ptr(offsets[b0:b0 + n]),
                                             ptr(offsets2[b0:b0 + n]) if offsets2 is not None else None,
@@ -513,7 +523,7 @@ def deform_project(feat_nhwc, pc_proj, n_pad, kh, kh2, num_classes, split=False,
     B, H, W, Cin = x.shape
     taps = kh * kh + kh2 * kh2
     width = 2 * n_pad if split else n_pad
-    y = torch.empty(B, H, W, taps * width, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(B, H, W, taps * width, dtype=torch.float16 if (not split and half_projections()) else torch.bfloat16, device=x.device)
     flops = 2.0 * B * H * W * (12 + 3 * num_classes) * Cin * taps
     tag = 'deform_head_x3' if split else 'deform_head_tc'
     label = '%s|%d @%dx%d k%d+%d project' % (tag, Cin, H, W, kh, kh2)
@@ -534,7 +544,8 @@ def deform_sample_group(projs, shapes, n_pad, num_classes, kh, pad, offsets, loc
     descs = (DeformHeadDesc * n)()
     for k, (B, H, W, Cin) in enumerate(shapes):
         descs[k] = DeformHeadDesc(B=B, H=H, W=W, Cin=Cin, num_classes=num_classes, dg=1, kh=kh, pad=pad, kh2=kh2, pad2=pad2,
-                                  P=P, prior_off=int(prior_offs[k]), softmax=int(softmax), split=int(split))
+                                  P=P, prior_off=int(prior_offs[k]), softmax=int(softmax),
+                                  split=2 if projs[k].dtype == torch.float16 else int(split))
     vp = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])
     with _Timed('%s|all %d levels k%d+%d sample' % ('deform_head_x3' if split else 'deform_head_tc', n, kh, kh2), 0.0):
         check(_lib.lib().tdrn_deform_head_sample_group(n, descs, vp(projs), width, vp(offsets),

@@ -257,6 +257,35 @@ def test_deform_sample_group_is_bit_identical_to_per_level(multihead, split, sof
     assert loc_a.abs().sum() > 0 and torch.equal(loc_a, loc_b) and torch.equal(conf_a, conf_b)
 
 
+def test_deform_heads_with_half_projections(monkeypatch):
+    """Opt-in TDRN_PROJ_F16=1: the per-tap projections are IEEE half (tdrn_conv2d_tc out_dtype TDRN_F16, tdrn_deform_head_desc.split = 2).
+    Same heads as with bf16 projections to within the projections' rounding; grouped launch == per-level launches bit for bit."""
+    from tdrn_b200 import ops
+    B, C, cin = 2, 21, 256
+    sizes = [(20, 24), (5, 6)]
+    g = torch.Generator().manual_seed(11)
+    P = sum(h * w * 3 for h, w in sizes)
+    lv = [0, sizes[0][0] * sizes[0][1] * 3]
+    feats = [torch.randn(B, h, w, cin, generator=g).to(torch.bfloat16).cuda() for h, w in sizes]
+    offs = [(torch.randn(B, h, w, 18, generator=g) * 1.5).cuda() for h, w in sizes]
+    packs = [ops.pack_deform_proj_weight(torch.randn(12 + 3 * C, cin, 3, 3, generator=g) * 0.03, None) for _ in sizes]
+    res = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('TDRN_PROJ_F16', mode)
+        loc = torch.zeros(B, P, 4, device='cuda'); conf = torch.zeros(B, P, C, device='cuda')
+        for k in range(2):
+            ops.deform_head_projected(feats[k], offs[k], packs[k][0], packs[k][1], C, 3, 1, loc, conf, P, lv[k], softmax=False)
+        ys = [ops.deform_project(feats[k], packs[k][0], packs[k][1], 3, 0, C) for k in range(2)]
+        assert ys[0].dtype == (torch.float16 if mode == '1' else torch.bfloat16)
+        loc_g = torch.zeros(B, P, 4, device='cuda'); conf_g = torch.zeros(B, P, C, device='cuda')
+        ops.deform_sample_group(ys, [tuple(f.shape) for f in feats], packs[0][1], C, 3, 1, offs, loc_g, conf_g, P, lv, softmax=False)
+        torch.cuda.synchronize()
+        assert torch.equal(loc, loc_g) and torch.equal(conf, conf_g)
+        res[mode] = (loc.cpu().numpy(), conf.cpu().numpy())
+    assert rel_err(res['1'][0], res['0'][0]) < 4e-3 and rel_err(res['1'][1], res['0'][1]) < 4e-3
+    assert not np.array_equal(res['1'][1], res['0'][1])
+
+
 @pytest.mark.parametrize('b,h,w,relu', [
     (2, 8, 64, True),          # 64x2 tiles, one tile row per image pair
     (3, 20, 96, True),         # 32x4 tiles
