@@ -11,6 +11,7 @@ LAYERS = [  # name, cin, cout, hw, pool
     ('conv1_2', 64, 64, 320, True), ('conv2_1', 64, 128, 160, False), ('conv2_2', 128, 128, 160, True),
     ('conv3_1', 128, 256, 80, False), ('conv3_2', 256, 256, 80, False), ('conv4_1', 256, 512, 40, False),
     ('conv4_2', 512, 512, 40, False), ('conv5_1', 512, 512, 20, False),
+    ('tcb0_1', 512, 256, 40, False), ('tcb0_2', 256, 256, 40, False), ('tcb1_1', 512, 256, 20, False), ('tcb2_1', 1024, 256, 10, False),
 ]
 only = sys.argv[1:] if len(sys.argv) > 1 else None
 g = torch.Generator().manual_seed(0)

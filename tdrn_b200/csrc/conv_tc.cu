@@ -1180,7 +1180,13 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         static const int mt2_min = getenv("TDRN_MT2_MIN") ? atoi(getenv("TDRN_MT2_MIN")) : 70;   // paired units per 100 SMs from which pairing pays
         const int num_kb = p.taps * (p.Cin >> 6);
         const int units2 = ((p.m_tiles + 1) / 2) * p.n_tiles;
-        p.mt2 = !no_mt2 && !d->split3 && BN == 256 && p.tma_out && !p.b_resident && !use_cluster && num_kb >= 64 && units2 * 100 >= g_num_sms * mt2_min;   // measured: K = 2304 (36 k-blocks) loses 5 %, K = 4608 gains 5-10 %
+        // r03: pairing must not cost a round of tiles: 512 -> 256 @40x40 at b32 is 427 tiles = 3 rounds on 148 SMs unpaired but 214
+        // units = 2 rounds of TWO tiles paired (TDRN_MT2_ROUNDS=0 switches the test off)
+        static const bool rounds_rule = !(getenv("TDRN_MT2_ROUNDS") && getenv("TDRN_MT2_ROUNDS")[0] == '0');
+        const int tiles1 = p.m_tiles * p.n_tiles;
+        const bool rounds_ok = !rounds_rule || 2 * ((units2 + g_num_sms - 1) / g_num_sms) <= (tiles1 + g_num_sms - 1) / g_num_sms;
+        p.mt2 = !no_mt2 && !d->split3 && BN == 256 && p.tma_out && !p.b_resident && !use_cluster && num_kb >= 64 && units2 * 100 >= g_num_sms * mt2_min &&
+                rounds_ok;   // measured: K = 2304 (36 k-blocks) loses 5 %, K = 4608 gains 5-10 %
     }
     cudaStream_t st = as_stream(stream);
     {   // development aid (TDRN_TC_VERBOSE=1): which tiling / variant a layer gets
