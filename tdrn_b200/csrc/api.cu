@@ -4,6 +4,7 @@
 #include <atomic>
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace tdrn {
 
@@ -19,6 +20,12 @@ void set_error(const char *fmt, ...)
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled()
+{
+    static const bool on = [] { const char *e = getenv("TDRN_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
 
 }  // namespace tdrn
 

@@ -34,6 +34,32 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// ---- programmatic dependent launch (TDRN_PDL=1) ---------------------------------------------------------------------
+// A kernel launched through launch_pdl() may be scheduled while its predecessor in the stream still runs; pdl_sync() at the end
+// of its prologue (barrier init, TMEM allocation, descriptor prefetch -- nothing that touches data another kernel produces) lets
+// ITS successor do the same and then waits until the predecessor's results are visible.  What overlaps is the launch latency
+// and the prologue of every kernel: the batch-1 video paths are chains of ~50 kernels that each run for a few microseconds.
+// Only kernels that call pdl_sync() may be launched with launch_pdl(); every other combination behaves like a plain launch.
+__device__ __forceinline__ void pdl_sync()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+bool pdl_enabled();                            // api.cu
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline cudaStream_t as_stream(tdrn_stream_t s) { return (cudaStream_t)s; }
 

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) conv_stem_tc_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_sync();                               // programmatic dependent launch (common.cuh): the image may still be in flight
 
     if (warp < 4) {
         // ===================== producers: fp32 NCHW patch (TMA ring) -> bf16 im2col rows =====================
@@ -246,7 +247,7 @@ template <bool SPLIT, int S, int COUT>
 static int launch_stem(const CUtensorMap &tmX, const CUtensorMap &tmO, const StemP &p, int grid, cudaStream_t st)
 {
     TDRN_CUDA(cudaFuncSetAttribute(conv_stem_tc_kernel<SPLIT, S, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, st_smem(S)));
-    conv_stem_tc_kernel<SPLIT, S, COUT><<<grid, ST_THREADS, st_smem(S), st>>>(tmX, tmO, p);
+    TDRN_CUDA(launch_pdl(conv_stem_tc_kernel<SPLIT, S, COUT>, dim3(grid), dim3(ST_THREADS), st_smem(S), st, tmX, tmO, p));
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;
 }

@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (CL == 2) cluster_sync_all();          // the peer's barriers are initialised before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_sync();                               // programmatic dependent launch: everything above overlaps the previous kernel's tail
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -928,7 +929,7 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmA2, const CUte
             using Cfg2 = TcCfg<256, 2>;
             const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
             TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256, 1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
-            conv_tc_kernel<256, 1, false, 2><<<units < g_num_sms ? units : g_num_sms, TC_THREADS, Cfg2::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+            TDRN_CUDA(launch_pdl(conv_tc_kernel<256, 1, false, 2>, dim3(units < g_num_sms ? units : g_num_sms), dim3(TC_THREADS), Cfg2::SMEM_BYTES, st, tmA, tmA2, tmB, tmO, tmO2, p));
             TDRN_LAUNCH_CHECK();
             return TDRN_OK;
         }
@@ -940,22 +941,22 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmA2, const CUte
         if constexpr (BN <= 128) {
             if (p.split_nacc == 3) {
                 TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, false, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                conv_tc_kernel<BN, 1, false, 1, 3><<<grid, TC_THREADS, smem, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+                TDRN_CUDA(launch_pdl(conv_tc_kernel<BN, 1, false, 1, 3>, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmA2, tmB, tmO, tmO2, p));
                 TDRN_LAUNCH_CHECK();
                 return TDRN_OK;
             }
         }
         TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, false, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        conv_tc_kernel<BN, 1, false, 1, 1><<<grid, TC_THREADS, smem, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+        TDRN_CUDA(launch_pdl(conv_tc_kernel<BN, 1, false, 1, 1>, dim3(grid), dim3(TC_THREADS), smem, st, tmA, tmA2, tmB, tmO, tmO2, p));
         TDRN_LAUNCH_CHECK();
         return TDRN_OK;
     }
     if (p.b_resident) {
         TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        conv_tc_kernel<BN, 1, true, 1><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+        TDRN_CUDA(launch_pdl(conv_tc_kernel<BN, 1, true, 1>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, tmA, tmA2, tmB, tmO, tmO2, p));
     } else {
         TDRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, 1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        conv_tc_kernel<BN, 1, false, 1><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmO, tmO2, p);
+        TDRN_CUDA(launch_pdl(conv_tc_kernel<BN, 1, false, 1>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, tmA, tmA2, tmB, tmO, tmO2, p));
     }
     TDRN_LAUNCH_CHECK();
     return TDRN_OK;

@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(128) dwconv3x3_half_kernel(const uint4 *__rest
     constexpr int XT = 4, NCOL = (XT - 1) * STRIDE + 3;
     const int CG = C >> 3, XS = (Wo + XT - 1) / XT;
     const unsigned e = blockIdx.x * 128u + threadIdx.x;
+    pdl_sync();
     if (e >= (unsigned)(XS * CG)) return;
     const int xs = (int)(e / (unsigned)CG), cg = (int)(e - (unsigned)xs * (unsigned)CG);
     const int y = blockIdx.y, b = blockIdx.z;
@@ -438,6 +439,7 @@ __global__ void __launch_bounds__(128, 3) dwconv3x3_half_roll_kernel(const uint4
     constexpr int XT = 4, NCOL = XT + 2;
     const int CG = C >> 3, XS = (W + XT - 1) / XT;                  // stride 1, pad 1: Ho = H, Wo = W
     const unsigned e = blockIdx.x * 128u + threadIdx.x;
+    pdl_sync();
     if (e >= (unsigned)(XS * CG)) return;
     const int xs = (int)(e / (unsigned)CG), cg = (int)(e - (unsigned)xs * (unsigned)CG);
     const int y_begin = blockIdx.y * YT, y_end = min(H, y_begin + YT), b = blockIdx.z;
@@ -822,10 +824,10 @@ static void launch_dw16(const void *in, const float *weight, const float *bias, 
         const long long roll_blocks = (long long)grid.x * ((Ho + YT - 1) / YT) * B;
         if (STRIDE == 1 && !no_roll && roll_blocks >= 1024) {          // enough CTAs to fill the GPU several times over: row-walking form
             const dim3 g2(grid.x, (unsigned)((Ho + YT - 1) / YT), (unsigned)B);
-            dwconv3x3_half_roll_kernel<YT><<<g2, 128, 0, st>>>((const uint4 *)in, weight, bias, (uint4 *)out, B, H, W, C, relu);
+            launch_pdl(dwconv3x3_half_roll_kernel<YT>, g2, dim3(128), 0, st, (const uint4 *)in, weight, bias, (uint4 *)out, B, H, W, C, relu);
             return;
         }
-        dwconv3x3_half_kernel<STRIDE><<<grid, 128, 0, st>>>((const uint4 *)in, weight, bias, (uint4 *)out, B, H, W, C, Ho, Wo, relu);
+        launch_pdl(dwconv3x3_half_kernel<STRIDE>, grid, dim3(128), 0, st, (const uint4 *)in, weight, bias, (uint4 *)out, B, H, W, C, Ho, Wo, relu);
         return;
     }
     if (f16in) { if (f16out) TDRN_DW(true, true); else TDRN_DW(true, false); }
