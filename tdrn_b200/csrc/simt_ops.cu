@@ -819,10 +819,12 @@ static void launch_dw16(const void *in, const float *weight, const float *bias, 
 #define TDRN_DW(FI, FO) dwconv3x3_bf16_kernel<STRIDE, FI, FO><<<grid, 128, 0, st>>>((const uint4 *)in, weight, bias, (uint4 *)out, B, H, W, C, Ho, Wo, relu)
     static const bool f32acc = getenv("TDRN_DW_F32ACC") != nullptr;    // half in/out with fp32 accumulation (the form the packed-half kernel replaced)
     if (f16in && f16out && !f32acc) {
-        static const bool no_roll = getenv("TDRN_DW_NOROLL") != nullptr;
+        // TDRN_DW_ROLL_MIN (read per call so that tests can switch it): CTAs from which the row-walking form is used; 0 = never
+        const char *rm = getenv("TDRN_DW_ROLL_MIN");
+        const long long roll_min = rm ? atoll(rm) : 1024;
         constexpr int YT = 8;
         const long long roll_blocks = (long long)grid.x * ((Ho + YT - 1) / YT) * B;
-        if (STRIDE == 1 && !no_roll && roll_blocks >= 1024) {          // enough CTAs to fill the GPU several times over: row-walking form
+        if (STRIDE == 1 && roll_min > 0 && roll_blocks >= roll_min) {   // enough CTAs to fill the GPU several times over: row-walking form
             const dim3 g2(grid.x, (unsigned)((Ho + YT - 1) / YT), (unsigned)B);
             launch_pdl(dwconv3x3_half_roll_kernel<YT>, g2, dim3(128), 0, st, (const uint4 *)in, weight, bias, (uint4 *)out, B, H, W, C, relu);
             return;

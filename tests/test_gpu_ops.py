@@ -275,3 +275,25 @@ def test_l2norm_half_in_bf16_out():
         assert rel_err(out.float().cpu().numpy(), ref.numpy()) < 6e-3
         out16 = ops.l2norm(x.cuda(), wt.cuda())
         assert out16.dtype == torch.float16 and rel_err(out16.float().cpu().numpy(), ref.numpy()) < 8e-4
+
+
+@pytest.mark.parametrize('b,c,h,w,relu', [(2, 64, 18, 22, True), (1, 256, 40, 40, True), (3, 32, 7, 5, False), (2, 1024, 20, 20, True), (1, 8, 9, 1, True)])
+def test_dwconv3x3_half_row_walking_form_is_bit_identical(b, c, h, w, relu, monkeypatch):
+    """The row-walking packed-half depthwise kernel (large batches; forced here with TDRN_DW_ROLL_MIN=1) performs the same FMAs in
+    the same order as the one-row form: identical bits, on ragged maps too (H not a multiple of 8, W not a multiple of 4, W = 1)."""
+    from tdrn_b200 import ops
+    g = torch.Generator().manual_seed(b * 1000 + c + h)
+    x = (torch.randn(b, h, w, c, generator=g) * 3).to(torch.float16).cuda()
+    wd = torch.randn(c, 1, 3, 3, generator=g)
+    bn = (torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g), torch.randn(c, generator=g), torch.rand(c, generator=g) + 0.5)
+    pd = ops.PackedDw(wd, bn, 1, 'cuda')
+    monkeypatch.setenv('TDRN_DW_ROLL_MIN', '0')
+    one_row = ops.dwconv3x3(x, pd, relu=relu)
+    monkeypatch.setenv('TDRN_DW_ROLL_MIN', '1')
+    walking = ops.dwconv3x3(x, pd, relu=relu)
+    torch.cuda.synchronize()
+    assert torch.equal(one_row, walking)
+    ref = F.batch_norm(F.conv2d(x.float().permute(0, 3, 1, 2).cpu(), wd, None, 1, 1, 1, c), bn[2], bn[3], bn[0], bn[1], False, 0.0, 1e-5)
+    if relu:
+        ref = F.relu(ref)
+    assert rel_err(walking.float().permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 3e-3
