@@ -88,6 +88,8 @@ struct TcConvP {
     long long out_sb, out_sp; int out_w;
     int relu, deconv, out_f32, pool;
     int f16_in, f16_out;         // TDRN_F16: operands (activations AND packed weights) / the 16-bit output are IEEE half instead of bf16
+    int mt_major;                // tile index = mu * n_tiles + nt (the N tiles of one M tile run at the same time on neighbouring CTAs: the
+                                 // activation boxes of the second one hit L2) instead of nt * m_units + mu
 };
 
 // split mode (fp32-accurate): ring stage = x_hi | x_lo | W_hi | W_lo boxes of one (tap, channel block); fp32 / (hi|lo) register-store epilogue
@@ -171,6 +173,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int tile_begin = RES ? (int)((long long)total_tiles * unit0 / unit_step) : unit0;
     const int tile_end = RES ? (int)((long long)total_tiles * (unit0 + 1) / unit_step) : total_tiles;
     const int tile_step = RES ? 1 : unit_step;
+    const bool mt_major = !RES && p.mt_major;
+    auto tile_nt = [&](int t) { return mt_major ? t % p.n_tiles : t / m_units; };     // N tile of work item t
+    auto tile_mu = [&](int t) { return mt_major ? t / p.n_tiles : t % m_units; };     // its M unit
     // shared-memory layout: ring of (A box | B box) stages, or -- resident weights -- num_kb B boxes followed by a ring of A boxes
     const uint32_t n_stages = RES ? (uint32_t)p.a_stages : (SPLIT ? (uint32_t)TcSplitCfg<BN>::STAGES : (uint32_t)Cfg::STAGES);
     constexpr uint32_t a_stride = RES ? (uint32_t)Cfg::A_BYTES : (SPLIT ? (uint32_t)TcSplitCfg<BN>::STAGE_BYTES : (uint32_t)Cfg::STAGE_BYTES);
@@ -201,20 +206,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             // their last use) and each CTA streams them through a ring that only holds a few k-blocks: prefetch this
             // CTA's first weight slice into L2 now, all boxes at once.
             if (p.l2_prefetch && unit0 < total_tiles) {
-                const int n0p = (unit0 / m_units) * BN + (CL == 2 ? cr * (int)(p.b_bytes >> 8) : 0);
+                const int n0p = tile_nt(unit0) * BN + (CL == 2 ? cr * (int)(p.b_bytes >> 8) : 0);
                 for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_l2_2d(&tmB, kb * 64, n0p);
             }
             uint32_t it = 0, s = 0, ph = 0;                    // running k-block counter across tiles; its ring stage and phase
             int nt_in_smem = -1;                               // b_resident: N tile whose weight boxes sit in the stages
             for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-                const int nt = tile / m_units;
+                const int nt = tile_nt(tile);
                 int w0[MT], h0[MT], b0[MT];
                 const CUtensorMap *mapA[MT];
                 uint32_t a_bytes = 0;
                 bool have[MT];
 #pragma unroll
                 for (int sub = 0; sub < MT; ++sub) {
-                    const int mt = (tile % m_units) * (CL * MT) + (MT == 2 ? sub : cr);
+                    const int mt = tile_mu(tile) * (CL * MT) + (MT == 2 ? sub : cr);
                     have[sub] = MT == 1 || mt < p.m_tiles;          // an odd M tile count leaves the last unit half empty
                     const bool tail = p.rr && mt >= p.nA;           // ragged-tail tile (leftover rows of g2 images)
                     const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
@@ -273,14 +278,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (elect_one()) {
             uint32_t s = 0, ph = 0, tcount = 0;
             for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
-                const int nt = tile / m_units;
+                const int nt = tile_nt(tile);
                 const int n_eff = min(BN, n_pad16 - nt * BN);           // UMMA N (multiple of 16)
                 const uint32_t idesc = umma_idesc_16(128, n_eff, p.f16_in);
                 const uint32_t buf = tcount % NBUF;
                 mbar_wait(&tmem_empty_bar[buf], ((tcount / NBUF) & 1u) ^ 1u);   // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
-                const bool have1 = MT == 2 && (tile % m_units) * 2 + 1 < p.m_tiles;
+                const bool have1 = MT == 2 && tile_mu(tile) * 2 + 1 < p.m_tiles;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t box_bytes = p.pool ? 32u * 128u : 128u * 128u;
             uint32_t tcount = 0, git = 0;
             for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
-                const int mt = tile % m_units, nt = tile / m_units;
+                const int mt = tile_mu(tile), nt = tile_nt(tile);
                 const int n0 = nt * BN;
                 const int n_eff = min(BN, n_pad16 - n0);
                 const uint32_t buf = tcount % NBUF;
@@ -458,43 +463,85 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const bool leader = threadIdx.x == 64;
             uint32_t tcount = 0, git = 0;
             for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
-                const int nt = tile / m_units;
+                const int nt = tile_nt(tile);
                 const int n0 = nt * BN;
                 const int n_eff = min(BN, n_pad16 - n0);
                 const uint32_t buf = tcount % NBUF;
                 mbar_wait(&tmem_full_bar[buf], (tcount / NBUF) & 1u);
                 tc_fence_after();
                 const int groups = (n_eff + 63) >> 6;
-                const int nsub = MT == 2 && (tile % m_units) * 2 + 1 < p.m_tiles ? 2 : 1;
+                const int nsub = MT == 2 && tile_mu(tile) * 2 + 1 < p.m_tiles ? 2 : 1;
                 for (int sub = 0; sub < nsub; ++sub) {
-                    const int mt = (tile % m_units) * (CL * MT) + (MT == 2 ? sub : cr);
+                    const int mt = tile_mu(tile) * (CL * MT) + (MT == 2 ? sub : cr);
                     const bool tail = p.rr && mt >= p.nA;
                     const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
                     const int x0 = tw * p.bw, y0 = tail ? p.qh * p.bh : th * p.bh, b0 = tail ? (mt - p.nA) * p.g2 : tn * p.bn;
                     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (MT == 2 ? sub * BN : buf * BN);
+                    // r03: on layers with a bias the accumulator load and the bias loads of a group are issued BEFORE the barrier that
+                    // waits for the staging box -- on short-K layers (MobileNet's pointwise convs) the epilogue's chain of latencies
+                    // (barrier -> tcgen05.ld -> bias from global -> convert -> store -> barrier), four times per tile, was longer than
+                    // the tile's MMAs (ncu source view r03m: the bias FADDs wait on the long scoreboard; 512 -> 512 @40x40 b64:
+                    // 0.074 -> 0.064 ms).  Measured and NOT kept: issuing group g + 1's loads while group g is converted (pointwise
+                    // convs another 3 % faster, but the bias-free per-tap projection GEMM 0.096 -> 0.132 ms), and the early issue on
+                    // that bias-free GEMM (+4 %): it keeps the original order.
+                    const bool early = p.bias != nullptr;
                     for (int g = 0; g < groups; ++g, ++git) {
                         uint8_t *o = stage_base + (git & 1u) * Cfg::OUT_STAGE_BYTES;
-                        if (leader) bulk_wait_read<1>();                 // the store that last read this box has drained
-                        named_bar(1, 256);
                         const int c0 = g * 64 + half * 32;
-                        if (c0 < n_eff) {                                // warp-uniform; columns >= n_eff are >= Cout: clipped
-                            float v[32];
-                            tmem_ld32(trow + (uint32_t)c0, v);
-                            const int n = n0 + c0;
-                            if (p.bias) {
+                        const bool have = c0 < n_eff;                    // warp-uniform; columns >= n_eff are >= Cout: clipped
+                        const int n = n0 + c0;
+                        if (early) {
+                            uint32_t ra[32];
+                            float bv[32];
+                            if (have) {
+                                tmem_ld32_issue(trow + (uint32_t)c0, ra);
+                                if (n + 32 <= p.n_total) {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) if (n + j < p.n_total) v[j] += __ldg(p.bias + n + j);
+                                    for (int j = 0; j < 32; j += 4) {
+                                        const float4 b4 = __ldg((const float4 *)(p.bias + n + j));      // n is a multiple of 32
+                                        bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) bv[j] = n + j < p.n_total ? __ldg(p.bias + n + j) : 0.f;
+                                }
                             }
-                            if (p.relu) {
+                            if (leader) bulk_wait_read<1>();             // the store that last read this box has drained
+                            named_bar(1, 256);
+                            if (have) {
+                                tmem_ld_wait32(ra);
+                                float v[32];
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + bv[j];
+                                if (p.relu) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                                }
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    uint32_t w[4];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) w[j] = pack16x2(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1], p.f16_out);
+                                    *(uint4 *)(o + sw128_offset(r, half * 4 + q)) = make_uint4(w[0], w[1], w[2], w[3]);
+                                }
                             }
+                        } else {
+                            if (leader) bulk_wait_read<1>();             // the store that last read this box has drained
+                            named_bar(1, 256);
+                            if (have) {
+                                float v[32];
+                                tmem_ld32(trow + (uint32_t)c0, v);
+                                if (p.relu) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint32_t w[4];
+                                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                                }
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) w[j] = pack16x2(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1], p.f16_out);
-                                *(uint4 *)(o + sw128_offset(r, half * 4 + q)) = make_uint4(w[0], w[1], w[2], w[3]);
+                                for (int q = 0; q < 4; ++q) {
+                                    uint32_t w[4];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) w[j] = pack16x2(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1], p.f16_out);
+                                    *(uint4 *)(o + sw128_offset(r, half * 4 + q)) = make_uint4(w[0], w[1], w[2], w[3]);
+                                }
                             }
                         }
                         if (g == groups - 1 && sub == nsub - 1) {        // all tcgen05.ld of this unit are complete
@@ -518,7 +565,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const bool res_bf16 = p.res != nullptr && !p.out_f32;
         uint32_t tcount = 0;
         for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
-            const int mt = (tile % m_units) * CL + cr, nt = tile / m_units;
+            const int mt = tile_mu(tile) * CL + cr, nt = tile_nt(tile);
             const bool tail = p.rr && mt >= p.nA;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
             const int x = tw * p.bw + wl;
@@ -1189,13 +1236,20 @@ extern "C" int tdrn_conv2d_tc(const tdrn_conv_desc *d, const void *in, const voi
         p.mt2 = !no_mt2 && !d->split3 && BN == 256 && p.tma_out && !p.b_resident && !use_cluster && num_kb >= 64 && units2 * 100 >= g_num_sms * mt2_min &&
                 rounds_ok;   // measured: K = 2304 (36 k-blocks) loses 5 %, K = 4608 gains 5-10 %
     }
+    {   // r03: N tiles of the same M tile next to each other in the tile walk.  Measured on the MobileNet pointwise convs at b64
+        // (512 -> 512 @40x40: a 105 MB input, two N tiles): with the N-tile-major walk the second N tile re-read the whole input from
+        // DRAM half a kernel later (ncu: 208.6 MB read for a 105 MB input).  TDRN_MT_MAJOR=0 / 1 forces the walk (read per call).
+        const char *e = getenv("TDRN_MT_MAJOR");
+        p.mt_major = e ? (e[0] == '1') : (p.n_tiles >= 2 && !p.b_resident && p.taps == 1);
+        if (use_cluster || p.splitk > 1) p.mt_major = 0;
+    }
     cudaStream_t st = as_stream(stream);
     {   // development aid (TDRN_TC_VERBOSE=1): which tiling / variant a layer gets
         static const bool verbose = getenv("TDRN_TC_VERBOSE") != nullptr;
         if (verbose)
-            fprintf(stderr, "conv_tc %dx%d k%d @%dx%d b%d: box %dx%dx%d, m_tiles %d (tail rr %d g2 %d), BN %d x %d, kb %d, mt2 %d cluster %d resident %d tma_out %d splitk %d\n",
+            fprintf(stderr, "conv_tc %dx%d k%d @%dx%d b%d: box %dx%dx%d, m_tiles %d (tail rr %d g2 %d), BN %d x %d, kb %d, mt2 %d cluster %d resident %d tma_out %d splitk %d mt_major %d\n",
                     d->Cin, d->Cout, kh, p.H, p.W, p.B, p.bw, p.bh, p.bn, p.m_tiles, p.rr, p.g2, BN, p.n_tiles, p.taps * (p.Cin >> 6), p.mt2,
-                    (int)use_cluster, p.b_resident, p.tma_out, p.splitk);
+                    (int)use_cluster, p.b_resident, p.tma_out, p.splitk, p.mt_major);
     }
     if (p.splitk > 1) {
         TDRN_CUDA(cudaFuncSetAttribute(conv_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
