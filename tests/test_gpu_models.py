@@ -284,6 +284,25 @@ def test_bf16_heads_with_reference_offsets(name):
     assert rel_err(out[3].cpu().numpy(), ref[3].numpy()) < tol
 
 
+def test_mobilenet_bf16_trunk_opt_out(monkeypatch):
+    """TDRN_MOBILE_BF16=1 keeps the bf16 trunk of round 2 (read when the engine is built): same interface, the known ~3.5e-2 on conf with
+    the oracle's offsets given, against 1.6e-2 for the IEEE-half trunk that is the default."""
+    from oracle import model_ref as M
+    from oracle.make_golden import CASES, make_input
+    mod_name, spec_fn, build_kw, spec_kw, _ = CASES['drn_mobilenet320']
+    x = make_input(2, 320, seed=9)
+    errs = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('TDRN_MOBILE_BF16', mode)
+        net, sd = _build(mod_name, spec_fn, build_kw, spec_kw, 'bf16')
+        with torch.no_grad():
+            if mode == '1':
+                ref = M.drn_mobilenet_forward(sd, x, **spec_kw)
+            out = net(x.cuda(), _offsets=([o.cuda() for o in ref[1]], None))
+        errs[mode] = rel_err(out[3].cpu().numpy(), ref[3].numpy())
+    assert errs['0'] < TOL['bf16'] < errs['1'] < 5e-2, errs
+
+
 def test_end_to_end_detections_fp32(golden):
     """net(x) + Detect: the set of kept detections equals the reference's for well-separated scores."""
     from oracle.make_golden import CASES, make_input
