@@ -154,3 +154,13 @@ def test_integration_md_python_stubs_are_valid_python_and_name_real_exports():
             assert hasattr(L, sym), sym
     # pointers are never passed as bare integers (ctypes would truncate them to a C int)
     assert '.ctypes.data,' not in src and '.ctypes.data)' not in src
+
+
+def test_dtype_codes_match_the_header():
+    """The Python mirror's format codes are the header's (TDRN_F16 = IEEE half, the MobileNet trunks' format, was added in round 2)."""
+    import re
+    from tdrn_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'include', 'tdrn_b200.h')).read()
+    codes = {m.group(1): int(m.group(2)) for m in re.finditer(r'#define\s+(TDRN_(?:F32|BF16|BF16_SPLIT|F16))\s+(\d+)', hdr)}
+    assert codes == {'TDRN_F32': _lib.F32, 'TDRN_BF16': _lib.BF16, 'TDRN_BF16_SPLIT': 2, 'TDRN_F16': _lib.F16}
+    assert len(set(codes.values())) == 4
